@@ -1,0 +1,416 @@
+// ref_harness.cpp — TEST INFRASTRUCTURE (oracle), not product code.
+//
+// Drives the UNMODIFIED reference sources (compiled where they lie under
+// /root/reference/source by oracle/build_ref.sh) in two ways:
+//
+//   ref_harness driver <config.txt>
+//       calls the reference's own entry points initialize_wghm / integrate_wghm
+//       (initializeWGHM.h:14, integrateWGHM.h:12) exactly like watergap.cpp:122-163 does.
+//       The run writes the reference's txt state files (16 significant digits).
+//
+//   ref_harness replay <config.txt> <dump.wgd> [--days A-B] [--every K] [--snow-days A-B]
+//                      [--final-state PREFIX] [--time-only]
+//       replays the orchestration of integrate_wghm_ (integrateWGHM.cpp:127-309 init
+//       sequence, :546-922 year/month/day loops) calling the reference's own
+//       dailyWaterBalanceClass::calcNewDay / routingClass::routing /
+//       routingClass::updateLandAreaFrac objects, and dumps IN-MEMORY doubles
+//       (private members reached with `#define private public`, this TU only)
+//       after selected days.  Also times the three phases of the day loop
+//       (the CPU baseline of BASELINE.md).
+//
+// The equality "replay final state == driver final state" is checked by
+// tests (tests/test_ref_harness.py) so that the replay is pinned to the
+// reference's own driver.
+//
+// Dump container ("WGD1"): a sequence of records
+//   char name[32]; int32 day (0 = static/initial, k = after k-th simulated day);
+//   char dtype[8] ("f64","f32","i32","i16","i8"); int64 count; raw little-endian data.
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <array>
+#include <map>
+#include <cmath>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define private public
+#define protected public
+#include "def.h"
+#include "common.h"
+#include "globals.h"
+#include "initializeWGHM.h"
+#include "integrateWGHM.h"
+#include "calib_param.h"
+#undef private
+#undef protected
+
+static FILE *g_dump = nullptr;
+
+static void put(const char *name, int day, const char *dtype, int64_t count, const void *data, size_t elsize) {
+    if (!g_dump) return;
+    char nm[32];
+    memset(nm, 0, sizeof nm);
+    strncpy(nm, name, 31);
+    char dt[8];
+    memset(dt, 0, sizeof dt);
+    strncpy(dt, dtype, 7);
+    int32_t d = day;
+    fwrite(nm, 1, 32, g_dump);
+    fwrite(&d, 4, 1, g_dump);
+    fwrite(dt, 1, 8, g_dump);
+    fwrite(&count, 8, 1, g_dump);
+    fwrite(data, elsize, (size_t)count, g_dump);
+}
+template <class G> static void put_f64(const char *name, int day, G &g, int64_t count = ng) {
+    put(name, day, "f64", count, g.getDataPointer(), 8);
+}
+template <class G> static void put_f32(const char *name, int day, G &g, int64_t count = ng) {
+    put(name, day, "f32", count, g.getDataPointer(), 4);
+}
+template <class G> static void put_i32(const char *name, int day, G &g, int64_t count = ng) {
+    put(name, day, "i32", count, g.getDataPointer(), 4);
+}
+template <class G> static void put_i16(const char *name, int day, G &g, int64_t count = ng) {
+    put(name, day, "i16", count, g.getDataPointer(), 2);
+}
+template <class G> static void put_i8(const char *name, int day, G &g, int64_t count = ng) {
+    put(name, day, "i8", count, g.getDataPointer(), 1);
+}
+
+struct Range { int a = 0, b = -1; bool has(int d) const { return d >= a && d <= b; } };
+static Range parse_range(const char *s) {
+    Range r;
+    if (sscanf(s, "%d-%d", &r.a, &r.b) != 2) { r.a = r.b = atoi(s); }
+    return r;
+}
+
+static void dump_static(calibParamClass &cal) {
+    // geometry / masks
+    std::vector<double> area(ng), p(ng);
+    for (int n = 0; n < ng; n++) area[n] = geo.areaOfCellByArrayPos(n);
+    put("area", 0, "f64", ng, area.data(), 8);
+    put_f64("contfreq", 0, geo.G_contfreq);
+    put_i16("contcell", 0, geo.G_contcell);
+    put_i16("row", 0, geo.G_row);
+    put_i16("toBeCalculated", 0, G_toBeCalculated);
+    put_i8("landcover", 0, land.G_landCover);
+    put_f32("builtup", 0, land.G_built_up);
+    put_i16("arid", 0, G_aindex);
+    put_i8("ldd", 0, G_LDD);
+    put_i16("elevation", 0, dailyWaterBalance.G_Elevation, (int64_t)ng * 101);
+    put_f32("smax", 0, maxSoilWaterCap.G_Smax);
+    put_f32("gwfactor", 0, GW.G_gwFactor);
+    put_i16("rgmax", 0, GW.G_Rgmax);
+    put_i8("texture", 0, GW.G_texture);
+    put_f32("laimax", 0, lai.G_LAImax);
+    put("lai_factor_a", 0, "f32", nlct, lai.lai_factor_a, 4);
+    put("lai_factor_b", 0, "f32", nlct, lai.lai_factor_b, 4);
+    put("lai_initial_days", 0, "i16", nlct, lai.initialDays, 2);
+    put("lai_kc_min", 0, "f64", nlct, lai.kc_min, 8);
+    put("lai_kc_max", 0, "f64", nlct, lai.kc_max, 8);
+    put("lct_albedo", 0, "f64", nlct, dailyWaterBalance.albedo_lct, sizeof(dailyWaterBalance.albedo_lct[0]));
+    put("lct_albedo_snow", 0, "f64", nlct, dailyWaterBalance.albedoSnow_lct, sizeof(dailyWaterBalance.albedoSnow_lct[0]));
+    put("lct_ddf", 0, "f64", nlct, dailyWaterBalance.ddf_lct, sizeof(dailyWaterBalance.ddf_lct[0]));
+    put("lct_emissivity", 0, "f64", nlct, dailyWaterBalance.emissivity_lct, sizeof(dailyWaterBalance.emissivity_lct[0]));
+    put("lct_rooting_depth", 0, "f32", nlct, dailyWaterBalance.rootingDepth_lct, sizeof(dailyWaterBalance.rootingDepth_lct[0]));
+    put_f64("gamma_hbv", 0, dailyWaterBalance.G_gammaHBV);
+    put_f64("cfa", 0, dailyWaterBalance.G_cellCorrFact);
+    put_f64("cfs", 0, routing.G_statCorrFact);
+    // the 26 per-cell calibration parameters, [26][ng]
+    std::vector<double> par((size_t)26 * ng);
+    for (int k = 0; k < 26; k++)
+        for (int n = 0; n < ng; n++) par[(size_t)k * ng + n] = cal.getValue((eCalibParam)k, n);
+    put("params", 0, "f64", (int64_t)26 * ng, par.data(), 8);
+    // routing statics
+    put_f64("loc_lake", 0, routing.G_loc_lake);
+    put_f64("loc_wetland", 0, routing.G_loc_wetland);
+    put_f64("glo_wetland", 0, routing.G_glo_wetland);
+    put_f64("glo_lake", 0, routing.G_glo_lake);
+    put_f64("glo_res", 0, routing.G_glo_res);
+    put_f64("lake_area", 0, routing.G_lake_area);
+    put_f64("reservoir_area", 0, routing.G_reservoir_area);
+    put_f64("stor_cap", 0, routing.G_stor_cap);
+    put_f64("mean_outflow", 0, routing.G_mean_outflow);
+    put_f64("mean_demand", 0, routing.G_mean_demand);
+    put_i8("res_type", 0, routing.G_res_type);
+    put_i8("start_month", 0, routing.G_start_month);
+    put_f64("river_length", 0, routing.G_riverLength);
+    put_f64("river_slope", 0, routing.G_RiverSlope);
+    put_f64("roughness", 0, routing.G_Roughness);
+    put_f64("river_bottom_width", 0, routing.G_riverBottomWidth);
+    put_f64("river_width_bf", 0, routing.G_RiverWidth_bf);
+    put_f64("river_storage_max", 0, routing.G_riverStorageMax);
+    put_f64("lake_depth_active", 0, routing.G_lakeDepthActive);
+    put_f64("wetl_depth_active", 0, routing.G_wetlDepthActive);
+    put_i32("downstream_cell", 0, routing.G_downstreamCell);
+    put_i32("routing_cell", 0, routing.G_routingCell);
+    put_f64("fswb_init", 0, routing.G_fswbInit);
+    put_f64("f_glo_lake", 0, routing.G_fGloLake);
+}
+
+static void dump_state(int day, bool with_snow) {
+    put_f64("canopy", day, dailyWaterBalance.G_canopyWaterContent);
+    put_f64("soil", day, dailyWaterBalance.G_soilWaterContent);
+    put_f64("snow", day, dailyWaterBalance.G_snow);
+    if (with_snow) put_f64("snow_bands", day, dailyWaterBalance.G_SnowInElevation, (int64_t)ng * 101);
+    put_i32("lai_days", day, lai.G_days_since_start);
+    put_i32("lai_status", day, lai.G_GrowingStatus);
+    put_f64("lai_precsum", day, lai.G_PrecSum);
+    put_f64("gw", day, routing.G_groundwaterStorage);
+    put_f64("loc_lake_stor", day, routing.G_locLakeStorage);
+    put_f64("loc_wetl_stor", day, routing.G_locWetlStorage);
+    put_f64("glo_lake_stor", day, routing.G_gloLakeStorage);
+    put_f64("glo_wetl_stor", day, routing.G_gloWetlStorage);
+    put_f64("res_stor", day, routing.G_gloResStorage);
+    put_f64("river_stor", day, routing.G_riverStorage);
+    put_f64("red_loc_lake", day, routing.G_locLakeAreaReductionFactor);
+    put_f64("red_loc_wetl", day, routing.G_locWetlAreaReductionFactor);
+    put_f64("red_glo_lake", day, routing.G_gloLakeEvapoReductionFactor);
+    put_f64("red_glo_wetl", day, routing.G_gloWetlAreaReductionFactor);
+    put_f64("red_res", day, routing.G_gloResEvapoReductionFactor);
+    put_f64("red_river", day, routing.G_riverAreaReductionFactor);
+    put_f64("k_release", day, routing.K_release);
+    put_f64("land_area_frac", day, routing.G_landAreaFrac);
+    put_f64("land_area_frac_prev", day, routing.G_landAreaFracPrevTimestep);
+    put_f64("land_area_frac_next", day, routing.G_landAreaFracNextTimestep);
+    put_f64("fswb_laf", day, routing.G_fswbLandAreaFrac);
+    put_f64("fswb_laf_next", day, routing.G_fswbLandAreaFracNextTimestep);
+    put_f64("river_area_frac_next", day, routing.G_riverAreaFracNextTimestep_Frac);
+    put_i16("status_laf_next", day, routing.statusStarted_landAreaFracNextTimestep);
+}
+
+static void dump_fluxes(int day, int doy) {
+    put_f64("lake_balance", day, dailyWaterBalance.G_lakeBalance);
+    put_f64("openwater_prec", day, dailyWaterBalance.G_openWaterPrec);
+    put_f64("openwater_pet", day, dailyWaterBalance.G_openWaterPET);
+    put_f64("surface_runoff", day, dailyWaterBalance.G_dailyLocalSurfaceRunoff);
+    put_f64("gw_recharge", day, dailyWaterBalance.G_dailyGwRecharge);
+    put_f64("storage_transfer", day, dailyWaterBalance.G_dailyStorageTransfer);
+    put_f64("land_aet", day, dailyWaterBalance.dailyCellLandAET);
+    put_f64("land_aet_uncorr", day, dailyWaterBalance.dailyCellLandAET_uncorr);
+    // river discharge of the day (transportedVolume, km3/d); kept by the reference in
+    // G_daily365RiverAvail when grid_store in {5,6} and output option 92 is on
+    // (routing.cpp:4219-4221); cells with LDD<0 keep 0 there.
+    if (routing.G_daily365RiverAvail.wasInitialized) {
+        std::vector<double> q(ng);
+        for (int n = 0; n < ng; n++) q[n] = routing.G_daily365RiverAvail(n, doy - 1);
+        put("discharge", day, "f64", ng, q.data(), 8);
+    }
+    put_f64("river_evapo", day, routing.G_dailyRiverEvapo);
+    put_f64("gwr_swb", day, routing.G_gwr_swb);
+}
+
+static double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int run_driver(const char *cfg) {
+    std::string progName = "OL", path_mean;
+    WghmStateFile *wghmState, *wghmMean;
+    calibParamClass *calParam;
+    AdditionalOutputInputFile *additionalOutIn;
+    SnowInElevationFile *snow;
+    ConfigFile *configFile;
+    long year = 0, month = 0, total_steps = 0, step = 0;
+    double t0 = now();
+    initialize_wghm(cfg, wghmState, calParam, additionalOutIn, snow, &year, &month, progName.c_str(), path_mean.c_str(), wghmMean);
+    integrate_wghm(cfg, configFile, wghmState, calParam, additionalOutIn, snow, &step, &total_steps, &year, &month, progName.c_str());
+    fprintf(stderr, "REF_DRIVER_SECONDS %.6f\n", now() - t0);
+    return 0;
+}
+
+static int run_replay(int argc, char **argv) {
+    const char *cfg = argv[2];
+    const char *dumpfile = argv[3];
+    Range days, snowdays;
+    int every = 0;
+    bool time_only = false;
+    std::string final_prefix;
+    for (int i = 4; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "--days" && i + 1 < argc) days = parse_range(argv[++i]);
+        else if (a == "--snow-days" && i + 1 < argc) snowdays = parse_range(argv[++i]);
+        else if (a == "--every" && i + 1 < argc) every = atoi(argv[++i]);
+        else if (a == "--final-state" && i + 1 < argc) final_prefix = argv[++i];
+        else if (a == "--time-only") time_only = true;
+    }
+    if (!time_only && strcmp(dumpfile, "-") != 0) {
+        g_dump = fopen(dumpfile, "wb");
+        if (!g_dump) { perror(dumpfile); return 2; }
+    }
+
+    std::string progName = "OL", path_mean;
+    WghmStateFile *wghmState, *wghmMean;
+    calibParamClass *calParam;
+    AdditionalOutputInputFile *additionalOutIn;
+    SnowInElevationFile *snow_in_elevation;
+    long lyear = 0, lmonth = 0;
+    initialize_wghm(cfg, wghmState, calParam, additionalOutIn, snow_in_elevation, &lyear, &lmonth, progName.c_str(), path_mean.c_str(), wghmMean);
+    ConfigFile *configFile = new ConfigFile(cfg, (int)lyear, (int)lmonth, progName);
+
+    const short number_of_days_in_month[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    const short last_day_in_month[12] = {30, 58, 89, 119, 150, 180, 211, 242, 272, 303, 333, 364};
+    short readinstatus = 1;
+#ifdef _OPENMP
+    omp_set_num_threads(8);  // integrateWGHM.cpp:106-111 (the reference aborts with any other team size)
+#endif
+    // ---- init sequence, integrateWGHM.cpp:127-286 -------------------------------------
+    options.init(*configFile);
+    options.createModelSettingsFile(options.output_dir);
+    options.closeModelSettingsFile();
+    if (1 == options.rout_prepare)
+        prepare_routing_files(options.input_dir, options.routing_dir, 1, options.resOpt);
+    geo.init(options.input_dir, options.fileEndianType);
+    climate.init();
+    short nSpecBasins = cbasin.prepare(options.input_dir, options.output_dir, options.routing_dir);
+    dailyWaterBalance.init(options.input_dir, nSpecBasins);
+    G_sbasin.read(options.output_dir + "/G_CALIB_BASIN.UNF2");
+    directUpstSt.findDirectStations(options.routing_dir);
+    allUpstSt.findAllStations(options.routing_dir);
+    geo.calibrun = 0;
+    land.init(options.input_dir);
+    G_aindex.read(options.input_dir + "/G_ARID_HUMID.UNF2");
+    G_LDD.read(options.routing_dir + "/G_LDD_2.UNF1");
+    dailyWaterBalance.G_Elevation.read(options.input_dir + "/G_ELEV_RANGE.101.UNF2");
+    lai.init(options.input_dir, options.output_dir, land.G_landCover, *additionalOutIn, *calParam);
+    routing.init(nSpecBasins, *configFile, *wghmState, *additionalOutIn);
+    routing.initLakeDepthActive(*calParam);
+    routing.initWetlDepthActive(*calParam);
+    // ---- body of the (single-pass) calibration do-while, integrateWGHM.cpp:291-476 ------
+    if (additionalOutIn->additionalfilestatus == 0) routing.initFractionStatus();
+    if (additionalOutIn->additionalfilestatus == 1) routing.initFractionStatusAdditionalOI(*additionalOutIn);
+    if (configFile->additionalfile.empty()) routing.setStoragesToZero();
+    else routing.setStorages(*wghmState, *additionalOutIn);
+    if (configFile->startvaluefile.empty()) routing.setLakeWetlToMaximum(options.start_year);
+    for (int n = 0; n < ng; ++n) G_toBeCalculated[n] = 1;  // options.basin == 1
+    for (int n = 0; n < ng; n++) {
+        dailyWaterBalance.G_gammaHBV[n] = calParam->getValue(P_GAMRUN_C, n);
+        dailyWaterBalance.G_cellCorrFact[n] = calParam->getValue(P_CFA, n);
+        routing.G_statCorrFact[n] = calParam->getValue(P_CFS, n);
+    }
+    if (configFile->additionalfile.empty()) dailyWaterBalance.setStoragesToZero();
+    else dailyWaterBalance.setStorages(*wghmState, *snow_in_elevation, *additionalOutIn);
+    maxSoilWaterCap.createMaxSoilWaterCapacityGrid(options.input_dir, options.output_dir, land.G_landCover, *calParam);
+    GW.createGrids(options.input_dir, options.output_dir, *calParam);
+    climate.read_climate_longtermAvg();
+
+    double t_vert = 0, t_rout = 0, t_laf = 0, t_io = 0;
+    long ndays_done = 0;
+    int simday = 0;
+    bool static_done = false;
+    short start_year = options.start_year, end_year = options.end_year;
+    short day = 0, month = 0, actual_year = 0;
+    for (actual_year = start_year; actual_year <= end_year; actual_year += options.time_step) {
+        dailyWaterBalance.annualInit();
+        routing.annualInit(actual_year, configFile->startMonth, *additionalOutIn);
+        day = 0;
+        if (actual_year == configFile->startYear)
+            for (int m = 1; m < configFile->startMonth; m++) day += number_of_days_in_month[m - 1];
+        if ((5 == options.grid_store) || (6 == options.grid_store)) {
+            dailyWaterBalance.daily365outInit();
+            routing.daily365outInit();
+        }
+        short start_month = configFile->startMonth, end_month = configFile->endMonth;
+        if (start_year == end_year) { /* as configured */ }
+        else if (actual_year == start_year) end_month = 12;
+        else if (actual_year == end_year) start_month = 1;
+        else { start_month = 1; end_month = 12; }
+        if (!static_done) {
+            dump_static(*calParam);
+            dump_state(0, true);
+            static_done = true;
+        }
+        for (month = start_month - 1; month < end_month; month++) {
+            double t0 = now();
+            climate.read_climate_data_daily(month + 1, actual_year);
+            wghmState->resetCells(number_of_days_in_month[month]);
+            t_io += now() - t0;
+            for (short day_in_month = 1; day_in_month <= number_of_days_in_month[month]; day_in_month++) {
+                day++;
+                simday++;
+                double ta = now();
+#pragma omp parallel for
+                for (int n = 0; n < ng; ++n) {
+                    if (geo.G_contcell[n])
+                        dailyWaterBalance.calcNewDay(day, month, day_in_month, last_day_in_month[month], actual_year, n,
+                                                     *wghmState, *additionalOutIn, *snow_in_elevation, readinstatus, *calParam);
+                }
+                double tb = now();
+                routing.routing(actual_year, day, month, day_in_month, last_day_in_month[month], *wghmState,
+                                *additionalOutIn, readinstatus, *calParam);
+                double tc = now();
+                routing.updateLandAreaFrac(*additionalOutIn);
+                double td = now();
+                t_vert += tb - ta; t_rout += tc - tb; t_laf += td - tc;
+                ndays_done++;
+                if (readinstatus == 1) readinstatus = 0;
+                bool want = days.has(simday) || (every > 0 && simday % every == 0);
+                if (g_dump && want) {
+                    dump_state(simday, snowdays.has(simday));
+                    dump_fluxes(simday, day);
+                    if (month >= 0) {
+                        // wghmState of the day (7 routing compartments, mm over continental area; routing.cpp:5002-5020)
+                        std::vector<double> v((size_t)7 * ng);
+                        for (int n = 0; n < ng; n++) {
+                            Cell &c = wghmState->cell(n);
+                            v[0 * (size_t)ng + n] = c.locallake(day_in_month - 1);
+                            v[1 * (size_t)ng + n] = c.localwetland(day_in_month - 1);
+                            v[2 * (size_t)ng + n] = c.globallake(day_in_month - 1);
+                            v[3 * (size_t)ng + n] = c.globalwetland(day_in_month - 1);
+                            v[4 * (size_t)ng + n] = c.reservoir(day_in_month - 1);
+                            v[5 * (size_t)ng + n] = c.river(day_in_month - 1);
+                            v[6 * (size_t)ng + n] = c.groundwater(day_in_month - 1);
+                        }
+                        put("wghm_routing_mm", simday, "f64", (int64_t)7 * ng, v.data(), 8);
+                    }
+                }
+            }
+            // month-end rescale into wghmState / snow_in_elevation, integrateWGHM.cpp:830-847
+            for (int n = 0; n < ng; ++n) {
+                double landAreaFrac = routing.getLandAreaFrac(n);
+                for (short elev = 0; elev <= 100; elev++) {
+                    if (landAreaFrac == 0.) snow_in_elevation->snowInElevation(n, elev) = 0.;
+                    else snow_in_elevation->snowInElevation(n, elev) =
+                             dailyWaterBalance.G_SnowInElevation(n, elev) * landAreaFrac / geo.G_contfreq[n];
+                }
+                for (short dim = 1; dim <= number_of_days_in_month[month]; dim++) {
+                    wghmState->cell(n).canopy(dim - 1) = dailyWaterBalance.G_canopyWaterContent[n] * landAreaFrac / geo.G_contfreq[n];
+                    wghmState->cell(n).snow(dim - 1) = dailyWaterBalance.G_snow[n] * landAreaFrac / geo.G_contfreq[n];
+                    wghmState->cell(n).soil(dim - 1) = dailyWaterBalance.G_soilWaterContent[n] * landAreaFrac / geo.G_contfreq[n];
+                }
+            }
+            if (!final_prefix.empty() && actual_year == end_year && month + 1 == end_month) {
+                wghmState->saveDay(final_prefix + "_state.txt", number_of_days_in_month[month] - 1);
+                additionalOutIn->save(final_prefix + "_additional.txt");
+                snow_in_elevation->save(final_prefix + "_snow.txt");
+            }
+        }
+        if (month == 12) routing.updateGloResPrevYear_pct();
+    }
+    if (g_dump) fclose(g_dump);
+    long ncalc = 0;
+    for (int n = 0; n < ng; n++) if (geo.G_contcell[n] && G_toBeCalculated[n] == 1) ncalc++;
+    double tt = t_vert + t_rout + t_laf;
+    printf("REF_TIMING {\"ng\": %d, \"cells\": %ld, \"days\": %ld, \"threads\": 8, \"t_vertical_s\": %.6f, "
+           "\"t_routing_s\": %.6f, \"t_landfrac_s\": %.6f, \"t_forcing_io_s\": %.6f, \"cell_days_per_s\": %.6e}\n",
+           (int)ng, ncalc, ndays_done, t_vert, t_rout, t_laf, t_io, tt > 0 ? (double)ncalc * ndays_done / tt : 0.0);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc >= 3 && std::string(argv[1]) == "driver") return run_driver(argv[2]);
+    if (argc >= 4 && std::string(argv[1]) == "replay") return run_replay(argc, argv);
+    fprintf(stderr, "usage: ref_harness driver <config> | replay <config> <dump|-> [--days A-B] [--every K] "
+                    "[--snow-days A-B] [--final-state PREFIX] [--time-only]\n");
+    return 1;
+}
