@@ -27,7 +27,7 @@ if [ ! -d "$SRC" ]; then
   exit 0
 fi
 mkdir -p "$OBJ"
-CXX="${CXX:-g++}"
+CXX="${WGK_CXX:-/usr/bin/g++}"  # NB: $CXX in this image points at /opt/gcc, which ships no libgomp
 FLAGS="-std=c++14 -O2 -fopenmp -ffp-contract=off -w -I$HERE/stub -I$SRC"
 if [ "$NG" != "67420" ]; then
   FLAGS="$FLAGS -DWGK_REF_NG=$NG -include $HERE/ref_def_override.h"
@@ -56,5 +56,5 @@ if [ ! -f "$OBJ/json11.o" ]; then
   rm -rf "$TMP"
 fi
 $CXX $FLAGS -c "$HERE/ref_harness.cpp" -o "$OBJ/ref_harness.o"
-$CXX "$OBJ"/*.o -o "$OUT/ref_harness_$NG" -lgomp -lpthread
+$CXX -fopenmp "$OBJ"/*.o -o "$OUT/ref_harness_$NG"
 echo "built $OUT/ref_harness_$NG"
