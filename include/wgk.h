@@ -1,0 +1,144 @@
+/* wgk.h — C ABI of the B200-native WaterGAP2 daily hot path ("wgk" = WaterGAP kernels).
+ *
+ * Drop-in boundary: the reference's hot path is entered through two C++
+ * class interfaces called from the day loop of integrate_wghm_ (integrateWGHM.cpp:755-798):
+ *
+ *   dailyWaterBalanceClass::calcNewDay(day, month, day_in_month, last_day_in_month, year, n, ...)
+ *                                                            daily.h:24,  daily.cpp:94-1264
+ *   routingClass::routing(year, day, month, day_in_month, last_day_in_month, ...)
+ *                                                            routing.h:44, routing.cpp:1629-5244
+ *   routingClass::updateLandAreaFrac(...)                    routing.h:46, routing.cpp:5343-5352
+ *
+ * plus the flow order produced by prepare_routing_files (rout_prepare.h:4, rout_prepare.cpp:61)
+ * and read back in routingClass::init (routing.cpp:526-538).  The entry points below are what a
+ * binding of those interfaces needs: plain pointers and sizes, int status codes, no C++ or
+ * torch types.  The host-side look-alike classes in watergap2_b200/csrc/host/ and the ctypes
+ * binding in watergap2_b200/__init__.py both sit on top of exactly this header; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every host array is in the REFERENCE's cell order (array position n = cell number - 1)
+ *    and in the reference's layout ([cell] or [cell][K]); the library permutes into its own
+ *    device layout (routing order, structure of arrays, band-major snow);
+ *  - the caller owns host buffers, the library owns device memory;
+ *  - all functions return 0 on success or a negative wgk_status; they never throw or exit;
+ *    wgk_last_error() gives the message of the last failure on that context;
+ *  - one context lives on one GPU; contexts are independent (thread-compatible);
+ *  - work is stream-ordered on the context's stream; wgk_synchronize() waits for it;
+ *  - `member` = one ensemble member / calibration run sharing the grid and topology
+ *    (enKF2wghmState.cpp / calibration.cpp run them as separate processes);
+ *    `pset` = one set of per-cell calibration parameters (calib_param.h:72-101); each member
+ *    points at one pset (wgk_set_member_pset), so an EnKF ensemble shares one pset and a
+ *    calibration sweep has one pset per member.
+ */
+#ifndef WGK_H
+#define WGK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WGK_VERSION 100
+#define WGK_NBAND 101   /* G_Elevation / G_SnowInElevation channels: [0] mean, [1..100] bands (daily.h) */
+#define WGK_NLCT 18     /* land cover classes, def.h:20 */
+#define WGK_NPARAM 26   /* eCalibParam, calib_param.h:72-101 */
+
+typedef struct wgk_ctx wgk_ctx;
+
+typedef enum {
+    WGK_OK = 0,
+    WGK_ERR_ARG = -1,        /* bad argument (unknown field, wrong size, index out of range) */
+    WGK_ERR_STATE = -2,      /* call order violated (e.g. step before topology) */
+    WGK_ERR_CUDA = -3,       /* CUDA runtime error, see wgk_last_error */
+    WGK_ERR_NOMEM = -4,
+    WGK_ERR_TOPOLOGY = -5    /* routing order inconsistent with the downstream map */
+} wgk_status;
+
+/* run-time options; defaults = canonical option vector (OPTIONS.DAT order of
+ * option.cpp:173-620).  Only the values listed are implemented; others return WGK_ERR_ARG. */
+typedef struct {
+    int restart;            /* additionalOutIn.additionalfilestatus (daily.cpp:165): 0 cold start, 1 from checkpoint */
+    int tail_threshold;     /* routing levels with <= this many cells are run by one persistent CTA per member (0 = auto) */
+    int use_graph;          /* 1: replay one captured CUDA graph per simulated day (default), 0: plain launches */
+} wgk_options;
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+int wgk_create(wgk_ctx **ctx, int device, int ncell, int nmember, int npset, const wgk_options *opt);
+void wgk_destroy(wgk_ctx *ctx);
+const char *wgk_last_error(const wgk_ctx *ctx);
+int wgk_synchronize(wgk_ctx *ctx);
+/* the cudaStream_t all work of this context is ordered on (as void* to keep the header C-only);
+ * wgk_set_stream adopts a caller stream (e.g. torch.cuda.current_stream().cuda_stream) */
+void *wgk_get_stream(wgk_ctx *ctx);
+int wgk_set_stream(wgk_ctx *ctx, void *cuda_stream);
+
+/* ---- topology: replaces routingClass::init's reading of G_ROUT_ORDER / G_OUTFLC
+ *      (routing.cpp:326, 526-538) ------------------------------------------------------ */
+/* rout_order[n]: 1-based routing rank of cell n (G_ROUT_ORDER.UNF4, rout_prepare.cpp:834-886);
+ * downstream_cell[n]: 1-based number of the cell n drains to, 0 = none (G_OUTFLC.UNF4). */
+int wgk_set_topology(wgk_ctx *ctx, const int32_t *rout_order, const int32_t *downstream_cell);
+int wgk_num_levels(const wgk_ctx *ctx);
+/* level[n] (0-based dependency level of cell n) for ncell cells; for tests and basin sharding */
+int wgk_get_levels(const wgk_ctx *ctx, int32_t *level);
+
+/* ---- fields ---------------------------------------------------------------------------- */
+/* Fields are addressed by the names used throughout the repository (wgk_fields.h; the same
+ * names as the oracle and the reference dump).  `index` is the member for state/flux
+ * fields, the pset for parameter-derived fields and ignored (0) for shared statics.
+ * `bytes` must equal the field's host size (checked).  Host layouts:
+ *   per-cell fields  [ncell];  "elevation" i16 [ncell][101];  "snow_bands" f64 [ncell][101];
+ *   "params" f64 [26][ncell] (eCalibParam order);  table fields [18]. */
+int wgk_field_id(const char *name);                     /* < 0 if unknown */
+int wgk_field_info(int field, const char **name, const char **dtype, int64_t *host_count_per_index, int ncell);
+int wgk_set_field(wgk_ctx *ctx, int field, int index, const void *host, size_t bytes);
+int wgk_get_field(wgk_ctx *ctx, int field, int index, void *host, size_t bytes);
+int wgk_set_member_pset(wgk_ctx *ctx, int member, int pset);
+/* raw device pointer of a per-member field (device layout: routing order, padded row of
+ * wgk_cell_stride() elements per member) for zero-copy collectives (NCCL via torch) */
+void *wgk_device_ptr(wgk_ctx *ctx, int field, int member);
+int64_t wgk_cell_stride(const wgk_ctx *ctx);
+/* rank_of_cell[n] = position of reference cell n in the device (routing) order */
+int wgk_get_device_order(const wgk_ctx *ctx, int32_t *rank_of_cell);
+
+/* ---- forcing: replaces climateClass::read_climate_data_daily's in-memory grids
+ *      G_precipitation_d / G_temperature_d / G_shortwave_d / G_longwave_d
+ *      (climate.cpp:93-138, climate.h:14-21; float [ncell][31]) --------------------------- */
+/* The context holds `nslots` forcing days on the device ([slot][cell] of float4 P,T,SW,LW).
+ * wgk_set_forcing copies `ndays` days starting at channel 0 of the four host grids (reference
+ * layout [ncell][stride], stride = 31 for the .31 monthly files) into slots slot0.. ;
+ * member < 0 = shared by all members, else per-member forcing (EnKF perturbed forcing).
+ * The transposition / permutation runs on the device. */
+int wgk_forcing_reserve(wgk_ctx *ctx, int nslots, int per_member);
+int wgk_set_forcing(wgk_ctx *ctx, int slot0, int ndays, int member, const float *prec, const float *temp,
+                    const float *shortwave, const float *longwave, int stride);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* One call = what the day loop of integrateWGHM.cpp:755-798 does for all cells and members:
+ * calcNewDay for every continental cell, routing(), updateLandAreaFrac().
+ * day 1..365 (day of the 365-day model year), month 0..11, day_in_month 1..31, slot =
+ * forcing slot of that day.  The three-call form exists for the class shims; wgk_step_days
+ * runs `ndays` consecutive days (calendar advanced on the device, forcing slots
+ * slot0, slot0+1, ... modulo the reserved slots) as one graph replay per day. */
+int wgk_vertical_day(wgk_ctx *ctx, int day, int month, int day_in_month, int slot);
+int wgk_routing_day(wgk_ctx *ctx, int day, int month, int day_in_month);
+int wgk_update_land_area_frac(wgk_ctx *ctx);
+int wgk_step_days(wgk_ctx *ctx, int day, int month, int day_in_month, int slot0, int ndays);
+
+/* ---- diagnostics ----------------------------------------------------------------------- */
+/* total water storage of one member in km3 (canopy+snow+soil on the land fraction, plus the
+ * seven routing compartments): the daily global mass-balance check of BASELINE.md */
+int wgk_total_storage_km3(wgk_ctx *ctx, int member, double *out);
+/* per-day record of river discharge at `ncells` chosen cells for the last wgk_step_days call
+ * (station series, routing.cpp:4232-4238); host out[ndays][ncells] */
+int wgk_record_cells(wgk_ctx *ctx, const int32_t *cells, int ncells, int max_days);
+int wgk_get_record(wgk_ctx *ctx, int member, double *out, int ndays);
+/* number of kernels this context has launched (graph nodes counted per replay) */
+int64_t wgk_kernel_launches(const wgk_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WGK_H */

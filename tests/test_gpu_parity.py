@@ -1,0 +1,178 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (include/wgk.h via ctypes), against
+(a) golden vectors dumped from the compiled reference and (b) the CPU oracle on seeded worlds."""
+import numpy as np
+import pytest
+
+from tests.util import assert_parity, golden_day
+
+pytestmark = pytest.mark.gpu
+
+COMPARE_FLOAT_MAX_FLIPS = 0
+
+
+def _model_from(fields, topo_ro, topo_down, ng, **kw):
+    import watergap2_b200 as wg
+    m = wg.Model(ng, **kw)
+    m.set_topology(topo_ro, topo_down)
+    m.load(fields)
+    return m
+
+
+def test_gpu_vs_reference_golden(golden):
+    """59 days on the 1000-cell world, compared with what the compiled reference held in memory."""
+    ng = int(golden["ng"])
+    d0 = golden_day(golden, 0)
+    ro = np.zeros(ng, np.int32)
+    ro[d0["routing_cell"] - 1] = np.arange(1, ng + 1)  # routing.cpp:530-538 inverted
+    m = _model_from(d0, ro, d0["downstream_cell"], ng)
+    m.forcing_reserve(31)
+    days = [int(d) for d in golden["days"]]
+    curm, nchk = -1, 0
+    for sd in range(1, max(days) + 1):
+        doy, mon, dom = ((sd - 1) % 365 + 1, 0 if sd <= 31 else 1, sd if sd <= 31 else sd - 31)
+        if mon != curm:
+            f = {k: golden[f"forcing{mon + 1}/{k}"] for k in ("P", "T", "SW", "LW")}
+            m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+            curm = mon
+        m.step_days(doy, mon, dom, dom - 1, 1)
+        if sd in days:
+            for name, ref in golden_day(golden, sd).items():
+                if m.has_field(name) and name != "status_laf_next":
+                    assert_parity(f"day{sd}/{name}", ref, m.get(name)) if False else assert_parity(name, ref, m.get(name))
+                    nchk += 1
+    assert nchk > 200
+
+
+def _run_pair(world, ndays, nmember=1, use_graph=1, psets=None, block=1):
+    """oracle(s) and a Model on the same world; returns (oracles, model)"""
+    from oracle import synth_world as sw, wg_init, wgo
+    ng = world.ng
+    psets = psets or [None]
+    inits = [wg_init.derive(world, p) for p in psets]
+    topo = inits[0]["_topology"]
+    import watergap2_b200 as wg
+    m = wg.Model(ng, nmember=nmember, npset=len(psets), use_graph=use_graph)
+    m.set_topology(topo["rout_order"], topo["outflow_cell"])
+    for i, ini in enumerate(inits):
+        m.load(ini, pset=i)
+    oracles = []
+    for mem in range(nmember):
+        o = wgo.Oracle(ng)
+        ini = inits[mem % len(psets)]
+        for k, v in ini.items():
+            if not k.startswith("_") and o.has(k):
+                o.set(k, v)
+        m.set_member_pset(mem, mem % len(psets))
+        oracles.append(o)
+    m.forcing_reserve(62)
+    for mon in (1, 2):
+        f = sw.forcing_month(world, 1901, mon)
+        m.set_forcing(31 * (mon - 1), 31, f["P"], f["T"], f["SW"], f["LW"])
+    sd = 1
+    while sd <= ndays:
+        n = min(block, ndays - sd + 1)
+        doy, mon, dom = wgo.calendar(sd)
+        n = min(n, wgo.NDAYS[mon] - dom + 1)  # slots are per month here
+        m.step_days(doy, mon, dom, 31 * mon + dom - 1, n)
+        for k in range(n):
+            doy, mon, dom = wgo.calendar(sd + k)
+            for o in oracles:
+                if dom == 1 or sd + k == 1:
+                    o.set_forcing_month(sw.forcing_month(world, 1901, mon + 1))
+                o.step_day(doy, mon, dom)
+        sd += n
+    return oracles, m
+
+
+def _compare(oracles, m, names):
+    flips = 0
+    for mem, o in enumerate(oracles):
+        for name in names:
+            flips += assert_parity(name, o.field(name), m.get(name, mem))
+    return flips
+
+
+def test_gpu_vs_oracle_3000_cells(world3000):
+    from oracle import wg_init
+    oracles, m = _run_pair(world3000, 45, block=7)
+    _compare(oracles, m, wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS)
+    # daily global mass balance: total storage equal to the oracle's (BASELINE.md parity gates)
+    a, b = oracles[0].total_storage_km3(), m.total_storage_km3()
+    assert abs(a - b) <= 1e-12 * abs(a)
+
+
+def test_members_and_parameter_sets(world3000):
+    """two members with different per-cell parameter sets advance independently and each
+    matches its own oracle run (calibration sweep layout, BASELINE config 3)."""
+    from oracle import synth_world as sw, wg_init
+    p0 = sw.default_params(world3000, 0)
+    p1 = sw.default_params(world3000, 5)
+    oracles, m = _run_pair(world3000, 20, nmember=2, psets=[p0, p1], block=5)
+    _compare(oracles, m, wg_init.STATE_FIELDS + ["discharge", "surface_runoff", "gw_recharge"])
+    assert not np.array_equal(m.get("discharge", 0), m.get("discharge", 1))
+
+
+def test_graph_replay_equals_plain_launches(world3000):
+    """size-independent property: one captured graph per day == plain launches == one call
+    per day, bit for bit (same kernels, same order)."""
+    from oracle import wg_init
+    _, a = _run_pair(world3000, 12, use_graph=1, block=12)
+    _, b = _run_pair(world3000, 12, use_graph=0, block=1)
+    for name in wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS:
+        assert np.array_equal(a.get(name), b.get(name)), name
+
+
+def test_identical_members_stay_identical_full_size():
+    """BASELINE-size property test (67 420 cells, 4 members): members with equal inputs give
+    bit-equal results, routing conserves the level order, and storages stay finite."""
+    from oracle import synth_world as sw, wg_init
+    import watergap2_b200 as wg
+    w = sw.build_world(67420)
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    m = wg.Model(w.ng, nmember=4)
+    m.set_topology(topo["rout_order"], topo["outflow_cell"])
+    m.load(ini)
+    f = sw.forcing_month(w, 1901, 1)
+    m.forcing_reserve(31)
+    m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+    s0 = m.total_storage_km3(0)
+    m.step_days(1, 0, 1, 0, 31)
+    for name in ("discharge", "river_stor", "snow_bands", "soil", "gw", "land_area_frac"):
+        ref = m.get(name, 0)
+        assert np.isfinite(ref).all(), name
+        for mem in (1, 2, 3):
+            assert np.array_equal(ref, m.get(name, mem)), name
+    lv = m.levels()
+    down = topo["outflow_cell"]
+    has = down > 0
+    assert (lv[has] < lv[down[has] - 1]).all()
+    assert m.nlevels == topo["nlevels"]
+    s1 = m.total_storage_km3(0)
+    assert np.isfinite(s1) and s1 > 0 and abs(s1 - s0) < 0.5 * s0
+
+
+def test_error_behaviour(world3000):
+    """invalid inputs are rejected with the reference's diagnostics instead of exit(1)"""
+    import watergap2_b200 as wg
+    from oracle import wg_init
+    ini = wg_init.derive(world3000)
+    topo = ini["_topology"]
+    m = wg.Model(world3000.ng)
+    with pytest.raises(wg.WgkError):  # fields before topology
+        m.set("area", ini["area"])
+    bad = topo["rout_order"].copy()
+    bad[[0, 1]] = bad[[1, 0]] if topo["outflow_cell"][0] == 0 else bad[[0, 1]]
+    ro = topo["rout_order"].copy()
+    ro[0] = ro[1]  # not a permutation
+    with pytest.raises(wg.WgkError):
+        m.set_topology(ro, topo["outflow_cell"])
+    m.set_topology(topo["rout_order"], topo["outflow_cell"])
+    arid = ini["arid"].copy()
+    arid[7] = 2  # daily.cpp:345-348 "Invalid value for Arid/humid index"
+    with pytest.raises(wg.WgkError, match="Arid/humid"):
+        m.set("arid", arid)
+    with pytest.raises(wg.WgkError):  # wrong size
+        m.set("area", ini["area"][:-1])
+    with pytest.raises(wg.WgkError):  # stepping without forcing
+        m.step_days(1, 0, 1, 0, 1)

@@ -1,0 +1,269 @@
+"""watergap2_b200 — B200-native WaterGAP2 daily hot path.
+
+Python here is plumbing only: a ctypes binding of the C ABI in ``include/wgk.h`` (the same
+entry points the C++ look-alike classes in ``csrc/host`` call), used by the tests, the
+benchmark and the multi-GPU launcher.  The compute path is ``libwgk.so`` (hand-written
+sm_100a kernels, ``csrc/wgk_kernels.cuh``); if the library is missing or no GPU is present
+every compute entry point raises — there is no CPU or PyTorch fallback.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+__all__ = ["Model", "WgkError", "lib", "LIB_PATH", "FIELD_DTYPES", "build"]
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwgk.so")
+NBAND, NLCT, NPARAM = 101, 18, 26
+FIELD_DTYPES = {"f64": np.float64, "f32": np.float32, "i32": np.int32, "i16": np.int16, "i8": np.int8}
+
+
+class WgkError(RuntimeError):
+    pass
+
+
+class _Options(ctypes.Structure):
+    _fields_ = [("restart", ctypes.c_int), ("tail_threshold", ctypes.c_int), ("use_graph", ctypes.c_int)]
+
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile csrc/wgk_api.cu into watergap2_b200/libwgk.so for sm_100a (in-tree)."""
+    import subprocess
+
+    src = os.path.join(HERE, "csrc", "wgk_api.cu")
+    deps = [src, os.path.join(HERE, "csrc", "wgk_kernels.cuh"), os.path.join(HERE, "csrc", "wgk_fields.h"),
+            os.path.join(HERE, "..", "include", "wgk.h")]
+    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+           "-shared", "-Xcompiler", "-fPIC", "--cudart", "static", "-o", LIB_PATH, src]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+def lib():
+    """Load libwgk.so (raises if it was not built: the CUDA library IS the product)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WgkError(f"{LIB_PATH} not found - run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cp = ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p
+    L.wgk_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ctypes.POINTER(_Options)]
+    L.wgk_destroy.argtypes = [vp]
+    L.wgk_destroy.restype = None
+    L.wgk_last_error.argtypes = [vp]
+    L.wgk_last_error.restype = cp
+    L.wgk_synchronize.argtypes = [vp]
+    L.wgk_get_stream.argtypes = [vp]
+    L.wgk_get_stream.restype = vp
+    L.wgk_set_stream.argtypes = [vp, vp]
+    L.wgk_set_topology.argtypes = [vp, vp, vp]
+    L.wgk_num_levels.argtypes = [vp]
+    L.wgk_get_levels.argtypes = [vp, vp]
+    L.wgk_field_id.argtypes = [cp]
+    L.wgk_field_info.argtypes = [ci, ctypes.POINTER(cp), ctypes.POINTER(cp), ctypes.POINTER(ctypes.c_int64), ci]
+    L.wgk_set_field.argtypes = [vp, ci, ci, vp, ctypes.c_size_t]
+    L.wgk_get_field.argtypes = [vp, ci, ci, vp, ctypes.c_size_t]
+    L.wgk_set_member_pset.argtypes = [vp, ci, ci]
+    L.wgk_device_ptr.argtypes = [vp, ci, ci]
+    L.wgk_device_ptr.restype = vp
+    L.wgk_cell_stride.argtypes = [vp]
+    L.wgk_cell_stride.restype = ctypes.c_int64
+    L.wgk_get_device_order.argtypes = [vp, vp]
+    L.wgk_forcing_reserve.argtypes = [vp, ci, ci]
+    L.wgk_set_forcing.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, ci]
+    L.wgk_vertical_day.argtypes = [vp, ci, ci, ci, ci]
+    L.wgk_routing_day.argtypes = [vp, ci, ci, ci]
+    L.wgk_update_land_area_frac.argtypes = [vp]
+    L.wgk_step_days.argtypes = [vp, ci, ci, ci, ci, ci]
+    L.wgk_total_storage_km3.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double)]
+    L.wgk_record_cells.argtypes = [vp, vp, ci, ci]
+    L.wgk_get_record.argtypes = [vp, ci, vp, ci]
+    L.wgk_kernel_launches.argtypes = [vp]
+    L.wgk_kernel_launches.restype = ctypes.c_int64
+    _lib = L
+    return L
+
+
+class Model:
+    """One wgk context: `nmember` members of a `ncell` grid on one GPU."""
+
+    def __init__(self, ncell, nmember=1, npset=1, device=0, restart=0, tail_threshold=0, use_graph=1):
+        self.ncell, self.nmember, self.npset, self.device = ncell, nmember, npset, device
+        self._L = lib()
+        self._c = ctypes.c_void_p()
+        opt = _Options(restart, tail_threshold, use_graph)
+        rc = self._L.wgk_create(ctypes.byref(self._c), device, ncell, nmember, npset, ctypes.byref(opt))
+        if rc != 0:
+            msg = self._L.wgk_last_error(self._c).decode() if self._c else "no CUDA device (wgk has no CPU fallback)"
+            if self._c:
+                self._L.wgk_destroy(self._c)
+            self._c = None
+            raise WgkError(f"wgk_create failed ({rc}): {msg}")
+        self._ids = {}
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise WgkError(f"wgk error {rc}: {self._L.wgk_last_error(self._c).decode()}")
+
+    def close(self):
+        if getattr(self, "_c", None):
+            self._L.wgk_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def field_id(self, name):
+        if name not in self._ids:
+            f = self._L.wgk_field_id(name.encode())
+            if f < 0:
+                raise KeyError(name)
+            self._ids[name] = f
+        return self._ids[name]
+
+    def has_field(self, name):
+        try:
+            self.field_id(name)
+            return True
+        except KeyError:
+            return False
+
+    def field_info(self, name):
+        f = self.field_id(name)
+        nm, dt, cnt = ctypes.c_char_p(), ctypes.c_char_p(), ctypes.c_int64()
+        scope = self._L.wgk_field_info(f, ctypes.byref(nm), ctypes.byref(dt), ctypes.byref(cnt), self.ncell)
+        return FIELD_DTYPES[dt.value.decode()], cnt.value, scope
+
+    # -- topology / fields --------------------------------------------------------------------
+    def set_topology(self, rout_order, downstream_cell):
+        ro = np.ascontiguousarray(rout_order, np.int32)
+        dc = np.ascontiguousarray(downstream_cell, np.int32)
+        assert ro.size == self.ncell and dc.size == self.ncell
+        self._ck(self._L.wgk_set_topology(self._c, ro.ctypes.data, dc.ctypes.data))
+
+    @property
+    def nlevels(self):
+        return self._L.wgk_num_levels(self._c)
+
+    def levels(self):
+        out = np.zeros(self.ncell, np.int32)
+        self._ck(self._L.wgk_get_levels(self._c, out.ctypes.data))
+        return out
+
+    def device_order(self):
+        out = np.zeros(self.ncell, np.int32)
+        self._ck(self._L.wgk_get_device_order(self._c, out.ctypes.data))
+        return out
+
+    def set(self, name, arr, index=0):
+        dt, cnt, _ = self.field_info(name)
+        a = np.ascontiguousarray(np.asarray(arr).astype(dt, copy=False)).ravel()
+        if a.size != cnt:
+            raise WgkError(f"field {name}: expected {cnt} elements, got {a.size}")
+        self._ck(self._L.wgk_set_field(self._c, self.field_id(name), index, a.ctypes.data, a.nbytes))
+
+    def get(self, name, index=0):
+        dt, cnt, _ = self.field_info(name)
+        out = np.empty(cnt, dt)
+        self._ck(self._L.wgk_get_field(self._c, self.field_id(name), index, out.ctypes.data, out.nbytes))
+        return out
+
+    def set_member_pset(self, member, pset):
+        self._ck(self._L.wgk_set_member_pset(self._c, member, pset))
+
+    def load(self, fields, member=None, pset=None, only=None):
+        """Set every entry of dict `fields` that names a wgk field (others are ignored).
+        Static fields go to index 0, pset fields to `pset` (default all), member fields to
+        `member` (default all)."""
+        n = 0
+        for name, arr in fields.items():
+            if name.startswith("_") or (only is not None and name not in only) or not self.has_field(name):
+                continue
+            _, _, scope = self.field_info(name)
+            if scope == 1:
+                idx = range(self.npset) if pset is None else [pset]
+            elif scope == 2:
+                idx = range(self.nmember) if member is None else [member]
+            else:
+                idx = [0]
+            for i in idx:
+                self.set(name, arr, i)
+            n += 1
+        return n
+
+    # -- forcing --------------------------------------------------------------------------------
+    def forcing_reserve(self, nslots, per_member=False):
+        self._ck(self._L.wgk_forcing_reserve(self._c, nslots, int(per_member)))
+
+    def set_forcing(self, slot0, ndays, prec, temp, sw, lw, member=-1):
+        arrs = [np.ascontiguousarray(x, np.float32) for x in (prec, temp, sw, lw)]
+        stride = arrs[0].size // self.ncell
+        for x in arrs:
+            assert x.size == self.ncell * stride
+        self._ck(self._L.wgk_set_forcing(self._c, slot0, ndays, member, *[x.ctypes.data for x in arrs], stride))
+        self._keep = arrs  # the copies are asynchronous: keep the host buffers alive
+
+    # -- hot path ---------------------------------------------------------------------------------
+    def vertical_day(self, day, month, dom, slot):
+        self._ck(self._L.wgk_vertical_day(self._c, day, month, dom, slot))
+
+    def routing_day(self, day, month, dom):
+        self._ck(self._L.wgk_routing_day(self._c, day, month, dom))
+
+    def update_land_area_frac(self):
+        self._ck(self._L.wgk_update_land_area_frac(self._c))
+
+    def step_days(self, day, month, dom, slot0, ndays):
+        self._ck(self._L.wgk_step_days(self._c, day, month, dom, slot0, ndays))
+
+    def synchronize(self):
+        self._ck(self._L.wgk_synchronize(self._c))
+
+    @property
+    def stream(self):
+        return self._L.wgk_get_stream(self._c)
+
+    def set_stream(self, cuda_stream):
+        self._ck(self._L.wgk_set_stream(self._c, ctypes.c_void_p(cuda_stream)))
+
+    # -- diagnostics ------------------------------------------------------------------------------
+    def total_storage_km3(self, member=0):
+        out = ctypes.c_double()
+        self._ck(self._L.wgk_total_storage_km3(self._c, member, ctypes.byref(out)))
+        return out.value
+
+    def record_cells(self, cells, max_days):
+        c = np.ascontiguousarray(cells, np.int32)
+        self._ck(self._L.wgk_record_cells(self._c, c.ctypes.data, c.size, max_days))
+        self._nrec = c.size
+
+    def get_record(self, ndays, member=0):
+        out = np.empty((ndays, self._nrec), np.float64)
+        self._ck(self._L.wgk_get_record(self._c, member, out.ctypes.data, ndays))
+        return out
+
+    @property
+    def kernel_launches(self):
+        return self._L.wgk_kernel_launches(self._c)
+
+    def device_ptr(self, name, member=0):
+        return self._L.wgk_device_ptr(self._c, self.field_id(name), member)
+
+    @property
+    def cell_stride(self):
+        return self._L.wgk_cell_stride(self._c)

@@ -1,0 +1,694 @@
+// wgk_api.cu — C ABI (include/wgk.h) over the sm_100a kernels of wgk_kernels.cuh.
+//
+// Owns device memory, the routing-order permutation, the level index and the per-day CUDA
+// graph.  There is no CPU fallback anywhere in this file: every entry point either runs the
+// CUDA path or returns an error code.
+#include "../../include/wgk.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+namespace wgk { constexpr int NBAND = 101; }
+#define WGK_NBAND_K wgk::NBAND
+#include "wgk_kernels.cuh"
+
+namespace {
+
+struct FieldInfo {
+    const char *name;
+    const char *dtype;
+    int scope;
+    int bands;
+    int elsize;
+    size_t offset;  // of the pointer inside WgkArrays
+};
+
+const FieldInfo kFields[] = {
+#define X(name, ctype, dt, scope, bands) {#name, dt, WGK_SCOPE_##scope, bands, (int)sizeof(ctype), offsetof(WgkArrays, name)},
+    WGK_FIELDS(X)
+#undef X
+};
+
+// eCalibParam -> device parameter array (calib_param.h:72-101)
+struct ParamMap { int k; int field; };
+const ParamMap kParamMap[] = {
+    {0, WGK_F_gamma_hbv}, {1, WGK_F_cfa}, {2, WGK_F_cfs}, {4, WGK_F_p_rivrgh}, {7, WGK_F_p_swoutf},
+    {8, WGK_F_p_evaredex}, {9, WGK_F_p_netrad}, {10, WGK_F_p_ptc_hum}, {11, WGK_F_p_ptc_ari},
+    {12, WGK_F_p_pet_mxdy}, {13, WGK_F_p_mcwh}, {15, WGK_F_p_snowfz}, {16, WGK_F_p_snowmt},
+    {17, WGK_F_p_degday}, {18, WGK_F_p_gradnt}, {21, WGK_F_p_pcrit}, {22, WGK_F_p_gwoutf}, {25, WGK_F_p_prec},
+};
+
+}  // namespace
+
+struct wgk_ctx {
+    int device = 0;
+    int ncell = 0, stride = 0, nmember = 0, npset = 0;
+    wgk_options opt{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    WgkArrays arrays{};
+    std::vector<void *> allocs;
+
+    // topology
+    bool have_topology = false;
+    int nlevels = 0;
+    int tail_level0 = 0;
+    std::vector<int32_t> rank_of_cell, cell_of_rank, level_off, level_of_rank;
+    int32_t *d_cell_of_rank = nullptr, *d_up_off = nullptr, *d_up_idx = nullptr, *d_down = nullptr, *d_level_off = nullptr;
+    int32_t *d_member_pset = nullptr;
+    std::vector<int32_t> member_pset;
+    int32_t *d_cal = nullptr;
+
+    // forcing
+    float4 *d_forcing = nullptr;
+    int forcing_nslots = 0, forcing_per_member = 0;
+    float *d_fstage = nullptr;  // 4 staging grids [ncell][stride]
+    size_t fstage_elems = 0;
+
+    // record
+    double *d_record = nullptr;
+    int32_t *d_record_cells = nullptr;
+    int nrec = 0, record_max_days = 0;
+
+    // staging
+    void *h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    double *d_partial = nullptr;
+
+    // graph of one simulated day
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_dirty = true;
+    int launches_per_day = 0;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(wgk_ctx *c, int code, const char *fmt, ...) {
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(c, WGK_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+void **field_slot(wgk_ctx *c, int f) { return (void **)((char *)&c->arrays + kFields[f].offset); }
+
+size_t field_rows(const wgk_ctx *c, int f) {
+    switch (kFields[f].scope) {
+        case WGK_SCOPE_CELL: return 1;
+        case WGK_SCOPE_PSET: return (size_t)c->npset;
+        case WGK_SCOPE_MEMBER: return (size_t)c->nmember;
+        default: return 1;
+    }
+}
+size_t field_row_elems(const wgk_ctx *c, int f) {
+    if (kFields[f].scope == WGK_SCOPE_TABLE) return WGK_NLCT;
+    return (size_t)c->stride * kFields[f].bands;
+}
+
+int ensure_stage(wgk_ctx *c, size_t bytes) {
+    if (c->h_stage_bytes >= bytes) return 0;
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr;
+    c->h_stage_bytes = 0;
+    CU(cudaMallocHost(&c->h_stage, bytes));
+    c->h_stage_bytes = bytes;
+    return 0;
+}
+
+WgkParams make_params(const wgk_ctx *c) {
+    WgkParams p{};
+    p.a = c->arrays;
+    p.member_pset = c->d_member_pset;
+    p.forcing = c->d_forcing;
+    p.up_off = c->d_up_off;
+    p.up_idx = c->d_up_idx;
+    p.down = c->d_down;
+    p.level_off = c->d_level_off;
+    p.cal = c->d_cal;
+    p.record = c->d_record;
+    p.record_cells = c->d_record_cells;
+    p.nrec = c->nrec;
+    p.record_max_days = c->record_max_days;
+    p.ncell = c->ncell;
+    p.stride = c->stride;
+    p.nmember = c->nmember;
+    p.npset = c->npset;
+    p.forcing_nslots = c->forcing_nslots;
+    p.forcing_per_member = c->forcing_per_member;
+    p.restart = c->opt.restart;
+    p.nlevels = c->nlevels;
+    return p;
+}
+
+// enqueue the kernels of one simulated day on c->stream (also used under stream capture)
+int enqueue_vertical(wgk_ctx *c, const WgkParams &p) {
+    dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
+    wgk::k_vertical<<<grid, block, 0, c->stream>>>(p);
+    return 1;
+}
+int enqueue_routing(wgk_ctx *c, const WgkParams &p) {
+    int n = 0;
+    dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
+    wgk::k_route_local<<<grid, block, 0, c->stream>>>(p);
+    n++;
+    for (int l = 0; l < c->tail_level0; l++) {
+        const int cnt = c->level_off[l + 1] - c->level_off[l];
+        dim3 g((cnt + 127) / 128, c->nmember);
+        wgk::k_route_level<<<g, block, 0, c->stream>>>(p, l);
+        n++;
+    }
+    if (c->tail_level0 < c->nlevels) {
+        wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, c->tail_level0);
+        n++;
+    }
+    return n;
+}
+
+void drop_graph(wgk_ctx *c) {
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    c->graph_exec = nullptr;
+    c->graph = nullptr;
+    c->graph_dirty = true;
+}
+
+int check_ready(wgk_ctx *c) {
+    if (!c) return WGK_ERR_ARG;
+    if (!c->have_topology) return fail(c, WGK_ERR_STATE, "wgk_set_topology must be called first");
+    if (!c->d_forcing) return fail(c, WGK_ERR_STATE, "no forcing on the device (wgk_forcing_reserve / wgk_set_forcing)");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, const wgk_options *opt) {
+    if (!out || ncell <= 0 || nmember <= 0 || npset <= 0) return WGK_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        *out = nullptr;
+        return WGK_ERR_CUDA;  // no GPU: the product path fails loudly, there is no CPU fallback
+    }
+    wgk_ctx *c = new wgk_ctx();
+    *out = c;
+    c->device = device;
+    c->ncell = ncell;
+    c->stride = (ncell + 31) / 32 * 32;
+    c->nmember = nmember;
+    c->npset = npset;
+    if (opt) c->opt = *opt;
+    else { c->opt.restart = 0; c->opt.tail_threshold = 0; c->opt.use_graph = 1; }
+    if (c->opt.tail_threshold <= 0) c->opt.tail_threshold = 256;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    for (int f = 0; f < WGK_F_COUNT; f++) {
+        const size_t bytes = field_rows(c, f) * field_row_elems(c, f) * kFields[f].elsize;
+        void *d = nullptr;
+        cudaError_t e = cudaMalloc(&d, bytes);
+        if (e != cudaSuccess) return fail(c, WGK_ERR_NOMEM, "cudaMalloc(%zu) for field %s: %s", bytes, kFields[f].name, cudaGetErrorString(e));
+        CU(cudaMemsetAsync(d, 0, bytes, c->stream));
+        *field_slot(c, f) = d;
+        c->allocs.push_back(d);
+    }
+    c->member_pset.assign(nmember, 0);
+    for (int m = 0; m < nmember; m++) c->member_pset[m] = (npset == nmember) ? m : 0;
+    CU(cudaMalloc(&c->d_member_pset, sizeof(int32_t) * nmember));
+    CU(cudaMemcpyAsync(c->d_member_pset, c->member_pset.data(), sizeof(int32_t) * nmember, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMalloc(&c->d_cal, sizeof(int32_t) * 8));
+    CU(cudaMemsetAsync(c->d_cal, 0, sizeof(int32_t) * 8, c->stream));
+    CU(cudaMalloc(&c->d_partial, sizeof(double) * 256));
+    CU(cudaStreamSynchronize(c->stream));
+    return WGK_OK;
+}
+
+void wgk_destroy(wgk_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drop_graph(c);
+    for (void *d : c->allocs) cudaFree(d);
+    cudaFree(c->d_cell_of_rank); cudaFree(c->d_up_off); cudaFree(c->d_up_idx); cudaFree(c->d_down);
+    cudaFree(c->d_level_off); cudaFree(c->d_member_pset); cudaFree(c->d_cal); cudaFree(c->d_forcing);
+    cudaFree(c->d_fstage); cudaFree(c->d_record); cudaFree(c->d_record_cells); cudaFree(c->d_partial);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *wgk_last_error(const wgk_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int wgk_synchronize(wgk_ctx *c) {
+    if (!c) return WGK_ERR_ARG;
+    CU(cudaStreamSynchronize(c->stream));
+    return WGK_OK;
+}
+
+void *wgk_get_stream(wgk_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int wgk_set_stream(wgk_ctx *c, void *s) {
+    if (!c) return WGK_ERR_ARG;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s;
+    c->own_stream = false;
+    drop_graph(c);
+    return WGK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// topology
+// ---------------------------------------------------------------------------------------
+int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downstream_cell) {
+    if (!c || !rout_order || !downstream_cell) return WGK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    const int ng = c->ncell;
+    c->rank_of_cell.assign(ng, -1);
+    c->cell_of_rank.assign(ng, -1);
+    for (int n = 0; n < ng; n++) {
+        const int r = rout_order[n] - 1;
+        if (r < 0 || r >= ng || c->cell_of_rank[r] != -1) return fail(c, WGK_ERR_TOPOLOGY, "rout_order is not a permutation of 1..ncell (cell %d)", n + 1);
+        c->cell_of_rank[r] = n;
+        c->rank_of_cell[n] = r;
+    }
+    std::vector<int32_t> down(ng, -1), nup(ng, 0);
+    for (int n = 0; n < ng; n++) {
+        const int d = downstream_cell[n];
+        if (d < 0 || d > ng) return fail(c, WGK_ERR_TOPOLOGY, "downstream cell of cell %d out of range", n + 1);
+        if (d > 0) {
+            const int rd = c->rank_of_cell[d - 1], rn = c->rank_of_cell[n];
+            if (rd <= rn) return fail(c, WGK_ERR_TOPOLOGY, "cell %d is routed before its upstream cell %d", d, n + 1);
+            down[rn] = rd;
+            nup[rd]++;
+        }
+    }
+    // upstream CSR in device order; entries ascending in rank = the order in which the
+    // reference adds them to G_riverInflow (routing.cpp:3955-3958)
+    std::vector<int32_t> up_off(ng + 1, 0);
+    for (int r = 0; r < ng; r++) up_off[r + 1] = up_off[r] + nup[r];
+    std::vector<int32_t> up_idx(std::max(1, up_off[ng])), fill(ng, 0);
+    for (int r = 0; r < ng; r++)
+        if (down[r] >= 0) up_idx[up_off[down[r]] + fill[down[r]]++] = r;
+    // dependency level = longest path from a headwater; the rank order of rout_prepare.cpp's
+    // Kahn sweeps is level-major, which is verified here
+    c->level_of_rank.assign(ng, 0);
+    for (int r = 0; r < ng; r++)
+        if (down[r] >= 0) c->level_of_rank[down[r]] = std::max(c->level_of_rank[down[r]], c->level_of_rank[r] + 1);
+    for (int r = 1; r < ng; r++)
+        if (c->level_of_rank[r] < c->level_of_rank[r - 1])
+            return fail(c, WGK_ERR_TOPOLOGY, "routing order is not level-major at rank %d (not produced by rout_order sweeps)", r);
+    c->nlevels = c->level_of_rank[ng - 1] + 1;
+    c->level_off.assign(c->nlevels + 1, 0);
+    for (int r = 0; r < ng; r++) c->level_off[c->level_of_rank[r] + 1]++;
+    for (int l = 0; l < c->nlevels; l++) c->level_off[l + 1] += c->level_off[l];
+    // narrow tail: first level from which every level has <= tail_threshold cells
+    c->tail_level0 = c->nlevels;
+    for (int l = c->nlevels - 1; l >= 0; l--) {
+        if (c->level_off[l + 1] - c->level_off[l] <= c->opt.tail_threshold) c->tail_level0 = l;
+        else break;
+    }
+    auto upload = [&](int32_t *&dptr, const std::vector<int32_t> &v) -> cudaError_t {
+        if (dptr) cudaFree(dptr);
+        dptr = nullptr;
+        cudaError_t e = cudaMalloc(&dptr, sizeof(int32_t) * std::max<size_t>(1, v.size()));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(dptr, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice);
+    };
+    CU(upload(c->d_cell_of_rank, c->cell_of_rank));
+    CU(upload(c->d_up_off, up_off));
+    CU(upload(c->d_up_idx, up_idx));
+    CU(upload(c->d_down, down));
+    CU(upload(c->d_level_off, c->level_off));
+    c->have_topology = true;
+    drop_graph(c);
+    return WGK_OK;
+}
+
+int wgk_num_levels(const wgk_ctx *c) { return c && c->have_topology ? c->nlevels : WGK_ERR_STATE; }
+
+int wgk_get_levels(const wgk_ctx *c, int32_t *level) {
+    if (!c || !level) return WGK_ERR_ARG;
+    if (!c->have_topology) return WGK_ERR_STATE;
+    for (int n = 0; n < c->ncell; n++) level[n] = c->level_of_rank[c->rank_of_cell[n]];
+    return WGK_OK;
+}
+
+int wgk_get_device_order(const wgk_ctx *c, int32_t *rank_of_cell) {
+    if (!c || !rank_of_cell) return WGK_ERR_ARG;
+    if (!c->have_topology) return WGK_ERR_STATE;
+    memcpy(rank_of_cell, c->rank_of_cell.data(), sizeof(int32_t) * c->ncell);
+    return WGK_OK;
+}
+
+int64_t wgk_cell_stride(const wgk_ctx *c) { return c ? c->stride : 0; }
+
+// ---------------------------------------------------------------------------------------
+// fields
+// ---------------------------------------------------------------------------------------
+int wgk_field_id(const char *name) {
+    if (!name) return WGK_ERR_ARG;
+    if (strcmp(name, "params") == 0) return WGK_F_params;
+    for (int f = 0; f < WGK_F_COUNT; f++)
+        if (strcmp(name, kFields[f].name) == 0) return f;
+    return WGK_ERR_ARG;
+}
+
+int wgk_field_info(int field, const char **name, const char **dtype, int64_t *count, int ncell) {
+    if (field == WGK_F_params) {
+        if (name) *name = "params";
+        if (dtype) *dtype = "f64";
+        if (count) *count = (int64_t)WGK_NPARAM * ncell;
+        return WGK_SCOPE_PSET;
+    }
+    if (field < 0 || field >= WGK_F_COUNT) return WGK_ERR_ARG;
+    if (name) *name = kFields[field].name;
+    if (dtype) *dtype = kFields[field].dtype;
+    if (count) *count = kFields[field].scope == WGK_SCOPE_TABLE ? WGK_NLCT : (int64_t)ncell * kFields[field].bands;
+    return kFields[field].scope;
+}
+
+static int set_field_raw(wgk_ctx *c, int f, int index, const void *host, size_t bytes) {
+    const FieldInfo &fi = kFields[f];
+    if (index < 0 || (size_t)index >= field_rows(c, f)) return fail(c, WGK_ERR_ARG, "index %d out of range for field %s", index, fi.name);
+    const size_t row_elems = field_row_elems(c, f);
+    char *dst = (char *)*field_slot(c, f) + (size_t)index * row_elems * fi.elsize;
+    if (fi.scope == WGK_SCOPE_TABLE) {
+        if (bytes != (size_t)WGK_NLCT * fi.elsize) return fail(c, WGK_ERR_ARG, "field %s expects %zu bytes, got %zu", fi.name, (size_t)WGK_NLCT * fi.elsize, bytes);
+        CU(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return WGK_OK;
+    }
+    const size_t want = (size_t)c->ncell * fi.bands * fi.elsize;
+    if (bytes != want) return fail(c, WGK_ERR_ARG, "field %s expects %zu bytes, got %zu", fi.name, want, bytes);
+    if (!c->have_topology) return fail(c, WGK_ERR_STATE, "wgk_set_topology must precede wgk_set_field (device order = routing order)");
+    if (f == WGK_F_arid) {  // daily.cpp:345-348: any value other than 0/1 aborts the reference
+        const int16_t *v = (const int16_t *)host;
+        for (int n = 0; n < c->ncell; n++)
+            if (v[n] != 0 && v[n] != 1) return fail(c, WGK_ERR_ARG, "Invalid value for Arid/humid index: %d (cell %d)", (int)v[n], n + 1);
+    }
+    const size_t row_bytes = row_elems * fi.elsize;
+    int rc = ensure_stage(c, row_bytes);
+    if (rc) return rc;
+    memset(c->h_stage, 0, row_bytes);
+    const int es = fi.elsize, nb = fi.bands, ng = c->ncell, st = c->stride;
+    const char *src = (const char *)host;
+    char *tmp = (char *)c->h_stage;
+    for (int r = 0; r < ng; r++) {
+        const size_t n = (size_t)c->cell_of_rank[r];
+        for (int b = 0; b < nb; b++) memcpy(tmp + ((size_t)b * st + r) * es, src + (n * nb + b) * es, es);
+    }
+    CU(cudaMemcpyAsync(dst, tmp, row_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return WGK_OK;
+}
+
+int wgk_set_field(wgk_ctx *c, int field, int index, const void *host, size_t bytes) {
+    if (!c || !host) return WGK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    if (field == WGK_F_params) {
+        const size_t want = (size_t)WGK_NPARAM * c->ncell * sizeof(double);
+        if (bytes != want) return fail(c, WGK_ERR_ARG, "params expects %zu bytes, got %zu", want, bytes);
+        const double *p = (const double *)host;
+        for (const ParamMap &pm : kParamMap) {
+            int rc = set_field_raw(c, pm.field, index, p + (size_t)pm.k * c->ncell, (size_t)c->ncell * sizeof(double));
+            if (rc) return rc;
+        }
+        // active lake / wetland depth in km (routing.cpp:5613-5628, conversion.h)
+        std::vector<double> d(c->ncell);
+        for (int n = 0; n < c->ncell; n++) d[n] = p[(size_t)5 * c->ncell + n] * 0.001;
+        int rc = set_field_raw(c, WGK_F_lake_depth_active, index, d.data(), d.size() * sizeof(double));
+        if (rc) return rc;
+        for (int n = 0; n < c->ncell; n++) d[n] = p[(size_t)6 * c->ncell + n] * 0.001;
+        return set_field_raw(c, WGK_F_wetl_depth_active, index, d.data(), d.size() * sizeof(double));
+    }
+    if (field < 0 || field >= WGK_F_COUNT) return fail(c, WGK_ERR_ARG, "unknown field %d", field);
+    return set_field_raw(c, field, index, host, bytes);
+}
+
+int wgk_get_field(wgk_ctx *c, int f, int index, void *host, size_t bytes) {
+    if (!c || !host) return WGK_ERR_ARG;
+    if (f < 0 || f >= WGK_F_COUNT) return fail(c, WGK_ERR_ARG, "unknown field %d", f);
+    CU(cudaSetDevice(c->device));
+    const FieldInfo &fi = kFields[f];
+    if (index < 0 || (size_t)index >= field_rows(c, f)) return fail(c, WGK_ERR_ARG, "index %d out of range for field %s", index, fi.name);
+    const size_t row_elems = field_row_elems(c, f);
+    const char *src = (const char *)*field_slot(c, f) + (size_t)index * row_elems * fi.elsize;
+    if (fi.scope == WGK_SCOPE_TABLE) {
+        if (bytes != (size_t)WGK_NLCT * fi.elsize) return fail(c, WGK_ERR_ARG, "field %s: wrong size", fi.name);
+        CU(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return WGK_OK;
+    }
+    const size_t want = (size_t)c->ncell * fi.bands * fi.elsize;
+    if (bytes != want) return fail(c, WGK_ERR_ARG, "field %s expects %zu bytes, got %zu", fi.name, want, bytes);
+    if (!c->have_topology) return fail(c, WGK_ERR_STATE, "no topology");
+    const size_t row_bytes = row_elems * fi.elsize;
+    int rc = ensure_stage(c, row_bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_stage, src, row_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const int es = fi.elsize, nb = fi.bands, ng = c->ncell, st = c->stride;
+    const char *tmp = (const char *)c->h_stage;
+    char *dst = (char *)host;
+    for (int r = 0; r < ng; r++) {
+        const size_t n = (size_t)c->cell_of_rank[r];
+        for (int b = 0; b < nb; b++) memcpy(dst + (n * nb + b) * es, tmp + ((size_t)b * st + r) * es, es);
+    }
+    return WGK_OK;
+}
+
+int wgk_set_member_pset(wgk_ctx *c, int member, int pset) {
+    if (!c || member < 0 || member >= c->nmember || pset < 0 || pset >= c->npset) return WGK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    c->member_pset[member] = pset;
+    CU(cudaMemcpyAsync(c->d_member_pset + member, &c->member_pset[member], sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return WGK_OK;
+}
+
+void *wgk_device_ptr(wgk_ctx *c, int f, int member) {
+    if (!c || f < 0 || f >= WGK_F_COUNT) return nullptr;
+    if (member < 0 || (size_t)member >= field_rows(c, f)) return nullptr;
+    return (char *)*field_slot(c, f) + (size_t)member * field_row_elems(c, f) * kFields[f].elsize;
+}
+
+// ---------------------------------------------------------------------------------------
+// forcing
+// ---------------------------------------------------------------------------------------
+int wgk_forcing_reserve(wgk_ctx *c, int nslots, int per_member) {
+    if (!c || nslots <= 0) return WGK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_forcing) cudaFree(c->d_forcing);
+    c->d_forcing = nullptr;
+    const size_t n = (size_t)nslots * (per_member ? c->nmember : 1) * c->stride;
+    cudaError_t e = cudaMalloc(&c->d_forcing, n * sizeof(float4));
+    if (e != cudaSuccess) return fail(c, WGK_ERR_NOMEM, "cudaMalloc forcing (%zu bytes): %s", n * sizeof(float4), cudaGetErrorString(e));
+    CU(cudaMemsetAsync(c->d_forcing, 0, n * sizeof(float4), c->stream));
+    c->forcing_nslots = nslots;
+    c->forcing_per_member = per_member ? 1 : 0;
+    drop_graph(c);
+    return WGK_OK;
+}
+
+int wgk_set_forcing(wgk_ctx *c, int slot0, int ndays, int member, const float *prec, const float *temp,
+                    const float *sw, const float *lw, int stride) {
+    if (!c || !prec || !temp || !sw || !lw || ndays <= 0 || stride < ndays) return WGK_ERR_ARG;
+    if (!c->have_topology) return fail(c, WGK_ERR_STATE, "wgk_set_topology must precede wgk_set_forcing");
+    if (!c->d_forcing) {
+        int rc = wgk_forcing_reserve(c, std::max(31, slot0 + ndays), member >= 0);
+        if (rc) return rc;
+    }
+    if (slot0 < 0 || slot0 + ndays > c->forcing_nslots) return fail(c, WGK_ERR_ARG, "forcing slots %d..%d exceed the %d reserved", slot0, slot0 + ndays - 1, c->forcing_nslots);
+    if ((member >= 0) != (c->forcing_per_member != 0))
+        return fail(c, WGK_ERR_ARG, "forcing was reserved %s", c->forcing_per_member ? "per member" : "shared");
+    if (member >= c->nmember) return WGK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    const size_t elems = (size_t)c->ncell * stride;
+    if (c->fstage_elems < elems) {
+        if (c->d_fstage) cudaFree(c->d_fstage);
+        c->d_fstage = nullptr;
+        CU(cudaMalloc(&c->d_fstage, 4 * elems * sizeof(float)));
+        c->fstage_elems = elems;
+    }
+    float *dP = c->d_fstage, *dT = dP + elems, *dS = dT + elems, *dL = dS + elems;
+    CU(cudaMemcpyAsync(dP, prec, elems * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dT, temp, elems * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dS, sw, elems * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dL, lw, elems * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    const int F = c->forcing_per_member ? c->nmember : 1;
+    const size_t pitch = (size_t)F * c->stride;
+    float4 *dst = c->d_forcing + (size_t)slot0 * pitch + (size_t)(c->forcing_per_member ? member : 0) * c->stride;
+    dim3 block(128), grid((c->ncell + 127) / 128, std::min(ndays, 31));
+    wgk::k_forcing_pack<<<grid, block, 0, c->stream>>>(dst, dP, dT, dS, dL, c->d_cell_of_rank, c->ncell, c->stride, ndays, stride, pitch);
+    c->launches++;
+    CU(cudaGetLastError());
+    return WGK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// hot path
+// ---------------------------------------------------------------------------------------
+static int set_calendar(wgk_ctx *c, int day, int month, int dom, int slot) {
+    if (day < 1 || day > 365 || month < 0 || month > 11 || dom < 1 || dom > 31) return fail(c, WGK_ERR_ARG, "bad date day=%d month=%d day_in_month=%d", day, month, dom);
+    if (slot < 0 || slot >= c->forcing_nslots) return fail(c, WGK_ERR_ARG, "forcing slot %d not reserved", slot);
+    wgk::k_set_calendar<<<1, 1, 0, c->stream>>>(c->d_cal, day, month, dom, slot);
+    return WGK_OK;
+}
+
+int wgk_vertical_day(wgk_ctx *c, int day, int month, int dom, int slot) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    rc = set_calendar(c, day, month, dom, slot);
+    if (rc) return rc;
+    c->launches += 1 + enqueue_vertical(c, make_params(c));
+    CU(cudaGetLastError());
+    return WGK_OK;
+}
+
+int wgk_routing_day(wgk_ctx *c, int day, int month, int dom) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if (day < 1 || day > 365 || month < 0 || month > 11 || dom < 1 || dom > 31) return fail(c, WGK_ERR_ARG, "bad date");
+    // keep the slot that the vertical step of the same day used
+    int32_t slot = 0;
+    CU(cudaMemcpyAsync(&slot, c->d_cal + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    wgk::k_set_calendar<<<1, 1, 0, c->stream>>>(c->d_cal, day, month, dom, slot);
+    c->launches += 1 + enqueue_routing(c, make_params(c));
+    CU(cudaGetLastError());
+    return WGK_OK;
+}
+
+int wgk_update_land_area_frac(wgk_ctx *c) {
+    // routingClass::updateLandAreaFrac is fused into the routing sweep (k_route_level /
+    // k_route_tail write prev <- cur <- next per cell); the entry point exists so that the
+    // three-call sequence of integrateWGHM.cpp:779-798 maps one to one.
+    int rc = check_ready(c);
+    return rc;
+}
+
+int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (ndays <= 0) return WGK_OK;
+    CU(cudaSetDevice(c->device));
+    rc = set_calendar(c, day, month, dom, slot0);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->d_cal + 4, 0, sizeof(int32_t), c->stream));
+    c->launches++;
+    const WgkParams p = make_params(c);
+    if (c->opt.use_graph) {
+        if (c->graph_dirty) {
+            drop_graph(c);
+            CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int n = enqueue_vertical(c, p);
+            n += enqueue_routing(c, p);
+            wgk::k_end_of_day<<<1, 256, 0, c->stream>>>(p);
+            n++;
+            cudaError_t e = cudaStreamEndCapture(c->stream, &c->graph);
+            if (e != cudaSuccess) return fail(c, WGK_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+            CU(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
+            c->launches_per_day = n;
+            c->graph_dirty = false;
+        }
+        for (int d = 0; d < ndays; d++) CU(cudaGraphLaunch(c->graph_exec, c->stream));
+        c->launches += (int64_t)c->launches_per_day * ndays;
+    } else {
+        for (int d = 0; d < ndays; d++) {
+            int n = enqueue_vertical(c, p);
+            n += enqueue_routing(c, p);
+            wgk::k_end_of_day<<<1, 256, 0, c->stream>>>(p);
+            c->launches += n + 1;
+        }
+    }
+    CU(cudaGetLastError());
+    return WGK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------------------
+int wgk_total_storage_km3(wgk_ctx *c, int member, double *out) {
+    if (!c || !out || member < 0 || member >= c->nmember) return WGK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    const int nblk = 128;
+    wgk::k_total_storage<<<nblk, 256, 0, c->stream>>>(make_params(c), member, c->d_partial);
+    c->launches++;
+    double part[128];
+    CU(cudaMemcpyAsync(part, c->d_partial, sizeof(double) * nblk, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    double s = 0.;
+    for (int i = 0; i < nblk; i++) s += part[i];
+    *out = s;
+    return WGK_OK;
+}
+
+int wgk_record_cells(wgk_ctx *c, const int32_t *cells, int ncells, int max_days) {
+    if (!c || ncells < 0 || max_days < 0) return WGK_ERR_ARG;
+    if (!c->have_topology) return fail(c, WGK_ERR_STATE, "no topology");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_record) cudaFree(c->d_record);
+    if (c->d_record_cells) cudaFree(c->d_record_cells);
+    c->d_record = nullptr;
+    c->d_record_cells = nullptr;
+    c->nrec = 0;
+    c->record_max_days = 0;
+    if (ncells > 0 && max_days > 0) {
+        std::vector<int32_t> ranks(ncells);
+        for (int k = 0; k < ncells; k++) {
+            if (cells[k] < 0 || cells[k] >= c->ncell) return fail(c, WGK_ERR_ARG, "record cell %d out of range", cells[k]);
+            ranks[k] = c->rank_of_cell[cells[k]];
+        }
+        CU(cudaMalloc(&c->d_record_cells, sizeof(int32_t) * ncells));
+        CU(cudaMemcpy(c->d_record_cells, ranks.data(), sizeof(int32_t) * ncells, cudaMemcpyHostToDevice));
+        const size_t n = (size_t)max_days * c->nmember * ncells;
+        CU(cudaMalloc(&c->d_record, n * sizeof(double)));
+        CU(cudaMemset(c->d_record, 0, n * sizeof(double)));
+        c->nrec = ncells;
+        c->record_max_days = max_days;
+    }
+    drop_graph(c);
+    return WGK_OK;
+}
+
+int wgk_get_record(wgk_ctx *c, int member, double *out, int ndays) {
+    if (!c || !out || member < 0 || member >= c->nmember || ndays < 0 || ndays > c->record_max_days) return WGK_ERR_ARG;
+    if (!c->d_record) return fail(c, WGK_ERR_STATE, "wgk_record_cells was not called");
+    CU(cudaSetDevice(c->device));
+    const size_t pitch = (size_t)c->nmember * c->nrec;
+    CU(cudaMemcpy2DAsync(out, (size_t)c->nrec * sizeof(double), c->d_record + (size_t)member * c->nrec, pitch * sizeof(double),
+                         (size_t)c->nrec * sizeof(double), ndays, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return WGK_OK;
+}
+
+int64_t wgk_kernel_launches(const wgk_ctx *c) { return c ? c->launches : 0; }
+
+}  // extern "C"

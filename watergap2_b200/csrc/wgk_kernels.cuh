@@ -1,0 +1,992 @@
+// wgk_kernels.cuh — sm_100a kernels of the WaterGAP2 daily hot path.
+//
+// FP64 structure-of-arrays, one thread per (member, cell); device cell order = routing order,
+// so every dependency level of the river network is one contiguous, coalesced index range.
+//
+//   k_vertical      : dailyWaterBalanceClass::calcNewDay for all cells   (daily.cpp:94-1264, lai.cpp:152-306)
+//   k_route_local   : cell-parallel part of routingClass::routing that does not depend on
+//                     upstream cells: runoff split, groundwater of humid cells and inland
+//                     sinks, local lake, local wetland                   (routing.cpp:1878-2617)
+//   k_route_level   : one dependency level of the ordered cell loop: upstream-inflow gather,
+//                     global lake, reservoir, global wetland, arid groundwater, river,
+//                     fused with the per-cell surface-water-fraction / land-area-fraction
+//                     pass and updateLandAreaFrac                         (routing.cpp:2623-3586,
+//                                                                          5034-5188, 5343-5352)
+//   k_route_tail    : the same for all remaining narrow levels inside ONE persistent CTA per
+//                     member, levels separated by __syncthreads() instead of kernel launches
+//   k_forcing_pack  : [cell][31] float grids -> [slot][cell] float4 in routing order
+//   k_advance_day   : calendar on the device (so that one captured graph replays day after day)
+//
+// Build with -fmad=false: the reference CPU build has no FMA contraction, and results are
+// compared at 1e-10 relative.  Expression shapes follow the reference line by line.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "wgk_fields.h"
+
+struct WgkParams {
+    WgkArrays a;
+    const int32_t *member_pset;   // [nmember]
+    const float4 *forcing;        // [slot][fmember][stride]  (P, T, SW, LW)
+    const int32_t *up_off;        // [ncell+1] CSR of upstream cells, device order
+    const int32_t *up_idx;        // upstream ranks, ascending (= reference accumulation order)
+    const int32_t *down;          // [ncell] downstream rank or -1
+    const int32_t *level_off;     // [nlevels+1]
+    int32_t *cal;                 // device calendar {day, month, day_in_month, slot, simday}
+    double *record;               // [max_days][nmember][nrec] discharge record, or null
+    const int32_t *record_cells;  // [nrec] device ranks
+    int nrec, record_max_days;
+    int ncell, stride, nmember, npset;
+    int forcing_nslots, forcing_per_member;
+    int restart;
+    int nlevels;
+};
+
+namespace wgk {
+
+constexpr double MIN_STOR_VOL = 1.e-15;  // routing.h:24
+
+// ----------------------------------------------------------------------------------------
+// LAI growing-season state machine (lai.cpp:179-293)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ double lai_growing(int &days, int initialDays, int &status, int lct, bool arid,
+                                              double LAImin, double LAImax, double &precsum, double prec) {
+    if (status == 0) {
+        if (days >= initialDays) {
+            days++;
+            precsum += prec;
+            if (precsum > 40.) {
+                if (days >= initialDays + 30) {
+                    days = initialDays + 30;
+                    status = 1;
+                }
+                return (LAImin + (LAImax - LAImin) * (days - initialDays) / 30.);
+            } else {
+                days = initialDays;
+                return LAImin;
+            }
+        } else {
+            days++;
+            precsum += prec;
+            return LAImin;
+        }
+    } else {
+        if (days <= 30) {
+            days--;
+            if (lct <= 2) status = 0;
+            if (days <= 0) {
+                days = 0;
+                status = 0;
+                precsum = 0.;
+            }
+            return (LAImax - (LAImax - LAImin) * (30 - days) / 30.);
+        } else {
+            if (arid && (prec < 0.5)) days--;
+            else days = 30 + initialDays;
+            return LAImax;
+        }
+    }
+}
+
+__device__ __forceinline__ double lai_nogrowing(int &days, int initialDays, int &status, double LAImin, double LAImax,
+                                                double &precsum, double prec) {
+    if (status == 0) {
+        if (days > initialDays) {
+            days++;
+            precsum += prec;
+            if (precsum > 40.) {
+                if (days >= initialDays + 30) {
+                    days = initialDays + 30;
+                    status = 1;
+                }
+                return (LAImin + (LAImax - LAImin) * (days - initialDays) / 30.);
+            } else {
+                days = initialDays;
+                return LAImin;
+            }
+        } else {
+            precsum += prec;
+            return LAImin;
+        }
+    } else {
+        if (days <= 30) {
+            days--;
+            if (days <= 0) {
+                days = 0;
+                status = 0;
+                precsum = 0.;
+            }
+            return (LAImax - (LAImax - LAImin) * (30 - days) / 30.);
+        } else {
+            days--;
+            return LAImax;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// vertical water balance
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_vertical(const __grid_constant__ WgkParams p) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (r >= p.ncell) return;
+    const WgkArrays &a = p.a;
+    if (!a.contcell[r]) return;  // integrateWGHM.cpp:772
+    const size_t i = (size_t)m * p.stride + r;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const int slot = p.cal[3];
+
+    // daily.cpp:159-169, routing.h:246-251
+    const int started = a.status_laf_next[i];
+    const double landAreaFrac = (0 == started) ? a.land_area_frac[i] : a.land_area_frac_next[i];
+    double lafPrev;
+    if (1 == started) lafPrev = a.land_area_frac_prev[i];
+    else if (p.restart == 1) lafPrev = a.land_area_frac_prev[i];
+    else lafPrev = landAreaFrac;
+
+    if (1 != a.toBeCalculated[r]) return;  // daily.cpp:177
+
+    const int lc = a.landcover[r] - 1;
+    const float4 f = p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r];
+    double dailyPrec = (double)f.x;
+    const double dailyTempC = (double)f.y;
+    const double dailyShortWave = (double)f.z;
+    const double dailyLongWave = (double)f.w;
+
+    dailyPrec = a.p_prec[q] * dailyPrec;  // :248
+    const double temp2 = dailyTempC + 237.3;
+    const double e_s = 0.6108 * exp(17.27 * dailyTempC / temp2);
+
+    // arid / humid (:331-348); any other index value is rejected on upload
+    const bool arid_gw = (a.arid[r] == 1);
+    const double alpha = arid_gw ? a.p_ptc_ari[q] : a.p_ptc_hum[q];
+    const double maxDailyPET = a.p_pet_mxdy[q];
+
+    // LAI / Kc (:355-356); LAImin in float arithmetic as in lai.cpp:154
+    const float laimax_f = a.laimax[q];
+    const float LAImin_f = __fadd_rn(a.lai_factor_a[lc], __fmul_rn(a.lai_factor_b[lc], laimax_f));
+    const double LAImin = (double)LAImin_f;
+    const double LAImaxd = (double)laimax_f;
+    int days = a.lai_days[i], status = a.lai_status[i];
+    double precsum = a.lai_precsum[i];
+    double dailyLai;
+    if (dailyTempC > 8.)
+        dailyLai = lai_growing(days, a.lai_initial_days[lc], status, lc + 1, arid_gw, LAImin, LAImaxd, precsum, dailyPrec);
+    else
+        dailyLai = lai_nogrowing(days, a.lai_initial_days[lc], status, LAImin, LAImaxd, precsum, dailyPrec);
+    a.lai_days[i] = days;
+    a.lai_status[i] = status;
+    a.lai_precsum[i] = precsum;
+    double dailyKc;
+    if ((LAImaxd - LAImin) == 0.) dailyKc = a.lai_kc_min[lc];
+    else dailyKc = a.lai_kc_min[lc] + (a.lai_kc_max[lc] - a.lai_kc_min[lc]) * (dailyLai - LAImin) / (LAImaxd - LAImin);
+
+    const double snow_prev = a.snow[i];
+    double albedo;
+    if (snow_prev > 3.) albedo = a.lct_albedo_snow[lc];  // :366
+    else albedo = 0.23;                                   // use_kc == 1
+
+    double lat_heat;
+    if (dailyTempC > 0) lat_heat = 2.501 - 0.002361 * dailyTempC;
+    else lat_heat = 2.835;
+
+    const double conv_Wm2_to_mmd = 0.0864 / lat_heat;
+    const double solar_rad = conv_Wm2_to_mmd * dailyShortWave;
+    const double long_wave_rad_in = conv_Wm2_to_mmd * dailyLongWave;
+    const double emissivity = a.lct_emissivity[lc];
+    const double temp_K = dailyTempC + 273.2;
+    const double stefan_boltz_const = 0.000000004903;
+    const double long_wave_rad_out = emissivity * stefan_boltz_const * pow(temp_K, 4.) / lat_heat;
+    const double net_long_wave_rad = long_wave_rad_in - long_wave_rad_out;
+    const double net_short_wave_rad = solar_rad * (1. - albedo);
+    const double net_rad = a.p_netrad[q] * (net_short_wave_rad + net_long_wave_rad);
+    const double openWaterNetShortWaveRad = solar_rad * (1. - 0.08);
+    const double openWaterNetRad = openWaterNetShortWaveRad + net_long_wave_rad;
+
+    double dailyPET, dailyOpenWaterPET;
+    const double inc_svp = 4098. * e_s / (temp2 * temp2);
+    const double c3 = 0.0016286 * 101.3;
+    const double gamma = c3 / lat_heat;
+    if (net_rad <= 0.) dailyPET = 0.;
+    else dailyPET = alpha * (inc_svp * net_rad) / (inc_svp + gamma);
+    if (openWaterNetRad <= 0.) dailyOpenWaterPET = 0.;
+    else dailyOpenWaterPET = alpha * (inc_svp * openWaterNetRad) / (inc_svp + gamma);
+    if (snow_prev <= 3.) {  // :768-771
+        dailyPET *= dailyKc;
+        dailyOpenWaterPET *= 1.05;
+    }
+    const double cfa = a.cfa[q];
+    a.lake_balance[i] = (dailyPrec - dailyOpenWaterPET) * cfa;
+    a.openwater_prec[i] = dailyPrec;
+    a.openwater_pet[i] = dailyOpenWaterPET;
+
+    double landStorageChangeSum = 0., initialStorage = 0.;
+    double dailyCanopyEvapo = 0., daily_prec_to_soil = 0., dailySoilPET = 0.;
+    double dailySnowEvapo = 0., dailyEffPrec = 0.;
+    double immediate_runoff = 0., dailyAET = 0., daily_runoff = 0., total_daily_runoff = 0.;
+    double daily_gw_recharge = 0., pot_gw_recharge = 0.;
+    double soil_water_overflow = 0., neg_land_aet = 0.;
+    double storage_transfer = 0.;
+    double land_aet = 0., land_aet_uncorr = 0.;
+
+    const double P_T_SNOWFZ = a.p_snowfz[q];
+    const double P_T_SNOWMT = a.p_snowmt[q];
+    const double P_T_GRADNT = a.p_gradnt[q];
+    const double M_DEGDAY_F = a.p_degday[q];
+    const bool noland = (landAreaFrac <= 0.);
+
+    // interception (:825-894)
+    double canopy = a.canopy[i];
+    if (noland) {
+        storage_transfer = canopy;
+        canopy = 0.;
+        dailyCanopyEvapo = 0.;
+    } else {
+        canopy *= lafPrev / landAreaFrac;
+        if (fabs(canopy) <= MIN_STOR_VOL) canopy = 0.;
+        initialStorage = canopy;
+        if (dailyLai > 0.00001) {
+            const double max_canopy_storage = a.p_mcwh[q] * dailyLai;
+            const double canopy_deficiency = max_canopy_storage - canopy;
+            if (dailyPrec < canopy_deficiency) {
+                canopy += dailyPrec;
+                daily_prec_to_soil = 0.;
+            } else {
+                canopy = max_canopy_storage;
+                daily_prec_to_soil = dailyPrec - canopy_deficiency;
+            }
+            const double canopy_water_content = canopy;
+            dailyCanopyEvapo = dailyPET * pow((canopy_water_content / max_canopy_storage), 0.66666666);
+            if (dailyCanopyEvapo > canopy_water_content) {
+                dailyCanopyEvapo = canopy_water_content;
+                dailySoilPET = dailyPET - canopy_water_content;
+                canopy = 0.0;
+            } else {
+                canopy -= dailyCanopyEvapo;
+                dailySoilPET = dailyPET - dailyCanopyEvapo;
+            }
+        } else {
+            daily_prec_to_soil = dailyPrec;
+            dailySoilPET = dailyPET;
+            dailyCanopyEvapo = 0.0;
+        }
+        landStorageChangeSum += canopy - initialStorage;
+    }
+    a.canopy[i] = canopy;
+    if (dailySoilPET < 0.) dailySoilPET = 0.0;
+
+    // snow in 100 elevation bands (:913-1062); band-major arrays: band e of this cell is
+    // S[e*stride], coalesced over the warp
+    double TempElevMax = 0., snowStorageChange = 0., snow = 0.;
+    int thresh_elev = 0;
+    double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r;
+    const int16_t *__restrict__ E = a.elevation + r;
+    const int elev0 = E[0];
+    const double ddf = M_DEGDAY_F * a.lct_ddf[lc];  // (M_DEGDAY_F * ddf_lct) * (...) keeps the reference association
+    if (noland) {
+#pragma unroll 4
+        for (int e = 1; e < 101; e++) {
+            storage_transfer += S[(size_t)e * p.stride] / 100.;
+            S[(size_t)e * p.stride] = 0.;
+        }
+        snow = 0.;
+    } else {
+        const double scale_num = lafPrev;
+#pragma unroll 4
+        for (int e = 1; e < 101; e++) {
+            const int elev_e = E[(size_t)e * p.stride];
+            double s = S[(size_t)e * p.stride];
+            double temp_elev = dailyTempC - ((elev_e - elev0) * P_T_GRADNT);
+            double snowmelt_elev = 0., effBefore = 0.;
+            s = s * scale_num / landAreaFrac;
+            if (fabs(s) <= MIN_STOR_VOL) s = 0.;
+            const double s0 = s;
+            if (s > 1000.) {  // :958-976
+                if (thresh_elev == 0) thresh_elev = elev_e;
+                else if (thresh_elev > 0) temp_elev = dailyTempC - ((thresh_elev - elev0) * P_T_GRADNT);
+            }
+            if (temp_elev <= P_T_SNOWFZ) {
+                s += daily_prec_to_soil;
+                if (s > dailySoilPET) {
+                    s -= dailySoilPET;
+                    dailySnowEvapo += dailySoilPET;
+                } else {
+                    dailySnowEvapo += s;
+                    s = 0.;
+                }
+            } else {
+                effBefore = daily_prec_to_soil;
+            }
+            if (temp_elev > P_T_SNOWMT) {
+                if (!(s < 0.)) {
+                    snowmelt_elev = ddf * (temp_elev - P_T_SNOWMT);
+                    if (snowmelt_elev > s) {
+                        snowmelt_elev = s;
+                        s = 0.;
+                    } else {
+                        s -= snowmelt_elev;
+                    }
+                }
+            }
+            snowStorageChange += s - s0;
+            if (e == 1) TempElevMax = temp_elev;
+            snow += s;
+            dailyEffPrec += effBefore + snowmelt_elev;
+            S[(size_t)e * p.stride] = s;
+        }
+        snow /= 100.;
+        dailyEffPrec /= 100.;
+        dailySnowEvapo /= 100.;
+        snowStorageChange /= 100.;
+        landStorageChangeSum += snowStorageChange;
+    }
+    a.snow[i] = snow;
+
+    // immediate runoff (:1068-1071)
+    const float builtup = a.builtup[r];
+    if (builtup > 0.) {
+        immediate_runoff = 0.5 * dailyEffPrec * builtup;
+        dailyEffPrec -= immediate_runoff;
+    }
+
+    // soil and AET (:1080-1239)
+    const double Smax = (double)a.smax[q];
+    double soil = a.soil[i];
+    if (noland) {
+        storage_transfer += soil;
+        storage_transfer *= cfa;
+        soil = 0.;
+        daily_gw_recharge = 0.;
+        total_daily_runoff = 0.;
+        a.gw_recharge[i] = 0.;
+        a.storage_transfer[i] = storage_transfer;
+    } else {
+        soil *= lafPrev / landAreaFrac;
+        initialStorage = soil;
+        soil_water_overflow = 0;
+        if (soil > Smax) {
+            soil_water_overflow = soil - Smax;
+            soil = Smax;
+        }
+        if (TempElevMax > P_T_SNOWFZ) {
+            if (Smax > 0.) {
+                const double soil_saturation = soil / Smax;
+                daily_runoff = dailyEffPrec * pow(soil_saturation, a.gamma_hbv[q]);
+                if (dailySoilPET > (maxDailyPET - dailyCanopyEvapo) * soil_saturation)
+                    dailyAET = (maxDailyPET - dailyCanopyEvapo) * soil_saturation;
+                else
+                    dailyAET = dailySoilPET;
+                soil += dailyEffPrec - dailyAET - daily_runoff;
+                if (fabs(soil) <= MIN_STOR_VOL) soil = 0.;
+                dailyEffPrec = 0.;
+                if (soil < 0.) {
+                    dailyAET += soil;
+                    soil = 0.;
+                }
+                daily_runoff *= cfa;
+                immediate_runoff *= cfa;
+                const short Rgmax = a.rgmax[q];
+                const float gwFactor = a.gwfactor[q];
+                if ((Rgmax / 100.) < (gwFactor * daily_runoff)) daily_gw_recharge = Rgmax / 100.;
+                else daily_gw_recharge = gwFactor * daily_runoff;
+                pot_gw_recharge = 0.;
+                if (((arid_gw) && (a.texture[r] < 21)) && (a.ldd[r] >= 0)) {  // :1165-1176
+                    if (dailyPrec <= a.p_pcrit[q]) {
+                        pot_gw_recharge = daily_gw_recharge;
+                        daily_gw_recharge = 0.;
+                    }
+                }
+                daily_runoff -= pot_gw_recharge;
+                pot_gw_recharge /= cfa;
+                soil += pot_gw_recharge;
+                if (soil > Smax) {
+                    soil_water_overflow += soil - Smax;
+                    soil = Smax;
+                }
+                soil_water_overflow *= cfa;
+                total_daily_runoff = daily_runoff + immediate_runoff + soil_water_overflow;
+            } else {
+                total_daily_runoff = 0.;
+                daily_gw_recharge = 0.;
+            }
+        } else {
+            soil_water_overflow *= cfa;
+            dailyEffPrec *= cfa;
+            total_daily_runoff += soil_water_overflow + dailyEffPrec;
+            daily_gw_recharge = 0.;
+            dailyAET = 0.;
+        }
+        a.gw_recharge[i] = daily_gw_recharge;  // :1221 (not updated by the fix-up below)
+        landStorageChangeSum += soil - initialStorage;
+        land_aet = landStorageChangeSum * (cfa - 1.0) - dailyPrec * (cfa - 1.0)
+                   + (dailyAET + dailyCanopyEvapo + dailySnowEvapo) * cfa;
+        if (land_aet < 0.) {
+            neg_land_aet = land_aet;
+            land_aet = 0.;
+        }
+        land_aet_uncorr = (dailyAET + dailyCanopyEvapo + dailySnowEvapo);
+    }
+    a.land_aet[i] = land_aet;
+    a.land_aet_uncorr[i] = land_aet_uncorr;
+
+    // surface runoff (:1244-1257)
+    if (neg_land_aet < 0.) total_daily_runoff = total_daily_runoff + neg_land_aet;
+    if (total_daily_runoff < 0.) total_daily_runoff = 0.;
+    if ((total_daily_runoff - daily_gw_recharge) < 0.) {
+        const double neg_runoff = total_daily_runoff - daily_gw_recharge;
+        daily_gw_recharge = total_daily_runoff;
+        soil += neg_runoff;
+    }
+    a.soil[i] = soil;
+    a.surface_runoff[i] = total_daily_runoff - daily_gw_recharge;
+}
+
+// ----------------------------------------------------------------------------------------
+// routing helpers
+// ----------------------------------------------------------------------------------------
+// groundwater linear reservoir (routing.cpp:1938-1958 and four identical copies)
+__device__ __forceinline__ double gw_step(double &Sg, double netGWin, double k) {
+    const double prev = Sg;
+    const double ek = exp(-1. * k);
+    Sg = prev * ek + (1. / k) * netGWin * (1. - ek);
+    if (fabs(Sg) <= MIN_STOR_VOL) Sg = 0.;
+    double qq = prev - Sg + netGWin;
+    if (qq <= 0.) {
+        qq = 0.;
+        Sg = prev + netGWin;
+        if (fabs(Sg) <= MIN_STOR_VOL) Sg = 0.;
+    }
+    return qq;
+}
+
+// routingClass::getRiverVelocity (routing.cpp:7274-7307)
+__device__ __forceinline__ double river_velocity(double slope_pow, double bottomWidth, double Roughness,
+                                                 double riverInflow, double M_RIVRGH_C) {
+    const double incoming_discharge = (riverInflow * 1000. * 1000. * 1000.) / (60. * 60. * 24.);
+    const double riverDepth = 0.349 * pow(incoming_discharge, 0.341);
+    const double crossSectionalArea = riverDepth * (2.0 * riverDepth + bottomWidth);
+    const double wettedPerimeter = bottomWidth + 2.0 * riverDepth * sqrt(5.0);
+    const double hydraulicRad = crossSectionalArea / wettedPerimeter;
+    double v = 1. / (M_RIVRGH_C * Roughness) * pow(hydraulicRad, (2. / 3.)) * slope_pow;
+    v = v * 86.4;
+    if (v < 0.00001) return 0.00001;
+    return v;
+}
+
+__device__ __forceinline__ double clamp01(double x) {
+    if (x < 0.) x = 0.;
+    if (x > 1.) x = 1.;
+    return x;
+}
+
+// ----------------------------------------------------------------------------------------
+// cell-parallel pre-pass of the routing day
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ WgkParams p) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (r >= p.ncell) return;
+    const WgkArrays &a = p.a;
+    const size_t i = (size_t)m * p.stride + r;
+    a.river_evapo[i] = 0.;  // routing.cpp:1781
+    if (!a.contcell[r]) return;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const double kG = a.p_gwoutf[q];
+    const double M_EVAREDEX = a.p_evaredex[q];
+    const double cellArea = a.area[r];
+    const double cfa = a.cfa[q];
+    const double owPrec = a.openwater_prec[i], owPET = a.openwater_pet[i];
+    const int ldd = a.ldd[r];
+    const int arid = a.arid[r];
+    const bool aridc = (1 == arid) && (ldd >= 0);
+    const double laf = a.land_area_frac[i];
+    double dailyLocalSurfaceRunoff;
+    double localRunoff = 0., localRunoffIntoRiver = 0., localGWRunoffIntoRiver = 0., fswb_catchment = 0.;
+    double gwr_loclak = 0., gwr_locwet = 0.;
+
+    if (laf <= 0.)  // :1885-1891
+        dailyLocalSurfaceRunoff = a.storage_transfer[i] * cellArea / 1000000. * a.land_area_frac_prev[i] / 100.;
+    else
+        dailyLocalSurfaceRunoff = a.surface_runoff[i] * cellArea / 1000000. * laf / 100.;
+    if (ldd >= 0) {  // :1898-1908
+        fswb_catchment = a.fswb_init[r] * 20.;
+        if (fswb_catchment > 1.) fswb_catchment = 1.;
+        localRunoffIntoRiver = (1. - fswb_catchment) * dailyLocalSurfaceRunoff;
+    }
+    if ((1 == arid) && (ldd >= 0)) {  // :1910-1915
+        localRunoff = fswb_catchment * dailyLocalSurfaceRunoff;
+    }
+    if ((0 == arid) && (ldd >= 0)) {  // :1979-2033
+        const double netGWin = a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
+        double Sg = a.gw[i];
+        const double qg = gw_step(Sg, netGWin, kG);
+        a.gw[i] = Sg;
+        localGWRunoffIntoRiver = (1. - fswb_catchment) * qg;
+        const double localGWRunoff = fswb_catchment * qg;
+        localRunoff = (fswb_catchment * dailyLocalSurfaceRunoff) + localGWRunoff;
+    }
+    if (ldd < 0) {  // :2123-2176
+        const double netGWin = a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
+        double Sg = a.gw[i];
+        const double qg = gw_step(Sg, netGWin, kG);
+        a.gw[i] = Sg;
+        if (laf == 0.)
+            dailyLocalSurfaceRunoff = a.storage_transfer[i] * cellArea / 1000000. * a.land_area_frac_prev[i] / 100.;
+        else
+            dailyLocalSurfaceRunoff = a.surface_runoff[i] * cellArea / 1000000. * laf / 100.;
+        localRunoff = dailyLocalSurfaceRunoff + qg;
+    }
+
+    double inflow = localRunoff;
+    if (0 != a.toBeCalculated[r]) {
+        const double kS = a.p_swoutf[q];
+        const double contf = a.contfreq[r];
+        const double loc_lake = a.loc_lake[r];
+        if (loc_lake > 0.) {  // local lake, :2318-2490
+            const double prev = a.loc_lake_stor[i];
+            const double maxStorage = ((loc_lake) / 100.) * cellArea * a.lake_depth_active[q];
+            const double rf = a.red_loc_lake[i];
+            double evapo = ((1.0 - cfa) * owPrec * rf) + (cfa * (owPET * rf));
+            if (evapo < 0.) evapo = 0.;
+            const double totalInflow = inflow + (owPrec * rf) * (cellArea / 1000000.) * (loc_lake / 100.);
+            if (aridc) gwr_loclak = 10. * rf * loc_lake / 100. / (contf / 100.);
+            const double PETgwr = evapo * (cellArea / 1000000.) * (loc_lake / 100.) + gwr_loclak * cellArea * (contf / 100.) / 1000000.;
+            double PETgwrMax = prev + maxStorage + totalInflow;
+            if (PETgwrMax < 0.) PETgwrMax = 0.;
+            double S;
+            if (PETgwr > PETgwrMax) {
+                S = (-1.) * maxStorage;
+                gwr_loclak *= PETgwrMax / PETgwr;
+            } else {
+                S = prev + totalInflow - PETgwr;
+            }
+            double outflow;
+            if (prev > 0.) {
+                outflow = kS * prev * pow((prev / maxStorage), 1.5);
+                if (S <= 0.) outflow = 0;
+                else if (outflow > S) outflow = S;
+            } else
+                outflow = 0.;
+            S -= outflow;
+            if (fabs(S) <= MIN_STOR_VOL) S = 0.;
+            if (S > maxStorage) {
+                outflow += (S - maxStorage);
+                S = maxStorage;
+            }
+            inflow = outflow;
+            a.loc_lake_stor[i] = S;
+            a.red_loc_lake[i] = clamp01(1. - pow(fabs(S - maxStorage) / (2. * maxStorage), (M_EVAREDEX * 3.32193)));
+        }
+        const double loc_wetland = a.loc_wetland[r];
+        if (loc_wetland > 0.) {  // local wetland, :2495-2617
+            const double prev = a.loc_wetl_stor[i];
+            const double maxStorage = ((loc_wetland) / 100.) * cellArea * a.wetl_depth_active[q];
+            const double rf = a.red_loc_wetl[i];
+            double evapo = ((1.0 - cfa) * owPrec * rf) + (cfa * (owPET * rf));
+            if (evapo < 0.) evapo = 0.;
+            const double totalInflow = inflow + (owPrec * rf * (cellArea / 1000000.) * (loc_wetland / 100.));
+            if (aridc) gwr_locwet = 10. * rf * loc_wetland / 100. / (contf / 100.);
+            const double PETgwr = evapo * (cellArea / 1000000.) * (loc_wetland / 100.) + gwr_locwet * cellArea * (contf / 100.) / 1000000.;
+            const double PETgwrMax = prev + totalInflow;
+            double S;
+            if (PETgwr > PETgwrMax) {
+                S = 0.;
+                gwr_locwet *= PETgwrMax / PETgwr;
+            } else {
+                S = prev + totalInflow - PETgwr;
+            }
+            if (fabs(S) <= MIN_STOR_VOL) S = 0.;
+            double outflow;
+            if (S > 0.) {
+                outflow = kS * S * pow((S / maxStorage), 2.5);
+                if (outflow > S) outflow = S;
+            } else
+                outflow = 0.;
+            S -= outflow;
+            if (S > maxStorage) {
+                outflow += (S - maxStorage);
+                S = maxStorage;
+            }
+            inflow = outflow;
+            a.loc_wetl_stor[i] = S;
+            a.red_loc_wetl[i] = clamp01(1. - pow(fabs(S - maxStorage) / (maxStorage), (M_EVAREDEX * 3.32193)));
+        }
+    }
+    a.t_inflow_local[i] = inflow;
+    a.t_runoff_to_river[i] = localRunoffIntoRiver;
+    a.t_gw_to_river[i] = localGWRunoffIntoRiver;
+    a.t_gwr_loclak[i] = gwr_loclak;
+    a.t_gwr_locwet[i] = gwr_locwet;
+}
+
+// ----------------------------------------------------------------------------------------
+// one cell of the ordered sweep: everything from "inflow += G_riverInflow[n]" on
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void route_cell(const WgkParams &p, const int r, const int m, const int day, const int month) {
+    const WgkArrays &a = p.a;
+    const size_t mb = (size_t)m * p.stride;
+    const size_t i = mb + r;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const bool active = a.contcell[r] && (0 != a.toBeCalculated[r]);
+    const double contf = a.contfreq[r];
+    const double cellArea = a.area[r];
+    double red_loc_lake = a.red_loc_lake[i], red_loc_wetl = a.red_loc_wetl[i], red_glo_wetl = a.red_glo_wetl[i];
+    double red_river = a.red_river[i];
+    double raf_next = a.river_area_frac_next[i];
+    double raf_change = a.river_area_frac_change[i];
+    const double laf = a.land_area_frac[i];
+    const double lake_area = a.lake_area[r];
+    const double reservoir_area = a.reservoir_area[r];
+    const double glo_wetland = a.glo_wetland[r];
+
+    if (active) {
+        const double M_EVAREDEX = a.p_evaredex[q];
+        const double kS = a.p_swoutf[q];
+        const double cfa = a.cfa[q];
+        const double owPrec = a.openwater_prec[i], owPET = a.openwater_pet[i];
+        const int ldd = a.ldd[r];
+        const bool aridc = (1 == a.arid[r]) && (ldd >= 0);
+        // loads that do not depend on upstream cells are issued before the gather
+        const double slope_pow = pow(a.river_slope[r], 0.5);
+        const double bw = a.river_bottom_width[r];
+        const double rough = a.roughness[r];
+        const double rivrgh = a.p_rivrgh[q];
+        const double river_length = a.river_length[r];
+        const double prevR = a.river_stor[i];
+        double inflow = a.t_inflow_local[i];
+
+        // upstream inflow in routing order (= order of the += at routing.cpp:3957)
+        double inflowUpstream = 0.;
+        for (int k = p.up_off[r]; k < p.up_off[r + 1]; k++) inflowUpstream += a.discharge[mb + p.up_idx[k]];
+        inflow += inflowUpstream;  // :2623
+
+        double gwr_glolak = 0., gwr_res = 0., gwr_glowet = 0.;
+        if (lake_area > 0.) {  // global lake, :2630-2804
+            const double prev = a.glo_lake_stor[i];
+            const double maxStorage = (lake_area)*a.lake_depth_active[q];
+            const double rf = a.red_glo_lake[i];
+            double evapo = ((1.0 - cfa) * owPrec) + (cfa * owPET * rf);
+            if (evapo < 0.) evapo = 0.;
+            const double totalInflow = inflow + (owPrec * (lake_area / 1000000.));
+            if (aridc) gwr_glolak = 10. * rf * (lake_area / (cellArea * (contf / 100.)));
+            const double PETgwrRemUse = evapo * (lake_area / 1000000.) + gwr_glolak * cellArea * (contf / 100.) / 1000000. + 0.;
+            const double PETgwrRemUseMax = totalInflow + maxStorage + prev;
+            double S, outflow;
+            if (PETgwrRemUse > PETgwrRemUseMax) {
+                S = (-1.) * maxStorage;
+                outflow = 0.;
+                gwr_glolak *= PETgwrRemUseMax / PETgwrRemUse;
+            } else {
+                const double ek = exp(-1. * kS);
+                S = prev * ek + (1. / kS) * (totalInflow - PETgwrRemUse) * (1. - ek);
+                outflow = totalInflow + prev - S - PETgwrRemUse;
+                if (S > maxStorage) {
+                    outflow += (S - maxStorage);
+                    S = maxStorage;
+                }
+                if (outflow < 0.) {
+                    outflow = 0.;
+                    S = prev + totalInflow - PETgwrRemUse;
+                }
+            }
+            if (fabs(S) <= MIN_STOR_VOL) S = 0.;
+            inflow = outflow;
+            a.glo_lake_stor[i] = S;
+            a.red_glo_lake[i] = clamp01(1. - pow(fabs(S - maxStorage) / (2. * maxStorage), (M_EVAREDEX * 3.32193)));
+        }
+        if (reservoir_area > 0.) {  // reservoir, :2807-3082
+            const double stor_cap = a.stor_cap[r];
+            const double mean_outflow = a.mean_outflow[r];
+            const double c_ratio = stor_cap / (mean_outflow * 31536000. / 1000000000.);
+            const double maxStorage = stor_cap;
+            const double prev = a.res_stor[i];
+            const double rf = a.red_res[i];
+            double evapo = ((1.0 - cfa) * owPrec) + (cfa * (owPET * rf));
+            if (evapo < 0.) evapo = 0.;
+            const double totalInflow = inflow + (owPrec * (reservoir_area / 1000000.));
+            if (aridc) gwr_res = 10. * rf * (reservoir_area / (cellArea * (contf / 100.)));
+            const double PETgwr = evapo * (reservoir_area / 1000000.) + gwr_res * cellArea * (contf / 100.) / 1000000.;
+            const double PETgwrMax = prev + totalInflow;
+            double S;
+            if (PETgwr > PETgwrMax) {
+                S = prev + totalInflow - PETgwrMax;
+                gwr_res *= PETgwrMax / PETgwr;
+            } else {
+                S = prev + totalInflow - PETgwr;
+            }
+            if (fabs(S) <= MIN_STOR_VOL) S = 0.;
+            double Krel = a.k_release[i];
+            const int fdim[12] = {1, 32, 60, 91, 121, 152, 182, 213, 244, 274, 305, 335};
+            if (month == a.start_month[r] - 1 && day == fdim[month]) {  // :2945-2956
+                if (S < (stor_cap * 0.1)) Krel = 0.1;
+                else Krel = S / (maxStorage * 0.85);
+                a.k_release[i] = Krel;
+            }
+            double prov_rel = 0.;
+            const int res_type = a.res_type[r];
+            if (res_type == 1) {  // irrigation reservoir; water use is not simulated: monthlyUse == 0
+                const double monthlyUse = 0.;
+                const double mean_demand = a.mean_demand[r];
+                if (mean_demand >= 0.5 * mean_outflow) prov_rel = mean_outflow / 2. * (1. + monthlyUse / mean_demand);
+                else prov_rel = mean_outflow + monthlyUse - mean_demand;
+            } else if (res_type == 2) {
+                prov_rel = mean_outflow;
+            }
+            double release;
+            if (c_ratio >= 0.5) release = Krel * prov_rel;
+            else
+                release = ((4. * c_ratio * c_ratio) * Krel * prov_rel)
+                          + ((1.0 - ((4. * c_ratio * c_ratio))) * inflow * 1000000000. / (24. * 3600.));
+            double outflow;
+            if (S >= (stor_cap * 0.1)) outflow = release * (24. * 3600.) / 1000000000.;
+            else outflow = 0.1 * release * (24. * 3600.) / 1000000000.;
+            if (outflow < 0.) outflow = 0.;
+            S -= outflow;
+            if (S > maxStorage) {
+                outflow += (S - maxStorage);
+                S = maxStorage;
+            }
+            if (S < 0.) {
+                outflow += S;
+                S = 0.;
+            }
+            inflow = outflow;
+            a.res_stor[i] = S;
+            a.red_res[i] = clamp01(1. - pow(fabs(S - maxStorage) / maxStorage, 2.81383));
+        }
+        if (glo_wetland > 0) {  // global wetland, :3178-3297
+            const double prev = a.glo_wetl_stor[i];
+            const double maxStorage = ((glo_wetland) / 100.) * cellArea * a.wetl_depth_active[q];
+            const double rf = red_glo_wetl;
+            double evapo = ((1.0 - cfa) * (owPrec * rf)) + (cfa * (owPET * rf));
+            if (evapo < 0.) evapo = 0.;
+            const double totalInflow = inflow + (owPrec * rf * (cellArea / 1000000.) * (glo_wetland / 100.));
+            if (aridc) gwr_glowet = 10. * rf * glo_wetland / 100. / (contf / 100.);
+            const double PETgwr = evapo * (cellArea / 1000000.) * ((glo_wetland) / 100.) + gwr_glowet * cellArea * (contf / 100.) / 1000000.;
+            const double PETgwrMax = totalInflow + prev;
+            double S, outflow;
+            if (PETgwr > PETgwrMax) {
+                S = 0.;
+                outflow = 0.;
+                gwr_glowet *= PETgwrMax / PETgwr;
+            } else {
+                const double ek = exp(-1. * kS);
+                S = prev * ek + (1. / kS) * (totalInflow - PETgwr) * (1. - ek);
+                outflow = totalInflow + prev - S - PETgwr;
+            }
+            if (S > maxStorage) {
+                outflow += (S - maxStorage);
+                S = maxStorage;
+            }
+            if (fabs(S) <= MIN_STOR_VOL) S = 0.;
+            inflow = outflow;
+            a.glo_wetl_stor[i] = S;
+            red_glo_wetl = clamp01(1. - pow(fabs(S - maxStorage) / maxStorage, (M_EVAREDEX * 3.32193)));
+        }
+        double gwToRiver = a.t_gw_to_river[i];
+        if (aridc) {  // :3305-3386
+            const double gwr_swb = a.t_gwr_loclak[i] + gwr_glolak + a.t_gwr_locwet[i] + gwr_glowet + gwr_res;
+            a.gwr_swb[i] = gwr_swb;
+            const double netGWin = gwr_swb * cellArea * (contf / 100.) / 1000000.
+                                   + a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
+            double Sg = a.gw[i];
+            gwToRiver = gw_step(Sg, netGWin, a.p_gwoutf[q]);
+            a.gw[i] = Sg;
+        }
+        // river, :3388-3586
+        double riverInflow = inflow;
+        if (ldd >= 0) {
+            riverInflow += a.t_runoff_to_river[i];
+            riverInflow += gwToRiver;
+        }
+        const double riverVelocity = river_velocity(slope_pow, bw, rough, riverInflow, rivrgh);
+        const double K = riverVelocity / river_length;
+        const double raf = raf_next;  // G_riverAreaFrac[n] = G_riverAreaFracNextTimestep_Frac[n]
+        double riverEvapo = ((1.0 - cfa) * (owPrec) + (cfa * owPET)) * raf / 100. * cellArea / 1000000.;
+        const double riverPrecip = owPrec * raf / 100. * cellArea / 1000000.;
+        riverInflow += riverPrecip;
+        const double RiverEvapoRemUse = 0. + riverEvapo;
+        const double eK = exp(-1. * K);
+        const double RivEvapoRemUseMax = riverInflow + (K * prevR * eK) / (1. - eK);
+        double Sr, transportedVolume;
+        if (RiverEvapoRemUse > RivEvapoRemUseMax) {
+            Sr = 0.;
+            transportedVolume = riverInflow + prevR - RivEvapoRemUseMax;
+            if (transportedVolume < 0.) transportedVolume = 0.;
+            riverEvapo *= RivEvapoRemUseMax / RiverEvapoRemUse;
+        } else {
+            Sr = prevR * eK + (1. / K) * (riverInflow - RiverEvapoRemUse) * (1. - eK);
+            if (fabs(Sr) <= MIN_STOR_VOL) Sr = 0.;
+            transportedVolume = riverInflow + prevR - Sr - RiverEvapoRemUse;
+            if (transportedVolume < 0.) transportedVolume = 0.;
+        }
+        // hand the outflow to the next level first: it is the only value other cells wait for.
+        // (inland sinks have no downstream cell; the reference keeps their river outflow out of
+        //  the discharge grid, routing.cpp:4219-4221, and books it as evaporation, :3935-3937)
+        a.discharge[i] = (ldd >= 0) ? transportedVolume : 0.;
+        a.cell_runoff[i] = (ldd < 0) ? (0. - inflowUpstream) : (transportedVolume - inflowUpstream);
+        a.river_stor[i] = Sr;
+        a.river_evapo[i] = riverEvapo;
+        {  // river width / area fraction for the next day, :3546-3586
+            const double crossSectionalArea = Sr / river_length;
+            const double riverDepth = -bw / (4. * 1000.) + sqrt(bw / 1000. * bw / (16. * 1000.) + 0.5 * crossSectionalArea);
+            double width = bw / 1000. + 4. * riverDepth;
+            const double wbf = a.river_width_bf[r];
+            if (width > wbf / 1000.) width = wbf / 1000.;
+            const double smaxr = a.river_storage_max[r];
+            red_river = clamp01(1. - pow(fabs(Sr - smaxr) / smaxr, (M_EVAREDEX * 3.32193)));
+            raf_next = red_river * river_length * width * 100. / cellArea;
+            raf_change = raf_next - raf;
+        }
+    }
+
+    // surface water body fractions and next-day land area fraction (:5034-5188), all cells
+    const double loc_lake = a.loc_lake[r], loc_wetland = a.loc_wetland[r];
+    double fLocLake = ((loc_lake > 0.) && (red_loc_lake > 0.)) ? (red_loc_lake * loc_lake / 100.) : 0.;
+    double fLocWet = ((loc_wetland > 0.) && (red_loc_wetl > 0.)) ? (red_loc_wetl * loc_wetland / 100.) : 0.;
+    double fGloWet = ((glo_wetland > 0.) && (red_glo_wetl > 0.)) ? (red_glo_wetl * glo_wetland / 100.) : 0.;
+    const double fswb_old = a.fswb_laf_next[i];
+    double fswb_next = fLocLake + fLocWet + fGloWet;
+    const double fGloLake = a.f_glo_lake[r];
+    const double maxRiverAreaFrac = contf / 100. - fGloLake;
+    if (((lake_area > 0.) || (reservoir_area > 0.)) && (fGloLake == 1.)) {
+        raf_next = 0.;
+        raf_change = 0.;
+        red_river = 0.;
+        a.river_evapo[i] = 0.;
+    } else {
+        if (raf_next <= maxRiverAreaFrac) {
+            if (fswb_next > (maxRiverAreaFrac - raf_next)) {
+                const double fswbFracCorr = (maxRiverAreaFrac - raf_next) / fswb_next;
+                red_loc_lake *= fswbFracCorr;
+                red_loc_wetl *= fswbFracCorr;
+                red_glo_wetl *= fswbFracCorr;
+                if ((fLocLake > 0.) && (red_loc_lake > 0.)) fLocLake = (red_loc_lake * loc_lake / 100.);
+                else { red_loc_lake = 0.; fLocLake = 0.; }
+                if ((fLocWet > 0.) && (red_loc_wetl > 0.)) fLocWet = (red_loc_wetl * loc_wetland / 100.);
+                else { red_loc_wetl = 0.; fLocWet = 0.; }
+                if ((fGloWet > 0.) && (red_glo_wetl > 0.)) fGloWet = (red_glo_wetl * glo_wetland / 100.);
+                else { red_glo_wetl = 0.; fGloWet = 0.; }
+            }
+        } else {
+            const double riverAreaFracDeficit = raf_next - maxRiverAreaFrac;
+            raf_change -= riverAreaFracDeficit;
+            red_river *= maxRiverAreaFrac / raf_next;
+            raf_next = maxRiverAreaFrac;
+            fLocLake = 0.;
+            fLocWet = 0.;
+            fGloWet = 0.;
+        }
+    }
+    fswb_next = fLocLake + fLocWet + fGloWet;
+    const double changePct = fswb_next * 100. - fswb_old * 100.;
+    double laf_next = laf - (changePct + (raf_change * 100.));
+    if (laf_next < 0.) laf_next = 0.;
+    a.red_loc_lake[i] = red_loc_lake;
+    a.red_loc_wetl[i] = red_loc_wetl;
+    a.red_glo_wetl[i] = red_glo_wetl;
+    a.red_river[i] = red_river;
+    a.river_area_frac_next[i] = raf_next;
+    a.river_area_frac_change[i] = raf_change;
+    a.fswb_laf[i] = fswb_old;
+    a.fswb_laf_next[i] = fswb_next;
+    a.status_laf_next[i] = 1;
+    // updateLandAreaFrac (:5343-5352) fused: prev <- cur, cur <- next
+    a.land_area_frac_next[i] = laf_next;
+    a.land_area_frac_prev[i] = laf;
+    a.land_area_frac[i] = laf_next;
+}
+
+// one dependency level per launch (wide levels)
+__global__ void __launch_bounds__(128) k_route_level(const __grid_constant__ WgkParams p, const int level) {
+    const int begin = p.level_off[level], end = p.level_off[level + 1];
+    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= end) return;
+    route_cell(p, r, blockIdx.y, p.cal[0], p.cal[1]);
+}
+
+// all levels from `level0` on inside one persistent CTA per member; levels are separated by
+// __syncthreads(), which also orders the global-memory hand-off of the discharge values
+__global__ void __launch_bounds__(256) k_route_tail(const __grid_constant__ WgkParams p, const int level0) {
+    const int m = blockIdx.x;
+    const int day = p.cal[0], month = p.cal[1];
+    for (int level = level0; level < p.nlevels; level++) {
+        const int begin = p.level_off[level], end = p.level_off[level + 1];
+        for (int r = begin + threadIdx.x; r < end; r += blockDim.x) route_cell(p, r, m, day, month);
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// calendar, forcing, diagnostics
+// ----------------------------------------------------------------------------------------
+__global__ void k_set_calendar(int32_t *cal, int day, int month, int dom, int slot) {
+    cal[0] = day; cal[1] = month; cal[2] = dom; cal[3] = slot;
+}
+
+// end of a simulated day: record station discharge, then advance the device calendar
+// (365-day years, integrateWGHM.cpp:100-102)
+__global__ void k_end_of_day(const __grid_constant__ WgkParams p) {
+    int32_t *cal = p.cal;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int simday = cal[4];
+    if (p.record && simday < p.record_max_days) {
+        const int total = p.nmember * p.nrec;
+        for (int k = t; k < total; k += gridDim.x * blockDim.x) {
+            const int m = k / p.nrec, c = k % p.nrec;
+            p.record[(size_t)simday * total + k] = p.a.discharge[(size_t)m * p.stride + p.record_cells[c]];
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        const int ndays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+        int day = cal[0], month = cal[1], dom = cal[2], slot = cal[3];
+        dom++;
+        day++;
+        if (dom > ndays[month]) { dom = 1; month++; }
+        if (month > 11) { month = 0; day = 1; }
+        slot++;
+        if (slot >= p.forcing_nslots) slot = 0;
+        cal[0] = day; cal[1] = month; cal[2] = dom; cal[3] = slot; cal[4] = simday + 1;
+    }
+}
+
+// host grids [cell][stride] (reference order) staged on the device -> [slot][cell] float4 (routing order)
+__global__ void k_forcing_pack(float4 *__restrict__ dst, const float *__restrict__ P, const float *__restrict__ T,
+                               const float *__restrict__ SW, const float *__restrict__ LW,
+                               const int32_t *__restrict__ cell_of_rank, int ncell, int stride_cells, int ndays,
+                               int src_stride, size_t slot_pitch) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ncell) return;
+    const int n = cell_of_rank[r];
+    for (int d = blockIdx.y; d < ndays; d += gridDim.y) {
+        const size_t s = (size_t)n * src_stride + d;
+        dst[(size_t)d * slot_pitch + r] = make_float4(P[s], T[s], SW[s], LW[s]);
+    }
+    (void)stride_cells;
+}
+
+// total water storage of one member (km3), block-reduced in a fixed order so that the value
+// is reproducible run to run
+__global__ void __launch_bounds__(256) k_total_storage(const __grid_constant__ WgkParams p, const int m, double *partial) {
+    __shared__ double sh[256];
+    const WgkArrays &a = p.a;
+    double s = 0.;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.ncell; r += gridDim.x * blockDim.x) {
+        const size_t i = (size_t)m * p.stride + r;
+        const double laf = (0 == a.status_laf_next[i]) ? a.land_area_frac[i] : a.land_area_frac_next[i];
+        const double land = (a.canopy[i] + a.snow[i] + a.soil[i]) * a.area[r] / 1000000. * laf / 100.;
+        s += land + a.gw[i] + a.loc_lake_stor[i] + a.loc_wetl_stor[i] + a.glo_lake_stor[i] + a.glo_wetl_stor[i]
+             + a.res_stor[i] + a.river_stor[i];
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+}  // namespace wgk
