@@ -9,7 +9,7 @@
 //       The run writes the reference's txt state files (16 significant digits).
 //
 //   ref_harness replay <config.txt> <dump.wgd> [--days A-B] [--every K] [--snow-days A-B]
-//                      [--final-state PREFIX] [--time-only]
+//                      [--final-state PREFIX] [--time-only] [--day-times FILE]
 //       replays the orchestration of integrate_wghm_ (integrateWGHM.cpp:127-309 init
 //       sequence, :546-922 year/month/day loops) calling the reference's own
 //       dailyWaterBalanceClass::calcNewDay / routingClass::routing /
@@ -235,7 +235,8 @@ static int run_replay(int argc, char **argv) {
     Range days, snowdays;
     int every = 0;
     bool time_only = false;
-    std::string final_prefix;
+    std::string final_prefix, day_times_file;
+    std::vector<double> day_times;
     for (int i = 4; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--days" && i + 1 < argc) days = parse_range(argv[++i]);
@@ -243,6 +244,7 @@ static int run_replay(int argc, char **argv) {
         else if (a == "--every" && i + 1 < argc) every = atoi(argv[++i]);
         else if (a == "--final-state" && i + 1 < argc) final_prefix = argv[++i];
         else if (a == "--time-only") time_only = true;
+        else if (a == "--day-times" && i + 1 < argc) day_times_file = argv[++i];
     }
     if (!time_only && strcmp(dumpfile, "-") != 0) {
         g_dump = fopen(dumpfile, "wb");
@@ -352,6 +354,7 @@ static int run_replay(int argc, char **argv) {
                 routing.updateLandAreaFrac(*additionalOutIn);
                 double td = now();
                 t_vert += tb - ta; t_rout += tc - tb; t_laf += td - tc;
+                day_times.push_back(td - ta);
                 ndays_done++;
                 if (readinstatus == 1) readinstatus = 0;
                 bool want = days.has(simday) || (every > 0 && simday % every == 0);
@@ -398,6 +401,10 @@ static int run_replay(int argc, char **argv) {
         if (month == 12) routing.updateGloResPrevYear_pct();
     }
     if (g_dump) fclose(g_dump);
+    if (!day_times_file.empty()) {  // seconds spent in the day-loop body, one line per simulated day
+        FILE *f = fopen(day_times_file.c_str(), "w");
+        if (f) { for (double t : day_times) fprintf(f, "%.9f\n", t); fclose(f); }
+    }
     long ncalc = 0;
     for (int n = 0; n < ng; n++) if (geo.G_contcell[n] && G_toBeCalculated[n] == 1) ncalc++;
     double tt = t_vert + t_rout + t_laf;
@@ -411,6 +418,6 @@ int main(int argc, char **argv) {
     if (argc >= 3 && std::string(argv[1]) == "driver") return run_driver(argv[2]);
     if (argc >= 4 && std::string(argv[1]) == "replay") return run_replay(argc, argv);
     fprintf(stderr, "usage: ref_harness driver <config> | replay <config> <dump|-> [--days A-B] [--every K] "
-                    "[--snow-days A-B] [--final-state PREFIX] [--time-only]\n");
+                    "[--snow-days A-B] [--final-state PREFIX] [--time-only] [--day-times FILE]\n");
     return 1;
 }

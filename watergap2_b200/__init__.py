@@ -89,6 +89,7 @@ def lib():
     L.wgk_total_storage_km3.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double)]
     L.wgk_record_cells.argtypes = [vp, vp, ci, ci]
     L.wgk_get_record.argtypes = [vp, ci, vp, ci]
+    L.wgk_profile_day.argtypes = [vp, ci, ci, ci, ci, ctypes.POINTER(ctypes.c_float)]
     L.wgk_kernel_launches.argtypes = [vp]
     L.wgk_kernel_launches.restype = ctypes.c_int64
     _lib = L
@@ -256,6 +257,16 @@ class Model:
         out = np.empty((ndays, self._nrec), np.float64)
         self._ck(self._L.wgk_get_record(self._c, member, out.ctypes.data, ndays))
         return out
+
+    def profile_day(self, day, month, dom, slot):
+        """-> dict of phase times in ms for one simulated day run with plain launches"""
+        ms = (ctypes.c_float * 5)()
+        self._ck(self._L.wgk_profile_day(self._c, day, month, dom, slot, ms))
+        return dict(zip(("vertical", "route_local", "route_levels", "route_tail", "day"), [float(x) for x in ms]))
+
+    @property
+    def tail_level0(self):
+        return None
 
     @property
     def kernel_launches(self):

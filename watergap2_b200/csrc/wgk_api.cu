@@ -689,6 +689,43 @@ int wgk_get_record(wgk_ctx *c, int member, double *out, int ndays) {
     return WGK_OK;
 }
 
+int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[5]) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (!ms) return WGK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    rc = set_calendar(c, day, month, dom, slot);
+    if (rc) return rc;
+    cudaEvent_t ev[5];
+    for (auto &e : ev) CU(cudaEventCreate(&e));
+    const WgkParams p = make_params(c);
+    dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
+    CU(cudaEventRecord(ev[0], c->stream));
+    wgk::k_vertical<<<grid, block, 0, c->stream>>>(p);
+    CU(cudaEventRecord(ev[1], c->stream));
+    wgk::k_route_local<<<grid, block, 0, c->stream>>>(p);
+    CU(cudaEventRecord(ev[2], c->stream));
+    int n = 3;
+    for (int l = 0; l < c->tail_level0; l++) {
+        const int cnt = c->level_off[l + 1] - c->level_off[l];
+        dim3 g((cnt + 127) / 128, c->nmember);
+        wgk::k_route_level<<<g, block, 0, c->stream>>>(p, l);
+        n++;
+    }
+    CU(cudaEventRecord(ev[3], c->stream));
+    if (c->tail_level0 < c->nlevels) {
+        wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, c->tail_level0);
+        n++;
+    }
+    CU(cudaEventRecord(ev[4], c->stream));
+    c->launches += n;
+    CU(cudaEventSynchronize(ev[4]));
+    for (int k = 0; k < 4; k++) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
+    CU(cudaEventElapsedTime(&ms[4], ev[0], ev[4]));
+    for (auto &e : ev) cudaEventDestroy(e);
+    return WGK_OK;
+}
+
 int64_t wgk_kernel_launches(const wgk_ctx *c) { return c ? c->launches : 0; }
 
 }  // extern "C"
