@@ -68,8 +68,8 @@ def main():
                     print(f"  day {sd} {name}: {nb} integer mismatches")
                     nbad += nb
                 continue
-            floor = 1e-12
-            d = rel_diff(x, y, floor)
+            from tests.util import floor_of
+            d = rel_diff(x, y, floor_of(name))
             nb = int((d > a.tol).sum())
             k = int(np.argmax(d))
             if d[k] > worst.get(name, (0,))[0]:
