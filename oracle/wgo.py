@@ -27,10 +27,8 @@ def build(force=False):
 _lib = None
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        _lib = ctypes.CDLL(build())
+def _bind(_lib):
+    if True:
         _lib.wgo_create.restype = ctypes.c_void_p
         _lib.wgo_create.argtypes = [ctypes.c_int]
         _lib.wgo_destroy.argtypes = [ctypes.c_void_p]
@@ -49,17 +47,26 @@ def lib():
     return _lib
 
 
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _bind(ctypes.CDLL(build()))
+    return _lib
+
+
 class Oracle:
     """Owns a wgo_ctx; fields are exposed as numpy views of the C arrays (zero copy)."""
 
-    def __init__(self, ncell):
+    def __init__(self, ncell, lib_path=None):
+        """lib_path: alternative build of wg_oracle.c (e.g. with FMA contraction) for sensitivity studies"""
         self.ncell = ncell
-        self._c = lib().wgo_create(ncell)
+        self._L = lib() if lib_path is None else _bind(ctypes.CDLL(lib_path))
+        self._c = self._L.wgo_create(ncell)
         self._views = {}
 
     def close(self):
         if self._c:
-            lib().wgo_destroy(self._c)
+            self._L.wgo_destroy(self._c)
             self._c = None
             self._views = {}
 
@@ -74,7 +81,7 @@ class Oracle:
             return self._views[name]
         dt = ctypes.c_char_p()
         cnt = ctypes.c_int64()
-        p = lib().wgo_field(self._c, name.encode(), ctypes.byref(dt), ctypes.byref(cnt))
+        p = self._L.wgo_field(self._c, name.encode(), ctypes.byref(dt), ctypes.byref(cnt))
         if not p:
             raise KeyError(name)
         npdt = DT[dt.value.decode()]
@@ -112,13 +119,13 @@ class Oracle:
         self.set("lw31", f["LW"])
 
     def vertical_day(self, day, month, dom):
-        lib().wgo_vertical_day(self._c, day, month, dom)
+        self._L.wgo_vertical_day(self._c, day, month, dom)
 
     def routing_day(self, day, month, dom):
-        lib().wgo_routing_day(self._c, day, month, dom)
+        self._L.wgo_routing_day(self._c, day, month, dom)
 
     def update_land_area_frac(self):
-        lib().wgo_update_land_area_frac(self._c)
+        self._L.wgo_update_land_area_frac(self._c)
 
     def step_day(self, day, month, dom):
         self.vertical_day(day, month, dom)
@@ -126,7 +133,7 @@ class Oracle:
         self.update_land_area_frac()
 
     def total_storage_km3(self):
-        return lib().wgo_total_storage_km3(self._c)
+        return self._L.wgo_total_storage_km3(self._c)
 
 
 def read_dump(path, days=None, names=None):

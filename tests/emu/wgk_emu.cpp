@@ -1,0 +1,128 @@
+// wgk_emu.cpp — TEST INFRASTRUCTURE: runs the CUDA kernel source of the product on the host
+// (see cuda_shim.h).  Device-order bookkeeping is re-derived here independently of
+// wgk_api.cu; only the kernel header is shared with the product.
+#include "cuda_shim.h"
+#define cuda_runtime_h_skip
+namespace wgk { constexpr int NBAND = 101; }
+#define WGK_NBAND_K wgk::NBAND
+#define WGK_EMU 1
+#include "../../watergap2_b200/csrc/wgk_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+struct Field { const char *name; const char *dtype; int scope, bands, elsize; size_t offset; };
+static const Field kFields[] = {
+#define X(name, ctype, dt, scope, bands) {#name, dt, WGK_SCOPE_##scope, bands, (int)sizeof(ctype), offsetof(WgkArrays, name)},
+    WGK_FIELDS(X)
+#undef X
+};
+
+struct Emu {
+    int ncell, stride, nlevels;
+    WgkParams p{};
+    std::vector<int32_t> rank_of_cell, cell_of_rank, up_off, up_idx, down, level_off, member_pset;
+    std::vector<float4> forcing;
+    int32_t cal[8] = {0};
+};
+
+template <class K, class... A> static void launch(K kern, dim3 grid, dim3 block, A... args) {
+    gridDim = grid; blockDim = block;
+    for (unsigned by = 0; by < grid.y; by++)
+        for (unsigned bx = 0; bx < grid.x; bx++)
+            for (unsigned tx = 0; tx < block.x; tx++) { blockIdx = dim3(bx, by); threadIdx = dim3(tx); kern(args...); }
+}
+
+extern "C" {
+
+Emu *emu_create(int ncell, const int32_t *rout_order, const int32_t *downstream) {
+    Emu *e = new Emu();
+    e->ncell = ncell;
+    e->stride = (ncell + 31) / 32 * 32;
+    for (const Field &f : kFields) {
+        size_t n = f.scope == WGK_SCOPE_TABLE ? 18 : (size_t)e->stride * f.bands;
+        *(void **)((char *)&e->p.a + f.offset) = calloc(n, f.elsize);
+    }
+    e->rank_of_cell.assign(ncell, 0); e->cell_of_rank.assign(ncell, 0);
+    for (int n = 0; n < ncell; n++) { e->rank_of_cell[n] = rout_order[n] - 1; e->cell_of_rank[rout_order[n] - 1] = n; }
+    e->down.assign(ncell, -1);
+    std::vector<int> nup(ncell, 0), lvl(ncell, 0);
+    for (int n = 0; n < ncell; n++) if (downstream[n] > 0) { int rd = e->rank_of_cell[downstream[n] - 1]; e->down[e->rank_of_cell[n]] = rd; nup[rd]++; }
+    e->up_off.assign(ncell + 1, 0);
+    for (int r = 0; r < ncell; r++) e->up_off[r + 1] = e->up_off[r] + nup[r];
+    e->up_idx.assign(std::max(1, e->up_off[ncell]), 0);
+    std::vector<int> fill(ncell, 0);
+    for (int r = 0; r < ncell; r++) if (e->down[r] >= 0) e->up_idx[e->up_off[e->down[r]] + fill[e->down[r]]++] = r;
+    for (int r = 0; r < ncell; r++) if (e->down[r] >= 0) lvl[e->down[r]] = std::max(lvl[e->down[r]], lvl[r] + 1);
+    e->nlevels = lvl[ncell - 1] + 1;
+    e->level_off.assign(e->nlevels + 1, 0);
+    for (int r = 0; r < ncell; r++) e->level_off[lvl[r] + 1]++;
+    for (int l = 0; l < e->nlevels; l++) e->level_off[l + 1] += e->level_off[l];
+    e->member_pset.assign(1, 0);
+    e->forcing.assign((size_t)31 * e->stride, float4{0, 0, 0, 0});
+    WgkParams &p = e->p;
+    p.member_pset = e->member_pset.data(); p.forcing = e->forcing.data(); p.up_off = e->up_off.data();
+    p.up_idx = e->up_idx.data(); p.down = e->down.data(); p.level_off = e->level_off.data(); p.cal = e->cal;
+    p.record = nullptr; p.record_cells = nullptr; p.nrec = 0; p.record_max_days = 0;
+    p.ncell = ncell; p.stride = e->stride; p.nmember = 1; p.npset = 1; p.forcing_nslots = 31; p.forcing_per_member = 0;
+    p.restart = 0; p.nlevels = e->nlevels;
+    return e;
+}
+
+static const Field *find(const char *name) {
+    for (const Field &f : kFields) if (!strcmp(f.name, name)) return &f;
+    return nullptr;
+}
+
+int emu_set(Emu *e, const char *name, const void *host) {
+    const Field *f = find(name);
+    if (!f) return -1;
+    char *dst = *(char **)((char *)&e->p.a + f->offset);
+    if (f->scope == WGK_SCOPE_TABLE) { memcpy(dst, host, (size_t)18 * f->elsize); return 0; }
+    for (int r = 0; r < e->ncell; r++)
+        for (int b = 0; b < f->bands; b++)
+            memcpy(dst + ((size_t)b * e->stride + r) * f->elsize, (const char *)host + ((size_t)e->cell_of_rank[r] * f->bands + b) * f->elsize, f->elsize);
+    return 0;
+}
+
+int emu_get(Emu *e, const char *name, void *host) {
+    const Field *f = find(name);
+    if (!f) return -1;
+    const char *src = *(char **)((char *)&e->p.a + f->offset);
+    if (f->scope == WGK_SCOPE_TABLE) { memcpy(host, src, (size_t)18 * f->elsize); return 0; }
+    for (int r = 0; r < e->ncell; r++)
+        for (int b = 0; b < f->bands; b++)
+            memcpy((char *)host + ((size_t)e->cell_of_rank[r] * f->bands + b) * f->elsize, src + ((size_t)b * e->stride + r) * f->elsize, f->elsize);
+    return 0;
+}
+
+void emu_set_forcing(Emu *e, const float *P, const float *T, const float *SW, const float *LW) {
+    for (int d = 0; d < 31; d++)
+        for (int r = 0; r < e->ncell; r++) {
+            size_t s = (size_t)e->cell_of_rank[r] * 31 + d;
+            e->forcing[(size_t)d * e->stride + r] = float4{P[s], T[s], SW[s], LW[s]};
+        }
+}
+
+// tail_level0 < 0: every level through k_route_level; else levels >= tail_level0 through k_route_tail
+void emu_day(Emu *e, int day, int month, int dom, int slot, int tail_level0) {
+    e->cal[0] = day; e->cal[1] = month; e->cal[2] = dom; e->cal[3] = slot;
+    const WgkParams &p = e->p;
+    dim3 block(128), grid((e->ncell + 127) / 128, 1);
+    launch(wgk::k_vertical, grid, block, p);
+    launch(wgk::k_route_local, grid, block, p);
+    int t0 = tail_level0 < 0 ? e->nlevels : tail_level0;
+    for (int l = 0; l < t0; l++) {
+        int cnt = e->level_off[l + 1] - e->level_off[l];
+        launch(wgk::k_route_level, dim3((cnt + 127) / 128, 1), block, p, l);
+    }
+    // a CTA whose threads run one after the other is only equivalent to the real one between
+    // barriers: emulate k_route_tail level by level
+    for (int l = t0; l < e->nlevels; l++)
+        for (int r = e->level_off[l]; r < e->level_off[l + 1]; r++) wgk::route_cell(p, r, 0, day, month);
+}
+
+int emu_nlevels(Emu *e) { return e->nlevels; }
+}

@@ -101,6 +101,64 @@ def test_gpu_vs_oracle_3000_cells(world3000):
     assert abs(a - b) <= 1e-12 * abs(a)
 
 
+def _resync_run(world, ndays, check_every=1):
+    """one-step parity: every day both sides start from the ORACLE's state (bit-identical to the
+    reference's), take one step and are compared.  This checks the kernels on every regime of
+    the simulated period without the chaotic error growth of a free run (two CPU
+    builds of the same source, strict vs FMA-contracted, already differ by 4e-8 after one day
+    and by O(1) in ~5 % of the cells after a year)."""
+    from oracle import synth_world as sw, wg_init, wgo
+    import watergap2_b200 as wg
+    ini = wg_init.derive(world)
+    topo = ini["_topology"]
+    o = wgo.Oracle(world.ng)
+    for k, v in ini.items():
+        if not k.startswith("_") and o.has(k):
+            o.set(k, v)
+    m = wg.Model(world.ng)
+    m.set_topology(topo["rout_order"], topo["outflow_cell"])
+    m.load(ini)
+    m.forcing_reserve(31)
+    worst = 0.0
+    from tests.util import rel_err
+    for sd in range(1, ndays + 1):
+        doy, mon, dom = wgo.calendar(sd)
+        if dom == 1:
+            f = sw.forcing_month(world, 1901, mon + 1)
+            o.set_forcing_month(f)
+            m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+        if sd > 1:
+            for name in wg_init.STATE_FIELDS + ["storage_transfer"]:
+                m.set(name, o.field(name))
+        o.step_day(doy, mon, dom)
+        m.step_days(doy, mon, dom, dom - 1, 1)
+        if sd % check_every == 0 or sd == ndays:
+            for name in wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS:
+                ref, got = o.field(name), m.get(name)
+                assert_parity(name, ref, got)
+                if ref.dtype.kind == "f":
+                    worst = max(worst, float(rel_err(name, ref, got).max()))
+    return worst
+
+
+def test_one_step_parity_every_day_of_a_year(world3000):
+    worst = _resync_run(world3000, 365)
+    assert worst < 1e-10
+
+
+def test_one_step_parity_full_size_120_days():
+    from oracle import synth_world as sw
+    worst = _resync_run(sw.build_world(67420), 120, check_every=3)
+    assert worst < 1e-10
+
+
+def test_free_run_full_size_20_days():
+    """free-running (no re-synchronisation) parity on the BASELINE-size grid"""
+    from oracle import synth_world as sw, wg_init
+    oracles, m = _run_pair(sw.build_world(67420), 20, block=10)
+    _compare(oracles, m, wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS)
+
+
 def test_members_and_parameter_sets(world3000):
     """two members with different per-cell parameter sets advance independently and each
     matches its own oracle run (calibration sweep layout, BASELINE config 3)."""

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-10)
     ap.add_argument("--check-every", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--stop-first", action="store_true", help="stop at the first day out of tolerance and dump the worst cell")
+    ap.add_argument("--tail-threshold", type=int, default=0)
     a = ap.parse_args()
     w = sw.build_world(a.ng)
     init = wg_init.derive(w)
@@ -37,7 +39,7 @@ def main():
     for k, v in init.items():
         if not k.startswith("_") and o.has(k):
             o.set(k, v)
-    m = wg.Model(a.ng, use_graph=0 if a.no_graph else 1)
+    m = wg.Model(a.ng, use_graph=0 if a.no_graph else 1, tail_threshold=a.tail_threshold)
     m.set_topology(topo["rout_order"], topo["outflow_cell"])
     print("levels", m.nlevels, "fields loaded", m.load(init))
     m.forcing_reserve(31)
@@ -77,6 +79,30 @@ def main():
             nbad += nb
             if nb:
                 print(f"  day {sd} {name}: {nb} cells > {a.tol:g}; worst cell {k}: oracle {x[k]!r} gpu {y[k]!r}")
+        if nbad and a.stop_first:
+            first = None
+            for name in COMPARE:
+                x = o.field(name); y = m.get(name)
+                if x.dtype.kind == "f":
+                    from tests.util import floor_of
+                    d = rel_diff(x, y, floor_of(name))
+                    if (d > a.tol).any():
+                        first = (name, int(np.argmax(d)))
+                        break
+            name, k = first
+            cell = k // 101 if name == "snow_bands" else k
+            print(f"FIRST OFFENDER day {sd}: field {name} index {k} -> cell {cell}; level {m.levels()[cell]}")
+            for nm in COMPARE + ["t_inflow_local", "t_runoff_to_river", "t_gw_to_river"]:
+                if nm == "snow_bands":
+                    continue
+                y = m.get(nm)
+                x = o.field(nm) if o.has(nm) else None
+                print(f"   {nm:24s} oracle {x[cell] if x is not None else None!r:>26} gpu {y[cell]!r}")
+            for nm in ["arid", "ldd", "landcover", "loc_lake", "loc_wetland", "glo_wetland", "lake_area", "reservoir_area", "contfreq", "smax", "downstream_cell"]:
+                print(f"   static {nm:18s} {np.asarray(init[nm]).ravel()[cell]!r}")
+            up = np.nonzero(np.asarray(init["downstream_cell"]) == cell + 1)[0]
+            print("   upstream cells", up.tolist(), "discharge oracle", o.field("discharge")[up].tolist(), "gpu", m.get("discharge")[up].tolist())
+            break
         ts_o, ts_g = o.total_storage_km3(), m.total_storage_km3()
         print(f"day {sd}: cells out of tolerance {nbad}; total storage oracle {ts_o:.9e} gpu {ts_g:.9e} rel {abs(ts_o-ts_g)/abs(ts_o):.2e}")
     print("worst relative differences:")

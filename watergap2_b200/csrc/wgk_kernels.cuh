@@ -21,7 +21,9 @@
 // compared at 1e-10 relative.  Expression shapes follow the reference line by line.
 #pragma once
 #include <cstdint>
+#ifndef WGK_EMU  // tests/emu compiles this header for the host to check the kernel logic
 #include <cuda_runtime.h>
+#endif
 #include "wgk_fields.h"
 
 struct WgkParams {
