@@ -160,7 +160,7 @@ def run_wgk(args):
     value = cell_days / (ms_max / 1e3)
 
     # ---- per-kernel roofline (CUDA events between the phases, plain launches) ------------------
-    prof = {"vertical": 0.0, "route_local": 0.0, "route_levels": 0.0, "route_tail": 0.0, "day": 0.0}
+    prof = {"vertical": 0.0, "route_local": 0.0, "route_levels": 0.0, "route_tail": 0.0, "route_post": 0.0, "day": 0.0}
     nprof = 20
     for d in range(nprof):
         p = m.profile_day(1 + d, 0, 1 + d, d)
@@ -169,7 +169,7 @@ def run_wgk(args):
     peak, peak_src = measured_peaks()
     bytes_v = BYTES_VERTICAL * w.ng * args.members
     ach_v = bytes_v / (prof["vertical"] * 1e-3) / 1e9
-    t_rout = prof["route_local"] + prof["route_levels"] + prof["route_tail"]
+    t_rout = prof["route_local"] + prof["route_levels"] + prof["route_tail"] + prof["route_post"]
     ach_r = BYTES_ROUTING * w.ng * args.members / (t_rout * 1e-3) / 1e9
     dominant = "k_vertical" if prof["vertical"] >= t_rout else "routing sweep (k_route_local + k_route_level x L + k_route_tail)"
     roofline = {"bound": "hbm", "kernel": "k_vertical", "achieved": round(ach_v, 1), "peak": peak, "unit": "GB/s",

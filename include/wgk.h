@@ -137,9 +137,10 @@ int wgk_record_cells(wgk_ctx *ctx, const int32_t *cells, int ncells, int max_day
 int wgk_get_record(wgk_ctx *ctx, int member, double *out, int ndays);
 /* one simulated day with plain launches and CUDA events between the phases, on the context's
  * stream: ms[0] vertical, ms[1] routing pre-pass (cell-parallel), ms[2] wide routing levels
- * (one launch each), ms[3] narrow-level tail (one persistent CTA per member), ms[4] whole day.
+ * (one launch each), ms[3] narrow-level tail (one persistent CTA per member), ms[4] routing
+ * post-pass (cell-parallel), ms[5] whole day.
  * Advances the model state by that day. Used by bench.py for the per-kernel roofline. */
-int wgk_profile_day(wgk_ctx *ctx, int day, int month, int day_in_month, int slot, float ms[5]);
+int wgk_profile_day(wgk_ctx *ctx, int day, int month, int day_in_month, int slot, float ms[6]);
 /* number of kernels this context has launched (graph nodes counted per replay) */
 int64_t wgk_kernel_launches(const wgk_ctx *ctx);
 

@@ -11,6 +11,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __grid_constant__
 #define __launch_bounds__(...)
 #define __restrict__
@@ -22,4 +23,4 @@ static thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline void __syncthreads() {}
-using std::exp; using std::pow; using std::sqrt; using std::fabs;
+using std::exp; using std::pow; using std::sqrt; using std::fabs; using std::log; using std::cbrt; using std::fma;

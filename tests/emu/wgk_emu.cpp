@@ -111,6 +111,7 @@ void emu_day(Emu *e, int day, int month, int dom, int slot, int tail_level0) {
     e->cal[0] = day; e->cal[1] = month; e->cal[2] = dom; e->cal[3] = slot;
     const WgkParams &p = e->p;
     dim3 block(128), grid((e->ncell + 127) / 128, 1);
+    launch(wgk::k_derive_static, grid, block, p);
     launch(wgk::k_vertical, grid, block, p);
     launch(wgk::k_route_local, grid, block, p);
     int t0 = tail_level0 < 0 ? e->nlevels : tail_level0;
@@ -121,7 +122,11 @@ void emu_day(Emu *e, int day, int month, int dom, int slot, int tail_level0) {
     // a CTA whose threads run one after the other is only equivalent to the real one between
     // barriers: emulate k_route_tail level by level
     for (int l = t0; l < e->nlevels; l++)
-        for (int r = e->level_off[l]; r < e->level_off[l + 1]; r++) wgk::route_cell(p, r, 0, day, month);
+        for (int r = e->level_off[l]; r < e->level_off[l + 1]; r++) {
+            const wgk::RiverCtx c = wgk::load_ctx(p, r, (size_t)r, (size_t)r);
+            if (c.flags & wgk::FL_ACTIVE) wgk::route_river(p, c, r, 0, (size_t)r, (size_t)r, wgk::gather_upstream(p, c, 0), day, month);
+        }
+    launch(wgk::k_route_post, grid, block, p);
 }
 
 int emu_nlevels(Emu *e) { return e->nlevels; }

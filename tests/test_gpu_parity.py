@@ -94,7 +94,7 @@ def _compare(oracles, m, names):
 
 def test_gpu_vs_oracle_3000_cells(world3000):
     from oracle import wg_init
-    oracles, m = _run_pair(world3000, 45, block=7)
+    oracles, m = _run_pair(world3000, 30, block=7)
     _compare(oracles, m, wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS)
     # daily global mass balance: total storage equal to the oracle's (BASELINE.md parity gates)
     a, b = oracles[0].total_storage_km3(), m.total_storage_km3()

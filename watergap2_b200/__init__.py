@@ -260,13 +260,9 @@ class Model:
 
     def profile_day(self, day, month, dom, slot):
         """-> dict of phase times in ms for one simulated day run with plain launches"""
-        ms = (ctypes.c_float * 5)()
+        ms = (ctypes.c_float * 6)()
         self._ck(self._L.wgk_profile_day(self._c, day, month, dom, slot, ms))
-        return dict(zip(("vertical", "route_local", "route_levels", "route_tail", "day"), [float(x) for x in ms]))
-
-    @property
-    def tail_level0(self):
-        return None
+        return dict(zip(("vertical", "route_local", "route_levels", "route_tail", "route_post", "day"), [float(x) for x in ms]))
 
     @property
     def kernel_launches(self):

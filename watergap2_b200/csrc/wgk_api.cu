@@ -90,6 +90,7 @@ struct wgk_ctx {
     bool graph_dirty = true;
     int launches_per_day = 0;
     int64_t launches = 0;
+    bool derived_dirty = true;  // s_c1 / s_slope_pow / s_flags need (re)computation
 };
 
 namespace {
@@ -183,7 +184,20 @@ int enqueue_routing(wgk_ctx *c, const WgkParams &p) {
         wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, c->tail_level0);
         n++;
     }
+    wgk::k_route_post<<<grid, block, 0, c->stream>>>(p);
+    n++;
     return n;
+}
+
+// inflow-independent river constants and cell class flags, recomputed after any static or
+// parameter upload (never inside a graph capture)
+int ensure_derived(wgk_ctx *c) {
+    if (!c->derived_dirty) return 0;
+    dim3 block(128), grid((c->ncell + 127) / 128, c->npset);
+    wgk::k_derive_static<<<grid, block, 0, c->stream>>>(make_params(c));
+    c->launches++;
+    c->derived_dirty = false;
+    return 0;
 }
 
 void drop_graph(wgk_ctx *c) {
@@ -422,6 +436,7 @@ static int set_field_raw(wgk_ctx *c, int f, int index, const void *host, size_t 
     }
     CU(cudaMemcpyAsync(dst, tmp, row_bytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (fi.scope != WGK_SCOPE_MEMBER) c->derived_dirty = true;
     return WGK_OK;
 }
 
@@ -565,6 +580,7 @@ int wgk_vertical_day(wgk_ctx *c, int day, int month, int dom, int slot) {
     CU(cudaSetDevice(c->device));
     rc = set_calendar(c, day, month, dom, slot);
     if (rc) return rc;
+    ensure_derived(c);
     c->launches += 1 + enqueue_vertical(c, make_params(c));
     CU(cudaGetLastError());
     return WGK_OK;
@@ -580,6 +596,7 @@ int wgk_routing_day(wgk_ctx *c, int day, int month, int dom) {
     CU(cudaMemcpyAsync(&slot, c->d_cal + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     wgk::k_set_calendar<<<1, 1, 0, c->stream>>>(c->d_cal, day, month, dom, slot);
+    ensure_derived(c);
     c->launches += 1 + enqueue_routing(c, make_params(c));
     CU(cudaGetLastError());
     return WGK_OK;
@@ -602,6 +619,7 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
     if (rc) return rc;
     CU(cudaMemsetAsync(c->d_cal + 4, 0, sizeof(int32_t), c->stream));
     c->launches++;
+    ensure_derived(c);
     const WgkParams p = make_params(c);
     if (c->opt.use_graph) {
         if (c->graph_dirty) {
@@ -689,14 +707,15 @@ int wgk_get_record(wgk_ctx *c, int member, double *out, int ndays) {
     return WGK_OK;
 }
 
-int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[5]) {
+int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[6]) {
     int rc = check_ready(c);
     if (rc) return rc;
     if (!ms) return WGK_ERR_ARG;
     CU(cudaSetDevice(c->device));
     rc = set_calendar(c, day, month, dom, slot);
     if (rc) return rc;
-    cudaEvent_t ev[5];
+    ensure_derived(c);
+    cudaEvent_t ev[6];
     for (auto &e : ev) CU(cudaEventCreate(&e));
     const WgkParams p = make_params(c);
     dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
@@ -705,7 +724,7 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     CU(cudaEventRecord(ev[1], c->stream));
     wgk::k_route_local<<<grid, block, 0, c->stream>>>(p);
     CU(cudaEventRecord(ev[2], c->stream));
-    int n = 3;
+    int n = 4;
     for (int l = 0; l < c->tail_level0; l++) {
         const int cnt = c->level_off[l + 1] - c->level_off[l];
         dim3 g((cnt + 127) / 128, c->nmember);
@@ -718,10 +737,12 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
         n++;
     }
     CU(cudaEventRecord(ev[4], c->stream));
+    wgk::k_route_post<<<grid, block, 0, c->stream>>>(p);
+    CU(cudaEventRecord(ev[5], c->stream));
     c->launches += n;
-    CU(cudaEventSynchronize(ev[4]));
-    for (int k = 0; k < 4; k++) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
-    CU(cudaEventElapsedTime(&ms[4], ev[0], ev[4]));
+    CU(cudaEventSynchronize(ev[5]));
+    for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
+    CU(cudaEventElapsedTime(&ms[5], ev[0], ev[5]));
     for (auto &e : ev) cudaEventDestroy(e);
     return WGK_OK;
 }

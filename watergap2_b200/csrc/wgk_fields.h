@@ -120,6 +120,12 @@
     X(t_gw_to_river, double, "f64", MEMBER, 1) \
     X(t_gwr_loclak, double, "f64", MEMBER, 1) \
     X(t_gwr_locwet, double, "f64", MEMBER, 1) \
+    X(t_river_precip, double, "f64", MEMBER, 1) \
+    X(t_river_evapo, double, "f64", MEMBER, 1) \
+    /* ---- derived once from the statics (k_derive_static) ---- */ \
+    X(s_c1, double, "f64", PSET, 1) \
+    X(s_slope_pow, double, "f64", PSET, 1) \
+    X(s_flags, int8_t, "i8", CELL, 1) \
     /* ---- land cover tables (LCT_22.DAT / LAI_22.DAT; daily.h:204-208, lai.h) ---- */ \
     X(lai_factor_a, float, "f32", TABLE, 1) \
     X(lai_factor_b, float, "f32", TABLE, 1) \

@@ -7,13 +7,15 @@
 //   k_route_local   : cell-parallel part of routingClass::routing that does not depend on
 //                     upstream cells: runoff split, groundwater of humid cells and inland
 //                     sinks, local lake, local wetland                   (routing.cpp:1878-2617)
-//   k_route_level   : one dependency level of the ordered cell loop: upstream-inflow gather,
-//                     global lake, reservoir, global wetland, arid groundwater, river,
-//                     fused with the per-cell surface-water-fraction / land-area-fraction
-//                     pass and updateLandAreaFrac                         (routing.cpp:2623-3586,
-//                                                                          5034-5188, 5343-5352)
+//   k_route_level   : one dependency level of the ordered cell loop, reduced to what depends
+//                     on upstream cells: inflow gather, global lake / reservoir / global
+//                     wetland / arid groundwater where present, river reach  (routing.cpp:2623-3545)
 //   k_route_tail    : the same for all remaining narrow levels inside ONE persistent CTA per
-//                     member, levels separated by __syncthreads() instead of kernel launches
+//                     member, levels separated by __syncthreads() instead of kernel launches,
+//                     next level's inputs prefetched before the barrier
+//   k_route_post    : cell-parallel: river width / area fraction, surface-water-body fractions,
+//                     next-day land area fraction, updateLandAreaFrac   (routing.cpp:3546-3586,
+//                                                                          5034-5188, 5343-5352)
 //   k_forcing_pack  : [cell][31] float grids -> [slot][cell] float4 in routing order
 //   k_advance_day   : calendar on the device (so that one captured graph replays day after day)
 //
@@ -199,7 +201,8 @@ __global__ void __launch_bounds__(128) k_vertical(const __grid_constant__ WgkPar
     const double emissivity = a.lct_emissivity[lc];
     const double temp_K = dailyTempC + 273.2;
     const double stefan_boltz_const = 0.000000004903;
-    const double long_wave_rad_out = emissivity * stefan_boltz_const * pow(temp_K, 4.) / lat_heat;
+    const double temp_K2 = temp_K * temp_K;  // pow(temp_K, 4.) (:423) as two squarings (<= 1 ulp apart)
+    const double long_wave_rad_out = emissivity * stefan_boltz_const * (temp_K2 * temp_K2) / lat_heat;
     const double net_long_wave_rad = long_wave_rad_in - long_wave_rad_out;
     const double net_short_wave_rad = solar_rad * (1. - albedo);
     const double net_rad = a.p_netrad[q] * (net_short_wave_rad + net_long_wave_rad);
@@ -279,63 +282,63 @@ __global__ void __launch_bounds__(128) k_vertical(const __grid_constant__ WgkPar
     if (dailySoilPET < 0.) dailySoilPET = 0.0;
 
     // snow in 100 elevation bands (:913-1062); band-major arrays: band e of this cell is
-    // S[e*stride], coalesced over the warp
+    // S[e*stride], coalesced over the warp.  The loop body is branch-free (selects), because the
+    // cells of one warp sit in different regimes (accumulating / melting / bare) on any given day.
     double TempElevMax = 0., snowStorageChange = 0., snow = 0.;
-    int thresh_elev = 0;
-    double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r;
+    double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r + p.stride;
     const int16_t *__restrict__ E = a.elevation + r;
     const int elev0 = E[0];
+    E += p.stride;
     const double ddf = M_DEGDAY_F * a.lct_ddf[lc];  // (M_DEGDAY_F * ddf_lct) * (...) keeps the reference association
     if (noland) {
 #pragma unroll 4
         for (int e = 1; e < 101; e++) {
-            storage_transfer += S[(size_t)e * p.stride] / 100.;
-            S[(size_t)e * p.stride] = 0.;
+            storage_transfer += *S / 100.;
+            *S = 0.;
+            S += p.stride;
         }
         snow = 0.;
     } else {
-        const double scale_num = lafPrev;
+        // S * lafPrev / landAreaFrac (:947): the quotient is formed with one correctly rounded
+        // reciprocal and a fused residual correction (Markstein), 4 instructions instead of a
+        // ~25-instruction division per band; the result is the correctly rounded quotient
+        const double inv_laf = 1. / landAreaFrac;
+        int thresh_elev = 0;
 #pragma unroll 4
         for (int e = 1; e < 101; e++) {
-            const int elev_e = E[(size_t)e * p.stride];
-            double s = S[(size_t)e * p.stride];
+            const int elev_e = *E;
+            const double sraw = *S;
             double temp_elev = dailyTempC - ((elev_e - elev0) * P_T_GRADNT);
-            double snowmelt_elev = 0., effBefore = 0.;
-            s = s * scale_num / landAreaFrac;
+            const double num = sraw * lafPrev;
+            double s = num * inv_laf;
+            s = fma(fma(-landAreaFrac, s, num), inv_laf, s);
             if (fabs(s) <= MIN_STOR_VOL) s = 0.;
             const double s0 = s;
-            if (s > 1000.) {  // :958-976
+            if (s > 1000.) {  // :958-976 (rare)
                 if (thresh_elev == 0) thresh_elev = elev_e;
                 else if (thresh_elev > 0) temp_elev = dailyTempC - ((thresh_elev - elev0) * P_T_GRADNT);
             }
-            if (temp_elev <= P_T_SNOWFZ) {
-                s += daily_prec_to_soil;
-                if (s > dailySoilPET) {
-                    s -= dailySoilPET;
-                    dailySnowEvapo += dailySoilPET;
-                } else {
-                    dailySnowEvapo += s;
-                    s = 0.;
-                }
-            } else {
-                effBefore = daily_prec_to_soil;
-            }
-            if (temp_elev > P_T_SNOWMT) {
-                if (!(s < 0.)) {
-                    snowmelt_elev = ddf * (temp_elev - P_T_SNOWMT);
-                    if (snowmelt_elev > s) {
-                        snowmelt_elev = s;
-                        s = 0.;
-                    } else {
-                        s -= snowmelt_elev;
-                    }
-                }
-            }
+            const bool frz = (temp_elev <= P_T_SNOWFZ);
+            // accumulation and sublimation (:982-999)
+            s = s + (frz ? daily_prec_to_soil : 0.);
+            const bool more = (s > dailySoilPET);
+            const double sub = frz ? (more ? dailySoilPET : s) : 0.;
+            dailySnowEvapo += sub;
+            s = frz ? (more ? s - dailySoilPET : 0.) : s;
+            const double effBefore = frz ? 0. : daily_prec_to_soil;
+            // melt (:1003-1019)
+            const bool mlt = (temp_elev > P_T_SNOWMT) && !(s < 0.);
+            const double m_raw = ddf * (temp_elev - P_T_SNOWMT);
+            const bool all = (m_raw > s);
+            const double snowmelt_elev = mlt ? (all ? s : m_raw) : 0.;
+            s = mlt ? (all ? 0. : s - m_raw) : s;
             snowStorageChange += s - s0;
             if (e == 1) TempElevMax = temp_elev;
             snow += s;
             dailyEffPrec += effBefore + snowmelt_elev;
-            S[(size_t)e * p.stride] = s;
+            *S = s;
+            S += p.stride;
+            E += p.stride;
         }
         snow /= 100.;
         dailyEffPrec /= 100.;
@@ -462,28 +465,40 @@ __device__ __forceinline__ double gw_step(double &Sg, double netGWin, double k) 
     return qq;
 }
 
-// routingClass::getRiverVelocity (routing.cpp:7274-7307)
-__device__ __forceinline__ double river_velocity(double slope_pow, double bottomWidth, double Roughness,
-                                                 double riverInflow, double M_RIVRGH_C) {
-    const double incoming_discharge = (riverInflow * 1000. * 1000. * 1000.) / (60. * 60. * 24.);
-    const double riverDepth = 0.349 * pow(incoming_discharge, 0.341);
-    const double crossSectionalArea = riverDepth * (2.0 * riverDepth + bottomWidth);
-    const double wettedPerimeter = bottomWidth + 2.0 * riverDepth * sqrt(5.0);
-    const double hydraulicRad = crossSectionalArea / wettedPerimeter;
-    double v = 1. / (M_RIVRGH_C * Roughness) * pow(hydraulicRad, (2. / 3.)) * slope_pow;
-    v = v * 86.4;
-    if (v < 0.00001) return 0.00001;
-    return v;
-}
-
 __device__ __forceinline__ double clamp01(double x) {
     if (x < 0.) x = 0.;
     if (x > 1.) x = 1.;
     return x;
 }
 
+// cell class bits (s_flags, derived once from the statics by k_derive_static)
+constexpr int FL_ACTIVE = 1, FL_LDD_OUT = 2, FL_ARIDC = 4, FL_LAKE = 8, FL_RES = 16, FL_GLOWET = 32;
+
+// one-time derivation of inflow-independent river constants (routing.cpp:7293-7296):
+//   s_c1 = 1 / (M_RIVRGH_C * roughness),  s_slope_pow = pow(slope, 0.5),  s_flags
+__global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ WgkParams p) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ps = blockIdx.y;
+    if (r >= p.ncell) return;
+    const WgkArrays &a = p.a;
+    const size_t q = (size_t)ps * p.stride + r;
+    a.s_c1[q] = 1. / (a.p_rivrgh[q] * a.roughness[r]);
+    a.s_slope_pow[q] = pow(a.river_slope[r], 0.5);
+    if (ps == 0) {
+        int f = 0;
+        const int ldd = a.ldd[r];
+        if (a.contcell[r] && (0 != a.toBeCalculated[r])) f |= FL_ACTIVE;
+        if (ldd >= 0) f |= FL_LDD_OUT;
+        if ((1 == a.arid[r]) && (ldd >= 0)) f |= FL_ARIDC;
+        if (a.lake_area[r] > 0.) f |= FL_LAKE;
+        if (a.reservoir_area[r] > 0.) f |= FL_RES;
+        if (a.glo_wetland[r] > 0) f |= FL_GLOWET;
+        a.s_flags[r] = (int8_t)f;
+    }
+}
+
 // ----------------------------------------------------------------------------------------
-// cell-parallel pre-pass of the routing day
+// cell-parallel pre-pass of the routing day: everything that does not depend on upstream cells
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ WgkParams p) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -494,6 +509,7 @@ __global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ Wgk
     a.river_evapo[i] = 0.;  // routing.cpp:1781
     if (!a.contcell[r]) return;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const int flags = a.s_flags[r];
     const double kG = a.p_gwoutf[q];
     const double M_EVAREDEX = a.p_evaredex[q];
     const double cellArea = a.area[r];
@@ -501,8 +517,9 @@ __global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ Wgk
     const double owPrec = a.openwater_prec[i], owPET = a.openwater_pet[i];
     const int ldd = a.ldd[r];
     const int arid = a.arid[r];
-    const bool aridc = (1 == arid) && (ldd >= 0);
+    const bool aridc = (flags & FL_ARIDC) != 0;
     const double laf = a.land_area_frac[i];
+    const double contf = a.contfreq[r];
     double dailyLocalSurfaceRunoff;
     double localRunoff = 0., localRunoffIntoRiver = 0., localGWRunoffIntoRiver = 0., fswb_catchment = 0.;
     double gwr_loclak = 0., gwr_locwet = 0.;
@@ -541,9 +558,8 @@ __global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ Wgk
     }
 
     double inflow = localRunoff;
-    if (0 != a.toBeCalculated[r]) {
+    if (flags & FL_ACTIVE) {
         const double kS = a.p_swoutf[q];
-        const double contf = a.contfreq[r];
         const double loc_lake = a.loc_lake[r];
         if (loc_lake > 0.) {  // local lake, :2318-2490
             const double prev = a.loc_lake_stor[i];
@@ -614,6 +630,20 @@ __global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ Wgk
             a.loc_wetl_stor[i] = S;
             a.red_loc_wetl[i] = clamp01(1. - pow(fabs(S - maxStorage) / (maxStorage), (M_EVAREDEX * 3.32193)));
         }
+        // arid cells without global lake / reservoir / global wetland: the groundwater step below
+        // the surface water bodies (:3305-3386) does not depend on upstream inflow either
+        if (aridc && !(flags & (FL_LAKE | FL_RES | FL_GLOWET))) {
+            const double gwr_swb = gwr_loclak + 0. + gwr_locwet + 0. + 0.;
+            a.gwr_swb[i] = gwr_swb;
+            const double netGWin = gwr_swb * cellArea * (contf / 100.) / 1000000. + a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
+            double Sg = a.gw[i];
+            localGWRunoffIntoRiver = gw_step(Sg, netGWin, kG);
+            a.gw[i] = Sg;
+        }
+        // river evaporation and precipitation on yesterday's river area fraction (:3425-3441)
+        const double raf = a.river_area_frac_next[i];
+        a.t_river_evapo[i] = ((1.0 - cfa) * (owPrec) + (cfa * owPET)) * raf / 100. * cellArea / 1000000.;
+        a.t_river_precip[i] = owPrec * raf / 100. * cellArea / 1000000.;
     }
     a.t_inflow_local[i] = inflow;
     a.t_runoff_to_river[i] = localRunoffIntoRiver;
@@ -623,14 +653,303 @@ __global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ Wgk
 }
 
 // ----------------------------------------------------------------------------------------
-// one cell of the ordered sweep: everything from "inflow += G_riverInflow[n]" on
+// the ordered sweep: only what depends on upstream cells stays on the level-to-level chain
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void route_cell(const WgkParams &p, const int r, const int m, const int day, const int month) {
+// inflow-independent inputs of one cell, loaded before the hand-off of the previous level
+struct RiverCtx {
+    double inflow_local, runoff_to_river, gw_to_river, c1, slope_pow, bw, river_length, prevR, precip, evapo;
+    int up0, up1, flags;
+};
+
+__device__ __forceinline__ RiverCtx load_ctx(const WgkParams &p, const int r, const size_t i, const size_t q) {
     const WgkArrays &a = p.a;
+    RiverCtx c;
+    c.flags = a.s_flags[r];
+    c.up0 = p.up_off[r];
+    c.up1 = p.up_off[r + 1];
+    c.inflow_local = a.t_inflow_local[i];
+    c.runoff_to_river = a.t_runoff_to_river[i];
+    c.gw_to_river = a.t_gw_to_river[i];
+    c.c1 = a.s_c1[q];
+    c.slope_pow = a.s_slope_pow[q];
+    c.bw = a.river_bottom_width[r];
+    c.river_length = a.river_length[r];
+    c.prevR = a.river_stor[i];
+    c.precip = a.t_river_precip[i];
+    c.evapo = a.t_river_evapo[i];
+    return c;
+}
+
+// global lake, reservoir, global wetland and the arid groundwater below them (routing.cpp:2630-3386)
+// for the few cells that have them; returns the inflow handed to the river
+__device__ __noinline__ double route_global_bodies(const WgkParams &p, const int r, const int m, const size_t i, const size_t q,
+                                                   double inflow, const int flags, const int day, const int month,
+                                                   double &gwToRiver) {
+    const WgkArrays &a = p.a;
+    const double M_EVAREDEX = a.p_evaredex[q];
+    const double kS = a.p_swoutf[q];
+    const double cfa = a.cfa[q];
+    const double owPrec = a.openwater_prec[i], owPET = a.openwater_pet[i];
+    const bool aridc = (flags & FL_ARIDC) != 0;
+    const double contf = a.contfreq[r];
+    const double cellArea = a.area[r];
+    const double lake_area = a.lake_area[r];
+    const double reservoir_area = a.reservoir_area[r];
+    const double glo_wetland = a.glo_wetland[r];
+    double gwr_glolak = 0., gwr_res = 0., gwr_glowet = 0.;
+    if (lake_area > 0.) {  // global lake, :2630-2804
+        const double prev = a.glo_lake_stor[i];
+        const double maxStorage = (lake_area)*a.lake_depth_active[q];
+        const double rf = a.red_glo_lake[i];
+        double evapo = ((1.0 - cfa) * owPrec) + (cfa * owPET * rf);
+        if (evapo < 0.) evapo = 0.;
+        const double totalInflow = inflow + (owPrec * (lake_area / 1000000.));
+        if (aridc) gwr_glolak = 10. * rf * (lake_area / (cellArea * (contf / 100.)));
+        const double PETgwrRemUse = evapo * (lake_area / 1000000.) + gwr_glolak * cellArea * (contf / 100.) / 1000000. + 0.;
+        const double PETgwrRemUseMax = totalInflow + maxStorage + prev;
+        double S, outflow;
+        if (PETgwrRemUse > PETgwrRemUseMax) {
+            S = (-1.) * maxStorage;
+            outflow = 0.;
+            gwr_glolak *= PETgwrRemUseMax / PETgwrRemUse;
+        } else {
+            const double ek = exp(-1. * kS);
+            S = prev * ek + (1. / kS) * (totalInflow - PETgwrRemUse) * (1. - ek);
+            outflow = totalInflow + prev - S - PETgwrRemUse;
+            if (S > maxStorage) {
+                outflow += (S - maxStorage);
+                S = maxStorage;
+            }
+            if (outflow < 0.) {
+                outflow = 0.;
+                S = prev + totalInflow - PETgwrRemUse;
+            }
+        }
+        if (fabs(S) <= MIN_STOR_VOL) S = 0.;
+        inflow = outflow;
+        a.glo_lake_stor[i] = S;
+        a.red_glo_lake[i] = clamp01(1. - pow(fabs(S - maxStorage) / (2. * maxStorage), (M_EVAREDEX * 3.32193)));
+    }
+    if (reservoir_area > 0.) {  // reservoir, :2807-3082
+        const double stor_cap = a.stor_cap[r];
+        const double mean_outflow = a.mean_outflow[r];
+        const double c_ratio = stor_cap / (mean_outflow * 31536000. / 1000000000.);
+        const double maxStorage = stor_cap;
+        const double prev = a.res_stor[i];
+        const double rf = a.red_res[i];
+        double evapo = ((1.0 - cfa) * owPrec) + (cfa * (owPET * rf));
+        if (evapo < 0.) evapo = 0.;
+        const double totalInflow = inflow + (owPrec * (reservoir_area / 1000000.));
+        if (aridc) gwr_res = 10. * rf * (reservoir_area / (cellArea * (contf / 100.)));
+        const double PETgwr = evapo * (reservoir_area / 1000000.) + gwr_res * cellArea * (contf / 100.) / 1000000.;
+        const double PETgwrMax = prev + totalInflow;
+        double S;
+        if (PETgwr > PETgwrMax) {
+            S = prev + totalInflow - PETgwrMax;
+            gwr_res *= PETgwrMax / PETgwr;
+        } else {
+            S = prev + totalInflow - PETgwr;
+        }
+        if (fabs(S) <= MIN_STOR_VOL) S = 0.;
+        double Krel = a.k_release[i];
+        const int fdim[12] = {1, 32, 60, 91, 121, 152, 182, 213, 244, 274, 305, 335};
+        if (month == a.start_month[r] - 1 && day == fdim[month]) {  // :2945-2956
+            if (S < (stor_cap * 0.1)) Krel = 0.1;
+            else Krel = S / (maxStorage * 0.85);
+            a.k_release[i] = Krel;
+        }
+        double prov_rel = 0.;
+        const int res_type = a.res_type[r];
+        if (res_type == 1) {  // irrigation reservoir; water use is not simulated: monthlyUse == 0
+            const double monthlyUse = 0.;
+            const double mean_demand = a.mean_demand[r];
+            if (mean_demand >= 0.5 * mean_outflow) prov_rel = mean_outflow / 2. * (1. + monthlyUse / mean_demand);
+            else prov_rel = mean_outflow + monthlyUse - mean_demand;
+        } else if (res_type == 2) {
+            prov_rel = mean_outflow;
+        }
+        double release;
+        if (c_ratio >= 0.5) release = Krel * prov_rel;
+        else
+            release = ((4. * c_ratio * c_ratio) * Krel * prov_rel)
+                      + ((1.0 - ((4. * c_ratio * c_ratio))) * inflow * 1000000000. / (24. * 3600.));
+        double outflow;
+        if (S >= (stor_cap * 0.1)) outflow = release * (24. * 3600.) / 1000000000.;
+        else outflow = 0.1 * release * (24. * 3600.) / 1000000000.;
+        if (outflow < 0.) outflow = 0.;
+        S -= outflow;
+        if (S > maxStorage) {
+            outflow += (S - maxStorage);
+            S = maxStorage;
+        }
+        if (S < 0.) {
+            outflow += S;
+            S = 0.;
+        }
+        inflow = outflow;
+        a.res_stor[i] = S;
+        a.red_res[i] = clamp01(1. - pow(fabs(S - maxStorage) / maxStorage, 2.81383));
+    }
+    if (glo_wetland > 0) {  // global wetland, :3178-3297
+        const double prev = a.glo_wetl_stor[i];
+        const double maxStorage = ((glo_wetland) / 100.) * cellArea * a.wetl_depth_active[q];
+        const double rf = a.red_glo_wetl[i];
+        double evapo = ((1.0 - cfa) * (owPrec * rf)) + (cfa * (owPET * rf));
+        if (evapo < 0.) evapo = 0.;
+        const double totalInflow = inflow + (owPrec * rf * (cellArea / 1000000.) * (glo_wetland / 100.));
+        if (aridc) gwr_glowet = 10. * rf * glo_wetland / 100. / (contf / 100.);
+        const double PETgwr = evapo * (cellArea / 1000000.) * ((glo_wetland) / 100.) + gwr_glowet * cellArea * (contf / 100.) / 1000000.;
+        const double PETgwrMax = totalInflow + prev;
+        double S, outflow;
+        if (PETgwr > PETgwrMax) {
+            S = 0.;
+            outflow = 0.;
+            gwr_glowet *= PETgwrMax / PETgwr;
+        } else {
+            const double ek = exp(-1. * kS);
+            S = prev * ek + (1. / kS) * (totalInflow - PETgwr) * (1. - ek);
+            outflow = totalInflow + prev - S - PETgwr;
+        }
+        if (S > maxStorage) {
+            outflow += (S - maxStorage);
+            S = maxStorage;
+        }
+        if (fabs(S) <= MIN_STOR_VOL) S = 0.;
+        inflow = outflow;
+        a.glo_wetl_stor[i] = S;
+        a.red_glo_wetl[i] = clamp01(1. - pow(fabs(S - maxStorage) / maxStorage, (M_EVAREDEX * 3.32193)));
+    }
+    if (aridc) {  // :3305-3386
+        const double gwr_swb = a.t_gwr_loclak[i] + gwr_glolak + a.t_gwr_locwet[i] + gwr_glowet + gwr_res;
+        a.gwr_swb[i] = gwr_swb;
+        const double laf = a.land_area_frac[i];
+        const double netGWin = gwr_swb * cellArea * (contf / 100.) / 1000000. + a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
+        double Sg = a.gw[i];
+        gwToRiver = gw_step(Sg, netGWin, a.p_gwoutf[q]);
+        a.gw[i] = Sg;
+    }
+    (void)m;
+    return inflow;
+}
+
+// river reach of one cell (routing.cpp:3388-3545), given the inflow-independent context and
+// the sum of upstream discharges; writes discharge / storage and returns nothing
+__device__ __forceinline__ void route_river(const WgkParams &p, const RiverCtx &c, const int r, const int m, const size_t i,
+                                            const size_t q, const double inflowUpstream, const int day, const int month) {
+    const WgkArrays &a = p.a;
+    double inflow = c.inflow_local + inflowUpstream;  // :2623
+    double gwToRiver = c.gw_to_river;
+    if (c.flags & (FL_LAKE | FL_RES | FL_GLOWET)) inflow = route_global_bodies(p, r, m, i, q, inflow, c.flags, day, month, gwToRiver);
+    double riverInflow = inflow;
+    if (c.flags & FL_LDD_OUT) {
+        riverInflow += c.runoff_to_river;
+        riverInflow += gwToRiver;
+    }
+    // routingClass::getRiverVelocity (routing.cpp:7274-7307); pow(x, 2/3) is evaluated as
+    // cbrt(x*x): same value to ~1 ulp with a much shorter dependent chain
+    const double incoming_discharge = (riverInflow * 1000. * 1000. * 1000.) / (60. * 60. * 24.);
+    const double riverDepth = 0.349 * pow(incoming_discharge, 0.341);
+    const double crossSectionalArea = riverDepth * (2.0 * riverDepth + c.bw);
+    const double wettedPerimeter = c.bw + 2.0 * riverDepth * sqrt(5.0);
+    const double hydraulicRad = crossSectionalArea / wettedPerimeter;
+    double v = c.c1 * cbrt(hydraulicRad * hydraulicRad) * c.slope_pow;
+    v = v * 86.4;
+    if (v < 0.00001) v = 0.00001;  // an empty river gives exp(-inf) = 0 -> v = 0 -> floor, as pow(0, y) does
+    const double K = v / c.river_length;
+    const double prevR = c.prevR;
+    double riverEvapo = c.evapo;
+    riverInflow += c.precip;
+    const double RiverEvapoRemUse = 0. + riverEvapo;
+    const double eK = exp(-1. * K);
+    const double RivEvapoRemUseMax = riverInflow + (K * prevR * eK) / (1. - eK);
+    double Sr, transportedVolume;
+    if (RiverEvapoRemUse > RivEvapoRemUseMax) {
+        Sr = 0.;
+        transportedVolume = riverInflow + prevR - RivEvapoRemUseMax;
+        if (transportedVolume < 0.) transportedVolume = 0.;
+        riverEvapo *= RivEvapoRemUseMax / RiverEvapoRemUse;
+    } else {
+        Sr = prevR * eK + (1. / K) * (riverInflow - RiverEvapoRemUse) * (1. - eK);
+        if (fabs(Sr) <= MIN_STOR_VOL) Sr = 0.;
+        transportedVolume = riverInflow + prevR - Sr - RiverEvapoRemUse;
+        if (transportedVolume < 0.) transportedVolume = 0.;
+    }
+    // (inland sinks have no downstream cell; the reference keeps their river outflow out of the
+    //  discharge grid, routing.cpp:4219-4221, and books it as evaporation, :3935-3937)
+    const bool out = (c.flags & FL_LDD_OUT) != 0;
+    a.discharge[i] = out ? transportedVolume : 0.;
+    a.cell_runoff[i] = out ? (transportedVolume - inflowUpstream) : (0. - inflowUpstream);
+    a.river_stor[i] = Sr;
+    a.river_evapo[i] = riverEvapo;
+}
+
+__device__ __forceinline__ double gather_upstream(const WgkParams &p, const RiverCtx &c, const size_t mb) {
+    // upstream inflow in routing order (= order of the += at routing.cpp:3957)
+    double s = 0.;
+    for (int k = c.up0; k < c.up1; k++) s += p.a.discharge[mb + p.up_idx[k]];
+    return s;
+}
+
+// one dependency level per launch (wide levels)
+__global__ void __launch_bounds__(128) k_route_level(const __grid_constant__ WgkParams p, const int level) {
+    const int begin = p.level_off[level], end = p.level_off[level + 1];
+    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= end) return;
+    const int m = blockIdx.y;
     const size_t mb = (size_t)m * p.stride;
-    const size_t i = mb + r;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
-    const bool active = a.contcell[r] && (0 != a.toBeCalculated[r]);
+    const RiverCtx c = load_ctx(p, r, mb + r, q);
+    if (!(c.flags & FL_ACTIVE)) return;
+    route_river(p, c, r, m, mb + r, q, gather_upstream(p, c, mb), p.cal[0], p.cal[1]);
+}
+
+// all levels from `level0` on inside one persistent CTA per member; levels are separated by
+// __syncthreads(), which also orders the global-memory hand-off of the discharge values.  The
+// context of the next level's cell is loaded BEFORE the barrier so that only the gather of the
+// upstream discharges and the river arithmetic remain on the level-to-level critical path.
+__global__ void __launch_bounds__(256) k_route_tail(const __grid_constant__ WgkParams p, const int level0) {
+    const int m = blockIdx.x;
+    const int day = p.cal[0], month = p.cal[1];
+    const size_t mb = (size_t)m * p.stride;
+    const size_t qb = (size_t)p.member_pset[m] * p.stride;
+    int begin = p.level_off[level0], end = p.level_off[level0 + 1];
+    int r = begin + threadIdx.x;
+    RiverCtx c;
+    c.flags = 0;
+    if (r < end) c = load_ctx(p, r, mb + r, qb + r);
+    for (int level = level0; level < p.nlevels; level++) {
+        if (r < end) {
+            if (c.flags & FL_ACTIVE) route_river(p, c, r, m, mb + r, qb + r, gather_upstream(p, c, mb), day, month);
+            // levels wider than the CTA (only possible when the tail threshold is raised)
+            for (int r2 = r + blockDim.x; r2 < end; r2 += blockDim.x) {
+                const RiverCtx c2 = load_ctx(p, r2, mb + r2, qb + r2);
+                if (c2.flags & FL_ACTIVE) route_river(p, c2, r2, m, mb + r2, qb + r2, gather_upstream(p, c2, mb), day, month);
+            }
+        }
+        if (level + 1 < p.nlevels) {
+            begin = end;
+            end = p.level_off[level + 2];
+            r = begin + threadIdx.x;
+            c.flags = 0;
+            if (r < end) c = load_ctx(p, r, mb + r, qb + r);
+        }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// cell-parallel post-pass: river width / area fraction of the next day (:3546-3586), surface
+// water body fractions and next-day land area fraction (:5034-5188), updateLandAreaFrac
+// (:5343-5352)
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkParams p) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (r >= p.ncell) return;
+    const WgkArrays &a = p.a;
+    const size_t i = (size_t)m * p.stride + r;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const int flags = a.s_flags[r];
     const double contf = a.contfreq[r];
     const double cellArea = a.area[r];
     double red_loc_lake = a.red_loc_lake[i], red_loc_wetl = a.red_loc_wetl[i], red_glo_wetl = a.red_glo_wetl[i];
@@ -638,212 +957,22 @@ __device__ __forceinline__ void route_cell(const WgkParams &p, const int r, cons
     double raf_next = a.river_area_frac_next[i];
     double raf_change = a.river_area_frac_change[i];
     const double laf = a.land_area_frac[i];
-    const double lake_area = a.lake_area[r];
-    const double reservoir_area = a.reservoir_area[r];
     const double glo_wetland = a.glo_wetland[r];
-
-    if (active) {
-        const double M_EVAREDEX = a.p_evaredex[q];
-        const double kS = a.p_swoutf[q];
-        const double cfa = a.cfa[q];
-        const double owPrec = a.openwater_prec[i], owPET = a.openwater_pet[i];
-        const int ldd = a.ldd[r];
-        const bool aridc = (1 == a.arid[r]) && (ldd >= 0);
-        // loads that do not depend on upstream cells are issued before the gather
-        const double slope_pow = pow(a.river_slope[r], 0.5);
-        const double bw = a.river_bottom_width[r];
-        const double rough = a.roughness[r];
-        const double rivrgh = a.p_rivrgh[q];
+    if (flags & FL_ACTIVE) {
+        const double raf = raf_next;  // G_riverAreaFrac[n] = G_riverAreaFracNextTimestep_Frac[n] (:3424)
+        const double Sr = a.river_stor[i];
         const double river_length = a.river_length[r];
-        const double prevR = a.river_stor[i];
-        double inflow = a.t_inflow_local[i];
-
-        // upstream inflow in routing order (= order of the += at routing.cpp:3957)
-        double inflowUpstream = 0.;
-        for (int k = p.up_off[r]; k < p.up_off[r + 1]; k++) inflowUpstream += a.discharge[mb + p.up_idx[k]];
-        inflow += inflowUpstream;  // :2623
-
-        double gwr_glolak = 0., gwr_res = 0., gwr_glowet = 0.;
-        if (lake_area > 0.) {  // global lake, :2630-2804
-            const double prev = a.glo_lake_stor[i];
-            const double maxStorage = (lake_area)*a.lake_depth_active[q];
-            const double rf = a.red_glo_lake[i];
-            double evapo = ((1.0 - cfa) * owPrec) + (cfa * owPET * rf);
-            if (evapo < 0.) evapo = 0.;
-            const double totalInflow = inflow + (owPrec * (lake_area / 1000000.));
-            if (aridc) gwr_glolak = 10. * rf * (lake_area / (cellArea * (contf / 100.)));
-            const double PETgwrRemUse = evapo * (lake_area / 1000000.) + gwr_glolak * cellArea * (contf / 100.) / 1000000. + 0.;
-            const double PETgwrRemUseMax = totalInflow + maxStorage + prev;
-            double S, outflow;
-            if (PETgwrRemUse > PETgwrRemUseMax) {
-                S = (-1.) * maxStorage;
-                outflow = 0.;
-                gwr_glolak *= PETgwrRemUseMax / PETgwrRemUse;
-            } else {
-                const double ek = exp(-1. * kS);
-                S = prev * ek + (1. / kS) * (totalInflow - PETgwrRemUse) * (1. - ek);
-                outflow = totalInflow + prev - S - PETgwrRemUse;
-                if (S > maxStorage) {
-                    outflow += (S - maxStorage);
-                    S = maxStorage;
-                }
-                if (outflow < 0.) {
-                    outflow = 0.;
-                    S = prev + totalInflow - PETgwrRemUse;
-                }
-            }
-            if (fabs(S) <= MIN_STOR_VOL) S = 0.;
-            inflow = outflow;
-            a.glo_lake_stor[i] = S;
-            a.red_glo_lake[i] = clamp01(1. - pow(fabs(S - maxStorage) / (2. * maxStorage), (M_EVAREDEX * 3.32193)));
-        }
-        if (reservoir_area > 0.) {  // reservoir, :2807-3082
-            const double stor_cap = a.stor_cap[r];
-            const double mean_outflow = a.mean_outflow[r];
-            const double c_ratio = stor_cap / (mean_outflow * 31536000. / 1000000000.);
-            const double maxStorage = stor_cap;
-            const double prev = a.res_stor[i];
-            const double rf = a.red_res[i];
-            double evapo = ((1.0 - cfa) * owPrec) + (cfa * (owPET * rf));
-            if (evapo < 0.) evapo = 0.;
-            const double totalInflow = inflow + (owPrec * (reservoir_area / 1000000.));
-            if (aridc) gwr_res = 10. * rf * (reservoir_area / (cellArea * (contf / 100.)));
-            const double PETgwr = evapo * (reservoir_area / 1000000.) + gwr_res * cellArea * (contf / 100.) / 1000000.;
-            const double PETgwrMax = prev + totalInflow;
-            double S;
-            if (PETgwr > PETgwrMax) {
-                S = prev + totalInflow - PETgwrMax;
-                gwr_res *= PETgwrMax / PETgwr;
-            } else {
-                S = prev + totalInflow - PETgwr;
-            }
-            if (fabs(S) <= MIN_STOR_VOL) S = 0.;
-            double Krel = a.k_release[i];
-            const int fdim[12] = {1, 32, 60, 91, 121, 152, 182, 213, 244, 274, 305, 335};
-            if (month == a.start_month[r] - 1 && day == fdim[month]) {  // :2945-2956
-                if (S < (stor_cap * 0.1)) Krel = 0.1;
-                else Krel = S / (maxStorage * 0.85);
-                a.k_release[i] = Krel;
-            }
-            double prov_rel = 0.;
-            const int res_type = a.res_type[r];
-            if (res_type == 1) {  // irrigation reservoir; water use is not simulated: monthlyUse == 0
-                const double monthlyUse = 0.;
-                const double mean_demand = a.mean_demand[r];
-                if (mean_demand >= 0.5 * mean_outflow) prov_rel = mean_outflow / 2. * (1. + monthlyUse / mean_demand);
-                else prov_rel = mean_outflow + monthlyUse - mean_demand;
-            } else if (res_type == 2) {
-                prov_rel = mean_outflow;
-            }
-            double release;
-            if (c_ratio >= 0.5) release = Krel * prov_rel;
-            else
-                release = ((4. * c_ratio * c_ratio) * Krel * prov_rel)
-                          + ((1.0 - ((4. * c_ratio * c_ratio))) * inflow * 1000000000. / (24. * 3600.));
-            double outflow;
-            if (S >= (stor_cap * 0.1)) outflow = release * (24. * 3600.) / 1000000000.;
-            else outflow = 0.1 * release * (24. * 3600.) / 1000000000.;
-            if (outflow < 0.) outflow = 0.;
-            S -= outflow;
-            if (S > maxStorage) {
-                outflow += (S - maxStorage);
-                S = maxStorage;
-            }
-            if (S < 0.) {
-                outflow += S;
-                S = 0.;
-            }
-            inflow = outflow;
-            a.res_stor[i] = S;
-            a.red_res[i] = clamp01(1. - pow(fabs(S - maxStorage) / maxStorage, 2.81383));
-        }
-        if (glo_wetland > 0) {  // global wetland, :3178-3297
-            const double prev = a.glo_wetl_stor[i];
-            const double maxStorage = ((glo_wetland) / 100.) * cellArea * a.wetl_depth_active[q];
-            const double rf = red_glo_wetl;
-            double evapo = ((1.0 - cfa) * (owPrec * rf)) + (cfa * (owPET * rf));
-            if (evapo < 0.) evapo = 0.;
-            const double totalInflow = inflow + (owPrec * rf * (cellArea / 1000000.) * (glo_wetland / 100.));
-            if (aridc) gwr_glowet = 10. * rf * glo_wetland / 100. / (contf / 100.);
-            const double PETgwr = evapo * (cellArea / 1000000.) * ((glo_wetland) / 100.) + gwr_glowet * cellArea * (contf / 100.) / 1000000.;
-            const double PETgwrMax = totalInflow + prev;
-            double S, outflow;
-            if (PETgwr > PETgwrMax) {
-                S = 0.;
-                outflow = 0.;
-                gwr_glowet *= PETgwrMax / PETgwr;
-            } else {
-                const double ek = exp(-1. * kS);
-                S = prev * ek + (1. / kS) * (totalInflow - PETgwr) * (1. - ek);
-                outflow = totalInflow + prev - S - PETgwr;
-            }
-            if (S > maxStorage) {
-                outflow += (S - maxStorage);
-                S = maxStorage;
-            }
-            if (fabs(S) <= MIN_STOR_VOL) S = 0.;
-            inflow = outflow;
-            a.glo_wetl_stor[i] = S;
-            red_glo_wetl = clamp01(1. - pow(fabs(S - maxStorage) / maxStorage, (M_EVAREDEX * 3.32193)));
-        }
-        double gwToRiver = a.t_gw_to_river[i];
-        if (aridc) {  // :3305-3386
-            const double gwr_swb = a.t_gwr_loclak[i] + gwr_glolak + a.t_gwr_locwet[i] + gwr_glowet + gwr_res;
-            a.gwr_swb[i] = gwr_swb;
-            const double netGWin = gwr_swb * cellArea * (contf / 100.) / 1000000.
-                                   + a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
-            double Sg = a.gw[i];
-            gwToRiver = gw_step(Sg, netGWin, a.p_gwoutf[q]);
-            a.gw[i] = Sg;
-        }
-        // river, :3388-3586
-        double riverInflow = inflow;
-        if (ldd >= 0) {
-            riverInflow += a.t_runoff_to_river[i];
-            riverInflow += gwToRiver;
-        }
-        const double riverVelocity = river_velocity(slope_pow, bw, rough, riverInflow, rivrgh);
-        const double K = riverVelocity / river_length;
-        const double raf = raf_next;  // G_riverAreaFrac[n] = G_riverAreaFracNextTimestep_Frac[n]
-        double riverEvapo = ((1.0 - cfa) * (owPrec) + (cfa * owPET)) * raf / 100. * cellArea / 1000000.;
-        const double riverPrecip = owPrec * raf / 100. * cellArea / 1000000.;
-        riverInflow += riverPrecip;
-        const double RiverEvapoRemUse = 0. + riverEvapo;
-        const double eK = exp(-1. * K);
-        const double RivEvapoRemUseMax = riverInflow + (K * prevR * eK) / (1. - eK);
-        double Sr, transportedVolume;
-        if (RiverEvapoRemUse > RivEvapoRemUseMax) {
-            Sr = 0.;
-            transportedVolume = riverInflow + prevR - RivEvapoRemUseMax;
-            if (transportedVolume < 0.) transportedVolume = 0.;
-            riverEvapo *= RivEvapoRemUseMax / RiverEvapoRemUse;
-        } else {
-            Sr = prevR * eK + (1. / K) * (riverInflow - RiverEvapoRemUse) * (1. - eK);
-            if (fabs(Sr) <= MIN_STOR_VOL) Sr = 0.;
-            transportedVolume = riverInflow + prevR - Sr - RiverEvapoRemUse;
-            if (transportedVolume < 0.) transportedVolume = 0.;
-        }
-        // hand the outflow to the next level first: it is the only value other cells wait for.
-        // (inland sinks have no downstream cell; the reference keeps their river outflow out of
-        //  the discharge grid, routing.cpp:4219-4221, and books it as evaporation, :3935-3937)
-        a.discharge[i] = (ldd >= 0) ? transportedVolume : 0.;
-        a.cell_runoff[i] = (ldd < 0) ? (0. - inflowUpstream) : (transportedVolume - inflowUpstream);
-        a.river_stor[i] = Sr;
-        a.river_evapo[i] = riverEvapo;
-        {  // river width / area fraction for the next day, :3546-3586
-            const double crossSectionalArea = Sr / river_length;
-            const double riverDepth = -bw / (4. * 1000.) + sqrt(bw / 1000. * bw / (16. * 1000.) + 0.5 * crossSectionalArea);
-            double width = bw / 1000. + 4. * riverDepth;
-            const double wbf = a.river_width_bf[r];
-            if (width > wbf / 1000.) width = wbf / 1000.;
-            const double smaxr = a.river_storage_max[r];
-            red_river = clamp01(1. - pow(fabs(Sr - smaxr) / smaxr, (M_EVAREDEX * 3.32193)));
-            raf_next = red_river * river_length * width * 100. / cellArea;
-            raf_change = raf_next - raf;
-        }
+        const double bw = a.river_bottom_width[r];
+        const double crossSectionalArea = Sr / river_length;
+        const double riverDepth = -bw / (4. * 1000.) + sqrt(bw / 1000. * bw / (16. * 1000.) + 0.5 * crossSectionalArea);
+        double width = bw / 1000. + 4. * riverDepth;
+        const double wbf = a.river_width_bf[r];
+        if (width > wbf / 1000.) width = wbf / 1000.;
+        const double smaxr = a.river_storage_max[r];
+        red_river = clamp01(1. - pow(fabs(Sr - smaxr) / smaxr, (a.p_evaredex[q] * 3.32193)));
+        raf_next = red_river * river_length * width * 100. / cellArea;
+        raf_change = raf_next - raf;
     }
-
-    // surface water body fractions and next-day land area fraction (:5034-5188), all cells
     const double loc_lake = a.loc_lake[r], loc_wetland = a.loc_wetland[r];
     double fLocLake = ((loc_lake > 0.) && (red_loc_lake > 0.)) ? (red_loc_lake * loc_lake / 100.) : 0.;
     double fLocWet = ((loc_wetland > 0.) && (red_loc_wetl > 0.)) ? (red_loc_wetl * loc_wetland / 100.) : 0.;
@@ -852,7 +981,7 @@ __device__ __forceinline__ void route_cell(const WgkParams &p, const int r, cons
     double fswb_next = fLocLake + fLocWet + fGloWet;
     const double fGloLake = a.f_glo_lake[r];
     const double maxRiverAreaFrac = contf / 100. - fGloLake;
-    if (((lake_area > 0.) || (reservoir_area > 0.)) && (fGloLake == 1.)) {
+    if ((flags & (FL_LAKE | FL_RES)) && (fGloLake == 1.)) {
         raf_next = 0.;
         raf_change = 0.;
         red_river = 0.;
@@ -894,30 +1023,10 @@ __device__ __forceinline__ void route_cell(const WgkParams &p, const int r, cons
     a.fswb_laf[i] = fswb_old;
     a.fswb_laf_next[i] = fswb_next;
     a.status_laf_next[i] = 1;
-    // updateLandAreaFrac (:5343-5352) fused: prev <- cur, cur <- next
+    // updateLandAreaFrac fused: prev <- cur, cur <- next
     a.land_area_frac_next[i] = laf_next;
     a.land_area_frac_prev[i] = laf;
     a.land_area_frac[i] = laf_next;
-}
-
-// one dependency level per launch (wide levels)
-__global__ void __launch_bounds__(128) k_route_level(const __grid_constant__ WgkParams p, const int level) {
-    const int begin = p.level_off[level], end = p.level_off[level + 1];
-    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= end) return;
-    route_cell(p, r, blockIdx.y, p.cal[0], p.cal[1]);
-}
-
-// all levels from `level0` on inside one persistent CTA per member; levels are separated by
-// __syncthreads(), which also orders the global-memory hand-off of the discharge values
-__global__ void __launch_bounds__(256) k_route_tail(const __grid_constant__ WgkParams p, const int level0) {
-    const int m = blockIdx.x;
-    const int day = p.cal[0], month = p.cal[1];
-    for (int level = level0; level < p.nlevels; level++) {
-        const int begin = p.level_off[level], end = p.level_off[level + 1];
-        for (int r = begin + threadIdx.x; r < end; r += blockDim.x) route_cell(p, r, m, day, month);
-        __syncthreads();
-    }
 }
 
 // ----------------------------------------------------------------------------------------
