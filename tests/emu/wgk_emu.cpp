@@ -25,6 +25,8 @@ struct Emu {
     WgkParams p{};
     std::vector<int32_t> rank_of_cell, cell_of_rank, up_off, up_idx, down, level_off, member_pset;
     std::vector<float4> forcing;
+    std::vector<int32_t> gidx;
+    std::vector<double> gbody;
     int32_t cal[8] = {0};
 };
 
@@ -109,9 +111,17 @@ void emu_set_forcing(Emu *e, const float *P, const float *T, const float *SW, co
 // tail_level0 < 0: every level through k_route_level; else levels >= tail_level0 through k_route_tail
 void emu_day(Emu *e, int day, int month, int dom, int slot, int tail_level0) {
     e->cal[0] = day; e->cal[1] = month; e->cal[2] = dom; e->cal[3] = slot;
-    const WgkParams &p = e->p;
+    WgkParams &p = e->p;
     dim3 block(128), grid((e->ncell + 127) / 128, 1);
     launch(wgk::k_derive_static, grid, block, p);
+    if (e->gidx.empty()) {
+        e->gidx.assign(e->ncell, -1);
+        int n = 0;
+        for (int r = 0; r < e->ncell; r++)
+            if (e->p.a.s_flags[r] & (wgk::FL_LAKE | wgk::FL_RES | wgk::FL_GLOWET)) e->gidx[r] = n++;
+        e->gbody.assign((size_t)std::max(1, n) * wgk::GB_N, 0.0);
+        e->p.gidx = e->gidx.data(); e->p.gbody = e->gbody.data(); e->p.ngbody = n;
+    }
     launch(wgk::k_vertical, grid, block, p);
     launch(wgk::k_route_local, grid, block, p);
     int t0 = tail_level0 < 0 ? e->nlevels : tail_level0;

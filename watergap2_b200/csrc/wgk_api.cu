@@ -91,6 +91,9 @@ struct wgk_ctx {
     int launches_per_day = 0;
     int64_t launches = 0;
     bool derived_dirty = true;  // s_c1 / s_slope_pow / s_flags need (re)computation
+    int32_t *d_gidx = nullptr;  // [ncell] index into the global-water-body scratch or -1
+    double *d_gbody = nullptr;  // [nmember][ngbody][GB_N]
+    int ngbody = 0;
 };
 
 namespace {
@@ -148,6 +151,9 @@ WgkParams make_params(const wgk_ctx *c) {
     p.down = c->d_down;
     p.level_off = c->d_level_off;
     p.cal = c->d_cal;
+    p.gidx = c->d_gidx;
+    p.gbody = c->d_gbody;
+    p.ngbody = c->ngbody;
     p.record = c->d_record;
     p.record_cells = c->d_record_cells;
     p.nrec = c->nrec;
@@ -161,6 +167,14 @@ WgkParams make_params(const wgk_ctx *c) {
     p.restart = c->opt.restart;
     p.nlevels = c->nlevels;
     return p;
+}
+
+void drop_graph(wgk_ctx *c) {
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    c->graph_exec = nullptr;
+    c->graph = nullptr;
+    c->graph_dirty = true;
 }
 
 // enqueue the kernels of one simulated day on c->stream (also used under stream capture)
@@ -196,16 +210,27 @@ int ensure_derived(wgk_ctx *c) {
     dim3 block(128), grid((c->ncell + 127) / 128, c->npset);
     wgk::k_derive_static<<<grid, block, 0, c->stream>>>(make_params(c));
     c->launches++;
+    // cells with a global lake / reservoir / global wetland get a slot in the per-day scratch
+    std::vector<int8_t> flags(c->stride);
+    CU(cudaMemcpyAsync(flags.data(), c->arrays.s_flags, c->stride, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<int32_t> gidx(c->ncell, -1);
+    int n = 0;
+    for (int r = 0; r < c->ncell; r++)
+        if (flags[r] & (wgk::FL_LAKE | wgk::FL_RES | wgk::FL_GLOWET)) gidx[r] = n++;
+    if (c->d_gidx) cudaFree(c->d_gidx);
+    if (c->d_gbody) cudaFree(c->d_gbody);
+    c->d_gidx = nullptr;
+    c->d_gbody = nullptr;
+    CU(cudaMalloc(&c->d_gidx, sizeof(int32_t) * c->ncell));
+    CU(cudaMemcpy(c->d_gidx, gidx.data(), sizeof(int32_t) * c->ncell, cudaMemcpyHostToDevice));
+    const size_t nb = (size_t)c->nmember * std::max(1, n) * wgk::GB_N;
+    CU(cudaMalloc(&c->d_gbody, nb * sizeof(double)));
+    CU(cudaMemset(c->d_gbody, 0, nb * sizeof(double)));
+    c->ngbody = n;
     c->derived_dirty = false;
+    drop_graph(c);
     return 0;
-}
-
-void drop_graph(wgk_ctx *c) {
-    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-    if (c->graph) cudaGraphDestroy(c->graph);
-    c->graph_exec = nullptr;
-    c->graph = nullptr;
-    c->graph_dirty = true;
 }
 
 int check_ready(wgk_ctx *c) {
@@ -267,6 +292,7 @@ void wgk_destroy(wgk_ctx *c) {
     for (void *d : c->allocs) cudaFree(d);
     cudaFree(c->d_cell_of_rank); cudaFree(c->d_up_off); cudaFree(c->d_up_idx); cudaFree(c->d_down);
     cudaFree(c->d_level_off); cudaFree(c->d_member_pset); cudaFree(c->d_cal); cudaFree(c->d_forcing);
+    cudaFree(c->d_gidx); cudaFree(c->d_gbody);
     cudaFree(c->d_fstage); cudaFree(c->d_record); cudaFree(c->d_record_cells); cudaFree(c->d_partial);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -580,7 +606,8 @@ int wgk_vertical_day(wgk_ctx *c, int day, int month, int dom, int slot) {
     CU(cudaSetDevice(c->device));
     rc = set_calendar(c, day, month, dom, slot);
     if (rc) return rc;
-    ensure_derived(c);
+    rc = ensure_derived(c);
+    if (rc) return rc;
     c->launches += 1 + enqueue_vertical(c, make_params(c));
     CU(cudaGetLastError());
     return WGK_OK;
@@ -596,7 +623,8 @@ int wgk_routing_day(wgk_ctx *c, int day, int month, int dom) {
     CU(cudaMemcpyAsync(&slot, c->d_cal + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     wgk::k_set_calendar<<<1, 1, 0, c->stream>>>(c->d_cal, day, month, dom, slot);
-    ensure_derived(c);
+    rc = ensure_derived(c);
+    if (rc) return rc;
     c->launches += 1 + enqueue_routing(c, make_params(c));
     CU(cudaGetLastError());
     return WGK_OK;
@@ -619,7 +647,8 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
     if (rc) return rc;
     CU(cudaMemsetAsync(c->d_cal + 4, 0, sizeof(int32_t), c->stream));
     c->launches++;
-    ensure_derived(c);
+    rc = ensure_derived(c);
+    if (rc) return rc;
     const WgkParams p = make_params(c);
     if (c->opt.use_graph) {
         if (c->graph_dirty) {
@@ -714,7 +743,8 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     CU(cudaSetDevice(c->device));
     rc = set_calendar(c, day, month, dom, slot);
     if (rc) return rc;
-    ensure_derived(c);
+    rc = ensure_derived(c);
+    if (rc) return rc;
     cudaEvent_t ev[6];
     for (auto &e : ev) CU(cudaEventCreate(&e));
     const WgkParams p = make_params(c);

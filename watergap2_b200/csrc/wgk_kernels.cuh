@@ -37,6 +37,9 @@ struct WgkParams {
     const int32_t *down;          // [ncell] downstream rank or -1
     const int32_t *level_off;     // [nlevels+1]
     int32_t *cal;                 // device calendar {day, month, day_in_month, slot, simday}
+    const int32_t *gidx;          // [ncell] index into the global-water-body scratch or -1
+    double *gbody;                // [nmember][ngbody][GB_N] inflow-independent terms of the day
+    int ngbody;
     double *record;               // [max_days][nmember][nrec] discharge record, or null
     const int32_t *record_cells;  // [nrec] device ranks
     int nrec, record_max_days;
@@ -471,6 +474,13 @@ __device__ __forceinline__ double clamp01(double x) {
     return x;
 }
 
+// Inflow-independent terms of the global lake / reservoir / global wetland / arid groundwater
+// equations of one cell and one day, computed by the cell-parallel pre-pass so that the ordered
+// sweep only evaluates what really depends on the upstream inflow.
+enum { GB_L_PREC, GB_L_PET, GB_L_MAX, GB_L_GWR, GB_R_PREC, GB_R_PET, GB_R_GWR, GB_R_C, GB_R_PROV, GB_R_CAP,
+       GB_W_PREC, GB_W_PET, GB_W_MAX, GB_W_GWR, GB_EKS, GB_INVKS, GB_EKG, GB_INVKG, GB_GWRECH, GB_LOC_GWR_LAK,
+       GB_LOC_GWR_WET, GB_N = 24 };
+
 // cell class bits (s_flags, derived once from the statics by k_derive_static)
 constexpr int FL_ACTIVE = 1, FL_LDD_OUT = 2, FL_ARIDC = 4, FL_LAKE = 8, FL_RES = 16, FL_GLOWET = 32;
 
@@ -640,6 +650,63 @@ __global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ Wgk
             localGWRunoffIntoRiver = gw_step(Sg, netGWin, kG);
             a.gw[i] = Sg;
         }
+        if (flags & (FL_LAKE | FL_RES | FL_GLOWET)) {
+            double *g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;
+            g[GB_EKS] = exp(-1. * kS);
+            g[GB_INVKS] = (1. / kS);
+            g[GB_EKG] = exp(-1. * kG);
+            g[GB_INVKG] = (1. / kG);
+            g[GB_GWRECH] = a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
+            g[GB_LOC_GWR_LAK] = gwr_loclak;
+            g[GB_LOC_GWR_WET] = gwr_locwet;
+            if (flags & FL_LAKE) {  // :2630-2676
+                const double lake_area = a.lake_area[r];
+                const double rf = a.red_glo_lake[i];
+                double evapo = ((1.0 - cfa) * owPrec) + (cfa * owPET * rf);
+                if (evapo < 0.) evapo = 0.;
+                const double gwr = aridc ? 10. * rf * (lake_area / (cellArea * (contf / 100.))) : 0.;
+                g[GB_L_PREC] = (owPrec * (lake_area / 1000000.));
+                g[GB_L_GWR] = gwr;
+                g[GB_L_PET] = evapo * (lake_area / 1000000.) + gwr * cellArea * (contf / 100.) / 1000000. + 0.;
+                g[GB_L_MAX] = (lake_area)*a.lake_depth_active[q];
+            }
+            if (flags & FL_RES) {  // :2807-2870, 2960-2983
+                const double reservoir_area = a.reservoir_area[r];
+                const double stor_cap = a.stor_cap[r];
+                const double mean_outflow = a.mean_outflow[r];
+                const double rf = a.red_res[i];
+                double evapo = ((1.0 - cfa) * owPrec) + (cfa * (owPET * rf));
+                if (evapo < 0.) evapo = 0.;
+                const double gwr = aridc ? 10. * rf * (reservoir_area / (cellArea * (contf / 100.))) : 0.;
+                g[GB_R_PREC] = (owPrec * (reservoir_area / 1000000.));
+                g[GB_R_GWR] = gwr;
+                g[GB_R_PET] = evapo * (reservoir_area / 1000000.) + gwr * cellArea * (contf / 100.) / 1000000.;
+                g[GB_R_C] = stor_cap / (mean_outflow * 31536000. / 1000000000.);
+                g[GB_R_CAP] = stor_cap;
+                double prov_rel = 0.;
+                const int res_type = a.res_type[r];
+                if (res_type == 1) {  // irrigation reservoir; water use is not simulated: monthlyUse == 0
+                    const double monthlyUse = 0.;
+                    const double mean_demand = a.mean_demand[r];
+                    if (mean_demand >= 0.5 * mean_outflow) prov_rel = mean_outflow / 2. * (1. + monthlyUse / mean_demand);
+                    else prov_rel = mean_outflow + monthlyUse - mean_demand;
+                } else if (res_type == 2) {
+                    prov_rel = mean_outflow;
+                }
+                g[GB_R_PROV] = prov_rel;
+            }
+            if (flags & FL_GLOWET) {  // :3178-3200
+                const double glo_wetland = a.glo_wetland[r];
+                const double rf = a.red_glo_wetl[i];
+                double evapo = ((1.0 - cfa) * (owPrec * rf)) + (cfa * (owPET * rf));
+                if (evapo < 0.) evapo = 0.;
+                const double gwr = aridc ? 10. * rf * glo_wetland / 100. / (contf / 100.) : 0.;
+                g[GB_W_PREC] = (owPrec * rf * (cellArea / 1000000.) * (glo_wetland / 100.));
+                g[GB_W_GWR] = gwr;
+                g[GB_W_PET] = evapo * (cellArea / 1000000.) * ((glo_wetland) / 100.) + gwr * cellArea * (contf / 100.) / 1000000.;
+                g[GB_W_MAX] = ((glo_wetland) / 100.) * cellArea * a.wetl_depth_active[q];
+            }
+        }
         // river evaporation and precipitation on yesterday's river area fraction (:3425-3441)
         const double raf = a.river_area_frac_next[i];
         a.t_river_evapo[i] = ((1.0 - cfa) * (owPrec) + (cfa * owPET)) * raf / 100. * cellArea / 1000000.;
@@ -681,74 +748,57 @@ __device__ __forceinline__ RiverCtx load_ctx(const WgkParams &p, const int r, co
 }
 
 // global lake, reservoir, global wetland and the arid groundwater below them (routing.cpp:2630-3386)
-// for the few cells that have them; returns the inflow handed to the river
-__device__ __noinline__ double route_global_bodies(const WgkParams &p, const int r, const int m, const size_t i, const size_t q,
+// for the few cells that have them: only the inflow-dependent arithmetic; exp(), 1/k, evaporation
+// and recharge demands come from the pre-pass (GBody), the reduction-factor pow() is done by the
+// post-pass.  Returns the inflow handed to the river.
+__device__ __noinline__ double route_global_bodies(const WgkParams &p, const int r, const int m, const size_t i,
                                                    double inflow, const int flags, const int day, const int month,
                                                    double &gwToRiver) {
     const WgkArrays &a = p.a;
-    const double M_EVAREDEX = a.p_evaredex[q];
-    const double kS = a.p_swoutf[q];
-    const double cfa = a.cfa[q];
-    const double owPrec = a.openwater_prec[i], owPET = a.openwater_pet[i];
-    const bool aridc = (flags & FL_ARIDC) != 0;
-    const double contf = a.contfreq[r];
-    const double cellArea = a.area[r];
-    const double lake_area = a.lake_area[r];
-    const double reservoir_area = a.reservoir_area[r];
-    const double glo_wetland = a.glo_wetland[r];
+    const double *__restrict__ g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;
+    const double ek = g[GB_EKS], invk = g[GB_INVKS];
     double gwr_glolak = 0., gwr_res = 0., gwr_glowet = 0.;
-    if (lake_area > 0.) {  // global lake, :2630-2804
+    if (flags & FL_LAKE) {  // :2677-2720
         const double prev = a.glo_lake_stor[i];
-        const double maxStorage = (lake_area)*a.lake_depth_active[q];
-        const double rf = a.red_glo_lake[i];
-        double evapo = ((1.0 - cfa) * owPrec) + (cfa * owPET * rf);
-        if (evapo < 0.) evapo = 0.;
-        const double totalInflow = inflow + (owPrec * (lake_area / 1000000.));
-        if (aridc) gwr_glolak = 10. * rf * (lake_area / (cellArea * (contf / 100.)));
-        const double PETgwrRemUse = evapo * (lake_area / 1000000.) + gwr_glolak * cellArea * (contf / 100.) / 1000000. + 0.;
-        const double PETgwrRemUseMax = totalInflow + maxStorage + prev;
+        const double maxStorage = g[GB_L_MAX], PET = g[GB_L_PET];
+        gwr_glolak = g[GB_L_GWR];
+        const double totalInflow = inflow + g[GB_L_PREC];
+        const double PETmax = totalInflow + maxStorage + prev;
         double S, outflow;
-        if (PETgwrRemUse > PETgwrRemUseMax) {
+        if (PET > PETmax) {
             S = (-1.) * maxStorage;
             outflow = 0.;
-            gwr_glolak *= PETgwrRemUseMax / PETgwrRemUse;
+            gwr_glolak *= PETmax / PET;
         } else {
-            const double ek = exp(-1. * kS);
-            S = prev * ek + (1. / kS) * (totalInflow - PETgwrRemUse) * (1. - ek);
-            outflow = totalInflow + prev - S - PETgwrRemUse;
+            S = prev * ek + invk * (totalInflow - PET) * (1. - ek);
+            outflow = totalInflow + prev - S - PET;
             if (S > maxStorage) {
                 outflow += (S - maxStorage);
                 S = maxStorage;
             }
             if (outflow < 0.) {
                 outflow = 0.;
-                S = prev + totalInflow - PETgwrRemUse;
+                S = prev + totalInflow - PET;
             }
         }
         if (fabs(S) <= MIN_STOR_VOL) S = 0.;
         inflow = outflow;
         a.glo_lake_stor[i] = S;
-        a.red_glo_lake[i] = clamp01(1. - pow(fabs(S - maxStorage) / (2. * maxStorage), (M_EVAREDEX * 3.32193)));
     }
-    if (reservoir_area > 0.) {  // reservoir, :2807-3082
-        const double stor_cap = a.stor_cap[r];
-        const double mean_outflow = a.mean_outflow[r];
-        const double c_ratio = stor_cap / (mean_outflow * 31536000. / 1000000000.);
+    if (flags & FL_RES) {  // :2871-3040
+        const double stor_cap = g[GB_R_CAP];
         const double maxStorage = stor_cap;
         const double prev = a.res_stor[i];
-        const double rf = a.red_res[i];
-        double evapo = ((1.0 - cfa) * owPrec) + (cfa * (owPET * rf));
-        if (evapo < 0.) evapo = 0.;
-        const double totalInflow = inflow + (owPrec * (reservoir_area / 1000000.));
-        if (aridc) gwr_res = 10. * rf * (reservoir_area / (cellArea * (contf / 100.)));
-        const double PETgwr = evapo * (reservoir_area / 1000000.) + gwr_res * cellArea * (contf / 100.) / 1000000.;
-        const double PETgwrMax = prev + totalInflow;
+        const double PET = g[GB_R_PET];
+        gwr_res = g[GB_R_GWR];
+        const double totalInflow = inflow + g[GB_R_PREC];
+        const double PETmax = prev + totalInflow;
         double S;
-        if (PETgwr > PETgwrMax) {
-            S = prev + totalInflow - PETgwrMax;
-            gwr_res *= PETgwrMax / PETgwr;
+        if (PET > PETmax) {
+            S = prev + totalInflow - PETmax;
+            gwr_res *= PETmax / PET;
         } else {
-            S = prev + totalInflow - PETgwr;
+            S = prev + totalInflow - PET;
         }
         if (fabs(S) <= MIN_STOR_VOL) S = 0.;
         double Krel = a.k_release[i];
@@ -758,16 +808,7 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
             else Krel = S / (maxStorage * 0.85);
             a.k_release[i] = Krel;
         }
-        double prov_rel = 0.;
-        const int res_type = a.res_type[r];
-        if (res_type == 1) {  // irrigation reservoir; water use is not simulated: monthlyUse == 0
-            const double monthlyUse = 0.;
-            const double mean_demand = a.mean_demand[r];
-            if (mean_demand >= 0.5 * mean_outflow) prov_rel = mean_outflow / 2. * (1. + monthlyUse / mean_demand);
-            else prov_rel = mean_outflow + monthlyUse - mean_demand;
-        } else if (res_type == 2) {
-            prov_rel = mean_outflow;
-        }
+        const double c_ratio = g[GB_R_C], prov_rel = g[GB_R_PROV];
         double release;
         if (c_ratio >= 0.5) release = Krel * prov_rel;
         else
@@ -788,27 +829,21 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
         }
         inflow = outflow;
         a.res_stor[i] = S;
-        a.red_res[i] = clamp01(1. - pow(fabs(S - maxStorage) / maxStorage, 2.81383));
     }
-    if (glo_wetland > 0) {  // global wetland, :3178-3297
+    if (flags & FL_GLOWET) {  // :3201-3260
         const double prev = a.glo_wetl_stor[i];
-        const double maxStorage = ((glo_wetland) / 100.) * cellArea * a.wetl_depth_active[q];
-        const double rf = a.red_glo_wetl[i];
-        double evapo = ((1.0 - cfa) * (owPrec * rf)) + (cfa * (owPET * rf));
-        if (evapo < 0.) evapo = 0.;
-        const double totalInflow = inflow + (owPrec * rf * (cellArea / 1000000.) * (glo_wetland / 100.));
-        if (aridc) gwr_glowet = 10. * rf * glo_wetland / 100. / (contf / 100.);
-        const double PETgwr = evapo * (cellArea / 1000000.) * ((glo_wetland) / 100.) + gwr_glowet * cellArea * (contf / 100.) / 1000000.;
-        const double PETgwrMax = totalInflow + prev;
+        const double maxStorage = g[GB_W_MAX], PET = g[GB_W_PET];
+        gwr_glowet = g[GB_W_GWR];
+        const double totalInflow = inflow + g[GB_W_PREC];
+        const double PETmax = totalInflow + prev;
         double S, outflow;
-        if (PETgwr > PETgwrMax) {
+        if (PET > PETmax) {
             S = 0.;
             outflow = 0.;
-            gwr_glowet *= PETgwrMax / PETgwr;
+            gwr_glowet *= PETmax / PET;
         } else {
-            const double ek = exp(-1. * kS);
-            S = prev * ek + (1. / kS) * (totalInflow - PETgwr) * (1. - ek);
-            outflow = totalInflow + prev - S - PETgwr;
+            S = prev * ek + invk * (totalInflow - PET) * (1. - ek);
+            outflow = totalInflow + prev - S - PET;
         }
         if (S > maxStorage) {
             outflow += (S - maxStorage);
@@ -817,15 +852,22 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
         if (fabs(S) <= MIN_STOR_VOL) S = 0.;
         inflow = outflow;
         a.glo_wetl_stor[i] = S;
-        a.red_glo_wetl[i] = clamp01(1. - pow(fabs(S - maxStorage) / maxStorage, (M_EVAREDEX * 3.32193)));
     }
-    if (aridc) {  // :3305-3386
-        const double gwr_swb = a.t_gwr_loclak[i] + gwr_glolak + a.t_gwr_locwet[i] + gwr_glowet + gwr_res;
+    if (flags & FL_ARIDC) {  // :3305-3386
+        const double gwr_swb = g[GB_LOC_GWR_LAK] + gwr_glolak + g[GB_LOC_GWR_WET] + gwr_glowet + gwr_res;
         a.gwr_swb[i] = gwr_swb;
-        const double laf = a.land_area_frac[i];
-        const double netGWin = gwr_swb * cellArea * (contf / 100.) / 1000000. + a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
-        double Sg = a.gw[i];
-        gwToRiver = gw_step(Sg, netGWin, a.p_gwoutf[q]);
+        const double netGWin = gwr_swb * a.area[r] * (a.contfreq[r] / 100.) / 1000000. + g[GB_GWRECH];
+        const double prev = a.gw[i];
+        const double ekg = g[GB_EKG];
+        double Sg = prev * ekg + g[GB_INVKG] * netGWin * (1. - ekg);
+        if (fabs(Sg) <= MIN_STOR_VOL) Sg = 0.;
+        double qq = prev - Sg + netGWin;
+        if (qq <= 0.) {
+            qq = 0.;
+            Sg = prev + netGWin;
+            if (fabs(Sg) <= MIN_STOR_VOL) Sg = 0.;
+        }
+        gwToRiver = qq;
         a.gw[i] = Sg;
     }
     (void)m;
@@ -839,7 +881,7 @@ __device__ __forceinline__ void route_river(const WgkParams &p, const RiverCtx &
     const WgkArrays &a = p.a;
     double inflow = c.inflow_local + inflowUpstream;  // :2623
     double gwToRiver = c.gw_to_river;
-    if (c.flags & (FL_LAKE | FL_RES | FL_GLOWET)) inflow = route_global_bodies(p, r, m, i, q, inflow, c.flags, day, month, gwToRiver);
+    if (c.flags & (FL_LAKE | FL_RES | FL_GLOWET)) inflow = route_global_bodies(p, r, m, i, inflow, c.flags, day, month, gwToRiver);
     double riverInflow = inflow;
     if (c.flags & FL_LDD_OUT) {
         riverInflow += c.runoff_to_river;
@@ -972,6 +1014,23 @@ __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkP
         red_river = clamp01(1. - pow(fabs(Sr - smaxr) / smaxr, (a.p_evaredex[q] * 3.32193)));
         raf_next = red_river * river_length * width * 100. / cellArea;
         raf_change = raf_next - raf;
+    }
+    if ((flags & FL_ACTIVE) && (flags & (FL_LAKE | FL_RES | FL_GLOWET))) {
+        // evaporation reduction factors of the global water bodies (:2790-2802, 3068-3078, 3287-3296)
+        const double *__restrict__ g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;
+        const double xexp = (a.p_evaredex[q] * 3.32193);
+        if (flags & FL_LAKE) {
+            const double maxStorage = g[GB_L_MAX];
+            a.red_glo_lake[i] = clamp01(1. - pow(fabs(a.glo_lake_stor[i] - maxStorage) / (2. * maxStorage), xexp));
+        }
+        if (flags & FL_RES) {
+            const double maxStorage = g[GB_R_CAP];
+            a.red_res[i] = clamp01(1. - pow(fabs(a.res_stor[i] - maxStorage) / maxStorage, 2.81383));
+        }
+        if (flags & FL_GLOWET) {
+            const double maxStorage = g[GB_W_MAX];
+            red_glo_wetl = clamp01(1. - pow(fabs(a.glo_wetl_stor[i] - maxStorage) / maxStorage, xexp));
+        }
     }
     const double loc_lake = a.loc_lake[r], loc_wetland = a.loc_wetland[r];
     double fLocLake = ((loc_lake > 0.) && (red_loc_lake > 0.)) ? (red_loc_lake * loc_lake / 100.) : 0.;
