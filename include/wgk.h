@@ -62,7 +62,7 @@ typedef enum {
 typedef struct {
     int restart;            /* additionalOutIn.additionalfilestatus (daily.cpp:165): 0 cold start, 1 from checkpoint */
     int tail_threshold;     /* routing levels with <= this many cells are run by one persistent CTA per member (0 = auto) */
-    int use_graph;          /* 1: replay one captured CUDA graph per simulated day (default), 0: plain launches */
+    int use_graph;          /* 1: one CUDA graph of (day, level) tasks per wgk_step_days call (default), 0: plain launches in dependency order */
 } wgk_options;
 
 /* ---- life cycle ---------------------------------------------------------------------- */
@@ -120,8 +120,9 @@ int wgk_set_forcing(wgk_ctx *ctx, int slot0, int ndays, int member, const float 
  * calcNewDay for every continental cell, routing(), updateLandAreaFrac().
  * day 1..365 (day of the 365-day model year), month 0..11, day_in_month 1..31, slot =
  * forcing slot of that day.  The three-call form exists for the class shims; wgk_step_days
- * runs `ndays` consecutive days (calendar advanced on the device, forcing slots
- * slot0, slot0+1, ... modulo the reserved slots) as one graph replay per day. */
+ * runs `ndays` (<= 366) consecutive days (365-day model years, forcing slots slot0, slot0+1, ...
+ * modulo the reserved slots) as ONE CUDA graph of (day, routing level) tasks whose edges are the
+ * data dependencies, so that the level chain of one day overlaps the following days. */
 int wgk_vertical_day(wgk_ctx *ctx, int day, int month, int day_in_month, int slot);
 int wgk_routing_day(wgk_ctx *ctx, int day, int month, int day_in_month);
 int wgk_update_land_area_frac(wgk_ctx *ctx);

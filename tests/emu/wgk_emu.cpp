@@ -26,7 +26,8 @@ struct Emu {
     std::vector<int32_t> rank_of_cell, cell_of_rank, up_off, up_idx, down, level_off, member_pset;
     std::vector<float4> forcing;
     std::vector<int32_t> gidx;
-    std::vector<double> gbody;
+    std::vector<double> gbody, qbuf;
+    int32_t cal_days[8] = {0};
     int32_t cal[8] = {0};
 };
 
@@ -70,6 +71,8 @@ Emu *emu_create(int ncell, const int32_t *rout_order, const int32_t *downstream)
     p.record = nullptr; p.record_cells = nullptr; p.nrec = 0; p.record_max_days = 0;
     p.ncell = ncell; p.stride = e->stride; p.nmember = 1; p.npset = 1; p.forcing_nslots = 31; p.forcing_per_member = 0;
     p.restart = 0; p.nlevels = e->nlevels;
+    e->qbuf.assign((size_t)wgk::QBUF_K * e->stride, 0.0);
+    p.qbuf = e->qbuf.data(); p.cal_days = e->cal_days;
     return e;
 }
 
@@ -108,9 +111,11 @@ void emu_set_forcing(Emu *e, const float *P, const float *T, const float *SW, co
         }
 }
 
-// tail_level0 < 0: every level through k_route_level; else levels >= tail_level0 through k_route_tail
+// tail_level0 < 0: every level through the fused per-(day, level) kernel k_day_level; else levels
+// >= tail_level0 through k_cells_pre + the tail-chunk path (emulated level by level, because a
+// CTA whose threads run one after the other is only equivalent to the real one between barriers)
 void emu_day(Emu *e, int day, int month, int dom, int slot, int tail_level0) {
-    e->cal[0] = day; e->cal[1] = month; e->cal[2] = dom; e->cal[3] = slot;
+    e->cal_days[0] = day; e->cal_days[1] = month; e->cal_days[2] = dom; e->cal_days[3] = slot;
     WgkParams &p = e->p;
     dim3 block(128), grid((e->ncell + 127) / 128, 1);
     launch(wgk::k_derive_static, grid, block, p);
@@ -122,21 +127,23 @@ void emu_day(Emu *e, int day, int month, int dom, int slot, int tail_level0) {
         e->gbody.assign((size_t)std::max(1, n) * wgk::GB_N, 0.0);
         e->p.gidx = e->gidx.data(); e->p.gbody = e->gbody.data(); e->p.ngbody = n;
     }
-    launch(wgk::k_vertical, grid, block, p);
-    launch(wgk::k_route_local, grid, block, p);
     int t0 = tail_level0 < 0 ? e->nlevels : tail_level0;
     for (int l = 0; l < t0; l++) {
         int cnt = e->level_off[l + 1] - e->level_off[l];
-        launch(wgk::k_route_level, dim3((cnt + 127) / 128, 1), block, p, l);
+        launch(wgk::k_day_level, dim3((cnt + 127) / 128, 1), block, p, 0, l);
     }
-    // a CTA whose threads run one after the other is only equivalent to the real one between
-    // barriers: emulate k_route_tail level by level
-    for (int l = t0; l < e->nlevels; l++)
-        for (int r = e->level_off[l]; r < e->level_off[l + 1]; r++) {
-            const wgk::RiverCtx c = wgk::load_ctx(p, r, (size_t)r, (size_t)r);
-            if (c.flags & wgk::FL_ACTIVE) wgk::route_river(p, c, r, 0, (size_t)r, (size_t)r, wgk::gather_upstream(p, c, 0), day, month);
-        }
-    launch(wgk::k_route_post, grid, block, p);
+    if (t0 < e->nlevels) {
+        int begin = e->level_off[t0], end = e->level_off[e->nlevels];
+        launch(wgk::k_cells_pre, dim3((end - begin + 127) / 128, 1), block, p, 0, begin, end);
+        double *qday = wgk::qbuf_of_day(p, 0);
+        for (int l = t0; l < e->nlevels; l++)
+            for (int r = e->level_off[l]; r < e->level_off[l + 1]; r++) {
+                const wgk::RiverCtx c = wgk::load_ctx(p, r, (size_t)r, (size_t)r);
+                if (c.flags & wgk::FL_ACTIVE) wgk::route_river(p, c, r, 0, (size_t)r, (size_t)r, wgk::gather_upstream(p, c, 0, qday), day, month, qday);
+            }
+        for (int r = begin; r < end; r++) wgk::route_post_cell(p, r, 0);
+    }
+    memcpy(p.a.discharge, wgk::qbuf_of_day(p, 0), sizeof(double) * e->stride);
 }
 
 int emu_nlevels(Emu *e) { return e->nlevels; }

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -84,11 +85,14 @@ struct wgk_ctx {
     size_t h_stage_bytes = 0;
     double *d_partial = nullptr;
 
-    // graph of one simulated day
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
-    bool graph_dirty = true;
-    int launches_per_day = 0;
+    // per-call calendar table and the discharge buffers of the days in flight
+    int32_t *d_cal_days = nullptr;
+    double *d_qbuf = nullptr;
+    std::vector<int> chunk_lo;  // tail chunks: levels [chunk_lo[c], chunk_lo[c+1])
+
+    // CUDA graphs of the (day, level) wavefront, one per call length
+    std::map<int, cudaGraphExec_t> graphs;
+    std::map<int, int> graph_nodes;
     int64_t launches = 0;
     bool derived_dirty = true;  // s_c1 / s_slope_pow / s_flags need (re)computation
     int32_t *d_gidx = nullptr;  // [ncell] index into the global-water-body scratch or -1
@@ -151,6 +155,8 @@ WgkParams make_params(const wgk_ctx *c) {
     p.down = c->d_down;
     p.level_off = c->d_level_off;
     p.cal = c->d_cal;
+    p.cal_days = c->d_cal_days;
+    p.qbuf = c->d_qbuf;
     p.gidx = c->d_gidx;
     p.gbody = c->d_gbody;
     p.ngbody = c->ngbody;
@@ -170,20 +176,22 @@ WgkParams make_params(const wgk_ctx *c) {
 }
 
 void drop_graph(wgk_ctx *c) {
-    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-    if (c->graph) cudaGraphDestroy(c->graph);
-    c->graph_exec = nullptr;
-    c->graph = nullptr;
-    c->graph_dirty = true;
+    for (auto &kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
+    c->graph_nodes.clear();
 }
 
-// enqueue the kernels of one simulated day on c->stream (also used under stream capture)
-int enqueue_vertical(wgk_ctx *c, const WgkParams &p) {
+constexpr int MAX_CALL_DAYS = 366;
+constexpr int LEVELS_PER_CHUNK = 8;
+
+// plain launches of one simulated day (day offset `d` of the current call) on c->stream, phase
+// by phase over the whole grid; used by the three-call class-shim path and by wgk_profile_day
+int enqueue_vertical(wgk_ctx *c, const WgkParams &p, int d) {
     dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
-    wgk::k_vertical<<<grid, block, 0, c->stream>>>(p);
+    wgk::k_vertical<<<grid, block, 0, c->stream>>>(p, d);
     return 1;
 }
-int enqueue_routing(wgk_ctx *c, const WgkParams &p) {
+int enqueue_routing(wgk_ctx *c, const WgkParams &p, int d) {
     int n = 0;
     dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
     wgk::k_route_local<<<grid, block, 0, c->stream>>>(p);
@@ -191,16 +199,111 @@ int enqueue_routing(wgk_ctx *c, const WgkParams &p) {
     for (int l = 0; l < c->tail_level0; l++) {
         const int cnt = c->level_off[l + 1] - c->level_off[l];
         dim3 g((cnt + 127) / 128, c->nmember);
-        wgk::k_route_level<<<g, block, 0, c->stream>>>(p, l);
+        wgk::k_route_level<<<g, block, 0, c->stream>>>(p, d, l);
         n++;
     }
     if (c->tail_level0 < c->nlevels) {
-        wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, c->tail_level0);
+        wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, d, c->tail_level0, c->nlevels);
         n++;
     }
     wgk::k_route_post<<<grid, block, 0, c->stream>>>(p);
     n++;
     return n;
+}
+
+// the kernels of `ndays` days as (day, level) tasks in dependency order; serial order on one
+// stream satisfies every dependency (used when use_graph == 0)
+int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
+    int n = 0;
+    dim3 block(128);
+    for (int d = 0; d < ndays; d++) {
+        for (int l = 0; l < c->tail_level0; l++) {
+            const int cnt = c->level_off[l + 1] - c->level_off[l];
+            wgk::k_day_level<<<dim3((cnt + 127) / 128, c->nmember), block, 0, c->stream>>>(p, d, l);
+            n++;
+        }
+        for (size_t k = 0; k + 1 < c->chunk_lo.size(); k++) {
+            const int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
+            const int begin = c->level_off[lo], end = c->level_off[hi];
+            wgk::k_cells_pre<<<dim3((end - begin + 127) / 128, c->nmember), block, 0, c->stream>>>(p, d, begin, end);
+            wgk::k_tail_chunk<<<c->nmember, 256, 0, c->stream>>>(p, d, lo, hi);
+            n += 2;
+        }
+        if (c->d_record) {
+            wgk::k_end_of_day<<<1, 256, 0, c->stream>>>(p, d);
+            n++;
+        }
+    }
+    return n;
+}
+
+// The same tasks as a CUDA graph whose edges are exactly the data dependencies:
+//   (d, l)   <- (d, l-1)        upstream discharge of the same day
+//   (d, l)   <- (d-1, l)        own state of the previous day
+//   first sweep task of day d <- end of day d-QBUF_K   (discharge buffer reuse)
+// so that (d, l), (d+1, l-1), (d+2, l-2) ... execute concurrently.
+int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphExec_t *out, int *nnodes) {
+    cudaGraph_t g;
+    CU(cudaGraphCreate(&g, 0));
+    const int W = c->tail_level0;
+    const int C = (int)c->chunk_lo.size() - 1 > 0 ? (int)c->chunk_lo.size() - 1 : 0;
+    std::vector<cudaGraphNode_t> prevW(W, nullptr), prevT(C, nullptr), dayEnd(ndays, nullptr);
+    int count = 0;
+    auto add = [&](void *fn, dim3 grid, dim3 block, void **args, std::vector<cudaGraphNode_t> deps, cudaGraphNode_t *node) -> cudaError_t {
+        cudaKernelNodeParams kp{};
+        kp.func = fn;
+        kp.gridDim = grid;
+        kp.blockDim = block;
+        kp.sharedMemBytes = 0;
+        kp.kernelParams = args;
+        kp.extra = nullptr;
+        std::vector<cudaGraphNode_t> dd;
+        for (auto x : deps) if (x) dd.push_back(x);
+        count++;
+        return cudaGraphAddKernelNode(node, g, dd.data(), dd.size(), &kp);
+    };
+    WgkParams pp = p;
+    for (int d = 0; d < ndays; d++) {
+        cudaGraphNode_t reuse = (d >= wgk::QBUF_K) ? dayEnd[d - wgk::QBUF_K] : nullptr;
+        cudaGraphNode_t last = nullptr;
+        bool first_sweep = true;
+        for (int l = 0; l < W; l++) {
+            const int cnt = c->level_off[l + 1] - c->level_off[l];
+            int dd = d, ll = l;
+            void *args[] = {&pp, &dd, &ll};
+            cudaGraphNode_t node;
+            CU(add((void *)wgk::k_day_level, dim3((cnt + 127) / 128, c->nmember), dim3(128), args,
+                   {last, prevW[l], first_sweep ? reuse : nullptr}, &node));
+            first_sweep = false;
+            prevW[l] = node;
+            last = node;
+        }
+        for (int k = 0; k < C; k++) {
+            int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
+            int begin = c->level_off[lo], end = c->level_off[hi], dd = d;
+            void *a1[] = {&pp, &dd, &begin, &end};
+            cudaGraphNode_t pre, sweep;
+            CU(add((void *)wgk::k_cells_pre, dim3((end - begin + 127) / 128, c->nmember), dim3(128), a1, {prevT[k]}, &pre));
+            void *a2[] = {&pp, &dd, &lo, &hi};
+            CU(add((void *)wgk::k_tail_chunk, dim3(c->nmember), dim3(256), a2, {pre, last, first_sweep ? reuse : nullptr}, &sweep));
+            first_sweep = false;
+            prevT[k] = sweep;
+            last = sweep;
+        }
+        if (c->d_record) {
+            int dd = d;
+            void *a3[] = {&pp, &dd};
+            cudaGraphNode_t e;
+            CU(add((void *)wgk::k_end_of_day, dim3(1), dim3(256), a3, {last}, &e));
+            last = e;
+        }
+        dayEnd[d] = last;
+    }
+    cudaError_t e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(c, WGK_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    *nnodes = count;
+    return 0;
 }
 
 // inflow-independent river constants and cell class flags, recomputed after any static or
@@ -280,6 +383,11 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     CU(cudaMalloc(&c->d_cal, sizeof(int32_t) * 8));
     CU(cudaMemsetAsync(c->d_cal, 0, sizeof(int32_t) * 8, c->stream));
     CU(cudaMalloc(&c->d_partial, sizeof(double) * 256));
+    CU(cudaMalloc(&c->d_cal_days, sizeof(int32_t) * 4 * MAX_CALL_DAYS));
+    CU(cudaMemsetAsync(c->d_cal_days, 0, sizeof(int32_t) * 4 * MAX_CALL_DAYS, c->stream));
+    const size_t qn = (size_t)wgk::QBUF_K * nmember * c->stride;
+    if (cudaMalloc(&c->d_qbuf, qn * sizeof(double)) != cudaSuccess) return fail(c, WGK_ERR_NOMEM, "cudaMalloc discharge buffers");
+    CU(cudaMemsetAsync(c->d_qbuf, 0, qn * sizeof(double), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return WGK_OK;
 }
@@ -292,7 +400,7 @@ void wgk_destroy(wgk_ctx *c) {
     for (void *d : c->allocs) cudaFree(d);
     cudaFree(c->d_cell_of_rank); cudaFree(c->d_up_off); cudaFree(c->d_up_idx); cudaFree(c->d_down);
     cudaFree(c->d_level_off); cudaFree(c->d_member_pset); cudaFree(c->d_cal); cudaFree(c->d_forcing);
-    cudaFree(c->d_gidx); cudaFree(c->d_gbody);
+    cudaFree(c->d_gidx); cudaFree(c->d_gbody); cudaFree(c->d_cal_days); cudaFree(c->d_qbuf);
     cudaFree(c->d_fstage); cudaFree(c->d_record); cudaFree(c->d_record_cells); cudaFree(c->d_partial);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -370,6 +478,9 @@ int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downs
         if (c->level_off[l + 1] - c->level_off[l] <= c->opt.tail_threshold) c->tail_level0 = l;
         else break;
     }
+    c->chunk_lo.clear();
+    for (int l = c->tail_level0; l < c->nlevels; l += LEVELS_PER_CHUNK) c->chunk_lo.push_back(l);
+    if (c->tail_level0 < c->nlevels) c->chunk_lo.push_back(c->nlevels);
     auto upload = [&](int32_t *&dptr, const std::vector<int32_t> &v) -> cudaError_t {
         if (dptr) cudaFree(dptr);
         dptr = nullptr;
@@ -593,10 +704,19 @@ int wgk_set_forcing(wgk_ctx *c, int slot0, int ndays, int member, const float *p
 // ---------------------------------------------------------------------------------------
 // hot path
 // ---------------------------------------------------------------------------------------
-static int set_calendar(wgk_ctx *c, int day, int month, int dom, int slot) {
+static int fill_calendar(wgk_ctx *c, int day, int month, int dom, int slot, int ndays) {
     if (day < 1 || day > 365 || month < 0 || month > 11 || dom < 1 || dom > 31) return fail(c, WGK_ERR_ARG, "bad date day=%d month=%d day_in_month=%d", day, month, dom);
     if (slot < 0 || slot >= c->forcing_nslots) return fail(c, WGK_ERR_ARG, "forcing slot %d not reserved", slot);
-    wgk::k_set_calendar<<<1, 1, 0, c->stream>>>(c->d_cal, day, month, dom, slot);
+    if (ndays < 1 || ndays > MAX_CALL_DAYS) return fail(c, WGK_ERR_ARG, "1..%d days per call", MAX_CALL_DAYS);
+    wgk::k_fill_calendar<<<1, 1, 0, c->stream>>>(c->d_cal_days, day, month, dom, slot, ndays, c->forcing_nslots);
+    c->launches++;
+    return WGK_OK;
+}
+
+// make the discharge of day offset `d` of the finished call the value of the "discharge" field
+static int publish_discharge(wgk_ctx *c, int d) {
+    const size_t n = (size_t)c->nmember * c->stride;
+    CU(cudaMemcpyAsync(c->arrays.discharge, c->d_qbuf + (size_t)(d % wgk::QBUF_K) * n, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return WGK_OK;
 }
 
@@ -604,11 +724,11 @@ int wgk_vertical_day(wgk_ctx *c, int day, int month, int dom, int slot) {
     int rc = check_ready(c);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    rc = set_calendar(c, day, month, dom, slot);
+    rc = fill_calendar(c, day, month, dom, slot, 1);
     if (rc) return rc;
     rc = ensure_derived(c);
     if (rc) return rc;
-    c->launches += 1 + enqueue_vertical(c, make_params(c));
+    c->launches += enqueue_vertical(c, make_params(c), 0);
     CU(cudaGetLastError());
     return WGK_OK;
 }
@@ -617,25 +737,20 @@ int wgk_routing_day(wgk_ctx *c, int day, int month, int dom) {
     int rc = check_ready(c);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    if (day < 1 || day > 365 || month < 0 || month > 11 || dom < 1 || dom > 31) return fail(c, WGK_ERR_ARG, "bad date");
-    // keep the slot that the vertical step of the same day used
-    int32_t slot = 0;
-    CU(cudaMemcpyAsync(&slot, c->d_cal + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    wgk::k_set_calendar<<<1, 1, 0, c->stream>>>(c->d_cal, day, month, dom, slot);
+    rc = fill_calendar(c, day, month, dom, 0, 1);  // the routing kernels do not read the forcing slot
+    if (rc) return rc;
     rc = ensure_derived(c);
     if (rc) return rc;
-    c->launches += 1 + enqueue_routing(c, make_params(c));
+    c->launches += enqueue_routing(c, make_params(c), 0);
     CU(cudaGetLastError());
-    return WGK_OK;
+    return publish_discharge(c, 0);
 }
 
 int wgk_update_land_area_frac(wgk_ctx *c) {
-    // routingClass::updateLandAreaFrac is fused into the routing sweep (k_route_level /
-    // k_route_tail write prev <- cur <- next per cell); the entry point exists so that the
-    // three-call sequence of integrateWGHM.cpp:779-798 maps one to one.
-    int rc = check_ready(c);
-    return rc;
+    // routingClass::updateLandAreaFrac is fused into the routing post-pass (prev <- cur <- next
+    // per cell); the entry point exists so that the three-call sequence of
+    // integrateWGHM.cpp:779-798 maps one to one.
+    return check_ready(c);
 }
 
 int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays) {
@@ -643,39 +758,29 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
     if (rc) return rc;
     if (ndays <= 0) return WGK_OK;
     CU(cudaSetDevice(c->device));
-    rc = set_calendar(c, day, month, dom, slot0);
+    rc = fill_calendar(c, day, month, dom, slot0, ndays);
     if (rc) return rc;
-    CU(cudaMemsetAsync(c->d_cal + 4, 0, sizeof(int32_t), c->stream));
-    c->launches++;
     rc = ensure_derived(c);
     if (rc) return rc;
     const WgkParams p = make_params(c);
     if (c->opt.use_graph) {
-        if (c->graph_dirty) {
-            drop_graph(c);
-            CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            int n = enqueue_vertical(c, p);
-            n += enqueue_routing(c, p);
-            wgk::k_end_of_day<<<1, 256, 0, c->stream>>>(p);
-            n++;
-            cudaError_t e = cudaStreamEndCapture(c->stream, &c->graph);
-            if (e != cudaSuccess) return fail(c, WGK_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
-            CU(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
-            c->launches_per_day = n;
-            c->graph_dirty = false;
+        auto it = c->graphs.find(ndays);
+        if (it == c->graphs.end()) {
+            cudaGraphExec_t ex;
+            int nn = 0;
+            rc = build_wavefront_graph(c, p, ndays, &ex, &nn);
+            if (rc) return rc;
+            c->graphs[ndays] = ex;
+            c->graph_nodes[ndays] = nn;
+            it = c->graphs.find(ndays);
         }
-        for (int d = 0; d < ndays; d++) CU(cudaGraphLaunch(c->graph_exec, c->stream));
-        c->launches += (int64_t)c->launches_per_day * ndays;
+        CU(cudaGraphLaunch(it->second, c->stream));
+        c->launches += c->graph_nodes[ndays];
     } else {
-        for (int d = 0; d < ndays; d++) {
-            int n = enqueue_vertical(c, p);
-            n += enqueue_routing(c, p);
-            wgk::k_end_of_day<<<1, 256, 0, c->stream>>>(p);
-            c->launches += n + 1;
-        }
+        c->launches += enqueue_wavefront_serial(c, p, ndays);
     }
     CU(cudaGetLastError());
-    return WGK_OK;
+    return publish_discharge(c, ndays - 1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -741,7 +846,7 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     if (rc) return rc;
     if (!ms) return WGK_ERR_ARG;
     CU(cudaSetDevice(c->device));
-    rc = set_calendar(c, day, month, dom, slot);
+    rc = fill_calendar(c, day, month, dom, slot, 1);
     if (rc) return rc;
     rc = ensure_derived(c);
     if (rc) return rc;
@@ -750,20 +855,20 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     const WgkParams p = make_params(c);
     dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
     CU(cudaEventRecord(ev[0], c->stream));
-    wgk::k_vertical<<<grid, block, 0, c->stream>>>(p);
+    wgk::k_vertical<<<grid, block, 0, c->stream>>>(p, 0);
     CU(cudaEventRecord(ev[1], c->stream));
     wgk::k_route_local<<<grid, block, 0, c->stream>>>(p);
     CU(cudaEventRecord(ev[2], c->stream));
-    int n = 4;
+    int n = 3;
     for (int l = 0; l < c->tail_level0; l++) {
         const int cnt = c->level_off[l + 1] - c->level_off[l];
         dim3 g((cnt + 127) / 128, c->nmember);
-        wgk::k_route_level<<<g, block, 0, c->stream>>>(p, l);
+        wgk::k_route_level<<<g, block, 0, c->stream>>>(p, 0, l);
         n++;
     }
     CU(cudaEventRecord(ev[3], c->stream));
     if (c->tail_level0 < c->nlevels) {
-        wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, c->tail_level0);
+        wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, 0, c->tail_level0, c->nlevels);
         n++;
     }
     CU(cudaEventRecord(ev[4], c->stream));
@@ -774,7 +879,7 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
     CU(cudaEventElapsedTime(&ms[5], ev[0], ev[5]));
     for (auto &e : ev) cudaEventDestroy(e);
-    return WGK_OK;
+    return publish_discharge(c, 0);
 }
 
 int64_t wgk_kernel_launches(const wgk_ctx *c) { return c ? c->launches : 0; }

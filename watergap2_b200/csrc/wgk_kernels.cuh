@@ -36,7 +36,9 @@ struct WgkParams {
     const int32_t *up_idx;        // upstream ranks, ascending (= reference accumulation order)
     const int32_t *down;          // [ncell] downstream rank or -1
     const int32_t *level_off;     // [nlevels+1]
-    int32_t *cal;                 // device calendar {day, month, day_in_month, slot, simday}
+    int32_t *cal;                 // base calendar of the current call {day, month, day_in_month, slot}
+    int32_t *cal_days;            // [max days per call][4] {day of year, month, day in month, forcing slot}
+    double *qbuf;                 // [QBUF_K][nmember][stride] river discharge of the days in flight
     const int32_t *gidx;          // [ncell] index into the global-water-body scratch or -1
     double *gbody;                // [nmember][ngbody][GB_N] inflow-independent terms of the day
     int ngbody;
@@ -134,15 +136,11 @@ __device__ __forceinline__ double lai_nogrowing(int &days, int initialDays, int 
 // ----------------------------------------------------------------------------------------
 // vertical water balance
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_vertical(const __grid_constant__ WgkParams p) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int m = blockIdx.y;
-    if (r >= p.ncell) return;
+__device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, const int m, const int slot) {
     const WgkArrays &a = p.a;
     if (!a.contcell[r]) return;  // integrateWGHM.cpp:772
     const size_t i = (size_t)m * p.stride + r;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
-    const int slot = p.cal[3];
 
     // daily.cpp:159-169, routing.h:246-251
     const int started = a.status_laf_next[i];
@@ -450,6 +448,15 @@ __global__ void __launch_bounds__(128) k_vertical(const __grid_constant__ WgkPar
     a.surface_runoff[i] = total_daily_runoff - daily_gw_recharge;
 }
 
+// number of days of river discharge kept in flight (temporal wavefront over the level graph)
+constexpr int QBUF_K = 8;
+
+__global__ void __launch_bounds__(128) k_vertical(const __grid_constant__ WgkParams p, const int dayofs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.ncell) return;
+    vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3]);
+}
+
 // ----------------------------------------------------------------------------------------
 // routing helpers
 // ----------------------------------------------------------------------------------------
@@ -510,10 +517,7 @@ __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ W
 // ----------------------------------------------------------------------------------------
 // cell-parallel pre-pass of the routing day: everything that does not depend on upstream cells
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ WgkParams p) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int m = blockIdx.y;
-    if (r >= p.ncell) return;
+__device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r, const int m) {
     const WgkArrays &a = p.a;
     const size_t i = (size_t)m * p.stride + r;
     a.river_evapo[i] = 0.;  // routing.cpp:1781
@@ -719,6 +723,12 @@ __global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ Wgk
     a.t_gwr_locwet[i] = gwr_locwet;
 }
 
+__global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ WgkParams p) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.ncell) return;
+    route_local_cell(p, r, blockIdx.y);
+}
+
 // ----------------------------------------------------------------------------------------
 // the ordered sweep: only what depends on upstream cells stays on the level-to-level chain
 // ----------------------------------------------------------------------------------------
@@ -877,7 +887,8 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
 // river reach of one cell (routing.cpp:3388-3545), given the inflow-independent context and
 // the sum of upstream discharges; writes discharge / storage and returns nothing
 __device__ __forceinline__ void route_river(const WgkParams &p, const RiverCtx &c, const int r, const int m, const size_t i,
-                                            const size_t q, const double inflowUpstream, const int day, const int month) {
+                                            const size_t q, const double inflowUpstream, const int day, const int month,
+                                            double *__restrict__ qday) {
     const WgkArrays &a = p.a;
     double inflow = c.inflow_local + inflowUpstream;  // :2623
     double gwToRiver = c.gw_to_river;
@@ -919,21 +930,26 @@ __device__ __forceinline__ void route_river(const WgkParams &p, const RiverCtx &
     // (inland sinks have no downstream cell; the reference keeps their river outflow out of the
     //  discharge grid, routing.cpp:4219-4221, and books it as evaporation, :3935-3937)
     const bool out = (c.flags & FL_LDD_OUT) != 0;
-    a.discharge[i] = out ? transportedVolume : 0.;
+    qday[i] = out ? transportedVolume : 0.;
     a.cell_runoff[i] = out ? (transportedVolume - inflowUpstream) : (0. - inflowUpstream);
     a.river_stor[i] = Sr;
     a.river_evapo[i] = riverEvapo;
 }
 
-__device__ __forceinline__ double gather_upstream(const WgkParams &p, const RiverCtx &c, const size_t mb) {
+__device__ __forceinline__ double gather_upstream(const WgkParams &p, const RiverCtx &c, const size_t mb,
+                                                  const double *qday) {
     // upstream inflow in routing order (= order of the += at routing.cpp:3957)
     double s = 0.;
-    for (int k = c.up0; k < c.up1; k++) s += p.a.discharge[mb + p.up_idx[k]];
+    for (int k = c.up0; k < c.up1; k++) s += qday[mb + p.up_idx[k]];
     return s;
 }
 
-// one dependency level per launch (wide levels)
-__global__ void __launch_bounds__(128) k_route_level(const __grid_constant__ WgkParams p, const int level) {
+__device__ __forceinline__ double *qbuf_of_day(const WgkParams &p, const int dayofs) {
+    return p.qbuf + (size_t)(dayofs % QBUF_K) * p.nmember * p.stride;
+}
+
+// one dependency level per launch (wide levels), routing sweep only
+__global__ void __launch_bounds__(128) k_route_level(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
     const int begin = p.level_off[level], end = p.level_off[level + 1];
     const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= end) return;
@@ -942,33 +958,34 @@ __global__ void __launch_bounds__(128) k_route_level(const __grid_constant__ Wgk
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
     const RiverCtx c = load_ctx(p, r, mb + r, q);
     if (!(c.flags & FL_ACTIVE)) return;
-    route_river(p, c, r, m, mb + r, q, gather_upstream(p, c, mb), p.cal[0], p.cal[1]);
+    double *qday = qbuf_of_day(p, dayofs);
+    route_river(p, c, r, m, mb + r, q, gather_upstream(p, c, mb, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
 }
 
-// all levels from `level0` on inside one persistent CTA per member; levels are separated by
+// levels [level_lo, level_hi) inside one persistent CTA per member; levels are separated by
 // __syncthreads(), which also orders the global-memory hand-off of the discharge values.  The
 // context of the next level's cell is loaded BEFORE the barrier so that only the gather of the
 // upstream discharges and the river arithmetic remain on the level-to-level critical path.
-__global__ void __launch_bounds__(256) k_route_tail(const __grid_constant__ WgkParams p, const int level0) {
-    const int m = blockIdx.x;
-    const int day = p.cal[0], month = p.cal[1];
+__device__ __forceinline__ void sweep_levels(const WgkParams &p, const int m, const int dayofs, const int level_lo, const int level_hi) {
+    const int day = p.cal_days[4 * dayofs], month = p.cal_days[4 * dayofs + 1];
+    double *qday = qbuf_of_day(p, dayofs);
     const size_t mb = (size_t)m * p.stride;
     const size_t qb = (size_t)p.member_pset[m] * p.stride;
-    int begin = p.level_off[level0], end = p.level_off[level0 + 1];
+    int begin = p.level_off[level_lo], end = p.level_off[level_lo + 1];
     int r = begin + threadIdx.x;
     RiverCtx c;
     c.flags = 0;
     if (r < end) c = load_ctx(p, r, mb + r, qb + r);
-    for (int level = level0; level < p.nlevels; level++) {
+    for (int level = level_lo; level < level_hi; level++) {
         if (r < end) {
-            if (c.flags & FL_ACTIVE) route_river(p, c, r, m, mb + r, qb + r, gather_upstream(p, c, mb), day, month);
+            if (c.flags & FL_ACTIVE) route_river(p, c, r, m, mb + r, qb + r, gather_upstream(p, c, mb, qday), day, month, qday);
             // levels wider than the CTA (only possible when the tail threshold is raised)
             for (int r2 = r + blockDim.x; r2 < end; r2 += blockDim.x) {
                 const RiverCtx c2 = load_ctx(p, r2, mb + r2, qb + r2);
-                if (c2.flags & FL_ACTIVE) route_river(p, c2, r2, m, mb + r2, qb + r2, gather_upstream(p, c2, mb), day, month);
+                if (c2.flags & FL_ACTIVE) route_river(p, c2, r2, m, mb + r2, qb + r2, gather_upstream(p, c2, mb, qday), day, month, qday);
             }
         }
-        if (level + 1 < p.nlevels) {
+        if (level + 1 < level_hi) {
             begin = end;
             end = p.level_off[level + 2];
             r = begin + threadIdx.x;
@@ -979,15 +996,16 @@ __global__ void __launch_bounds__(256) k_route_tail(const __grid_constant__ WgkP
     }
 }
 
+__global__ void __launch_bounds__(256) k_route_tail(const __grid_constant__ WgkParams p, const int dayofs, const int level_lo, const int level_hi) {
+    sweep_levels(p, blockIdx.x, dayofs, level_lo, level_hi);
+}
+
 // ----------------------------------------------------------------------------------------
 // cell-parallel post-pass: river width / area fraction of the next day (:3546-3586), surface
 // water body fractions and next-day land area fraction (:5034-5188), updateLandAreaFrac
 // (:5343-5352)
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkParams p) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int m = blockIdx.y;
-    if (r >= p.ncell) return;
+__device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r, const int m) {
     const WgkArrays &a = p.a;
     const size_t i = (size_t)m * p.stride + r;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
@@ -1088,37 +1106,80 @@ __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkP
     a.land_area_frac[i] = laf_next;
 }
 
+__global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkParams p) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.ncell) return;
+    route_post_cell(p, r, blockIdx.y);
+}
+
+// ----------------------------------------------------------------------------------------
+// temporal wavefront: one kernel per (day, dependency level).  A cell of level l on day d needs
+// its own state of day d-1 and the discharge of its upstream cells (levels < l) of day d, so
+// (d, l), (d+1, l-1), (d+2, l-2) ... are independent and run concurrently as branches of one
+// CUDA graph; the level-to-level latency chain of a day is hidden behind the work of the
+// following days instead of serialising the run.
+// ----------------------------------------------------------------------------------------
+// whole day of the cells of one wide level: vertical balance, local routing, river reach, post
+__global__ void __launch_bounds__(128) k_day_level(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
+    const int begin = p.level_off[level], end = p.level_off[level + 1];
+    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= end) return;
+    const int m = blockIdx.y;
+    vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3]);
+    route_local_cell(p, r, m);
+    const size_t mb = (size_t)m * p.stride;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const RiverCtx c = load_ctx(p, r, mb + r, q);
+    if (c.flags & FL_ACTIVE) {
+        double *qday = qbuf_of_day(p, dayofs);
+        route_river(p, c, r, m, mb + r, q, gather_upstream(p, c, mb, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
+    }
+    route_post_cell(p, r, m);
+}
+
+// vertical balance + local routing of the cells [begin, end) (the cells of one tail chunk)
+__global__ void __launch_bounds__(128) k_cells_pre(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
+    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= end) return;
+    vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3]);
+    route_local_cell(p, r, blockIdx.y);
+}
+
+// narrow levels [level_lo, level_hi) of one day in one persistent CTA per member, then the
+// post-pass of those cells
+__global__ void __launch_bounds__(256) k_tail_chunk(const __grid_constant__ WgkParams p, const int dayofs, const int level_lo, const int level_hi) {
+    const int m = blockIdx.x;
+    sweep_levels(p, m, dayofs, level_lo, level_hi);
+    for (int r = p.level_off[level_lo] + threadIdx.x; r < p.level_off[level_hi]; r += blockDim.x) route_post_cell(p, r, m);
+}
+
 // ----------------------------------------------------------------------------------------
 // calendar, forcing, diagnostics
 // ----------------------------------------------------------------------------------------
-__global__ void k_set_calendar(int32_t *cal, int day, int month, int dom, int slot) {
-    cal[0] = day; cal[1] = month; cal[2] = dom; cal[3] = slot;
-}
-
-// end of a simulated day: record station discharge, then advance the device calendar
-// (365-day years, integrateWGHM.cpp:100-102)
-__global__ void k_end_of_day(const __grid_constant__ WgkParams p) {
-    int32_t *cal = p.cal;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int simday = cal[4];
-    if (p.record && simday < p.record_max_days) {
-        const int total = p.nmember * p.nrec;
-        for (int k = t; k < total; k += gridDim.x * blockDim.x) {
-            const int m = k / p.nrec, c = k % p.nrec;
-            p.record[(size_t)simday * total + k] = p.a.discharge[(size_t)m * p.stride + p.record_cells[c]];
-        }
-    }
-    __syncthreads();
-    if (t == 0) {
-        const int ndays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
-        int day = cal[0], month = cal[1], dom = cal[2], slot = cal[3];
+// calendar of the `ndays` days of one call, starting at (day, month, day_in_month, slot);
+// 365-day years (integrateWGHM.cpp:100-102), forcing slots cycle through the reserved ones
+__global__ void k_fill_calendar(int32_t *cal_days, int day, int month, int dom, int slot, int ndays, int nslots) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int nd[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    for (int d = 0; d < ndays; d++) {
+        cal_days[4 * d] = day; cal_days[4 * d + 1] = month; cal_days[4 * d + 2] = dom; cal_days[4 * d + 3] = slot;
         dom++;
         day++;
-        if (dom > ndays[month]) { dom = 1; month++; }
+        if (dom > nd[month]) { dom = 1; month++; }
         if (month > 11) { month = 0; day = 1; }
         slot++;
-        if (slot >= p.forcing_nslots) slot = 0;
-        cal[0] = day; cal[1] = month; cal[2] = dom; cal[3] = slot; cal[4] = simday + 1;
+        if (slot >= nslots) slot = 0;
+    }
+}
+
+// end of a simulated day: record the discharge of the station cells
+__global__ void k_end_of_day(const __grid_constant__ WgkParams p, const int dayofs) {
+    if (!p.record || dayofs >= p.record_max_days) return;
+    const double *qday = qbuf_of_day(p, dayofs);
+    const int total = p.nmember * p.nrec;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        const int m = k / p.nrec, cidx = k % p.nrec;
+        p.record[(size_t)dayofs * total + k] = qday[(size_t)m * p.stride + p.record_cells[cidx]];
     }
 }
 
