@@ -31,10 +31,10 @@ def rel_err(name, a, b):
     return np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor_of(name))
 
 
-def assert_parity(name, ref, got, rtol=RTOL, max_flips=0):
+def assert_parity(name, ref, got, rtol=RTOL, max_flips=0, outlier_rtol=1e-6):
     """Integer fields bit-exact; floating point within rtol except for at most `max_flips`
-    cells (threshold flips: snow>3 mm albedo switch, 1000 mm cap, ... SURVEY.md hard parts),
-    which are reported."""
+    cells (free runs only: cells whose dynamics amplify ulp noise), which must
+    still be within `outlier_rtol`."""
     ref = np.asarray(ref)
     got = np.asarray(got)
     assert ref.shape == got.shape, (name, ref.shape, got.shape)
@@ -44,7 +44,7 @@ def assert_parity(name, ref, got, rtol=RTOL, max_flips=0):
         return 0
     e = rel_err(name, ref, got)
     bad = np.nonzero(~(e <= rtol))[0]
-    if bad.size > max_flips:
+    if bad.size > max_flips or (bad.size and not (e[bad] <= outlier_rtol).all()):
         k = bad[np.argmax(e[bad])]
         raise AssertionError(f"{name}: {bad.size} cells beyond rtol={rtol:g} (allowed {max_flips}); worst cell {k}: "
                              f"ref {ref[k]!r} got {got[k]!r} rel {e[k]:.3e}")
