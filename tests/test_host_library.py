@@ -1,0 +1,128 @@
+"""The C++ drop-in layer (watergap2_b200/csrc/host -> libwghost.so): flow topology builder,
+checkpoint file codecs (CPU) and the integrate_wghm-shaped driver over the C ABI (GPU)."""
+import ctypes
+import filecmp
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+LIB = os.path.join(ROOT, "watergap2_b200", "libwghost.so")
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness_3000")
+
+
+@pytest.fixture(scope="module")
+def host():
+    if not os.path.exists(LIB):
+        import watergap2_b200 as wg
+        wg.build()
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "watergap2_b200", "csrc", "host")])
+    L = ctypes.CDLL(LIB)
+    L.wg_host_integrate.restype = ctypes.c_long
+    L.wg_host_integrate.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_char_p, ctypes.c_size_t]
+    L.wg_host_prepare_routing_files.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_size_t]
+    L.wg_host_state_roundtrip.argtypes = [ctypes.c_char_p] * 3 + [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
+    return L
+
+
+def test_flow_topology_files_byte_identical_to_reference(host, golden, world1000, tmp_path):
+    """prepare_routing_files of the product writes the same bytes as the reference's
+    rout_prepare.cpp did for the golden world (G_ROUT_ORDER, G_INFLC.9, G_OUTFLC, basins ...)."""
+    from oracle import synth_world as sw
+    sw.write_world(world1000, str(tmp_path), (1901, 1901), (1, 1))
+    rd = tmp_path / "routing"
+    err = ctypes.create_string_buffer(512)
+    nlev = ctypes.c_int()
+    rc = host.wg_host_prepare_routing_files(str(tmp_path / "input").encode(), str(rd).encode(), 1, 1000, ctypes.byref(nlev), err, 512)
+    assert rc == 0, err.value
+    for fname, dt in [("G_LDD_2.UNF1", "i1"), ("G_INFLC.9.UNF4", "i4"), ("G_FLOW_ACC.UNF2", "i2"), ("G_CELLS_TO_OUTLET.UNF2", "u2"),
+                      ("G_BASINS.UNF2", "u2"), ("G_BASINS_2.UNF2", "u2"), ("G_OUTFLC.UNF4", "i4"), ("G_ROUT_ORDER.UNF4", "i4"),
+                      ("G_RIVERSLOPE.UNF0", "f4"), ("G_RIVER_LENGTH.UNF0", "f4"), ("G_ALLOC_COEFF.5.UNF0", "f4"), ("G_START_MONTH.UNF1", "i1")]:
+        got = np.fromfile(rd / fname, dtype=np.dtype(dt).newbyteorder(">")).astype(dt)
+        assert np.array_equal(golden["routing/" + fname], got), fname
+    assert nlev.value > 5
+
+
+def test_empty_and_cyclic_flow_directions(host, tmp_path):
+    """edge cases of the topology builder: a world whose cells all drain to the ocean (every
+    cell its own basin, one level) and a two-cell loop, which rout_prepare.cpp:164-177 breaks."""
+    from oracle import synth_world as sw, wgo
+    w = sw.build_world(1000)
+    w.flowdir[:] = 0
+    t = wgo.rout_prepare(w.flowdir, w.row, w.col, w.gcrc.T)
+    assert t["nlevels"] == 1 and (t["basins2"] == 0).all() and sorted(t["rout_order"]) == list(range(1, 1001))
+    sw.write_world(w, str(tmp_path), (1901, 1901), (1, 1))
+    err = ctypes.create_string_buffer(512)
+    nlev = ctypes.c_int()
+    assert host.wg_host_prepare_routing_files(str(tmp_path / "input").encode(), str(tmp_path / "routing").encode(), 1, 1000, ctypes.byref(nlev), err, 512) == 0
+    assert nlev.value == 1
+    ro = np.fromfile(tmp_path / "routing" / "G_ROUT_ORDER.UNF4", dtype=">i4")
+    assert np.array_equal(ro, t["rout_order"])
+    # two horizontally adjacent cells pointing at each other
+    n = int(np.nonzero((w.col[:-1] + 1 == w.col[1:]) & (w.row[:-1] == w.row[1:]))[0][0])
+    w.flowdir[n], w.flowdir[n + 1] = 1, 16
+    t2 = wgo.rout_prepare(w.flowdir, w.row, w.col, w.gcrc.T)
+    assert t2["ldd"][n] == 5 and t2["ldd"][n + 1] == 5 and t2["ldd_2"][n] == 6
+    sw.write_world(w, str(tmp_path), (1901, 1901), (1, 1))
+    assert host.wg_host_prepare_routing_files(str(tmp_path / "input").encode(), str(tmp_path / "routing").encode(), 1, 1000, ctypes.byref(nlev), err, 512) == 0
+    assert np.array_equal(np.fromfile(tmp_path / "routing" / "G_ROUT_ORDER.UNF4", dtype=">i4"), t2["rout_order"])
+
+
+def _ref_outputs(tmp, world, months):
+    from oracle import synth_world as sw
+    sw.write_world(world, tmp, (1901, 1901), (1, months))
+    log = open(os.path.join(tmp, "driver.log"), "w")
+    subprocess.check_call([HARNESS, "driver", os.path.join(tmp, "config.txt")], stdout=log, stderr=log, cwd=tmp)
+    out = os.path.join(tmp, "output")
+    keep = {}
+    for k in ("wghm_state_lastday.txt", "snow_lastday.txt", "additional_lastday.txt"):
+        os.rename(os.path.join(out, k), os.path.join(out, "ref_" + k))
+        keep[k] = os.path.join(out, "ref_" + k)
+    return keep
+
+
+def test_checkpoint_codecs_round_trip_reference_files(host, world3000, tmp_path):
+    """files written by the compiled reference, read and re-written by the product's codecs:
+    the state and snow files come back byte-identical, the additional file value-identical."""
+    if not os.path.exists(HARNESS):
+        pytest.skip("compiled reference not available")
+    ref = _ref_outputs(str(tmp_path), world3000, 1)
+    err = ctypes.create_string_buffer(512)
+    for kind, key in (("state", "wghm_state_lastday.txt"), ("snow", "snow_lastday.txt"), ("additional", "additional_lastday.txt")):
+        out = str(tmp_path / ("rt_" + key))
+        assert host.wg_host_state_roundtrip(kind.encode(), ref[key].encode(), out.encode(), 3000, err, 512) == 0, err.value
+        if kind == "additional":  # header labels differ, numbers must not
+            a = np.loadtxt(ref[key], skiprows=2)
+            b = np.loadtxt(out, skiprows=2)
+            assert np.array_equal(a, b)
+        else:
+            assert filecmp.cmp(ref[key], out, shallow=False), kind
+
+
+@pytest.mark.gpu
+def test_host_driver_matches_reference_driver(host, world3000, tmp_path):
+    """end to end drop-in: the same config.txt / OPTIONS.DAT / UNF inputs through (a) the
+    reference's initialize_wghm + integrate_wghm and (b) the C++ look-alike classes over the
+    C ABI; the final wghm state and snow-band files must agree (31-day free run)."""
+    if not os.path.exists(HARNESS):
+        pytest.skip("compiled reference not available")
+    from tests.util import rel_err
+    ref = _ref_outputs(str(tmp_path), world3000, 1)
+    err = ctypes.create_string_buffer(1024)
+    secs = ctypes.c_double()
+    nd = host.wg_host_integrate(str(tmp_path / "config.txt").encode(), 3000, 0, ctypes.byref(secs), err, 1024)
+    assert nd == 31, err.value
+    out = tmp_path / "output"
+    a = np.loadtxt(ref["wghm_state_lastday.txt"], skiprows=2)
+    b = np.loadtxt(out / "wghm_state_lastday.txt", skiprows=2)
+    assert a.shape == b.shape == (3000, 12)
+    assert np.array_equal(a[:, 0], b[:, 0])
+    e = np.abs(a[:, 1:] - b[:, 1:]) / np.maximum(np.maximum(np.abs(a[:, 1:]), np.abs(b[:, 1:])), 1.0)  # mm over the continental area
+    assert (e <= 1e-10).mean() > 0.995 and e.max() < 1e-6, (float(e.max()), float((e > 1e-10).mean()))
+    sa = np.loadtxt(ref["snow_lastday.txt"], skiprows=1)
+    sb = np.loadtxt(out / "snow_lastday.txt", skiprows=1)
+    es = np.abs(sa - sb) / np.maximum(np.maximum(np.abs(sa), np.abs(sb)), 1.0)
+    assert (es <= 1e-10).mean() > 0.995 and es.max() < 1e-6

@@ -1,0 +1,684 @@
+// wg_model.cpp — see wg_model.h.  Host-side drop-in layer over the C ABI (include/wgk.h).
+#include "wg_model.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+namespace wg {
+
+// ------------------------------------------------------------------------------------------
+// parameters / config / options
+// ------------------------------------------------------------------------------------------
+static const char *kParamNames[26] = {  // calib_param.cpp:140-171
+    "gammaHBV_runoff_coeff", "CFA_cellCorrFactor", "CFS_statCorrFactor", "root_depth_multiplier",
+    "river_roughness_coeff_mult", "lake_depth", "wetland_depth", "surfacewater_outflow_coefficient",
+    "evapo_red_fact_exp_mult", "net_radiation_mult", "PT_coeff_humid", "PT_coeff_arid", "max_daily_PET", "mcwh",
+    "LAI_mult", "snow_freeze_temp", "snow_melt_temp", "degree_day_factor_mult", "temperature_gradient", "gw_factor_mult",
+    "rg_max_mult", "pcrit_aridgw", "groundwater_outflow_coeff", "net_abstraction_surfacewater_mult",
+    "net_abstraction_groundwater_mult", "precip_mult"};
+
+void calibParamClass::readJson(const std::string &file, int ncell) {
+    // The parameter file is one JSON object of "name": number | [numbers]; a full DOM is not
+    // needed (and is what makes getValue() slow in the reference, calib_param.h:131-222).
+    std::ifstream f(file, std::ios::binary);
+    if (!f) throw std::runtime_error("Unable to open file '" + file + "'");
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string txt = ss.str();
+    ncell_ = ncell;
+    v_.assign((size_t)26 * ncell, 0.0);
+    auto find_key = [&](const std::string &key) -> size_t {
+        const std::string q = "\"" + key + "\"";
+        size_t p = txt.find(q);
+        if (p == std::string::npos) return p;
+        p = txt.find(':', p + q.size());
+        return p == std::string::npos ? p : p + 1;
+    };
+    size_t p = find_key("ng_param");
+    if (p == std::string::npos) throw std::runtime_error("ERROR readJson(): calibParamJson.is_object() == false");
+    const int ng_file = (int)strtod(txt.c_str() + p, nullptr);
+    if (ng_file != ncell)
+        throw std::runtime_error("ERROR readJson(): Predefined number of grid cells " + std::to_string(ncell) +
+                                 " does not match number found in JSON object header " + std::to_string(ng_file));
+    for (int k = 0; k < 26; k++) {
+        p = find_key(kParamNames[k]);
+        if (p == std::string::npos) continue;  // missing parameters read as 0, like the reference's DOM lookup
+        p = txt.find('[', p);
+        const char *s = txt.c_str() + p + 1;
+        for (int n = 0; n < ncell; n++) {
+            char *e;
+            v_[(size_t)k * ncell + n] = strtod(s, &e);
+            s = e;
+            while (*s == ',' || *s == ' ' || *s == '\n') s++;
+        }
+    }
+}
+
+ConfigFile::ConfigFile(const std::string &file) {
+    std::ifstream f(file);
+    if (!f) throw std::runtime_error("error by opening file " + file);
+    std::string line;
+    while (std::getline(f, line)) {
+        std::stringstream ss(line);
+        std::string tag;
+        if (!(ss >> tag) || tag[0] == '#') continue;
+        if (tag == "end_of_head") break;
+        std::map<std::string, std::string *> str = {
+            {"wghm_state", &startvaluefile}, {"param_json", &parameterfile}, {"snowInElevation_startvalues", &snowInElevationfile},
+            {"additionalOutIn_startvalues", &additionalfile}, {"output_state_mean", &outputmeanfile},
+            {"output_state_lastday", &outputlastdayfile}, {"output_snowInElevation_lastday", &outputsnowlastdayfile},
+            {"additionalOutIn_lastday", &outputadditionalfile}, {"runtime_options", &runtimeoptionsfile},
+            {"output_options", &outputoptionsfile}, {"routing", &routingoptionsfile}, {"stations", &stationsfile},
+            {"input_dir", &inputDir}, {"output_dir", &outputDir}, {"climate_dir", &climateDir}, {"routing_dir", &routingDir}};
+        std::map<std::string, int *> num = {{"start_month", &startMonth}, {"start_year", &startYear}, {"end_month", &endMonth},
+                                            {"end_year", &endYear}, {"time_step", &timeStep}, {"num_init_years", &numInitYears}};
+        if (str.count(tag)) ss >> *str[tag];
+        else if (num.count(tag)) ss >> *num[tag];
+    }
+}
+
+void optionClass::init(const ConfigFile &cfg) {
+    // defaults of option.cpp:120-165
+    const int def[36] = {2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 2000, 1900, 2010, 0, 1971, 2000, 0, 0};
+    std::memcpy(v, def, sizeof v);
+    std::ifstream f(cfg.runtimeoptionsfile);
+    std::string line;
+    int i = 0;
+    while (f && std::getline(f, line))
+        if (line.compare(0, 6, "Value:") == 0 && i < 36) v[i++] = atoi(line.c_str() + 7);
+    input_dir = cfg.inputDir; output_dir = cfg.outputDir; climate_dir = cfg.climateDir; routing_dir = cfg.routingDir;
+    start_year = cfg.startYear; end_year = cfg.endYear;
+}
+
+void optionClass::require_canonical() const {
+    struct { int idx, want; const char *name; } req[] = {
+        {5, 0, "time_series"}, {6, 1, "cloud"}, {7, 1, "intercept"}, {8, 0, "calc_albedo"}, {9, 0, "petOpt"}, {10, 1, "use_kc"},
+        {14, 1, "riverveloOpt"}, {15, 0, "subtract_use"}, {18, 0, "clclOpt"}, {20, 1, "resOpt"}, {21, 0, "statcorrOpt"},
+        {22, 1, "aridareaOpt"}, {23, 1, "fractionalRoutingOpt"}, {24, 1, "riverEvapoOpt"}, {27, 0, "resYearOpt"},
+        {31, 0, "antNatOpt"}, {34, 0, "calc_wtemp"}, {35, 0, "glacierOpt"}, {1, 1, "basin"}};
+    for (auto &r : req)
+        if (v[r.idx] != r.want)
+            throw std::runtime_error(std::string("option ") + r.name + " = " + std::to_string(v[r.idx]) +
+                                     " is outside the implemented hot path (canonical value " + std::to_string(r.want) + ")");
+}
+
+void geoClass::init(const std::string &in, int ncell, int resOpt) {  // geo.cpp:7-45
+    std::vector<float> a(360);
+    read_unf_raw(in + "/GAREA.UNF0", a.data(), a.size());
+    area.assign(a.begin(), a.end());
+    G_row.initialize(ncell); G_col.initialize(ncell); G_contcell.initialize(ncell); G_contfreq.initialize(ncell);
+    G_row.read(in + "/GR.UNF2");
+    G_col.read(in + "/GC.UNF2");
+    G_contfreq.read(in + "/GCONTFREQ.UNF0");
+    Grid<double> fw(ncell), tmp(ncell);
+    for (const char *nm : {"/G_LOCLAK.UNF0", "/G_GLOLAK.UNF0"}) { tmp.read(in + nm); for (int n = 0; n < ncell; n++) fw[n] += tmp[n]; }
+    if (resOpt == 1)
+        for (const char *nm : {"/G_LOCRES.UNF0", "/G_RES/G_RES_FRAC.UNF0"}) { tmp.read(in + nm); for (int n = 0; n < ncell; n++) fw[n] += tmp[n]; }
+    for (int n = 0; n < ncell; n++) {
+        if (fw[n] > G_contfreq[n]) G_contfreq[n] = fw[n];
+        G_contcell[n] = (G_contfreq[n] < 0.000001) ? 0 : 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------
+Engine::Engine(int nc, int device) : ncell(nc), dailyWaterBalance(*this), routing(*this) {
+    wgk_options opt{0, 0, 1};
+    check(wgk_create(&ctx, device, ncell, 1, 1, &opt), "wgk_create");
+}
+Engine::~Engine() { wgk_destroy(ctx); }
+
+void Engine::check(int rc, const char *what) {
+    if (rc != 0) throw std::runtime_error(std::string(what) + ": " + (ctx ? wgk_last_error(ctx) : "no CUDA device (wgk has no CPU fallback)"));
+}
+template <class T, int C> void Engine::set(const char *name, const Grid<T, C> &g, int index) {
+    check(wgk_set_field(ctx, wgk_field_id(name), index, g.data(), g.size() * sizeof(T)), name);
+}
+template <class T, int C> void Engine::get(const char *name, Grid<T, C> &g, int index) {
+    if (!g.initialized()) g.initialize(ncell);
+    check(wgk_get_field(ctx, wgk_field_id(name), index, g.data(), g.size() * sizeof(T)), name);
+}
+
+void Engine::land_init() {
+    G_built_up.initialize(ncell); G_landCover.initialize(ncell);
+    G_built_up.read(options.input_dir + "/GBUILTUP.UNF0");
+    G_landCover.read(options.input_dir + "/G_LANDCOVER.UNF1");
+}
+
+static void skip_comments(std::ifstream &f) {
+    std::string line;
+    while (f && f.peek() == '#') std::getline(f, line);
+}
+
+void dailyWaterBalanceClass::init(const std::string &input_dir, short) {  // readLCTdata, daily.cpp:1925-1959
+    std::ifstream f(input_dir + "/LCT_22.DAT");
+    if (!f) throw std::runtime_error("Can not open file " + input_dir + "/LCT_22.DAT for reading.");
+    skip_comments(f);
+    for (int i = 0; i < 18; i++) {
+        int idx;
+        f >> idx >> rootingDepth_lct[i] >> albedo_lct[i] >> albedoSnow_lct[i] >> ddf_lct[i] >> emissivity_lct[i];
+        if (idx - 1 != i) throw std::runtime_error("Problem with LCT_22.DAT");
+    }
+    const int ng = eng.ncell;
+    for (auto *g : {&G_gammaHBV, &G_cellCorrFact, &G_snow, &G_soilWaterContent, &G_canopyWaterContent, &G_lakeBalance, &G_openWaterPET,
+                    &G_openWaterPrec, &G_dailyLocalSurfaceRunoff, &G_dailyGwRecharge, &G_dailyStorageTransfer})
+        g->initialize(ng);
+    G_Elevation.initialize(ng);
+    G_SnowInElevation.initialize(ng);
+}
+
+void Engine::lai_init() {  // lai.cpp:40-148
+    std::ifstream f(options.input_dir + "/LAI_22.DAT");
+    if (!f) throw std::runtime_error("Can not open file " + options.input_dir + "/LAI_22.DAT for reading.");
+    skip_comments(f);
+    float LeafAreaIndex[18], decid[18], evergreen[18];
+    for (int i = 0; i < 18; i++) {
+        int idx;
+        f >> idx >> LeafAreaIndex[i] >> decid[i] >> evergreen[i] >> lai_initialDays[i] >> kc_min[i] >> kc_max[i];
+        if (idx - 1 != i) throw std::runtime_error("Problem with LAI_22.DAT");
+    }
+    G_LAImax.initialize(ncell);
+    for (int n = 0; n < ncell; n++) G_LAImax[n] = calParam.getValue(M_LAI, n) * LeafAreaIndex[G_landCover[n] - 1];
+    for (int i = 0; i < 18; i++) {
+        lai_factor_a[i] = 0.1 * decid[i];
+        lai_factor_b[i] = (1 - decid[i]) * evergreen[i];
+    }
+    lai_days.initialize(ncell); lai_status.initialize(ncell); lai_precsum.initialize(ncell);
+}
+
+void Engine::createMaxSoilWaterCapacityGrid() {  // s_max.cpp:40-75
+    Grid<float> G_TAWC(ncell);
+    G_TAWC.read(options.input_dir + "/G_TAWC.UNF0");
+    G_Smax.initialize(ncell);
+    for (int n = 0; n < ncell; n++) {
+        const float rootDepth = calParam.getValue(M_ROOT_D, n) * (double)dailyWaterBalance.rootingDepth_lct[G_landCover[n] - 1];
+        if (G_TAWC[n] < 0) G_Smax[n] = -9999;
+        else G_Smax[n] = G_TAWC[n] * rootDepth;
+    }
+}
+
+void Engine::createGroundwaterGrids() {  // gw_frac.cpp:36-275
+    const std::string in = options.input_dir;
+    Grid<int8_t> slope_class(ncell), permaglac(ncell), aquifer(ncell);
+    slope_class.read(in + "/G_SLOPE_CLASS.UNF1");
+    G_texture.initialize(ncell);
+    G_texture.read(in + "/G_TEXTURE.UNF1");
+    permaglac.read(in + "/G_PERMAGLAC.UNF1");
+    aquifer.read(in + "/G_AQ_FACTOR.UNF1");
+    Grid<float> slope_factor(ncell), texture_factor(ncell), Rgmax_f(ncell), corr(ncell);
+    const short slope_class_table[7] = {10, 20, 30, 40, 50, 60, 70};
+    const float slope_factor_table[7] = {1.00, 0.95, 0.90, 0.75, 0.60, 0.30, 0.15};
+    for (int n = 0; n < ncell; n++) {
+        if (slope_class[n] == 0) slope_class[n] = 10;
+        if (slope_class_table[6] == slope_class[n]) { slope_factor[n] = slope_factor_table[6]; continue; }
+        for (short i = 0; i <= 5; i++) {
+            if (slope_class_table[i] == slope_class[n]) { slope_factor[n] = slope_factor_table[i]; break; }
+            if (slope_class[n] > slope_class_table[i] && slope_class[n] < slope_class_table[i + 1]) {
+                slope_factor[n] = slope_factor_table[i] + (((slope_factor_table[i + 1] - slope_factor_table[i]) / (slope_class_table[i + 1] - slope_class_table[i])) * (slope_class[n] - slope_class_table[i]));
+                break;
+            }
+        }
+    }
+    const short texture_table[3] = {10, 20, 30};
+    float Rgmax_table[3] = {5., 3., 1.5};
+    const float Rgmax_tableWFD[3] = {7., 4.5, 2.5};
+    if (0 == options.time_series) for (int i = 0; i < 3; i++) Rgmax_table[i] = Rgmax_tableWFD[i];
+    const float texture_factor_table[3] = {1, 0.95, 0.70};
+    for (int n = 0; n < ncell; n++) {
+        const double M_RG_MAX = calParam.getValue(wg::M_RG_MAX, n);
+        if (G_texture[n] <= 0 || 2 == G_texture[n]) { texture_factor[n] = 0.95; Rgmax_f[n] = 3; continue; }
+        if (1 == G_texture[n]) { texture_factor[n] = 0; Rgmax_f[n] = 0; continue; }
+        for (short i = 0; i <= 2; i++) {
+            if (texture_table[i] == G_texture[n]) { texture_factor[n] = texture_factor_table[i]; Rgmax_f[n] = M_RG_MAX * Rgmax_table[i]; break; }
+            if (i < 2 && G_texture[n] > texture_table[i] && G_texture[n] < texture_table[i + 1]) {
+                texture_factor[n] = texture_factor_table[i] + (((texture_factor_table[i + 1] - texture_factor_table[i]) / (texture_table[i + 1] - texture_table[i])) * (G_texture[n] - texture_table[i]));
+                Rgmax_f[n] = (M_RG_MAX * Rgmax_table[i]) + ((M_RG_MAX * (Rgmax_table[i + 1] - Rgmax_table[i]) / (texture_table[i + 1] - texture_table[i])) * (G_texture[n] - texture_table[i]));
+                break;
+            }
+        }
+    }
+    G_gwFactor.initialize(ncell);
+    for (int n = 0; n < ncell; n++) {
+        if (texture_factor[n] < 0) { G_gwFactor[n] = -99; continue; }
+        float slopeFactor = slope_factor[n], textureFactor = texture_factor[n];
+        float aquiferFactor = (short)aquifer[n] / 100.0;
+        float permaFactor = 1. - (((float)permaglac[n] / 100.));
+        auto clamp = [](float x) { return x < 0 ? 0.f : (x > 1 ? 1.f : x); };
+        slopeFactor = clamp(slopeFactor); aquiferFactor = clamp(aquiferFactor); textureFactor = clamp(textureFactor); permaFactor = clamp(permaFactor);
+        G_gwFactor[n] = calParam.getValue(M_GW_F, n) * slopeFactor * textureFactor * aquiferFactor * permaFactor;
+        if (G_gwFactor[n] > 1.) G_gwFactor[n] = 0.95;
+    }
+    G_Rgmax.initialize(ncell);
+    for (int n = 0; n < ncell; n++) G_Rgmax[n] = (Rgmax_f[n] >= 0) ? (short)floor(Rgmax_f[n] * 100 + 0.5) : -9999;
+    corr.read(in + "/G_GW_FACTOR_CORR.UNF0");
+    for (int n = 0; n < ncell; n++)
+        if (corr[n] > 0.) {
+            G_gwFactor[n] = calParam.getValue(M_GW_F, n) * corr[n];
+            if (G_gwFactor[n] > 1.) G_gwFactor[n] = 0.95;
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// routing class
+// ------------------------------------------------------------------------------------------
+void routingClass::init(short, const ConfigFile &) {  // routing.cpp:131-742 (canonical: antNatOpt 0, resOpt 1)
+    const int ng = eng.ncell;
+    const std::string in = eng.options.input_dir, rd = eng.options.routing_dir;
+    for (auto *g : {&G_statCorrFact, &G_landAreaFrac, &G_landAreaFracNextTimestep, &G_landAreaFracPrevTimestep, &G_locLakeStorage,
+                    &G_locWetlStorage, &G_gloLakeStorage, &G_gloWetlStorage, &G_gloResStorage, &G_riverStorage, &G_groundwaterStorage,
+                    &G_locLakeAreaReductionFactor, &G_locWetlAreaReductionFactor, &G_gloLakeEvapoReductionFactor,
+                    &G_gloWetlAreaReductionFactor, &G_gloResEvapoReductionFactor, &G_riverAreaReductionFactor, &G_glo_lake, &G_loc_lake,
+                    &G_loc_res, &G_glo_wetland, &G_loc_wetland, &G_reg_lake, &G_glo_res, &G_glores_prevyear, &G_lake_area,
+                    &G_reservoir_area, &G_reservoir_area_full, &G_stor_cap, &G_stor_cap_full, &G_mean_outflow, &G_mean_demand,
+                    &G_riverLength, &G_RiverSlope, &G_Roughness, &G_bankfull_flow, &G_RiverWidth_bf, &G_RiverDepth_bf,
+                    &G_riverBottomWidth, &G_riverStorageMax, &G_lakeDepthActive, &G_wetlDepthActive, &G_fswbInit, &G_fswbLandAreaFrac,
+                    &G_fswbLandAreaFracNextTimestep, &G_fGloLake, &G_riverAreaFracNextTimestep_Frac, &K_release, &G_riverDischarge})
+        g->initialize(ng);
+    statusStarted_landAreaFracNextTimestep.initialize(ng);
+    statusStarted_landfreq.assign(ng, 0);
+    G_res_type.initialize(ng); G_start_month.initialize(ng); G_reg_lake_status.initialize(ng); G_LDD.initialize(ng);
+    G_res_start_year.initialize(ng); G_downstreamCell.initialize(ng); G_routOrder.initialize(ng);
+    G_glo_lake.read(in + "/G_GLOLAK.UNF0"); G_loc_lake.read(in + "/G_LOCLAK.UNF0"); G_glo_wetland.read(in + "/G_GLOWET.UNF0");
+    G_loc_wetland.read(in + "/G_LOCWET.UNF0"); G_lake_area.read(in + "/G_LAKAREA.UNF0"); G_reservoir_area_full.read(in + "/G_RESAREA.UNF0");
+    G_reg_lake.read(in + "/G_REGLAKE.UNF0"); G_reg_lake_status.read(in + "/G_REG_LAKE.UNF1");
+    for (int n = 0; n < ng; n++)
+        for (auto *g : {&G_glo_lake, &G_glo_wetland, &G_loc_lake, &G_loc_wetland, &G_lake_area, &G_reservoir_area_full, &G_reg_lake})
+            if ((*g)[n] < 0.) (*g)[n] = 0.;
+    G_downstreamCell.read(rd + "/G_OUTFLC.UNF4");
+    G_loc_res.read(in + "/G_LOCRES.UNF0");
+    for (int n = 0; n < ng; n++) G_loc_lake[n] += G_loc_res[n];
+    G_res_type.read(in + "/G_RES_TYPE.UNF1"); G_res_start_year.read(in + "/G_START_YEAR.UNF4");
+    G_start_month.read(rd + "/G_START_MONTH.UNF1"); G_mean_outflow.read(in + "/G_MEAN_OUTFLOW.UNF0");
+    G_stor_cap_full.read(in + "/G_STORAGE_CAPACITY.UNF0");
+    Grid<double> mean_NUs(ng);
+    mean_NUs.read(in + "/G_NUs_1971_2000.UNF0");
+    Grid<double, 5> alloc(ng);
+    alloc.read(rd + "/G_ALLOC_COEFF.5.UNF0");
+    for (int n = 0; n < ng; n++) {  // :361-377 (incl. the reference's un-decremented index into G_reservoir_area_full)
+        G_mean_demand[n] = mean_NUs[n];
+        short i = 0;
+        int d = G_downstreamCell[n];
+        while (i < 5 && d > 0 && d < ng && G_reservoir_area_full[d] <= 0) {
+            G_mean_demand[n] += mean_NUs[d - 1] * alloc(n, i++);
+            d = G_downstreamCell[d - 1];
+        }
+    }
+    for (int n = 0; n < ng; n++) {
+        if (G_stor_cap_full[n] < 0.) G_stor_cap_full[n] = 0.;
+        K_release[n] = 0.1;
+        G_mean_outflow[n] = G_mean_outflow[n] * 12. * 1000000000. / 31536000.;
+        G_mean_demand[n] = G_mean_demand[n] / 31536000.;
+    }
+    G_riverLength.read(rd + "/G_RIVER_LENGTH.UNF0");
+    for (int n = 0; n < ng; n++) G_riverLength[n] *= eng.geo.G_contfreq[n] / 100.;
+    G_RiverSlope.read(rd + "/G_RIVERSLOPE.UNF0"); G_Roughness.read(in + "/G_ROUGHNESS.UNF0"); G_bankfull_flow.read(in + "/G_BANKFULL.UNF0");
+    for (int n = 0; n < ng; n++) {  // :492-507
+        if (G_bankfull_flow[n] < 0.05) G_bankfull_flow[n] = 0.05;
+        G_RiverWidth_bf[n] = 2.71 * pow(G_bankfull_flow[n], 0.557);
+        G_RiverDepth_bf[n] = 0.349 * pow(G_bankfull_flow[n], 0.341);
+        G_riverBottomWidth[n] = G_RiverWidth_bf[n] - 2.0 * 2.0 * G_RiverDepth_bf[n];
+        G_riverStorageMax[n] = G_riverLength[n] * 0.5 * G_RiverDepth_bf[n] / 1000. * (G_riverBottomWidth[n] / 1000. + G_RiverWidth_bf[n] / 1000.);
+    }
+    G_routOrder.read(rd + "/G_ROUT_ORDER.UNF4");
+    G_LDD.read(rd + "/G_LDD_2.UNF1");
+}
+
+void routingClass::initLakeDepthActive(const calibParamClass &cp) { for (int n = 0; n < eng.ncell; n++) G_lakeDepthActive[n] = cp.getValue(P_LAK_D, n) * 0.001; }
+void routingClass::initWetlDepthActive(const calibParamClass &cp) { for (int n = 0; n < eng.ncell; n++) G_wetlDepthActive[n] = cp.getValue(P_WET_D, n) * 0.001; }
+
+void routingClass::initFractionStatus() {  // :745-765
+    for (int n = 0; n < eng.ncell; n++) {
+        statusStarted_landfreq[n] = 0;
+        statusStarted_landAreaFracNextTimestep[n] = 0;
+        G_fGloLake[n] = G_glo_lake[n] / 100.;
+        G_fswbInit[n] = G_loc_lake[n] / 100. + G_loc_wetland[n] / 100. + G_glo_wetland[n] / 100.;
+        G_fswbLandAreaFrac[n] = G_fswbInit[n];
+        G_fswbLandAreaFracNextTimestep[n] = G_fswbLandAreaFrac[n];
+    }
+    statusStarted_updateGloResPrevYear = 0;
+}
+
+void routingClass::setStoragesToZero() {  // :789-847 (riverveloOpt 1: rivers start empty)
+    for (auto *g : {&G_locLakeStorage, &G_locWetlStorage, &G_gloLakeStorage, &G_gloWetlStorage, &G_gloResStorage, &G_riverStorage, &G_groundwaterStorage})
+        g->fill(0.);
+}
+
+void routingClass::setStorages(WghmStateFile &st, AdditionalOutputInputFile &) {  // :851-882
+    for (int n = 0; n < eng.ncell; n++) {
+        const double f = ((eng.geo.areaOfCellByArrayPos(n) * (eng.geo.G_contfreq[n] / 100.)) / 1000000.);
+        Cell &c = st.cell(n);
+        G_locLakeStorage[n] = c.locallake(0) * f; G_locWetlStorage[n] = c.localwetland(0) * f; G_gloLakeStorage[n] = c.globallake(0) * f;
+        G_gloWetlStorage[n] = c.globalwetland(0) * f; G_riverStorage[n] = c.river(0) * f; G_groundwaterStorage[n] = c.groundwater(0) * f;
+        G_gloResStorage[n] = c.reservoir(0) * f;
+    }
+}
+
+void routingClass::setLakeWetlToMaximum(short) {  // :5647-5720 (resYearOpt 0)
+    const int ref = eng.options.resYearReference;
+    for (int n = 0; n < eng.ncell; n++) {
+        const double A = eng.geo.areaOfCellByArrayPos(n);
+        G_locLakeStorage[n] = (G_loc_lake[n] / 100.) * A * G_lakeDepthActive[n];
+        G_locWetlStorage[n] = (G_loc_wetland[n] / 100.) * A * G_wetlDepthActive[n];
+        G_gloLakeStorage[n] = G_lake_area[n] * G_lakeDepthActive[n];
+        G_gloWetlStorage[n] = (G_glo_wetland[n] / 100.) * A * G_wetlDepthActive[n];
+        if (ref >= G_res_start_year[n] && G_stor_cap_full[n] > -99) G_gloResStorage[n] = G_stor_cap_full[n];
+        G_gloResEvapoReductionFactor[n] = 0.;  // the second if/else of the reference overrides the first with resYearOpt == 0
+        if (G_reg_lake_status[n] == 1 && ref < G_res_start_year[n]) G_gloResStorage[n] += G_reservoir_area_full[n] * G_lakeDepthActive[n];
+        G_locLakeAreaReductionFactor[n] = 1.; G_locWetlAreaReductionFactor[n] = 1.; G_gloLakeEvapoReductionFactor[n] = 1.; G_gloWetlAreaReductionFactor[n] = 1.;
+        G_riverAreaReductionFactor[n] = 0.5;
+        G_riverAreaFracNextTimestep_Frac[n] = G_riverAreaReductionFactor[n] * G_riverLength[n] * G_RiverWidth_bf[n] / 1000. / A;
+    }
+}
+
+void routingClass::annualInit(short, int) {  // :979-1291 (resYearOpt 0: G_RES_<reference year>; no commissioning dynamics)
+    const int ng = eng.ncell, ref = eng.options.resYearReference;
+    for (int n = 0; n < ng; n++) { G_reservoir_area[n] = 0.; G_stor_cap[n] = 0.; }
+    for (int n = 0; n < ng; n++)
+        if (G_reg_lake_status[n] == 1) { G_reservoir_area[n] = G_reservoir_area_full[n]; G_stor_cap[n] = G_stor_cap_full[n]; }
+    G_glo_res.read(eng.options.input_dir + "/G_RES/G_RES_" + std::to_string(ref) + ".UNF0");
+    if (0 == statusStarted_updateGloResPrevYear) { updateGloResPrevYear_pct(); statusStarted_updateGloResPrevYear = 1; }
+    for (int n = 0; n < ng; n++)
+        if (ref >= G_res_start_year[n]) { G_reservoir_area[n] = G_reservoir_area_full[n]; G_stor_cap[n] = G_stor_cap_full[n]; }
+    for (int n = 0; n < ng; n++)
+        if (G_reservoir_area[n] > 0. && ref >= G_res_start_year[n] && ((G_res_type[n] + 0 == 0) || G_mean_outflow[n] <= 0.)) {
+            G_lake_area[n] += G_reservoir_area_full[n];  // treated as a global lake (:1107-1146)
+            G_reservoir_area[n] = 0.;
+            G_reservoir_area_full[n] = 0.;
+        }
+    for (int n = 0; n < ng; n++) {
+        if (0 == statusStarted_landfreq[n]) {
+            G_landAreaFrac[n] = (eng.geo.G_contfreq[n] - (G_glo_lake[n] + G_glo_wetland[n] + G_loc_lake[n] + G_loc_wetland[n] + G_glo_res[n]));
+            G_landAreaFracPrevTimestep[n] = 0.;
+            if (G_landAreaFrac[n] < 0.) G_landAreaFrac[n] = 0.;
+            statusStarted_landfreq[n] = 1;
+        }
+    }
+}
+
+void routingClass::routing(short, short day, short month, short dom, short, WghmStateFile &st, AdditionalOutputInputFile &, short, calibParamClass &) {
+    eng.check(wgk_routing_day(eng.ctx, day, month, dom), "wgk_routing_day");
+    // wghmState of the day (routing.cpp:5002-5020): km3 -> mm over the continental area
+    pull();
+    for (int n = 0; n < eng.ncell; n++) {
+        const double f = ((eng.geo.areaOfCellByArrayPos(n) * (eng.geo.G_contfreq[n] / 100.)) / 1000000.);
+        Cell &c = st.cell(n);
+        c.locallake(dom - 1) = G_locLakeStorage[n] / f; c.localwetland(dom - 1) = G_locWetlStorage[n] / f;
+        c.globallake(dom - 1) = G_gloLakeStorage[n] / f; c.globalwetland(dom - 1) = G_gloWetlStorage[n] / f;
+        c.reservoir(dom - 1) = G_gloResStorage[n] / f; c.river(dom - 1) = G_riverStorage[n] / f;
+        c.groundwater(dom - 1) = G_groundwaterStorage[n] / f;
+    }
+}
+
+void routingClass::updateLandAreaFrac(AdditionalOutputInputFile &add) {
+    eng.check(wgk_update_land_area_frac(eng.ctx), "wgk_update_land_area_frac");
+    for (int n = 0; n < eng.ncell; n++) {  // :5347-5350
+        add.additionalOutputInput(n, 6) = G_landAreaFrac[n];
+        add.additionalOutputInput(n, 7) = G_landAreaFracPrevTimestep[n];
+    }
+}
+
+void routingClass::pull() {
+    Engine &e = eng;
+    e.get("loc_lake_stor", G_locLakeStorage); e.get("loc_wetl_stor", G_locWetlStorage); e.get("glo_lake_stor", G_gloLakeStorage);
+    e.get("glo_wetl_stor", G_gloWetlStorage); e.get("res_stor", G_gloResStorage); e.get("river_stor", G_riverStorage);
+    e.get("gw", G_groundwaterStorage); e.get("land_area_frac", G_landAreaFrac); e.get("land_area_frac_prev", G_landAreaFracPrevTimestep);
+    e.get("land_area_frac_next", G_landAreaFracNextTimestep); e.get("status_laf_next", statusStarted_landAreaFracNextTimestep);
+    e.get("red_loc_lake", G_locLakeAreaReductionFactor); e.get("red_loc_wetl", G_locWetlAreaReductionFactor);
+    e.get("red_glo_lake", G_gloLakeEvapoReductionFactor); e.get("red_glo_wetl", G_gloWetlAreaReductionFactor);
+    e.get("red_res", G_gloResEvapoReductionFactor); e.get("red_river", G_riverAreaReductionFactor); e.get("k_release", K_release);
+    e.get("fswb_laf", G_fswbLandAreaFrac); e.get("fswb_laf_next", G_fswbLandAreaFracNextTimestep);
+    e.get("river_area_frac_next", G_riverAreaFracNextTimestep_Frac); e.get("discharge", G_riverDischarge);
+}
+
+// ------------------------------------------------------------------------------------------
+// daily class
+// ------------------------------------------------------------------------------------------
+void dailyWaterBalanceClass::setStoragesToZero() {
+    G_soilWaterContent.fill(0.); G_canopyWaterContent.fill(0.); G_snow.fill(0.); G_dailyStorageTransfer.fill(0.); G_SnowInElevation.fill(0.);
+}
+
+void dailyWaterBalanceClass::setStorages(WghmStateFile &st, SnowInElevationFile &snow, AdditionalOutputInputFile &) {  // :1896-1924
+    for (int n = 0; n < eng.ncell; n++) {
+        const double laf = eng.routing.getLandAreaFrac(n);
+        if (laf <= 0.) {
+            G_canopyWaterContent[n] = G_snow[n] = G_soilWaterContent[n] = 0.;
+            for (int e = 0; e <= 100; e++) G_SnowInElevation(n, e) = 0.;
+        } else {
+            const double cf = eng.geo.G_contfreq[n];
+            G_canopyWaterContent[n] = st.cell(n).canopy(0) * cf / laf;
+            G_snow[n] = st.cell(n).snow(0) * cf / laf;
+            G_soilWaterContent[n] = st.cell(n).soil(0) * cf / laf;
+            for (int e = 0; e <= 100; e++) G_SnowInElevation(n, e) = snow.snowInElevation(n, e) * cf / laf;
+        }
+    }
+}
+
+void dailyWaterBalanceClass::calcNewDayAll(short day, short month, short dom) {
+    eng.check(wgk_vertical_day(eng.ctx, day, month, dom, dom - 1), "wgk_vertical_day");
+}
+
+void dailyWaterBalanceClass::calcNewDay(short day, short month, short dom, short, short year, int, WghmStateFile &, AdditionalOutputInputFile &,
+                                        SnowInElevationFile &, short, calibParamClass &) {
+    const int key = (int)year * 1000 + day;  // one whole-grid launch per simulated day
+    if (key == last_day_launched) return;
+    last_day_launched = key;
+    calcNewDayAll(day, month, dom);
+}
+
+void dailyWaterBalanceClass::pull() {
+    Engine &e = eng;
+    e.get("canopy", G_canopyWaterContent); e.get("soil", G_soilWaterContent); e.get("snow", G_snow); e.get("snow_bands", G_SnowInElevation);
+    e.get("lake_balance", G_lakeBalance); e.get("openwater_pet", G_openWaterPET); e.get("openwater_prec", G_openWaterPrec);
+    e.get("surface_runoff", G_dailyLocalSurfaceRunoff); e.get("gw_recharge", G_dailyGwRecharge); e.get("storage_transfer", G_dailyStorageTransfer);
+}
+
+// ------------------------------------------------------------------------------------------
+// device synchronisation
+// ------------------------------------------------------------------------------------------
+void Engine::push_static() {
+    check(wgk_set_topology(ctx, routing.G_routOrder.data(), routing.G_downstreamCell.data()), "wgk_set_topology");
+    Grid<double> area(ncell);
+    for (int n = 0; n < ncell; n++) area[n] = geo.areaOfCellByArrayPos(n);
+    set("area", area); set("contfreq", geo.G_contfreq); set("contcell", geo.G_contcell); set("row", geo.G_row);
+    set("toBeCalculated", G_toBeCalculated); set("landcover", G_landCover); set("builtup", G_built_up); set("arid", G_aindex);
+    set("ldd", routing.G_LDD); set("texture", G_texture); set("elevation", dailyWaterBalance.G_Elevation);
+    set("loc_lake", routing.G_loc_lake); set("loc_wetland", routing.G_loc_wetland); set("glo_wetland", routing.G_glo_wetland);
+    set("lake_area", routing.G_lake_area); set("reservoir_area", routing.G_reservoir_area); set("stor_cap", routing.G_stor_cap);
+    set("mean_outflow", routing.G_mean_outflow); set("mean_demand", routing.G_mean_demand); set("res_type", routing.G_res_type);
+    set("start_month", routing.G_start_month); set("river_length", routing.G_riverLength); set("river_slope", routing.G_RiverSlope);
+    set("roughness", routing.G_Roughness); set("river_bottom_width", routing.G_riverBottomWidth); set("river_width_bf", routing.G_RiverWidth_bf);
+    set("river_storage_max", routing.G_riverStorageMax); set("fswb_init", routing.G_fswbInit); set("f_glo_lake", routing.G_fGloLake);
+    check(wgk_set_field(ctx, wgk_field_id("params"), 0, calParam.block(), (size_t)26 * ncell * sizeof(double)), "params");
+    set("gamma_hbv", dailyWaterBalance.G_gammaHBV); set("cfa", dailyWaterBalance.G_cellCorrFact); set("cfs", routing.G_statCorrFact);
+    set("smax", G_Smax); set("gwfactor", G_gwFactor); set("rgmax", G_Rgmax); set("laimax", G_LAImax);
+    set("lake_depth_active", routing.G_lakeDepthActive); set("wetl_depth_active", routing.G_wetlDepthActive);
+    auto table = [&](const char *name, const void *p, size_t bytes) { check(wgk_set_field(ctx, wgk_field_id(name), 0, p, bytes), name); };
+    table("lai_factor_a", lai_factor_a, sizeof lai_factor_a); table("lai_factor_b", lai_factor_b, sizeof lai_factor_b);
+    table("lai_initial_days", lai_initialDays, sizeof lai_initialDays); table("lai_kc_min", kc_min, sizeof kc_min); table("lai_kc_max", kc_max, sizeof kc_max);
+    table("lct_albedo", dailyWaterBalance.albedo_lct, sizeof dailyWaterBalance.albedo_lct);
+    table("lct_albedo_snow", dailyWaterBalance.albedoSnow_lct, sizeof dailyWaterBalance.albedoSnow_lct);
+    table("lct_ddf", dailyWaterBalance.ddf_lct, sizeof dailyWaterBalance.ddf_lct);
+    table("lct_emissivity", dailyWaterBalance.emissivity_lct, sizeof dailyWaterBalance.emissivity_lct);
+}
+
+void Engine::push_state() {
+    auto &d = dailyWaterBalance;
+    auto &r = routing;
+    set("canopy", d.G_canopyWaterContent); set("soil", d.G_soilWaterContent); set("snow", d.G_snow); set("snow_bands", d.G_SnowInElevation);
+    set("storage_transfer", d.G_dailyStorageTransfer); set("lai_days", lai_days); set("lai_status", lai_status); set("lai_precsum", lai_precsum);
+    set("gw", r.G_groundwaterStorage); set("loc_lake_stor", r.G_locLakeStorage); set("loc_wetl_stor", r.G_locWetlStorage);
+    set("glo_lake_stor", r.G_gloLakeStorage); set("glo_wetl_stor", r.G_gloWetlStorage); set("res_stor", r.G_gloResStorage);
+    set("river_stor", r.G_riverStorage); set("red_loc_lake", r.G_locLakeAreaReductionFactor); set("red_loc_wetl", r.G_locWetlAreaReductionFactor);
+    set("red_glo_lake", r.G_gloLakeEvapoReductionFactor); set("red_glo_wetl", r.G_gloWetlAreaReductionFactor);
+    set("red_res", r.G_gloResEvapoReductionFactor); set("red_river", r.G_riverAreaReductionFactor); set("k_release", r.K_release);
+    set("land_area_frac", r.G_landAreaFrac); set("land_area_frac_prev", r.G_landAreaFracPrevTimestep);
+    set("land_area_frac_next", r.G_landAreaFracNextTimestep); set("fswb_laf", r.G_fswbLandAreaFrac);
+    set("fswb_laf_next", r.G_fswbLandAreaFracNextTimestep); set("river_area_frac_next", r.G_riverAreaFracNextTimestep_Frac);
+    set("status_laf_next", r.statusStarted_landAreaFracNextTimestep);
+}
+
+void Engine::set_forcing_month(int month1, int year) {  // climate.cpp:93-123 (.31 files, cloud == 1)
+    const std::string c = options.climate_dir, sfx = "_" + std::to_string(year) + "_" + std::to_string(month1) + ".31.UNF0";
+    Grid<float, 31> P(ncell), T(ncell), SW(ncell), LW(ncell);
+    T.read(c + "/GTEMP" + sfx); P.read(c + "/GPREC" + sfx); SW.read(c + "/GSHORTWAVE" + sfx); LW.read(c + "/GLONGWAVE_DOWN" + sfx);
+    check(wgk_set_forcing(ctx, 0, 31, -1, P.data(), T.data(), SW.data(), LW.data(), 31), "wgk_set_forcing");
+    check(wgk_synchronize(ctx), "sync");  // the host grids go out of scope
+}
+
+// ------------------------------------------------------------------------------------------
+// integrate_wghm-shaped driver
+// ------------------------------------------------------------------------------------------
+long integrate_wghm(const std::string &config_file, int ncell, int device, double *seconds_day_loop) {
+    ConfigFile cfg(config_file);
+    Engine E(ncell, device);
+    E.options.init(cfg);
+    E.options.require_canonical();
+    WghmStateFile wghmState(ncell, 1);
+    if (!cfg.startvaluefile.empty()) wghmState.load(cfg.startvaluefile);
+    E.calParam.readJson(cfg.parameterfile, ncell);
+    AdditionalOutputInputFile additionalOutIn(ncell);
+    SnowInElevationFile snow_in_elevation(ncell);
+    if (!cfg.additionalfile.empty() || !cfg.snowInElevationfile.empty())
+        throw std::runtime_error("restart from additionalOutIn / snowInElevation start values is not implemented yet");
+    const short number_of_days_in_month[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    const short last_day_in_month[12] = {30, 58, 89, 119, 150, 180, 211, 242, 272, 303, 333, 364};
+    short readinstatus = 1;
+    // init sequence, integrateWGHM.cpp:127-286
+    if (1 == E.options.rout_prepare) E.topo = prepare_routing_files(E.options.input_dir, E.options.routing_dir, 1, E.options.resOpt, ncell);
+    E.geo.init(E.options.input_dir, ncell, E.options.resOpt);
+    E.dailyWaterBalance.init(E.options.input_dir, 0);
+    E.land_init();
+    E.G_aindex.initialize(ncell);
+    E.G_aindex.read(E.options.input_dir + "/G_ARID_HUMID.UNF2");
+    E.dailyWaterBalance.G_Elevation.read(E.options.input_dir + "/G_ELEV_RANGE.101.UNF2");
+    E.lai_init();
+    E.routing.init(0, cfg);
+    E.routing.initLakeDepthActive(E.calParam);
+    E.routing.initWetlDepthActive(E.calParam);
+    // body of the single-pass calibration loop, :291-476
+    E.routing.initFractionStatus();
+    E.routing.setStoragesToZero();
+    if (cfg.startvaluefile.empty()) E.routing.setLakeWetlToMaximum(E.options.start_year);
+    E.G_toBeCalculated.initialize(ncell);
+    E.G_toBeCalculated.fill(1);
+    for (int n = 0; n < ncell; n++) {
+        E.dailyWaterBalance.G_gammaHBV[n] = E.calParam.getValue(P_GAMRUN_C, n);
+        E.dailyWaterBalance.G_cellCorrFact[n] = E.calParam.getValue(P_CFA, n);
+        E.routing.G_statCorrFact[n] = E.calParam.getValue(P_CFS, n);
+    }
+    E.dailyWaterBalance.setStoragesToZero();
+    E.createMaxSoilWaterCapacityGrid();
+    E.createGroundwaterGrids();
+    E.check(wgk_forcing_reserve(E.ctx, 31, 0), "wgk_forcing_reserve");
+
+    long ndays = 0;
+    double secs = 0.;
+    bool pushed = false;
+    for (short year = E.options.start_year; year <= E.options.end_year; year++) {
+        E.dailyWaterBalance.annualInit();
+        E.routing.annualInit(year, cfg.startMonth);
+        if (!pushed) { E.push_static(); E.push_state(); pushed = true; }  // (yearly reservoir changes do not occur with resYearOpt 0)
+        short day = 0;
+        if (year == cfg.startYear) for (int m = 1; m < cfg.startMonth; m++) day += number_of_days_in_month[m - 1];
+        short start_month = cfg.startMonth, end_month = cfg.endMonth;
+        if (E.options.start_year != E.options.end_year) {
+            if (year == E.options.start_year) end_month = 12;
+            else if (year == E.options.end_year) start_month = 1;
+            else { start_month = 1; end_month = 12; }
+        }
+        for (short month = start_month - 1; month < end_month; month++) {
+            E.set_forcing_month(month + 1, year);
+            wghmState.resetCells(number_of_days_in_month[month]);
+            const auto t0 = std::chrono::steady_clock::now();
+            for (short dom = 1; dom <= number_of_days_in_month[month]; dom++) {
+                day++;
+                ndays++;
+                // the reference's per-cell loop (integrateWGHM.cpp:770-783) through the shim
+                for (int n = 0; n < ncell; n++)
+                    if (E.geo.G_contcell[n])
+                        E.dailyWaterBalance.calcNewDay(day, month, dom, last_day_in_month[month], year, n, wghmState, additionalOutIn,
+                                                       snow_in_elevation, readinstatus, E.calParam);
+                E.routing.routing(year, day, month, dom, last_day_in_month[month], wghmState, additionalOutIn, readinstatus, E.calParam);
+                E.routing.updateLandAreaFrac(additionalOutIn);
+                if (readinstatus == 1) readinstatus = 0;
+            }
+            secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            // month-end rescale, integrateWGHM.cpp:830-847
+            E.dailyWaterBalance.pull();
+            for (int n = 0; n < ncell; n++) {
+                const double laf = E.routing.getLandAreaFrac(n), cf = E.geo.G_contfreq[n];
+                for (short e = 0; e <= 100; e++)
+                    snow_in_elevation.snowInElevation(n, e) = (laf == 0.) ? 0. : E.dailyWaterBalance.G_SnowInElevation(n, e) * laf / cf;
+                for (short dom = 1; dom <= number_of_days_in_month[month]; dom++) {
+                    wghmState.cell(n).canopy(dom - 1) = E.dailyWaterBalance.G_canopyWaterContent[n] * laf / cf;
+                    wghmState.cell(n).snow(dom - 1) = E.dailyWaterBalance.G_snow[n] * laf / cf;
+                    wghmState.cell(n).soil(dom - 1) = E.dailyWaterBalance.G_soilWaterContent[n] * laf / cf;
+                }
+            }
+            if (year == E.options.end_year && month + 1 == end_month) {  // :853-901
+                if (!cfg.outputmeanfile.empty()) wghmState.saveMean(cfg.outputmeanfile);
+                if (!cfg.outputlastdayfile.empty()) wghmState.saveDay(cfg.outputlastdayfile, number_of_days_in_month[month] - 1);
+                if (!cfg.outputadditionalfile.empty()) {
+                    // columns the hot path owns (additionalOutputInputFile.cpp:19-71)
+                    Grid<int32_t> ld, ls; Grid<double> lp;
+                    E.get("lai_days", ld); E.get("lai_status", ls); E.get("lai_precsum", lp);
+                    for (int n = 0; n < ncell; n++) {
+                        additionalOutIn.additionalOutputInput(n, 0) = ld[n]; additionalOutIn.additionalOutputInput(n, 1) = ls[n];
+                        additionalOutIn.additionalOutputInput(n, 2) = lp[n]; additionalOutIn.additionalOutputInput(n, 5) = E.routing.K_release[n];
+                        additionalOutIn.additionalOutputInput(n, 10) = E.routing.G_groundwaterStorage[n];
+                        additionalOutIn.additionalOutputInput(n, 14) = E.routing.G_fswbInit[n];
+                        additionalOutIn.additionalOutputInput(n, 33) = E.routing.G_fswbLandAreaFracNextTimestep[n];
+                    }
+                    additionalOutIn.save(cfg.outputadditionalfile);
+                }
+                if (!cfg.outputsnowlastdayfile.empty()) snow_in_elevation.save(cfg.outputsnowlastdayfile);
+            }
+        }
+    }
+    if (seconds_day_loop) *seconds_day_loop = secs;
+    return ndays;
+}
+
+}  // namespace wg
+
+extern "C" {
+long wg_host_integrate(const char *config_file, int ncell, int device, double *seconds_day_loop, char *err, size_t errlen) {
+    try {
+        return wg::integrate_wghm(config_file, ncell, device, seconds_day_loop);
+    } catch (std::exception &e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}
+// load + re-save of the three checkpoint files (format round trip, used by the tests)
+int wg_host_state_roundtrip(const char *kind, const char *in, const char *out, int ncell, char *err, size_t errlen) {
+    try {
+        const std::string k(kind);
+        if (k == "state") { wg::WghmStateFile f(ncell, 1); f.load(in); f.saveDay(out, 0); }
+        else if (k == "snow") { wg::SnowInElevationFile f(ncell); f.load(in); f.save(out); }
+        else if (k == "additional") { wg::AdditionalOutputInputFile f(ncell); f.load(in); f.save(out); }
+        else throw std::runtime_error("unknown kind " + k);
+        return 0;
+    } catch (std::exception &e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}
+int wg_host_prepare_routing_files(const char *input_dir, const char *routing_dir, int resOpt, int ncell, int *nlevels, char *err, size_t errlen) {
+    try {
+        wg::FlowTopology t = wg::prepare_routing_files(input_dir, routing_dir, 1, (short)resOpt, ncell);
+        if (nlevels) *nlevels = t.nlevels;
+        return 0;
+    } catch (std::exception &e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}
+}
