@@ -1,0 +1,61 @@
+"""CPU, world_size 2 over gloo: member sharding and the ensemble-statistics all-reduce."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from watergap2_b200.ensemble import ensemble_mean_var, shard_by_basin, shard_members
+
+
+def test_shard_members_partition():
+    for total in (0, 1, 7, 256, 1024):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_members(total, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and sum(c for _, c in blocks) == total
+            for (f0, c0), (f1, _) in zip(blocks, blocks[1:]):
+                assert f0 + c0 == f1
+            assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
+    with pytest.raises(ValueError):
+        shard_members(8, 2, 2)
+
+
+def test_shard_by_basin_keeps_basins_whole(world3000, oracle_lib):
+    w = world3000
+    t = oracle_lib.rout_prepare(w.flowdir, w.row, w.col, w.gcrc.T)
+    rank = shard_by_basin(t["basins2"], 4)
+    b = t["basins2"]
+    for bid in np.unique(b[b > 0]):
+        assert len(set(rank[b == bid])) == 1
+    down = t["outflow_cell"]
+    has = down > 0
+    assert (rank[has] == rank[down[has] - 1]).all()  # water never crosses a rank boundary
+    load = np.bincount(rank, minlength=4)
+    assert load.max() <= 1.3 * load.mean() + np.bincount(b[b > 0]).max()
+
+
+def _worker(rank, world, port, total, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.from_numpy(np.random.default_rng(7).standard_normal((total, n)))
+    first, count = shard_members(total, world, rank)
+    mean, var = ensemble_mean_var(full[first:first + count].clone(), total)
+    if rank == 0:
+        torch.save({"mean": mean, "var": var, "ref_mean": full.mean(0), "ref_var": full.var(0, unbiased=False)}, out)
+    dist.destroy_process_group()
+
+
+def test_ensemble_statistics_world_size_2(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "stats.pt")
+    mp.spawn(_worker, args=(2, port, 13, 257, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert torch.allclose(r["mean"], r["ref_mean"], rtol=0, atol=1e-14)
+    assert torch.allclose(r["var"], r["ref_var"], rtol=1e-12, atol=1e-14)

@@ -1,0 +1,73 @@
+"""Member sharding and ensemble statistics across GPUs (plumbing over torch.distributed).
+
+The daily hot path shards by member (calibration parameter sets, EnKF ensemble members —
+calibration.cpp / enKF2wghmState.cpp run them as separate processes); members never exchange
+data inside a simulated day, so there is NO data-path collective.  The only exchange is the
+statistic an assimilation cycle needs once per cycle: all-reduce of the sum and
+the sum of squares of a state field over all members of all ranks (NCCL over NVLink on GPUs,
+gloo in the CPU tests).
+"""
+import numpy as np
+
+
+def shard_members(nmember_total, world_size, rank):
+    """contiguous block of members owned by `rank`: (first, count); blocks differ by at most one"""
+    if not (0 <= rank < world_size) or nmember_total < 0:
+        raise ValueError("bad rank / world size")
+    base, extra = divmod(nmember_total, world_size)
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def shard_by_basin(basin_of_cell, world_size):
+    """whole drainage basins to ranks, longest-processing-time first by cell count (config 5:
+    high-resolution grids are split by basin; basins exchange no water without water use).
+    -> rank_of_cell (int32).  Basin id 0 (single-cell basins of G_BASINS_2) is spread cell-wise."""
+    b = np.asarray(basin_of_cell).astype(np.int64)
+    ids, counts = np.unique(b[b > 0], return_counts=True)
+    load = np.zeros(world_size, np.int64)
+    rank_of_basin = {}
+    for i in np.argsort(-counts, kind="stable"):
+        r = int(np.argmin(load))
+        rank_of_basin[int(ids[i])] = r
+        load[r] += counts[i]
+    out = np.empty(b.size, np.int32)
+    for n in range(b.size):
+        if b[n] > 0:
+            out[n] = rank_of_basin[int(b[n])]
+        else:
+            r = int(np.argmin(load))
+            out[n] = r
+            load[r] += 1
+    return out
+
+
+class _CudaArray:
+    """zero-copy view of a wgk device buffer for torch.as_tensor (CUDA array interface v2)"""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def member_tensor(model, field):
+    """torch view [nmember, cell_stride] (device layout: routing order, padded) of a per-member
+    f64 field of a wgk Model, without a copy"""
+    import torch
+    ptr = model.device_ptr(field, 0)
+    return torch.as_tensor(_CudaArray(ptr, (model.nmember, model.cell_stride)), device=f"cuda:{model.device}")
+
+
+def ensemble_mean_var(local, nmember_total, group=None):
+    """mean and (population) variance over ALL members of all ranks of `local` [members_on_this_rank, n]
+    (torch tensor on the rank's device).  Two all-reduces of n doubles each."""
+    import torch
+    import torch.distributed as dist
+    s = local.sum(0)
+    ss = (local * local).sum(0)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(ss, op=dist.ReduceOp.SUM, group=group)
+    mean = s / nmember_total
+    var = torch.clamp(ss / nmember_total - mean * mean, min=0.0)
+    return mean, var
