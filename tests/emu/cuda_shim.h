@@ -23,4 +23,7 @@ static thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline void __syncthreads() {}
+static inline void __pipeline_memcpy_async(void *dst, const void *src, size_t n) { std::memcpy(dst, src, n); }
+static inline void __pipeline_commit() {}
+static inline void __pipeline_wait_prior(int) {}
 using std::exp; using std::pow; using std::sqrt; using std::fabs; using std::log; using std::cbrt; using std::fma;

@@ -126,6 +126,7 @@
     X(s_c1, double, "f64", PSET, 1) \
     X(s_slope_pow, double, "f64", PSET, 1) \
     X(s_flags, int8_t, "i8", CELL, 1) \
+    X(s_elev32, int32_t, "i32", CELL, 101) \
     /* ---- land cover tables (LCT_22.DAT / LAI_22.DAT; daily.h:204-208, lai.h) ---- */ \
     X(lai_factor_a, float, "f32", TABLE, 1) \
     X(lai_factor_b, float, "f32", TABLE, 1) \

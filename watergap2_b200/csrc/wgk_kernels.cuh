@@ -24,6 +24,7 @@
 #pragma once
 #include <cstdint>
 #ifndef WGK_EMU  // tests/emu compiles this header for the host to check the kernel logic
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #endif
 #include "wgk_fields.h"
@@ -54,6 +55,27 @@ struct WgkParams {
 namespace wgk {
 
 constexpr double MIN_STOR_VOL = 1.e-15;  // routing.h:24
+
+// Shared-memory staging of the 100 snow bands of a cell: the band columns of the CTA's 128
+// cells are brought in by cp.async (LDGSTS) in chunks of SNOW_CH bands, double buffered, so
+// that all loads of the band loop are in flight while the thread evaluates radiation / PET /
+// canopy, and the loop itself reads shared memory.  Every thread copies and reads only its own
+// column, so no block-wide barrier is involved.
+constexpr int SNOW_CH = 10, SNOW_NCH = 10, VBLOCK = 128;
+struct SnowStage {
+    double s[2][SNOW_CH][VBLOCK];
+    int32_t e[2][SNOW_CH][VBLOCK];
+};
+__device__ __forceinline__ void stage_issue(SnowStage *st, const int buf, const int t, const double *S, const int32_t *E,
+                                            const size_t stride) {
+#pragma unroll
+    for (int k = 0; k < SNOW_CH; k++) {
+        __pipeline_memcpy_async(&st->s[buf][k][t], S + (size_t)k * stride, sizeof(double));
+        __pipeline_memcpy_async(&st->e[buf][k][t], E + (size_t)k * stride, sizeof(int32_t));
+    }
+    __pipeline_commit();
+}
+
 
 // ----------------------------------------------------------------------------------------
 // LAI growing-season state machine (lai.cpp:179-293)
@@ -136,11 +158,17 @@ __device__ __forceinline__ double lai_nogrowing(int &days, int initialDays, int 
 // ----------------------------------------------------------------------------------------
 // vertical water balance
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, const int m, const int slot) {
+__device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, const int m, const int slot, SnowStage *st) {
     const WgkArrays &a = p.a;
     if (!a.contcell[r]) return;  // integrateWGHM.cpp:772
     const size_t i = (size_t)m * p.stride + r;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    // start streaming the snow bands (bands 1..100; band 0 is the unused mean slot)
+    const int tid = threadIdx.x;
+    double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r + p.stride;
+    const int32_t *__restrict__ E = a.s_elev32 + r + p.stride;
+    stage_issue(st, 0, tid, S, E, p.stride);
+    stage_issue(st, 1, tid, S + (size_t)SNOW_CH * p.stride, E + (size_t)SNOW_CH * p.stride, p.stride);
 
     // daily.cpp:159-169, routing.h:246-251
     const int started = a.status_laf_next[i];
@@ -150,7 +178,10 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
     else if (p.restart == 1) lafPrev = a.land_area_frac_prev[i];
     else lafPrev = landAreaFrac;
 
-    if (1 != a.toBeCalculated[r]) return;  // daily.cpp:177
+    if (1 != a.toBeCalculated[r]) {  // daily.cpp:177
+        __pipeline_wait_prior(0);
+        return;
+    }
 
     const int lc = a.landcover[r] - 1;
     const float4 f = p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r];
@@ -282,16 +313,13 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
     a.canopy[i] = canopy;
     if (dailySoilPET < 0.) dailySoilPET = 0.0;
 
-    // snow in 100 elevation bands (:913-1062); band-major arrays: band e of this cell is
-    // S[e*stride], coalesced over the warp.  The loop body is branch-free (selects), because the
-    // cells of one warp sit in different regimes (accumulating / melting / bare) on any given day.
+    // snow in 100 elevation bands (:913-1062).  The loop body is branch-free (selects), because
+    // the cells of one warp sit in different regimes (accumulating / melting / bare) on a given day.
     double TempElevMax = 0., snowStorageChange = 0., snow = 0.;
-    double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r + p.stride;
-    const int16_t *__restrict__ E = a.elevation + r;
-    const int elev0 = E[0];
-    E += p.stride;
+    const int elev0 = a.s_elev32[r];
     const double ddf = M_DEGDAY_F * a.lct_ddf[lc];  // (M_DEGDAY_F * ddf_lct) * (...) keeps the reference association
     if (noland) {
+        __pipeline_wait_prior(0);
 #pragma unroll 4
         for (int e = 1; e < 101; e++) {
             storage_transfer += *S / 100.;
@@ -305,41 +333,47 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
         // ~25-instruction division per band; the result is the correctly rounded quotient
         const double inv_laf = 1. / landAreaFrac;
         int thresh_elev = 0;
-#pragma unroll 4
-        for (int e = 1; e < 101; e++) {
-            const int elev_e = *E;
-            const double sraw = *S;
-            double temp_elev = dailyTempC - ((elev_e - elev0) * P_T_GRADNT);
-            const double num = sraw * lafPrev;
-            double s = num * inv_laf;
-            s = fma(fma(-landAreaFrac, s, num), inv_laf, s);
-            if (fabs(s) <= MIN_STOR_VOL) s = 0.;
-            const double s0 = s;
-            if (s > 1000.) {  // :958-976 (rare)
-                if (thresh_elev == 0) thresh_elev = elev_e;
-                else if (thresh_elev > 0) temp_elev = dailyTempC - ((thresh_elev - elev0) * P_T_GRADNT);
+        for (int c = 0; c < SNOW_NCH; c++) {
+            const int buf = c & 1;
+            if (c + 1 < SNOW_NCH) __pipeline_wait_prior(1);
+            else __pipeline_wait_prior(0);
+#pragma unroll
+            for (int k = 0; k < SNOW_CH; k++) {
+                const int elev_e = st->e[buf][k][tid];
+                const double sraw = st->s[buf][k][tid];
+                double temp_elev = dailyTempC - ((elev_e - elev0) * P_T_GRADNT);
+                const double num = sraw * lafPrev;
+                double s = num * inv_laf;
+                s = fma(fma(-landAreaFrac, s, num), inv_laf, s);
+                if (fabs(s) <= MIN_STOR_VOL) s = 0.;
+                const double s0 = s;
+                if (s > 1000.) {  // :958-976 (rare)
+                    if (thresh_elev == 0) thresh_elev = elev_e;
+                    else if (thresh_elev > 0) temp_elev = dailyTempC - ((thresh_elev - elev0) * P_T_GRADNT);
+                }
+                const bool frz = (temp_elev <= P_T_SNOWFZ);
+                // accumulation and sublimation (:982-999)
+                s = s + (frz ? daily_prec_to_soil : 0.);
+                const bool more = (s > dailySoilPET);
+                const double sub = frz ? (more ? dailySoilPET : s) : 0.;
+                dailySnowEvapo += sub;
+                s = frz ? (more ? s - dailySoilPET : 0.) : s;
+                const double effBefore = frz ? 0. : daily_prec_to_soil;
+                // melt (:1003-1019)
+                const bool mlt = (temp_elev > P_T_SNOWMT) && !(s < 0.);
+                const double m_raw = ddf * (temp_elev - P_T_SNOWMT);
+                const bool all = (m_raw > s);
+                const double snowmelt_elev = mlt ? (all ? s : m_raw) : 0.;
+                s = mlt ? (all ? 0. : s - m_raw) : s;
+                snowStorageChange += s - s0;
+                if (c == 0 && k == 0) TempElevMax = temp_elev;
+                snow += s;
+                dailyEffPrec += effBefore + snowmelt_elev;
+                S[(size_t)(c * SNOW_CH + k) * p.stride] = s;
             }
-            const bool frz = (temp_elev <= P_T_SNOWFZ);
-            // accumulation and sublimation (:982-999)
-            s = s + (frz ? daily_prec_to_soil : 0.);
-            const bool more = (s > dailySoilPET);
-            const double sub = frz ? (more ? dailySoilPET : s) : 0.;
-            dailySnowEvapo += sub;
-            s = frz ? (more ? s - dailySoilPET : 0.) : s;
-            const double effBefore = frz ? 0. : daily_prec_to_soil;
-            // melt (:1003-1019)
-            const bool mlt = (temp_elev > P_T_SNOWMT) && !(s < 0.);
-            const double m_raw = ddf * (temp_elev - P_T_SNOWMT);
-            const bool all = (m_raw > s);
-            const double snowmelt_elev = mlt ? (all ? s : m_raw) : 0.;
-            s = mlt ? (all ? 0. : s - m_raw) : s;
-            snowStorageChange += s - s0;
-            if (e == 1) TempElevMax = temp_elev;
-            snow += s;
-            dailyEffPrec += effBefore + snowmelt_elev;
-            *S = s;
-            S += p.stride;
-            E += p.stride;
+            // refill the buffer just consumed with the chunk after next (same thread: no barrier)
+            if (c + 2 < SNOW_NCH)
+                stage_issue(st, buf, tid, S + (size_t)(c + 2) * SNOW_CH * p.stride, E + (size_t)(c + 2) * SNOW_CH * p.stride, p.stride);
         }
         snow /= 100.;
         dailyEffPrec /= 100.;
@@ -451,10 +485,11 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
 // number of days of river discharge kept in flight (temporal wavefront over the level graph)
 constexpr int QBUF_K = 8;
 
-__global__ void __launch_bounds__(128) k_vertical(const __grid_constant__ WgkParams p, const int dayofs) {
+__global__ void __launch_bounds__(VBLOCK) k_vertical(const __grid_constant__ WgkParams p, const int dayofs) {
+    __shared__ SnowStage stage;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.ncell) return;
-    vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3]);
+    vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3], &stage);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -502,6 +537,7 @@ __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ W
     a.s_c1[q] = 1. / (a.p_rivrgh[q] * a.roughness[r]);
     a.s_slope_pow[q] = pow(a.river_slope[r], 0.5);
     if (ps == 0) {
+        for (int b = 0; b < WGK_NBAND_K; b++) a.s_elev32[(size_t)b * p.stride + r] = a.elevation[(size_t)b * p.stride + r];
         int f = 0;
         const int ldd = a.ldd[r];
         if (a.contcell[r] && (0 != a.toBeCalculated[r])) f |= FL_ACTIVE;
@@ -1120,12 +1156,13 @@ __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkP
 // following days instead of serialising the run.
 // ----------------------------------------------------------------------------------------
 // whole day of the cells of one wide level: vertical balance, local routing, river reach, post
-__global__ void __launch_bounds__(128) k_day_level(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
+__global__ void __launch_bounds__(VBLOCK) k_day_level(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
+    __shared__ SnowStage stage;
     const int begin = p.level_off[level], end = p.level_off[level + 1];
     const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= end) return;
     const int m = blockIdx.y;
-    vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3]);
+    vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3], &stage);
     route_local_cell(p, r, m);
     const size_t mb = (size_t)m * p.stride;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
@@ -1138,10 +1175,11 @@ __global__ void __launch_bounds__(128) k_day_level(const __grid_constant__ WgkPa
 }
 
 // vertical balance + local routing of the cells [begin, end) (the cells of one tail chunk)
-__global__ void __launch_bounds__(128) k_cells_pre(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
+__global__ void __launch_bounds__(VBLOCK) k_cells_pre(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
+    __shared__ SnowStage stage;
     const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= end) return;
-    vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3]);
+    vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3], &stage);
     route_local_cell(p, r, blockIdx.y);
 }
 
