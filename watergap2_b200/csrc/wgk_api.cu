@@ -218,9 +218,11 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
     dim3 block(128);
     for (int d = 0; d < ndays; d++) {
         for (int l = 0; l < c->tail_level0; l++) {
-            const int cnt = c->level_off[l + 1] - c->level_off[l];
-            wgk::k_day_level<<<dim3((cnt + 127) / 128, c->nmember), block, 0, c->stream>>>(p, d, l);
-            n++;
+            const int begin = c->level_off[l], end = c->level_off[l + 1];
+            const dim3 g((end - begin + 127) / 128, c->nmember);
+            wgk::k_cells_pre<<<g, block, 0, c->stream>>>(p, d, begin, end);
+            wgk::k_river_level<<<g, block, 0, c->stream>>>(p, d, l);
+            n += 2;
         }
         for (size_t k = 0; k + 1 < c->chunk_lo.size(); k++) {
             const int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
@@ -238,10 +240,10 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
 }
 
 // The same tasks as a CUDA graph whose edges are exactly the data dependencies:
-//   (d, l)   <- (d, l-1)        upstream discharge of the same day
-//   (d, l)   <- (d-1, l)        own state of the previous day
-//   first sweep task of day d <- end of day d-QBUF_K   (discharge buffer reuse)
-// so that (d, l), (d+1, l-1), (d+2, l-2) ... execute concurrently.
+//   V(d, l)  <- R(d-1, l)             vertical balance + local routing: own state of the previous day
+//   R(d, l)  <- V(d, l), R(d, l-1)    river + post: upstream discharge of the same day
+//   first R task of day d <- end of day d-QBUF_K   (discharge buffer reuse)
+// so that R(d, l), R(d+1, l-1), R(d+2, l-2) ... and all V tasks execute concurrently.
 int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphExec_t *out, int *nnodes) {
     cudaGraph_t g;
     CU(cudaGraphCreate(&g, 0));
@@ -268,12 +270,16 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
         cudaGraphNode_t last = nullptr;
         bool first_sweep = true;
         for (int l = 0; l < W; l++) {
-            const int cnt = c->level_off[l + 1] - c->level_off[l];
+            int begin = c->level_off[l], end = c->level_off[l + 1];
             int dd = d, ll = l;
-            void *args[] = {&pp, &dd, &ll};
-            cudaGraphNode_t node;
-            CU(add((void *)wgk::k_day_level, dim3((cnt + 127) / 128, c->nmember), dim3(128), args,
-                   {last, prevW[l], first_sweep ? reuse : nullptr}, &node));
+            const dim3 grid((end - begin + 127) / 128, c->nmember);
+            // V(d, l): vertical balance + local routing, waits only for the cells' own previous day
+            void *a1[] = {&pp, &dd, &begin, &end};
+            cudaGraphNode_t pre, node;
+            CU(add((void *)wgk::k_cells_pre, grid, dim3(128), a1, {prevW[l]}, &pre));
+            // R(d, l): river + post, additionally waits for the upstream level of the same day
+            void *a2[] = {&pp, &dd, &ll};
+            CU(add((void *)wgk::k_river_level, grid, dim3(128), a2, {pre, last, first_sweep ? reuse : nullptr}, &node));
             first_sweep = false;
             prevW[l] = node;
             last = node;

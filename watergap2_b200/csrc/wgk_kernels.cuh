@@ -483,7 +483,7 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
 }
 
 // number of days of river discharge kept in flight (temporal wavefront over the level graph)
-constexpr int QBUF_K = 8;
+constexpr int QBUF_K = 32;
 
 __global__ void __launch_bounds__(VBLOCK) k_vertical(const __grid_constant__ WgkParams p, const int dayofs) {
     __shared__ SnowStage stage;
@@ -1164,6 +1164,24 @@ __global__ void __launch_bounds__(VBLOCK) k_day_level(const __grid_constant__ Wg
     const int m = blockIdx.y;
     vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3], &stage);
     route_local_cell(p, r, m);
+    const size_t mb = (size_t)m * p.stride;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const RiverCtx c = load_ctx(p, r, mb + r, q);
+    if (c.flags & FL_ACTIVE) {
+        double *qday = qbuf_of_day(p, dayofs);
+        route_river(p, c, r, m, mb + r, q, gather_upstream(p, c, mb, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
+    }
+    route_post_cell(p, r, m);
+}
+
+// river reach + post-pass of the cells of one wide level (the part of the day that waits for the
+// upstream level); the vertical balance and the local routing of the same cells run in a separate,
+// earlier task (k_cells_pre) that only waits for the cells' own previous day
+__global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
+    const int begin = p.level_off[level], end = p.level_off[level + 1];
+    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= end) return;
+    const int m = blockIdx.y;
     const size_t mb = (size_t)m * p.stride;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
     const RiverCtx c = load_ctx(p, r, mb + r, q);
