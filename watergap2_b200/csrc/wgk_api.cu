@@ -182,7 +182,15 @@ void drop_graph(wgk_ctx *c) {
 }
 
 constexpr int MAX_CALL_DAYS = 366;
-constexpr int LEVELS_PER_CHUNK = 8;
+int levels_per_chunk() {  // tuning knob (WGK_LEVELS_PER_CHUNK); measured optimum on B200: 1
+    const char *e = getenv("WGK_LEVELS_PER_CHUNK");
+    const int v = e ? atoi(e) : 1;
+    return v > 0 ? v : 1;
+}
+bool fuse_narrow() {  // WGK_FUSE_NARROW=1: one fused task (k_day_level) per narrow level instead of V + R
+    const char *e = getenv("WGK_FUSE_NARROW");
+    return e && atoi(e) != 0;
+}
 
 // plain launches of one simulated day (day offset `d` of the current call) on c->stream, phase
 // by phase over the whole grid; used by the three-call class-shim path and by wgk_profile_day
@@ -287,6 +295,16 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
         for (int k = 0; k < C; k++) {
             int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
             int begin = c->level_off[lo], end = c->level_off[hi], dd = d;
+            if (fuse_narrow() && hi == lo + 1) {
+                void *af[] = {&pp, &dd, &lo};
+                cudaGraphNode_t node;
+                CU(add((void *)wgk::k_day_level, dim3((end - begin + 127) / 128, c->nmember), dim3(128), af,
+                       {prevT[k], last, first_sweep ? reuse : nullptr}, &node));
+                first_sweep = false;
+                prevT[k] = node;
+                last = node;
+                continue;
+            }
             void *a1[] = {&pp, &dd, &begin, &end};
             cudaGraphNode_t pre, sweep;
             CU(add((void *)wgk::k_cells_pre, dim3((end - begin + 127) / 128, c->nmember), dim3(128), a1, {prevT[k]}, &pre));
@@ -369,7 +387,10 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     c->npset = npset;
     if (opt) c->opt = *opt;
     else { c->opt.restart = 0; c->opt.tail_threshold = 0; c->opt.use_graph = 1; }
-    if (c->opt.tail_threshold <= 0) c->opt.tail_threshold = 256;
+    if (c->opt.tail_threshold <= 0) {
+        const char *e = getenv("WGK_TAIL_THRESHOLD");
+        c->opt.tail_threshold = (e && atoi(e) > 0) ? atoi(e) : 256;
+    }
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
@@ -485,7 +506,7 @@ int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downs
         else break;
     }
     c->chunk_lo.clear();
-    for (int l = c->tail_level0; l < c->nlevels; l += LEVELS_PER_CHUNK) c->chunk_lo.push_back(l);
+    for (int l = c->tail_level0; l < c->nlevels; l += levels_per_chunk()) c->chunk_lo.push_back(l);
     if (c->tail_level0 < c->nlevels) c->chunk_lo.push_back(c->nlevels);
     auto upload = [&](int32_t *&dptr, const std::vector<int32_t> &v) -> cudaError_t {
         if (dptr) cudaFree(dptr);
