@@ -9,7 +9,7 @@
 //       The run writes the reference's txt state files (16 significant digits).
 //
 //   ref_harness replay <config.txt> <dump.wgd> [--days A-B] [--every K] [--snow-days A-B]
-//                      [--final-state PREFIX] [--time-only] [--day-times FILE]
+//                      [--final-state PREFIX] [--time-only] [--day-times FILE] [--deep-snow]
 //       replays the orchestration of integrate_wghm_ (integrateWGHM.cpp:127-309 init
 //       sequence, :546-922 year/month/day loops) calling the reference's own
 //       dailyWaterBalanceClass::calcNewDay / routingClass::routing /
@@ -234,7 +234,7 @@ static int run_replay(int argc, char **argv) {
     const char *dumpfile = argv[3];
     Range days, snowdays;
     int every = 0;
-    bool time_only = false;
+    bool time_only = false, deep_snow = false;
     std::string final_prefix, day_times_file;
     std::vector<double> day_times;
     for (int i = 4; i < argc; i++) {
@@ -244,6 +244,7 @@ static int run_replay(int argc, char **argv) {
         else if (a == "--every" && i + 1 < argc) every = atoi(argv[++i]);
         else if (a == "--final-state" && i + 1 < argc) final_prefix = argv[++i];
         else if (a == "--time-only") time_only = true;
+        else if (a == "--deep-snow") deep_snow = true;
         else if (a == "--day-times" && i + 1 < argc) day_times_file = argv[++i];
     }
     if (!time_only && strcmp(dumpfile, "-") != 0) {
@@ -328,6 +329,20 @@ static int run_replay(int argc, char **argv) {
         else if (actual_year == end_year) start_month = 1;
         else { start_month = 1; end_month = 12; }
         if (!static_done) {
+            if (deep_snow) {
+                // fixture for the 1000 mm snow cap (daily.cpp:958-976), which a run from empty storages does
+                // not reach within months: preload the band snow of every third cell through the public
+                // grid (the reference's code is untouched, only its start state differs)
+                for (int n = 0; n < ng; n += 3) {
+                    double sum = 0.;
+                    for (short e = 1; e <= 100; e++) {
+                        double v = ((n / 3) % 2) ? 900. + 3. * e : (double)((n * 131 + e * 37) % 1400) + 0.25 * e;
+                        dailyWaterBalance.G_SnowInElevation(n, e) = v;
+                        sum += v;
+                    }
+                    dailyWaterBalance.G_snow[n] = sum / 100.;
+                }
+            }
             dump_static(*calParam);
             dump_state(0, true);
             static_done = true;

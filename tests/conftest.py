@@ -21,6 +21,16 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_deep(golden):
+    """The same 1000-cell world started with up to 1400 mm of snow in the elevation bands of every
+    third cell (reference harness --deep-snow): day-0 records of `golden` with the band snow replaced."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ref_ng1000_deepsnow.npz"))
+    g = {k: v for k, v in golden.items() if k.startswith("d0/") or k.startswith("forcing") or k == "ng"}
+    g.update({k: z[k] for k in z.files})
+    return g
+
+
+@pytest.fixture(scope="session")
 def oracle_lib():
     from oracle import wgo
     wgo.build()

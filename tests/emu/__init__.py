@@ -24,7 +24,7 @@ def build():
 
 
 class Emu:
-    def __init__(self, ncell, rout_order, downstream):
+    def __init__(self, ncell, rout_order, downstream, form="bands"):
         L = ctypes.CDLL(build())
         vp, ci = ctypes.c_void_p, ctypes.c_int
         L.emu_create.restype = vp
@@ -37,6 +37,8 @@ class Emu:
         ro = np.ascontiguousarray(rout_order, np.int32)
         dn = np.ascontiguousarray(downstream, np.int32)
         self.e = L.emu_create(ncell, ro.ctypes.data, dn.ctypes.data)
+        L.emu_set_form.argtypes = [vp, ci]
+        L.emu_set_form(self.e, {"bands": 0, "cells": 1}[form])
 
     def set(self, name, arr, dtype):
         a = np.ascontiguousarray(np.asarray(arr).astype(dtype))

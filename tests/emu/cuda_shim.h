@@ -26,4 +26,6 @@ static inline void __syncthreads() {}
 static inline void __pipeline_memcpy_async(void *dst, const void *src, size_t n) { std::memcpy(dst, src, n); }
 static inline void __pipeline_commit() {}
 static inline void __pipeline_wait_prior(int) {}
+static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
+static inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
 using std::exp; using std::pow; using std::sqrt; using std::fabs; using std::log; using std::cbrt; using std::fma;

@@ -29,6 +29,8 @@ struct Emu {
     std::vector<double> gbody, qbuf;
     int32_t cal_days[8] = {0};
     int32_t cal[8] = {0};
+    bool derived = false;
+    int form = 0;  // 0: band-parallel tiles, 1: thread per cell
 };
 
 template <class K, class... A> static void launch(K kern, dim3 grid, dim3 block, A... args) {
@@ -84,6 +86,7 @@ static const Field *find(const char *name) {
 int emu_set(Emu *e, const char *name, const void *host) {
     const Field *f = find(name);
     if (!f) return -1;
+    e->derived = false;
     char *dst = *(char **)((char *)&e->p.a + f->offset);
     if (f->scope == WGK_SCOPE_TABLE) { memcpy(dst, host, (size_t)18 * f->elsize); return 0; }
     for (int r = 0; r < e->ncell; r++)
@@ -111,14 +114,59 @@ void emu_set_forcing(Emu *e, const float *P, const float *T, const float *SW, co
         }
 }
 
-// tail_level0 < 0: every level through the fused per-(day, level) kernel k_day_level; else levels
-// >= tail_level0 through k_cells_pre + the tail-chunk path (emulated level by level, because a
-// CTA whose threads run one after the other is only equivalent to the real one between barriers)
+// k_cells_pre on the host: the phases of vertical_tile() in the order of the kernel, each phase run
+// for all threads of the CTA before the next one starts (= the barriers of the kernel)
+static void emu_cells_pre(Emu *e, int begin, int end) {
+    using namespace wgk;
+    WgkParams &p = e->p;
+    if (e->form == 1) {  // thread-per-cell form
+        launch(k_cells_pre_tpc, dim3((end - begin + VBLOCK - 1) / VBLOCK, 1), dim3(VBLOCK), p, 0, begin, end);
+        return;
+    }
+    static VTile sm;
+    static VThread ts[V_THREADS];
+    const int slot = p.cal_days[3], m = 0;
+    for (int tile = 0; tile < v_num_tiles(begin, end); tile++) {
+        const int r0 = (begin & ~3) + 32 * tile;
+        auto each = [&](auto fn) { for (int t = 0; t < V_THREADS; t++) fn(t >> 5, t & 31, ts[t]); };
+        each([&](int w, int lane, VThread &) { if (w == 0) v_mode(p, sm, r0, begin, end, m, slot, lane); else v_preload(p, sm, r0, begin, end, m, slot, w, lane); });
+        if (sm.nband_cells == 0) {
+            for (int lane = 0; lane < 32; lane++) v_head(p, sm, r0, m, slot, lane);
+            for (int lane = 0; lane < 32; lane++) v_bare_sums(p, sm, r0, lane);
+        } else {
+            each([&](int w, int lane, VThread &t) { v_prefetch(p, sm, t, r0, m, 0, w, lane); });
+            for (int lane = 0; lane < 32; lane++) v_head(p, sm, r0, m, slot, lane);
+            for (int slab = 0; slab < V_NSLAB; slab++) {
+                each([&](int w, int lane, VThread &t) { v_scale(p, sm, t, r0, m, slab, w, lane); });
+                if (sm.cap_any[slab]) each([&](int w, int lane, VThread &t) { v_cap_resolve(sm, t, slab, w, lane); });
+                each([&](int w, int lane, VThread &t) { v_band(p, sm, t, r0, m, slab, w, lane); });
+                each([&](int w, int lane, VThread &t) { if (w < 4) v_sum(sm, t, slab, w, lane); });
+            }
+        }
+        for (int lane = 0; lane < 32; lane++) v_finish<true>(p, sm, r0, begin, end, m, lane);
+    }
+}
+
+static void emu_river(Emu *e, int l, int day, int month) {
+    WgkParams &p = e->p;
+    double *qday = wgk::qbuf_of_day(p, 0);
+    for (int r = e->level_off[l]; r < e->level_off[l + 1]; r++) {
+        const wgk::RiverCtx c = wgk::load_ctx(p, r, (size_t)r, (size_t)r);
+        if (c.flags & wgk::FL_ACTIVE) wgk::route_river(p, c, r, 0, (size_t)r, (size_t)r, wgk::gather_upstream(p, c, 0, qday), day, month, qday);
+    }
+}
+
+// tail_level0 < 0: every level as its own (V, R) task pair; else the levels >= tail_level0 as one
+// k_cells_pre over all their cells followed by the level-by-level river sweep and the post-pass
 void emu_day(Emu *e, int day, int month, int dom, int slot, int tail_level0) {
     e->cal_days[0] = day; e->cal_days[1] = month; e->cal_days[2] = dom; e->cal_days[3] = slot;
     WgkParams &p = e->p;
     dim3 block(128), grid((e->ncell + 127) / 128, 1);
-    launch(wgk::k_derive_static, grid, block, p);
+    if (!e->derived) {
+        launch(wgk::k_derive_static, grid, block, p);
+        launch(wgk::k_derive_member, grid, block, p);
+        e->derived = true;
+    }
     if (e->gidx.empty()) {
         e->gidx.assign(e->ncell, -1);
         int n = 0;
@@ -129,22 +177,19 @@ void emu_day(Emu *e, int day, int month, int dom, int slot, int tail_level0) {
     }
     int t0 = tail_level0 < 0 ? e->nlevels : tail_level0;
     for (int l = 0; l < t0; l++) {
-        int cnt = e->level_off[l + 1] - e->level_off[l];
-        launch(wgk::k_day_level, dim3((cnt + 127) / 128, 1), block, p, 0, l);
+        emu_cells_pre(e, e->level_off[l], e->level_off[l + 1]);
+        emu_river(e, l, day, month);
+        for (int r = e->level_off[l]; r < e->level_off[l + 1]; r++) wgk::route_post_cell(p, r, 0);
     }
     if (t0 < e->nlevels) {
         int begin = e->level_off[t0], end = e->level_off[e->nlevels];
-        launch(wgk::k_cells_pre, dim3((end - begin + 127) / 128, 1), block, p, 0, begin, end);
-        double *qday = wgk::qbuf_of_day(p, 0);
-        for (int l = t0; l < e->nlevels; l++)
-            for (int r = e->level_off[l]; r < e->level_off[l + 1]; r++) {
-                const wgk::RiverCtx c = wgk::load_ctx(p, r, (size_t)r, (size_t)r);
-                if (c.flags & wgk::FL_ACTIVE) wgk::route_river(p, c, r, 0, (size_t)r, (size_t)r, wgk::gather_upstream(p, c, 0, qday), day, month, qday);
-            }
+        emu_cells_pre(e, begin, end);
+        for (int l = t0; l < e->nlevels; l++) emu_river(e, l, day, month);
         for (int r = begin; r < end; r++) wgk::route_post_cell(p, r, 0);
     }
     memcpy(p.a.discharge, wgk::qbuf_of_day(p, 0), sizeof(double) * e->stride);
 }
 
+void emu_set_form(Emu *e, int form) { e->form = form; }
 int emu_nlevels(Emu *e) { return e->nlevels; }
 }

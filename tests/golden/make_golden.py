@@ -55,6 +55,23 @@ def main():
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) / 1e6, "MB")
 
+    # second fixture: the same world started with 0..1400 mm of snow in the elevation bands of every
+    # third cell (harness option --deep-snow), so that the 1000 mm cap of daily.cpp:958-976 and the
+    # melt/sublimation branches of deep snow packs are pinned; statics and forcing are those above
+    dump2 = os.path.join(tmp, "dump_deep.wgd")
+    subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", f"ref_harness_{NG}"), "replay",
+                           os.path.join(tmp, "config.txt"), dump2, "--days", "1-6", "--snow-days", "1-6", "--deep-snow"],
+                          stdout=subprocess.DEVNULL, cwd=tmp)
+    recs = wgo.read_dump(dump2, days={0, 1, 2, 6})
+    deep = {"days": np.array([1, 2, 6], np.int32)}
+    for (name, day), a in recs.items():
+        if day == 0 and name not in ("snow_bands", "snow"):
+            continue  # as in ref_ng1000.npz
+        deep[f"d{day}/{name}"] = a
+    path = os.path.join(ROOT, "tests", "golden", f"ref_ng{NG}_deepsnow.npz")
+    np.savez_compressed(path, **deep)
+    print("wrote", path, os.path.getsize(path) / 1e6, "MB")
+
 
 if __name__ == "__main__":
     main()

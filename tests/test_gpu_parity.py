@@ -18,7 +18,14 @@ def _model_from(fields, topo_ro, topo_down, ng, **kw):
     return m
 
 
-def test_gpu_vs_reference_golden(golden):
+@pytest.fixture(params=["bands", "cells"])
+def form(request, monkeypatch):
+    """both forms of the vertical kernel: CTA-cooperative band-parallel / thread per cell"""
+    monkeypatch.setenv("WGK_VERTICAL_FORM", request.param)
+    return request.param
+
+
+def test_gpu_vs_reference_golden(golden, form):
     """59 days on the 1000-cell world, compared with what the compiled reference held in memory."""
     ng = int(golden["ng"])
     d0 = golden_day(golden, 0)
@@ -45,6 +52,29 @@ def test_gpu_vs_reference_golden(golden):
                     assert_parity(name, ref, m.get(name), rtol=rtol, max_flips=max(1, ref.size // 200))
                     nchk += 1
     assert nchk > 200
+
+
+def test_gpu_deep_snow_vs_reference_golden(golden_deep, form):
+    """snow packs of up to 1400 mm per band (reference harness --deep-snow): the 1000 mm cap of
+    daily.cpp:958-976, sublimation and melt of deep packs, and the s_snowfree bookkeeping of the
+    band-parallel kernel (cells flip between the bare fast path and the band loop)."""
+    g = golden_deep
+    ng = int(g["ng"])
+    d0 = golden_day(g, 0)
+    ro = np.zeros(ng, np.int32)
+    ro[d0["routing_cell"] - 1] = np.arange(1, ng + 1)
+    m = _model_from(d0, ro, d0["downstream_cell"], ng)
+    m.forcing_reserve(31)
+    f = {k: g[f"forcing1/{k}"] for k in ("P", "T", "SW", "LW")}
+    m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+    nchk = 0
+    for sd, n in ((1, 1), (2, 1), (6, 4)):  # days 3-6 in one call: the wavefront graph with 4 days in flight
+        m.step_days(sd - n + 1, 0, sd - n + 1, sd - n, n)
+        for name, ref in golden_day(g, sd).items():
+            if m.has_field(name) and name != "status_laf_next":
+                assert_parity(name, ref, m.get(name), rtol=1e-12 if name in ("snow_bands", "snow") else 1e-10)
+                nchk += 1
+    assert nchk > 100
 
 
 def _run_pair(world, ndays, nmember=1, use_graph=1, psets=None, block=1):
@@ -97,7 +127,7 @@ def _compare(oracles, m, names, free_run=True):
     return flips
 
 
-def test_gpu_vs_oracle_3000_cells(world3000):
+def test_gpu_vs_oracle_3000_cells(world3000, form):
     from oracle import wg_init
     oracles, m = _run_pair(world3000, 30, block=7)
     _compare(oracles, m, wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS)

@@ -15,8 +15,8 @@ import pytest
 from tests.util import rel_err
 
 
-@pytest.mark.parametrize("tail_level0", [-1, 3])
-def test_kernel_source_on_host_matches_oracle(world3000, oracle_lib, tail_level0):
+@pytest.mark.parametrize("tail_level0,form", [(-1, "bands"), (3, "bands"), (3, "cells")])
+def test_kernel_source_on_host_matches_oracle(world3000, oracle_lib, tail_level0, form):
     from oracle import synth_world as sw, wg_init
     from tests.emu import Emu
     wgo = oracle_lib
@@ -27,7 +27,7 @@ def test_kernel_source_on_host_matches_oracle(world3000, oracle_lib, tail_level0
     for k, v in ini.items():
         if not k.startswith("_") and o.has(k):
             o.set(k, v)
-    e = Emu(w.ng, topo["rout_order"], topo["outflow_cell"])
+    e = Emu(w.ng, topo["rout_order"], topo["outflow_cell"], form)
     e.load(ini, o)
     names = wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS
     worst = 0.0
@@ -50,3 +50,44 @@ def test_kernel_source_on_host_matches_oracle(world3000, oracle_lib, tail_level0
                     worst = max(worst, d)
                     assert d < 2e-11, f"day {sd} {nm}: {d:.2e}"
     assert worst > 0  # the four substitutions are really in effect
+
+
+@pytest.mark.parametrize("form", ["bands", "cells"])
+def test_kernel_source_deep_snow_vs_reference_golden(golden_deep, oracle_lib, form):
+    """band-parallel snow kernel on packs of up to 1400 mm per band (1000 mm cap, daily.cpp:958-976)
+    against what the compiled reference held in memory; the snow bands themselves must be within
+    1e-12 (no libm call is involved in the band loop), integer state exact."""
+    from tests.emu import Emu
+    from tests.util import golden_day
+    g = golden_deep
+    ng = int(g["ng"])
+    d0 = golden_day(g, 0)
+    o = oracle_lib.Oracle(ng)
+    o.load_records({(k, 0): v for k, v in d0.items()}, 0)
+    d0 = dict(d0)
+    d0["params"] = d0["params"].reshape(26, ng)
+    d0.setdefault("lake_depth_active", d0["params"][5] * 0.001)  # routing.cpp:5613-5628
+    d0.setdefault("wetl_depth_active", d0["params"][6] * 0.001)
+    ro = np.zeros(ng, np.int32)
+    ro[d0["routing_cell"] - 1] = np.arange(1, ng + 1)
+    e = Emu(ng, ro, d0["downstream_cell"], form)
+    e.load(d0, o)
+    e.set_forcing({k: g[f"forcing1/{k}"] for k in ("P", "T", "SW", "LW")})
+    n = 0
+    for sd in range(1, 7):
+        e.day(sd, 0, sd, sd - 1, -1)
+        if sd in (1, 2, 6):
+            for nm, ref in golden_day(g, sd).items():
+                if not o.has(nm) or nm in ("status_laf_next",):
+                    continue
+                try:
+                    got = e.get(nm, ref)
+                except AssertionError:
+                    continue
+                if ref.dtype.kind != "f":
+                    assert np.array_equal(ref, got), f"day {sd} {nm}"
+                else:
+                    d = float(rel_err(nm, ref, got).max())
+                    assert d < (1e-12 if nm in ("snow_bands", "snow") else 2e-11), f"day {sd} {nm}: {d:.2e}"
+                n += 1
+    assert n > 100

@@ -41,6 +41,25 @@ def test_oracle_bit_exact_vs_reference_golden(golden, oracle_lib):
     assert (g59["res_stor"] > 0).sum() >= 5 and (g59["glo_lake_stor"] != 0).sum() >= 5
 
 
+def test_oracle_bit_exact_deep_snow(golden_deep, oracle_lib):
+    """snow packs of up to 1400 mm per band: pins the 1000 mm cap (daily.cpp:958-976), sublimation
+    and melt of deep packs; bands, sums and all downstream fluxes bit-identical for 6 days."""
+    wgo = oracle_lib
+    g = golden_deep
+    o = _oracle_from_golden(wgo, g)
+    assert (golden_day(g, 0)["snow_bands"] > 1000).sum() > 5000
+    o.set_forcing_month({k: g[f"forcing1/{k}"] for k in ("P", "T", "SW", "LW")})
+    checked = 0
+    for sd in range(1, 7):
+        o.step_day(sd, 0, sd)
+        if sd in (1, 2, 6):
+            for name, ref in golden_day(g, sd).items():
+                if o.has(name):
+                    assert np.array_equal(ref, o.field(name)), f"day {sd} field {name}: {int((ref != o.field(name)).sum())} differ"
+                    checked += 1
+    assert checked > 100
+
+
 def test_topology_bit_exact_vs_reference_files(golden, oracle_lib, world1000):
     """rout_prepare.cpp restatement against the routing files the reference wrote."""
     wgo = oracle_lib

@@ -95,6 +95,8 @@ struct wgk_ctx {
     std::map<int, int> graph_nodes;
     int64_t launches = 0;
     bool derived_dirty = true;  // s_c1 / s_slope_pow / s_flags need (re)computation
+    bool member_dirty = true;   // s_snowfree needs (re)computation (band state uploaded or exposed)
+    bool band_parallel = true;  // vertical kernel form: CTA-cooperative band-parallel (few members) or thread per cell
     int32_t *d_gidx = nullptr;  // [ncell] index into the global-water-body scratch or -1
     double *d_gbody = nullptr;  // [nmember][ngbody][GB_N]
     int ngbody = 0;
@@ -187,16 +189,24 @@ int levels_per_chunk() {  // tuning knob (WGK_LEVELS_PER_CHUNK); measured optimu
     const int v = e ? atoi(e) : 1;
     return v > 0 ? v : 1;
 }
-bool fuse_narrow() {  // WGK_FUSE_NARROW=1: one fused task (k_day_level) per narrow level instead of V + R
-    const char *e = getenv("WGK_FUSE_NARROW");
-    return e && atoi(e) != 0;
+
+void launch_cells_pre(wgk_ctx *c, const WgkParams &p, int d, int begin, int end) {
+    if (c->band_parallel)
+        wgk::k_cells_pre<<<dim3(wgk::v_num_tiles(begin, end), c->nmember), wgk::V_THREADS, 0, c->stream>>>(p, d, begin, end);
+    else
+        wgk::k_cells_pre_tpc<<<dim3((end - begin + wgk::VBLOCK - 1) / wgk::VBLOCK, c->nmember), wgk::VBLOCK, 0, c->stream>>>(p, d, begin, end);
+}
+void launch_vertical(wgk_ctx *c, const WgkParams &p, int d) {
+    if (c->band_parallel)
+        wgk::k_vertical<<<dim3(wgk::v_num_tiles(0, c->ncell), c->nmember), wgk::V_THREADS, 0, c->stream>>>(p, d);
+    else
+        wgk::k_vertical_tpc<<<dim3((c->ncell + wgk::VBLOCK - 1) / wgk::VBLOCK, c->nmember), wgk::VBLOCK, 0, c->stream>>>(p, d);
 }
 
 // plain launches of one simulated day (day offset `d` of the current call) on c->stream, phase
 // by phase over the whole grid; used by the three-call class-shim path and by wgk_profile_day
 int enqueue_vertical(wgk_ctx *c, const WgkParams &p, int d) {
-    dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
-    wgk::k_vertical<<<grid, block, 0, c->stream>>>(p, d);
+    launch_vertical(c, p, d);
     return 1;
 }
 int enqueue_routing(wgk_ctx *c, const WgkParams &p, int d) {
@@ -228,14 +238,14 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
         for (int l = 0; l < c->tail_level0; l++) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
             const dim3 g((end - begin + 127) / 128, c->nmember);
-            wgk::k_cells_pre<<<g, block, 0, c->stream>>>(p, d, begin, end);
+            launch_cells_pre(c, p, d, begin, end);
             wgk::k_river_level<<<g, block, 0, c->stream>>>(p, d, l);
             n += 2;
         }
         for (size_t k = 0; k + 1 < c->chunk_lo.size(); k++) {
             const int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
             const int begin = c->level_off[lo], end = c->level_off[hi];
-            wgk::k_cells_pre<<<dim3((end - begin + 127) / 128, c->nmember), block, 0, c->stream>>>(p, d, begin, end);
+            launch_cells_pre(c, p, d, begin, end);
             wgk::k_tail_chunk<<<c->nmember, 256, 0, c->stream>>>(p, d, lo, hi);
             n += 2;
         }
@@ -273,6 +283,11 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
         return cudaGraphAddKernelNode(node, g, dd.data(), dd.size(), &kp);
     };
     WgkParams pp = p;
+    void *pre_fn = c->band_parallel ? (void *)wgk::k_cells_pre : (void *)wgk::k_cells_pre_tpc;
+    const dim3 pre_block(c->band_parallel ? wgk::V_THREADS : wgk::VBLOCK);
+    auto pre_grid = [&](int begin, int end) {
+        return c->band_parallel ? dim3(wgk::v_num_tiles(begin, end), c->nmember) : dim3((end - begin + wgk::VBLOCK - 1) / wgk::VBLOCK, c->nmember);
+    };
     for (int d = 0; d < ndays; d++) {
         cudaGraphNode_t reuse = (d >= wgk::QBUF_K) ? dayEnd[d - wgk::QBUF_K] : nullptr;
         cudaGraphNode_t last = nullptr;
@@ -284,7 +299,7 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
             // V(d, l): vertical balance + local routing, waits only for the cells' own previous day
             void *a1[] = {&pp, &dd, &begin, &end};
             cudaGraphNode_t pre, node;
-            CU(add((void *)wgk::k_cells_pre, grid, dim3(128), a1, {prevW[l]}, &pre));
+            CU(add(pre_fn, pre_grid(begin, end), pre_block, a1, {prevW[l]}, &pre));
             // R(d, l): river + post, additionally waits for the upstream level of the same day
             void *a2[] = {&pp, &dd, &ll};
             CU(add((void *)wgk::k_river_level, grid, dim3(128), a2, {pre, last, first_sweep ? reuse : nullptr}, &node));
@@ -295,19 +310,9 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
         for (int k = 0; k < C; k++) {
             int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
             int begin = c->level_off[lo], end = c->level_off[hi], dd = d;
-            if (fuse_narrow() && hi == lo + 1) {
-                void *af[] = {&pp, &dd, &lo};
-                cudaGraphNode_t node;
-                CU(add((void *)wgk::k_day_level, dim3((end - begin + 127) / 128, c->nmember), dim3(128), af,
-                       {prevT[k], last, first_sweep ? reuse : nullptr}, &node));
-                first_sweep = false;
-                prevT[k] = node;
-                last = node;
-                continue;
-            }
             void *a1[] = {&pp, &dd, &begin, &end};
             cudaGraphNode_t pre, sweep;
-            CU(add((void *)wgk::k_cells_pre, dim3((end - begin + 127) / 128, c->nmember), dim3(128), a1, {prevT[k]}, &pre));
+            CU(add(pre_fn, pre_grid(begin, end), pre_block, a1, {prevT[k]}, &pre));
             void *a2[] = {&pp, &dd, &lo, &hi};
             CU(add((void *)wgk::k_tail_chunk, dim3(c->nmember), dim3(256), a2, {pre, last, first_sweep ? reuse : nullptr}, &sweep));
             first_sweep = false;
@@ -333,6 +338,12 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
 // inflow-independent river constants and cell class flags, recomputed after any static or
 // parameter upload (never inside a graph capture)
 int ensure_derived(wgk_ctx *c) {
+    if (c->member_dirty) {
+        dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
+        wgk::k_derive_member<<<grid, block, 0, c->stream>>>(make_params(c));
+        c->launches++;
+        c->member_dirty = false;
+    }
     if (!c->derived_dirty) return 0;
     dim3 block(128), grid((c->ncell + 127) / 128, c->npset);
     wgk::k_derive_static<<<grid, block, 0, c->stream>>>(make_params(c));
@@ -387,12 +398,25 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     c->npset = npset;
     if (opt) c->opt = *opt;
     else { c->opt.restart = 0; c->opt.tail_threshold = 0; c->opt.use_graph = 1; }
+    {   // small problems (members x cells cannot fill the GPU with one thread per cell): the cell-day -> cell-day
+        // latency chain bounds the run, use the band-parallel form; otherwise the thread-per-cell form, which
+        // keeps every lane busy in the scalar parts of the step
+        const char *e = getenv("WGK_VERTICAL_FORM");  // "bands" | "cells" (tests exercise both)
+        if (e && !strcmp(e, "bands")) c->band_parallel = true;
+        else if (e && !strcmp(e, "cells")) c->band_parallel = false;
+        else c->band_parallel = ((long long)nmember * ncell < 32768);
+    }
     if (c->opt.tail_threshold <= 0) {
         const char *e = getenv("WGK_TAIL_THRESHOLD");
         c->opt.tail_threshold = (e && atoi(e) > 0) ? atoi(e) : 256;
     }
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // the tile kernels stage 36 KB per CTA: ask for the largest shared-memory carve-out so that 6 CTAs fit an SM
+    CU(cudaFuncSetAttribute((const void *)wgk::k_cells_pre, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute((const void *)wgk::k_vertical, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute((const void *)wgk::k_cells_pre_tpc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute((const void *)wgk::k_vertical_tpc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     c->own_stream = true;
     for (int f = 0; f < WGK_F_COUNT; f++) {
         const size_t bytes = field_rows(c, f) * field_row_elems(c, f) * kFields[f].elsize;
@@ -601,6 +625,7 @@ static int set_field_raw(wgk_ctx *c, int f, int index, const void *host, size_t 
     CU(cudaMemcpyAsync(dst, tmp, row_bytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (fi.scope != WGK_SCOPE_MEMBER) c->derived_dirty = true;
+    if (f == WGK_F_snow_bands) c->member_dirty = true;
     return WGK_OK;
 }
 
@@ -671,6 +696,7 @@ int wgk_set_member_pset(wgk_ctx *c, int member, int pset) {
 void *wgk_device_ptr(wgk_ctx *c, int f, int member) {
     if (!c || f < 0 || f >= WGK_F_COUNT) return nullptr;
     if (member < 0 || (size_t)member >= field_rows(c, f)) return nullptr;
+    if (f == WGK_F_snow_bands) c->member_dirty = true;  // the caller may write the bands on the device
     return (char *)*field_slot(c, f) + (size_t)member * field_row_elems(c, f) * kFields[f].elsize;
 }
 
@@ -882,7 +908,7 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     const WgkParams p = make_params(c);
     dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
     CU(cudaEventRecord(ev[0], c->stream));
-    wgk::k_vertical<<<grid, block, 0, c->stream>>>(p, 0);
+    launch_vertical(c, p, 0);
     CU(cudaEventRecord(ev[1], c->stream));
     wgk::k_route_local<<<grid, block, 0, c->stream>>>(p);
     CU(cudaEventRecord(ev[2], c->stream));

@@ -125,8 +125,15 @@
     /* ---- derived once from the statics (k_derive_static) ---- */ \
     X(s_c1, double, "f64", PSET, 1) \
     X(s_slope_pow, double, "f64", PSET, 1) \
+    X(s_ekg, double, "f64", PSET, 1) \
+    X(s_invkg, double, "f64", PSET, 1) \
     X(s_flags, int8_t, "i8", CELL, 1) \
     X(s_elev32, int32_t, "i32", CELL, 101) \
+    X(s_delev, int16_t, "i16", CELL, 101) \
+    X(s_de_min, int16_t, "i16", CELL, 1) \
+    X(s_de_max, int16_t, "i16", CELL, 1) \
+    /* ---- derived from the member state (k_derive_member), maintained by the vertical kernel ---- */ \
+    X(s_snowfree, int8_t, "i8", MEMBER, 1) \
     /* ---- land cover tables (LCT_22.DAT / LAI_22.DAT; daily.h:204-208, lai.h) ---- */ \
     X(lai_factor_a, float, "f32", TABLE, 1) \
     X(lai_factor_b, float, "f32", TABLE, 1) \

@@ -156,19 +156,16 @@ __device__ __forceinline__ double lai_nogrowing(int &days, int initialDays, int 
 }
 
 // ----------------------------------------------------------------------------------------
-// vertical water balance
+// vertical water balance, one thread per cell (throughput form, used when members x cells fill the GPU)
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, const int m, const int slot, SnowStage *st) {
     const WgkArrays &a = p.a;
     if (!a.contcell[r]) return;  // integrateWGHM.cpp:772
     const size_t i = (size_t)m * p.stride + r;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
-    // start streaming the snow bands (bands 1..100; band 0 is the unused mean slot)
     const int tid = threadIdx.x;
     double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r + p.stride;
     const int32_t *__restrict__ E = a.s_elev32 + r + p.stride;
-    stage_issue(st, 0, tid, S, E, p.stride);
-    stage_issue(st, 1, tid, S + (size_t)SNOW_CH * p.stride, E + (size_t)SNOW_CH * p.stride, p.stride);
 
     // daily.cpp:159-169, routing.h:246-251
     const int started = a.status_laf_next[i];
@@ -178,13 +175,28 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
     else if (p.restart == 1) lafPrev = a.land_area_frac_prev[i];
     else lafPrev = landAreaFrac;
 
-    if (1 != a.toBeCalculated[r]) {  // daily.cpp:177
-        __pipeline_wait_prior(0);
-        return;
+    if (1 != a.toBeCalculated[r]) return;  // daily.cpp:177
+
+    const float4 f = p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r];
+    const int lc = a.landcover[r] - 1;
+    const double P_T_SNOWFZ = a.p_snowfz[q];
+    const double P_T_SNOWMT = a.p_snowmt[q];
+    const double P_T_GRADNT = a.p_gradnt[q];
+    const double ddf = a.p_degday[q] * a.lct_ddf[lc];  // (M_DEGDAY_F * ddf_lct) * (...) keeps the reference association
+    const bool noland = (landAreaFrac <= 0.);
+    // cells without snow whose lowest and highest band are above the freezing threshold take no part
+    // in the band loop (see the note on the band-parallel form below); the band columns of the others
+    // start streaming now (bands 1..100; band 0 is the unused mean slot)
+    bool bare = false;
+    if (a.s_snowfree[i]) {
+        const double t_top = (double)f.y - ((double)a.s_de_max[r] * P_T_GRADNT), t_bot = (double)f.y - ((double)a.s_de_min[r] * P_T_GRADNT);
+        bare = noland || (ddf >= 0. && t_top > P_T_SNOWFZ && t_bot > P_T_SNOWFZ);
+    }
+    if (!bare) {
+        stage_issue(st, 0, tid, S, E, p.stride);
+        stage_issue(st, 1, tid, S + (size_t)SNOW_CH * p.stride, E + (size_t)SNOW_CH * p.stride, p.stride);
     }
 
-    const int lc = a.landcover[r] - 1;
-    const float4 f = p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r];
     double dailyPrec = (double)f.x;
     const double dailyTempC = (double)f.y;
     const double dailyShortWave = (double)f.z;
@@ -267,11 +279,6 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
     double storage_transfer = 0.;
     double land_aet = 0., land_aet_uncorr = 0.;
 
-    const double P_T_SNOWFZ = a.p_snowfz[q];
-    const double P_T_SNOWMT = a.p_snowmt[q];
-    const double P_T_GRADNT = a.p_gradnt[q];
-    const double M_DEGDAY_F = a.p_degday[q];
-    const bool noland = (landAreaFrac <= 0.);
 
     // interception (:825-894)
     double canopy = a.canopy[i];
@@ -317,8 +324,19 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
     // the cells of one warp sit in different regimes (accumulating / melting / bare) on a given day.
     double TempElevMax = 0., snowStorageChange = 0., snow = 0.;
     const int elev0 = a.s_elev32[r];
-    const double ddf = M_DEGDAY_F * a.lct_ddf[lc];  // (M_DEGDAY_F * ddf_lct) * (...) keeps the reference association
-    if (noland) {
+    int nz = 0;
+    if (bare) {
+        // the additions the band loop performs on all-zero bands
+        if (noland) {
+            storage_transfer += 0.;
+        } else {
+            const double x = daily_prec_to_soil + 0.;
+#pragma unroll 10
+            for (int e = 0; e < 100; e++) dailyEffPrec += x;
+            dailyEffPrec /= 100.;
+            TempElevMax = dailyTempC - ((a.s_elev32[(size_t)p.stride + r] - elev0) * P_T_GRADNT);
+        }
+    } else if (noland) {
         __pipeline_wait_prior(0);
 #pragma unroll 4
         for (int e = 1; e < 101; e++) {
@@ -351,24 +369,39 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
                     if (thresh_elev == 0) thresh_elev = elev_e;
                     else if (thresh_elev > 0) temp_elev = dailyTempC - ((thresh_elev - elev0) * P_T_GRADNT);
                 }
-                const bool frz = (temp_elev <= P_T_SNOWFZ);
-                // accumulation and sublimation (:982-999)
-                s = s + (frz ? daily_prec_to_soil : 0.);
-                const bool more = (s > dailySoilPET);
-                const double sub = frz ? (more ? dailySoilPET : s) : 0.;
-                dailySnowEvapo += sub;
-                s = frz ? (more ? s - dailySoilPET : 0.) : s;
-                const double effBefore = frz ? 0. : daily_prec_to_soil;
-                // melt (:1003-1019)
-                const bool mlt = (temp_elev > P_T_SNOWMT) && !(s < 0.);
-                const double m_raw = ddf * (temp_elev - P_T_SNOWMT);
-                const bool all = (m_raw > s);
-                const double snowmelt_elev = mlt ? (all ? s : m_raw) : 0.;
-                s = mlt ? (all ? 0. : s - m_raw) : s;
+                // accumulation and sublimation (:982-999), melt (:1003-1019).  Written with short if-bodies:
+                // the compiler predicates them (no divergent branch), which takes ~25 % fewer instructions
+                // than the select form; adding a contribution of exactly 0 is skipped (x + 0 == x)
+                double effmelt = 0.;
+                if (temp_elev <= P_T_SNOWFZ) {
+                    s += daily_prec_to_soil;
+                    if (s > dailySoilPET) {
+                        dailySnowEvapo += dailySoilPET;
+                        s -= dailySoilPET;
+                    } else {
+                        dailySnowEvapo += s;
+                        s = 0.;
+                    }
+                } else {
+                    effmelt = daily_prec_to_soil;
+                }
+                if (temp_elev > P_T_SNOWMT && !(s < 0.)) {
+                    const double m_raw = ddf * (temp_elev - P_T_SNOWMT);
+                    if (m_raw > s) {
+                        effmelt += s;
+                        s = 0.;
+                    } else {
+                        effmelt += m_raw;
+                        s -= m_raw;
+                    }
+                } else {
+                    effmelt += 0.;
+                }
                 snowStorageChange += s - s0;
                 if (c == 0 && k == 0) TempElevMax = temp_elev;
                 snow += s;
-                dailyEffPrec += effBefore + snowmelt_elev;
+                nz |= (s != 0.);
+                dailyEffPrec += effmelt;
                 S[(size_t)(c * SNOW_CH + k) * p.stride] = s;
             }
             // refill the buffer just consumed with the chunk after next (same thread: no barrier)
@@ -382,6 +415,7 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
         landStorageChangeSum += snowStorageChange;
     }
     a.snow[i] = snow;
+    if (!bare) a.s_snowfree[i] = (int8_t)(nz == 0);
 
     // immediate runoff (:1068-1071)
     const float builtup = a.builtup[r];
@@ -482,24 +516,560 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
     a.surface_runoff[i] = total_daily_runoff - daily_gw_recharge;
 }
 
+// ----------------------------------------------------------------------------------------
+// vertical water balance (daily.cpp:94-1264), CTA-cooperative and band-parallel
+//
+// One CTA of V_NW warps works on a TILE of 32 consecutive cells (lane = cell):
+//   v_mode   warp 0   per-cell regime (off / no land / bare and warm / needs the band loop) and the
+//                     scalars the band threads need that do not depend on the head
+//   v_head   warp 0   forcing, LAI, radiation, PET, interception          (daily.cpp:186-894)
+//   slabs    all      the 100 snow bands in V_NSLAB slabs of V_SLAB bands; inside a slab warp w owns
+//                     V_BPW consecutive bands of the 32 cells (coalesced 256 B rows), the loads of
+//                     the next slab are in flight while the current one is evaluated     (:913-1062)
+//   v_sum    warps 0-3  the four band sums (storage change, effective precipitation, sublimation,
+//                     snow) are accumulated IN BAND ORDER from per-band contributions staged in
+//                     shared memory: the value is the one the serial loop of the reference produces
+//   v_tail   warp 0   immediate runoff, soil, AET, runoff split                        (:1068-1257)
+// so the dependent instruction chain of one cell-day is ~1/4 of the one-thread-per-cell form; this
+// chain (cell-day -> cell-day) is what bounds a single-member run.
+//
+// Cells whose 100 bands are all exactly zero (s_snowfree, maintained by v_sum) and whose lowest and
+// highest band are both above the freezing threshold take no part in the band loop: every band
+// would read 0, add 0 and write 0 (the elevation-band temperature is monotone in the elevation, so
+// checking the two extreme bands covers all of them).  The sums of such a cell are formed by the
+// same additions the loop would do (100 x "+= precipitation"), so results are unchanged; a tile
+// made of such cells only never touches the band arrays.
+// ----------------------------------------------------------------------------------------
+constexpr int V_NW = 5, V_BPW = 4;
+constexpr int V_SLAB = V_NW * V_BPW, V_NSLAB = 100 / V_SLAB, V_THREADS = 32 * V_NW;
+static_assert(V_SLAB * V_NSLAB == 100 && V_NW == 5, "slabs must tile the 100 bands; warps 1-4 preload, warps 0-3 sum");
+enum { VM_ACTIVE = 1, VM_NOLAND = 2, VM_BARE = 4 };
+enum { Q_CHG = 0, Q_EFF = 1, Q_SUB = 2, Q_SNOW = 3 };
+
+// slots of the preloaded per-cell inputs (VTile::pd / pf / pk)
+enum { LI_ekg, LI_invkg, LI_evaredex, LI_area, LI_cfa, LI_contf, LI_fswb_init, LI_loc_lake, LI_loc_wetland, LI_kS, LI_lake_depth,
+       LI_wetl_depth, LI_laf, LI_laf_prev, LI_gw, LI_loc_lake_stor, LI_red_loc_lake, LI_loc_wetl_stor, LI_red_loc_wetl,
+       LI_raf_next, LI_transfer_old, TI_soil, TI_gamma, TI_pcrit, HI_p_prec, HI_ptc_ari, HI_ptc_hum, HI_lai_precsum, HI_snow, HI_netrad,
+       HI_canopy, HI_mcwh, HI_pet_mxdy, VP_ND };
+enum { TI_builtup, TI_smax, TI_gwfactor, HI_laimax, VP_NF };
+enum { K_contcell, K_flags, K_ldd, K_arid, K_texture, K_rgmax, K_lc, K_lai_days, K_lai_status, VP_NK };
+
+struct VTile {
+    // band-loop scalars of the tile's cells
+    double T[32], grad[32], lafPrev[32], laf[32], inv_laf[32], fz[32], mt[32], ddf[32], prec[32], pet[32];
+    int elev0[32], mode[32];
+    int cap_first[32], cap_elev[32], cap_any[V_NSLAB], nband_cells;
+    double temp1[32];  // temperature of band 1 (TempElevMax, daily.cpp:1030)
+    double contrib[4][V_SLAB][32], acc_init[32], fin[4][32];
+    int nz[32];
+    // head -> tail
+    double h_prec[32], h_cfa[32], h_canopy_evapo[32], h_lsc[32], h_maxpet[32], h_owpet[32];
+    // inputs of the head, the tail and the local routing, brought in by warps 1-4 (cp.async) while
+    // warp 0 determines the regimes: after the first barrier warp 0 computes from shared memory only
+    double pd[VP_ND][32];
+    float pf[VP_NF][32];
+    float4 pforce[32];
+    int pk[VP_NK][32];
+};
+
+// registers of one thread that live across the barriers of a tile
+struct VThread {
+    double pre_s[V_BPW], cur_s[V_BPW], acc;
+    int pre_e[V_BPW], cur_e[V_BPW], nz;
+};
+
+// regime of the cell and head-independent scalars (warp 0, lane = cell)
+__device__ __forceinline__ void v_mode(const WgkParams &p, VTile &sm, const int r0, const int begin, const int end, const int m,
+                                       const int slot, const int lane) {
+    const WgkArrays &a = p.a;
+    const int r = r0 + lane;
+    if (lane == 0) sm.nband_cells = 0;
+    if (lane < V_NSLAB) sm.cap_any[lane] = 0;
+    sm.cap_first[lane] = 1000;
+    sm.cap_elev[lane] = 0;
+#ifndef WGK_EMU
+    __syncwarp();
+#endif
+    int mode = 0;
+    if (r >= begin && r < end && a.contcell[r]) {  // integrateWGHM.cpp:772
+        const size_t i = (size_t)m * p.stride + r;
+        const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+        // daily.cpp:159-169, routing.h:246-251 (all candidates are loaded at once: one memory round trip)
+        const int started = a.status_laf_next[i];
+        const double laf_cur = a.land_area_frac[i], laf_next = a.land_area_frac_next[i], laf_prev = a.land_area_frac_prev[i];
+        const double landAreaFrac = (0 == started) ? laf_cur : laf_next;
+        double lafPrev;
+        if (1 == started) lafPrev = laf_prev;
+        else if (p.restart == 1) lafPrev = laf_prev;
+        else lafPrev = landAreaFrac;
+        if (1 == a.toBeCalculated[r]) {  // daily.cpp:177
+            mode = VM_ACTIVE;
+            const bool noland = (landAreaFrac <= 0.);
+            if (noland) mode |= VM_NOLAND;
+            const float4 f = p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r];
+            const double T = (double)f.y;
+            const double grad = a.p_gradnt[q], fz = a.p_snowfz[q];
+            const double ddf = a.p_degday[q] * a.lct_ddf[a.landcover[r] - 1];  // (M_DEGDAY_F * ddf_lct) * (...) keeps the reference association
+            sm.T[lane] = T;
+            sm.grad[lane] = grad;
+            sm.fz[lane] = fz;
+            sm.mt[lane] = a.p_snowmt[q];
+            sm.ddf[lane] = ddf;
+            sm.lafPrev[lane] = lafPrev;
+            sm.laf[lane] = landAreaFrac;
+            // S * lafPrev / landAreaFrac (:947): the quotient is formed with one correctly rounded
+            // reciprocal and a fused residual correction (Markstein), 4 instructions instead of a
+            // ~25-instruction division per band; the result is the correctly rounded quotient
+            sm.inv_laf[lane] = noland ? 0. : 1. / landAreaFrac;
+            sm.elev0[lane] = a.elevation[r];
+            if (a.s_snowfree[i]) {
+                const double t_top = T - ((double)a.s_de_max[r] * grad), t_bot = T - ((double)a.s_de_min[r] * grad);
+                if (noland || (ddf >= 0. && t_top > fz && t_bot > fz)) mode |= VM_BARE;
+            }
+            if (!(mode & VM_BARE)) atomicAdd(&sm.nband_cells, 1);
+        }
+    }
+    sm.mode[lane] = mode;
+}
+
+// issue the loads of slab `slab` (bands slab*V_SLAB + w*V_BPW + j + 1) into the prefetch registers
+__device__ __forceinline__ void v_prefetch(const WgkParams &p, const VTile &sm, VThread &ts, const int r0, const int m, const int slab,
+                                           const int w, const int lane) {
+    const int mode = sm.mode[lane];
+    const bool on = (mode & VM_ACTIVE) && !(mode & VM_BARE);
+    const size_t r = (size_t)(r0 + lane);
+    const int e0 = slab * V_SLAB + w * V_BPW + 1;
+    const double *__restrict__ S = p.a.snow_bands + ((size_t)m * WGK_NBAND_K + e0) * p.stride + r;
+    const int16_t *__restrict__ E = p.a.s_delev + (size_t)e0 * p.stride + r;
+#pragma unroll
+    for (int j = 0; j < V_BPW; j++) {
+        ts.pre_s[j] = on ? S[(size_t)j * p.stride] : 0.;
+        ts.pre_e[j] = on ? (int)E[(size_t)j * p.stride] : 0;
+    }
+}
+
+// forcing, LAI, radiation, PET, interception (warp 0, lane = cell)
+__device__ __forceinline__ void v_head(const WgkParams &p, VTile &sm, const int r0, const int m, const int slot, const int lane) {
+    const WgkArrays &a = p.a;
+    const int mode = sm.mode[lane];
+    if (!(mode & VM_ACTIVE)) return;
+    const int r = r0 + lane;
+    const size_t i = (size_t)m * p.stride + r;
+    const double landAreaFrac = sm.laf[lane], lafPrev = sm.lafPrev[lane];
+    const int lc = sm.pk[K_lc][lane] - 1;
+    const float4 f = sm.pforce[lane];
+    double dailyPrec = (double)f.x;
+    const double dailyTempC = (double)f.y;
+    const double dailyShortWave = (double)f.z;
+    const double dailyLongWave = (double)f.w;
+
+    dailyPrec = sm.pd[HI_p_prec][lane] * dailyPrec;  // :248
+    const double temp2 = dailyTempC + 237.3;
+    const double e_s = 0.6108 * exp(17.27 * dailyTempC / temp2);
+
+    // arid / humid (:331-348); any other index value is rejected on upload
+    const bool arid_gw = (sm.pk[K_arid][lane] == 1);
+    const double alpha = arid_gw ? sm.pd[HI_ptc_ari][lane] : sm.pd[HI_ptc_hum][lane];
+
+    // LAI / Kc (:355-356); LAImin in float arithmetic as in lai.cpp:154
+    const float laimax_f = sm.pf[HI_laimax][lane];
+    const float LAImin_f = __fadd_rn(a.lai_factor_a[lc], __fmul_rn(a.lai_factor_b[lc], laimax_f));
+    const double LAImin = (double)LAImin_f;
+    const double LAImaxd = (double)laimax_f;
+    int days = sm.pk[K_lai_days][lane], status = sm.pk[K_lai_status][lane];
+    double precsum = sm.pd[HI_lai_precsum][lane];
+    double dailyLai;
+    if (dailyTempC > 8.)
+        dailyLai = lai_growing(days, a.lai_initial_days[lc], status, lc + 1, arid_gw, LAImin, LAImaxd, precsum, dailyPrec);
+    else
+        dailyLai = lai_nogrowing(days, a.lai_initial_days[lc], status, LAImin, LAImaxd, precsum, dailyPrec);
+    a.lai_days[i] = days;
+    a.lai_status[i] = status;
+    a.lai_precsum[i] = precsum;
+    double dailyKc;
+    if ((LAImaxd - LAImin) == 0.) dailyKc = a.lai_kc_min[lc];
+    else dailyKc = a.lai_kc_min[lc] + (a.lai_kc_max[lc] - a.lai_kc_min[lc]) * (dailyLai - LAImin) / (LAImaxd - LAImin);
+
+    const double snow_prev = sm.pd[HI_snow][lane];
+    double albedo;
+    if (snow_prev > 3.) albedo = a.lct_albedo_snow[lc];  // :366
+    else albedo = 0.23;                                   // use_kc == 1
+
+    double lat_heat;
+    if (dailyTempC > 0) lat_heat = 2.501 - 0.002361 * dailyTempC;
+    else lat_heat = 2.835;
+
+    const double conv_Wm2_to_mmd = 0.0864 / lat_heat;
+    const double solar_rad = conv_Wm2_to_mmd * dailyShortWave;
+    const double long_wave_rad_in = conv_Wm2_to_mmd * dailyLongWave;
+    const double emissivity = a.lct_emissivity[lc];
+    const double temp_K = dailyTempC + 273.2;
+    const double stefan_boltz_const = 0.000000004903;
+    const double temp_K2 = temp_K * temp_K;  // pow(temp_K, 4.) (:423) as two squarings (<= 1 ulp apart)
+    const double long_wave_rad_out = emissivity * stefan_boltz_const * (temp_K2 * temp_K2) / lat_heat;
+    const double net_long_wave_rad = long_wave_rad_in - long_wave_rad_out;
+    const double net_short_wave_rad = solar_rad * (1. - albedo);
+    const double net_rad = sm.pd[HI_netrad][lane] * (net_short_wave_rad + net_long_wave_rad);
+    const double openWaterNetShortWaveRad = solar_rad * (1. - 0.08);
+    const double openWaterNetRad = openWaterNetShortWaveRad + net_long_wave_rad;
+
+    double dailyPET, dailyOpenWaterPET;
+    const double inc_svp = 4098. * e_s / (temp2 * temp2);
+    const double c3 = 0.0016286 * 101.3;
+    const double gamma = c3 / lat_heat;
+    if (net_rad <= 0.) dailyPET = 0.;
+    else dailyPET = alpha * (inc_svp * net_rad) / (inc_svp + gamma);
+    if (openWaterNetRad <= 0.) dailyOpenWaterPET = 0.;
+    else dailyOpenWaterPET = alpha * (inc_svp * openWaterNetRad) / (inc_svp + gamma);
+    if (snow_prev <= 3.) {  // :768-771
+        dailyPET *= dailyKc;
+        dailyOpenWaterPET *= 1.05;
+    }
+    const double cfa = sm.pd[LI_cfa][lane];
+    a.lake_balance[i] = (dailyPrec - dailyOpenWaterPET) * cfa;
+    a.openwater_prec[i] = dailyPrec;
+    a.openwater_pet[i] = dailyOpenWaterPET;
+
+    double landStorageChangeSum = 0.;
+    double dailyCanopyEvapo = 0., daily_prec_to_soil = 0., dailySoilPET = 0.;
+    // interception (:825-894)
+    double canopy = sm.pd[HI_canopy][lane];
+    double acc_init = 0.;
+    if (mode & VM_NOLAND) {
+        acc_init = canopy;  // storage_transfer starts with the canopy water (:829)
+        canopy = 0.;
+    } else {
+        canopy *= lafPrev / landAreaFrac;
+        if (fabs(canopy) <= MIN_STOR_VOL) canopy = 0.;
+        const double initialStorage = canopy;
+        if (dailyLai > 0.00001) {
+            const double max_canopy_storage = sm.pd[HI_mcwh][lane] * dailyLai;
+            const double canopy_deficiency = max_canopy_storage - canopy;
+            if (dailyPrec < canopy_deficiency) {
+                canopy += dailyPrec;
+                daily_prec_to_soil = 0.;
+            } else {
+                canopy = max_canopy_storage;
+                daily_prec_to_soil = dailyPrec - canopy_deficiency;
+            }
+            const double canopy_water_content = canopy;
+            dailyCanopyEvapo = dailyPET * pow((canopy_water_content / max_canopy_storage), 0.66666666);
+            if (dailyCanopyEvapo > canopy_water_content) {
+                dailyCanopyEvapo = canopy_water_content;
+                dailySoilPET = dailyPET - canopy_water_content;
+                canopy = 0.0;
+            } else {
+                canopy -= dailyCanopyEvapo;
+                dailySoilPET = dailyPET - dailyCanopyEvapo;
+            }
+        } else {
+            daily_prec_to_soil = dailyPrec;
+            dailySoilPET = dailyPET;
+            dailyCanopyEvapo = 0.0;
+        }
+        landStorageChangeSum += canopy - initialStorage;
+    }
+    a.canopy[i] = canopy;
+    if (dailySoilPET < 0.) dailySoilPET = 0.0;
+    sm.prec[lane] = daily_prec_to_soil;
+    sm.pet[lane] = dailySoilPET;
+    sm.acc_init[lane] = acc_init;
+    sm.h_prec[lane] = dailyPrec;
+    sm.h_cfa[lane] = cfa;
+    sm.h_canopy_evapo[lane] = dailyCanopyEvapo;
+    sm.h_lsc[lane] = landStorageChangeSum;
+    sm.h_maxpet[lane] = sm.pd[HI_pet_mxdy][lane];
+    sm.h_owpet[lane] = dailyOpenWaterPET;
+}
+
+// take over the prefetched slab, start the next one, rescale to the new land area fraction and
+// look for bands above the 1000 mm cap (:947-976)
+__device__ __forceinline__ void v_scale(const WgkParams &p, VTile &sm, VThread &ts, const int r0, const int m, const int slab,
+                                        const int w, const int lane) {
+    const int mode = sm.mode[lane];
+#pragma unroll
+    for (int j = 0; j < V_BPW; j++) {
+        ts.cur_s[j] = ts.pre_s[j];
+        ts.cur_e[j] = ts.pre_e[j];
+    }
+    if (slab + 1 < V_NSLAB) v_prefetch(p, sm, ts, r0, m, slab + 1, w, lane);
+    if (!(mode & VM_ACTIVE) || (mode & VM_NOLAND)) return;
+    const double lafPrev = sm.lafPrev[lane], laf = sm.laf[lane], inv_laf = sm.inv_laf[lane];
+    bool capped = false;
+#pragma unroll
+    for (int j = 0; j < V_BPW; j++) {
+        const double num = ts.cur_s[j] * lafPrev;
+        double s = num * inv_laf;
+        s = fma(fma(-laf, s, num), inv_laf, s);
+        if (fabs(s) <= MIN_STOR_VOL) s = 0.;
+        ts.cur_s[j] = s;
+        if (s > 1000.) {
+            capped = true;
+            if (ts.cur_e[j] + sm.elev0[lane] != 0) atomicMin(&sm.cap_first[lane], slab * V_SLAB + w * V_BPW + j + 1);
+        }
+    }
+    if (capped) sm.cap_any[slab] = 1;
+}
+
+// only when a band of the tile is above the cap: the first such band of a cell (in band order,
+// with a non-zero elevation) fixes the elevation whose temperature all later capped bands use
+__device__ __forceinline__ void v_cap_resolve(VTile &sm, const VThread &ts, const int slab, const int w, const int lane) {
+#pragma unroll
+    for (int j = 0; j < V_BPW; j++)
+        if (slab * V_SLAB + w * V_BPW + j + 1 == sm.cap_first[lane]) sm.cap_elev[lane] = ts.cur_e[j] + sm.elev0[lane];
+}
+
+// the bands of one slab: accumulation, sublimation, melt (:978-1045); per-band contributions to
+// the four ordered sums go to shared memory, the new band storage to global memory
+__device__ __forceinline__ void v_band(const WgkParams &p, VTile &sm, const VThread &ts, const int r0, const int m, const int slab,
+                                       const int w, const int lane) {
+    const int mode = sm.mode[lane];
+    const bool store = (mode & VM_ACTIVE) && !(mode & VM_BARE);
+    const int k0 = w * V_BPW, e0 = slab * V_SLAB + k0 + 1;
+    double *__restrict__ S = p.a.snow_bands + ((size_t)m * WGK_NBAND_K + e0) * p.stride + (size_t)(r0 + lane);
+    if (mode & VM_NOLAND) {  // :916-922
+#pragma unroll
+        for (int j = 0; j < V_BPW; j++) {
+            sm.contrib[Q_CHG][k0 + j][lane] = ts.cur_s[j] / 100.;
+            sm.contrib[Q_EFF][k0 + j][lane] = 0.;
+            sm.contrib[Q_SUB][k0 + j][lane] = 0.;
+            sm.contrib[Q_SNOW][k0 + j][lane] = 0.;
+            if (store) S[(size_t)j * p.stride] = 0.;
+        }
+        return;
+    }
+    const double T = sm.T[lane], grad = sm.grad[lane], fz = sm.fz[lane], mt = sm.mt[lane], ddf = sm.ddf[lane];
+    const double prec = sm.prec[lane], pet = sm.pet[lane];
+    const bool cap_slab = sm.cap_any[slab] != 0 || sm.cap_elev[lane] != 0;
+#pragma unroll
+    for (int j = 0; j < V_BPW; j++) {
+        const int de = ts.cur_e[j];
+        double temp_elev = T - ((double)de * grad);
+        double s = ts.cur_s[j];
+        const double s0 = s;
+        if (cap_slab && s > 1000.) {  // :958-976
+            const int ce = sm.cap_elev[lane];
+            if (ce > 0 && e0 + j > sm.cap_first[lane]) temp_elev = T - ((double)(ce - sm.elev0[lane]) * grad);
+        }
+        double sub = 0., eff = 0.;
+        if (temp_elev <= fz) {  // accumulation and sublimation (:982-999)
+            s += prec;
+            if (s > pet) {
+                sub = pet;
+                s -= pet;
+            } else {
+                sub = s;
+                s = 0.;
+            }
+        } else {
+            eff = prec;
+        }
+        double melt = 0.;
+        if (temp_elev > mt && !(s < 0.)) {  // melt (:1003-1019)
+            const double m_raw = ddf * (temp_elev - mt);
+            if (m_raw > s) {
+                melt = s;
+                s = 0.;
+            } else {
+                melt = m_raw;
+                s -= m_raw;
+            }
+        }
+        if (slab == 0 && k0 + j == 0) sm.temp1[lane] = temp_elev;
+        sm.contrib[Q_CHG][k0 + j][lane] = s - s0;
+        sm.contrib[Q_EFF][k0 + j][lane] = eff + melt;
+        sm.contrib[Q_SUB][k0 + j][lane] = sub;
+        sm.contrib[Q_SNOW][k0 + j][lane] = s;
+        if (store) S[(size_t)j * p.stride] = s;
+    }
+}
+
+// ordered accumulation of the slab's contributions: warp q sums quantity q of the 32 cells
+__device__ __forceinline__ void v_sum(VTile &sm, VThread &ts, const int slab, const int q, const int lane) {
+    if (slab == 0) {
+        ts.acc = (q == Q_CHG) ? sm.acc_init[lane] : 0.;
+        ts.nz = 0;
+    }
+    double acc = ts.acc;
+    int nz = ts.nz;
+#pragma unroll
+    for (int k = 0; k < V_SLAB; k++) {
+        const double c = sm.contrib[q][k][lane];
+        acc += c;
+        nz |= (c != 0.);
+    }
+    ts.acc = acc;
+    ts.nz = nz;
+    if (slab == V_NSLAB - 1) {
+        sm.fin[q][lane] = acc;
+        if (q == Q_SNOW) sm.nz[lane] = nz;
+    }
+}
+
+// a tile without any cell in the band loop: the sums of its bare cells by the additions the loop
+// would perform on all-zero bands
+__device__ __forceinline__ void v_bare_sums(const WgkParams &p, VTile &sm, const int r0, const int lane) {
+    const int mode = sm.mode[lane];
+    if (!(mode & VM_ACTIVE)) return;
+    double eff = 0.;
+    if (!(mode & VM_NOLAND)) {
+        const double x = sm.prec[lane] + 0.;
+#pragma unroll 10
+        for (int e = 0; e < 100; e++) eff += x;
+        sm.temp1[lane] = sm.T[lane] - ((double)p.a.s_delev[(size_t)p.stride + r0 + lane] * sm.grad[lane]);
+    }
+    sm.fin[Q_CHG][lane] = sm.acc_init[lane] + 0.;
+    sm.fin[Q_EFF][lane] = eff;
+    sm.fin[Q_SUB][lane] = 0.;
+    sm.fin[Q_SNOW][lane] = 0.;
+    sm.nz[lane] = 0;
+}
+
+// immediate runoff, soil, AET, runoff split (warp 0, lane = cell)
+__device__ __forceinline__ void v_tail(const WgkParams &p, VTile &sm, const int r0, const int m, const int lane, double flux[3]) {
+    const WgkArrays &a = p.a;
+    const int mode = sm.mode[lane];
+    if (!(mode & VM_ACTIVE)) return;
+    const int r = r0 + lane;
+    const size_t i = (size_t)m * p.stride + r;
+    const bool noland = (mode & VM_NOLAND) != 0;
+    const double landAreaFrac = sm.laf[lane], lafPrev = sm.lafPrev[lane];
+    const double dailyPrec = sm.h_prec[lane], cfa = sm.h_cfa[lane], dailyCanopyEvapo = sm.h_canopy_evapo[lane];
+    const double dailySoilPET = sm.pet[lane], maxDailyPET = sm.h_maxpet[lane];
+    const double P_T_SNOWFZ = sm.fz[lane];
+    double landStorageChangeSum = sm.h_lsc[lane];
+    double storage_transfer = 0., snow = 0., dailyEffPrec = 0., dailySnowEvapo = 0., TempElevMax = 0.;
+    if (noland) {
+        storage_transfer = sm.fin[Q_CHG][lane];
+    } else {
+        snow = sm.fin[Q_SNOW][lane] / 100.;
+        dailyEffPrec = sm.fin[Q_EFF][lane] / 100.;
+        dailySnowEvapo = sm.fin[Q_SUB][lane] / 100.;
+        landStorageChangeSum += sm.fin[Q_CHG][lane] / 100.;
+        TempElevMax = sm.temp1[lane];
+    }
+    a.snow[i] = snow;
+    if (!(mode & VM_BARE)) a.s_snowfree[i] = (int8_t)(sm.nz[lane] == 0);
+
+    double immediate_runoff = 0., dailyAET = 0., daily_runoff = 0., total_daily_runoff = 0.;
+    double daily_gw_recharge = 0., pot_gw_recharge = 0.;
+    double soil_water_overflow = 0., neg_land_aet = 0.;
+    double land_aet = 0., land_aet_uncorr = 0.;
+
+    // immediate runoff (:1068-1071)
+    const float builtup = sm.pf[TI_builtup][lane];
+    if (builtup > 0.) {
+        immediate_runoff = 0.5 * dailyEffPrec * builtup;
+        dailyEffPrec -= immediate_runoff;
+    }
+
+    // soil and AET (:1080-1239)
+    const double Smax = (double)sm.pf[TI_smax][lane];
+    double soil = sm.pd[TI_soil][lane];
+    if (noland) {
+        storage_transfer += soil;
+        storage_transfer *= cfa;
+        soil = 0.;
+        daily_gw_recharge = 0.;
+        total_daily_runoff = 0.;
+        a.gw_recharge[i] = 0.;
+        a.storage_transfer[i] = storage_transfer;
+        flux[2] = 0.;
+    } else {
+        soil *= lafPrev / landAreaFrac;
+        const double initialStorage = soil;
+        soil_water_overflow = 0;
+        if (soil > Smax) {
+            soil_water_overflow = soil - Smax;
+            soil = Smax;
+        }
+        if (TempElevMax > P_T_SNOWFZ) {
+            if (Smax > 0.) {
+                const double soil_saturation = soil / Smax;
+                daily_runoff = dailyEffPrec * pow(soil_saturation, sm.pd[TI_gamma][lane]);
+                if (dailySoilPET > (maxDailyPET - dailyCanopyEvapo) * soil_saturation)
+                    dailyAET = (maxDailyPET - dailyCanopyEvapo) * soil_saturation;
+                else
+                    dailyAET = dailySoilPET;
+                soil += dailyEffPrec - dailyAET - daily_runoff;
+                if (fabs(soil) <= MIN_STOR_VOL) soil = 0.;
+                dailyEffPrec = 0.;
+                if (soil < 0.) {
+                    dailyAET += soil;
+                    soil = 0.;
+                }
+                daily_runoff *= cfa;
+                immediate_runoff *= cfa;
+                const short Rgmax = (short)sm.pk[K_rgmax][lane];
+                const float gwFactor = sm.pf[TI_gwfactor][lane];
+                if ((Rgmax / 100.) < (gwFactor * daily_runoff)) daily_gw_recharge = Rgmax / 100.;
+                else daily_gw_recharge = gwFactor * daily_runoff;
+                pot_gw_recharge = 0.;
+                if (((sm.pk[K_arid][lane] == 1) && (sm.pk[K_texture][lane] < 21)) && (sm.pk[K_ldd][lane] >= 0)) {  // :1165-1176
+                    if (dailyPrec <= sm.pd[TI_pcrit][lane]) {
+                        pot_gw_recharge = daily_gw_recharge;
+                        daily_gw_recharge = 0.;
+                    }
+                }
+                daily_runoff -= pot_gw_recharge;
+                pot_gw_recharge /= cfa;
+                soil += pot_gw_recharge;
+                if (soil > Smax) {
+                    soil_water_overflow += soil - Smax;
+                    soil = Smax;
+                }
+                soil_water_overflow *= cfa;
+                total_daily_runoff = daily_runoff + immediate_runoff + soil_water_overflow;
+            } else {
+                total_daily_runoff = 0.;
+                daily_gw_recharge = 0.;
+            }
+        } else {
+            soil_water_overflow *= cfa;
+            dailyEffPrec *= cfa;
+            total_daily_runoff += soil_water_overflow + dailyEffPrec;
+            daily_gw_recharge = 0.;
+            dailyAET = 0.;
+        }
+        a.gw_recharge[i] = daily_gw_recharge;  // :1221 (not updated by the fix-up below)
+        flux[2] = daily_gw_recharge;
+        landStorageChangeSum += soil - initialStorage;
+        land_aet = landStorageChangeSum * (cfa - 1.0) - dailyPrec * (cfa - 1.0)
+                   + (dailyAET + dailyCanopyEvapo + dailySnowEvapo) * cfa;
+        if (land_aet < 0.) {
+            neg_land_aet = land_aet;
+            land_aet = 0.;
+        }
+        land_aet_uncorr = (dailyAET + dailyCanopyEvapo + dailySnowEvapo);
+    }
+    a.land_aet[i] = land_aet;
+    a.land_aet_uncorr[i] = land_aet_uncorr;
+
+    // surface runoff (:1244-1257)
+    if (neg_land_aet < 0.) total_daily_runoff = total_daily_runoff + neg_land_aet;
+    if (total_daily_runoff < 0.) total_daily_runoff = 0.;
+    if ((total_daily_runoff - daily_gw_recharge) < 0.) {
+        const double neg_runoff = total_daily_runoff - daily_gw_recharge;
+        daily_gw_recharge = total_daily_runoff;
+        soil += neg_runoff;
+    }
+    a.soil[i] = soil;
+    a.surface_runoff[i] = total_daily_runoff - daily_gw_recharge;
+    flux[0] = noland ? storage_transfer : sm.pd[LI_transfer_old][lane];  // G_dailyStorageTransfer keeps its last value (:1113)
+    flux[1] = total_daily_runoff - daily_gw_recharge;
+}
+
 // number of days of river discharge kept in flight (temporal wavefront over the level graph)
 constexpr int QBUF_K = 32;
-
-__global__ void __launch_bounds__(VBLOCK) k_vertical(const __grid_constant__ WgkParams p, const int dayofs) {
-    __shared__ SnowStage stage;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.ncell) return;
-    vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3], &stage);
-}
 
 // ----------------------------------------------------------------------------------------
 // routing helpers
 // ----------------------------------------------------------------------------------------
 // groundwater linear reservoir (routing.cpp:1938-1958 and four identical copies)
-__device__ __forceinline__ double gw_step(double &Sg, double netGWin, double k) {
+__device__ __forceinline__ double gw_step(double &Sg, double netGWin, double ek, double invk) {
+    // ek = exp(-1. * k) and invk = (1. / k) depend on the parameter P_GWOUTF_C only: derived once (k_derive_static)
     const double prev = Sg;
-    const double ek = exp(-1. * k);
-    Sg = prev * ek + (1. / k) * netGWin * (1. - ek);
+    Sg = prev * ek + invk * netGWin * (1. - ek);
     if (fabs(Sg) <= MIN_STOR_VOL) Sg = 0.;
     double qq = prev - Sg + netGWin;
     if (qq <= 0.) {
@@ -535,9 +1105,23 @@ __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ W
     const WgkArrays &a = p.a;
     const size_t q = (size_t)ps * p.stride + r;
     a.s_c1[q] = 1. / (a.p_rivrgh[q] * a.roughness[r]);
+    a.s_ekg[q] = exp(-1. * a.p_gwoutf[q]);  // routing.cpp:1940
+    a.s_invkg[q] = (1. / a.p_gwoutf[q]);
     a.s_slope_pow[q] = pow(a.river_slope[r], 0.5);
     if (ps == 0) {
+        // band elevation minus cell mean elevation (the integer the lapse rate multiplies, daily.cpp:935) and its extremes
+        const int e0 = a.elevation[r];
+        int lo = 32767, hi = -32768;
+        for (int b = 1; b < WGK_NBAND_K; b++) {
+            const int de = a.elevation[(size_t)b * p.stride + r] - e0;
+            a.s_delev[(size_t)b * p.stride + r] = (int16_t)de;
+            lo = de < lo ? de : lo;
+            hi = de > hi ? de : hi;
+        }
+        a.s_delev[r] = 0;
         for (int b = 0; b < WGK_NBAND_K; b++) a.s_elev32[(size_t)b * p.stride + r] = a.elevation[(size_t)b * p.stride + r];
+        a.s_de_min[r] = (int16_t)lo;
+        a.s_de_max[r] = (int16_t)hi;
         int f = 0;
         const int ldd = a.ldd[r];
         if (a.contcell[r] && (0 != a.toBeCalculated[r])) f |= FL_ACTIVE;
@@ -550,36 +1134,103 @@ __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ W
     }
 }
 
+// s_snowfree: all 100 elevation bands of the cell hold exactly zero snow (recomputed after every
+// upload of the band state; afterwards maintained by the vertical kernel)
+__global__ void __launch_bounds__(128) k_derive_member(const __grid_constant__ WgkParams p) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (r >= p.ncell) return;
+    const double *S = p.a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r;
+    int nz = 0;
+    for (int b = 1; b < WGK_NBAND_K; b++) nz |= (S[(size_t)b * p.stride] != 0.);
+    p.a.s_snowfree[(size_t)m * p.stride + r] = (int8_t)(nz == 0);
+}
+
 // ----------------------------------------------------------------------------------------
 // cell-parallel pre-pass of the routing day: everything that does not depend on upstream cells
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r, const int m) {
+// inputs of the cell-parallel routing pre-pass that are known before today's vertical step (statics,
+// parameters, yesterday's state): the band-parallel kernel loads them at its very start, in a warp of
+// its own, so that no global-memory latency is left between the vertical step and the local routing
+struct LocalIn {
+    double ekg, invkg, evaredex, area, cfa, contf, fswb_init, loc_lake, loc_wetland, kS, lake_depth, wetl_depth;
+    double laf, laf_prev, gw, loc_lake_stor, red_loc_lake, loc_wetl_stor, red_loc_wetl, raf_next;
+    int contcell, flags, ldd, arid;
+};
+// today's fluxes of the vertical step (daily.h G_openWaterPrec ... G_dailyStorageTransfer)
+struct LocalFlux {
+    double owPrec, owPET, storage_transfer, surface_runoff, gw_recharge;
+};
+
+__device__ __forceinline__ LocalIn local_load(const WgkParams &p, const int r, const int m) {
+    const WgkArrays &a = p.a;
+    const size_t i = (size_t)m * p.stride + r;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    LocalIn li;
+    li.contcell = a.contcell[r];
+    li.flags = a.s_flags[r];
+    li.ldd = a.ldd[r];
+    li.arid = a.arid[r];
+    li.ekg = a.s_ekg[q];
+    li.invkg = a.s_invkg[q];
+    li.evaredex = a.p_evaredex[q];
+    li.area = a.area[r];
+    li.cfa = a.cfa[q];
+    li.contf = a.contfreq[r];
+    li.fswb_init = a.fswb_init[r];
+    li.loc_lake = a.loc_lake[r];
+    li.loc_wetland = a.loc_wetland[r];
+    li.kS = a.p_swoutf[q];
+    li.lake_depth = a.lake_depth_active[q];
+    li.wetl_depth = a.wetl_depth_active[q];
+    li.laf = a.land_area_frac[i];
+    li.laf_prev = a.land_area_frac_prev[i];
+    li.gw = a.gw[i];
+    li.loc_lake_stor = a.loc_lake_stor[i];
+    li.red_loc_lake = a.red_loc_lake[i];
+    li.loc_wetl_stor = a.loc_wetl_stor[i];
+    li.red_loc_wetl = a.red_loc_wetl[i];
+    li.raf_next = a.river_area_frac_next[i];
+    return li;
+}
+
+__device__ __forceinline__ LocalFlux local_flux_load(const WgkParams &p, const int r, const int m) {
+    const WgkArrays &a = p.a;
+    const size_t i = (size_t)m * p.stride + r;
+    LocalFlux fx;
+    fx.owPrec = a.openwater_prec[i];
+    fx.owPET = a.openwater_pet[i];
+    fx.storage_transfer = a.storage_transfer[i];
+    fx.surface_runoff = a.surface_runoff[i];
+    fx.gw_recharge = a.gw_recharge[i];
+    return fx;
+}
+
+__device__ __forceinline__ void local_compute(const WgkParams &p, const int r, const int m, const LocalIn &li, const LocalFlux &fx) {
     const WgkArrays &a = p.a;
     const size_t i = (size_t)m * p.stride + r;
     a.river_evapo[i] = 0.;  // routing.cpp:1781
-    if (!a.contcell[r]) return;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
-    const int flags = a.s_flags[r];
-    const double kG = a.p_gwoutf[q];
-    const double M_EVAREDEX = a.p_evaredex[q];
-    const double cellArea = a.area[r];
-    const double cfa = a.cfa[q];
-    const double owPrec = a.openwater_prec[i], owPET = a.openwater_pet[i];
-    const int ldd = a.ldd[r];
-    const int arid = a.arid[r];
+    if (!li.contcell) return;
+    const int flags = li.flags;
+    const double M_EVAREDEX = li.evaredex;
+    const double cellArea = li.area;
+    const double cfa = li.cfa;
+    const double owPrec = fx.owPrec, owPET = fx.owPET;
+    const int ldd = li.ldd;
+    const int arid = li.arid;
     const bool aridc = (flags & FL_ARIDC) != 0;
-    const double laf = a.land_area_frac[i];
-    const double contf = a.contfreq[r];
+    const double laf = li.laf;
+    const double contf = li.contf;
     double dailyLocalSurfaceRunoff;
     double localRunoff = 0., localRunoffIntoRiver = 0., localGWRunoffIntoRiver = 0., fswb_catchment = 0.;
     double gwr_loclak = 0., gwr_locwet = 0.;
 
     if (laf <= 0.)  // :1885-1891
-        dailyLocalSurfaceRunoff = a.storage_transfer[i] * cellArea / 1000000. * a.land_area_frac_prev[i] / 100.;
+        dailyLocalSurfaceRunoff = fx.storage_transfer * cellArea / 1000000. * li.laf_prev / 100.;
     else
-        dailyLocalSurfaceRunoff = a.surface_runoff[i] * cellArea / 1000000. * laf / 100.;
+        dailyLocalSurfaceRunoff = fx.surface_runoff * cellArea / 1000000. * laf / 100.;
     if (ldd >= 0) {  // :1898-1908
-        fswb_catchment = a.fswb_init[r] * 20.;
+        fswb_catchment = li.fswb_init * 20.;
         if (fswb_catchment > 1.) fswb_catchment = 1.;
         localRunoffIntoRiver = (1. - fswb_catchment) * dailyLocalSurfaceRunoff;
     }
@@ -587,34 +1238,34 @@ __device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r
         localRunoff = fswb_catchment * dailyLocalSurfaceRunoff;
     }
     if ((0 == arid) && (ldd >= 0)) {  // :1979-2033
-        const double netGWin = a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
-        double Sg = a.gw[i];
-        const double qg = gw_step(Sg, netGWin, kG);
+        const double netGWin = fx.gw_recharge * cellArea * (laf / 100.) / 1000000.;
+        double Sg = li.gw;
+        const double qg = gw_step(Sg, netGWin, li.ekg, li.invkg);
         a.gw[i] = Sg;
         localGWRunoffIntoRiver = (1. - fswb_catchment) * qg;
         const double localGWRunoff = fswb_catchment * qg;
         localRunoff = (fswb_catchment * dailyLocalSurfaceRunoff) + localGWRunoff;
     }
     if (ldd < 0) {  // :2123-2176
-        const double netGWin = a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
-        double Sg = a.gw[i];
-        const double qg = gw_step(Sg, netGWin, kG);
+        const double netGWin = fx.gw_recharge * cellArea * (laf / 100.) / 1000000.;
+        double Sg = li.gw;
+        const double qg = gw_step(Sg, netGWin, li.ekg, li.invkg);
         a.gw[i] = Sg;
         if (laf == 0.)
-            dailyLocalSurfaceRunoff = a.storage_transfer[i] * cellArea / 1000000. * a.land_area_frac_prev[i] / 100.;
+            dailyLocalSurfaceRunoff = fx.storage_transfer * cellArea / 1000000. * li.laf_prev / 100.;
         else
-            dailyLocalSurfaceRunoff = a.surface_runoff[i] * cellArea / 1000000. * laf / 100.;
+            dailyLocalSurfaceRunoff = fx.surface_runoff * cellArea / 1000000. * laf / 100.;
         localRunoff = dailyLocalSurfaceRunoff + qg;
     }
 
     double inflow = localRunoff;
     if (flags & FL_ACTIVE) {
-        const double kS = a.p_swoutf[q];
-        const double loc_lake = a.loc_lake[r];
+        const double kS = li.kS;
+        const double loc_lake = li.loc_lake;
         if (loc_lake > 0.) {  // local lake, :2318-2490
-            const double prev = a.loc_lake_stor[i];
-            const double maxStorage = ((loc_lake) / 100.) * cellArea * a.lake_depth_active[q];
-            const double rf = a.red_loc_lake[i];
+            const double prev = li.loc_lake_stor;
+            const double maxStorage = ((loc_lake) / 100.) * cellArea * li.lake_depth;
+            const double rf = li.red_loc_lake;
             double evapo = ((1.0 - cfa) * owPrec * rf) + (cfa * (owPET * rf));
             if (evapo < 0.) evapo = 0.;
             const double totalInflow = inflow + (owPrec * rf) * (cellArea / 1000000.) * (loc_lake / 100.);
@@ -631,7 +1282,10 @@ __device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r
             }
             double outflow;
             if (prev > 0.) {
-                outflow = kS * prev * pow((prev / maxStorage), 1.5);
+                {
+                    const double x = (prev / maxStorage);  // pow(x, 1.5) (:2440) as x * sqrt(x), <= 1 ulp apart
+                    outflow = kS * prev * (x * sqrt(x));
+                }
                 if (S <= 0.) outflow = 0;
                 else if (outflow > S) outflow = S;
             } else
@@ -646,11 +1300,11 @@ __device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r
             a.loc_lake_stor[i] = S;
             a.red_loc_lake[i] = clamp01(1. - pow(fabs(S - maxStorage) / (2. * maxStorage), (M_EVAREDEX * 3.32193)));
         }
-        const double loc_wetland = a.loc_wetland[r];
+        const double loc_wetland = li.loc_wetland;
         if (loc_wetland > 0.) {  // local wetland, :2495-2617
-            const double prev = a.loc_wetl_stor[i];
-            const double maxStorage = ((loc_wetland) / 100.) * cellArea * a.wetl_depth_active[q];
-            const double rf = a.red_loc_wetl[i];
+            const double prev = li.loc_wetl_stor;
+            const double maxStorage = ((loc_wetland) / 100.) * cellArea * li.wetl_depth;
+            const double rf = li.red_loc_wetl;
             double evapo = ((1.0 - cfa) * owPrec * rf) + (cfa * (owPET * rf));
             if (evapo < 0.) evapo = 0.;
             const double totalInflow = inflow + (owPrec * rf * (cellArea / 1000000.) * (loc_wetland / 100.));
@@ -667,7 +1321,10 @@ __device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r
             if (fabs(S) <= MIN_STOR_VOL) S = 0.;
             double outflow;
             if (S > 0.) {
-                outflow = kS * S * pow((S / maxStorage), 2.5);
+                {
+                    const double x = (S / maxStorage);  // pow(x, 2.5) (:2580) as x * x * sqrt(x)
+                    outflow = kS * S * ((x * x) * sqrt(x));
+                }
                 if (outflow > S) outflow = S;
             } else
                 outflow = 0.;
@@ -685,18 +1342,18 @@ __device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r
         if (aridc && !(flags & (FL_LAKE | FL_RES | FL_GLOWET))) {
             const double gwr_swb = gwr_loclak + 0. + gwr_locwet + 0. + 0.;
             a.gwr_swb[i] = gwr_swb;
-            const double netGWin = gwr_swb * cellArea * (contf / 100.) / 1000000. + a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
-            double Sg = a.gw[i];
-            localGWRunoffIntoRiver = gw_step(Sg, netGWin, kG);
+            const double netGWin = gwr_swb * cellArea * (contf / 100.) / 1000000. + fx.gw_recharge * cellArea * (laf / 100.) / 1000000.;
+            double Sg = li.gw;
+            localGWRunoffIntoRiver = gw_step(Sg, netGWin, li.ekg, li.invkg);
             a.gw[i] = Sg;
         }
         if (flags & (FL_LAKE | FL_RES | FL_GLOWET)) {
             double *g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;
             g[GB_EKS] = exp(-1. * kS);
             g[GB_INVKS] = (1. / kS);
-            g[GB_EKG] = exp(-1. * kG);
-            g[GB_INVKG] = (1. / kG);
-            g[GB_GWRECH] = a.gw_recharge[i] * cellArea * (laf / 100.) / 1000000.;
+            g[GB_EKG] = li.ekg;
+            g[GB_INVKG] = li.invkg;
+            g[GB_GWRECH] = fx.gw_recharge * cellArea * (laf / 100.) / 1000000.;
             g[GB_LOC_GWR_LAK] = gwr_loclak;
             g[GB_LOC_GWR_WET] = gwr_locwet;
             if (flags & FL_LAKE) {  // :2630-2676
@@ -708,7 +1365,7 @@ __device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r
                 g[GB_L_PREC] = (owPrec * (lake_area / 1000000.));
                 g[GB_L_GWR] = gwr;
                 g[GB_L_PET] = evapo * (lake_area / 1000000.) + gwr * cellArea * (contf / 100.) / 1000000. + 0.;
-                g[GB_L_MAX] = (lake_area)*a.lake_depth_active[q];
+                g[GB_L_MAX] = (lake_area)*li.lake_depth;
             }
             if (flags & FL_RES) {  // :2807-2870, 2960-2983
                 const double reservoir_area = a.reservoir_area[r];
@@ -744,11 +1401,11 @@ __device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r
                 g[GB_W_PREC] = (owPrec * rf * (cellArea / 1000000.) * (glo_wetland / 100.));
                 g[GB_W_GWR] = gwr;
                 g[GB_W_PET] = evapo * (cellArea / 1000000.) * ((glo_wetland) / 100.) + gwr * cellArea * (contf / 100.) / 1000000.;
-                g[GB_W_MAX] = ((glo_wetland) / 100.) * cellArea * a.wetl_depth_active[q];
+                g[GB_W_MAX] = ((glo_wetland) / 100.) * cellArea * li.wetl_depth;
             }
         }
         // river evaporation and precipitation on yesterday's river area fraction (:3425-3441)
-        const double raf = a.river_area_frac_next[i];
+        const double raf = li.raf_next;
         a.t_river_evapo[i] = ((1.0 - cfa) * (owPrec) + (cfa * owPET)) * raf / 100. * cellArea / 1000000.;
         a.t_river_precip[i] = owPrec * raf / 100. * cellArea / 1000000.;
     }
@@ -757,6 +1414,12 @@ __device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r
     a.t_gw_to_river[i] = localGWRunoffIntoRiver;
     a.t_gwr_loclak[i] = gwr_loclak;
     a.t_gwr_locwet[i] = gwr_locwet;
+}
+
+
+__device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r, const int m) {
+    const LocalIn li = local_load(p, r, m);
+    local_compute(p, r, m, li, local_flux_load(p, r, m));
 }
 
 __global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ WgkParams p) {
@@ -1155,25 +1818,6 @@ __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkP
 // CUDA graph; the level-to-level latency chain of a day is hidden behind the work of the
 // following days instead of serialising the run.
 // ----------------------------------------------------------------------------------------
-// whole day of the cells of one wide level: vertical balance, local routing, river reach, post
-__global__ void __launch_bounds__(VBLOCK) k_day_level(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
-    __shared__ SnowStage stage;
-    const int begin = p.level_off[level], end = p.level_off[level + 1];
-    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= end) return;
-    const int m = blockIdx.y;
-    vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3], &stage);
-    route_local_cell(p, r, m);
-    const size_t mb = (size_t)m * p.stride;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
-    const RiverCtx c = load_ctx(p, r, mb + r, q);
-    if (c.flags & FL_ACTIVE) {
-        double *qday = qbuf_of_day(p, dayofs);
-        route_river(p, c, r, m, mb + r, q, gather_upstream(p, c, mb, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
-    }
-    route_post_cell(p, r, m);
-}
-
 // river reach + post-pass of the cells of one wide level (the part of the day that waits for the
 // upstream level); the vertical balance and the local routing of the same cells run in a separate,
 // earlier task (k_cells_pre) that only waits for the cells' own previous day
@@ -1192,8 +1836,165 @@ __global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ Wgk
     route_post_cell(p, r, m);
 }
 
-// vertical balance + local routing of the cells [begin, end) (the cells of one tail chunk)
-__global__ void __launch_bounds__(VBLOCK) k_cells_pre(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
+// vertical balance (+ local routing) of the cells [begin, end), one CTA per tile of 32 cells; tiles
+// start at a multiple of 4 cells so that every 256 B band row of a warp is sector aligned
+__host__ __device__ __forceinline__ int v_num_tiles(const int begin, const int end) { return (end - (begin & ~3) + 31) / 32; }
+
+// warps 1-4: bring the per-cell inputs of the head, the tail and the local routing into shared memory
+// (cp.async for 4/8/16-byte items, plain loads for the 1/2-byte flags) while warp 0 is in v_mode
+__device__ __forceinline__ void v_preload(const WgkParams &p, VTile &sm, const int r0, const int begin, const int end, const int m,
+                                          const int slot, const int w, const int lane) {
+    const WgkArrays &a = p.a;
+    const int r = r0 + lane;
+    if (r < begin || r >= end) return;
+    const size_t i = (size_t)m * p.stride + r;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+#define VP_D(slot_, src_) __pipeline_memcpy_async(&sm.pd[slot_][lane], &(src_), sizeof(double))
+#define VP_F(slot_, src_) __pipeline_memcpy_async(&sm.pf[slot_][lane], &(src_), sizeof(float))
+    if (w == 1) {
+        VP_D(LI_ekg, a.s_ekg[q]); VP_D(LI_invkg, a.s_invkg[q]); VP_D(LI_evaredex, a.p_evaredex[q]); VP_D(LI_area, a.area[r]); VP_D(LI_cfa, a.cfa[q]);
+        VP_D(LI_contf, a.contfreq[r]); VP_D(LI_fswb_init, a.fswb_init[r]); VP_D(LI_loc_lake, a.loc_lake[r]);
+        VP_D(LI_loc_wetland, a.loc_wetland[r]); VP_D(LI_kS, a.p_swoutf[q]); VP_D(LI_lake_depth, a.lake_depth_active[q]);
+        VP_D(LI_wetl_depth, a.wetl_depth_active[q]);
+    } else if (w == 2) {
+        VP_D(LI_laf, a.land_area_frac[i]); VP_D(LI_laf_prev, a.land_area_frac_prev[i]); VP_D(LI_gw, a.gw[i]);
+        VP_D(LI_loc_lake_stor, a.loc_lake_stor[i]); VP_D(LI_red_loc_lake, a.red_loc_lake[i]);
+        VP_D(LI_loc_wetl_stor, a.loc_wetl_stor[i]); VP_D(LI_red_loc_wetl, a.red_loc_wetl[i]);
+        VP_D(LI_raf_next, a.river_area_frac_next[i]); VP_D(LI_transfer_old, a.storage_transfer[i]);
+        sm.pk[K_contcell][lane] = a.contcell[r];
+        sm.pk[K_flags][lane] = a.s_flags[r];
+        sm.pk[K_ldd][lane] = a.ldd[r];
+    } else if (w == 3) {
+        __pipeline_memcpy_async(&sm.pforce[lane],
+                                &p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r],
+                                sizeof(float4));
+        VP_D(HI_p_prec, a.p_prec[q]); VP_D(HI_ptc_ari, a.p_ptc_ari[q]); VP_D(HI_ptc_hum, a.p_ptc_hum[q]);
+        VP_D(HI_lai_precsum, a.lai_precsum[i]); VP_D(HI_snow, a.snow[i]); VP_D(HI_netrad, a.p_netrad[q]);
+        VP_D(HI_canopy, a.canopy[i]); VP_D(HI_mcwh, a.p_mcwh[q]); VP_D(HI_pet_mxdy, a.p_pet_mxdy[q]);
+        VP_F(HI_laimax, a.laimax[q]);
+        __pipeline_memcpy_async(&sm.pk[K_lai_days][lane], &a.lai_days[i], sizeof(int32_t));
+        __pipeline_memcpy_async(&sm.pk[K_lai_status][lane], &a.lai_status[i], sizeof(int32_t));
+        sm.pk[K_lc][lane] = a.landcover[r];
+        sm.pk[K_arid][lane] = a.arid[r];
+    } else if (w == 4) {
+        VP_D(TI_soil, a.soil[i]); VP_D(TI_gamma, a.gamma_hbv[q]); VP_D(TI_pcrit, a.p_pcrit[q]);
+        VP_F(TI_builtup, a.builtup[r]); VP_F(TI_smax, a.smax[q]); VP_F(TI_gwfactor, a.gwfactor[q]);
+        sm.pk[K_texture][lane] = a.texture[r];
+        sm.pk[K_rgmax][lane] = a.rgmax[q];
+    }
+#undef VP_D
+#undef VP_F
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+}
+
+__device__ __forceinline__ LocalIn local_from_tile(const VTile &sm, const int lane) {
+    LocalIn li;
+    li.contcell = sm.pk[K_contcell][lane];
+    li.flags = sm.pk[K_flags][lane];
+    li.ldd = sm.pk[K_ldd][lane];
+    li.arid = sm.pk[K_arid][lane];
+    li.ekg = sm.pd[LI_ekg][lane];
+    li.invkg = sm.pd[LI_invkg][lane];
+    li.evaredex = sm.pd[LI_evaredex][lane];
+    li.area = sm.pd[LI_area][lane];
+    li.cfa = sm.pd[LI_cfa][lane];
+    li.contf = sm.pd[LI_contf][lane];
+    li.fswb_init = sm.pd[LI_fswb_init][lane];
+    li.loc_lake = sm.pd[LI_loc_lake][lane];
+    li.loc_wetland = sm.pd[LI_loc_wetland][lane];
+    li.kS = sm.pd[LI_kS][lane];
+    li.lake_depth = sm.pd[LI_lake_depth][lane];
+    li.wetl_depth = sm.pd[LI_wetl_depth][lane];
+    li.laf = sm.pd[LI_laf][lane];
+    li.laf_prev = sm.pd[LI_laf_prev][lane];
+    li.gw = sm.pd[LI_gw][lane];
+    li.loc_lake_stor = sm.pd[LI_loc_lake_stor][lane];
+    li.red_loc_lake = sm.pd[LI_red_loc_lake][lane];
+    li.loc_wetl_stor = sm.pd[LI_loc_wetl_stor][lane];
+    li.red_loc_wetl = sm.pd[LI_red_loc_wetl][lane];
+    li.raf_next = sm.pd[LI_raf_next][lane];
+    return li;
+}
+
+// tail of the tile (warp 0): soil / runoff, then the local routing with the fluxes handed over in registers
+template <bool LOCAL>
+__device__ __forceinline__ void v_finish(const WgkParams &p, VTile &sm, const int r0, const int begin, const int end, const int m,
+                                         const int lane) {
+    double flux[3] = {0., 0., 0.};
+    v_tail(p, sm, r0, m, lane, flux);
+    const int r = r0 + lane;
+    if (LOCAL && r >= begin && r < end) {
+        LocalFlux fx;
+        if (sm.mode[lane] & VM_ACTIVE) {
+            fx.owPrec = sm.h_prec[lane];
+            fx.owPET = sm.h_owpet[lane];
+            fx.storage_transfer = flux[0];
+            fx.surface_runoff = flux[1];
+            fx.gw_recharge = flux[2];
+        } else {
+            fx = local_flux_load(p, r, m);  // cells outside the computed region keep their last fluxes
+        }
+        local_compute(p, r, m, local_from_tile(sm, lane), fx);
+    }
+}
+
+template <bool LOCAL>
+__device__ __forceinline__ void vertical_tile(const WgkParams &p, VTile &sm, const int begin, const int end, const int m, const int dayofs) {
+    const int slot = p.cal_days[4 * dayofs + 3];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = (begin & ~3) + 32 * blockIdx.x;
+    VThread ts;
+    if (w == 0) v_mode(p, sm, r0, begin, end, m, slot, lane);
+    else v_preload(p, sm, r0, begin, end, m, slot, w, lane);
+    __syncthreads();
+    const bool bands = sm.nband_cells != 0;  // else nothing but bare / inactive cells: the band arrays are not touched
+    if (!bands && w != 0) return;
+    if (bands) v_prefetch(p, sm, ts, r0, m, 0, w, lane);
+    if (w == 0) v_head(p, sm, r0, m, slot, lane);
+    if (bands) {
+        __syncthreads();
+#pragma unroll 1
+        for (int slab = 0; slab < V_NSLAB; slab++) {
+            v_scale(p, sm, ts, r0, m, slab, w, lane);
+            __syncthreads();
+            if (sm.cap_any[slab]) {
+                v_cap_resolve(sm, ts, slab, w, lane);
+                __syncthreads();
+            }
+            v_band(p, sm, ts, r0, m, slab, w, lane);
+            __syncthreads();
+            if (w < 4) v_sum(sm, ts, slab, w, lane);
+        }
+        __syncthreads();
+        if (w != 0) return;
+    } else {
+        v_bare_sums(p, sm, r0, lane);
+    }
+    v_finish<LOCAL>(p, sm, r0, begin, end, m, lane);
+}
+
+__global__ void __launch_bounds__(V_THREADS, 6) k_cells_pre(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
+    __shared__ VTile sm;
+    vertical_tile<true>(p, sm, begin, end, blockIdx.y, dayofs);
+}
+
+// the vertical balance alone over the whole grid (wgk_vertical_day, wgk_profile_day)
+__global__ void __launch_bounds__(V_THREADS, 6) k_vertical(const __grid_constant__ WgkParams p, const int dayofs) {
+    __shared__ VTile sm;
+    vertical_tile<false>(p, sm, 0, p.ncell, blockIdx.y, dayofs);
+}
+
+// thread-per-cell forms of k_vertical and k_cells_pre
+__global__ void __launch_bounds__(VBLOCK) k_vertical_tpc(const __grid_constant__ WgkParams p, const int dayofs) {
+    __shared__ SnowStage stage;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.ncell) return;
+    vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3], &stage);
+}
+
+
+__global__ void __launch_bounds__(VBLOCK) k_cells_pre_tpc(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
     __shared__ SnowStage stage;
     const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= end) return;
