@@ -96,7 +96,7 @@ def make_model(w, ini, members, device):
     import watergap2_b200 as wg
     m = wg.Model(w.ng, nmember=members, npset=1, device=device)
     topo = ini["_topology"]
-    m.set_topology(topo["rout_order"], topo["outflow_cell"])
+    m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
     m.load(ini)
     return m
 

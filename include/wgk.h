@@ -80,6 +80,12 @@ int wgk_set_stream(wgk_ctx *ctx, void *cuda_stream);
 /* rout_order[n]: 1-based routing rank of cell n (G_ROUT_ORDER.UNF4, rout_prepare.cpp:834-886);
  * downstream_cell[n]: 1-based number of the cell n drains to, 0 = none (G_OUTFLC.UNF4). */
 int wgk_set_topology(wgk_ctx *ctx, const int32_t *rout_order, const int32_t *downstream_cell);
+/* Optional, BEFORE wgk_set_topology: a small class key per cell (e.g. bit 0 local lake, bit 1 local wetland,
+ * bit 2 global lake/reservoir/wetland, bit 3 arid).  Inside one dependency level the device order is free
+ * (the upstream sums keep the reference's order through the CSR), so cells of equal class are stored next
+ * to each other and the warps of the cell-parallel kernels skip the water-body code they do not need.
+ * Results do not depend on it.  NULL resets to plain routing order. */
+int wgk_set_cell_classes(wgk_ctx *ctx, const uint8_t *cell_class);
 int wgk_num_levels(const wgk_ctx *ctx);
 /* level[n] (0-based dependency level of cell n) for ncell cells; for tests and basin sharding */
 int wgk_get_levels(const wgk_ctx *ctx, int32_t *level);

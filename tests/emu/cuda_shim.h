@@ -23,6 +23,7 @@ static thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline void __syncthreads() {}
+static inline int __syncthreads_or(int p) { return p; }  // only in kernel drivers, which the emulation replaces
 static inline void __pipeline_memcpy_async(void *dst, const void *src, size_t n) { std::memcpy(dst, src, n); }
 static inline void __pipeline_commit() {}
 static inline void __pipeline_wait_prior(int) {}

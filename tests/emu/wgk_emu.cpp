@@ -30,7 +30,7 @@ struct Emu {
     int32_t cal_days[8] = {0};
     int32_t cal[8] = {0};
     bool derived = false;
-    int form = 0;  // 0: band-parallel tiles, 1: thread per cell
+    int form = 0;  // 0: band-parallel tiles (5 warps), 1: thread per cell, 2: band-parallel tiles (2 warps)
 };
 
 template <class K, class... A> static void launch(K kern, dim3 grid, dim3 block, A... args) {
@@ -114,36 +114,48 @@ void emu_set_forcing(Emu *e, const float *P, const float *T, const float *SW, co
         }
 }
 
+}  // extern "C"
+
 // k_cells_pre on the host: the phases of vertical_tile() in the order of the kernel, each phase run
 // for all threads of the CTA before the next one starts (= the barriers of the kernel)
-static void emu_cells_pre(Emu *e, int begin, int end) {
+template <class C>
+static void emu_cells_pre_tiles(Emu *e, int begin, int end) {
     using namespace wgk;
     WgkParams &p = e->p;
-    if (e->form == 1) {  // thread-per-cell form
-        launch(k_cells_pre_tpc, dim3((end - begin + VBLOCK - 1) / VBLOCK, 1), dim3(VBLOCK), p, 0, begin, end);
-        return;
-    }
-    static VTile sm;
-    static VThread ts[V_THREADS];
+    static VTile<C> sm;
+    static VThread<C> ts[C::THREADS];
     const int slot = p.cal_days[3], m = 0;
     for (int tile = 0; tile < v_num_tiles(begin, end); tile++) {
         const int r0 = (begin & ~3) + 32 * tile;
-        auto each = [&](auto fn) { for (int t = 0; t < V_THREADS; t++) fn(t >> 5, t & 31, ts[t]); };
-        each([&](int w, int lane, VThread &) { if (w == 0) v_mode(p, sm, r0, begin, end, m, slot, lane); else v_preload(p, sm, r0, begin, end, m, slot, w, lane); });
+        auto each = [&](auto fn) { for (int t = 0; t < C::THREADS; t++) fn(t >> 5, t & 31, ts[t]); };
+        each([&](int w, int lane, VThread<C> &) { if (w == 0) v_mode<C>(p, sm, r0, begin, end, m, slot, lane); else v_preload<C>(p, sm, r0, begin, end, m, slot, w, lane); });
         if (sm.nband_cells == 0) {
-            for (int lane = 0; lane < 32; lane++) v_head(p, sm, r0, m, slot, lane);
-            for (int lane = 0; lane < 32; lane++) v_bare_sums(p, sm, r0, lane);
+            for (int lane = 0; lane < 32; lane++) v_head<C>(p, sm, r0, m, slot, lane);
+            for (int lane = 0; lane < 32; lane++) v_bare_sums<C>(p, sm, r0, lane);
         } else {
-            each([&](int w, int lane, VThread &t) { v_prefetch(p, sm, t, r0, m, 0, w, lane); });
-            for (int lane = 0; lane < 32; lane++) v_head(p, sm, r0, m, slot, lane);
-            for (int slab = 0; slab < V_NSLAB; slab++) {
-                each([&](int w, int lane, VThread &t) { v_scale(p, sm, t, r0, m, slab, w, lane); });
-                if (sm.cap_any[slab]) each([&](int w, int lane, VThread &t) { v_cap_resolve(sm, t, slab, w, lane); });
-                each([&](int w, int lane, VThread &t) { v_band(p, sm, t, r0, m, slab, w, lane); });
-                each([&](int w, int lane, VThread &t) { if (w < 4) v_sum(sm, t, slab, w, lane); });
+            each([&](int w, int lane, VThread<C> &t) { v_prefetch<C>(p, sm, t, r0, m, 0, w, lane); });
+            for (int lane = 0; lane < 32; lane++) v_head<C>(p, sm, r0, m, slot, lane);
+            for (int slab = 0; slab < C::NSLAB; slab++) {
+                each([&](int w, int lane, VThread<C> &t) { v_scale<C>(p, sm, t, r0, m, slab, w, lane); });
+                if (sm.cap_any[slab]) each([&](int w, int lane, VThread<C> &t) { v_cap_resolve<C>(sm, t, slab, w, lane); });
+                each([&](int w, int lane, VThread<C> &t) { v_band<C>(p, sm, t, r0, m, slab, w, lane); });
+                each([&](int w, int lane, VThread<C> &t) { if (w < 4) v_sum<C>(sm, t, slab, w, lane); });
             }
         }
-        for (int lane = 0; lane < 32; lane++) v_finish<true>(p, sm, r0, begin, end, m, lane);
+        for (int lane = 0; lane < 32; lane++) v_finish<C, true>(p, sm, r0, begin, end, m, lane);
+    }
+}
+
+extern "C" {
+
+static void emu_cells_pre(Emu *e, int begin, int end) {
+    using namespace wgk;
+    if (e->form == 1) {  // thread-per-cell form
+        launch(k_cells_pre_tpc, dim3((end - begin + VBLOCK - 1) / VBLOCK, 1), dim3(VBLOCK), e->p, 0, begin, end);
+    } else if (e->form == 2) {
+        emu_cells_pre_tiles<VCfgMid>(e, begin, end);
+    } else {
+        emu_cells_pre_tiles<VCfgSmall>(e, begin, end);
     }
 }
 
@@ -188,6 +200,30 @@ void emu_day(Emu *e, int day, int month, int dom, int slot, int tail_level0) {
         for (int r = begin; r < end; r++) wgk::route_post_cell(p, r, 0);
     }
     memcpy(p.a.discharge, wgk::qbuf_of_day(p, 0), sizeof(double) * e->stride);
+}
+
+// exactness of the constant-division helper of the kernels: number of operands (out of n pseudo-random ones
+// spread over 600 binades, plus neighbours of powers of two and of multiples of c) whose quotient differs
+// from the IEEE division
+long emu_test_constdiv(long n, unsigned long long seed) {
+    const wgk::ConstDiv cs[4] = {wgk::C100, wgk::C1E6, wgk::C1000, wgk::C30};
+    long bad = 0;
+    unsigned long long x = seed ? seed : 88172645463325252ull;
+    for (long k = 0; k < n; k++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;  // xorshift64
+        unsigned long long bits = (x & 0x000fffffffffffffull) | ((unsigned long long)(1023 - 300 + (int)((x >> 52) % 600)) << 52) | (x & 0x8000000000000000ull);
+        double v;
+        memcpy(&v, &bits, 8);
+        for (const wgk::ConstDiv &c : cs) {
+            const volatile double ref = v / c.c;
+            if (!((v / c) == ref)) bad++;
+            // operands whose quotient is at or next to a representable number
+            const double w = std::nextafter(ref * c.c, (k & 1) ? 1e308 : -1e308);
+            const volatile double ref2 = w / c.c;
+            if (!((w / c) == ref2)) bad++;
+        }
+    }
+    return bad;
 }
 
 void emu_set_form(Emu *e, int form) { e->form = form; }

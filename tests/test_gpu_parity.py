@@ -18,7 +18,7 @@ def _model_from(fields, topo_ro, topo_down, ng, **kw):
     return m
 
 
-@pytest.fixture(params=["bands", "cells"])
+@pytest.fixture(params=["bands", "cells", "bands2"])
 def form(request, monkeypatch):
     """both forms of the vertical kernel: CTA-cooperative band-parallel / thread per cell"""
     monkeypatch.setenv("WGK_VERTICAL_FORM", request.param)
@@ -192,6 +192,29 @@ def test_free_run_full_size_20_days():
     from oracle import synth_world as sw, wg_init
     oracles, m = _run_pair(sw.build_world(67420), 20, block=10)
     _compare(oracles, m, wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS)
+
+
+def test_cell_class_order_does_not_change_results(world3000):
+    """wgk_set_cell_classes re-sorts the device order inside each dependency level; the upstream sums
+    keep the reference's order, so every field must be BIT-identical with and without it."""
+    from oracle import synth_world as sw, wg_init
+    import watergap2_b200 as wg
+    ini = wg_init.derive(world3000)
+    topo = ini["_topology"]
+    f = sw.forcing_month(world3000, 1901, 1)
+    out = []
+    for cls in (None, wg.cell_classes(ini)):
+        m = wg.Model(world3000.ng)
+        m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=cls)
+        m.load(ini)
+        m.forcing_reserve(31)
+        m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+        m.step_days(1, 0, 1, 0, 20)
+        out.append({k: m.get(k) for k in wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS})
+        if cls is not None:
+            assert not np.array_equal(m.device_order(), np.asarray(topo["rout_order"]) - 1)
+    for k in out[0]:
+        assert np.array_equal(out[0][k], out[1][k]), k
 
 
 def test_members_and_parameter_sets(world3000):

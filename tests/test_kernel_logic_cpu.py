@@ -15,7 +15,7 @@ import pytest
 from tests.util import rel_err
 
 
-@pytest.mark.parametrize("tail_level0,form", [(-1, "bands"), (3, "bands"), (3, "cells")])
+@pytest.mark.parametrize("tail_level0,form", [(-1, "bands"), (3, "bands"), (3, "cells"), (-1, "bands2")])
 def test_kernel_source_on_host_matches_oracle(world3000, oracle_lib, tail_level0, form):
     from oracle import synth_world as sw, wg_init
     from tests.emu import Emu
@@ -52,7 +52,7 @@ def test_kernel_source_on_host_matches_oracle(world3000, oracle_lib, tail_level0
     assert worst > 0  # the four substitutions are really in effect
 
 
-@pytest.mark.parametrize("form", ["bands", "cells"])
+@pytest.mark.parametrize("form", ["bands", "cells", "bands2"])
 def test_kernel_source_deep_snow_vs_reference_golden(golden_deep, oracle_lib, form):
     """band-parallel snow kernel on packs of up to 1400 mm per band (1000 mm cap, daily.cpp:958-976)
     against what the compiled reference held in memory; the snow bands themselves must be within
@@ -91,3 +91,14 @@ def test_kernel_source_deep_snow_vs_reference_golden(golden_deep, oracle_lib, fo
                     assert d < (1e-12 if nm in ("snow_bands", "snow") else 2e-11), f"day {sd} {nm}: {d:.2e}"
                 n += 1
     assert n > 100
+
+
+def test_const_division_is_exact():
+    """x / 100., / 1e6, / 1000., / 30. through the kernels' Markstein helper (3 FP64 instructions) must be
+    bit-identical to the IEEE division of the reference for every operand: 4e7 operands over 600 binades."""
+    import ctypes
+    from tests import emu
+    L = ctypes.CDLL(emu.build())
+    L.emu_test_constdiv.restype = ctypes.c_long
+    L.emu_test_constdiv.argtypes = [ctypes.c_long, ctypes.c_ulonglong]
+    assert L.emu_test_constdiv(5_000_000, 20240607) == 0

@@ -20,7 +20,7 @@ def main():
     w, ini = bench.build_inputs()
     m = wg.Model(w.ng, nmember=a.members, use_graph=a.graph)
     topo = ini["_topology"]
-    m.set_topology(topo["rout_order"], topo["outflow_cell"])
+    m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
     m.load(ini)
     f = sw.forcing_month(w, 1901, 1)
     m.forcing_reserve(31)

@@ -19,10 +19,10 @@ def main():
     ini = wg_init.derive(w)
     topo = ini["_topology"]
     f = sw.forcing_month(w, 1901, 1)
-    for form in ("bands", "cells"):
+    for form in ("bands", "bands2", "cells"):
         os.environ["WGK_VERTICAL_FORM"] = form
         m = wg.Model(w.ng, nmember=a.members)
-        m.set_topology(topo["rout_order"], topo["outflow_cell"])
+        m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
         m.load(ini)
         m.forcing_reserve(31)
         m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-__all__ = ["Model", "WgkError", "lib", "LIB_PATH", "FIELD_DTYPES", "build"]
+__all__ = ["Model", "WgkError", "lib", "LIB_PATH", "FIELD_DTYPES", "build", "cell_classes"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwgk.so")
@@ -21,6 +21,15 @@ FIELD_DTYPES = {"f64": np.float64, "f32": np.float32, "i32": np.int32, "i16": np
 
 class WgkError(RuntimeError):
     pass
+
+
+def cell_classes(fields):
+    """Class key per cell for Model.set_topology(cell_class=...): which water-body code a cell needs
+    (bit 0 local lake, bit 1 local wetland, bit 2 global lake / reservoir / global wetland, bit 3 arid)."""
+    f = fields
+    z = lambda k: np.asarray(f[k]).ravel() > 0
+    return (z("loc_lake") * 1 + z("loc_wetland") * 2 + (z("lake_area") | z("reservoir_area") | z("glo_wetland")) * 4
+            + (np.asarray(f["arid"]).ravel() == 1) * 8).astype(np.uint8)
 
 
 class _Options(ctypes.Structure):
@@ -68,6 +77,7 @@ def lib():
     L.wgk_get_stream.restype = vp
     L.wgk_set_stream.argtypes = [vp, vp]
     L.wgk_set_topology.argtypes = [vp, vp, vp]
+    L.wgk_set_cell_classes.argtypes = [vp, vp]
     L.wgk_num_levels.argtypes = [vp]
     L.wgk_get_levels.argtypes = [vp, vp]
     L.wgk_field_id.argtypes = [cp]
@@ -151,10 +161,14 @@ class Model:
         return FIELD_DTYPES[dt.value.decode()], cnt.value, scope
 
     # -- topology / fields --------------------------------------------------------------------
-    def set_topology(self, rout_order, downstream_cell):
+    def set_topology(self, rout_order, downstream_cell, cell_class=None):
         ro = np.ascontiguousarray(rout_order, np.int32)
         dc = np.ascontiguousarray(downstream_cell, np.int32)
         assert ro.size == self.ncell and dc.size == self.ncell
+        if cell_class is not None:
+            cc = np.ascontiguousarray(cell_class, np.uint8)
+            assert cc.size == self.ncell
+            self._ck(self._L.wgk_set_cell_classes(self._c, cc.ctypes.data))
         self._ck(self._L.wgk_set_topology(self._c, ro.ctypes.data, dc.ctypes.data))
 
     @property

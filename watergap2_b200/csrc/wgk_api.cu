@@ -63,7 +63,10 @@ struct wgk_ctx {
     bool have_topology = false;
     int nlevels = 0;
     int tail_level0 = 0;
+    // "rank" below = device position: the routing rank, or - with cell classes - the routing rank re-sorted by
+    // class inside each dependency level
     std::vector<int32_t> rank_of_cell, cell_of_rank, level_off, level_of_rank;
+    std::vector<uint8_t> cell_class;
     int32_t *d_cell_of_rank = nullptr, *d_up_off = nullptr, *d_up_idx = nullptr, *d_down = nullptr, *d_level_off = nullptr;
     int32_t *d_member_pset = nullptr;
     std::vector<int32_t> member_pset;
@@ -96,7 +99,7 @@ struct wgk_ctx {
     int64_t launches = 0;
     bool derived_dirty = true;  // s_c1 / s_slope_pow / s_flags need (re)computation
     bool member_dirty = true;   // s_snowfree needs (re)computation (band state uploaded or exposed)
-    bool band_parallel = true;  // vertical kernel form: CTA-cooperative band-parallel (few members) or thread per cell
+    int form = 0;               // vertical kernel form: 0 thread per cell, 1 band-parallel 5 threads/cell, 2 band-parallel 2 threads/cell
     int32_t *d_gidx = nullptr;  // [ncell] index into the global-water-body scratch or -1
     double *d_gbody = nullptr;  // [nmember][ngbody][GB_N]
     int ngbody = 0;
@@ -190,17 +193,23 @@ int levels_per_chunk() {  // tuning knob (WGK_LEVELS_PER_CHUNK); measured optimu
     return v > 0 ? v : 1;
 }
 
-void launch_cells_pre(wgk_ctx *c, const WgkParams &p, int d, int begin, int end) {
-    if (c->band_parallel)
-        wgk::k_cells_pre<<<dim3(wgk::v_num_tiles(begin, end), c->nmember), wgk::V_THREADS, 0, c->stream>>>(p, d, begin, end);
-    else
-        wgk::k_cells_pre_tpc<<<dim3((end - begin + wgk::VBLOCK - 1) / wgk::VBLOCK, c->nmember), wgk::VBLOCK, 0, c->stream>>>(p, d, begin, end);
+void *cells_pre_fn(const wgk_ctx *c) {
+    return c->form == 1 ? (void *)wgk::k_cells_pre<wgk::VCfgSmall> : c->form == 2 ? (void *)wgk::k_cells_pre<wgk::VCfgMid> : (void *)wgk::k_cells_pre_tpc;
 }
-void launch_vertical(wgk_ctx *c, const WgkParams &p, int d) {
-    if (c->band_parallel)
-        wgk::k_vertical<<<dim3(wgk::v_num_tiles(0, c->ncell), c->nmember), wgk::V_THREADS, 0, c->stream>>>(p, d);
-    else
-        wgk::k_vertical_tpc<<<dim3((c->ncell + wgk::VBLOCK - 1) / wgk::VBLOCK, c->nmember), wgk::VBLOCK, 0, c->stream>>>(p, d);
+void *vertical_fn(const wgk_ctx *c) {
+    return c->form == 1 ? (void *)wgk::k_vertical<wgk::VCfgSmall> : c->form == 2 ? (void *)wgk::k_vertical<wgk::VCfgMid> : (void *)wgk::k_vertical_tpc;
+}
+dim3 cells_pre_block(const wgk_ctx *c) { return dim3(c->form == 1 ? wgk::VCfgSmall::THREADS : c->form == 2 ? wgk::VCfgMid::THREADS : wgk::VBLOCK); }
+dim3 cells_pre_grid(const wgk_ctx *c, int begin, int end) {
+    return c->form ? dim3(wgk::v_num_tiles(begin, end), c->nmember) : dim3((end - begin + wgk::VBLOCK - 1) / wgk::VBLOCK, c->nmember);
+}
+cudaError_t launch_cells_pre(wgk_ctx *c, const WgkParams &p, int d, int begin, int end) {
+    void *args[] = {(void *)&p, &d, &begin, &end};
+    return cudaLaunchKernel(cells_pre_fn(c), cells_pre_grid(c, begin, end), cells_pre_block(c), args, 0, c->stream);
+}
+cudaError_t launch_vertical(wgk_ctx *c, const WgkParams &p, int d) {
+    void *args[] = {(void *)&p, &d};
+    return cudaLaunchKernel(vertical_fn(c), cells_pre_grid(c, 0, c->ncell), cells_pre_block(c), args, 0, c->stream);
 }
 
 // plain launches of one simulated day (day offset `d` of the current call) on c->stream, phase
@@ -283,11 +292,9 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
         return cudaGraphAddKernelNode(node, g, dd.data(), dd.size(), &kp);
     };
     WgkParams pp = p;
-    void *pre_fn = c->band_parallel ? (void *)wgk::k_cells_pre : (void *)wgk::k_cells_pre_tpc;
-    const dim3 pre_block(c->band_parallel ? wgk::V_THREADS : wgk::VBLOCK);
-    auto pre_grid = [&](int begin, int end) {
-        return c->band_parallel ? dim3(wgk::v_num_tiles(begin, end), c->nmember) : dim3((end - begin + wgk::VBLOCK - 1) / wgk::VBLOCK, c->nmember);
-    };
+    void *pre_fn = cells_pre_fn(c);
+    const dim3 pre_block = cells_pre_block(c);
+    auto pre_grid = [&](int begin, int end) { return cells_pre_grid(c, begin, end); };
     for (int d = 0; d < ndays; d++) {
         cudaGraphNode_t reuse = (d >= wgk::QBUF_K) ? dayEnd[d - wgk::QBUF_K] : nullptr;
         cudaGraphNode_t last = nullptr;
@@ -398,13 +405,16 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     c->npset = npset;
     if (opt) c->opt = *opt;
     else { c->opt.restart = 0; c->opt.tail_threshold = 0; c->opt.use_graph = 1; }
-    {   // small problems (members x cells cannot fill the GPU with one thread per cell): the cell-day -> cell-day
-        // latency chain bounds the run, use the band-parallel form; otherwise the thread-per-cell form, which
-        // keeps every lane busy in the scalar parts of the step
-        const char *e = getenv("WGK_VERTICAL_FORM");  // "bands" | "cells" (tests exercise both)
-        if (e && !strcmp(e, "bands")) c->band_parallel = true;
-        else if (e && !strcmp(e, "cells")) c->band_parallel = false;
-        else c->band_parallel = ((long long)nmember * ncell < 32768);
+    {   // Form of the vertical kernel.  Small problems cannot fill the GPU with one thread per cell: the
+        // cell-day -> cell-day latency chain bounds the run and the band-parallel forms shorten it (5 threads
+        // per cell while far from full, 2 threads per cell while all tiles still fit the SMs at once);
+        // beyond that the thread-per-cell form, which keeps every lane busy in the scalar parts of the step.
+        const char *e = getenv("WGK_VERTICAL_FORM");  // "cells" | "bands" | "bands2" (tests exercise all)
+        const long long work = (long long)nmember * ncell;
+        if (e && !strcmp(e, "bands")) c->form = 1;
+        else if (e && !strcmp(e, "bands2")) c->form = 2;
+        else if (e && !strcmp(e, "cells")) c->form = 0;
+        else c->form = work < 32768 ? 1 : 0;  // (the 2-threads-per-cell form never beat both others on B200)
     }
     if (c->opt.tail_threshold <= 0) {
         const char *e = getenv("WGK_TAIL_THRESHOLD");
@@ -412,12 +422,11 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     }
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    // the tile kernels stage 36 KB per CTA: ask for the largest shared-memory carve-out so that 6 CTAs fit an SM
-    CU(cudaFuncSetAttribute((const void *)wgk::k_cells_pre, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute((const void *)wgk::k_vertical, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute((const void *)wgk::k_cells_pre_tpc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute((const void *)wgk::k_vertical_tpc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    c->own_stream = true;
+    // the tile kernels keep up to 36 KB per CTA in shared memory: ask for the largest carve-out
+    for (const void *fn : {(const void *)wgk::k_cells_pre<wgk::VCfgSmall>, (const void *)wgk::k_cells_pre<wgk::VCfgMid>,
+                           (const void *)wgk::k_vertical<wgk::VCfgSmall>, (const void *)wgk::k_vertical<wgk::VCfgMid>,
+                           (const void *)wgk::k_cells_pre_tpc, (const void *)wgk::k_vertical_tpc})
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     for (int f = 0; f < WGK_F_COUNT; f++) {
         const size_t bytes = field_rows(c, f) * field_row_elems(c, f) * kFields[f].elsize;
         void *d = nullptr;
@@ -481,48 +490,79 @@ int wgk_set_stream(wgk_ctx *c, void *s) {
 // ---------------------------------------------------------------------------------------
 // topology
 // ---------------------------------------------------------------------------------------
+int wgk_set_cell_classes(wgk_ctx *c, const uint8_t *cell_class) {
+    if (!c) return WGK_ERR_ARG;
+    if (cell_class) c->cell_class.assign(cell_class, cell_class + c->ncell);
+    else c->cell_class.clear();
+    return WGK_OK;
+}
+
 int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downstream_cell) {
     if (!c || !rout_order || !downstream_cell) return WGK_ERR_ARG;
     CU(cudaSetDevice(c->device));
     const int ng = c->ncell;
-    c->rank_of_cell.assign(ng, -1);
-    c->cell_of_rank.assign(ng, -1);
+    // reference routing rank (G_ROUT_ORDER) <-> cell
+    std::vector<int32_t> cell_of_r(ng, -1), r_of_cell(ng, -1);
     for (int n = 0; n < ng; n++) {
         const int r = rout_order[n] - 1;
-        if (r < 0 || r >= ng || c->cell_of_rank[r] != -1) return fail(c, WGK_ERR_TOPOLOGY, "rout_order is not a permutation of 1..ncell (cell %d)", n + 1);
-        c->cell_of_rank[r] = n;
-        c->rank_of_cell[n] = r;
+        if (r < 0 || r >= ng || cell_of_r[r] != -1) return fail(c, WGK_ERR_TOPOLOGY, "rout_order is not a permutation of 1..ncell (cell %d)", n + 1);
+        cell_of_r[r] = n;
+        r_of_cell[n] = r;
     }
-    std::vector<int32_t> down(ng, -1), nup(ng, 0);
+    std::vector<int32_t> down_r(ng, -1);
     for (int n = 0; n < ng; n++) {
         const int d = downstream_cell[n];
         if (d < 0 || d > ng) return fail(c, WGK_ERR_TOPOLOGY, "downstream cell of cell %d out of range", n + 1);
         if (d > 0) {
-            const int rd = c->rank_of_cell[d - 1], rn = c->rank_of_cell[n];
+            const int rd = r_of_cell[d - 1], rn = r_of_cell[n];
             if (rd <= rn) return fail(c, WGK_ERR_TOPOLOGY, "cell %d is routed before its upstream cell %d", d, n + 1);
-            down[rn] = rd;
-            nup[rd]++;
+            down_r[rn] = rd;
         }
     }
-    // upstream CSR in device order; entries ascending in rank = the order in which the
-    // reference adds them to G_riverInflow (routing.cpp:3955-3958)
-    std::vector<int32_t> up_off(ng + 1, 0);
-    for (int r = 0; r < ng; r++) up_off[r + 1] = up_off[r] + nup[r];
-    std::vector<int32_t> up_idx(std::max(1, up_off[ng])), fill(ng, 0);
-    for (int r = 0; r < ng; r++)
-        if (down[r] >= 0) up_idx[up_off[down[r]] + fill[down[r]]++] = r;
     // dependency level = longest path from a headwater; the rank order of rout_prepare.cpp's
     // Kahn sweeps is level-major, which is verified here
-    c->level_of_rank.assign(ng, 0);
+    std::vector<int32_t> level_r(ng, 0);
     for (int r = 0; r < ng; r++)
-        if (down[r] >= 0) c->level_of_rank[down[r]] = std::max(c->level_of_rank[down[r]], c->level_of_rank[r] + 1);
+        if (down_r[r] >= 0) level_r[down_r[r]] = std::max(level_r[down_r[r]], level_r[r] + 1);
     for (int r = 1; r < ng; r++)
-        if (c->level_of_rank[r] < c->level_of_rank[r - 1])
+        if (level_r[r] < level_r[r - 1])
             return fail(c, WGK_ERR_TOPOLOGY, "routing order is not level-major at rank %d (not produced by rout_order sweeps)", r);
-    c->nlevels = c->level_of_rank[ng - 1] + 1;
+    c->nlevels = level_r[ng - 1] + 1;
     c->level_off.assign(c->nlevels + 1, 0);
-    for (int r = 0; r < ng; r++) c->level_off[c->level_of_rank[r] + 1]++;
+    for (int r = 0; r < ng; r++) c->level_off[level_r[r] + 1]++;
     for (int l = 0; l < c->nlevels; l++) c->level_off[l + 1] += c->level_off[l];
+    // device position: rank order, stably re-sorted by class inside each level
+    std::vector<int32_t> r_of_pos(ng), pos_of_r(ng);
+    for (int r = 0; r < ng; r++) r_of_pos[r] = r;
+    if (!c->cell_class.empty())
+        for (int l = 0; l < c->nlevels; l++)
+            std::stable_sort(r_of_pos.begin() + c->level_off[l], r_of_pos.begin() + c->level_off[l + 1],
+                             [&](int a, int b) { return c->cell_class[cell_of_r[a]] < c->cell_class[cell_of_r[b]]; });
+    for (int x = 0; x < ng; x++) pos_of_r[r_of_pos[x]] = x;
+    c->rank_of_cell.assign(ng, -1);
+    c->cell_of_rank.assign(ng, -1);
+    c->level_of_rank.assign(ng, 0);
+    std::vector<int32_t> down(ng, -1), nup(ng, 0);
+    for (int x = 0; x < ng; x++) {
+        const int r = r_of_pos[x];
+        c->cell_of_rank[x] = cell_of_r[r];
+        c->rank_of_cell[cell_of_r[r]] = x;
+        c->level_of_rank[x] = level_r[r];
+        if (down_r[r] >= 0) {
+            down[x] = pos_of_r[down_r[r]];
+            nup[down[x]]++;
+        }
+    }
+    // upstream CSR in device positions; the entries of a cell ascend in reference rank = the order in
+    // which the reference adds them to G_riverInflow (routing.cpp:3955-3958)
+    std::vector<int32_t> up_off(ng + 1, 0);
+    for (int x = 0; x < ng; x++) up_off[x + 1] = up_off[x] + nup[x];
+    std::vector<int32_t> up_idx(std::max(1, up_off[ng])), fill(ng, 0);
+    for (int r = 0; r < ng; r++)
+        if (down_r[r] >= 0) {
+            const int xd = pos_of_r[down_r[r]];
+            up_idx[up_off[xd] + fill[xd]++] = pos_of_r[r];
+        }
     // narrow tail: first level from which every level has <= tail_threshold cells
     c->tail_level0 = c->nlevels;
     for (int l = c->nlevels - 1; l >= 0; l--) {
@@ -934,6 +974,17 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     for (auto &e : ev) cudaEventDestroy(e);
     return publish_discharge(c, 0);
 }
+
+#ifdef WGK_PHASE_TIMING
+// development builds only (-DWGK_PHASE_TIMING): read and reset the per-phase cycle counters of the tile kernels
+int wgk_debug_phases(wgk_ctx *c, unsigned long long out[8]) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyFromSymbol(out, wgk::g_phase, sizeof(unsigned long long) * 8));
+    unsigned long long z[8] = {0};
+    CU(cudaMemcpyToSymbol(wgk::g_phase, z, sizeof z));
+    return WGK_OK;
+}
+#endif
 
 int64_t wgk_kernel_launches(const wgk_ctx *c) { return c ? c->launches : 0; }
 

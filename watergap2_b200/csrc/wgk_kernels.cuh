@@ -56,6 +56,20 @@ namespace wgk {
 
 constexpr double MIN_STOR_VOL = 1.e-15;  // routing.h:24
 
+// Division by one of the unit-conversion constants of the reference (/ 100., / 1000000., / 1000., / 30.):
+// q0 = x * RN(1/c), then one FMA residual correction (Markstein).  With RN(1/c) correctly rounded and the
+// significand of c not all ones the result IS the correctly rounded quotient x / c, i.e. bit-identical to the
+// division it replaces, in 3 dependent FP64 instructions instead of ~25 (there are ~80 such divisions on the
+// path of one cell-day).  tests/test_kernel_logic_cpu.py::test_const_division_is_exact checks 4e7 operands.
+struct ConstDiv {
+    double c, rc;
+};
+__device__ __forceinline__ double operator/(const double x, const ConstDiv d) {
+    const double q = x * d.rc;
+    return fma(fma(-d.c, q, x), d.rc, q);
+}
+constexpr ConstDiv C100{100., 0.01}, C1E6{1000000., 1e-6}, C1000{1000., 0.001}, C30{30., 1. / 30.};
+
 // Shared-memory staging of the 100 snow bands of a cell: the band columns of the CTA's 128
 // cells are brought in by cp.async (LDGSTS) in chunks of SNOW_CH bands, double buffered, so
 // that all loads of the band loop are in flight while the thread evaluates radiation / PET /
@@ -91,7 +105,7 @@ __device__ __forceinline__ double lai_growing(int &days, int initialDays, int &s
                     days = initialDays + 30;
                     status = 1;
                 }
-                return (LAImin + (LAImax - LAImin) * (days - initialDays) / 30.);
+                return (LAImin + (LAImax - LAImin) * (days - initialDays) / C30);
             } else {
                 days = initialDays;
                 return LAImin;
@@ -110,7 +124,7 @@ __device__ __forceinline__ double lai_growing(int &days, int initialDays, int &s
                 status = 0;
                 precsum = 0.;
             }
-            return (LAImax - (LAImax - LAImin) * (30 - days) / 30.);
+            return (LAImax - (LAImax - LAImin) * (30 - days) / C30);
         } else {
             if (arid && (prec < 0.5)) days--;
             else days = 30 + initialDays;
@@ -130,7 +144,7 @@ __device__ __forceinline__ double lai_nogrowing(int &days, int initialDays, int 
                     days = initialDays + 30;
                     status = 1;
                 }
-                return (LAImin + (LAImax - LAImin) * (days - initialDays) / 30.);
+                return (LAImin + (LAImax - LAImin) * (days - initialDays) / C30);
             } else {
                 days = initialDays;
                 return LAImin;
@@ -147,7 +161,7 @@ __device__ __forceinline__ double lai_nogrowing(int &days, int initialDays, int 
                 status = 0;
                 precsum = 0.;
             }
-            return (LAImax - (LAImax - LAImin) * (30 - days) / 30.);
+            return (LAImax - (LAImax - LAImin) * (30 - days) / C30);
         } else {
             days--;
             return LAImax;
@@ -340,7 +354,7 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
         __pipeline_wait_prior(0);
 #pragma unroll 4
         for (int e = 1; e < 101; e++) {
-            storage_transfer += *S / 100.;
+            storage_transfer += *S / C100;
             *S = 0.;
             S += p.stride;
         }
@@ -462,7 +476,7 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
                 immediate_runoff *= cfa;
                 const short Rgmax = a.rgmax[q];
                 const float gwFactor = a.gwfactor[q];
-                if ((Rgmax / 100.) < (gwFactor * daily_runoff)) daily_gw_recharge = Rgmax / 100.;
+                if ((Rgmax / C100) < (gwFactor * daily_runoff)) daily_gw_recharge = Rgmax / C100;
                 else daily_gw_recharge = gwFactor * daily_runoff;
                 pot_gw_recharge = 0.;
                 if (((arid_gw) && (a.texture[r] < 21)) && (a.ldd[r] >= 0)) {  // :1165-1176
@@ -519,11 +533,11 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
 // ----------------------------------------------------------------------------------------
 // vertical water balance (daily.cpp:94-1264), CTA-cooperative and band-parallel
 //
-// One CTA of V_NW warps works on a TILE of 32 consecutive cells (lane = cell):
+// One CTA of NW warps works on a TILE of 32 consecutive cells (lane = cell):
 //   v_mode   warp 0   per-cell regime (off / no land / bare and warm / needs the band loop) and the
 //                     scalars the band threads need that do not depend on the head
 //   v_head   warp 0   forcing, LAI, radiation, PET, interception          (daily.cpp:186-894)
-//   slabs    all      the 100 snow bands in V_NSLAB slabs of V_SLAB bands; inside a slab warp w owns
+//   slabs    all      the 100 snow bands in NSLAB slabs of SLAB bands; inside a slab warp w owns
 //                     V_BPW consecutive bands of the 32 cells (coalesced 256 B rows), the loads of
 //                     the next slab are in flight while the current one is evaluated     (:913-1062)
 //   v_sum    warps 0-3  the four band sums (storage change, effective precipitation, sublimation,
@@ -540,9 +554,18 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
 // same additions the loop would do (100 x "+= precipitation"), so results are unchanged; a tile
 // made of such cells only never touches the band arrays.
 // ----------------------------------------------------------------------------------------
-constexpr int V_NW = 5, V_BPW = 4;
-constexpr int V_SLAB = V_NW * V_BPW, V_NSLAB = 100 / V_SLAB, V_THREADS = 32 * V_NW;
-static_assert(V_SLAB * V_NSLAB == 100 && V_NW == 5, "slabs must tile the 100 bands; warps 1-4 preload, warps 0-3 sum");
+// NW warps per tile, BPW bands per warp and slab; PRE: inputs of head / tail / local routing preloaded into
+// shared memory by the warps that idle while warp 0 determines the regimes
+template <int NW_, int BPW_, bool PRE_>
+struct VCfg {
+    static constexpr int NW = NW_, BPW = BPW_, SLAB = NW_ * BPW_, NSLAB = 100 / (NW_ * BPW_), THREADS = 32 * NW_;
+    static constexpr int NQ = (4 + NW_ - 1) / NW_;  // band sums per warp
+    static constexpr bool PRE = PRE_;
+    static_assert(SLAB * NSLAB == 100, "slabs must tile the 100 bands");
+    static_assert(!PRE_ || NW_ >= 2, "the preload needs a warp besides warp 0");
+};
+using VCfgSmall = VCfg<5, 4, true>;  // 5 threads per cell: shortest chain, for problems far too small to fill the GPU
+using VCfgMid = VCfg<2, 5, false>;   // 2 threads per cell: all tiles of a 0.5 degree member resident at once
 enum { VM_ACTIVE = 1, VM_NOLAND = 2, VM_BARE = 4 };
 enum { Q_CHG = 0, Q_EFF = 1, Q_SUB = 2, Q_SNOW = 3 };
 
@@ -554,37 +577,44 @@ enum { LI_ekg, LI_invkg, LI_evaredex, LI_area, LI_cfa, LI_contf, LI_fswb_init, L
 enum { TI_builtup, TI_smax, TI_gwfactor, HI_laimax, VP_NF };
 enum { K_contcell, K_flags, K_ldd, K_arid, K_texture, K_rgmax, K_lc, K_lai_days, K_lai_status, VP_NK };
 
+template <class C>
 struct VTile {
     // band-loop scalars of the tile's cells
     double T[32], grad[32], lafPrev[32], laf[32], inv_laf[32], fz[32], mt[32], ddf[32], prec[32], pet[32];
     int elev0[32], mode[32];
-    int cap_first[32], cap_elev[32], cap_any[V_NSLAB], nband_cells;
+    int cap_first[32], cap_elev[32], cap_any[C::NSLAB], nband_cells;
     double temp1[32];  // temperature of band 1 (TempElevMax, daily.cpp:1030)
-    double contrib[4][V_SLAB][32], acc_init[32], fin[4][32];
+    double contrib[4][C::SLAB][32], acc_init[32], fin[4][32];
     int nz[32];
     // head -> tail
     double h_prec[32], h_cfa[32], h_canopy_evapo[32], h_lsc[32], h_maxpet[32], h_owpet[32];
     // inputs of the head, the tail and the local routing, brought in by warps 1-4 (cp.async) while
     // warp 0 determines the regimes: after the first barrier warp 0 computes from shared memory only
-    double pd[VP_ND][32];
-    float pf[VP_NF][32];
-    float4 pforce[32];
-    int pk[VP_NK][32];
+    double pd[C::PRE ? VP_ND : 1][32];
+    float pf[C::PRE ? VP_NF : 1][32];
+    float4 pforce[C::PRE ? 32 : 1];
+    int pk[C::PRE ? VP_NK : 1][32];
 };
 
 // registers of one thread that live across the barriers of a tile
+template <class C>
 struct VThread {
-    double pre_s[V_BPW], cur_s[V_BPW], acc;
-    int pre_e[V_BPW], cur_e[V_BPW], nz;
+    double pre_s[C::BPW], cur_s[C::BPW], acc[C::NQ];
+    int pre_e[C::BPW], cur_e[C::BPW], nz;
 };
+// input of the scalar phases: from the preloaded shared-memory slot or straight from global memory
+#define VIN_D(slot_, expr_) (C::PRE ? sm.pd[C::PRE ? (slot_) : 0][lane] : (double)(expr_))
+#define VIN_F(slot_, expr_) (C::PRE ? sm.pf[C::PRE ? (slot_) : 0][lane] : (float)(expr_))
+#define VIN_K(slot_, expr_) (C::PRE ? sm.pk[C::PRE ? (slot_) : 0][lane] : (int)(expr_))
 
 // regime of the cell and head-independent scalars (warp 0, lane = cell)
-__device__ __forceinline__ void v_mode(const WgkParams &p, VTile &sm, const int r0, const int begin, const int end, const int m,
+template <class C>
+__device__ __forceinline__ void v_mode(const WgkParams &p, VTile<C> &sm, const int r0, const int begin, const int end, const int m,
                                        const int slot, const int lane) {
     const WgkArrays &a = p.a;
     const int r = r0 + lane;
     if (lane == 0) sm.nband_cells = 0;
-    if (lane < V_NSLAB) sm.cap_any[lane] = 0;
+    if (lane < C::NSLAB) sm.cap_any[lane] = 0;
     sm.cap_first[lane] = 1000;
     sm.cap_elev[lane] = 0;
 #ifndef WGK_EMU
@@ -632,52 +662,56 @@ __device__ __forceinline__ void v_mode(const WgkParams &p, VTile &sm, const int 
     sm.mode[lane] = mode;
 }
 
-// issue the loads of slab `slab` (bands slab*V_SLAB + w*V_BPW + j + 1) into the prefetch registers
-__device__ __forceinline__ void v_prefetch(const WgkParams &p, const VTile &sm, VThread &ts, const int r0, const int m, const int slab,
+// issue the loads of slab `slab` (bands slab*C::SLAB + w*C::BPW + j + 1) into the prefetch registers
+template <class C>
+__device__ __forceinline__ void v_prefetch(const WgkParams &p, const VTile<C> &sm, VThread<C> &ts, const int r0, const int m, const int slab,
                                            const int w, const int lane) {
     const int mode = sm.mode[lane];
     const bool on = (mode & VM_ACTIVE) && !(mode & VM_BARE);
     const size_t r = (size_t)(r0 + lane);
-    const int e0 = slab * V_SLAB + w * V_BPW + 1;
+    const int e0 = slab * C::SLAB + w * C::BPW + 1;
     const double *__restrict__ S = p.a.snow_bands + ((size_t)m * WGK_NBAND_K + e0) * p.stride + r;
     const int16_t *__restrict__ E = p.a.s_delev + (size_t)e0 * p.stride + r;
 #pragma unroll
-    for (int j = 0; j < V_BPW; j++) {
+    for (int j = 0; j < C::BPW; j++) {
         ts.pre_s[j] = on ? S[(size_t)j * p.stride] : 0.;
         ts.pre_e[j] = on ? (int)E[(size_t)j * p.stride] : 0;
     }
 }
 
 // forcing, LAI, radiation, PET, interception (warp 0, lane = cell)
-__device__ __forceinline__ void v_head(const WgkParams &p, VTile &sm, const int r0, const int m, const int slot, const int lane) {
+template <class C>
+__device__ __forceinline__ void v_head(const WgkParams &p, VTile<C> &sm, const int r0, const int m, const int slot, const int lane) {
     const WgkArrays &a = p.a;
     const int mode = sm.mode[lane];
     if (!(mode & VM_ACTIVE)) return;
     const int r = r0 + lane;
     const size_t i = (size_t)m * p.stride + r;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
     const double landAreaFrac = sm.laf[lane], lafPrev = sm.lafPrev[lane];
-    const int lc = sm.pk[K_lc][lane] - 1;
-    const float4 f = sm.pforce[lane];
+    const int lc = VIN_K(K_lc, a.landcover[r]) - 1;
+    const float4 f = C::PRE ? sm.pforce[C::PRE ? lane : 0]
+                            : p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r];
     double dailyPrec = (double)f.x;
     const double dailyTempC = (double)f.y;
     const double dailyShortWave = (double)f.z;
     const double dailyLongWave = (double)f.w;
 
-    dailyPrec = sm.pd[HI_p_prec][lane] * dailyPrec;  // :248
+    dailyPrec = VIN_D(HI_p_prec, a.p_prec[q]) * dailyPrec;  // :248
     const double temp2 = dailyTempC + 237.3;
     const double e_s = 0.6108 * exp(17.27 * dailyTempC / temp2);
 
     // arid / humid (:331-348); any other index value is rejected on upload
-    const bool arid_gw = (sm.pk[K_arid][lane] == 1);
-    const double alpha = arid_gw ? sm.pd[HI_ptc_ari][lane] : sm.pd[HI_ptc_hum][lane];
+    const bool arid_gw = (VIN_K(K_arid, a.arid[r]) == 1);
+    const double alpha = arid_gw ? VIN_D(HI_ptc_ari, a.p_ptc_ari[q]) : VIN_D(HI_ptc_hum, a.p_ptc_hum[q]);
 
     // LAI / Kc (:355-356); LAImin in float arithmetic as in lai.cpp:154
-    const float laimax_f = sm.pf[HI_laimax][lane];
+    const float laimax_f = VIN_F(HI_laimax, a.laimax[q]);
     const float LAImin_f = __fadd_rn(a.lai_factor_a[lc], __fmul_rn(a.lai_factor_b[lc], laimax_f));
     const double LAImin = (double)LAImin_f;
     const double LAImaxd = (double)laimax_f;
-    int days = sm.pk[K_lai_days][lane], status = sm.pk[K_lai_status][lane];
-    double precsum = sm.pd[HI_lai_precsum][lane];
+    int days = VIN_K(K_lai_days, a.lai_days[i]), status = VIN_K(K_lai_status, a.lai_status[i]);
+    double precsum = VIN_D(HI_lai_precsum, a.lai_precsum[i]);
     double dailyLai;
     if (dailyTempC > 8.)
         dailyLai = lai_growing(days, a.lai_initial_days[lc], status, lc + 1, arid_gw, LAImin, LAImaxd, precsum, dailyPrec);
@@ -690,7 +724,7 @@ __device__ __forceinline__ void v_head(const WgkParams &p, VTile &sm, const int 
     if ((LAImaxd - LAImin) == 0.) dailyKc = a.lai_kc_min[lc];
     else dailyKc = a.lai_kc_min[lc] + (a.lai_kc_max[lc] - a.lai_kc_min[lc]) * (dailyLai - LAImin) / (LAImaxd - LAImin);
 
-    const double snow_prev = sm.pd[HI_snow][lane];
+    const double snow_prev = VIN_D(HI_snow, a.snow[i]);
     double albedo;
     if (snow_prev > 3.) albedo = a.lct_albedo_snow[lc];  // :366
     else albedo = 0.23;                                   // use_kc == 1
@@ -709,7 +743,7 @@ __device__ __forceinline__ void v_head(const WgkParams &p, VTile &sm, const int 
     const double long_wave_rad_out = emissivity * stefan_boltz_const * (temp_K2 * temp_K2) / lat_heat;
     const double net_long_wave_rad = long_wave_rad_in - long_wave_rad_out;
     const double net_short_wave_rad = solar_rad * (1. - albedo);
-    const double net_rad = sm.pd[HI_netrad][lane] * (net_short_wave_rad + net_long_wave_rad);
+    const double net_rad = VIN_D(HI_netrad, a.p_netrad[q]) * (net_short_wave_rad + net_long_wave_rad);
     const double openWaterNetShortWaveRad = solar_rad * (1. - 0.08);
     const double openWaterNetRad = openWaterNetShortWaveRad + net_long_wave_rad;
 
@@ -725,7 +759,7 @@ __device__ __forceinline__ void v_head(const WgkParams &p, VTile &sm, const int 
         dailyPET *= dailyKc;
         dailyOpenWaterPET *= 1.05;
     }
-    const double cfa = sm.pd[LI_cfa][lane];
+    const double cfa = VIN_D(LI_cfa, a.cfa[q]);
     a.lake_balance[i] = (dailyPrec - dailyOpenWaterPET) * cfa;
     a.openwater_prec[i] = dailyPrec;
     a.openwater_pet[i] = dailyOpenWaterPET;
@@ -733,7 +767,7 @@ __device__ __forceinline__ void v_head(const WgkParams &p, VTile &sm, const int 
     double landStorageChangeSum = 0.;
     double dailyCanopyEvapo = 0., daily_prec_to_soil = 0., dailySoilPET = 0.;
     // interception (:825-894)
-    double canopy = sm.pd[HI_canopy][lane];
+    double canopy = VIN_D(HI_canopy, a.canopy[i]);
     double acc_init = 0.;
     if (mode & VM_NOLAND) {
         acc_init = canopy;  // storage_transfer starts with the canopy water (:829)
@@ -743,7 +777,7 @@ __device__ __forceinline__ void v_head(const WgkParams &p, VTile &sm, const int 
         if (fabs(canopy) <= MIN_STOR_VOL) canopy = 0.;
         const double initialStorage = canopy;
         if (dailyLai > 0.00001) {
-            const double max_canopy_storage = sm.pd[HI_mcwh][lane] * dailyLai;
+            const double max_canopy_storage = VIN_D(HI_mcwh, a.p_mcwh[q]) * dailyLai;
             const double canopy_deficiency = max_canopy_storage - canopy;
             if (dailyPrec < canopy_deficiency) {
                 canopy += dailyPrec;
@@ -778,26 +812,27 @@ __device__ __forceinline__ void v_head(const WgkParams &p, VTile &sm, const int 
     sm.h_cfa[lane] = cfa;
     sm.h_canopy_evapo[lane] = dailyCanopyEvapo;
     sm.h_lsc[lane] = landStorageChangeSum;
-    sm.h_maxpet[lane] = sm.pd[HI_pet_mxdy][lane];
+    sm.h_maxpet[lane] = VIN_D(HI_pet_mxdy, a.p_pet_mxdy[q]);
     sm.h_owpet[lane] = dailyOpenWaterPET;
 }
 
 // take over the prefetched slab, start the next one, rescale to the new land area fraction and
 // look for bands above the 1000 mm cap (:947-976)
-__device__ __forceinline__ void v_scale(const WgkParams &p, VTile &sm, VThread &ts, const int r0, const int m, const int slab,
+template <class C>
+__device__ __forceinline__ void v_scale(const WgkParams &p, VTile<C> &sm, VThread<C> &ts, const int r0, const int m, const int slab,
                                         const int w, const int lane) {
     const int mode = sm.mode[lane];
 #pragma unroll
-    for (int j = 0; j < V_BPW; j++) {
+    for (int j = 0; j < C::BPW; j++) {
         ts.cur_s[j] = ts.pre_s[j];
         ts.cur_e[j] = ts.pre_e[j];
     }
-    if (slab + 1 < V_NSLAB) v_prefetch(p, sm, ts, r0, m, slab + 1, w, lane);
+    if (slab + 1 < C::NSLAB) v_prefetch<C>(p, sm, ts, r0, m, slab + 1, w, lane);
     if (!(mode & VM_ACTIVE) || (mode & VM_NOLAND)) return;
     const double lafPrev = sm.lafPrev[lane], laf = sm.laf[lane], inv_laf = sm.inv_laf[lane];
     bool capped = false;
 #pragma unroll
-    for (int j = 0; j < V_BPW; j++) {
+    for (int j = 0; j < C::BPW; j++) {
         const double num = ts.cur_s[j] * lafPrev;
         double s = num * inv_laf;
         s = fma(fma(-laf, s, num), inv_laf, s);
@@ -805,7 +840,7 @@ __device__ __forceinline__ void v_scale(const WgkParams &p, VTile &sm, VThread &
         ts.cur_s[j] = s;
         if (s > 1000.) {
             capped = true;
-            if (ts.cur_e[j] + sm.elev0[lane] != 0) atomicMin(&sm.cap_first[lane], slab * V_SLAB + w * V_BPW + j + 1);
+            if (ts.cur_e[j] + sm.elev0[lane] != 0) atomicMin(&sm.cap_first[lane], slab * C::SLAB + w * C::BPW + j + 1);
         }
     }
     if (capped) sm.cap_any[slab] = 1;
@@ -813,24 +848,26 @@ __device__ __forceinline__ void v_scale(const WgkParams &p, VTile &sm, VThread &
 
 // only when a band of the tile is above the cap: the first such band of a cell (in band order,
 // with a non-zero elevation) fixes the elevation whose temperature all later capped bands use
-__device__ __forceinline__ void v_cap_resolve(VTile &sm, const VThread &ts, const int slab, const int w, const int lane) {
+template <class C>
+__device__ __forceinline__ void v_cap_resolve(VTile<C> &sm, const VThread<C> &ts, const int slab, const int w, const int lane) {
 #pragma unroll
-    for (int j = 0; j < V_BPW; j++)
-        if (slab * V_SLAB + w * V_BPW + j + 1 == sm.cap_first[lane]) sm.cap_elev[lane] = ts.cur_e[j] + sm.elev0[lane];
+    for (int j = 0; j < C::BPW; j++)
+        if (slab * C::SLAB + w * C::BPW + j + 1 == sm.cap_first[lane]) sm.cap_elev[lane] = ts.cur_e[j] + sm.elev0[lane];
 }
 
 // the bands of one slab: accumulation, sublimation, melt (:978-1045); per-band contributions to
 // the four ordered sums go to shared memory, the new band storage to global memory
-__device__ __forceinline__ void v_band(const WgkParams &p, VTile &sm, const VThread &ts, const int r0, const int m, const int slab,
+template <class C>
+__device__ __forceinline__ void v_band(const WgkParams &p, VTile<C> &sm, const VThread<C> &ts, const int r0, const int m, const int slab,
                                        const int w, const int lane) {
     const int mode = sm.mode[lane];
     const bool store = (mode & VM_ACTIVE) && !(mode & VM_BARE);
-    const int k0 = w * V_BPW, e0 = slab * V_SLAB + k0 + 1;
+    const int k0 = w * C::BPW, e0 = slab * C::SLAB + k0 + 1;
     double *__restrict__ S = p.a.snow_bands + ((size_t)m * WGK_NBAND_K + e0) * p.stride + (size_t)(r0 + lane);
     if (mode & VM_NOLAND) {  // :916-922
 #pragma unroll
-        for (int j = 0; j < V_BPW; j++) {
-            sm.contrib[Q_CHG][k0 + j][lane] = ts.cur_s[j] / 100.;
+        for (int j = 0; j < C::BPW; j++) {
+            sm.contrib[Q_CHG][k0 + j][lane] = ts.cur_s[j] / C100;
             sm.contrib[Q_EFF][k0 + j][lane] = 0.;
             sm.contrib[Q_SUB][k0 + j][lane] = 0.;
             sm.contrib[Q_SNOW][k0 + j][lane] = 0.;
@@ -842,7 +879,7 @@ __device__ __forceinline__ void v_band(const WgkParams &p, VTile &sm, const VThr
     const double prec = sm.prec[lane], pet = sm.pet[lane];
     const bool cap_slab = sm.cap_any[slab] != 0 || sm.cap_elev[lane] != 0;
 #pragma unroll
-    for (int j = 0; j < V_BPW; j++) {
+    for (int j = 0; j < C::BPW; j++) {
         const int de = ts.cur_e[j];
         double temp_elev = T - ((double)de * grad);
         double s = ts.cur_s[j];
@@ -884,31 +921,34 @@ __device__ __forceinline__ void v_band(const WgkParams &p, VTile &sm, const VThr
     }
 }
 
-// ordered accumulation of the slab's contributions: warp q sums quantity q of the 32 cells
-__device__ __forceinline__ void v_sum(VTile &sm, VThread &ts, const int slab, const int q, const int lane) {
-    if (slab == 0) {
-        ts.acc = (q == Q_CHG) ? sm.acc_init[lane] : 0.;
-        ts.nz = 0;
-    }
-    double acc = ts.acc;
-    int nz = ts.nz;
+// ordered accumulation of the slab's contributions: warp w sums the quantities w, w + NW, ... of the 32 cells
+template <class C>
+__device__ __forceinline__ void v_sum(VTile<C> &sm, VThread<C> &ts, const int slab, const int w, const int lane) {
 #pragma unroll
-    for (int k = 0; k < V_SLAB; k++) {
-        const double c = sm.contrib[q][k][lane];
-        acc += c;
-        nz |= (c != 0.);
-    }
-    ts.acc = acc;
-    ts.nz = nz;
-    if (slab == V_NSLAB - 1) {
-        sm.fin[q][lane] = acc;
-        if (q == Q_SNOW) sm.nz[lane] = nz;
+    for (int qi = 0; qi < C::NQ; qi++) {
+        const int q = w + qi * C::NW;
+        if (q >= 4) break;
+        double acc = (slab == 0) ? ((q == Q_CHG) ? sm.acc_init[lane] : 0.) : ts.acc[qi];
+        int nz = (slab == 0) ? 0 : ts.nz;
+#pragma unroll
+        for (int k = 0; k < C::SLAB; k++) {
+            const double c = sm.contrib[q][k][lane];
+            acc += c;
+            if (q == Q_SNOW) nz |= (c != 0.);
+        }
+        ts.acc[qi] = acc;
+        if (q == Q_SNOW) ts.nz = nz;
+        if (slab == C::NSLAB - 1) {
+            sm.fin[q][lane] = acc;
+            if (q == Q_SNOW) sm.nz[lane] = nz;
+        }
     }
 }
 
 // a tile without any cell in the band loop: the sums of its bare cells by the additions the loop
 // would perform on all-zero bands
-__device__ __forceinline__ void v_bare_sums(const WgkParams &p, VTile &sm, const int r0, const int lane) {
+template <class C>
+__device__ __forceinline__ void v_bare_sums(const WgkParams &p, VTile<C> &sm, const int r0, const int lane) {
     const int mode = sm.mode[lane];
     if (!(mode & VM_ACTIVE)) return;
     double eff = 0.;
@@ -926,12 +966,14 @@ __device__ __forceinline__ void v_bare_sums(const WgkParams &p, VTile &sm, const
 }
 
 // immediate runoff, soil, AET, runoff split (warp 0, lane = cell)
-__device__ __forceinline__ void v_tail(const WgkParams &p, VTile &sm, const int r0, const int m, const int lane, double flux[3]) {
+template <class C>
+__device__ __forceinline__ void v_tail(const WgkParams &p, VTile<C> &sm, const int r0, const int m, const int lane, double flux[3]) {
     const WgkArrays &a = p.a;
     const int mode = sm.mode[lane];
     if (!(mode & VM_ACTIVE)) return;
     const int r = r0 + lane;
     const size_t i = (size_t)m * p.stride + r;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
     const bool noland = (mode & VM_NOLAND) != 0;
     const double landAreaFrac = sm.laf[lane], lafPrev = sm.lafPrev[lane];
     const double dailyPrec = sm.h_prec[lane], cfa = sm.h_cfa[lane], dailyCanopyEvapo = sm.h_canopy_evapo[lane];
@@ -942,10 +984,10 @@ __device__ __forceinline__ void v_tail(const WgkParams &p, VTile &sm, const int 
     if (noland) {
         storage_transfer = sm.fin[Q_CHG][lane];
     } else {
-        snow = sm.fin[Q_SNOW][lane] / 100.;
-        dailyEffPrec = sm.fin[Q_EFF][lane] / 100.;
-        dailySnowEvapo = sm.fin[Q_SUB][lane] / 100.;
-        landStorageChangeSum += sm.fin[Q_CHG][lane] / 100.;
+        snow = sm.fin[Q_SNOW][lane] / C100;
+        dailyEffPrec = sm.fin[Q_EFF][lane] / C100;
+        dailySnowEvapo = sm.fin[Q_SUB][lane] / C100;
+        landStorageChangeSum += sm.fin[Q_CHG][lane] / C100;
         TempElevMax = sm.temp1[lane];
     }
     a.snow[i] = snow;
@@ -957,15 +999,15 @@ __device__ __forceinline__ void v_tail(const WgkParams &p, VTile &sm, const int 
     double land_aet = 0., land_aet_uncorr = 0.;
 
     // immediate runoff (:1068-1071)
-    const float builtup = sm.pf[TI_builtup][lane];
+    const float builtup = VIN_F(TI_builtup, a.builtup[r]);
     if (builtup > 0.) {
         immediate_runoff = 0.5 * dailyEffPrec * builtup;
         dailyEffPrec -= immediate_runoff;
     }
 
     // soil and AET (:1080-1239)
-    const double Smax = (double)sm.pf[TI_smax][lane];
-    double soil = sm.pd[TI_soil][lane];
+    const double Smax = (double)VIN_F(TI_smax, a.smax[q]);
+    double soil = VIN_D(TI_soil, a.soil[i]);
     if (noland) {
         storage_transfer += soil;
         storage_transfer *= cfa;
@@ -986,7 +1028,7 @@ __device__ __forceinline__ void v_tail(const WgkParams &p, VTile &sm, const int 
         if (TempElevMax > P_T_SNOWFZ) {
             if (Smax > 0.) {
                 const double soil_saturation = soil / Smax;
-                daily_runoff = dailyEffPrec * pow(soil_saturation, sm.pd[TI_gamma][lane]);
+                daily_runoff = dailyEffPrec * pow(soil_saturation, VIN_D(TI_gamma, a.gamma_hbv[q]));
                 if (dailySoilPET > (maxDailyPET - dailyCanopyEvapo) * soil_saturation)
                     dailyAET = (maxDailyPET - dailyCanopyEvapo) * soil_saturation;
                 else
@@ -1000,13 +1042,13 @@ __device__ __forceinline__ void v_tail(const WgkParams &p, VTile &sm, const int 
                 }
                 daily_runoff *= cfa;
                 immediate_runoff *= cfa;
-                const short Rgmax = (short)sm.pk[K_rgmax][lane];
-                const float gwFactor = sm.pf[TI_gwfactor][lane];
-                if ((Rgmax / 100.) < (gwFactor * daily_runoff)) daily_gw_recharge = Rgmax / 100.;
+                const short Rgmax = (short)VIN_K(K_rgmax, a.rgmax[q]);
+                const float gwFactor = VIN_F(TI_gwfactor, a.gwfactor[q]);
+                if ((Rgmax / C100) < (gwFactor * daily_runoff)) daily_gw_recharge = Rgmax / C100;
                 else daily_gw_recharge = gwFactor * daily_runoff;
                 pot_gw_recharge = 0.;
-                if (((sm.pk[K_arid][lane] == 1) && (sm.pk[K_texture][lane] < 21)) && (sm.pk[K_ldd][lane] >= 0)) {  // :1165-1176
-                    if (dailyPrec <= sm.pd[TI_pcrit][lane]) {
+                if (((VIN_K(K_arid, a.arid[r]) == 1) && (VIN_K(K_texture, a.texture[r]) < 21)) && (VIN_K(K_ldd, a.ldd[r]) >= 0)) {  // :1165-1176
+                    if (dailyPrec <= VIN_D(TI_pcrit, a.p_pcrit[q])) {
                         pot_gw_recharge = daily_gw_recharge;
                         daily_gw_recharge = 0.;
                     }
@@ -1055,7 +1097,7 @@ __device__ __forceinline__ void v_tail(const WgkParams &p, VTile &sm, const int 
     }
     a.soil[i] = soil;
     a.surface_runoff[i] = total_daily_runoff - daily_gw_recharge;
-    flux[0] = noland ? storage_transfer : sm.pd[LI_transfer_old][lane];  // G_dailyStorageTransfer keeps its last value (:1113)
+    flux[0] = noland ? storage_transfer : VIN_D(LI_transfer_old, a.storage_transfer[i]);  // G_dailyStorageTransfer keeps its last value (:1113)
     flux[1] = total_daily_runoff - daily_gw_recharge;
 }
 
@@ -1226,9 +1268,9 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
     double gwr_loclak = 0., gwr_locwet = 0.;
 
     if (laf <= 0.)  // :1885-1891
-        dailyLocalSurfaceRunoff = fx.storage_transfer * cellArea / 1000000. * li.laf_prev / 100.;
+        dailyLocalSurfaceRunoff = fx.storage_transfer * cellArea / C1E6 * li.laf_prev / C100;
     else
-        dailyLocalSurfaceRunoff = fx.surface_runoff * cellArea / 1000000. * laf / 100.;
+        dailyLocalSurfaceRunoff = fx.surface_runoff * cellArea / C1E6 * laf / C100;
     if (ldd >= 0) {  // :1898-1908
         fswb_catchment = li.fswb_init * 20.;
         if (fswb_catchment > 1.) fswb_catchment = 1.;
@@ -1238,7 +1280,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
         localRunoff = fswb_catchment * dailyLocalSurfaceRunoff;
     }
     if ((0 == arid) && (ldd >= 0)) {  // :1979-2033
-        const double netGWin = fx.gw_recharge * cellArea * (laf / 100.) / 1000000.;
+        const double netGWin = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
         double Sg = li.gw;
         const double qg = gw_step(Sg, netGWin, li.ekg, li.invkg);
         a.gw[i] = Sg;
@@ -1247,14 +1289,14 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
         localRunoff = (fswb_catchment * dailyLocalSurfaceRunoff) + localGWRunoff;
     }
     if (ldd < 0) {  // :2123-2176
-        const double netGWin = fx.gw_recharge * cellArea * (laf / 100.) / 1000000.;
+        const double netGWin = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
         double Sg = li.gw;
         const double qg = gw_step(Sg, netGWin, li.ekg, li.invkg);
         a.gw[i] = Sg;
         if (laf == 0.)
-            dailyLocalSurfaceRunoff = fx.storage_transfer * cellArea / 1000000. * li.laf_prev / 100.;
+            dailyLocalSurfaceRunoff = fx.storage_transfer * cellArea / C1E6 * li.laf_prev / C100;
         else
-            dailyLocalSurfaceRunoff = fx.surface_runoff * cellArea / 1000000. * laf / 100.;
+            dailyLocalSurfaceRunoff = fx.surface_runoff * cellArea / C1E6 * laf / C100;
         localRunoff = dailyLocalSurfaceRunoff + qg;
     }
 
@@ -1264,13 +1306,13 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
         const double loc_lake = li.loc_lake;
         if (loc_lake > 0.) {  // local lake, :2318-2490
             const double prev = li.loc_lake_stor;
-            const double maxStorage = ((loc_lake) / 100.) * cellArea * li.lake_depth;
+            const double maxStorage = ((loc_lake) / C100) * cellArea * li.lake_depth;
             const double rf = li.red_loc_lake;
             double evapo = ((1.0 - cfa) * owPrec * rf) + (cfa * (owPET * rf));
             if (evapo < 0.) evapo = 0.;
-            const double totalInflow = inflow + (owPrec * rf) * (cellArea / 1000000.) * (loc_lake / 100.);
-            if (aridc) gwr_loclak = 10. * rf * loc_lake / 100. / (contf / 100.);
-            const double PETgwr = evapo * (cellArea / 1000000.) * (loc_lake / 100.) + gwr_loclak * cellArea * (contf / 100.) / 1000000.;
+            const double totalInflow = inflow + (owPrec * rf) * (cellArea / C1E6) * (loc_lake / C100);
+            if (aridc) gwr_loclak = 10. * rf * loc_lake / C100 / (contf / C100);
+            const double PETgwr = evapo * (cellArea / C1E6) * (loc_lake / C100) + gwr_loclak * cellArea * (contf / C100) / C1E6;
             double PETgwrMax = prev + maxStorage + totalInflow;
             if (PETgwrMax < 0.) PETgwrMax = 0.;
             double S;
@@ -1303,13 +1345,13 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
         const double loc_wetland = li.loc_wetland;
         if (loc_wetland > 0.) {  // local wetland, :2495-2617
             const double prev = li.loc_wetl_stor;
-            const double maxStorage = ((loc_wetland) / 100.) * cellArea * li.wetl_depth;
+            const double maxStorage = ((loc_wetland) / C100) * cellArea * li.wetl_depth;
             const double rf = li.red_loc_wetl;
             double evapo = ((1.0 - cfa) * owPrec * rf) + (cfa * (owPET * rf));
             if (evapo < 0.) evapo = 0.;
-            const double totalInflow = inflow + (owPrec * rf * (cellArea / 1000000.) * (loc_wetland / 100.));
-            if (aridc) gwr_locwet = 10. * rf * loc_wetland / 100. / (contf / 100.);
-            const double PETgwr = evapo * (cellArea / 1000000.) * (loc_wetland / 100.) + gwr_locwet * cellArea * (contf / 100.) / 1000000.;
+            const double totalInflow = inflow + (owPrec * rf * (cellArea / C1E6) * (loc_wetland / C100));
+            if (aridc) gwr_locwet = 10. * rf * loc_wetland / C100 / (contf / C100);
+            const double PETgwr = evapo * (cellArea / C1E6) * (loc_wetland / C100) + gwr_locwet * cellArea * (contf / C100) / C1E6;
             const double PETgwrMax = prev + totalInflow;
             double S;
             if (PETgwr > PETgwrMax) {
@@ -1342,7 +1384,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
         if (aridc && !(flags & (FL_LAKE | FL_RES | FL_GLOWET))) {
             const double gwr_swb = gwr_loclak + 0. + gwr_locwet + 0. + 0.;
             a.gwr_swb[i] = gwr_swb;
-            const double netGWin = gwr_swb * cellArea * (contf / 100.) / 1000000. + fx.gw_recharge * cellArea * (laf / 100.) / 1000000.;
+            const double netGWin = gwr_swb * cellArea * (contf / C100) / C1E6 + fx.gw_recharge * cellArea * (laf / C100) / C1E6;
             double Sg = li.gw;
             localGWRunoffIntoRiver = gw_step(Sg, netGWin, li.ekg, li.invkg);
             a.gw[i] = Sg;
@@ -1353,7 +1395,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
             g[GB_INVKS] = (1. / kS);
             g[GB_EKG] = li.ekg;
             g[GB_INVKG] = li.invkg;
-            g[GB_GWRECH] = fx.gw_recharge * cellArea * (laf / 100.) / 1000000.;
+            g[GB_GWRECH] = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
             g[GB_LOC_GWR_LAK] = gwr_loclak;
             g[GB_LOC_GWR_WET] = gwr_locwet;
             if (flags & FL_LAKE) {  // :2630-2676
@@ -1361,10 +1403,10 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 const double rf = a.red_glo_lake[i];
                 double evapo = ((1.0 - cfa) * owPrec) + (cfa * owPET * rf);
                 if (evapo < 0.) evapo = 0.;
-                const double gwr = aridc ? 10. * rf * (lake_area / (cellArea * (contf / 100.))) : 0.;
-                g[GB_L_PREC] = (owPrec * (lake_area / 1000000.));
+                const double gwr = aridc ? 10. * rf * (lake_area / (cellArea * (contf / C100))) : 0.;
+                g[GB_L_PREC] = (owPrec * (lake_area / C1E6));
                 g[GB_L_GWR] = gwr;
-                g[GB_L_PET] = evapo * (lake_area / 1000000.) + gwr * cellArea * (contf / 100.) / 1000000. + 0.;
+                g[GB_L_PET] = evapo * (lake_area / C1E6) + gwr * cellArea * (contf / C100) / C1E6 + 0.;
                 g[GB_L_MAX] = (lake_area)*li.lake_depth;
             }
             if (flags & FL_RES) {  // :2807-2870, 2960-2983
@@ -1374,10 +1416,10 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 const double rf = a.red_res[i];
                 double evapo = ((1.0 - cfa) * owPrec) + (cfa * (owPET * rf));
                 if (evapo < 0.) evapo = 0.;
-                const double gwr = aridc ? 10. * rf * (reservoir_area / (cellArea * (contf / 100.))) : 0.;
-                g[GB_R_PREC] = (owPrec * (reservoir_area / 1000000.));
+                const double gwr = aridc ? 10. * rf * (reservoir_area / (cellArea * (contf / C100))) : 0.;
+                g[GB_R_PREC] = (owPrec * (reservoir_area / C1E6));
                 g[GB_R_GWR] = gwr;
-                g[GB_R_PET] = evapo * (reservoir_area / 1000000.) + gwr * cellArea * (contf / 100.) / 1000000.;
+                g[GB_R_PET] = evapo * (reservoir_area / C1E6) + gwr * cellArea * (contf / C100) / C1E6;
                 g[GB_R_C] = stor_cap / (mean_outflow * 31536000. / 1000000000.);
                 g[GB_R_CAP] = stor_cap;
                 double prov_rel = 0.;
@@ -1397,17 +1439,17 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 const double rf = a.red_glo_wetl[i];
                 double evapo = ((1.0 - cfa) * (owPrec * rf)) + (cfa * (owPET * rf));
                 if (evapo < 0.) evapo = 0.;
-                const double gwr = aridc ? 10. * rf * glo_wetland / 100. / (contf / 100.) : 0.;
-                g[GB_W_PREC] = (owPrec * rf * (cellArea / 1000000.) * (glo_wetland / 100.));
+                const double gwr = aridc ? 10. * rf * glo_wetland / C100 / (contf / C100) : 0.;
+                g[GB_W_PREC] = (owPrec * rf * (cellArea / C1E6) * (glo_wetland / C100));
                 g[GB_W_GWR] = gwr;
-                g[GB_W_PET] = evapo * (cellArea / 1000000.) * ((glo_wetland) / 100.) + gwr * cellArea * (contf / 100.) / 1000000.;
-                g[GB_W_MAX] = ((glo_wetland) / 100.) * cellArea * li.wetl_depth;
+                g[GB_W_PET] = evapo * (cellArea / C1E6) * ((glo_wetland) / C100) + gwr * cellArea * (contf / C100) / C1E6;
+                g[GB_W_MAX] = ((glo_wetland) / C100) * cellArea * li.wetl_depth;
             }
         }
         // river evaporation and precipitation on yesterday's river area fraction (:3425-3441)
         const double raf = li.raf_next;
-        a.t_river_evapo[i] = ((1.0 - cfa) * (owPrec) + (cfa * owPET)) * raf / 100. * cellArea / 1000000.;
-        a.t_river_precip[i] = owPrec * raf / 100. * cellArea / 1000000.;
+        a.t_river_evapo[i] = ((1.0 - cfa) * (owPrec) + (cfa * owPET)) * raf / C100 * cellArea / C1E6;
+        a.t_river_precip[i] = owPrec * raf / C100 * cellArea / C1E6;
     }
     a.t_inflow_local[i] = inflow;
     a.t_runoff_to_river[i] = localRunoffIntoRiver;
@@ -1565,7 +1607,7 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
     if (flags & FL_ARIDC) {  // :3305-3386
         const double gwr_swb = g[GB_LOC_GWR_LAK] + gwr_glolak + g[GB_LOC_GWR_WET] + gwr_glowet + gwr_res;
         a.gwr_swb[i] = gwr_swb;
-        const double netGWin = gwr_swb * a.area[r] * (a.contfreq[r] / 100.) / 1000000. + g[GB_GWRECH];
+        const double netGWin = gwr_swb * a.area[r] * (a.contfreq[r] / C100) / C1E6 + g[GB_GWRECH];
         const double prev = a.gw[i];
         const double ekg = g[GB_EKG];
         double Sg = prev * ekg + g[GB_INVKG] * netGWin * (1. - ekg);
@@ -1723,10 +1765,10 @@ __device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r,
         const double river_length = a.river_length[r];
         const double bw = a.river_bottom_width[r];
         const double crossSectionalArea = Sr / river_length;
-        const double riverDepth = -bw / (4. * 1000.) + sqrt(bw / 1000. * bw / (16. * 1000.) + 0.5 * crossSectionalArea);
-        double width = bw / 1000. + 4. * riverDepth;
+        const double riverDepth = -bw / (4. * 1000.) + sqrt(bw / C1000 * bw / (16. * 1000.) + 0.5 * crossSectionalArea);
+        double width = bw / C1000 + 4. * riverDepth;
         const double wbf = a.river_width_bf[r];
-        if (width > wbf / 1000.) width = wbf / 1000.;
+        if (width > wbf / C1000) width = wbf / C1000;
         const double smaxr = a.river_storage_max[r];
         red_river = clamp01(1. - pow(fabs(Sr - smaxr) / smaxr, (a.p_evaredex[q] * 3.32193)));
         raf_next = red_river * river_length * width * 100. / cellArea;
@@ -1750,13 +1792,13 @@ __device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r,
         }
     }
     const double loc_lake = a.loc_lake[r], loc_wetland = a.loc_wetland[r];
-    double fLocLake = ((loc_lake > 0.) && (red_loc_lake > 0.)) ? (red_loc_lake * loc_lake / 100.) : 0.;
-    double fLocWet = ((loc_wetland > 0.) && (red_loc_wetl > 0.)) ? (red_loc_wetl * loc_wetland / 100.) : 0.;
-    double fGloWet = ((glo_wetland > 0.) && (red_glo_wetl > 0.)) ? (red_glo_wetl * glo_wetland / 100.) : 0.;
+    double fLocLake = ((loc_lake > 0.) && (red_loc_lake > 0.)) ? (red_loc_lake * loc_lake / C100) : 0.;
+    double fLocWet = ((loc_wetland > 0.) && (red_loc_wetl > 0.)) ? (red_loc_wetl * loc_wetland / C100) : 0.;
+    double fGloWet = ((glo_wetland > 0.) && (red_glo_wetl > 0.)) ? (red_glo_wetl * glo_wetland / C100) : 0.;
     const double fswb_old = a.fswb_laf_next[i];
     double fswb_next = fLocLake + fLocWet + fGloWet;
     const double fGloLake = a.f_glo_lake[r];
-    const double maxRiverAreaFrac = contf / 100. - fGloLake;
+    const double maxRiverAreaFrac = contf / C100 - fGloLake;
     if ((flags & (FL_LAKE | FL_RES)) && (fGloLake == 1.)) {
         raf_next = 0.;
         raf_change = 0.;
@@ -1769,11 +1811,11 @@ __device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r,
                 red_loc_lake *= fswbFracCorr;
                 red_loc_wetl *= fswbFracCorr;
                 red_glo_wetl *= fswbFracCorr;
-                if ((fLocLake > 0.) && (red_loc_lake > 0.)) fLocLake = (red_loc_lake * loc_lake / 100.);
+                if ((fLocLake > 0.) && (red_loc_lake > 0.)) fLocLake = (red_loc_lake * loc_lake / C100);
                 else { red_loc_lake = 0.; fLocLake = 0.; }
-                if ((fLocWet > 0.) && (red_loc_wetl > 0.)) fLocWet = (red_loc_wetl * loc_wetland / 100.);
+                if ((fLocWet > 0.) && (red_loc_wetl > 0.)) fLocWet = (red_loc_wetl * loc_wetland / C100);
                 else { red_loc_wetl = 0.; fLocWet = 0.; }
-                if ((fGloWet > 0.) && (red_glo_wetl > 0.)) fGloWet = (red_glo_wetl * glo_wetland / 100.);
+                if ((fGloWet > 0.) && (red_glo_wetl > 0.)) fGloWet = (red_glo_wetl * glo_wetland / C100);
                 else { red_glo_wetl = 0.; fGloWet = 0.; }
             }
         } else {
@@ -1842,21 +1884,26 @@ __host__ __device__ __forceinline__ int v_num_tiles(const int begin, const int e
 
 // warps 1-4: bring the per-cell inputs of the head, the tail and the local routing into shared memory
 // (cp.async for 4/8/16-byte items, plain loads for the 1/2-byte flags) while warp 0 is in v_mode
-__device__ __forceinline__ void v_preload(const WgkParams &p, VTile &sm, const int r0, const int begin, const int end, const int m,
+template <class C>
+__device__ __forceinline__ void v_preload(const WgkParams &p, VTile<C> &sm, const int r0, const int begin, const int end, const int m,
                                           const int slot, const int w, const int lane) {
     const WgkArrays &a = p.a;
     const int r = r0 + lane;
-    if (r < begin || r >= end) return;
+    if (!C::PRE || r < begin || r >= end) return;
     const size_t i = (size_t)m * p.stride + r;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    // four groups of copies, dealt round-robin to the warps 1 .. NW-1
+#pragma unroll
+    for (int task = 1; task <= 4; task++) {
+    if (1 + (task - 1) % (C::NW > 1 ? C::NW - 1 : 1) != w) continue;
 #define VP_D(slot_, src_) __pipeline_memcpy_async(&sm.pd[slot_][lane], &(src_), sizeof(double))
 #define VP_F(slot_, src_) __pipeline_memcpy_async(&sm.pf[slot_][lane], &(src_), sizeof(float))
-    if (w == 1) {
+    if (task == 1) {
         VP_D(LI_ekg, a.s_ekg[q]); VP_D(LI_invkg, a.s_invkg[q]); VP_D(LI_evaredex, a.p_evaredex[q]); VP_D(LI_area, a.area[r]); VP_D(LI_cfa, a.cfa[q]);
         VP_D(LI_contf, a.contfreq[r]); VP_D(LI_fswb_init, a.fswb_init[r]); VP_D(LI_loc_lake, a.loc_lake[r]);
         VP_D(LI_loc_wetland, a.loc_wetland[r]); VP_D(LI_kS, a.p_swoutf[q]); VP_D(LI_lake_depth, a.lake_depth_active[q]);
         VP_D(LI_wetl_depth, a.wetl_depth_active[q]);
-    } else if (w == 2) {
+    } else if (task == 2) {
         VP_D(LI_laf, a.land_area_frac[i]); VP_D(LI_laf_prev, a.land_area_frac_prev[i]); VP_D(LI_gw, a.gw[i]);
         VP_D(LI_loc_lake_stor, a.loc_lake_stor[i]); VP_D(LI_red_loc_lake, a.red_loc_lake[i]);
         VP_D(LI_loc_wetl_stor, a.loc_wetl_stor[i]); VP_D(LI_red_loc_wetl, a.red_loc_wetl[i]);
@@ -1864,7 +1911,7 @@ __device__ __forceinline__ void v_preload(const WgkParams &p, VTile &sm, const i
         sm.pk[K_contcell][lane] = a.contcell[r];
         sm.pk[K_flags][lane] = a.s_flags[r];
         sm.pk[K_ldd][lane] = a.ldd[r];
-    } else if (w == 3) {
+    } else if (task == 3) {
         __pipeline_memcpy_async(&sm.pforce[lane],
                                 &p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r],
                                 sizeof(float4));
@@ -1876,7 +1923,7 @@ __device__ __forceinline__ void v_preload(const WgkParams &p, VTile &sm, const i
         __pipeline_memcpy_async(&sm.pk[K_lai_status][lane], &a.lai_status[i], sizeof(int32_t));
         sm.pk[K_lc][lane] = a.landcover[r];
         sm.pk[K_arid][lane] = a.arid[r];
-    } else if (w == 4) {
+    } else if (task == 4) {
         VP_D(TI_soil, a.soil[i]); VP_D(TI_gamma, a.gamma_hbv[q]); VP_D(TI_pcrit, a.p_pcrit[q]);
         VP_F(TI_builtup, a.builtup[r]); VP_F(TI_smax, a.smax[q]); VP_F(TI_gwfactor, a.gwfactor[q]);
         sm.pk[K_texture][lane] = a.texture[r];
@@ -1884,11 +1931,13 @@ __device__ __forceinline__ void v_preload(const WgkParams &p, VTile &sm, const i
     }
 #undef VP_D
 #undef VP_F
+    }
     __pipeline_commit();
     __pipeline_wait_prior(0);
 }
 
-__device__ __forceinline__ LocalIn local_from_tile(const VTile &sm, const int lane) {
+template <class C>
+__device__ __forceinline__ LocalIn local_from_tile(const VTile<C> &sm, const int lane) {
     LocalIn li;
     li.contcell = sm.pk[K_contcell][lane];
     li.flags = sm.pk[K_flags][lane];
@@ -1918,11 +1967,11 @@ __device__ __forceinline__ LocalIn local_from_tile(const VTile &sm, const int la
 }
 
 // tail of the tile (warp 0): soil / runoff, then the local routing with the fluxes handed over in registers
-template <bool LOCAL>
-__device__ __forceinline__ void v_finish(const WgkParams &p, VTile &sm, const int r0, const int begin, const int end, const int m,
+template <class C, bool LOCAL>
+__device__ __forceinline__ void v_finish(const WgkParams &p, VTile<C> &sm, const int r0, const int begin, const int end, const int m,
                                          const int lane) {
     double flux[3] = {0., 0., 0.};
-    v_tail(p, sm, r0, m, lane, flux);
+    v_tail<C>(p, sm, r0, m, lane, flux);
     const int r = r0 + lane;
     if (LOCAL && r >= begin && r < end) {
         LocalFlux fx;
@@ -1935,54 +1984,74 @@ __device__ __forceinline__ void v_finish(const WgkParams &p, VTile &sm, const in
         } else {
             fx = local_flux_load(p, r, m);  // cells outside the computed region keep their last fluxes
         }
-        local_compute(p, r, m, local_from_tile(sm, lane), fx);
+        local_compute(p, r, m, C::PRE ? local_from_tile<C>(sm, lane) : local_load(p, r, m), fx);
     }
 }
 
-template <bool LOCAL>
-__device__ __forceinline__ void vertical_tile(const WgkParams &p, VTile &sm, const int begin, const int end, const int m, const int dayofs) {
+#ifdef WGK_PHASE_TIMING  // development aid: SM-clock cycles per phase of the tile kernels, summed over tiles
+__device__ unsigned long long g_phase[8];
+#define WGK_TICK(k_) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase[k_], (unsigned long long)(t_ - tick_)); tick_ = t_; } } while (0)
+#define WGK_TICK0() long long tick_ = clock64()
+#else
+#define WGK_TICK(k_) do { } while (0)
+#define WGK_TICK0() do { } while (0)
+#endif
+
+template <class C, bool LOCAL>
+__device__ __forceinline__ void vertical_tile(const WgkParams &p, VTile<C> &sm, const int begin, const int end, const int m, const int dayofs) {
     const int slot = p.cal_days[4 * dayofs + 3];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = (begin & ~3) + 32 * blockIdx.x;
-    VThread ts;
-    if (w == 0) v_mode(p, sm, r0, begin, end, m, slot, lane);
-    else v_preload(p, sm, r0, begin, end, m, slot, w, lane);
+    VThread<C> ts;
+    WGK_TICK0();
+    if (w == 0) v_mode<C>(p, sm, r0, begin, end, m, slot, lane);
+    else v_preload<C>(p, sm, r0, begin, end, m, slot, w, lane);
     __syncthreads();
+    WGK_TICK(0);
     const bool bands = sm.nband_cells != 0;  // else nothing but bare / inactive cells: the band arrays are not touched
     if (!bands && w != 0) return;
-    if (bands) v_prefetch(p, sm, ts, r0, m, 0, w, lane);
-    if (w == 0) v_head(p, sm, r0, m, slot, lane);
+    if (bands) v_prefetch<C>(p, sm, ts, r0, m, 0, w, lane);
+    if (w == 0) v_head<C>(p, sm, r0, m, slot, lane);
+    WGK_TICK(1);
     if (bands) {
         __syncthreads();
 #pragma unroll 1
-        for (int slab = 0; slab < V_NSLAB; slab++) {
-            v_scale(p, sm, ts, r0, m, slab, w, lane);
+        for (int slab = 0; slab < C::NSLAB; slab++) {
+            v_scale<C>(p, sm, ts, r0, m, slab, w, lane);
             __syncthreads();
             if (sm.cap_any[slab]) {
-                v_cap_resolve(sm, ts, slab, w, lane);
+                v_cap_resolve<C>(sm, ts, slab, w, lane);
                 __syncthreads();
             }
-            v_band(p, sm, ts, r0, m, slab, w, lane);
+            v_band<C>(p, sm, ts, r0, m, slab, w, lane);
             __syncthreads();
-            if (w < 4) v_sum(sm, ts, slab, w, lane);
+            if (w < 4) v_sum<C>(sm, ts, slab, w, lane);
         }
         __syncthreads();
+        WGK_TICK(2);
         if (w != 0) return;
     } else {
-        v_bare_sums(p, sm, r0, lane);
+        v_bare_sums<C>(p, sm, r0, lane);
+        WGK_TICK(3);
     }
-    v_finish<LOCAL>(p, sm, r0, begin, end, m, lane);
+    v_finish<C, LOCAL>(p, sm, r0, begin, end, m, lane);
+    WGK_TICK(4);
+#ifdef WGK_PHASE_TIMING
+    if (threadIdx.x == 0) atomicAdd(&g_phase[bands ? 6 : 7], 1ull);
+#endif
 }
 
-__global__ void __launch_bounds__(V_THREADS, 6) k_cells_pre(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
-    __shared__ VTile sm;
-    vertical_tile<true>(p, sm, begin, end, blockIdx.y, dayofs);
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::NW == 5 ? 6 : 12) k_cells_pre(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
+    __shared__ VTile<C> sm;
+    vertical_tile<C, true>(p, sm, begin, end, blockIdx.y, dayofs);
 }
 
 // the vertical balance alone over the whole grid (wgk_vertical_day, wgk_profile_day)
-__global__ void __launch_bounds__(V_THREADS, 6) k_vertical(const __grid_constant__ WgkParams p, const int dayofs) {
-    __shared__ VTile sm;
-    vertical_tile<false>(p, sm, 0, p.ncell, blockIdx.y, dayofs);
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::NW == 5 ? 6 : 12) k_vertical(const __grid_constant__ WgkParams p, const int dayofs) {
+    __shared__ VTile<C> sm;
+    vertical_tile<C, false>(p, sm, 0, p.ncell, blockIdx.y, dayofs);
 }
 
 // thread-per-cell forms of k_vertical and k_cells_pre
@@ -2064,7 +2133,7 @@ __global__ void __launch_bounds__(256) k_total_storage(const __grid_constant__ W
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.ncell; r += gridDim.x * blockDim.x) {
         const size_t i = (size_t)m * p.stride + r;
         const double laf = (0 == a.status_laf_next[i]) ? a.land_area_frac[i] : a.land_area_frac_next[i];
-        const double land = (a.canopy[i] + a.snow[i] + a.soil[i]) * a.area[r] / 1000000. * laf / 100.;
+        const double land = (a.canopy[i] + a.snow[i] + a.soil[i]) * a.area[r] / C1E6 * laf / C100;
         s += land + a.gw[i] + a.loc_lake_stor[i] + a.loc_wetl_stor[i] + a.glo_lake_stor[i] + a.glo_wetl_stor[i]
              + a.res_stor[i] + a.river_stor[i];
     }
