@@ -101,14 +101,16 @@ def make_model(w, ini, members, device):
     return m
 
 
-def upload_year(m, forcing):
-    m.forcing_reserve(365)
-    slot = 0
+def upload_year(m, forcing, slot0=0, reserve=True):
+    if reserve:
+        m.forcing_reserve(730)  # two years of slots: the e2e loop uploads one year while the other is stepped
+    slot = slot0
     for mon in range(12):
         f = forcing[mon]
         m.set_forcing(slot, NDAYS[mon], f["P"], f["T"], f["SW"], f["LW"])
         slot += NDAYS[mon]
-    m.synchronize()
+    if reserve:
+        m.synchronize()
 
 
 def run_wgk(args):
@@ -197,24 +199,29 @@ def run_wgk(args):
     out_host = torch.empty(w.ng, dtype=torch.float64).pin_memory().numpy()
     e2e_steps = max(1, min(args.steps, 5))
 
-    def e2e_year():
-        slot = 0
+    def upload(year):  # the year's 12 x 4 grids from pinned host memory into the slots of its parity (asynchronous)
+        slot = 365 * (year % 2)
         for mon in range(12):
             f = pinned[mon]
             m.set_forcing(slot, NDAYS[mon], f["P"].numpy(), f["T"].numpy(), f["SW"].numpy(), f["LW"].numpy())
             slot += NDAYS[mon]
-        m.step_days(1, 0, 1, 0, 365)
+
+    def e2e_year(year):
+        m.step_days(1, 0, 1, 365 * (year % 2), 365)
+        upload(year + 1)  # copy + pack of the next year overlap this year's stepping (own stream, event-ordered)
         res = []
         for mem in range(args.members):
             out_host[:] = m.get("discharge", mem)
             res.append(m.get_record(365, mem))
         return res
 
-    e2e_year()  # warm-up (graph re-instantiation after record_cells)
+    upload(0)
+    e2e_year(0)  # warm-up (graph re-instantiation after record_cells)
+    m.synchronize()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_year()
+    for y in range(1, e2e_steps + 1):
+        e2e_year(y)
     m.synchronize()
     barrier()
     dt = time.perf_counter() - t0
@@ -225,7 +232,8 @@ def run_wgk(args):
     h2d = sum(4 * w.ng * 31 * 4 for _ in range(12))
     d2h = (w.ng * 8 + 365 * len(stations) * 8) * args.members
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "steps": e2e_steps, "timing": "host wall clock around the API calls, max over ranks"}
+           "steps": e2e_steps, "timing": "host wall clock around the API calls, max over ranks; every step copies one year of "
+           "forcing from pinned host memory (for the following year, on the library's copy stream) and reads the results back"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -206,7 +206,7 @@ void emu_day(Emu *e, int day, int month, int dom, int slot, int tail_level0) {
 // spread over 600 binades, plus neighbours of powers of two and of multiples of c) whose quotient differs
 // from the IEEE division
 long emu_test_constdiv(long n, unsigned long long seed) {
-    const wgk::ConstDiv cs[4] = {wgk::C100, wgk::C1E6, wgk::C1000, wgk::C30};
+    const wgk::ConstDiv cs[5] = {wgk::C100, wgk::C1E6, wgk::C1000, wgk::C30, wgk::C86400};
     long bad = 0;
     unsigned long long x = seed ? seed : 88172645463325252ull;
     for (long k = 0; k < n; k++) {

@@ -217,6 +217,39 @@ def test_cell_class_order_does_not_change_results(world3000):
         assert np.array_equal(out[0][k], out[1][k]), k
 
 
+def test_basin_shards_equal_full_grid(world3000):
+    """BASELINE config 5 at test size: the grid split into two shards of whole drainage basins, each run as
+    its own context (as on two GPUs), gives BIT-identical results to the single full-grid run."""
+    from oracle import synth_world as sw, wg_init, wgo
+    import watergap2_b200 as wg
+    from watergap2_b200.ensemble import shard_by_basin, subgrid_inputs
+    w = world3000
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    ro, dc = np.asarray(topo["rout_order"]), np.asarray(topo["outflow_cell"])
+    f = sw.forcing_month(w, 1901, 1)
+    names = wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS
+
+    def run(fields, ro, dc, forcing):
+        m = wg.Model(ro.size)
+        m.set_topology(ro, dc, cell_class=wg.cell_classes(fields))
+        m.load(fields)
+        m.forcing_reserve(31)
+        m.set_forcing(0, 31, forcing["P"], forcing["T"], forcing["SW"], forcing["LW"])
+        m.step_days(1, 0, 1, 0, 15)
+        return {k: m.get(k) for k in names}
+
+    full = run(ini, ro, dc, f)
+    rank = shard_by_basin(wgo.rout_prepare(w.flowdir, w.row, w.col, w.gcrc.T)["basins2"], 2)
+    for r in range(2):
+        cells = np.nonzero(rank == r)[0]
+        sub, sro, sdc = subgrid_inputs(ini, ro, dc, cells)
+        got = run(sub, sro, sdc, {k: v[cells] for k, v in f.items()})
+        for k in names:
+            ref = full[k].reshape(w.ng, -1)[cells].ravel()
+            assert np.array_equal(ref, got[k]), (r, k)
+
+
 def test_members_and_parameter_sets(world3000):
     """two members with different per-cell parameter sets advance independently and each
     matches its own oracle run (calibration sweep layout, BASELINE config 3)."""

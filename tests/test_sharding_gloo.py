@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from watergap2_b200.ensemble import ensemble_mean_var, shard_by_basin, shard_members
+from watergap2_b200.ensemble import ensemble_mean_var, shard_by_basin, shard_members, subgrid_inputs
 
 
 def test_shard_members_partition():
@@ -35,6 +35,36 @@ def test_shard_by_basin_keeps_basins_whole(world3000, oracle_lib):
     assert (rank[has] == rank[down[has] - 1]).all()  # water never crosses a rank boundary
     load = np.bincount(rank, minlength=4)
     assert load.max() <= 1.3 * load.mean() + np.bincount(b[b > 0]).max()
+
+
+def test_subgrid_inputs_keep_order_and_levels(world3000, oracle_lib):
+    """basin shards as stand-alone grids: ranks stay level-major, relative order and levels unchanged"""
+    from oracle import wg_init
+    w = world3000
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    rank = shard_by_basin(oracle_lib.rout_prepare(w.flowdir, w.row, w.col, w.gcrc.T)["basins2"], 2)
+    ro, dc = np.asarray(topo["rout_order"]), np.asarray(topo["outflow_cell"])
+    def levels(ro, dc):
+        lvl = np.zeros(ro.size, int)
+        for n in np.argsort(ro):
+            if dc[n] > 0:
+                lvl[dc[n] - 1] = max(lvl[dc[n] - 1], lvl[n] + 1)
+        return lvl
+    full = levels(ro, dc)
+    seen = 0
+    for r in range(2):
+        cells = np.nonzero(rank == r)[0]
+        f, sro, sdc = subgrid_inputs(ini, ro, dc, cells)
+        assert sorted(sro.tolist()) == list(range(1, cells.size + 1))
+        assert (np.argsort(sro) == np.argsort(ro[cells])).all()
+        assert np.array_equal(levels(sro, sdc), full[cells])
+        assert f["area"].shape[0] == cells.size and f["params"].shape == (26, cells.size)
+        assert np.asarray(f["snow_bands"]).size == cells.size * 101 and np.asarray(f["lct_ddf"]).size == 18
+        seen += cells.size
+    assert seen == w.ng
+    with pytest.raises(ValueError):
+        subgrid_inputs(ini, ro, dc, np.nonzero(dc > 0)[0][:5])  # cells cut out of their basins
 
 
 def _worker(rank, world, port, total, n, out):

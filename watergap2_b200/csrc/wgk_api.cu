@@ -76,6 +76,14 @@ struct wgk_ctx {
     float4 *d_forcing = nullptr;
     int forcing_nslots = 0, forcing_per_member = 0;
     float *d_fstage = nullptr;  // 4 staging grids [ncell][stride]
+    // forcing uploads run on their own stream, so that the host->device copy and the pack of the next
+    // period overlap the stepping of the current one; ordering against the steps is by events:
+    // a step waits for the uploads issued before it, an upload waits for the steps that still read its slots
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_forcing = nullptr;
+    bool forcing_pending = false;
+    struct SlotUse { int lo, n; cudaEvent_t ev; };
+    std::vector<SlotUse> slot_uses;
     size_t fstage_elems = 0;
 
     // record
@@ -422,6 +430,8 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     }
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_forcing, cudaEventDisableTiming));
     // the tile kernels keep up to 36 KB per CTA in shared memory: ask for the largest carve-out
     for (const void *fn : {(const void *)wgk::k_cells_pre<wgk::VCfgSmall>, (const void *)wgk::k_cells_pre<wgk::VCfgMid>,
                            (const void *)wgk::k_vertical<wgk::VCfgSmall>, (const void *)wgk::k_vertical<wgk::VCfgMid>,
@@ -456,6 +466,9 @@ void wgk_destroy(wgk_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (auto &u : c->slot_uses) cudaEventDestroy(u.ev);
+    if (c->ev_forcing) cudaEventDestroy(c->ev_forcing);
     drop_graph(c);
     for (void *d : c->allocs) cudaFree(d);
     cudaFree(c->d_cell_of_rank); cudaFree(c->d_up_off); cudaFree(c->d_up_idx); cudaFree(c->d_down);
@@ -471,6 +484,7 @@ const char *wgk_last_error(const wgk_ctx *c) { return c ? c->err.c_str() : "null
 
 int wgk_synchronize(wgk_ctx *c) {
     if (!c) return WGK_ERR_ARG;
+    CU(cudaStreamSynchronize(c->copy_stream));
     CU(cudaStreamSynchronize(c->stream));
     return WGK_OK;
 }
@@ -746,6 +760,7 @@ void *wgk_device_ptr(wgk_ctx *c, int f, int member) {
 int wgk_forcing_reserve(wgk_ctx *c, int nslots, int per_member) {
     if (!c || nslots <= 0) return WGK_ERR_ARG;
     CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
     CU(cudaStreamSynchronize(c->stream));
     if (c->d_forcing) cudaFree(c->d_forcing);
     c->d_forcing = nullptr;
@@ -779,24 +794,58 @@ int wgk_set_forcing(wgk_ctx *c, int slot0, int ndays, int member, const float *p
         CU(cudaMalloc(&c->d_fstage, 4 * elems * sizeof(float)));
         c->fstage_elems = elems;
     }
+    // wait for the steps that still read these slots (and drop the records of finished steps)
+    for (size_t k = 0; k < c->slot_uses.size();) {
+        wgk_ctx::SlotUse &u = c->slot_uses[k];
+        if (cudaEventQuery(u.ev) == cudaSuccess) {
+            cudaEventDestroy(u.ev);
+            c->slot_uses.erase(c->slot_uses.begin() + k);
+            continue;
+        }
+        if (u.lo < slot0 + ndays && slot0 < u.lo + u.n) CU(cudaStreamWaitEvent(c->copy_stream, u.ev, 0));
+        k++;
+    }
     float *dP = c->d_fstage, *dT = dP + elems, *dS = dT + elems, *dL = dS + elems;
-    CU(cudaMemcpyAsync(dP, prec, elems * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(dT, temp, elems * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(dS, sw, elems * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(dL, lw, elems * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    cudaStream_t cs = c->copy_stream;
+    CU(cudaMemcpyAsync(dP, prec, elems * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(dT, temp, elems * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(dS, sw, elems * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(dL, lw, elems * sizeof(float), cudaMemcpyHostToDevice, cs));
     const int F = c->forcing_per_member ? c->nmember : 1;
     const size_t pitch = (size_t)F * c->stride;
     float4 *dst = c->d_forcing + (size_t)slot0 * pitch + (size_t)(c->forcing_per_member ? member : 0) * c->stride;
     dim3 block(128), grid((c->ncell + 127) / 128, std::min(ndays, 31));
-    wgk::k_forcing_pack<<<grid, block, 0, c->stream>>>(dst, dP, dT, dS, dL, c->d_cell_of_rank, c->ncell, c->stride, ndays, stride, pitch);
+    wgk::k_forcing_pack<<<grid, block, 0, cs>>>(dst, dP, dT, dS, dL, c->d_cell_of_rank, c->ncell, c->stride, ndays, stride, pitch);
     c->launches++;
     CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_forcing, cs));
+    c->forcing_pending = true;
     return WGK_OK;
 }
 
 // ---------------------------------------------------------------------------------------
 // hot path
 // ---------------------------------------------------------------------------------------
+// a step is ordered after every forcing upload issued before it ...
+static int forcing_before_step(wgk_ctx *c) {
+    if (c->forcing_pending) {
+        CU(cudaStreamWaitEvent(c->stream, c->ev_forcing, 0));
+        c->forcing_pending = false;
+    }
+    return WGK_OK;
+}
+// ... and remembers which slots it reads until it has finished
+static int forcing_after_step(wgk_ctx *c, int slot0, int ndays) {
+    wgk_ctx::SlotUse u;
+    u.lo = slot0;
+    u.n = ndays;
+    if (slot0 + ndays > c->forcing_nslots) { u.lo = 0; u.n = c->forcing_nslots; }  // the slots wrap around
+    CU(cudaEventCreateWithFlags(&u.ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(u.ev, c->stream));
+    c->slot_uses.push_back(u);
+    return WGK_OK;
+}
+
 static int fill_calendar(wgk_ctx *c, int day, int month, int dom, int slot, int ndays) {
     if (day < 1 || day > 365 || month < 0 || month > 11 || dom < 1 || dom > 31) return fail(c, WGK_ERR_ARG, "bad date day=%d month=%d day_in_month=%d", day, month, dom);
     if (slot < 0 || slot >= c->forcing_nslots) return fail(c, WGK_ERR_ARG, "forcing slot %d not reserved", slot);
@@ -821,9 +870,11 @@ int wgk_vertical_day(wgk_ctx *c, int day, int month, int dom, int slot) {
     if (rc) return rc;
     rc = ensure_derived(c);
     if (rc) return rc;
+    rc = forcing_before_step(c);
+    if (rc) return rc;
     c->launches += enqueue_vertical(c, make_params(c), 0);
     CU(cudaGetLastError());
-    return WGK_OK;
+    return forcing_after_step(c, slot, 1);
 }
 
 int wgk_routing_day(wgk_ctx *c, int day, int month, int dom) {
@@ -855,6 +906,8 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
     if (rc) return rc;
     rc = ensure_derived(c);
     if (rc) return rc;
+    rc = forcing_before_step(c);
+    if (rc) return rc;
     const WgkParams p = make_params(c);
     if (c->opt.use_graph) {
         auto it = c->graphs.find(ndays);
@@ -873,7 +926,9 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
         c->launches += enqueue_wavefront_serial(c, p, ndays);
     }
     CU(cudaGetLastError());
-    return publish_discharge(c, ndays - 1);
+    rc = publish_discharge(c, ndays - 1);
+    if (rc) return rc;
+    return forcing_after_step(c, slot0, ndays);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -942,6 +997,8 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     rc = fill_calendar(c, day, month, dom, slot, 1);
     if (rc) return rc;
     rc = ensure_derived(c);
+    if (rc) return rc;
+    rc = forcing_before_step(c);
     if (rc) return rc;
     cudaEvent_t ev[6];
     for (auto &e : ev) CU(cudaEventCreate(&e));

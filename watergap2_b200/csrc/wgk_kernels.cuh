@@ -68,7 +68,8 @@ __device__ __forceinline__ double operator/(const double x, const ConstDiv d) {
     const double q = x * d.rc;
     return fma(fma(-d.c, q, x), d.rc, q);
 }
-constexpr ConstDiv C100{100., 0.01}, C1E6{1000000., 1e-6}, C1000{1000., 0.001}, C30{30., 1. / 30.};
+constexpr ConstDiv C100{100., 0.01}, C1E6{1000000., 1e-6}, C1000{1000., 0.001}, C30{30., 1. / 30.},
+                   C86400{86400., 1. / 86400.};
 
 // Shared-memory staging of the 100 snow bands of a cell: the band columns of the CTA's 128
 // cells are brought in by cp.async (LDGSTS) in chunks of SNOW_CH bands, double buffered, so
@@ -1641,7 +1642,7 @@ __device__ __forceinline__ void route_river(const WgkParams &p, const RiverCtx &
     }
     // routingClass::getRiverVelocity (routing.cpp:7274-7307); pow(x, 2/3) is evaluated as
     // cbrt(x*x): same value to ~1 ulp with a much shorter dependent chain
-    const double incoming_discharge = (riverInflow * 1000. * 1000. * 1000.) / (60. * 60. * 24.);
+    const double incoming_discharge = (riverInflow * 1000. * 1000. * 1000.) / C86400;  // (60. * 60. * 24.)
     const double riverDepth = 0.349 * pow(incoming_discharge, 0.341);
     const double crossSectionalArea = riverDepth * (2.0 * riverDepth + c.bw);
     const double wettedPerimeter = c.bw + 2.0 * riverDepth * sqrt(5.0);

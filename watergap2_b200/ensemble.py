@@ -43,6 +43,39 @@ def shard_by_basin(basin_of_cell, world_size):
     return out
 
 
+def subgrid_inputs(fields, rout_order, downstream_cell, cells, ncell_table=18):
+    """Inputs of a model context that holds only `cells` (0-based indices of WHOLE drainage basins, e.g. the
+    cells shard_by_basin gave to one rank): per-cell fields are cut, the routing ranks are renumbered
+    1..len(cells) in unchanged relative order (so the dependency levels and the order of every upstream sum
+    stay those of the full grid and the shard's results are bit-identical to the full run's), downstream
+    cell numbers are translated.  -> (fields, rout_order, downstream_cell) of the shard."""
+    cells = np.asarray(cells, np.int64)
+    ro = np.asarray(rout_order)
+    dc = np.asarray(downstream_cell)
+    ng = ro.size
+    new_of_old = np.zeros(ng + 1, np.int64)  # 1-based old cell number -> 1-based new, 0 = outside / none
+    new_of_old[cells + 1] = np.arange(1, cells.size + 1)
+    sub_dc = new_of_old[dc[cells]]
+    if ((dc[cells] > 0) & (sub_dc == 0)).any():
+        raise ValueError("cells do not form whole drainage basins: a downstream cell lies outside the shard")
+    sub_ro = np.empty(cells.size, np.int32)
+    sub_ro[np.argsort(ro[cells], kind="stable")] = np.arange(1, cells.size + 1)
+    out = {}
+    for k, v in fields.items():
+        if k.startswith("_"):
+            continue
+        a = np.asarray(v)
+        if a.ndim >= 1 and a.shape[0] == ng:
+            out[k] = a[cells]
+        elif a.ndim == 2 and a.shape[1] == ng:  # params [26][ncell]
+            out[k] = a[:, cells]
+        elif a.ndim == 1 and a.size % ng == 0 and a.size != ncell_table and a.size > ng:  # flattened [ncell][bands]
+            out[k] = a.reshape(ng, -1)[cells].ravel()
+        else:
+            out[k] = a  # land-cover tables, scalars
+    return out, sub_ro, sub_dc.astype(np.int32)
+
+
 class _CudaArray:
     """zero-copy view of a wgk device buffer for torch.as_tensor (CUDA array interface v2)"""
 
