@@ -170,41 +170,118 @@ __device__ __forceinline__ double lai_nogrowing(int &days, int initialDays, int 
     }
 }
 
+// inputs of the cell-parallel routing pre-pass that are known before today's vertical step (statics,
+// parameters, yesterday's state): the band-parallel kernel loads them at its very start, in a warp of
+// its own, so that no global-memory latency is left between the vertical step and the local routing
+struct LocalIn {
+    double ekg, invkg, evaredex, area, cfa, contf, fswb_init, loc_lake, loc_wetland, kS, lake_depth, wetl_depth;
+    double laf, laf_prev, gw, loc_lake_stor, red_loc_lake, loc_wetl_stor, red_loc_wetl, raf_next;
+    int contcell, flags, ldd, arid;
+};
+// today's fluxes of the vertical step (daily.h G_openWaterPrec ... G_dailyStorageTransfer)
+struct LocalFlux {
+    double owPrec, owPET, storage_transfer, surface_runoff, gw_recharge;
+};
+
+__device__ __forceinline__ LocalIn local_load(const WgkParams &p, const int r, const int m) {
+    const WgkArrays &a = p.a;
+    const size_t i = (size_t)m * p.stride + r;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    LocalIn li;
+    li.contcell = a.contcell[r];
+    li.flags = a.s_flags[r];
+    li.ldd = a.ldd[r];
+    li.arid = a.arid[r];
+    li.ekg = a.s_ekg[q];
+    li.invkg = a.s_invkg[q];
+    li.evaredex = a.p_evaredex[q];
+    li.area = a.area[r];
+    li.cfa = a.cfa[q];
+    li.contf = a.contfreq[r];
+    li.fswb_init = a.fswb_init[r];
+    li.loc_lake = a.loc_lake[r];
+    li.loc_wetland = a.loc_wetland[r];
+    li.kS = a.p_swoutf[q];
+    li.lake_depth = a.lake_depth_active[q];
+    li.wetl_depth = a.wetl_depth_active[q];
+    li.laf = a.land_area_frac[i];
+    li.laf_prev = a.land_area_frac_prev[i];
+    li.gw = a.gw[i];
+    li.loc_lake_stor = a.loc_lake_stor[i];
+    li.red_loc_lake = a.red_loc_lake[i];
+    li.loc_wetl_stor = a.loc_wetl_stor[i];
+    li.red_loc_wetl = a.red_loc_wetl[i];
+    li.raf_next = a.river_area_frac_next[i];
+    return li;
+}
+
+__device__ __forceinline__ LocalFlux local_flux_load(const WgkParams &p, const int r, const int m) {
+    const WgkArrays &a = p.a;
+    const size_t i = (size_t)m * p.stride + r;
+    LocalFlux fx;
+    fx.owPrec = a.openwater_prec[i];
+    fx.owPET = a.openwater_pet[i];
+    fx.storage_transfer = a.storage_transfer[i];
+    fx.surface_runoff = a.surface_runoff[i];
+    fx.gw_recharge = a.gw_recharge[i];
+    return fx;
+}
+
 // ----------------------------------------------------------------------------------------
 // vertical water balance, one thread per cell (throughput form, used when members x cells fill the GPU)
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, const int m, const int slot, SnowStage *st) {
+// -> true when the cell was computed; then *li (if given) holds the inputs of the local routing, loaded together
+// with those of the soil part, and *fx today's fluxes (otherwise the caller reads both from global memory)
+__device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, const int m, const int slot, SnowStage *st,
+                                              LocalIn *li = nullptr, LocalFlux *fx = nullptr) {
     const WgkArrays &a = p.a;
-    if (!a.contcell[r]) return;  // integrateWGHM.cpp:772
     const size_t i = (size_t)m * p.stride + r;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
     const int tid = threadIdx.x;
     double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r + p.stride;
     const int32_t *__restrict__ E = a.s_elev32 + r + p.stride;
 
-    // daily.cpp:159-169, routing.h:246-251
-    const int started = a.status_laf_next[i];
-    const double landAreaFrac = (0 == started) ? a.land_area_frac[i] : a.land_area_frac_next[i];
-    double lafPrev;
-    if (1 == started) lafPrev = a.land_area_frac_prev[i];
-    else if (p.restart == 1) lafPrev = a.land_area_frac_prev[i];
-    else lafPrev = landAreaFrac;
-
-    if (1 != a.toBeCalculated[r]) return;  // daily.cpp:177
-
+    // Every input of the head is loaded here, unconditionally and before the first store: one memory round
+    // trip instead of one per use (the compiler may not move a load above a store or an early return).
+    const int in_contcell = a.contcell[r], in_tbc = a.toBeCalculated[r], started = a.status_laf_next[i];
+    const double in_laf = a.land_area_frac[i], in_laf_next = a.land_area_frac_next[i], in_laf_prev = a.land_area_frac_prev[i];
     const float4 f = p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r];
     const int lc = a.landcover[r] - 1;
     const double P_T_SNOWFZ = a.p_snowfz[q];
     const double P_T_SNOWMT = a.p_snowmt[q];
     const double P_T_GRADNT = a.p_gradnt[q];
-    const double ddf = a.p_degday[q] * a.lct_ddf[lc];  // (M_DEGDAY_F * ddf_lct) * (...) keeps the reference association
+    const double in_degday = a.p_degday[q];
+    const int in_snowfree = a.s_snowfree[i], in_de_max = a.s_de_max[r], in_de_min = a.s_de_min[r];
+    const double in_p_prec = a.p_prec[q], in_ptc_ari = a.p_ptc_ari[q], in_ptc_hum = a.p_ptc_hum[q], in_pet_mxdy = a.p_pet_mxdy[q];
+    const int in_arid = a.arid[r];
+    const float in_laimax = a.laimax[q];
+    const int in_lai_days = a.lai_days[i], in_lai_status = a.lai_status[i];
+    const double in_lai_precsum = a.lai_precsum[i], in_snow = a.snow[i], in_netrad = a.p_netrad[q], in_cfa = a.cfa[q];
+    const double in_canopy = a.canopy[i], in_mcwh = a.p_mcwh[q];
+    const int elev0 = a.s_elev32[r];
+    if (!in_contcell) return false;  // integrateWGHM.cpp:772
+
+    // daily.cpp:159-169, routing.h:246-251
+    const double landAreaFrac = (0 == started) ? in_laf : in_laf_next;
+    double lafPrev;
+    if (1 == started) lafPrev = in_laf_prev;
+    else if (p.restart == 1) lafPrev = in_laf_prev;
+    else lafPrev = landAreaFrac;
+
+    if (1 != in_tbc) return false;  // daily.cpp:177
+
+    // second round: the land-cover tables (18 entries each, cache resident)
+    const double ddf = in_degday * a.lct_ddf[lc];  // (M_DEGDAY_F * ddf_lct) * (...) keeps the reference association
+    const float in_fa = a.lai_factor_a[lc], in_fb = a.lai_factor_b[lc];
+    const int in_initial_days = a.lai_initial_days[lc];
+    const double in_kc_min = a.lai_kc_min[lc], in_kc_max = a.lai_kc_max[lc], in_albedo_snow = a.lct_albedo_snow[lc], in_emissivity = a.lct_emissivity[lc];
     const bool noland = (landAreaFrac <= 0.);
     // cells without snow whose lowest and highest band are above the freezing threshold take no part
     // in the band loop (see the note on the band-parallel form below); the band columns of the others
     // start streaming now (bands 1..100; band 0 is the unused mean slot)
     bool bare = false;
-    if (a.s_snowfree[i]) {
-        const double t_top = (double)f.y - ((double)a.s_de_max[r] * P_T_GRADNT), t_bot = (double)f.y - ((double)a.s_de_min[r] * P_T_GRADNT);
+    if (in_snowfree) {
+        const double t_top = (double)f.y - ((double)in_de_max * P_T_GRADNT), t_bot = (double)f.y - ((double)in_de_min * P_T_GRADNT);
         bare = noland || (ddf >= 0. && t_top > P_T_SNOWFZ && t_bot > P_T_SNOWFZ);
     }
     if (!bare) {
@@ -217,37 +294,37 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
     const double dailyShortWave = (double)f.z;
     const double dailyLongWave = (double)f.w;
 
-    dailyPrec = a.p_prec[q] * dailyPrec;  // :248
+    dailyPrec = in_p_prec * dailyPrec;  // :248
     const double temp2 = dailyTempC + 237.3;
     const double e_s = 0.6108 * exp(17.27 * dailyTempC / temp2);
 
     // arid / humid (:331-348); any other index value is rejected on upload
-    const bool arid_gw = (a.arid[r] == 1);
-    const double alpha = arid_gw ? a.p_ptc_ari[q] : a.p_ptc_hum[q];
-    const double maxDailyPET = a.p_pet_mxdy[q];
+    const bool arid_gw = (in_arid == 1);
+    const double alpha = arid_gw ? in_ptc_ari : in_ptc_hum;
+    const double maxDailyPET = in_pet_mxdy;
 
     // LAI / Kc (:355-356); LAImin in float arithmetic as in lai.cpp:154
-    const float laimax_f = a.laimax[q];
-    const float LAImin_f = __fadd_rn(a.lai_factor_a[lc], __fmul_rn(a.lai_factor_b[lc], laimax_f));
+    const float laimax_f = in_laimax;
+    const float LAImin_f = __fadd_rn(in_fa, __fmul_rn(in_fb, laimax_f));
     const double LAImin = (double)LAImin_f;
     const double LAImaxd = (double)laimax_f;
-    int days = a.lai_days[i], status = a.lai_status[i];
-    double precsum = a.lai_precsum[i];
+    int days = in_lai_days, status = in_lai_status;
+    double precsum = in_lai_precsum;
     double dailyLai;
     if (dailyTempC > 8.)
-        dailyLai = lai_growing(days, a.lai_initial_days[lc], status, lc + 1, arid_gw, LAImin, LAImaxd, precsum, dailyPrec);
+        dailyLai = lai_growing(days, in_initial_days, status, lc + 1, arid_gw, LAImin, LAImaxd, precsum, dailyPrec);
     else
-        dailyLai = lai_nogrowing(days, a.lai_initial_days[lc], status, LAImin, LAImaxd, precsum, dailyPrec);
+        dailyLai = lai_nogrowing(days, in_initial_days, status, LAImin, LAImaxd, precsum, dailyPrec);
     a.lai_days[i] = days;
     a.lai_status[i] = status;
     a.lai_precsum[i] = precsum;
     double dailyKc;
-    if ((LAImaxd - LAImin) == 0.) dailyKc = a.lai_kc_min[lc];
-    else dailyKc = a.lai_kc_min[lc] + (a.lai_kc_max[lc] - a.lai_kc_min[lc]) * (dailyLai - LAImin) / (LAImaxd - LAImin);
+    if ((LAImaxd - LAImin) == 0.) dailyKc = in_kc_min;
+    else dailyKc = in_kc_min + (in_kc_max - in_kc_min) * (dailyLai - LAImin) / (LAImaxd - LAImin);
 
-    const double snow_prev = a.snow[i];
+    const double snow_prev = in_snow;
     double albedo;
-    if (snow_prev > 3.) albedo = a.lct_albedo_snow[lc];  // :366
+    if (snow_prev > 3.) albedo = in_albedo_snow;  // :366
     else albedo = 0.23;                                   // use_kc == 1
 
     double lat_heat;
@@ -257,14 +334,14 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
     const double conv_Wm2_to_mmd = 0.0864 / lat_heat;
     const double solar_rad = conv_Wm2_to_mmd * dailyShortWave;
     const double long_wave_rad_in = conv_Wm2_to_mmd * dailyLongWave;
-    const double emissivity = a.lct_emissivity[lc];
+    const double emissivity = in_emissivity;
     const double temp_K = dailyTempC + 273.2;
     const double stefan_boltz_const = 0.000000004903;
     const double temp_K2 = temp_K * temp_K;  // pow(temp_K, 4.) (:423) as two squarings (<= 1 ulp apart)
     const double long_wave_rad_out = emissivity * stefan_boltz_const * (temp_K2 * temp_K2) / lat_heat;
     const double net_long_wave_rad = long_wave_rad_in - long_wave_rad_out;
     const double net_short_wave_rad = solar_rad * (1. - albedo);
-    const double net_rad = a.p_netrad[q] * (net_short_wave_rad + net_long_wave_rad);
+    const double net_rad = in_netrad * (net_short_wave_rad + net_long_wave_rad);
     const double openWaterNetShortWaveRad = solar_rad * (1. - 0.08);
     const double openWaterNetRad = openWaterNetShortWaveRad + net_long_wave_rad;
 
@@ -280,7 +357,7 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
         dailyPET *= dailyKc;
         dailyOpenWaterPET *= 1.05;
     }
-    const double cfa = a.cfa[q];
+    const double cfa = in_cfa;
     a.lake_balance[i] = (dailyPrec - dailyOpenWaterPET) * cfa;
     a.openwater_prec[i] = dailyPrec;
     a.openwater_pet[i] = dailyOpenWaterPET;
@@ -296,7 +373,7 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
 
 
     // interception (:825-894)
-    double canopy = a.canopy[i];
+    double canopy = in_canopy;
     if (noland) {
         storage_transfer = canopy;
         canopy = 0.;
@@ -306,7 +383,7 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
         if (fabs(canopy) <= MIN_STOR_VOL) canopy = 0.;
         initialStorage = canopy;
         if (dailyLai > 0.00001) {
-            const double max_canopy_storage = a.p_mcwh[q] * dailyLai;
+            const double max_canopy_storage = in_mcwh * dailyLai;
             const double canopy_deficiency = max_canopy_storage - canopy;
             if (dailyPrec < canopy_deficiency) {
                 canopy += dailyPrec;
@@ -338,7 +415,6 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
     // snow in 100 elevation bands (:913-1062).  The loop body is branch-free (selects), because
     // the cells of one warp sit in different regimes (accumulating / melting / bare) on a given day.
     double TempElevMax = 0., snowStorageChange = 0., snow = 0.;
-    const int elev0 = a.s_elev32[r];
     int nz = 0;
     if (bare) {
         // the additions the band loop performs on all-zero bands
@@ -432,16 +508,23 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
     a.snow[i] = snow;
     if (!bare) a.s_snowfree[i] = (int8_t)(nz == 0);
 
+    double gw_recharge_out = 0.;
+    // inputs of the soil part: one round of loads
+    const float builtup = a.builtup[r], in_smax = a.smax[q], gwFactor = a.gwfactor[q];
+    const double in_soil = a.soil[i], in_gamma = a.gamma_hbv[q], in_pcrit = a.p_pcrit[q];
+    const short Rgmax = a.rgmax[q];
+    const int in_texture = a.texture[r], in_ldd = a.ldd[r];
+    const double in_transfer_old = a.storage_transfer[i];
+    if (li) *li = local_load(p, r, m);
     // immediate runoff (:1068-1071)
-    const float builtup = a.builtup[r];
     if (builtup > 0.) {
         immediate_runoff = 0.5 * dailyEffPrec * builtup;
         dailyEffPrec -= immediate_runoff;
     }
 
     // soil and AET (:1080-1239)
-    const double Smax = (double)a.smax[q];
-    double soil = a.soil[i];
+    const double Smax = (double)in_smax;
+    double soil = in_soil;
     if (noland) {
         storage_transfer += soil;
         storage_transfer *= cfa;
@@ -450,6 +533,7 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
         total_daily_runoff = 0.;
         a.gw_recharge[i] = 0.;
         a.storage_transfer[i] = storage_transfer;
+        gw_recharge_out = 0.;
     } else {
         soil *= lafPrev / landAreaFrac;
         initialStorage = soil;
@@ -461,7 +545,7 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
         if (TempElevMax > P_T_SNOWFZ) {
             if (Smax > 0.) {
                 const double soil_saturation = soil / Smax;
-                daily_runoff = dailyEffPrec * pow(soil_saturation, a.gamma_hbv[q]);
+                daily_runoff = dailyEffPrec * pow(soil_saturation, in_gamma);
                 if (dailySoilPET > (maxDailyPET - dailyCanopyEvapo) * soil_saturation)
                     dailyAET = (maxDailyPET - dailyCanopyEvapo) * soil_saturation;
                 else
@@ -475,13 +559,11 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
                 }
                 daily_runoff *= cfa;
                 immediate_runoff *= cfa;
-                const short Rgmax = a.rgmax[q];
-                const float gwFactor = a.gwfactor[q];
                 if ((Rgmax / C100) < (gwFactor * daily_runoff)) daily_gw_recharge = Rgmax / C100;
                 else daily_gw_recharge = gwFactor * daily_runoff;
                 pot_gw_recharge = 0.;
-                if (((arid_gw) && (a.texture[r] < 21)) && (a.ldd[r] >= 0)) {  // :1165-1176
-                    if (dailyPrec <= a.p_pcrit[q]) {
+                if (((arid_gw) && (in_texture < 21)) && (in_ldd >= 0)) {  // :1165-1176
+                    if (dailyPrec <= in_pcrit) {
                         pot_gw_recharge = daily_gw_recharge;
                         daily_gw_recharge = 0.;
                     }
@@ -507,6 +589,7 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
             dailyAET = 0.;
         }
         a.gw_recharge[i] = daily_gw_recharge;  // :1221 (not updated by the fix-up below)
+        gw_recharge_out = daily_gw_recharge;
         landStorageChangeSum += soil - initialStorage;
         land_aet = landStorageChangeSum * (cfa - 1.0) - dailyPrec * (cfa - 1.0)
                    + (dailyAET + dailyCanopyEvapo + dailySnowEvapo) * cfa;
@@ -529,6 +612,14 @@ __device__ __forceinline__ void vertical_cell(const WgkParams &p, const int r, c
     }
     a.soil[i] = soil;
     a.surface_runoff[i] = total_daily_runoff - daily_gw_recharge;
+    if (fx) {
+        fx->owPrec = dailyPrec;
+        fx->owPET = dailyOpenWaterPET;
+        fx->storage_transfer = noland ? storage_transfer : in_transfer_old;  // G_dailyStorageTransfer keeps its last value (:1113)
+        fx->surface_runoff = total_daily_runoff - daily_gw_recharge;
+        fx->gw_recharge = gw_recharge_out;
+    }
+    return true;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1192,63 +1283,6 @@ __global__ void __launch_bounds__(128) k_derive_member(const __grid_constant__ W
 // ----------------------------------------------------------------------------------------
 // cell-parallel pre-pass of the routing day: everything that does not depend on upstream cells
 // ----------------------------------------------------------------------------------------
-// inputs of the cell-parallel routing pre-pass that are known before today's vertical step (statics,
-// parameters, yesterday's state): the band-parallel kernel loads them at its very start, in a warp of
-// its own, so that no global-memory latency is left between the vertical step and the local routing
-struct LocalIn {
-    double ekg, invkg, evaredex, area, cfa, contf, fswb_init, loc_lake, loc_wetland, kS, lake_depth, wetl_depth;
-    double laf, laf_prev, gw, loc_lake_stor, red_loc_lake, loc_wetl_stor, red_loc_wetl, raf_next;
-    int contcell, flags, ldd, arid;
-};
-// today's fluxes of the vertical step (daily.h G_openWaterPrec ... G_dailyStorageTransfer)
-struct LocalFlux {
-    double owPrec, owPET, storage_transfer, surface_runoff, gw_recharge;
-};
-
-__device__ __forceinline__ LocalIn local_load(const WgkParams &p, const int r, const int m) {
-    const WgkArrays &a = p.a;
-    const size_t i = (size_t)m * p.stride + r;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
-    LocalIn li;
-    li.contcell = a.contcell[r];
-    li.flags = a.s_flags[r];
-    li.ldd = a.ldd[r];
-    li.arid = a.arid[r];
-    li.ekg = a.s_ekg[q];
-    li.invkg = a.s_invkg[q];
-    li.evaredex = a.p_evaredex[q];
-    li.area = a.area[r];
-    li.cfa = a.cfa[q];
-    li.contf = a.contfreq[r];
-    li.fswb_init = a.fswb_init[r];
-    li.loc_lake = a.loc_lake[r];
-    li.loc_wetland = a.loc_wetland[r];
-    li.kS = a.p_swoutf[q];
-    li.lake_depth = a.lake_depth_active[q];
-    li.wetl_depth = a.wetl_depth_active[q];
-    li.laf = a.land_area_frac[i];
-    li.laf_prev = a.land_area_frac_prev[i];
-    li.gw = a.gw[i];
-    li.loc_lake_stor = a.loc_lake_stor[i];
-    li.red_loc_lake = a.red_loc_lake[i];
-    li.loc_wetl_stor = a.loc_wetl_stor[i];
-    li.red_loc_wetl = a.red_loc_wetl[i];
-    li.raf_next = a.river_area_frac_next[i];
-    return li;
-}
-
-__device__ __forceinline__ LocalFlux local_flux_load(const WgkParams &p, const int r, const int m) {
-    const WgkArrays &a = p.a;
-    const size_t i = (size_t)m * p.stride + r;
-    LocalFlux fx;
-    fx.owPrec = a.openwater_prec[i];
-    fx.owPET = a.openwater_pet[i];
-    fx.storage_transfer = a.storage_transfer[i];
-    fx.surface_runoff = a.surface_runoff[i];
-    fx.gw_recharge = a.gw_recharge[i];
-    return fx;
-}
-
 __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, const int m, const LocalIn &li, const LocalFlux &fx) {
     const WgkArrays &a = p.a;
     const size_t i = (size_t)m * p.stride + r;
@@ -1628,7 +1662,7 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
 
 // river reach of one cell (routing.cpp:3388-3545), given the inflow-independent context and
 // the sum of upstream discharges; writes discharge / storage and returns nothing
-__device__ __forceinline__ void route_river(const WgkParams &p, const RiverCtx &c, const int r, const int m, const size_t i,
+__device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx &c, const int r, const int m, const size_t i,
                                             const size_t q, const double inflowUpstream, const int day, const int month,
                                             double *__restrict__ qday) {
     const WgkArrays &a = p.a;
@@ -1676,6 +1710,7 @@ __device__ __forceinline__ void route_river(const WgkParams &p, const RiverCtx &
     a.cell_runoff[i] = out ? (transportedVolume - inflowUpstream) : (0. - inflowUpstream);
     a.river_stor[i] = Sr;
     a.river_evapo[i] = riverEvapo;
+    return Sr;
 }
 
 __device__ __forceinline__ double gather_upstream(const WgkParams &p, const RiverCtx &c, const size_t mb,
@@ -1747,38 +1782,72 @@ __global__ void __launch_bounds__(256) k_route_tail(const __grid_constant__ WgkP
 // water body fractions and next-day land area fraction (:5034-5188), updateLandAreaFrac
 // (:5343-5352)
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r, const int m) {
+// inputs of the post-pass that do not depend on today's river step: loaded together with the river
+// context, before the hand-off from the upstream level is awaited
+struct PostIn {
+    double contf, area, red_loc_lake, red_loc_wetl, red_glo_wetl, red_river, raf_next, raf_change, laf, glo_wetland;
+    double river_length, bw, wbf, smaxr, evaredex, loc_lake, loc_wetland, fswb_old, f_glo_lake;
+    int flags;
+};
+
+__device__ __forceinline__ PostIn post_load(const WgkParams &p, const int r, const int m) {
     const WgkArrays &a = p.a;
     const size_t i = (size_t)m * p.stride + r;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
-    const int flags = a.s_flags[r];
-    const double contf = a.contfreq[r];
-    const double cellArea = a.area[r];
-    double red_loc_lake = a.red_loc_lake[i], red_loc_wetl = a.red_loc_wetl[i], red_glo_wetl = a.red_glo_wetl[i];
-    double red_river = a.red_river[i];
-    double raf_next = a.river_area_frac_next[i];
-    double raf_change = a.river_area_frac_change[i];
-    const double laf = a.land_area_frac[i];
-    const double glo_wetland = a.glo_wetland[r];
+    PostIn in;
+    in.flags = a.s_flags[r];
+    in.contf = a.contfreq[r];
+    in.area = a.area[r];
+    in.red_loc_lake = a.red_loc_lake[i];
+    in.red_loc_wetl = a.red_loc_wetl[i];
+    in.red_glo_wetl = a.red_glo_wetl[i];
+    in.red_river = a.red_river[i];
+    in.raf_next = a.river_area_frac_next[i];
+    in.raf_change = a.river_area_frac_change[i];
+    in.laf = a.land_area_frac[i];
+    in.glo_wetland = a.glo_wetland[r];
+    in.river_length = a.river_length[r];
+    in.bw = a.river_bottom_width[r];
+    in.wbf = a.river_width_bf[r];
+    in.smaxr = a.river_storage_max[r];
+    in.evaredex = a.p_evaredex[q];
+    in.loc_lake = a.loc_lake[r];
+    in.loc_wetland = a.loc_wetland[r];
+    in.fswb_old = a.fswb_laf_next[i];
+    in.f_glo_lake = a.f_glo_lake[r];
+    return in;
+}
+
+__device__ __forceinline__ void route_post_compute(const WgkParams &p, const int r, const int m, const PostIn &in, const double Sr) {
+    const WgkArrays &a = p.a;
+    const size_t i = (size_t)m * p.stride + r;
+    const int flags = in.flags;
+    const double contf = in.contf;
+    const double cellArea = in.area;
+    double red_loc_lake = in.red_loc_lake, red_loc_wetl = in.red_loc_wetl, red_glo_wetl = in.red_glo_wetl;
+    double red_river = in.red_river;
+    double raf_next = in.raf_next;
+    double raf_change = in.raf_change;
+    const double laf = in.laf;
+    const double glo_wetland = in.glo_wetland;
     if (flags & FL_ACTIVE) {
         const double raf = raf_next;  // G_riverAreaFrac[n] = G_riverAreaFracNextTimestep_Frac[n] (:3424)
-        const double Sr = a.river_stor[i];
-        const double river_length = a.river_length[r];
-        const double bw = a.river_bottom_width[r];
+        const double river_length = in.river_length;
+        const double bw = in.bw;
         const double crossSectionalArea = Sr / river_length;
         const double riverDepth = -bw / (4. * 1000.) + sqrt(bw / C1000 * bw / (16. * 1000.) + 0.5 * crossSectionalArea);
         double width = bw / C1000 + 4. * riverDepth;
-        const double wbf = a.river_width_bf[r];
+        const double wbf = in.wbf;
         if (width > wbf / C1000) width = wbf / C1000;
-        const double smaxr = a.river_storage_max[r];
-        red_river = clamp01(1. - pow(fabs(Sr - smaxr) / smaxr, (a.p_evaredex[q] * 3.32193)));
+        const double smaxr = in.smaxr;
+        red_river = clamp01(1. - pow(fabs(Sr - smaxr) / smaxr, (in.evaredex * 3.32193)));
         raf_next = red_river * river_length * width * 100. / cellArea;
         raf_change = raf_next - raf;
     }
     if ((flags & FL_ACTIVE) && (flags & (FL_LAKE | FL_RES | FL_GLOWET))) {
         // evaporation reduction factors of the global water bodies (:2790-2802, 3068-3078, 3287-3296)
         const double *__restrict__ g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;
-        const double xexp = (a.p_evaredex[q] * 3.32193);
+        const double xexp = (in.evaredex * 3.32193);
         if (flags & FL_LAKE) {
             const double maxStorage = g[GB_L_MAX];
             a.red_glo_lake[i] = clamp01(1. - pow(fabs(a.glo_lake_stor[i] - maxStorage) / (2. * maxStorage), xexp));
@@ -1792,13 +1861,13 @@ __device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r,
             red_glo_wetl = clamp01(1. - pow(fabs(a.glo_wetl_stor[i] - maxStorage) / maxStorage, xexp));
         }
     }
-    const double loc_lake = a.loc_lake[r], loc_wetland = a.loc_wetland[r];
+    const double loc_lake = in.loc_lake, loc_wetland = in.loc_wetland;
     double fLocLake = ((loc_lake > 0.) && (red_loc_lake > 0.)) ? (red_loc_lake * loc_lake / C100) : 0.;
     double fLocWet = ((loc_wetland > 0.) && (red_loc_wetl > 0.)) ? (red_loc_wetl * loc_wetland / C100) : 0.;
     double fGloWet = ((glo_wetland > 0.) && (red_glo_wetl > 0.)) ? (red_glo_wetl * glo_wetland / C100) : 0.;
-    const double fswb_old = a.fswb_laf_next[i];
+    const double fswb_old = in.fswb_old;
     double fswb_next = fLocLake + fLocWet + fGloWet;
-    const double fGloLake = a.f_glo_lake[r];
+    const double fGloLake = in.f_glo_lake;
     const double maxRiverAreaFrac = contf / C100 - fGloLake;
     if ((flags & (FL_LAKE | FL_RES)) && (fGloLake == 1.)) {
         raf_next = 0.;
@@ -1848,6 +1917,11 @@ __device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r,
     a.land_area_frac[i] = laf_next;
 }
 
+__device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r, const int m) {
+    const PostIn in = post_load(p, r, m);
+    route_post_compute(p, r, m, in, p.a.river_stor[(size_t)m * p.stride + r]);
+}
+
 __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkParams p) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.ncell) return;
@@ -1872,11 +1946,13 @@ __global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ Wgk
     const size_t mb = (size_t)m * p.stride;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
     const RiverCtx c = load_ctx(p, r, mb + r, q);
+    const PostIn in = post_load(p, r, m);  // same round of loads as the river context
+    double Sr = c.prevR;
     if (c.flags & FL_ACTIVE) {
         double *qday = qbuf_of_day(p, dayofs);
-        route_river(p, c, r, m, mb + r, q, gather_upstream(p, c, mb, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
+        Sr = route_river(p, c, r, m, mb + r, q, gather_upstream(p, c, mb, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
     }
-    route_post_cell(p, r, m);
+    route_post_compute(p, r, m, in, Sr);
 }
 
 // vertical balance (+ local routing) of the cells [begin, end), one CTA per tile of 32 cells; tiles
@@ -2068,8 +2144,10 @@ __global__ void __launch_bounds__(VBLOCK) k_cells_pre_tpc(const __grid_constant_
     __shared__ SnowStage stage;
     const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= end) return;
-    vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3], &stage);
-    route_local_cell(p, r, blockIdx.y);
+    LocalIn li;
+    LocalFlux fx;
+    if (vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, blockIdx.y, li, fx);
+    else route_local_cell(p, r, blockIdx.y);
 }
 
 // narrow levels [level_lo, level_hi) of one day in one persistent CTA per member, then the
