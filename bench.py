@@ -173,10 +173,24 @@ def run_wgk(args):
     ach_v = bytes_v / (prof["vertical"] * 1e-3) / 1e9
     t_rout = prof["route_local"] + prof["route_levels"] + prof["route_tail"] + prof["route_post"]
     ach_r = BYTES_ROUTING * w.ng * args.members / (t_rout * 1e-3) / 1e9
-    dominant = "k_vertical" if prof["vertical"] >= t_rout else "routing sweep (k_route_local + k_route_level x L + k_route_tail)"
-    roofline = {"bound": "hbm", "kernel": "k_vertical", "achieved": round(ach_v, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach_v / peak, 4), "traffic": None, "peak_source": peak_src,
+    form = os.environ.get("WGK_VERTICAL_FORM") or ("bands" if w.ng * args.members < 32768 else "cells")
+    kname = {"cells": "k_vertical_tpc", "bands": "k_vertical<VCfgSmall>", "bands2": "k_vertical<VCfgMid>"}[form]
+    dominant = kname if prof["vertical"] >= t_rout else "routing sweep (k_route_local + k_route_level x L + k_route_tail)"
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/traffic.json, written by
+    # tools/ncu_summary.py traffic ...): bytes per launch at this member count, or null when there is no capture
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get(kname.split("<")[0], {}).get(str(args.members))
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": kname + " (vertical balance of the whole grid; the same device code runs per routing level "
+                                            "inside k_cells_pre* in the timed graph)",
+                "achieved": round(ach_v, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach_v / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_v, "avg_launch_ms": round(prof["vertical"], 5),
+                "note": "algorithmic bytes count every cell's 100 snow bands (SURVEY 8d: 2099 B per cell-day); cells without snow and above "
+                        "freezing skip the band loop, so the measured DRAM traffic is lower than the algorithmic bytes",
                 "share_of_day": round(prof["vertical"] / prof["day"], 4),
                 "dominant_by_time": dominant,
                 "routing": {"achieved": round(ach_r, 1), "frac": round(ach_r / peak, 4), "ms_per_day": round(t_rout, 5),

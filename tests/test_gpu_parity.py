@@ -194,6 +194,33 @@ def test_free_run_full_size_20_days():
     _compare(oracles, m, wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS)
 
 
+def test_whole_day_schedule_equals_wavefront(world3000, monkeypatch):
+    """the schedule of a multi-day call (wavefront of (day, level) tasks / whole-grid kernels day after day)
+    and the form of the vertical kernel must not change a single bit"""
+    from oracle import synth_world as sw, wg_init
+    import watergap2_b200 as wg
+    ini = wg_init.derive(world3000)
+    topo = ini["_topology"]
+    f = sw.forcing_month(world3000, 1901, 1)
+    out = []
+    for sched, form in (("wavefront", "cells"), ("wholeday", "cells"), ("wholeday", "bands")):
+        monkeypatch.setenv("WGK_DAY_SCHEDULE", sched)
+        monkeypatch.setenv("WGK_VERTICAL_FORM", form)
+        m = wg.Model(world3000.ng, nmember=2)
+        m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+        m.load(ini)
+        m.forcing_reserve(31)
+        m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+        m.record_cells(np.arange(0, world3000.ng, 97, dtype=np.int32), 31)
+        m.step_days(1, 0, 1, 0, 12)
+        m.step_days(13, 0, 13, 12, 5)
+        out.append(({k: m.get(k, 1) for k in wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS}, m.get_record(5, 1)))
+    for fields, rec in out[1:]:
+        assert np.array_equal(out[0][1], rec)
+        for k in out[0][0]:
+            assert np.array_equal(out[0][0][k], fields[k]), k
+
+
 def test_cell_class_order_does_not_change_results(world3000):
     """wgk_set_cell_classes re-sorts the device order inside each dependency level; the upstream sums
     keep the reference's order, so every field must be BIT-identical with and without it."""

@@ -77,35 +77,63 @@ def full(rep, dst, note=""):
         except Exception as e:  # noqa: BLE001
             lines += ["", f"(traffic not derived: {e})"]
         lines.append("")
-    # hottest source lines (needs -lineinfo and --import-source on)
+    # where the warps spend their time: warp-state samples and executed instructions per device function and per
+    # source line (needs -lineinfo and --import-source on); the CUDA+SASS source page carries the metrics
     try:
-        src = ncu_csv(rep, "source", ["--print-source", "cuda"])
-        if src and len(src) > 2:
-            h = src[0]
-            def col(name):
-                for i, x in enumerate(h):
-                    if x.strip() == name:
-                        return i
-                return None
-            ci, cs, cl = col("# Samples") or col("Sampling Data (All)"), col("Source"), col("#")
-            if ci is None:
-                for i, x in enumerate(h):
-                    if "Samples" in x or "Sampling" in x:
-                        ci = i
-                        break
-            if ci is not None and cs is not None:
-                scored = []
-                for r in src[1:]:
-                    try:
-                        scored.append((float(r[ci]), r[cl] if cl is not None else "", r[cs].strip()))
-                    except Exception:  # noqa: BLE001
-                        pass
-                tot = sum(s for s, _, _ in scored) or 1.0
-                scored.sort(reverse=True)
-                lines += ["## hottest source lines (warp-state samples)", "", "| % samples | line | source |", "|---|---|---|"]
-                for s, ln, text in scored[:25]:
-                    lines.append(f"| {100*s/tot:.1f} | {ln} | `{text[:110].replace('|', '/')}` |")
-                lines.append("")
+        import os
+        import re
+        src = ncu_csv(rep, "source", ["--print-source", "cuda,sass"])
+        hdr_i = next(i for i, r in enumerate(src) if r and r[0] == "Line No")
+        h = src[hdr_i]
+        fpath = next((r[1] for r in src[:hdr_i] if r and r[0] == "File Path"), None)
+        stall = [i for i, n in enumerate(h) if n.startswith("stall_") and "Not Issued" not in n]
+        num = lambda x: float(x) if x not in ("", "-") else 0.0
+        agg = defaultdict(lambda: [0.0, 0.0, "", defaultdict(float)])
+        for r in src[hdr_i + 1:]:
+            if r and r[0] != "":
+                try:
+                    ln = int(r[0])
+                except ValueError:
+                    continue
+                agg[ln][0] += num(r[6])
+                agg[ln][1] += num(r[7])
+                agg[ln][2] = r[1]
+                for i in stall:
+                    agg[ln][3][h[i][6:]] += num(r[i])
+        tot_s = sum(v[0] for v in agg.values()) or 1.0
+        tot_i = sum(v[1] for v in agg.values()) or 1.0
+        starts = []
+        if fpath and os.path.exists(fpath):
+            for n, l in enumerate(open(fpath).read().split("\n"), 1):
+                mm = re.match(r"^__device__ .*? (\w+)\(", l) or re.match(r"^__global__ void (?:__launch_bounds__\([^)]*\) )?(\w+)\(", l)
+                if mm:
+                    starts.append((n, mm.group(1)))
+        def region(ln):
+            name = "(kernel body / inlined libm)"
+            for n, f in starts:
+                if n <= ln:
+                    name = f
+                else:
+                    break
+            return name
+        reg = defaultdict(lambda: [0.0, 0.0, defaultdict(float)])
+        for ln, v in agg.items():
+            r_ = reg[region(ln)]
+            r_[0] += v[0]
+            r_[1] += v[1]
+            for k, x in v[3].items():
+                r_[2][k] += x
+        lines += ["## warp-state samples and executed warp instructions per device function", "",
+                  "(function = the last `__device__`/`__global__` definition above the source line in the current tree)", "",
+                  "| function | % samples | % instructions | dominant stall reasons |", "|---|---|---|---|"]
+        for k, v in sorted(reg.items(), key=lambda kv: -kv[1][0])[:14]:
+            top = sorted(v[2].items(), key=lambda kv: -kv[1])[:3]
+            lines.append(f"| {k} | {100*v[0]/tot_s:.1f} | {100*v[1]/tot_i:.1f} | " + ", ".join(f"{a_} {100*b_/max(v[0],1):.0f}%" for a_, b_ in top) + " |")
+        lines += ["", "## hottest source lines", "", "| % samples | % instr | line | source | stalls |", "|---|---|---|---|---|"]
+        for ln, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:20]:
+            top = sorted(v[3].items(), key=lambda kv: -kv[1])[:2]
+            lines.append(f"| {100*v[0]/tot_s:.1f} | {100*v[1]/tot_i:.1f} | {ln} | `{v[2][:90].replace('|', '/')}` | " + ", ".join(f"{a_} {100*b_/max(v[0],1):.0f}%" for a_, b_ in top) + " |")
+        lines.append("")
     except Exception as e:  # noqa: BLE001
         lines += [f"(source page not available: {e})", ""]
     open(dst, "w").write("\n".join(lines))
@@ -143,7 +171,27 @@ def launch_list(path, dst, note=""):
     print("wrote", dst)
 
 
+def traffic(rep, dst, members):
+    """add the DRAM bytes per launch of the kernels in `rep` to the json `dst` ({kernel: {members: bytes}})"""
+    import json
+    import os
+    rows = ncu_csv(rep, "raw")
+    hdr, units = rows[0], rows[1]
+    out = json.load(open(dst)) if os.path.exists(dst) else {}
+    scale = {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "tbyte": 1e12}
+    for r in rows[2:]:
+        d, u = dict(zip(hdr, r)), dict(zip(hdr, units))
+        b = sum(float(d[k]) * scale[u[k].lower()] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        name = d["Kernel Name"].split("(")[0].split("<")[0]
+        out.setdefault(name, {})[str(members)] = int(b)
+    json.dump(out, open(dst, "w"), indent=1, sort_keys=True)
+    print("wrote", dst, out)
+
+
 if __name__ == "__main__":
     mode, src, dst = sys.argv[1:4]
     note = " ".join(sys.argv[4:])
-    (full if mode == "full" else launch_list)(src, dst, note)
+    if mode == "traffic":
+        traffic(src, dst, int(sys.argv[4]))
+    else:
+        (full if mode == "full" else launch_list)(src, dst, note)

@@ -107,6 +107,7 @@ struct wgk_ctx {
     int64_t launches = 0;
     bool derived_dirty = true;  // s_c1 / s_slope_pow / s_flags need (re)computation
     bool member_dirty = true;   // s_snowfree needs (re)computation (band state uploaded or exposed)
+    bool whole_day = false;     // many members: whole-grid kernels day after day instead of the (day, level) wavefront
     int form = 0;               // vertical kernel form: 0 thread per cell, 1 band-parallel 5 threads/cell, 2 band-parallel 2 threads/cell
     int32_t *d_gidx = nullptr;  // [ncell] index into the global-water-body scratch or -1
     double *d_gbody = nullptr;  // [nmember][ngbody][GB_N]
@@ -274,6 +275,33 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
     return n;
 }
 
+// whole-grid kernels day after day (many members): vertical + local routing of all cells, the wide levels
+// one launch each, the narrow tail in one persistent CTA per member, in stream order
+int enqueue_whole_days(wgk_ctx *c, const WgkParams &p, int ndays) {
+    int n = 0;
+    dim3 block(128);
+    for (int d = 0; d < ndays; d++) {
+        launch_cells_pre(c, p, d, 0, c->ncell);
+        n++;
+        for (int l = 0; l < c->tail_level0; l++) {
+            const int begin = c->level_off[l], end = c->level_off[l + 1];
+            wgk::k_river_level<<<dim3((end - begin + 127) / 128, c->nmember), block, 0, c->stream>>>(p, d, l);
+            n++;
+        }
+        if (c->tail_level0 < c->nlevels) {
+            const int begin = c->level_off[c->tail_level0];
+            wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, d, c->tail_level0, c->nlevels);
+            wgk::k_post_range<<<dim3((c->ncell - begin + 127) / 128, c->nmember), block, 0, c->stream>>>(p, begin, c->ncell);
+            n += 2;
+        }
+        if (c->d_record) {
+            wgk::k_end_of_day<<<1, 256, 0, c->stream>>>(p, d);
+            n++;
+        }
+    }
+    return n;
+}
+
 // The same tasks as a CUDA graph whose edges are exactly the data dependencies:
 //   V(d, l)  <- R(d-1, l)             vertical balance + local routing: own state of the previous day
 //   R(d, l)  <- V(d, l), R(d, l-1)    river + post: upstream discharge of the same day
@@ -423,6 +451,16 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
         else if (e && !strcmp(e, "bands2")) c->form = 2;
         else if (e && !strcmp(e, "cells")) c->form = 0;
         else c->form = work < 32768 ? 1 : 0;  // (the 2-threads-per-cell form never beat both others on B200)
+    }
+    {   // Schedule of a multi-day call.  Few members: the (day, level) wavefront, which hides the level-to-level
+        // latency chain of a day behind the following days.  Many members: every kernel fills the GPU on its own,
+        // and whole-grid kernels day after day avoid the partial waves of 57 small launches per day
+        // (measured on B200, 0.5 degree grid, per member-day: 128 members wavefront 43.7 us, whole-day 41.6 us;
+        // 32 members wavefront 45.5 us, whole-day 51.5 us).
+        const char *e = getenv("WGK_DAY_SCHEDULE");  // "wavefront" | "wholeday"
+        if (e && !strcmp(e, "wavefront")) c->whole_day = false;
+        else if (e && !strcmp(e, "wholeday")) c->whole_day = true;
+        else c->whole_day = ((long long)nmember * ncell >= 6000000);
     }
     if (c->opt.tail_threshold <= 0) {
         const char *e = getenv("WGK_TAIL_THRESHOLD");
@@ -914,8 +952,18 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
         if (it == c->graphs.end()) {
             cudaGraphExec_t ex;
             int nn = 0;
-            rc = build_wavefront_graph(c, p, ndays, &ex, &nn);
-            if (rc) return rc;
+            if (c->whole_day) {  // linear chain, recorded by stream capture
+                cudaGraph_t g;
+                CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                nn = enqueue_whole_days(c, p, ndays);
+                CU(cudaStreamEndCapture(c->stream, &g));
+                cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+                cudaGraphDestroy(g);
+                if (e != cudaSuccess) return fail(c, WGK_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+            } else {
+                rc = build_wavefront_graph(c, p, ndays, &ex, &nn);
+                if (rc) return rc;
+            }
             c->graphs[ndays] = ex;
             c->graph_nodes[ndays] = nn;
             it = c->graphs.find(ndays);
@@ -923,7 +971,7 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
         CU(cudaGraphLaunch(it->second, c->stream));
         c->launches += c->graph_nodes[ndays];
     } else {
-        c->launches += enqueue_wavefront_serial(c, p, ndays);
+        c->launches += c->whole_day ? enqueue_whole_days(c, p, ndays) : enqueue_wavefront_serial(c, p, ndays);
     }
     CU(cudaGetLastError());
     rc = publish_discharge(c, ndays - 1);

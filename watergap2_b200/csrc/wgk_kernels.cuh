@@ -1922,6 +1922,13 @@ __device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r,
     route_post_compute(p, r, m, in, p.a.river_stor[(size_t)m * p.stride + r]);
 }
 
+// post-pass of the cells [begin, end) (whole-day schedule: the cells of the narrow tail levels)
+__global__ void __launch_bounds__(128) k_post_range(const __grid_constant__ WgkParams p, const int begin, const int end) {
+    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= end) return;
+    route_post_cell(p, r, blockIdx.y);
+}
+
 __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkParams p) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.ncell) return;
