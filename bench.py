@@ -187,7 +187,10 @@ def run_wgk(args):
     roofline = {"bound": "hbm", "kernel": kname + " (vertical balance of the whole grid; the same device code runs per routing level "
                                             "inside k_cells_pre* in the timed graph)",
                 "achieved": round(ach_v, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach_v / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "frac": round(ach_v / peak, 4), "traffic": traffic,
+                "dram_achieved": round(traffic / (prof["vertical"] * 1e-3) / 1e9, 1) if traffic else None,
+                "dram_frac": round(traffic / (prof["vertical"] * 1e-3) / 1e9 / peak, 4) if traffic else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_v, "avg_launch_ms": round(prof["vertical"], 5),
                 "note": "algorithmic bytes count every cell's 100 snow bands (SURVEY 8d: 2099 B per cell-day); cells without snow and above "
                         "freezing skip the band loop, so the measured DRAM traffic is lower than the algorithmic bytes",

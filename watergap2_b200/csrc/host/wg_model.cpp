@@ -483,6 +483,14 @@ void dailyWaterBalanceClass::pull() {
 // device synchronisation
 // ------------------------------------------------------------------------------------------
 void Engine::push_static() {
+    // class key per cell (which water-body code the cell needs): lets the library store cells of equal class
+    // next to each other inside a routing level; results do not depend on it (include/wgk.h)
+    std::vector<uint8_t> cls(ncell);
+    for (int n = 0; n < ncell; n++)
+        cls[n] = (uint8_t)((routing.G_loc_lake[n] > 0.) * 1 + (routing.G_loc_wetland[n] > 0.) * 2
+                           + ((routing.G_lake_area[n] > 0.) || (routing.G_reservoir_area[n] > 0.) || (routing.G_glo_wetland[n] > 0.)) * 4
+                           + (G_aindex[n] == 1) * 8);
+    check(wgk_set_cell_classes(ctx, cls.data()), "wgk_set_cell_classes");
     check(wgk_set_topology(ctx, routing.G_routOrder.data(), routing.G_downstreamCell.data()), "wgk_set_topology");
     Grid<double> area(ncell);
     for (int n = 0; n < ncell; n++) area[n] = geo.areaOfCellByArrayPos(n);
