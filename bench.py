@@ -126,7 +126,31 @@ def run_wgk(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w, ini = build_inputs()
     forcing = year_forcing(w)
-    m = make_model(w, ini, args.members, local)
+    ncell, tiles, shard = w.ng, 1, None
+    if args.workload == "5arcmin":
+        # 32 copies of the 0.5 degree world as one grid; with N GPUs every rank takes whole drainage basins
+        import watergap2_b200 as wg
+        from watergap2_b200.ensemble import shard_by_basin, subgrid_inputs, tile_inputs
+        tiles = 32
+        topo = ini["_topology"]
+        fields, ro, dc = tile_inputs(ini, topo["rout_order"], topo["outflow_cell"], tiles)
+        if world > 1:
+            b = np.asarray(topo["basins2"]).astype(np.int64)
+            basins = np.concatenate([np.where(b > 0, b + t * (int(b.max()) + 1), 0) for t in range(tiles)])
+            shard = np.nonzero(shard_by_basin(basins, world) == rank)[0]
+            fields, ro, dc = subgrid_inputs(fields, ro, dc, shard)
+        ncell = int(np.asarray(ro).size)
+        m = wg.Model(ncell, nmember=args.members, npset=1, device=local)
+        m.set_topology(ro, dc, cell_class=wg.cell_classes(fields))
+        m.load(fields)
+        del fields
+
+        def grid_of(a):  # a [ng][31] grid of the base world -> the rank's cells of the tiled grid
+            t = np.concatenate([a] * tiles, axis=0)
+            return np.ascontiguousarray(t if shard is None else t[shard])
+        forcing = [{k: grid_of(v) for k, v in f.items()} for f in forcing]
+    else:
+        m = make_model(w, ini, args.members, local)
     upload_year(m, forcing)
     stream = torch.cuda.ExternalStream(m.stream, device=local)
 
@@ -158,7 +182,13 @@ def run_wgk(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    cell_days = float(w.ng) * 365 * args.members * world * args.steps
+    ncell_all = torch.tensor([float(ncell)], device="cuda", dtype=torch.float64)  # ranks hold different shards
+    if world > 1 and args.workload == "5arcmin":
+        dist.all_reduce(ncell_all, op=dist.ReduceOp.SUM)
+    elif world > 1:
+        ncell_all *= world
+    total_cells = float(ncell_all.item())
+    cell_days = total_cells * 365 * args.members * args.steps
     value = cell_days / (ms_max / 1e3)
 
     # ---- per-kernel roofline (CUDA events between the phases, plain launches) ------------------
@@ -169,11 +199,11 @@ def run_wgk(args):
         for k in prof:
             prof[k] += p[k] / nprof
     peak, peak_src = measured_peaks()
-    bytes_v = BYTES_VERTICAL * w.ng * args.members
+    bytes_v = BYTES_VERTICAL * ncell * args.members
     ach_v = bytes_v / (prof["vertical"] * 1e-3) / 1e9
     t_rout = prof["route_local"] + prof["route_levels"] + prof["route_tail"] + prof["route_post"]
-    ach_r = BYTES_ROUTING * w.ng * args.members / (t_rout * 1e-3) / 1e9
-    form = os.environ.get("WGK_VERTICAL_FORM") or ("bands" if w.ng * args.members < 32768 else "cells")
+    ach_r = BYTES_ROUTING * ncell * args.members / (t_rout * 1e-3) / 1e9
+    form = os.environ.get("WGK_VERTICAL_FORM") or ("bands" if ncell * args.members < 32768 else "cells")
     kname = {"cells": "k_vertical_tpc", "bands": "k_vertical<VCfgSmall>", "bands2": "k_vertical<VCfgMid>"}[form]
     dominant = kname if prof["vertical"] >= t_rout else "routing sweep (k_route_local + k_route_level x L + k_route_tail)"
     # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/traffic.json, written by
@@ -181,7 +211,7 @@ def run_wgk(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(kname.split("<")[0], {}).get(str(args.members))
+            traffic = json.load(fh).get(kname.split("<")[0], {}).get(str(args.members)) if tiles == 1 else None
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": kname + " (vertical balance of the whole grid; the same device code runs per routing level "
@@ -211,9 +241,9 @@ def run_wgk(args):
         for k in ("P", "T", "SW", "LW"):
             d[k] = torch.from_numpy(np.ascontiguousarray(forcing[mon][k])).pin_memory()
         pinned.append(d)
-    stations = np.argsort(-w.acc)[:50].astype(np.int32)
+    stations = np.argsort(-w.acc)[:50].astype(np.int32) if tiles == 1 else np.arange(0, ncell, max(1, ncell // 50), dtype=np.int32)[:50]
     m.record_cells(stations, 365)
-    out_host = torch.empty(w.ng, dtype=torch.float64).pin_memory().numpy()
+    out_host = torch.empty(ncell, dtype=torch.float64).pin_memory().numpy()
     e2e_steps = max(1, min(args.steps, 5))
 
     def upload(year):  # the year's 12 x 4 grids from pinned host memory into the slots of its parity (asynchronous)
@@ -245,21 +275,24 @@ def run_wgk(args):
     tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_val = float(w.ng) * 365 * args.members * world * e2e_steps / float(tt.item())
-    h2d = sum(4 * w.ng * 31 * 4 for _ in range(12))
-    d2h = (w.ng * 8 + 365 * len(stations) * 8) * args.members
+    e2e_val = total_cells * 365 * args.members * e2e_steps / float(tt.item())
+    h2d = sum(4 * ncell * 31 * 4 for _ in range(12))
+    d2h = (ncell * 8 + 365 * len(stations) * 8) * args.members
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "steps": e2e_steps, "timing": "host wall clock around the API calls, max over ranks; every step copies one year of "
            "forcing from pinned host memory (for the following year, on the library's copy stream) and reads the results back"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak" if tiles == 1 else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: 0.5deg global synthetic grid (67420 cells), daily, routing + 100-band snow; "
-                                   "1 step = 1 simulated year (365 days), default 30 steps = the 30-year run",
-                       "cells": w.ng, "members_per_gpu": args.members, "days_per_step": 365,
-                       "parallelism": f"{world} independent member shard(s), no data-path collective",
-                       "l2": "inputs larger than L2: 183 MB state+statics per member and 394 MB of forcing per year are streamed every step",
+            "config": {"workload": ("configs[1]: 0.5deg global synthetic grid (67420 cells), daily, routing + 100-band snow; "
+                                    "1 step = 1 simulated year (365 days), default 30 steps = the 30-year run") if tiles == 1 else
+                                   ("configs[4] at its size: synthetic grid with the cell count of a 5-arcmin world (32 disjoint copies of the 0.5deg "
+                                    "world = 2157440 cells), one member, sharded by whole drainage basin over the GPUs; 1 step = 1 simulated year"),
+                       "cells": int(total_cells) if tiles > 1 else w.ng, "cells_this_rank": ncell, "members_per_gpu": args.members, "days_per_step": 365,
+                       "parallelism": (f"{world} independent member shard(s), no data-path collective" if tiles == 1 else
+                                       f"{world} basin shard(s) of one grid, no data-path collective"),
+                       "l2": "inputs larger than L2: 183 MB state+statics per member and 394 MB of forcing per year are streamed every step (x32 for 5arcmin)",
                        "routing_levels": m.nlevels},
             "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "clocks": clocks}
     if rank == 0:
@@ -373,6 +406,10 @@ def main():
     ap.add_argument("--impl", default="wgk", choices=["wgk", "reference"])
     ap.add_argument("--members", type=int, default=1, help="members (independent model runs) per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--workload", default="0.5deg", choices=["0.5deg", "5arcmin"],
+                    help="0.5deg: BASELINE configs[1] (default, the driver's line).  5arcmin: configs[4], a grid with the cell count of a "
+                         "5-arcmin world (32 disjoint copies of the 0.5 degree world = 2 157 440 cells), one member, sharded by whole "
+                         "drainage basin over the GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -277,6 +277,37 @@ def test_basin_shards_equal_full_grid(world3000):
             assert np.array_equal(ref, got[k]), (r, k)
 
 
+def test_tiled_grid_equals_single_world(world1000):
+    """a grid of 4 disjoint copies of a world (how the 5-arcmin-sized workload of bench.py is built): every
+    copy must reproduce the single-world run bit for bit, through the same kernels and the wavefront graph"""
+    from oracle import synth_world as sw, wg_init
+    import watergap2_b200 as wg
+    from watergap2_b200.ensemble import tile_inputs
+    w = world1000
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    ro, dc = np.asarray(topo["rout_order"]), np.asarray(topo["outflow_cell"])
+    f = sw.forcing_month(w, 1901, 1)
+    names = wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS
+
+    def run(fields, ro, dc, forcing):
+        m = wg.Model(ro.size)
+        m.set_topology(ro, dc, cell_class=wg.cell_classes(fields))
+        m.load(fields)
+        m.forcing_reserve(31)
+        m.set_forcing(0, 31, forcing["P"], forcing["T"], forcing["SW"], forcing["LW"])
+        m.step_days(1, 0, 1, 0, 12)
+        return {k: m.get(k) for k in names}
+
+    one = run(ini, ro, dc, f)
+    tf, tro, tdc = tile_inputs(ini, ro, dc, 4)
+    many = run(tf, tro, tdc, {k: np.concatenate([v] * 4, axis=0) for k, v in f.items()})
+    for k in names:
+        got = many[k].reshape(4, -1)
+        for t in range(4):
+            assert np.array_equal(one[k], got[t]), (k, t)
+
+
 def test_members_and_parameter_sets(world3000):
     """two members with different per-cell parameter sets advance independently and each
     matches its own oracle run (calibration sweep layout, BASELINE config 3)."""

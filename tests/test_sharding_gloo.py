@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from watergap2_b200.ensemble import ensemble_mean_var, shard_by_basin, shard_members, subgrid_inputs
+from watergap2_b200.ensemble import ensemble_mean_var, routing_levels, shard_by_basin, shard_members, subgrid_inputs, tile_inputs
 
 
 def test_shard_members_partition():
@@ -65,6 +65,23 @@ def test_subgrid_inputs_keep_order_and_levels(world3000, oracle_lib):
     assert seen == w.ng
     with pytest.raises(ValueError):
         subgrid_inputs(ini, ro, dc, np.nonzero(dc > 0)[0][:5])  # cells cut out of their basins
+
+
+def test_tile_inputs_is_a_valid_level_major_grid(world1000):
+    from oracle import wg_init
+    ini = wg_init.derive(world1000)
+    topo = ini["_topology"]
+    ro, dc = np.asarray(topo["rout_order"]), np.asarray(topo["outflow_cell"])
+    f, tro, tdc = tile_inputs(ini, ro, dc, 3)
+    ng = ro.size
+    assert sorted(tro.tolist()) == list(range(1, 3 * ng + 1))
+    lvl = routing_levels(tro, tdc)
+    assert np.array_equal(lvl, np.tile(routing_levels(ro, dc), 3))
+    assert (np.diff(lvl[np.argsort(tro)]) >= 0).all()  # level-major, as rout_order's sweeps number the cells
+    has = tdc > 0
+    assert ((tdc[has] - 1) // ng == np.nonzero(has)[0] // ng).all()  # no water between the copies
+    assert f["params"].shape == (26, 3 * ng) and np.asarray(f["snow_bands"]).size == 3 * ng * 101
+    assert np.array_equal(np.asarray(f["area"])[ng:2 * ng], np.asarray(ini["area"]))
 
 
 def _worker(rank, world, port, total, n, out):

@@ -76,6 +76,50 @@ def subgrid_inputs(fields, rout_order, downstream_cell, cells, ncell_table=18):
     return out, sub_ro, sub_dc.astype(np.int32)
 
 
+def routing_levels(rout_order, downstream_cell):
+    """0-based dependency level of every cell (longest path from a headwater)"""
+    ro = np.asarray(rout_order)
+    dc = np.asarray(downstream_cell)
+    lvl = np.zeros(ro.size, np.int32)
+    for n in np.argsort(ro, kind="stable"):
+        d = dc[n]
+        if d > 0 and lvl[d - 1] < lvl[n] + 1:
+            lvl[d - 1] = lvl[n] + 1
+    return lvl
+
+
+def tile_inputs(fields, rout_order, downstream_cell, ntiles):
+    """A grid of `ntiles` disjoint copies of a world (cell t*ncell + n = cell n of copy t): the way the test-suite
+    and bench.py build a grid with the cell count of a 5-arcmin world (2.2 M cells) from the 0.5 degree
+    generator, whose raster is fixed.  Ranks are renumbered level-major (level, copy, original rank), as
+    rout_order's sweeps would number them; every copy keeps its own basins.
+    -> (fields, rout_order, downstream_cell) of the tiled grid."""
+    ro = np.asarray(rout_order)
+    dc = np.asarray(downstream_cell)
+    ng, T = ro.size, int(ntiles)
+    lvl = routing_levels(ro, dc)
+    order = np.lexsort((np.tile(ro, T), np.repeat(np.arange(T), ng), np.tile(lvl, T)))
+    new_ro = np.empty(ng * T, np.int32)
+    new_ro[order] = np.arange(1, ng * T + 1, dtype=np.int32)
+    off = np.repeat(np.arange(T, dtype=np.int64) * ng, ng)
+    tdc = np.tile(dc.astype(np.int64), T)
+    new_dc = np.where(tdc > 0, tdc + off, 0).astype(np.int32)
+    out = {}
+    for k, v in fields.items():
+        if k.startswith("_"):
+            continue
+        a = np.asarray(v)
+        if a.ndim >= 1 and a.shape[0] == ng:
+            out[k] = np.concatenate([a] * T, axis=0)
+        elif a.ndim == 2 and a.shape[1] == ng:  # params [26][ncell]
+            out[k] = np.concatenate([a] * T, axis=1)
+        elif a.ndim == 1 and a.size > ng and a.size % ng == 0:  # flattened [ncell][bands]
+            out[k] = np.tile(a, T)
+        else:
+            out[k] = a
+    return out, new_ro, new_dc
+
+
 class _CudaArray:
     """zero-copy view of a wgk device buffer for torch.as_tensor (CUDA array interface v2)"""
 
