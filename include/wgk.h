@@ -142,6 +142,24 @@ int wgk_total_storage_km3(wgk_ctx *ctx, int member, double *out);
  * (station series, routing.cpp:4232-4238); host out[ndays][ncells] */
 int wgk_record_cells(wgk_ctx *ctx, const int32_t *cells, int ncells, int max_days);
 int wgk_get_record(wgk_ctx *ctx, int member, double *out, int ndays);
+/* ---- EnKF state bridge (what the PDAF coupling of the reference exchanges with the model) ----------
+ * wgk_month_begin: start accumulating the daily WghmStateFile entries of the seven routing compartments
+ * (routing.cpp:5002-5020) for Cell::mean (wghmStateFile.cpp:711-728); every stepped day counts.
+ * wgk_state_vector: extract_sub_ (extractsub.cpp:65-79) for one member: out[ncells][10] = canopy, snow, soil,
+ * local lake, local wetland, global lake, global wetland, reservoir, river, groundwater of the given cells
+ * (0-based) in mm over the continental area, kind 0 = mean of the month so far, kind 1 = last day, minus
+ * mean_field[ncells][10] (NULL: nothing subtracted).
+ * wgk_enkf_update: enkf_wghmstate_ (enKF2wghmState.cpp:89-121, 440-471) for one member: last-day state +=
+ * field - prediction with the reference's limits (canopy, snow <= 1000, soil, local / global wetland,
+ * reservoir, river >= 0; lakes and groundwater may go negative), snow bands rescaled by (field + mean_field) /
+ * monthly mean snow (or set to 1/100 of it where that mean is 0) within [0, 1000], and the result restored as
+ * the start state of the next cycle (daily.cpp:1896-1924, routing.cpp:851-882).  field, prediction, mean_field:
+ * host [ncells][10]. */
+int wgk_month_begin(wgk_ctx *ctx);
+int wgk_state_vector(wgk_ctx *ctx, int member, int kind, const int32_t *cells, int ncells, const double *mean_field, double *out);
+int wgk_enkf_update(wgk_ctx *ctx, int member, const int32_t *cells, int ncells, const double *field, const double *prediction,
+                    const double *mean_field);
+
 /* one simulated day with plain launches and CUDA events between the phases, on the context's
  * stream: ms[0] vertical, ms[1] routing pre-pass (cell-parallel), ms[2] wide routing levels
  * (one launch each), ms[3] narrow-level tail (one persistent CTA per member), ms[4] routing

@@ -78,6 +78,9 @@ def lib():
     L.wgk_set_stream.argtypes = [vp, vp]
     L.wgk_set_topology.argtypes = [vp, vp, vp]
     L.wgk_set_cell_classes.argtypes = [vp, vp]
+    L.wgk_month_begin.argtypes = [vp]
+    L.wgk_state_vector.argtypes = [vp, ci, ci, vp, ci, vp, vp]
+    L.wgk_enkf_update.argtypes = [vp, ci, vp, ci, vp, vp, vp]
     L.wgk_num_levels.argtypes = [vp]
     L.wgk_get_levels.argtypes = [vp, vp]
     L.wgk_field_id.argtypes = [cp]
@@ -255,6 +258,25 @@ class Model:
 
     def set_stream(self, cuda_stream):
         self._ck(self._L.wgk_set_stream(self._c, ctypes.c_void_p(cuda_stream)))
+
+    # -- EnKF state bridge ------------------------------------------------------------------------
+    def month_begin(self):
+        self._ck(self._L.wgk_month_begin(self._c))
+
+    def state_vector(self, cells, kind="month", member=0, mean_field=None):
+        """[ncells, 10] state vector of extract_sub_ (mm over the continental area) for `cells` (0-based)"""
+        c = np.ascontiguousarray(cells, np.int32)
+        out = np.empty((c.size, 10), np.float64)
+        mf = None if mean_field is None else np.ascontiguousarray(mean_field, np.float64)
+        self._ck(self._L.wgk_state_vector(self._c, member, {"month": 0, "lastday": 1}[kind], c.ctypes.data, c.size,
+                                          None if mf is None else mf.ctypes.data, out.ctypes.data))
+        return out
+
+    def enkf_update(self, cells, field, prediction, mean_field, member=0):
+        c = np.ascontiguousarray(cells, np.int32)
+        a = [np.ascontiguousarray(x, np.float64) for x in (field, prediction, mean_field)]
+        assert all(x.size == c.size * 10 for x in a)
+        self._ck(self._L.wgk_enkf_update(self._c, member, c.ctypes.data, c.size, *[x.ctypes.data for x in a]))
 
     # -- diagnostics ------------------------------------------------------------------------------
     def total_storage_km3(self, member=0):

@@ -107,6 +107,8 @@ struct wgk_ctx {
     int64_t launches = 0;
     bool derived_dirty = true;  // s_c1 / s_slope_pow / s_flags need (re)computation
     bool member_dirty = true;   // s_snowfree needs (re)computation (band state uploaded or exposed)
+    bool month_acc = false;     // EnKF bridge: accumulate the daily WghmStateFile entries of the month
+    int month_days = 0;
     bool whole_day = false;     // many members: whole-grid kernels day after day instead of the (day, level) wavefront
     int form = 0;               // vertical kernel form: 0 thread per cell, 1 band-parallel 5 threads/cell, 2 band-parallel 2 threads/cell
     int32_t *d_gidx = nullptr;  // [ncell] index into the global-water-body scratch or -1
@@ -185,6 +187,7 @@ WgkParams make_params(const wgk_ctx *c) {
     p.forcing_nslots = c->forcing_nslots;
     p.forcing_per_member = c->forcing_per_member;
     p.restart = c->opt.restart;
+    p.month_acc = c->month_acc ? 1 : 0;
     p.nlevels = c->nlevels;
     return p;
 }
@@ -925,6 +928,7 @@ int wgk_routing_day(wgk_ctx *c, int day, int month, int dom) {
     if (rc) return rc;
     c->launches += enqueue_routing(c, make_params(c), 0);
     CU(cudaGetLastError());
+    if (c->month_acc) c->month_days += 1;
     return publish_discharge(c, 0);
 }
 
@@ -976,7 +980,84 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
     CU(cudaGetLastError());
     rc = publish_discharge(c, ndays - 1);
     if (rc) return rc;
+    if (c->month_acc) c->month_days += ndays;
     return forcing_after_step(c, slot0, ndays);
+}
+
+// ---------------------------------------------------------------------------------------
+// EnKF state bridge
+// ---------------------------------------------------------------------------------------
+int wgk_month_begin(wgk_ctx *c) {
+    if (!c) return WGK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->arrays.mon_acc, 0, (size_t)c->nmember * 7 * c->stride * sizeof(double), c->stream));
+    if (!c->month_acc) drop_graph(c);  // the flag is part of the kernel parameters baked into the graphs
+    c->month_acc = true;
+    c->month_days = 0;
+    return WGK_OK;
+}
+
+namespace {
+// device copies of the region's cell list (as device positions) and of up to three [ncells][10] host arrays
+struct BridgeBuffers {
+    int32_t *pos = nullptr;
+    double *d[3] = {nullptr, nullptr, nullptr};
+    ~BridgeBuffers() {
+        cudaFree(pos);
+        for (double *x : d) cudaFree(x);
+    }
+};
+int bridge_upload(wgk_ctx *c, BridgeBuffers &b, const int32_t *cells, int ncells, const double *h0, const double *h1, const double *h2) {
+    if (!c->have_topology) return fail(c, WGK_ERR_STATE, "no topology");
+    std::vector<int32_t> pos(ncells);
+    for (int k = 0; k < ncells; k++) {
+        if (cells[k] < 0 || cells[k] >= c->ncell) return fail(c, WGK_ERR_ARG, "cell %d out of range", cells[k]);
+        pos[k] = c->rank_of_cell[cells[k]];
+    }
+    CU(cudaMalloc(&b.pos, sizeof(int32_t) * std::max(1, ncells)));
+    CU(cudaMemcpyAsync(b.pos, pos.data(), sizeof(int32_t) * ncells, cudaMemcpyHostToDevice, c->stream));
+    const double *h[3] = {h0, h1, h2};
+    for (int k = 0; k < 3; k++) {
+        CU(cudaMalloc(&b.d[k], sizeof(double) * 10 * std::max(1, ncells)));
+        if (h[k]) CU(cudaMemcpyAsync(b.d[k], h[k], sizeof(double) * 10 * ncells, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));  // pos / h* are host temporaries of the caller
+    return WGK_OK;
+}
+}  // namespace
+
+int wgk_state_vector(wgk_ctx *c, int member, int kind, const int32_t *cells, int ncells, const double *mean_field, double *out) {
+    if (!c || !cells || !out || ncells < 0 || member < 0 || member >= c->nmember || (kind != 0 && kind != 1)) return WGK_ERR_ARG;
+    if (kind == 0 && (!c->month_acc || c->month_days <= 0)) return fail(c, WGK_ERR_STATE, "wgk_month_begin and at least one stepped day must precede a monthly state vector");
+    if (ncells == 0) return WGK_OK;
+    CU(cudaSetDevice(c->device));
+    BridgeBuffers b;
+    int rc = bridge_upload(c, b, cells, ncells, mean_field, nullptr, nullptr);
+    if (rc) return rc;
+    wgk::k_state_vector<<<(ncells + 127) / 128, 128, 0, c->stream>>>(make_params(c), member, kind, c->month_days, b.pos, ncells,
+                                                                     mean_field ? b.d[0] : nullptr, b.d[1]);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, b.d[1], sizeof(double) * 10 * ncells, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return WGK_OK;
+}
+
+int wgk_enkf_update(wgk_ctx *c, int member, const int32_t *cells, int ncells, const double *field, const double *prediction,
+                    const double *mean_field) {
+    if (!c || !cells || !field || !prediction || !mean_field || ncells < 0 || member < 0 || member >= c->nmember) return WGK_ERR_ARG;
+    if (!c->month_acc || c->month_days <= 0) return fail(c, WGK_ERR_STATE, "wgk_month_begin and the month's days must precede wgk_enkf_update");
+    if (ncells == 0) return WGK_OK;
+    CU(cudaSetDevice(c->device));
+    BridgeBuffers b;
+    int rc = bridge_upload(c, b, cells, ncells, field, prediction, mean_field);
+    if (rc) return rc;
+    wgk::k_enkf_update<<<(ncells + 127) / 128, 128, 0, c->stream>>>(make_params(c), member, c->month_days, b.pos, ncells, b.d[0], b.d[1], b.d[2]);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    c->member_dirty = true;  // the band state changed: s_snowfree is recomputed before the next step
+    return WGK_OK;
 }
 
 // ---------------------------------------------------------------------------------------

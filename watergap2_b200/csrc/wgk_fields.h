@@ -132,6 +132,9 @@
     X(s_delev, int16_t, "i16", CELL, 101) \
     X(s_de_min, int16_t, "i16", CELL, 1) \
     X(s_de_max, int16_t, "i16", CELL, 1) \
+    /* ---- monthly sums of the seven routing compartments in mm over the continental area (the daily values the \
+       reference writes to WghmStateFile, routing.cpp:5002-5020), band-major [7][cell]; only while enabled ---- */ \
+    X(mon_acc, double, "f64", MEMBER, 7) \
     /* ---- derived from the member state (k_derive_member), maintained by the vertical kernel ---- */ \
     X(s_snowfree, int8_t, "i8", MEMBER, 1) \
     /* ---- land cover tables (LCT_22.DAT / LAI_22.DAT; daily.h:204-208, lai.h) ---- */ \

@@ -49,6 +49,7 @@ struct WgkParams {
     int ncell, stride, nmember, npset;
     int forcing_nslots, forcing_per_member;
     int restart;
+    int month_acc;                // accumulate the daily WghmStateFile values of the month (EnKF bridge)
     int nlevels;
 };
 
@@ -1910,6 +1911,19 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
     a.river_area_frac_change[i] = raf_change;
     a.fswb_laf[i] = fswb_old;
     a.fswb_laf_next[i] = fswb_next;
+    if (p.month_acc) {
+        // the day's entry of WghmStateFile for the seven routing compartments (routing.cpp:5002-5020), summed in
+        // day order as Cell::mean does (wghmStateFile.cpp:711-728)
+        const double denom = ((cellArea * (contf / C100)) / C1E6);
+        double *__restrict__ acc = a.mon_acc + (size_t)m * 7 * p.stride + r;
+        acc[0 * (size_t)p.stride] += a.loc_lake_stor[i] / denom;
+        acc[1 * (size_t)p.stride] += a.loc_wetl_stor[i] / denom;
+        acc[2 * (size_t)p.stride] += a.glo_lake_stor[i] / denom;
+        acc[3 * (size_t)p.stride] += a.glo_wetl_stor[i] / denom;
+        acc[4 * (size_t)p.stride] += a.res_stor[i] / denom;
+        acc[5 * (size_t)p.stride] += Sr / denom;
+        acc[6 * (size_t)p.stride] += a.gw[i] / denom;
+    }
     a.status_laf_next[i] = 1;
     // updateLandAreaFrac fused: prev <- cur, cur <- next
     a.land_area_frac_next[i] = laf_next;
@@ -2230,6 +2244,106 @@ __global__ void __launch_bounds__(256) k_total_storage(const __grid_constant__ W
         __syncthreads();
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// ----------------------------------------------------------------------------------------
+// EnKF state bridge: the state vector PDAF sees and the analysis increment it hands back
+// ----------------------------------------------------------------------------------------
+// land area fraction as routingClass::getLandAreaFrac (routing.h:246-251)
+__device__ __forceinline__ double laf_of(const WgkArrays &a, const size_t i) {
+    return (0 == a.status_laf_next[i]) ? a.land_area_frac[i] : a.land_area_frac_next[i];
+}
+
+// the ten compartments of one cell in mm over the continental area, order of extractsub.cpp:65-79:
+// canopy, snow, soil, local lake, local wetland, global lake, global wetland, reservoir, river, groundwater.
+// kind 1: the last day (integrateWGHM.cpp:838-847, routing.cpp:5002-5020); kind 0: the mean of the month's
+// `ndays` entries (Cell::mean): canopy / snow / soil carry the month-end value on every day of the month.
+__device__ __forceinline__ void state_of_cell(const WgkParams &p, const int x, const int m, const int kind, const int ndays, double v[10]) {
+    const WgkArrays &a = p.a;
+    const size_t i = (size_t)m * p.stride + x;
+    const double laf = laf_of(a, i), contf = a.contfreq[x];
+    const double land[3] = {a.canopy[i] * laf / contf, a.snow[i] * laf / contf, a.soil[i] * laf / contf};
+    const double denom = ((a.area[x] * (contf / C100)) / C1E6);
+    const double stor[7] = {a.loc_lake_stor[i], a.loc_wetl_stor[i], a.glo_lake_stor[i], a.glo_wetl_stor[i], a.res_stor[i], a.river_stor[i], a.gw[i]};
+    if (kind == 1) {
+        for (int k = 0; k < 3; k++) v[k] = land[k];
+        for (int k = 0; k < 7; k++) v[3 + k] = stor[k] / denom;
+    } else {
+        for (int k = 0; k < 3; k++) {
+            double s = 0.0;
+            for (int d = 0; d < ndays; d++) s += land[k];
+            v[k] = s / (double)ndays;
+        }
+        for (int k = 0; k < 7; k++) v[3 + k] = a.mon_acc[((size_t)m * 7 + k) * p.stride + x] / (double)ndays;
+    }
+}
+
+// extract_sub_ (extractsub.cpp:65-79): state vector of the region's cells minus the temporal mean field
+__global__ void __launch_bounds__(128) k_state_vector(const __grid_constant__ WgkParams p, const int m, const int kind, const int ndays,
+                                                      const int32_t *__restrict__ pos, const int ncells,
+                                                      const double *__restrict__ mean_field, double *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncells) return;
+    double v[10];
+    state_of_cell(p, pos[j], m, kind, ndays, v);
+    for (int k = 0; k < 10; k++) out[(size_t)j * 10 + k] = v[k] - (mean_field ? mean_field[(size_t)j * 10 + k] : 0.);
+}
+
+// enkf_wghmstate_ (enKF2wghmState.cpp:89-121, 440-471) followed by the restore of the next cycle's start
+// (daily.cpp:1896-1924, routing.cpp:851-882): the last day's state plus (analysis - prediction) with the
+// reference's limits, the snow bands rescaled by assimilated / predicted monthly snow, back to device units
+__global__ void __launch_bounds__(128) k_enkf_update(const __grid_constant__ WgkParams p, const int m, const int ndays,
+                                                     const int32_t *__restrict__ pos, const int ncells,
+                                                     const double *__restrict__ field, const double *__restrict__ prediction,
+                                                     const double *__restrict__ mean_field) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncells) return;
+    const WgkArrays &a = p.a;
+    const int x = pos[j];
+    const size_t i = (size_t)m * p.stride + x;
+    double w[10], mon[10];
+    state_of_cell(p, x, m, 1, ndays, w);
+    state_of_cell(p, x, m, 0, ndays, mon);
+    const double *fl = field + (size_t)j * 10, *pr = prediction + (size_t)j * 10, *mf = mean_field + (size_t)j * 10;
+    for (int k = 0; k < 10; k++) w[k] += (fl[k] - pr[k]);
+    if (w[0] < 0.) w[0] = 0.;
+    if (w[1] < 0.) w[1] = 0.;
+    if (w[1] > 1000.) w[1] = 1000.;
+    if (w[2] < 0.) w[2] = 0.;
+    if (w[4] < 0.) w[4] = 0.;
+    if (w[6] < 0.) w[6] = 0.;
+    if (w[7] < 0.) w[7] = 0.;
+    if (w[8] < 0.) w[8] = 0.;
+    // snow in elevation bands (:440-471), in the file's units (band * landAreaFrac / contfreq, integrateWGHM.cpp:830-836)
+    const double laf = laf_of(a, i), contf = a.contfreq[x];
+    const double snow_mean_before = mon[1];
+    const double snow_after = fl[1] + mf[1];
+    double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + x;
+    for (int e = 1; e < WGK_NBAND_K; e++) {
+        double sie = (laf == 0.) ? 0. : S[(size_t)e * p.stride] * laf / contf;
+        if (snow_mean_before == 0) sie = snow_after / 100;
+        else sie *= snow_after / snow_mean_before;
+        if (sie < 0.) sie = 0.;
+        if (sie > 1000.) sie = 1000.;
+        S[(size_t)e * p.stride] = (laf <= 0.) ? 0. : sie * contf / laf;  // daily.cpp:1904-1922
+    }
+    if (laf <= 0.) {
+        a.canopy[i] = 0.;
+        a.snow[i] = 0.;
+        a.soil[i] = 0.;
+    } else {
+        a.canopy[i] = w[0] * contf / laf;
+        a.snow[i] = w[1] * contf / laf;
+        a.soil[i] = w[2] * contf / laf;
+    }
+    const double denom = ((a.area[x] * (contf / C100)) / C1E6);
+    a.loc_lake_stor[i] = w[3] * denom;
+    a.loc_wetl_stor[i] = w[4] * denom;
+    a.glo_lake_stor[i] = w[5] * denom;
+    a.glo_wetl_stor[i] = w[6] * denom;
+    a.res_stor[i] = w[7] * denom;
+    a.river_stor[i] = w[8] * denom;
+    a.gw[i] = w[9] * denom;
 }
 
 }  // namespace wgk
