@@ -359,6 +359,74 @@ def test_identical_members_stay_identical_full_size():
     assert np.isfinite(s1) and s1 > 0 and abs(s1 - s0) < 0.5 * s0
 
 
+@pytest.mark.parametrize("ng", [1, 2, 33, 130])
+def test_tiny_worlds_all_forms(ng, monkeypatch):
+    """edge sizes: a single cell, fewer cells than a warp, tiles and levels that end inside a warp; every form
+    of the vertical kernel and both schedules against the oracle after 12 days (tolerance of DESIGN.md 6)"""
+    from oracle import synth_world as sw, wg_init, wgo
+    import watergap2_b200 as wg
+    w = sw.build_world(ng)
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    f = sw.forcing_month(w, 1901, 1)
+    o = wgo.Oracle(ng)
+    for k, v in ini.items():
+        if not k.startswith("_") and o.has(k):
+            o.set(k, v)
+    o.set_forcing_month(f)
+    for d in range(1, 13):
+        o.step_day(d, 0, d)
+    for form, sched in (("bands", "wavefront"), ("cells", "wavefront"), ("bands2", "wholeday")):
+        monkeypatch.setenv("WGK_VERTICAL_FORM", form)
+        monkeypatch.setenv("WGK_DAY_SCHEDULE", sched)
+        m = wg.Model(ng)
+        m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+        m.load(ini)
+        m.forcing_reserve(31)
+        m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+        m.step_days(1, 0, 1, 0, 5)
+        m.step_days(6, 0, 6, 5, 7)
+        for name in wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS:
+            assert_parity(name, o.field(name), m.get(name), max_flips=max(1, ng // 200))
+        assert abs(m.total_storage_km3() - o.total_storage_km3()) <= 1e-12 * abs(o.total_storage_km3()) + 1e-18
+
+
+def test_per_member_forcing(world3000):
+    """BASELINE config 4 layout: every member has its own forcing (perturbed precipitation and temperature);
+    each member must match an oracle run with that member's forcing"""
+    from oracle import synth_world as sw, wg_init, wgo
+    import watergap2_b200 as wg
+    w = world3000
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    base = sw.forcing_month(w, 1901, 1)
+    rng = np.random.default_rng(11)
+    forc = []
+    for mem in range(3):
+        f = {k: v.copy() for k, v in base.items()}
+        f["P"] = (f["P"] * np.exp(rng.normal(0., 0.1, f["P"].shape))).astype(np.float32)
+        f["T"] = (f["T"] + rng.normal(0., 1., f["T"].shape)).astype(np.float32)
+        forc.append(f)
+    m = wg.Model(w.ng, nmember=3)
+    m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+    m.load(ini)
+    m.forcing_reserve(31, per_member=True)
+    for mem, f in enumerate(forc):
+        m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"], member=mem)
+    m.step_days(1, 0, 1, 0, 10)
+    for mem, f in enumerate(forc):
+        o = wgo.Oracle(w.ng)
+        for k, v in ini.items():
+            if not k.startswith("_") and o.has(k):
+                o.set(k, v)
+        o.set_forcing_month(f)
+        for d in range(1, 11):
+            o.step_day(d, 0, d)
+        for name in wg_init.STATE_FIELDS + ["discharge", "surface_runoff"]:
+            assert_parity(name, o.field(name), m.get(name, mem), max_flips=max(1, w.ng // 200))
+    assert not np.array_equal(m.get("soil", 0), m.get("soil", 1))
+
+
 def test_error_behaviour(world3000):
     """invalid inputs are rejected with the reference's diagnostics instead of exit(1)"""
     import watergap2_b200 as wg

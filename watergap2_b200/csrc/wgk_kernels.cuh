@@ -1,23 +1,30 @@
 // wgk_kernels.cuh — sm_100a kernels of the WaterGAP2 daily hot path.
 //
-// FP64 structure-of-arrays, one thread per (member, cell); device cell order = routing order,
-// so every dependency level of the river network is one contiguous, coalesced index range.
+// FP64 structure-of-arrays; device cell order = routing order by dependency level (inside a level optionally
+// sorted by cell class), so every level of the river network is one contiguous, coalesced index range.
 //
-//   k_vertical      : dailyWaterBalanceClass::calcNewDay for all cells   (daily.cpp:94-1264, lai.cpp:152-306)
-//   k_route_local   : cell-parallel part of routingClass::routing that does not depend on
-//                     upstream cells: runoff split, groundwater of humid cells and inland
-//                     sinks, local lake, local wetland                   (routing.cpp:1878-2617)
-//   k_route_level   : one dependency level of the ordered cell loop, reduced to what depends
-//                     on upstream cells: inflow gather, global lake / reservoir / global
-//                     wetland / arid groundwater where present, river reach  (routing.cpp:2623-3545)
-//   k_route_tail    : the same for all remaining narrow levels inside ONE persistent CTA per
-//                     member, levels separated by __syncthreads() instead of kernel launches,
-//                     next level's inputs prefetched before the barrier
-//   k_route_post    : cell-parallel: river width / area fraction, surface-water-body fractions,
-//                     next-day land area fraction, updateLandAreaFrac   (routing.cpp:3546-3586,
-//                                                                          5034-5188, 5343-5352)
-//   k_forcing_pack  : [cell][31] float grids -> [slot][cell] float4 in routing order
-//   k_advance_day   : calendar on the device (so that one captured graph replays day after day)
+// timed path (wgk_step_days: one CUDA graph of (day, level) tasks)
+//   k_cells_pre_tpc / k_vertical_tpc   dailyWaterBalanceClass::calcNewDay (daily.cpp:94-1264, lai.cpp:152-306), one
+//                     thread per (member, cell), band columns staged by cp.async; k_cells_pre* adds the cell-parallel
+//                     part of routingClass::routing that does not depend on upstream cells: runoff split,
+//                     groundwater of humid cells and inland sinks, local lake, local wetland (routing.cpp:1878-2617)
+//   k_cells_pre<VCfg> / k_vertical<VCfg>   the same, CTA-cooperative and band-parallel (tile of 32 cells x NW warps)
+//   k_river_level     one dependency level of the ordered cell loop, reduced to what depends on upstream cells:
+//                     inflow gather, global lake / reservoir / global wetland / arid groundwater where present,
+//                     river reach (routing.cpp:2623-3545), then the post-pass of the same cells: river width /
+//                     area fraction, surface-water-body fractions, next-day land area fraction,
+//                     updateLandAreaFrac (routing.cpp:3546-3586, 5034-5188, 5343-5352)
+//   k_tail_chunk      the same for narrow levels inside ONE persistent CTA per member, levels separated by
+//                     __syncthreads() instead of kernel launches, next level's inputs prefetched before the barrier
+//   k_end_of_day      station discharge record
+// three-call class-shim path (wgk_vertical_day / wgk_routing_day) and wgk_profile_day
+//   k_route_local, k_route_level, k_route_tail, k_route_post, k_post_range
+// set-up and exchange
+//   k_derive_static, k_derive_member   quantities derived once from statics / parameters / uploaded state
+//   k_forcing_pack    [cell][31] float grids -> [slot][cell] float4 in device order
+//   k_fill_calendar   calendar of a multi-day call on the device (one graph replays for any start date)
+//   k_state_vector, k_enkf_update      EnKF state bridge (extractsub.cpp:65-79, enKF2wghmState.cpp:89-121, 440-471)
+//   k_total_storage   global storage in km3 (mass-balance check)
 //
 // Build with -fmad=false: the reference CPU build has no FMA contraction, and results are
 // compared at 1e-10 relative.  Expression shapes follow the reference line by line.
