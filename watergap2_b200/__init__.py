@@ -14,7 +14,7 @@ import numpy as np
 __all__ = ["Model", "WgkError", "lib", "LIB_PATH", "FIELD_DTYPES", "build", "cell_classes"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwgk.so")
+LIB_PATH = os.environ.get("WGK_LIB") or os.path.join(HERE, "libwgk.so")  # WGK_LIB: development override (kernel variants)
 NBAND, NLCT, NPARAM = 101, 18, 26
 FIELD_DTYPES = {"f64": np.float64, "f32": np.float32, "i32": np.int32, "i16": np.int16, "i8": np.int8}
 
