@@ -19,6 +19,8 @@ timeout 900 python bench.py --steps ${STEPS:-30} --warmup 3 > $OUT/${TAG}_bench_
 tail -c 400 $OUT/${TAG}_bench_m1.json
 timeout 600 python bench.py --steps 3 --warmup 3 --members 16 --no-cpu > $OUT/${TAG}_bench_m16.json 2> $OUT/${TAG}_bench_m16.err
 timeout 900 python bench.py --steps 2 --warmup 3 --members 128 --no-cpu > $OUT/${TAG}_bench_m128.json 2> $OUT/${TAG}_bench_m128.err
+timeout 900 python bench.py --steps 2 --warmup 3 --workload 5arcmin --no-cpu > $OUT/${TAG}_bench_5arcmin.json 2> $OUT/${TAG}_bench_5arcmin.err
+python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; tail -1 $OUT/${TAG}_smoke.log
 if [ -n "$REF_ARM" ]; then
   timeout 600 python bench.py --impl reference --steps 6 --warmup 3 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
 fi
