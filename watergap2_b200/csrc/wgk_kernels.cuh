@@ -1369,7 +1369,11 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
             if (prev > 0.) {
                 {
                     const double x = (prev / maxStorage);  // pow(x, 1.5) (:2440) as x * sqrt(x), <= 1 ulp apart
+                    #ifdef WGK_LIBM_POW
+                    outflow = kS * prev * pow(x, 1.5);
+#else
                     outflow = kS * prev * (x * sqrt(x));
+#endif
                 }
                 if (S <= 0.) outflow = 0;
                 else if (outflow > S) outflow = S;
@@ -1408,7 +1412,11 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
             if (S > 0.) {
                 {
                     const double x = (S / maxStorage);  // pow(x, 2.5) (:2580) as x * x * sqrt(x)
+                    #ifdef WGK_LIBM_POW
+                    outflow = kS * S * pow(x, 2.5);
+#else
                     outflow = kS * S * ((x * x) * sqrt(x));
+#endif
                 }
                 if (outflow > S) outflow = S;
             } else
