@@ -32,6 +32,10 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches_m16.csv \
     python tools/profile_run.py --members 16 --days 2 > $OUT/${TAG}_prof_m16.log 2>&1
 
+# the same pass over the bench command itself (first 1500 kernels: set-up, then ~13 simulated days of graph nodes)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches_bench.csv \
+    python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/${TAG}_bench_under_ncu.log 2>&1
+
 # full captures: first launch of each dominant kernel (= the widest level / whole grid)
 for K in k_cells_pre_tpc k_river_level k_tail_chunk k_vertical_tpc; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^$K\$" -c 1 -f -o $OUT/${TAG}_${K}_m1 \
