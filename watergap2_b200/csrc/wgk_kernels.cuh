@@ -85,6 +85,10 @@ constexpr ConstDiv C100{100., 0.01}, C1E6{1000000., 1e-6}, C1000{1000., 0.001}, 
 // canopy, and the loop itself reads shared memory.  Every thread copies and reads only its own
 // column, so no block-wide barrier is involved.
 constexpr int SNOW_CH = 10, SNOW_NCH = 10, VBLOCK = 128;
+#ifndef WGK_TPC_MINB
+#define WGK_TPC_MINB 4  // resident CTAs per SM the thread-per-cell kernels are compiled for (register cap 65536 / (128 * MINB));
+                        // 5 and 6 spill and measured 9 % / 14 % slower at one member on B200
+#endif
 struct SnowStage {
     double s[2][SNOW_CH][VBLOCK];
     int32_t e[2][SNOW_CH][VBLOCK];
@@ -2168,7 +2172,7 @@ __global__ void __launch_bounds__(C::THREADS, C::NW == 5 ? 6 : 12) k_vertical(co
 }
 
 // thread-per-cell forms of k_vertical and k_cells_pre
-__global__ void __launch_bounds__(VBLOCK) k_vertical_tpc(const __grid_constant__ WgkParams p, const int dayofs) {
+__global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_vertical_tpc(const __grid_constant__ WgkParams p, const int dayofs) {
     __shared__ SnowStage stage;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.ncell) return;
@@ -2176,7 +2180,7 @@ __global__ void __launch_bounds__(VBLOCK) k_vertical_tpc(const __grid_constant__
 }
 
 
-__global__ void __launch_bounds__(VBLOCK) k_cells_pre_tpc(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
+__global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_cells_pre_tpc(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
     __shared__ SnowStage stage;
     const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= end) return;
