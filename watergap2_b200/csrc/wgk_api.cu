@@ -878,6 +878,14 @@ static int forcing_before_step(wgk_ctx *c) {
 }
 // ... and remembers which slots it reads until it has finished
 static int forcing_after_step(wgk_ctx *c, int slot0, int ndays) {
+    for (size_t k = 0; k < c->slot_uses.size();) {  // forget the steps that have finished
+        if (cudaEventQuery(c->slot_uses[k].ev) == cudaSuccess) {
+            cudaEventDestroy(c->slot_uses[k].ev);
+            c->slot_uses.erase(c->slot_uses.begin() + k);
+        } else {
+            k++;
+        }
+    }
     wgk_ctx::SlotUse u;
     u.lo = slot0;
     u.n = ndays;
