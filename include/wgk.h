@@ -120,6 +120,11 @@ int wgk_get_device_order(const wgk_ctx *ctx, int32_t *rank_of_cell);
 int wgk_forcing_reserve(wgk_ctx *ctx, int nslots, int per_member);
 int wgk_set_forcing(wgk_ctx *ctx, int slot0, int ndays, int member, const float *prec, const float *temp,
                     const float *shortwave, const float *longwave, int stride);
+/* the same with the four buffers holding the BYTES of the reference's big-endian UNF0 files
+ * (GPREC_<year>_<month>.31.UNF0 ..., climate.cpp:100-123; e.g. the mmap'ed files): byte order and layout are
+ * converted on the device */
+int wgk_set_forcing_unf(wgk_ctx *ctx, int slot0, int ndays, int member, const void *prec, const void *temp,
+                        const void *shortwave, const void *longwave, int stride);
 
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* One call = what the day loop of integrateWGHM.cpp:755-798 does for all cells and members:

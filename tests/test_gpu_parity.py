@@ -427,6 +427,30 @@ def test_per_member_forcing(world3000):
     assert not np.array_equal(m.get("soil", 0), m.get("soil", 1))
 
 
+def test_forcing_from_big_endian_file_bytes(world3000):
+    """wgk_set_forcing_unf: the bytes of the reference's big-endian .31 files give the same device forcing (and run)
+    as the host-decoded grids"""
+    from oracle import synth_world as sw, wg_init
+    import watergap2_b200 as wg
+    ini = wg_init.derive(world3000)
+    topo = ini["_topology"]
+    f = sw.forcing_month(world3000, 1901, 1)
+    out = []
+    for raw in (False, True):
+        m = wg.Model(world3000.ng)
+        m.set_topology(topo["rout_order"], topo["outflow_cell"])
+        m.load(ini)
+        m.forcing_reserve(31)
+        if raw:
+            m.set_forcing_unf(0, 31, *[np.ascontiguousarray(f[k], ">f4").tobytes() for k in ("P", "T", "SW", "LW")])
+        else:
+            m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+        m.step_days(1, 0, 1, 0, 5)
+        out.append({k: m.get(k) for k in ("soil", "snow", "discharge", "canopy")})
+    for k in out[0]:
+        assert np.array_equal(out[0][k], out[1][k]), k
+
+
 def test_error_behaviour(world3000):
     """invalid inputs are rejected with the reference's diagnostics instead of exit(1)"""
     import watergap2_b200 as wg

@@ -78,6 +78,7 @@ def lib():
     L.wgk_set_stream.argtypes = [vp, vp]
     L.wgk_set_topology.argtypes = [vp, vp, vp]
     L.wgk_set_cell_classes.argtypes = [vp, vp]
+    L.wgk_set_forcing_unf.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, ci]
     L.wgk_month_begin.argtypes = [vp]
     L.wgk_state_vector.argtypes = [vp, ci, ci, vp, ci, vp, vp]
     L.wgk_enkf_update.argtypes = [vp, ci, vp, ci, vp, vp, vp]
@@ -235,6 +236,14 @@ class Model:
             assert x.size == self.ncell * stride
         self._ck(self._L.wgk_set_forcing(self._c, slot0, ndays, member, *[x.ctypes.data for x in arrs], stride))
         self._keep = arrs  # the copies are asynchronous: keep the host buffers alive
+
+    def set_forcing_unf(self, slot0, ndays, prec, temp, sw, lw, member=-1, stride=31):
+        """the four buffers are the raw bytes of the reference's big-endian [ncell][stride] float32 UNF0 files"""
+        arrs = [np.frombuffer(x, np.uint8) if not isinstance(x, np.ndarray) else x.view(np.uint8).ravel() for x in (prec, temp, sw, lw)]
+        for x in arrs:
+            assert x.size == self.ncell * stride * 4
+        self._ck(self._L.wgk_set_forcing_unf(self._c, slot0, ndays, member, *[x.ctypes.data for x in arrs], stride))
+        self._keep = arrs
 
     # -- hot path ---------------------------------------------------------------------------------
     def vertical_day(self, day, month, dom, slot):

@@ -816,8 +816,8 @@ int wgk_forcing_reserve(wgk_ctx *c, int nslots, int per_member) {
     return WGK_OK;
 }
 
-int wgk_set_forcing(wgk_ctx *c, int slot0, int ndays, int member, const float *prec, const float *temp,
-                    const float *sw, const float *lw, int stride) {
+static int set_forcing_impl(wgk_ctx *c, int slot0, int ndays, int member, const float *prec, const float *temp,
+                            const float *sw, const float *lw, int stride, bool big_endian) {
     if (!c || !prec || !temp || !sw || !lw || ndays <= 0 || stride < ndays) return WGK_ERR_ARG;
     if (!c->have_topology) return fail(c, WGK_ERR_STATE, "wgk_set_topology must precede wgk_set_forcing");
     if (!c->d_forcing) {
@@ -857,12 +857,23 @@ int wgk_set_forcing(wgk_ctx *c, int slot0, int ndays, int member, const float *p
     const size_t pitch = (size_t)F * c->stride;
     float4 *dst = c->d_forcing + (size_t)slot0 * pitch + (size_t)(c->forcing_per_member ? member : 0) * c->stride;
     dim3 block(128), grid((c->ncell + 127) / 128, std::min(ndays, 31));
-    wgk::k_forcing_pack<<<grid, block, 0, cs>>>(dst, dP, dT, dS, dL, c->d_cell_of_rank, c->ncell, c->stride, ndays, stride, pitch);
+    if (big_endian) wgk::k_forcing_pack<true><<<grid, block, 0, cs>>>(dst, dP, dT, dS, dL, c->d_cell_of_rank, c->ncell, ndays, stride, pitch);
+    else wgk::k_forcing_pack<false><<<grid, block, 0, cs>>>(dst, dP, dT, dS, dL, c->d_cell_of_rank, c->ncell, ndays, stride, pitch);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev_forcing, cs));
     c->forcing_pending = true;
     return WGK_OK;
+}
+
+int wgk_set_forcing(wgk_ctx *c, int slot0, int ndays, int member, const float *prec, const float *temp,
+                    const float *sw, const float *lw, int stride) {
+    return set_forcing_impl(c, slot0, ndays, member, prec, temp, sw, lw, stride, false);
+}
+
+int wgk_set_forcing_unf(wgk_ctx *c, int slot0, int ndays, int member, const void *prec, const void *temp,
+                        const void *sw, const void *lw, int stride) {
+    return set_forcing_impl(c, slot0, ndays, member, (const float *)prec, (const float *)temp, (const float *)sw, (const float *)lw, stride, true);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -2228,19 +2228,26 @@ __global__ void k_end_of_day(const __grid_constant__ WgkParams p, const int dayo
     }
 }
 
-// host grids [cell][stride] (reference order) staged on the device -> [slot][cell] float4 (routing order)
+// host grids [cell][stride] (reference order) staged on the device -> [slot][cell] float4 (device order).
+// SWAP: the staged words are the bytes of the reference's big-endian .31 / .365 UNF0 files as they lie on
+// disk (climate.cpp:100-123, gridio byte order), swapped here instead of on the host.
+template <bool SWAP>
 __global__ void k_forcing_pack(float4 *__restrict__ dst, const float *__restrict__ P, const float *__restrict__ T,
                                const float *__restrict__ SW, const float *__restrict__ LW,
-                               const int32_t *__restrict__ cell_of_rank, int ncell, int stride_cells, int ndays,
-                               int src_stride, size_t slot_pitch) {
+                               const int32_t *__restrict__ cell_of_rank, int ncell, int ndays, int src_stride, size_t slot_pitch) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= ncell) return;
     const int n = cell_of_rank[r];
+    auto word = [](const float *a, const size_t k) -> float {
+#ifndef WGK_EMU
+        if (SWAP) return __uint_as_float(__byte_perm(__float_as_uint(a[k]), 0, 0x0123));
+#endif
+        return a[k];
+    };
     for (int d = blockIdx.y; d < ndays; d += gridDim.y) {
         const size_t s = (size_t)n * src_stride + d;
-        dst[(size_t)d * slot_pitch + r] = make_float4(P[s], T[s], SW[s], LW[s]);
+        dst[(size_t)d * slot_pitch + r] = make_float4(word(P, s), word(T, s), word(SW, s), word(LW, s));
     }
-    (void)stride_cells;
 }
 
 // total water storage of one member (km3), block-reduced in a fixed order so that the value
