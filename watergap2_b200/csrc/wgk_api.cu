@@ -114,6 +114,17 @@ struct wgk_ctx {
     int32_t *d_gidx = nullptr;  // [ncell] index into the global-water-body scratch or -1
     double *d_gbody = nullptr;  // [nmember][ngbody][GB_N]
     int ngbody = 0;
+
+    // cell-owner schedule (k_days_owner): one launch per call, every thread owns one cell for all its days
+    int owner_mode = 0;         // 1 = WGK_DAY_SCHEDULE=owner (opt-in)
+    int owner_fits = -1;        // cached co-residency check (-1 unknown)
+    int owner_nwarps = 0;
+    int32_t *d_own_warp_begin = nullptr, *d_own_warp_end = nullptr, *d_own_cell_warp = nullptr, *d_own_abort = nullptr;
+    uint32_t *d_own_progress = nullptr;
+    unsigned long long *d_own_ring = nullptr;  // [QBUF_K][nmember][stride][2] tagged discharge entries
+    uint32_t owner_base = 0;                   // days stepped by k_days_owner so far (tag base)
+    int32_t *d_rec_head = nullptr, *d_rec_next = nullptr;
+    long long *d_own_timing = nullptr;  // WGK_OWNER_TIMING=1: per-warp cycle counts of the last call (development aid)
 };
 
 namespace {
@@ -381,6 +392,52 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
     return 0;
 }
 
+// cell-owner schedule: usable when every CTA of k_days_owner is resident at the same time (the threads wait for
+// each other inside the kernel), which the cooperative launch then guarantees
+bool owner_usable(wgk_ctx *c) {
+    if (c->owner_mode == 0 || c->owner_nwarps <= 0) return false;
+    if (c->owner_fits < 0) {
+        int nb = 0, sms = 0, coop = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        const size_t smem = sizeof(wgk::SnowStage) * (wgk::OWN_BLOCK / wgk::VBLOCK);
+        cudaFuncSetAttribute(wgk::k_days_owner, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wgk::k_days_owner, wgk::OWN_BLOCK, smem);
+        const long long ctas = (long long)((c->owner_nwarps + wgk::OWN_BLOCK / 32 - 1) / (wgk::OWN_BLOCK / 32)) * c->nmember;
+        c->owner_fits = (coop && ctas <= (long long)nb * sms) ? 1 : 0;
+    }
+    return c->owner_fits == 1;
+}
+int launch_owner(wgk_ctx *c, const WgkParams &p, int ndays) {
+    wgk::WgkOwner s{};
+    s.warp_begin = c->d_own_warp_begin;
+    s.warp_end = c->d_own_warp_end;
+    s.cell_warp = c->d_own_cell_warp;
+    s.progress = c->d_own_progress;
+    s.abort = c->d_own_abort;
+    s.rec_head = c->d_rec_head;
+    s.rec_next = c->d_rec_next;
+    s.nwarps = c->owner_nwarps;
+    if (getenv("WGK_OWNER_TIMING")) {
+        if (!c->d_own_timing) CU(cudaMalloc(&c->d_own_timing, sizeof(long long) * 4 * (size_t)c->nmember * c->owner_nwarps));
+        s.timing = c->d_own_timing;
+    }
+    if (!c->d_own_ring) {
+        const size_t bytes = sizeof(unsigned long long) * 2 * wgk::QBUF_K * (size_t)c->nmember * c->stride;
+        CU(cudaMalloc(&c->d_own_ring, bytes));
+        CU(cudaMemsetAsync(c->d_own_ring, 0, bytes, c->stream));
+    }
+    s.ring = c->d_own_ring;
+    s.base = c->owner_base;
+    c->owner_base += (uint32_t)ndays;
+    const dim3 grid((c->owner_nwarps + wgk::OWN_BLOCK / 32 - 1) / (wgk::OWN_BLOCK / 32), c->nmember);
+    void *args[] = {(void *)&p, (void *)&s, (void *)&ndays};
+    CU(cudaLaunchCooperativeKernel((void *)wgk::k_days_owner, grid, dim3(wgk::OWN_BLOCK), args,
+                                   sizeof(wgk::SnowStage) * (wgk::OWN_BLOCK / wgk::VBLOCK), c->stream));
+    c->launches += 1;
+    return WGK_OK;
+}
+
 // inflow-independent river constants and cell class flags, recomputed after any static or
 // parameter upload (never inside a graph capture)
 int ensure_derived(wgk_ctx *c) {
@@ -461,10 +518,13 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
         // and whole-grid kernels day after day avoid the partial waves of 57 small launches per day
         // (measured on B200, 0.5 degree grid, per member-day: 128 members wavefront 43.7 us, whole-day 41.6 us;
         // 32 members wavefront 45.5 us, whole-day 51.5 us).
-        const char *e = getenv("WGK_DAY_SCHEDULE");  // "wavefront" | "wholeday"
+        const char *e = getenv("WGK_DAY_SCHEDULE");  // "owner" | "wavefront" | "wholeday"
         if (e && !strcmp(e, "wavefront")) c->whole_day = false;
         else if (e && !strcmp(e, "wholeday")) c->whole_day = true;
         else c->whole_day = ((long long)nmember * ncell >= 6000000);
+        // "owner": one launch per call, a thread owns its cell for all days (k_days_owner); needs every cell-member
+        // co-resident (<= 75 776 on B200).  Opt-in: measured slower than the wavefront (113 vs 67 us per day, see the kernel).
+        c->owner_mode = (e && !strcmp(e, "owner")) ? 1 : 0;
     }
     if (c->opt.tail_threshold <= 0) {
         const char *e = getenv("WGK_TAIL_THRESHOLD");
@@ -517,6 +577,8 @@ void wgk_destroy(wgk_ctx *c) {
     cudaFree(c->d_level_off); cudaFree(c->d_member_pset); cudaFree(c->d_cal); cudaFree(c->d_forcing);
     cudaFree(c->d_gidx); cudaFree(c->d_gbody); cudaFree(c->d_cal_days); cudaFree(c->d_qbuf);
     cudaFree(c->d_fstage); cudaFree(c->d_record); cudaFree(c->d_record_cells); cudaFree(c->d_partial);
+    cudaFree(c->d_own_warp_begin); cudaFree(c->d_own_warp_end); cudaFree(c->d_own_cell_warp); cudaFree(c->d_own_progress);
+    cudaFree(c->d_own_abort); cudaFree(c->d_rec_head); cudaFree(c->d_rec_next); cudaFree(c->d_own_timing); cudaFree(c->d_own_ring);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -528,6 +590,14 @@ int wgk_synchronize(wgk_ctx *c) {
     if (!c) return WGK_ERR_ARG;
     CU(cudaStreamSynchronize(c->copy_stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->d_own_abort) {  // a hand-off wait of the cell-owner schedule timed out (never expected; not a hang)
+        int32_t ab = 0;
+        CU(cudaMemcpy(&ab, c->d_own_abort, sizeof ab, cudaMemcpyDeviceToHost));
+        if (ab) {
+            cudaMemset(c->d_own_abort, 0, sizeof ab);
+            return fail(c, WGK_ERR_CUDA, "cell-owner schedule aborted: a discharge hand-off was not published in time; the state is incomplete");
+        }
+    }
     return WGK_OK;
 }
 
@@ -640,6 +710,31 @@ int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downs
     CU(upload(c->d_up_idx, up_idx));
     CU(upload(c->d_down, down));
     CU(upload(c->d_level_off, c->level_off));
+    {   // cell-owner schedule: warps of <= 32 consecutive cells that never straddle a dependency level
+        std::vector<int32_t> wb, we, cw(std::max(1, ng), 0);
+        for (int l = 0; l < c->nlevels; l++)
+            for (int b = c->level_off[l]; b < c->level_off[l + 1]; b += 32) {
+                const int e = std::min(b + 32, c->level_off[l + 1]);
+                for (int x = b; x < e; x++) cw[x] = (int32_t)wb.size();
+                wb.push_back(b);
+                we.push_back(e);
+            }
+        c->owner_nwarps = (int)wb.size();
+        CU(upload(c->d_own_warp_begin, wb));
+        CU(upload(c->d_own_warp_end, we));
+        CU(upload(c->d_own_cell_warp, cw));
+        if (c->d_own_progress) cudaFree(c->d_own_progress);
+        c->d_own_progress = nullptr;
+        CU(cudaMalloc(&c->d_own_progress, sizeof(uint32_t) * (size_t)c->nmember * std::max(1, c->owner_nwarps)));
+        CU(cudaMemset(c->d_own_progress, 0, sizeof(uint32_t) * (size_t)c->nmember * std::max(1, c->owner_nwarps)));
+        if (c->d_own_ring) CU(cudaMemset(c->d_own_ring, 0, sizeof(unsigned long long) * 2 * wgk::QBUF_K * (size_t)c->nmember * c->stride));
+        c->owner_base = 0;
+        if (!c->d_own_abort) {
+            CU(cudaMalloc(&c->d_own_abort, sizeof(int32_t)));
+            CU(cudaMemset(c->d_own_abort, 0, sizeof(int32_t)));
+        }
+        c->owner_fits = -1;
+    }
     c->have_topology = true;
     drop_graph(c);
     return WGK_OK;
@@ -952,6 +1047,17 @@ int wgk_routing_day(wgk_ctx *c, int day, int month, int dom) {
     return publish_discharge(c, 0);
 }
 
+// development aid (not part of include/wgk.h): per-warp cycle counts of the last cell-owner call, [nwarps][4]
+// = {vertical + local routing, hand-off waits, river + release, post-pass}, and the first cell / level width of each warp
+extern "C" int wgk_debug_owner_timing(wgk_ctx *c, long long *out, int32_t *warp_begin, int max_warps) {
+    if (!c || !c->d_own_timing) return -1;
+    const int n = std::min(max_warps, c->owner_nwarps);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(out, c->d_own_timing, sizeof(long long) * 4 * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (warp_begin && cudaMemcpy(warp_begin, c->d_own_warp_begin, sizeof(int32_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return c->owner_nwarps;
+}
+
 int wgk_update_land_area_frac(wgk_ctx *c) {
     // routingClass::updateLandAreaFrac is fused into the routing post-pass (prev <- cur <- next
     // per cell); the entry point exists so that the three-call sequence of
@@ -971,7 +1077,14 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
     rc = forcing_before_step(c);
     if (rc) return rc;
     const WgkParams p = make_params(c);
-    if (c->opt.use_graph) {
+    if (c->owner_mode == 1 && !owner_usable(c))
+        return fail(c, WGK_ERR_STATE, "WGK_DAY_SCHEDULE=owner: %d warps x %d members are not co-resident on this GPU", c->owner_nwarps, c->nmember);
+    bool owner = false;
+    if ((c->opt.use_graph || c->owner_mode == 1) && owner_usable(c)) {
+        rc = launch_owner(c, p, ndays);
+        if (rc) return rc;
+        owner = true;  // the discharge field is written by the kernel itself
+    } else if (c->opt.use_graph) {
         auto it = c->graphs.find(ndays);
         if (it == c->graphs.end()) {
             cudaGraphExec_t ex;
@@ -998,8 +1111,10 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
         c->launches += c->whole_day ? enqueue_whole_days(c, p, ndays) : enqueue_wavefront_serial(c, p, ndays);
     }
     CU(cudaGetLastError());
-    rc = publish_discharge(c, ndays - 1);
-    if (rc) return rc;
+    if (!owner) {
+        rc = publish_discharge(c, ndays - 1);
+        if (rc) return rc;
+    }
     if (c->month_acc) c->month_days += ndays;
     return forcing_after_step(c, slot0, ndays);
 }
@@ -1105,8 +1220,12 @@ int wgk_record_cells(wgk_ctx *c, const int32_t *cells, int ncells, int max_days)
     CU(cudaStreamSynchronize(c->stream));
     if (c->d_record) cudaFree(c->d_record);
     if (c->d_record_cells) cudaFree(c->d_record_cells);
+    if (c->d_rec_head) cudaFree(c->d_rec_head);
+    if (c->d_rec_next) cudaFree(c->d_rec_next);
     c->d_record = nullptr;
     c->d_record_cells = nullptr;
+    c->d_rec_head = nullptr;
+    c->d_rec_next = nullptr;
     c->nrec = 0;
     c->record_max_days = 0;
     if (ncells > 0 && max_days > 0) {
@@ -1117,6 +1236,16 @@ int wgk_record_cells(wgk_ctx *c, const int32_t *cells, int ncells, int max_days)
         }
         CU(cudaMalloc(&c->d_record_cells, sizeof(int32_t) * ncells));
         CU(cudaMemcpy(c->d_record_cells, ranks.data(), sizeof(int32_t) * ncells, cudaMemcpyHostToDevice));
+        // the same list per cell, for the cell-owner schedule (a cell may be recorded more than once)
+        std::vector<int32_t> head(c->ncell, -1), next(ncells, -1);
+        for (int k = ncells - 1; k >= 0; k--) {
+            next[k] = head[ranks[k]];
+            head[ranks[k]] = k;
+        }
+        CU(cudaMalloc(&c->d_rec_head, sizeof(int32_t) * c->ncell));
+        CU(cudaMalloc(&c->d_rec_next, sizeof(int32_t) * ncells));
+        CU(cudaMemcpy(c->d_rec_head, head.data(), sizeof(int32_t) * c->ncell, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_rec_next, next.data(), sizeof(int32_t) * ncells, cudaMemcpyHostToDevice));
         const size_t n = (size_t)max_days * c->nmember * ncells;
         CU(cudaMalloc(&c->d_record, n * sizeof(double)));
         CU(cudaMemset(c->d_record, 0, n * sizeof(double)));

@@ -249,7 +249,7 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
     const WgkArrays &a = p.a;
     const size_t i = (size_t)m * p.stride + r;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x & (VBLOCK - 1);  // column of the (128-thread) staging block handed in by the kernel
     double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r + p.stride;
     const int32_t *__restrict__ E = a.s_elev32 + r + p.stride;
 
@@ -1561,7 +1561,7 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
                                                    double inflow, const int flags, const int day, const int month,
                                                    double &gwToRiver) {
     const WgkArrays &a = p.a;
-    const double *__restrict__ g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;
+    const double *g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;  // (no __restrict__: written earlier by the same thread in k_days_persistent)
     const double ek = g[GB_EKS], invk = g[GB_INVKS];
     double gwr_glolak = 0., gwr_res = 0., gwr_glowet = 0.;
     if (flags & FL_LAKE) {  // :2677-2720
@@ -1684,7 +1684,7 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
 // the sum of upstream discharges; writes discharge / storage and returns nothing
 __device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx &c, const int r, const int m, const size_t i,
                                             const size_t q, const double inflowUpstream, const int day, const int month,
-                                            double *__restrict__ qday) {
+                                            double *__restrict__ qday, double *qout = nullptr) {
     const WgkArrays &a = p.a;
     double inflow = c.inflow_local + inflowUpstream;  // :2623
     double gwToRiver = c.gw_to_river;
@@ -1727,6 +1727,7 @@ __device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx
     //  discharge grid, routing.cpp:4219-4221, and books it as evaporation, :3935-3937)
     const bool out = (c.flags & FL_LDD_OUT) != 0;
     qday[i] = out ? transportedVolume : 0.;
+    if (qout) *qout = out ? transportedVolume : 0.;
     a.cell_runoff[i] = out ? (transportedVolume - inflowUpstream) : (0. - inflowUpstream);
     a.river_stor[i] = Sr;
     a.river_evapo[i] = riverEvapo;
@@ -1866,7 +1867,7 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
     }
     if ((flags & FL_ACTIVE) && (flags & (FL_LAKE | FL_RES | FL_GLOWET))) {
         // evaporation reduction factors of the global water bodies (:2790-2802, 3068-3078, 3287-3296)
-        const double *__restrict__ g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;
+        const double *g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;  // (no __restrict__: written earlier by the same thread in k_days_persistent)
         const double xexp = (in.evaredex * 3.32193);
         if (flags & FL_LAKE) {
             const double maxStorage = g[GB_L_MAX];
@@ -2197,6 +2198,162 @@ __global__ void __launch_bounds__(256) k_tail_chunk(const __grid_constant__ WgkP
     sweep_levels(p, m, dayofs, level_lo, level_hi);
     for (int r = p.level_off[level_lo] + threadIdx.x; r < p.level_off[level_hi]; r += blockDim.x) route_post_cell(p, r, m);
 }
+
+#ifndef WGK_EMU
+// ----------------------------------------------------------------------------------------
+// Cell-owner schedule: ONE launch for all days of a call.  Every thread owns one cell for the whole
+// call and walks its days in order - vertical balance, local routing, river reach, post-pass - so the
+// cell's own day -> day recurrence needs no kernel boundary at all.  The only exchange between
+// threads is the river discharge handed to the downstream cell.  It travels through a ring of
+// QBUF_K days of 16-byte entries, each 8-byte half carrying 32 bits of the value and a 32-bit day tag:
+// an aligned 8-byte store is single-copy atomic, so a consumer that polls the entry until both tags
+// name the day it needs holds a complete value - no fence on either side (a release fence, MEMBAR.GPU,
+// measured ~50 us per warp and day here because it waits for the band stores of the whole SM; an
+// acquire load empties the SM's L1).  Back pressure for the reuse of a ring slot: a warp stores the
+// number of days it has consumed into its progress word, and a cell waits until the warp of its
+// downstream cell is less than QBUF_K days behind before it overwrites an entry.
+// Warps never straddle a dependency level (WgkOwner::warp_begin/end), so a lane never waits for its
+// own warp; every wait is on a strictly earlier (day, level), and all CTAs are co-resident
+// (cooperative launch), hence the schedule cannot deadlock.  A wait that exceeds WGK_SPIN_LIMIT cycles
+// raises the abort word and ends the kernel (reported by the host) instead of hanging the GPU.
+// The arithmetic is that of k_cells_pre_tpc + k_river_level: results are bit-identical to the
+// (day, level) wavefront (tests/test_gpu_parity.py::test_cell_owner_schedule_equals_wavefront).
+// MEASURED (B200, 0.5 degree grid, one member): 113 us per simulated day against 67 us of the
+// wavefront graph, so this schedule is opt-in (WGK_DAY_SCHEDULE=owner) and not the default.  The cell-day is
+// ~130 KB of SASS and the instruction cache holds 32 KB: warps that drift apart in the day loop wait for
+// instructions (ncu: no_instruction 47 % of the vertical step, the step itself 2x slower); the day barrier that
+// keeps an SM's warps in step (below) repairs that but couples 16 warps to the slowest hand-off among them.
+// ----------------------------------------------------------------------------------------
+struct WgkOwner {
+    const int32_t *warp_begin, *warp_end;  // [nwarps] device-order cell range of a warp (one level, <= 32 cells)
+    const int32_t *cell_warp;              // [ncell] warp that owns a cell
+    unsigned long long *ring;              // [QBUF_K][nmember][stride][2] tagged discharge entries
+    uint32_t *progress;                    // [nmember][nwarps] tag of the last day a warp has consumed
+    int32_t *abort;                        // set when a wait timed out
+    const int32_t *rec_head, *rec_next;    // station records of a cell: rec_head[cell] -> k, rec_next[k] -> k' (or -1)
+    long long *timing;                     // optional [nwarps][4] cycles of lane 0: vertical+local, waits, river+hand-off, post (tools/owner_timing.py)
+    uint32_t base;                         // tag of day offset d of this call = base + d + 1 (days stepped so far by this context)
+    int nwarps;
+};
+constexpr long long WGK_SPIN_LIMIT = 4000000000LL;  // ~2 s at 1.965 GHz
+
+// all polling goes to L2 (relaxed at GPU scope), never to the non-coherent L1
+__device__ __forceinline__ uint32_t ld_progress(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_progress(uint32_t *p, const uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void ring_put(unsigned long long *e, const double v, const uint32_t tag) {
+    const unsigned long long lo = ((unsigned long long)tag << 32) | (uint32_t)__double2loint(v);
+    const unsigned long long hi = ((unsigned long long)tag << 32) | (uint32_t)__double2hiint(v);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(e), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ bool ring_try(const unsigned long long *e, const uint32_t tag, double &v) {
+    unsigned long long lo, hi;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(e) : "memory");
+    v = __hiloint2double((int)(uint32_t)hi, (int)(uint32_t)lo);
+    return (uint32_t)(lo >> 32) == tag && (uint32_t)(hi >> 32) == tag;
+}
+// a wait gives up when the run was aborted by any thread or after WGK_SPIN_LIMIT cycles
+__device__ __forceinline__ bool spin_check(unsigned &it, const long long t0, int32_t *abort) {
+    if ((++it & 63u) != 0u) return true;
+    if (*(volatile int32_t *)abort) return false;
+    if (clock64() - t0 > WGK_SPIN_LIMIT) {
+        atomicExch(abort, 1);
+        return false;
+    }
+    return true;
+}
+__device__ __forceinline__ bool ring_get(const unsigned long long *e, const uint32_t tag, double &v, int32_t *abort) {
+    if (ring_try(e, tag, v)) return true;
+    const long long t0 = clock64();
+    unsigned it = 0;
+    while (!ring_try(e, tag, v))
+        if (!spin_check(it, t0, abort)) return false;
+    return true;
+}
+// tags are compared as wrapping 32-bit distances
+__device__ __forceinline__ bool wait_progress(const uint32_t *flag, const uint32_t target, int32_t *abort) {
+    if ((int32_t)(ld_progress(flag) - target) >= 0) return true;
+    const long long t0 = clock64();
+    unsigned it = 0;
+    while ((int32_t)(ld_progress(flag) - target) < 0)
+        if (!spin_check(it, t0, abort)) return false;
+    return true;
+}
+
+// CTAs of OWN_BLOCK threads, one per SM, with a CTA barrier at the start of every day: the 16 warps of an SM then walk
+// the ~130 KB of code of a cell-day in step and share its instruction fetches (the instruction cache holds 32 KB;
+// warps left to drift apart spent half of their vertical step waiting for instructions - ncu no_instruction 47 %).
+constexpr int OWN_BLOCK = 512;
+__global__ void __launch_bounds__(OWN_BLOCK, 1) k_days_owner(const __grid_constant__ WgkParams p, const __grid_constant__ WgkOwner s,
+                                                            const int ndays) {
+    extern __shared__ __align__(16) unsigned char own_smem[];
+    SnowStage *stage = reinterpret_cast<SnowStage *>(own_smem) + threadIdx.x / VBLOCK;
+    const int w = blockIdx.x * (OWN_BLOCK / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int r = w < s.nwarps ? s.warp_begin[w] + lane : 0;
+    const bool valid = w < s.nwarps && r < s.warp_end[w];  // lanes without a cell only take part in the barriers
+    const int m = blockIdx.y;
+    const size_t mb = (size_t)m * p.stride;
+    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    uint32_t *prog = s.progress + (size_t)m * s.nwarps;
+    const int up0 = valid ? p.up_off[r] : 0, up1 = valid ? p.up_off[r + 1] : 0;
+    const int dn = valid ? p.down[r] : -1;
+    const int dn_w = dn >= 0 ? s.cell_warp[dn] : -1;
+    const int rec0 = (valid && p.record && s.rec_head) ? s.rec_head[r] : -1;
+    long long tacc[4] = {0, 0, 0, 0}, tk = s.timing ? clock64() : 0;
+#define WGK_OWNER_TICK(k_) do { if (s.timing) { const long long t_ = clock64(); tacc[k_] += t_ - tk; tk = t_; } } while (0)
+    bool ok = true;
+    for (int d = 0; d < ndays; d++) {
+        if (__syncthreads_or(!ok)) return;  // day barrier; a timed-out wait ends the CTA (the others see the abort word)
+        if (!valid) continue;
+        {   // vertical balance + local routing of the day (k_cells_pre_tpc)
+            LocalIn li;
+            LocalFlux fx;
+            if (vertical_cell(p, r, m, p.cal_days[4 * d + 3], stage, &li, &fx)) local_compute(p, r, m, li, fx);
+            else route_local_cell(p, r, m);
+        }
+        // river reach + post-pass (k_river_level); everything that does not depend on upstream cells is loaded
+        // before the hand-off is awaited
+        const RiverCtx c = load_ctx(p, r, mb + r, q);
+        const PostIn in = post_load(p, r, m);
+        const uint32_t tag = s.base + (uint32_t)d + 1u;
+        unsigned long long *ring = s.ring + ((size_t)(d % QBUF_K) * p.nmember * p.stride + mb) * 2;
+        double Sr = c.prevR, qv = 0.;
+        WGK_OWNER_TICK(0);
+        if (c.flags & FL_ACTIVE) {
+            double inflowUpstream = 0.;  // in routing order (= order of the += at routing.cpp:3957)
+            for (int k = up0; k < up1 && ok; k++) {
+                double v;
+                ok = ring_get(ring + 2 * (size_t)p.up_idx[k], tag, v, s.abort);
+                inflowUpstream += v;
+            }
+            WGK_OWNER_TICK(1);
+            if (ok) Sr = route_river(p, c, r, m, mb + r, q, inflowUpstream, p.cal_days[4 * d], p.cal_days[4 * d + 1], p.a.discharge, &qv);
+        } else {
+            p.a.discharge[mb + r] = 0.;
+        }
+        // ring slot reuse: the downstream cell's warp must have consumed day d - QBUF_K
+        if (d >= QBUF_K && dn_w >= 0 && ok) ok = wait_progress(prog + dn_w, tag - (uint32_t)QBUF_K, s.abort);
+        if (ok) ring_put(ring + 2 * (size_t)r, qv, tag);
+        WGK_OWNER_TICK(2);
+        if (ok) route_post_compute(p, r, m, in, Sr);
+        if (rec0 >= 0 && d < p.record_max_days)
+            for (int k = rec0; k >= 0; k = s.rec_next[k]) p.record[((size_t)d * p.nmember + m) * p.nrec + k] = qv;
+        // every lane's gather of day d has returned (its values were used above): the warp has consumed day d
+        __syncwarp(__activemask());
+        if (lane == 0) st_progress(prog + w, tag);
+        WGK_OWNER_TICK(3);
+    }
+    if (s.timing && valid && lane == 0)
+        for (int k = 0; k < 4; k++) s.timing[((size_t)m * s.nwarps + w) * 4 + k] = tacc[k];
+#undef WGK_OWNER_TICK
+}
+#endif  // WGK_EMU
 
 // ----------------------------------------------------------------------------------------
 // calendar, forcing, diagnostics
