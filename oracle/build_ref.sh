@@ -35,7 +35,7 @@ fi
 FILES="additionalOutputInputFile calcWaterTemp calib_basins calib_param calibration clcl climate
  climateYear configFile daily geo globals glacierYear gw_frac initializeWGHM integrateWGHM lai land
  option permafrost random rout_prepare routing s_max snowInElevationFile timestring
- upstream_stations wghmStateFile"
+ upstream_stations wghmStateFile enKF2wghmState extractsub parameterJsonFile matrix"
 pids=()
 for f in $FILES; do
   if [ ! -f "$OBJ/$f.o" ] || [ "$SRC/$f.cpp" -nt "$OBJ/$f.o" ]; then

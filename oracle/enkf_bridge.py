@@ -9,8 +9,11 @@
   enkf_update()    enKF2wghmState.cpp:89-121 (last day += field - prediction, limits), :440-471 (snow bands) and the
                    restore of the next cycle (daily.cpp:1896-1924, routing.cpp:851-882)
 
-parity unpinned: enkf_wghmstate_ / extract_sub_ need the PDAF driver's files and cannot be run from the harness; the
-restatement follows the cited lines and pins the CUDA kernels (tests/test_enkf_bridge.py), nothing more.
+Pinned against the compiled reference: `ref_harness replay --enkf` (oracle/ref_harness.cpp) calls the reference's own
+extract_sub_, enkf_wghmstate_ and setStorages on January 1901 of the 1000-cell world; every function here is bit-identical
+to what they computed (tests/golden/ref_ng1000_enkf.npz, made by tests/golden/make_golden_enkf.py; checked by
+tests/test_enkf_bridge.py::test_restatement_bit_exact_vs_reference_golden).  Note enKF2wghmState.cpp:92-120 reads
+`field[count] - prediction[count++]` (unsequenced); g++ 13 -O2 evaluates both at the same index, which is what is restated.
 Only tests/ may import this module.
 """
 import numpy as np

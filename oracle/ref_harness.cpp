@@ -23,6 +23,14 @@
 // reference's own driver.
 //
 // Dump container ("WGD1"): a sequence of records
+//   replay ... --enkf DIR
+//       after the last simulated month: the reference's own PDAF exchange functions on the month just run -
+//       extract_sub_ (extractsub.cpp:17) packs the monthly-mean state vector of the cells listed in DIR/ids.txt
+//       minus the mean field DIR/meanfield.bin; the "analysis" is that vector plus DIR/perturb.bin;
+//       enkf_wghmstate_ (enKF2wghmState.cpp:17) applies it; then the restore of the next cycle
+//       (routingClass::setStorages, dailyWaterBalanceClass::setStorages, integrateWGHM.cpp:303/407).
+//       Dumped (day tag 9000): enkf_extract, enkf_field, enkf_prediction, enkf_lastday [n][10], enkf_snow_elev
+//       [n][101] and the restored in-memory state.
 //   char name[32]; int32 day (0 = static/initial, k = after k-th simulated day);
 //   char dtype[8] ("f64","f32","i32","i16","i8"); int64 count; raw little-endian data.
 
@@ -51,6 +59,8 @@
 #include "initializeWGHM.h"
 #include "integrateWGHM.h"
 #include "calib_param.h"
+#include "extractsub.h"
+#include "enKF2wghmState.h"
 #undef private
 #undef protected
 
@@ -214,6 +224,95 @@ static double now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+
+static std::vector<double> read_f64(const std::string &path) {
+    std::vector<double> v;
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) { perror(path.c_str()); exit(2); }
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f) / 8;
+    fseek(f, 0, SEEK_SET);
+    v.resize(n);
+    if (fread(v.data(), 8, n, f) != (size_t)n) { perror("read"); exit(2); }
+    fclose(f);
+    return v;
+}
+
+// The state exchange of one assimilation cycle through the reference's own functions (see the header comment).
+static void run_enkf(const std::string &dir, ConfigFile *&configFile, WghmStateFile *&wghmState, calibParamClass *&calParam,
+                     AdditionalOutputInputFile *&additionalOutIn, SnowInElevationFile *&snow, int year_, int month_) {
+    const std::string ids_file = dir + "/ids.txt";
+    std::vector<int> ids;
+    {
+        std::ifstream in(ids_file);
+        std::string line;
+        std::getline(in, line);
+        while (std::getline(in, line)) {
+            if (line.empty()) continue;
+            std::stringstream ss(line);
+            int id; double lo, la;
+            ss >> id >> lo >> la;
+            ids.push_back(id);
+        }
+    }
+    const long n = (long)ids.size();
+    std::vector<double> meanf = read_f64(dir + "/meanfield.bin"), pert = read_f64(dir + "/perturb.bin");
+    if ((long)meanf.size() != n * 10 || (long)pert.size() != n * 10) { fprintf(stderr, "enkf: input sizes\n"); exit(2); }
+    WghmStateFile *wghmMean = new WghmStateFile(ng, 1);
+    for (long i = 0; i < n; i++) {
+        Cell &c = wghmMean->cell(ids[i] - 1);
+        c.canopy(0) = meanf[i * 10 + 0]; c.snow(0) = meanf[i * 10 + 1]; c.soil(0) = meanf[i * 10 + 2];
+        c.locallake(0) = meanf[i * 10 + 3]; c.localwetland(0) = meanf[i * 10 + 4]; c.globallake(0) = meanf[i * 10 + 5];
+        c.globalwetland(0) = meanf[i * 10 + 6]; c.reservoir(0) = meanf[i * 10 + 7]; c.river(0) = meanf[i * 10 + 8];
+        c.groundwater(0) = meanf[i * 10 + 9];
+    }
+    long oy = 0, total_nr_calPar = 26, calpar_size = 0, ny = n * 10, step = 0, total_steps = 100, year = year_, month = month_;
+    double *output = nullptr;
+    extract_sub_(ids_file.c_str(), wghmState, output, &oy, calParam, &total_nr_calPar, &calpar_size, nullptr, "", wghmMean, nullptr);
+    put("enkf_extract", 9000, "f64", n * 10, output, 8);
+    std::vector<double> prediction(output, output + n * 10), field(n * 10);
+    for (long k = 0; k < n * 10; k++) field[k] = prediction[k] + pert[k];
+    delete[] output;
+    put("enkf_field", 9000, "f64", n * 10, field.data(), 8);
+    put("enkf_prediction", 9000, "f64", n * 10, prediction.data(), 8);
+    // monthly mean of every cell as the reference forms it (Cell::mean, wghmStateFile.cpp:711)
+    {
+        std::vector<double> mm((size_t)ng * 10);
+        for (int c = 0; c < ng; c++) {
+            Cell m = wghmState->cell(c).mean();
+            double v[10] = {m.canopy(0), m.snow(0), m.soil(0), m.locallake(0), m.localwetland(0), m.globallake(0),
+                            m.globalwetland(0), m.reservoir(0), m.river(0), m.groundwater(0)};
+            for (int k = 0; k < 10; k++) mm[(size_t)c * 10 + k] = v[k];
+        }
+        put("enkf_month_mean", 9000, "f64", (int64_t)ng * 10, mm.data(), 8);
+    }
+    configFile->outputmeanfile = dir + "/mean_001.txt";
+    configFile->outputlastdayfile = dir + "/lastday_001.txt";
+    configFile->outputsnowlastdayfile = dir + "/snowlastday_001.txt";
+    configFile->outputadditionalfile = "";
+    double *factor = nullptr;
+    WghmStateFile *wghmStateMean = nullptr;
+    const std::string s2 = dir + "/";
+    enkf_wghmstate_(ids_file.c_str(), field.data(), prediction.data(), configFile, wghmState, additionalOutIn, snow, &step, &total_steps,
+                    &year, &month, &ny, factor, wghmStateMean, s2.c_str(), calParam, &calpar_size, "", "", "", wghmMean, nullptr, &oy,
+                    &total_nr_calPar, nullptr, nullptr);
+    std::vector<double> last(n * 10), sie(n * 101);
+    for (long i = 0; i < n; i++) {
+        Cell &c = wghmState->cell(ids[i] - 1);
+        double v[10] = {c.canopy(0), c.snow(0), c.soil(0), c.locallake(0), c.localwetland(0), c.globallake(0),
+                        c.globalwetland(0), c.reservoir(0), c.river(0), c.groundwater(0)};
+        for (int k = 0; k < 10; k++) last[i * 10 + k] = v[k];
+        for (int e = 0; e < 101; e++) sie[i * 101 + e] = snow->snowInElevation(ids[i] - 1, e);
+    }
+    put("enkf_lastday", 9000, "f64", n * 10, last.data(), 8);
+    put("enkf_snow_elev", 9000, "f64", n * 101, sie.data(), 8);
+    // restore of the next cycle (integrateWGHM.cpp:303, 407)
+    routing.setStorages(*wghmState, *additionalOutIn);
+    dailyWaterBalance.setStorages(*wghmState, *snow, *additionalOutIn);
+    dump_state(9000, true);
+    delete wghmMean;
+}
+
 static int run_driver(const char *cfg) {
     std::string progName = "OL", path_mean;
     WghmStateFile *wghmState, *wghmMean;
@@ -235,7 +334,7 @@ static int run_replay(int argc, char **argv) {
     Range days, snowdays;
     int every = 0;
     bool time_only = false, deep_snow = false;
-    std::string final_prefix, day_times_file;
+    std::string final_prefix, day_times_file, enkf_dir;
     std::vector<double> day_times;
     for (int i = 4; i < argc; i++) {
         std::string a = argv[i];
@@ -246,6 +345,7 @@ static int run_replay(int argc, char **argv) {
         else if (a == "--time-only") time_only = true;
         else if (a == "--deep-snow") deep_snow = true;
         else if (a == "--day-times" && i + 1 < argc) day_times_file = argv[++i];
+        else if (a == "--enkf" && i + 1 < argc) enkf_dir = argv[++i];
     }
     if (!time_only && strcmp(dumpfile, "-") != 0) {
         g_dump = fopen(dumpfile, "wb");
@@ -407,6 +507,8 @@ static int run_replay(int argc, char **argv) {
                     wghmState->cell(n).soil(dim - 1) = dailyWaterBalance.G_soilWaterContent[n] * landAreaFrac / geo.G_contfreq[n];
                 }
             }
+            if (!enkf_dir.empty() && actual_year == end_year && month + 1 == end_month)
+                run_enkf(enkf_dir, configFile, wghmState, calParam, additionalOutIn, snow_in_elevation, actual_year, month + 1);
             if (!final_prefix.empty() && actual_year == end_year && month + 1 == end_month) {
                 wghmState->saveDay(final_prefix + "_state.txt", number_of_days_in_month[month] - 1);
                 additionalOutIn->save(final_prefix + "_additional.txt");
