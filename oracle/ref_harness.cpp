@@ -31,6 +31,13 @@
 //       (routingClass::setStorages, dailyWaterBalanceClass::setStorages, integrateWGHM.cpp:303/407).
 //       Dumped (day tag 9000): enkf_extract, enkf_field, enkf_prediction, enkf_lastday [n][10], enkf_snow_elev
 //       [n][101] and the restored in-memory state.
+//   ref_harness calib <dir>
+//       the calibration loop of integrate_wghm_ (integrateWGHM.cpp:1091-1116) around the reference's own
+//       calibGammaClass (calibration.cpp): init / setRunoff / setUpstInflow / setWaterUse / findNewGamma /
+//       writeCorrFactors / writeCalibStatus, with the model run replaced by a closed-form response of the annual
+//       station discharge to gamma read from <dir>/CALIB_IN.txt.  Runs inside <dir> (the class writes CALIBRATION.OUT,
+//       CALIBRATION.LOG, CALIBSTATUS.OUT, STAT_CORR_FACTOR.OUT and G_CORR_FACTOR.UNF0 into the working directory) and prints one
+//       "CALIB ..." line per findNewGamma call.
 //   char name[32]; int32 day (0 = static/initial, k = after k-th simulated day);
 //   char dtype[8] ("f64","f32","i32","i16","i8"); int64 count; raw little-endian data.
 
@@ -61,6 +68,8 @@
 #include "calib_param.h"
 #include "extractsub.h"
 #include "enKF2wghmState.h"
+#include "calibration.h"
+#include <unistd.h>
 #undef private
 #undef protected
 
@@ -313,6 +322,63 @@ static void run_enkf(const std::string &dir, ConfigFile *&configFile, WghmStateF
     delete wghmMean;
 }
 
+
+static int run_calib(const char *dir) {
+    if (chdir(dir) != 0) { perror(dir); return 2; }
+    FILE *f = fopen("CALIB_IN.txt", "r");
+    if (!f) { perror("CALIB_IN.txt"); return 2; }
+    int y0, y1, station;
+    double gamma0, s0, s1;
+    if (fscanf(f, "%d %d %lf %lf %lf %d", &y0, &y1, &gamma0, &s0, &s1, &station) != 6) return 2;
+    const int ny = y1 - y0 + 1;
+    std::vector<double> base(ny), inflow(ny), use(ny);
+    for (int i = 0; i < ny; i++)
+        if (fscanf(f, "%lf %lf %lf", &base[i], &inflow[i], &use[i]) != 3) return 2;
+    fclose(f);
+    options.evalStartYear = (short)y0;
+    options.end_year = (short)y1;
+    options.output_dir = ".";
+    {   // basin mask for createCorrectionGrid, native int16 [ng]
+        FILE *b = fopen("SBASIN.bin", "rb");
+        if (b) {
+            std::vector<short> sb(ng);
+            if (fread(sb.data(), 2, ng, b) == (size_t)ng)
+                for (int n = 0; n < ng; n++) G_sbasin[n] = sb[n];
+            fclose(b);
+        }
+    }
+    for (int n = 0; n < ng; n++) dailyWaterBalance.G_cellCorrFact[n] = 1.0;
+    calibGammaClass cg;
+    cg.calibStationNumber = (short)station;
+    cg.prepareFiles();
+    cg.init();
+    float gamma = (float)gamma0;
+    bool testRun = false;
+    for (int it = 0; it < 60; it++) {
+        for (int i = 0; i < ny; i++) {
+            // the "model run": annual discharge falls with gamma
+            cg.setRunoff(y0 + i, (float)(base[i] * (s0 + s1 / (1.0 + (double)gamma))));
+            cg.setWaterUse(y0 + i, (float)use[i]);
+            cg.setUpstInflow(y0 + i, (float)inflow[i]);
+        }
+        if (testRun) {
+            cg.writeCorrFactors(gamma, cg.cellCorrFactorInd);
+            cg.writeCalibStatus(cg.getCalibStatus());
+            printf("CALIB_END %.9g %d %d %.9g\n", (double)gamma, cg.cellCorrFactorInd, cg.getCalibStatus(), (double)cg.getCellCorrFactor());
+            break;
+        }
+        const float gamma_old = gamma;
+        gamma = cg.findNewGamma(gamma);
+        printf("CALIB %d %.9g %.9g %d %d %.9g %d\n", (int)cg.getCallCounter(), (double)gamma_old, (double)gamma, cg.gammaCond,
+               cg.getCalibStatus(), (double)cg.getCellCorrFactor(), cg.cellCorrFactorInd);
+        if (gamma < 0) {
+            testRun = true;
+            gamma = gamma_old;
+        }
+    }
+    return 0;
+}
+
 static int run_driver(const char *cfg) {
     std::string progName = "OL", path_mean;
     WghmStateFile *wghmState, *wghmMean;
@@ -534,6 +600,7 @@ static int run_replay(int argc, char **argv) {
 int main(int argc, char **argv) {
     if (argc >= 3 && std::string(argv[1]) == "driver") return run_driver(argv[2]);
     if (argc >= 4 && std::string(argv[1]) == "replay") return run_replay(argc, argv);
+    if (argc >= 3 && std::string(argv[1]) == "calib") return run_calib(argv[2]);
     fprintf(stderr, "usage: ref_harness driver <config> | replay <config> <dump|-> [--days A-B] [--every K] "
                     "[--snow-days A-B] [--final-state PREFIX] [--time-only] [--day-times FILE]\n");
     return 1;

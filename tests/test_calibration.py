@@ -53,3 +53,63 @@ def test_sweep_finds_the_generating_parameter_set(world3000):
     assert cal.best_member(crit, 0) == 2
     sims = [cal.annual_runoff_km3(m.get_record(62, k), 31)[:, 0].sum() for k in range(4)]
     assert sims[0] > sims[1] > sims[2] > sims[3]  # a larger gamma keeps more water in the soil
+
+
+# ---- calibGammaClass against the compiled reference (tests/golden/ref_calibration.json) --------------------------------
+def _golden_calibration():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "ref_calibration.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("scenario", ["bisection", "first_call_ok", "upper_limit_10pct_ok", "upper_limit_cfa", "lower_limit_cfa",
+                                      "lower_limit_10pct_ok", "start_at_upper_limit"])
+def test_gamma_search_equals_reference(scenario):
+    """GammaCalibration (the reference's bisection for gamma, its 1 % / 10 % criteria, CFA, correction grid and CFS) replays
+    the calibration loop of integrateWGHM.cpp:1091-1116 on the inputs the compiled reference was given: the gamma sequence and
+    the public state after every call are equal to the last printed digit, the CALIBRATION.OUT / STAT_CORR_FACTOR.OUT lines
+    are equal as text, the correction grid is equal as float32."""
+    from watergap2_b200.calibration import GammaCalibration
+    G = _golden_calibration()
+    sc = G["scenarios"][scenario]
+    y0, y1 = G["eval_start_year"], G["end_year"]
+    cal = GammaCalibration(y0, y1, G["station"])
+    yrs = [y for y in range(y0, y1 + 1) if y not in sc["skip_years"]]
+    cal.read_observed(yrs, [G["observed_m3s"][y - y0] for y in yrs])
+    gamma, test_run, k = np.float32(sc["gamma0"]), False, 0
+    ccf = np.ones(len(G["sbasin"]))
+    g9 = lambda x: "%.9g" % float(x)
+    for _ in range(60):
+        for i in range(y1 - y0 + 1):
+            cal.set_runoff(y0 + i, np.float32(G["base"][i] * (sc["s0"] + sc["s1"] / (1.0 + float(gamma)))))
+            cal.set_water_use(y0 + i, np.float32(G["water_use"][i]))
+            cal.set_upst_inflow(y0 + i, np.float32(G["inflow"][i]))
+        if test_run:
+            cfs, line = cal.write_corr_factors(gamma)
+            assert [g9(gamma), str(cal.cell_corr_factor_ind), str(cal.calib_status), g9(cal.cell_corr_factor)] == sc["end"]
+            assert line == sc["stat_corr_factor_out"][0]
+            assert [str(cal.calib_status)] == sc["calibstatus_out"]
+            break
+        gamma_old = gamma
+        gamma = cal.find_new_gamma(gamma)
+        ref = sc["calls"][k]
+        assert [str(cal.call_counter), g9(gamma_old), g9(gamma), str(cal.gamma_cond), str(cal.calib_status), g9(cal.cell_corr_factor),
+                str(cal.cell_corr_factor_ind)] == ref, (k, ref)
+        # CALIBRATION.OUT: column 13 (runoffGeneratedInBasin) is an uninitialised variable in the reference until CFA is computed
+        mine, theirs = cal.result_lines[k].split("\t"), sc["calibration_out"][k].split("\t")
+        if mine[12] == "?":
+            mine[12] = theirs[12]
+        assert mine == theirs, (k, mine, theirs)
+        from watergap2_b200.calibration import criteria
+        c = criteria(cal.measured, cal.sim_runoff)  # the sweep objectives are the same numbers
+        assert ["%g" % c["nse"], "%g" % c["sum_of_differences"], str(c["years"])] == [theirs[1], theirs[2], theirs[6]]
+        k += 1
+        if hasattr(cal, "correction_grid_due") and sc["corr_factor_grid"] is not None and gamma < 0:
+            ccf = cal.correction_grid(np.array(G["pot_cell_runoff"], np.float32), np.array(G["sbasin"], np.int16), ccf)
+        if gamma < 0:
+            test_run, gamma = True, gamma_old
+    assert k == len(sc["calls"]) and test_run
+    if sc["corr_factor_grid"] is not None:
+        assert np.array_equal(ccf.astype(np.float32), np.array(sc["corr_factor_grid"], np.float32))
+        assert (ccf == 0.5).any() or (ccf == 1.5).any() or np.ptp(ccf) > 0

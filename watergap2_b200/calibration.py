@@ -7,8 +7,11 @@ sets as members of one context (and the members sharded over the GPUs) a whole s
 records the daily discharge of the station cells on the device (wgk_record_cells), and the functions here turn
 those records into the reference's criteria for all parameter sets at once.
 
-parity unpinned: calibration.cpp needs the station / basin files of a calibration set-up and is not run by the
-harness; the formulas follow the cited lines.
+The gamma search itself (calibGammaClass: bisection, 1 % / 10 % criteria, CFA, correction grid, CFS) is GammaCalibration
+below.  Pinned against the compiled reference: `ref_harness calib` runs the reference's calibGammaClass in the calibration
+loop of integrate_wghm_ on seven scenarios (tests/golden/ref_calibration.json, tests/test_calibration.py); GammaCalibration
+reproduces its gamma sequences, CALIBRATION.OUT / STAT_CORR_FACTOR.OUT lines and G_CORR_FACTOR grid exactly, and criteria()
+gives the same Nash-Sutcliffe / sum-of-differences values.
 """
 import numpy as np
 
@@ -85,3 +88,198 @@ def gather_criteria(crit, group=None):
     parts = [None] * dist.get_world_size(group)
     dist.all_gather_object(parts, crit, group=group)
     return [c for p in parts for c in p]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The reference's gamma search itself (calibGammaClass, calibration.cpp:45-801), as host logic above the C ABI:
+# a calibration run of integrate_wghm_ (integrateWGHM.cpp:213-264, 967-972, 1091-1116) is
+#     cal = GammaCalibration(eval_start_year, end_year); cal.read_observed(...)
+#     loop: run the evaluation years on the GPU with gamma, cal.set_runoff / set_upst_inflow / set_water_use per year,
+#           gamma = cal.find_new_gamma(gamma)  until it returns -99, then one test run and cal.write_corr_factors(...)
+# Everything is single precision in the reference's operand order; the CALIBRATION.OUT / STAT_CORR_FACTOR.OUT lines
+# have the reference's layout.  Pinned against the compiled reference (`ref_harness calib`, tests/test_calibration.py,
+# golden tests/golden/ref_calibration.json).
+# ----------------------------------------------------------------------------------------------------------------
+_f = np.float32
+
+
+def _g(x):
+    """operator<< of a float / double in the default ostream format (%g, 6 significant digits)"""
+    return "%g" % float(x)
+
+
+class GammaCalibration:
+    GAMMA_UPPER, GAMMA_LOWER = _f(5.), _f(0.1)  # calibration.cpp:45-49
+
+    def __init__(self, eval_start_year, end_year, station_number=0):
+        self.y0, self.y1 = int(eval_start_year), int(end_year)
+        n = self.y1 - self.y0 + 1
+        self.years = [self.y0 + i for i in range(n)]
+        self.measured = np.full(n, -99, _f)        # calibGammaClass::init (:239-249)
+        self.sim_runoff = np.full(n, -99, _f)
+        self.sim_inflow = np.full(n, -99, _f)
+        self.sim_water_use = np.full(n, -99, _f)
+        self.station_number = int(station_number)
+        self.cell_corr_factor = _f(1.)
+        self.cell_corr_factor_ind = 1
+        self.gamma_cond = 0
+        self.calib_status = 0
+        # function-local statics of findNewGamma (:277-284)
+        self.call_counter = 0
+        self.gamma_low, self.gamma_high = _f(-99), _f(-99)
+        self.sum_of_differences_old = _f(0)
+        self.gamma_of_previous_run = _f(0)
+        self.result_lines, self.log = [], []
+        self.runoff_generated_in_basin = None
+
+    def read_observed(self, years, m3_per_s):
+        """RIVER.DAT: year, observed discharge in m3/s -> km3/year (readObservedData, :212-237)"""
+        for y, q in zip(years, m3_per_s):
+            self.measured[int(y) - self.y0] = measured_km3_per_year(_f(q))
+
+    def set_runoff(self, year, value):
+        self.sim_runoff[year - self.y0] = _f(value)
+
+    def set_upst_inflow(self, year, value):
+        self.sim_inflow[year - self.y0] = _f(value)
+
+    def set_water_use(self, year, value):
+        self.sim_water_use[year - self.y0] = _f(value)
+
+    def find_new_gamma(self, gamma_old):
+        """calibGammaClass::findNewGamma (:266-636) -> gamma of the next run, or -99 when the search has ended"""
+        gamma_old = _f(gamma_old)
+        self.call_counter += 1
+        cc = self.call_counter
+        UP, LO = self.GAMMA_UPPER, self.GAMMA_LOWER
+        sod, msum, isum, usum, rsum, n = _f(0), _f(0), _f(0), _f(0), _f(0), 0
+        for i in range(self.measured.size):  # :300-313
+            if self.measured[i] > -1:
+                n += 1
+                sod = _f(sod + _f(self.sim_runoff[i] - self.measured[i]))
+                msum = _f(msum + self.measured[i])
+                rsum = _f(rsum + self.sim_runoff[i])
+                isum = _f(isum + self.sim_inflow[i])
+                usum = _f(usum + self.sim_water_use[i])
+        avg = _f(msum / _f(n))
+        crit = abs(float(_f(sod / _f(_f(n) * avg))))
+        gamma = None  # the reference leaves `gamma` uninitialised on the paths that do not assign it
+        half = lambda: _f((float(_f(self.gamma_low + self.gamma_high))) / 2.0)
+        if crit < 0.01:  # the 1 % criterion, identical in all three branches (:317-330, 369-379, 452-462)
+            gamma, self.gamma_cond, self.calib_status = _f(-99), 1, 1
+        elif cc == 1:    # first call: go to a limit (:331-361)
+            if sod > 0:
+                if gamma_old >= UP:
+                    gamma = _f(-99)
+                else:
+                    self.gamma_low, gamma = gamma_old, UP
+            else:
+                if gamma_old <= LO:
+                    gamma = _f(-99)
+                else:
+                    self.gamma_high, gamma = gamma_old, LO
+        else:            # bisection (:380-446 second call, :463-526 later calls)
+            if sod > 0:
+                if gamma_old == UP:
+                    if cc == 2:
+                        gamma, self.gamma_high = gamma_old, UP
+                    else:
+                        gamma, self.gamma_cond = _f(-99), 2
+                elif gamma_old < UP:
+                    if self.gamma_high < 0:
+                        self.gamma_low, gamma = gamma_old, _f(float(gamma_old) * 2.0)
+                    else:
+                        self.gamma_low = gamma_old
+                        gamma = half()  # second call: guarded by `gamma != gammaUpperLimit` on an uninitialised gamma (:404)
+            else:
+                if gamma_old == LO:
+                    if cc == 2:
+                        gamma, self.gamma_low = gamma_old, LO
+                    else:
+                        gamma, self.gamma_cond = _f(-99), 2
+                elif gamma_old > LO:
+                    if self.gamma_low < 0:
+                        gamma, self.gamma_high = _f(float(gamma_old) / 2.0), gamma_old
+                    else:
+                        self.gamma_high = gamma_old
+                        gamma = half()
+        # Nash-Sutcliffe (:529-546)
+        if self.y1 - self.y0 > 0:
+            s1, s2 = _f(0), _f(0)
+            for i in range(self.measured.size):
+                if self.measured[i] > -1:
+                    s1 = _f(s1 + _f(_f(self.measured[i] - avg) * _f(self.measured[i] - avg)))
+                    s2 = _f(s2 + _f(_f(self.sim_runoff[i] - self.measured[i]) * _f(self.sim_runoff[i] - self.measured[i])))
+            nse = _f(_f(s1 - s2) / s1)
+        else:
+            nse = _f(-99)
+        # 10 % criterion at a limit (:551-574)
+        avg_adapt = avg
+        sim_avg = _f(rsum / _f(n))
+        for limit, factor, ok in ((UP, 1.1, lambda: sim_avg < avg_adapt), (LO, 0.9, lambda: sim_avg > avg_adapt)):
+            if gamma_old == limit and self.gamma_cond == 2:
+                avg_adapt = _f(float(avg) * factor)
+                if ok():
+                    self.calib_status = 2
+                else:
+                    self.cell_corr_factor_ind = 99
+        # CFA (:583-592)
+        if self.cell_corr_factor_ind == 99:
+            self.cell_corr_factor = _f(_f(avg_adapt + _f(_f(usum - isum) / _f(n))) / _f(_f(_f(rsum + usum) - isum) / _f(n)))
+            self.runoff_generated_in_basin = _f(_f(_f(rsum / _f(n)) + _f(usum / _f(n))) - _f(isum / _f(n)))
+        # CALIBRATION.OUT line (:594-607); column 13 is uninitialised in the reference unless CFA was computed
+        rgb = "?" if self.runoff_generated_in_basin is None else _g(self.runoff_generated_in_basin)
+        self.result_lines.append("\t".join([_g(gamma_old), _g(nse), _g(sod), _g(self.gamma_low), _g(self.gamma_high), _g(avg_adapt), str(n),
+                                            _g(_f(avg_adapt / sim_avg)), _g(_f(isum / _f(n))), _g(_f(usum / _f(n))), "0", _g(sim_avg), rgb,
+                                            _g(self.cell_corr_factor)]) + "\t")
+        if gamma is not None:
+            if gamma > 0 and float(gamma) < 0.99 * float(LO) and cc > 2:  # :609-613
+                gamma = _f(-99)
+            if gamma > 0 and sod != 0 and abs(float(_f(_f(self.sum_of_differences_old / sod) - _f(1)))) < 0.0001:  # :614-619
+                gamma = _f(-99)
+        self.sum_of_differences_old = sod
+        self.last = {"sim_avg": sim_avg, "avg_adapt": avg_adapt, "nse": nse, "sum_of_differences": sod, "years": n}
+        if gamma is not None and gamma < 0 and abs(float(_f(self.cell_corr_factor - _f(1)))) > 0.01:  # :623-627
+            self.calib_status = 3
+            self.correction_grid_due = (sim_avg, avg_adapt)  # createCorrectionGrid(evalStartYear, end_year, sim, measured)
+        self.gamma_of_previous_run = gamma_old
+        return gamma if gamma is not None else _f(np.nan)
+
+    def correction_grid(self, annual_pot_cell_runoff, sbasin, cell_corr_fact):
+        """createCorrectionGrid (:730-801): annual_pot_cell_runoff float32 [nyears][ng] (the G_POT_CELL_RUNOFF_<year> grids),
+        sbasin int16 [ng]; updates and returns cell_corr_fact [ng] (G_cellCorrFact) for the cells of the station's basin"""
+        sim, meas = self.correction_grid_due
+        a = np.asarray(annual_pot_cell_runoff, _f)
+        mean = np.zeros(a.shape[1], _f)
+        for y in range(a.shape[0]):
+            mean = (mean + a[y]).astype(_f)
+        mean = (mean / _f(a.shape[0])).astype(_f)
+        inb = np.asarray(sbasin) == self.station_number
+        tot = np.cumsum(np.abs(mean[inb]), dtype=_f)[-1] if inb.any() else _f(0)  # sequential single-precision sum, cell order
+        out = np.array(cell_corr_fact, np.float64, copy=True)
+        d = _f(sim - meas)
+        v = (_f(1) - (np.sign(mean[inb]).astype(_f) * d).astype(_f) / tot).astype(_f)
+        out[inb] = np.clip(v.astype(np.float64), 0.5, 1.5)
+        return out
+
+    def write_corr_factors(self, gamma, cell_corr_fact_ind=None):
+        """writeCorrFactors (:660-728): the station correction factor CFS -> (cfs, STAT_CORR_FACTOR.OUT data line)"""
+        ind = self.cell_corr_factor_ind if cell_corr_fact_ind is None else cell_corr_fact_ind
+        gamma = _f(gamma)
+        msum, rsum, n = _f(0), _f(0), 0
+        for i in range(self.measured.size):
+            if self.measured[i] > -1:
+                n += 1
+                msum = _f(msum + self.measured[i])
+                rsum = _f(rsum + self.sim_runoff[i])
+        if gamma == self.GAMMA_UPPER and ind == 99:
+            msum = _f(float(msum) * 1.1)
+        if gamma == self.GAMMA_LOWER and ind == 99:
+            msum = _f(float(msum) * 0.9)
+        cfs = _f(msum / rsum) if ind == 99 else _f(1.0)
+        if (1.0 < float(cfs) < 1.01) or (0.99 < float(cfs) < 1.0):
+            cfs = _f(1.0)
+        if cfs > 1.0 or cfs < 1.0:
+            self.calib_status = 4
+        line = "\t".join([_g(_f(msum / _f(n))), _g(_f(rsum / _f(n))), _g(self.gamma_of_previous_run), _g(self.cell_corr_factor), _g(cfs)])
+        return float(cfs), line
