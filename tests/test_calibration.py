@@ -55,6 +55,46 @@ def test_sweep_finds_the_generating_parameter_set(world3000):
     assert sims[0] > sims[1] > sims[2] > sims[3]  # a larger gamma keeps more water in the soil
 
 
+@pytest.mark.gpu
+def test_gamma_search_on_the_gpu_recovers_gamma(world3000):
+    """the reference's calibration procedure end to end: calibrate_gamma drives GPU runs of the evaluation 'years' with the
+    reference's bisection; observations generated with gamma = 0.3 in the station's basin are matched within the 1 % criterion"""
+    from oracle import synth_world as sw, wg_init
+    import watergap2_b200 as wg
+    w = world3000
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    station = int(np.argsort(-w.acc)[0])
+    basin = cal.upstream_basin(topo["outflow_cell"], station)
+    assert 10 < basin.sum() < w.ng
+    m = wg.Model(w.ng)
+    m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+    f = sw.forcing_month(w, 1901, 1)
+    m.forcing_reserve(31)
+    m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+    m.record_cells(np.array([station], np.int32), 93)
+    g0 = np.asarray(ini["gamma_hbv"], np.float64).copy()
+
+    def run_years(gamma):
+        m.load(ini)                       # every run starts from the same state (integrateWGHM.cpp:291-407)
+        g = g0.copy()
+        g[basin] = gamma
+        m.set("gamma_hbv", g)
+        m.step_days(1, 0, 1, 0, 93)       # three 31-day "years" on the January forcing
+        q = cal.annual_runoff_km3(m.get_record(93, 0), days_per_year=31)[:, 0]
+        return [(float(x), 0., 0.) for x in q]
+
+    truth = run_years(0.3)
+    c = cal.GammaCalibration(1901, 1903, station_number=1)
+    c.measured[:] = [np.float32(q) for q, _, _ in truth]
+    out = cal.calibrate_gamma(run_years, c, 2.0)
+    assert out["calib_status"] == 1 and out["cfa"] == 1.0 and out["cfs"] == 1.0 and 3 <= out["runs"] <= 25, out
+    assert c.last["years"] == 3 and abs(float(c.last["sum_of_differences"]) / sum(q for q, _, _ in truth)) < 0.01
+    again = run_years(out["gamma"])  # the run with the calibrated gamma meets the criterion
+    assert abs(sum(q for q, _, _ in again) - sum(q for q, _, _ in truth)) / sum(q for q, _, _ in truth) < 0.01
+    assert out["gamma"] < 2.0  # moved towards the generating value (a smaller gamma yields more runoff)
+
+
 # ---- calibGammaClass against the compiled reference (tests/golden/ref_calibration.json) --------------------------------
 def _golden_calibration():
     import json

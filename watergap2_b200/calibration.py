@@ -283,3 +283,41 @@ class GammaCalibration:
             self.calib_status = 4
         line = "\t".join([_g(_f(msum / _f(n))), _g(_f(rsum / _f(n))), _g(self.gamma_of_previous_run), _g(self.cell_corr_factor), _g(cfs)])
         return float(cfs), line
+
+
+def upstream_basin(downstream_cell, station_cell):
+    """bool [ncell]: the station cell and every cell draining into it (what G_sbasin == station marks, calib_basins.cpp);
+    downstream_cell holds 1-based cell numbers (G_OUTFLC), station_cell is 0-based"""
+    dc = np.asarray(downstream_cell, np.int64) - 1
+    inb = np.zeros(dc.size, bool)
+    inb[station_cell] = True
+    while True:
+        new = (dc >= 0) & inb[np.clip(dc, 0, None)] & ~inb
+        if not new.any():
+            return inb
+        inb |= new
+
+
+def calibrate_gamma(run_years, cal, gamma0, max_runs=60):
+    """The calibration loop of integrate_wghm_ (integrateWGHM.cpp:289, 967-972, 1091-1116) around GammaCalibration `cal`:
+    run_years(gamma) simulates the evaluation years with gamma in the station's basin and returns, per evaluation year,
+    (annual station discharge, satisfied water use, upstream-station inflow) in km3/year.  The search ends when
+    find_new_gamma returns -99; one more run with the last gamma (the reference's test run) fixes CFS.
+    -> dict(gamma, cfa, cfs, calib_status, runs, stat_corr_factor_line)"""
+    gamma, test_run, runs = np.float32(gamma0), False, 0
+    while runs < max_runs:
+        res = run_years(float(gamma))
+        runs += 1
+        for i, (q, use, inflow) in enumerate(res):
+            cal.set_runoff(cal.y0 + i, q)
+            cal.set_water_use(cal.y0 + i, use)
+            cal.set_upst_inflow(cal.y0 + i, inflow)
+        if test_run:
+            cfs, line = cal.write_corr_factors(gamma)
+            return {"gamma": float(gamma), "cfa": float(cal.cell_corr_factor), "cfs": cfs, "calib_status": cal.calib_status, "runs": runs,
+                    "stat_corr_factor_line": line}
+        gamma_old = gamma
+        gamma = cal.find_new_gamma(gamma)
+        if gamma < 0:
+            test_run, gamma = True, gamma_old
+    raise RuntimeError("calibrate_gamma: no termination within max_runs")
