@@ -525,7 +525,7 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
         else if (e && !strcmp(e, "wholeday")) c->whole_day = true;
         else c->whole_day = ((long long)nmember * ncell >= 6000000);
         // "owner": one launch per call, a thread owns its cell for all days (k_days_owner); needs every cell-member
-        // co-resident (<= 75 776 on B200).  Opt-in: measured slower than the wavefront (113 vs 67 us per day, see the kernel).
+        // co-resident (<= 75 776 on B200).  Opt-in: measured slower than the wavefront (93 vs 67 us per day, see the kernel).
         c->owner_mode = (e && !strcmp(e, "owner")) ? 1 : 0;
     }
     if (c->opt.tail_threshold <= 0) {

@@ -2218,11 +2218,12 @@ __global__ void __launch_bounds__(256) k_tail_chunk(const __grid_constant__ WgkP
 // raises the abort word and ends the kernel (reported by the host) instead of hanging the GPU.
 // The arithmetic is that of k_cells_pre_tpc + k_river_level: results are bit-identical to the
 // (day, level) wavefront (tests/test_gpu_parity.py::test_cell_owner_schedule_equals_wavefront).
-// MEASURED (B200, 0.5 degree grid, one member): 113 us per simulated day against 67 us of the
+// MEASURED (B200, 0.5 degree grid, one member): 93 us per simulated day against 67 us of the
 // wavefront graph, so this schedule is opt-in (WGK_DAY_SCHEDULE=owner) and not the default.  The cell-day is
 // ~130 KB of SASS and the instruction cache holds 32 KB: warps that drift apart in the day loop wait for
 // instructions (ncu: no_instruction 47 % of the vertical step, the step itself 2x slower); the day barrier that
-// keeps an SM's warps in step (below) repairs that but couples 16 warps to the slowest hand-off among them.
+// keeps a CTA's warps in step (below) repairs that but couples them to the slowest hand-off among them
+// (CTAs of 512 / 256 / 128 threads: 112 / 90 / 90 us per day; without any hand-off wait the barrier form runs at 63 us).
 // ----------------------------------------------------------------------------------------
 struct WgkOwner {
     const int32_t *warp_begin, *warp_end;  // [nwarps] device-order cell range of a warp (one level, <= 32 cells)
@@ -2285,11 +2286,14 @@ __device__ __forceinline__ bool wait_progress(const uint32_t *flag, const uint32
     return true;
 }
 
-// CTAs of OWN_BLOCK threads, one per SM, with a CTA barrier at the start of every day: the 16 warps of an SM then walk
+// CTAs of OWN_BLOCK threads with a CTA barrier at the start of every day: the warps of a CTA then walk
 // the ~130 KB of code of a cell-day in step and share its instruction fetches (the instruction cache holds 32 KB;
 // warps left to drift apart spent half of their vertical step waiting for instructions - ncu no_instruction 47 %).
-constexpr int OWN_BLOCK = 512;
-__global__ void __launch_bounds__(OWN_BLOCK, 1) k_days_owner(const __grid_constant__ WgkParams p, const __grid_constant__ WgkOwner s,
+#ifndef WGK_OWN_BLOCK
+#define WGK_OWN_BLOCK 256  // measured: 512 -> 112 us, 256 -> 90 us, 128 -> 90 us per simulated day (wavefront graph: 67 us)
+#endif
+constexpr int OWN_BLOCK = WGK_OWN_BLOCK;
+__global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) k_days_owner(const __grid_constant__ WgkParams p, const __grid_constant__ WgkOwner s,
                                                             const int ndays) {
     extern __shared__ __align__(16) unsigned char own_smem[];
     SnowStage *stage = reinterpret_cast<SnowStage *>(own_smem) + threadIdx.x / VBLOCK;
@@ -2297,6 +2301,7 @@ __global__ void __launch_bounds__(OWN_BLOCK, 1) k_days_owner(const __grid_consta
     const int lane = threadIdx.x & 31;
     const int r = w < s.nwarps ? s.warp_begin[w] + lane : 0;
     const bool valid = w < s.nwarps && r < s.warp_end[w];  // lanes without a cell only take part in the barriers
+    const unsigned mask = __ballot_sync(0xffffffffu, valid);  // the lanes of this warp that own a cell
     const int m = blockIdx.y;
     const size_t mb = (size_t)m * p.stride;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
@@ -2344,8 +2349,9 @@ __global__ void __launch_bounds__(OWN_BLOCK, 1) k_days_owner(const __grid_consta
         if (ok) route_post_compute(p, r, m, in, Sr);
         if (rec0 >= 0 && d < p.record_max_days)
             for (int k = rec0; k >= 0; k = s.rec_next[k]) p.record[((size_t)d * p.nmember + m) * p.nrec + k] = qv;
-        // every lane's gather of day d has returned (its values were used above): the warp has consumed day d
-        __syncwarp(__activemask());
+        // once EVERY lane's gather of day d has returned (its values were used above) the warp has consumed day d;
+        // the full mask matters: lanes still polling must not be overtaken by the producer of day d + QBUF_K
+        __syncwarp(mask);
         if (lane == 0) st_progress(prog + w, tag);
         WGK_OWNER_TICK(3);
     }
