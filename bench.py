@@ -225,6 +225,10 @@ def run_wgk(args):
                 "note": "algorithmic bytes count every cell's 100 snow bands (SURVEY 8d: 2099 B per cell-day); cells without snow and above "
                         "freezing skip the band loop, so the measured DRAM traffic is lower than the algorithmic bytes",
                 "share_of_day": round(prof["vertical"] / prof["day"], 4),
+                # the whole timed step against the same peak: all kernels of a simulated year, (2099 + 617) B per cell-day
+                # (per GPU)
+                "step_achieved": round((BYTES_VERTICAL + BYTES_ROUTING) * cell_days / world / (ms_max / 1e3) / 1e9, 1),
+                "step_frac": round((BYTES_VERTICAL + BYTES_ROUTING) * cell_days / world / (ms_max / 1e3) / 1e9 / peak, 4),
                 "dominant_by_time": dominant,
                 "routing": {"achieved": round(ach_r, 1), "frac": round(ach_r / peak, 4), "ms_per_day": round(t_rout, 5),
                             "levels": m.nlevels, "note": "latency-bound dependency chain at 1 member"},

@@ -224,7 +224,8 @@ def test_whole_day_schedule_equals_wavefront(world3000, monkeypatch):
 def test_cell_owner_schedule_equals_wavefront(world3000, monkeypatch):
     """k_days_owner (one launch per call, a thread owns its cell for all days, discharge handed downstream through
     acquire/release progress words) against the (day, level) wavefront graph: every field, the station record and the
-    monthly sums of the EnKF bridge bit for bit; 45 days in one call, i.e. more than the 32 discharge buffers in flight"""
+    monthly sums of the EnKF bridge bit for bit; 150 days in one call, i.e. several turns of the 32-day discharge ring
+    (fast headwater cells run into its back pressure)"""
     from oracle import synth_world as sw, wg_init
     import watergap2_b200 as wg
     ini = wg_init.derive(world3000)
@@ -242,14 +243,14 @@ def test_cell_owner_schedule_equals_wavefront(world3000, monkeypatch):
             f = sw.forcing_month(world3000, 1901, mon)
             m.set_forcing(31 * (mon - 1), 31, f["P"], f["T"], f["SW"], f["LW"])
         rec_cells = np.concatenate([np.arange(0, world3000.ng, 97), [97, 97, 0]]).astype(np.int32)  # duplicates allowed
-        m.record_cells(rec_cells, 62)
+        m.record_cells(rec_cells, 150)
         m.step_days(1, 0, 1, 0, 1)
         m.month_begin()
-        m.step_days(2, 0, 2, 1, 45)
+        m.step_days(2, 0, 2, 1, 150)
         m.synchronize()
         launches = m.kernel_launches
         out.append(({k: m.get(k, 1) for k in wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS + ["discharge", "snow_bands"]},
-                    m.get_record(45, 1), m.state_vector(cells, "month", member=1), launches))
+                    m.get_record(150, 1), m.state_vector(cells, "month", member=1), launches))
     assert out[1][3] < 50 < out[0][3]  # the owner schedule really ran: a handful of launches instead of thousands
     assert np.array_equal(out[0][1], out[1][1])
     assert np.array_equal(out[0][2], out[1][2])

@@ -19,6 +19,11 @@ timeout 900 python bench.py --steps ${STEPS:-30} --warmup 3 > $OUT/${TAG}_bench_
 tail -c 400 $OUT/${TAG}_bench_m1.json
 timeout 600 python bench.py --steps 3 --warmup 3 --members 16 --no-cpu > $OUT/${TAG}_bench_m16.json 2> $OUT/${TAG}_bench_m16.err
 timeout 900 python bench.py --steps 2 --warmup 3 --members 128 --no-cpu > $OUT/${TAG}_bench_m128.json 2> $OUT/${TAG}_bench_m128.err
+timeout 900 python bench.py --steps 2 --warmup 3 --members 256 --no-cpu > $OUT/${TAG}_bench_m256.json 2> $OUT/${TAG}_bench_m256.err
+if [ -n "$BIG" ]; then   # configs[2] at its size: 1024 parameter sets on one GPU (about 2.5 minutes)
+  timeout 900 python bench.py --steps 1 --warmup 3 --members 1024 --no-cpu > $OUT/${TAG}_bench_m1024.json 2> $OUT/${TAG}_bench_m1024.err
+fi
+WGK_DAY_SCHEDULE=owner timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu > $OUT/${TAG}_bench_owner.json 2> $OUT/${TAG}_bench_owner.err
 timeout 900 python bench.py --steps 2 --warmup 3 --workload 5arcmin --no-cpu > $OUT/${TAG}_bench_5arcmin.json 2> $OUT/${TAG}_bench_5arcmin.err
 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; tail -1 $OUT/${TAG}_smoke.log
 if [ -n "$REF_ARM" ]; then
@@ -48,4 +53,8 @@ done
 # the band-parallel tile form (small problems), forced on the full grid for comparison
 WGK_VERTICAL_FORM=bands timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^k_cells_pre$' -c 1 -f \
     -o $OUT/${TAG}_k_cells_pre_bands_m1 python tools/profile_run.py --members 1 --days 1 > $OUT/${TAG}_ncu_bands_m1.log 2>&1
+# the opt-in cell-owner schedule: one launch of 30 simulated days
+WGK_DAY_SCHEDULE=owner timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^k_days_owner$' -c 1 -f \
+    -o $OUT/${TAG}_k_days_owner_m1 python tools/profile_run.py --members 1 --days 30 --graph 1 > $OUT/${TAG}_ncu_owner_m1.log 2>&1
+WGK_DAY_SCHEDULE=owner timeout 300 python tools/owner_timing.py --days 365 > $OUT/${TAG}_owner_timing.log 2>&1
 ls -la $OUT | grep ${TAG}_ | tail -40
