@@ -289,25 +289,16 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
     return n;
 }
 
-// whole-grid kernels day after day (many members): vertical + local routing of all cells, the wide levels
-// one launch each, the narrow tail in one persistent CTA per member, in stream order
+// whole-grid kernels day after day (many members), in stream order: the vertical balance, the local routing, the wide
+// levels one launch each, the narrow tail in one persistent CTA per member, the post-pass.  These are the UNFUSED kernels of
+// the three-call path: with every kernel filling the GPU, the fused forms of the wavefront (vertical + local routing in
+// k_cells_pre*, river + post in k_river_level) lose more to their register count and code size than they save in re-loads
+// (measured on B200, 0.5 degree grid, us per member-day, fused / unfused: 64 members 44.5 / 39.1, 128 members 41.2 / 35.8).
 int enqueue_whole_days(wgk_ctx *c, const WgkParams &p, int ndays) {
     int n = 0;
-    dim3 block(128);
     for (int d = 0; d < ndays; d++) {
-        launch_cells_pre(c, p, d, 0, c->ncell);
-        n++;
-        for (int l = 0; l < c->tail_level0; l++) {
-            const int begin = c->level_off[l], end = c->level_off[l + 1];
-            wgk::k_river_level<<<dim3((end - begin + 127) / 128, c->nmember), block, 0, c->stream>>>(p, d, l);
-            n++;
-        }
-        if (c->tail_level0 < c->nlevels) {
-            const int begin = c->level_off[c->tail_level0];
-            wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, d, c->tail_level0, c->nlevels);
-            wgk::k_post_range<<<dim3((c->ncell - begin + 127) / 128, c->nmember), block, 0, c->stream>>>(p, begin, c->ncell);
-            n += 2;
-        }
+        n += enqueue_vertical(c, p, d);
+        n += enqueue_routing(c, p, d);
         if (c->d_record) {
             wgk::k_end_of_day<<<1, 256, 0, c->stream>>>(p, d);
             n++;
@@ -516,14 +507,15 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
                                               // (the 2-threads-per-cell form never beat both others)
     }
     {   // Schedule of a multi-day call.  Few members: the (day, level) wavefront, which hides the level-to-level
-        // latency chain of a day behind the following days.  Many members: every kernel fills the GPU on its own,
-        // and whole-grid kernels day after day avoid the partial waves of 57 small launches per day
-        // (measured on B200, 0.5 degree grid, per member-day: 128 members wavefront 43.7 us, whole-day 41.6 us;
-        // 32 members wavefront 45.5 us, whole-day 51.5 us).
+        // latency chain of a day behind the following days.  Many members: every kernel fills the GPU on its own, and
+        // whole-grid (unfused) kernels day after day win (measured on B200, 0.5 degree grid, us per member-day,
+        // wavefront / whole-day: 16 members 46.7 / 56.4, 32 members 45.4 / 44.4, 64 members 44.3 / 38.1,
+        // 128 members 43.6 / 35.1).  A single member on a 2.2 M-cell grid stays with the wavefront (475 vs 590 ms per
+        // year): its narrow levels are one CTA per member.
         const char *e = getenv("WGK_DAY_SCHEDULE");  // "owner" | "wavefront" | "wholeday"
         if (e && !strcmp(e, "wavefront")) c->whole_day = false;
         else if (e && !strcmp(e, "wholeday")) c->whole_day = true;
-        else c->whole_day = ((long long)nmember * ncell >= 6000000);
+        else c->whole_day = (nmember >= 32 && (long long)nmember * ncell >= 2000000);
         // "owner": one launch per call, a thread owns its cell for all days (k_days_owner); needs every cell-member
         // co-resident (<= 75 776 on B200).  Opt-in: measured slower than the wavefront (93 vs 67 us per day, see the kernel).
         c->owner_mode = (e && !strcmp(e, "owner")) ? 1 : 0;

@@ -17,8 +17,9 @@
 //   k_tail_chunk      the same for narrow levels inside ONE persistent CTA per member, levels separated by
 //                     __syncthreads() instead of kernel launches, next level's inputs prefetched before the barrier
 //   k_end_of_day      station discharge record
+//   k_days_owner      opt-in alternative to the graph: one launch per call, a thread owns its cell for all days
 // three-call class-shim path (wgk_vertical_day / wgk_routing_day) and wgk_profile_day
-//   k_route_local, k_route_level, k_route_tail, k_route_post, k_post_range
+//   k_route_local, k_route_level, k_route_tail, k_route_post   (also the whole-day schedule of many-member runs)
 // set-up and exchange
 //   k_derive_static, k_derive_member   quantities derived once from statics / parameters / uploaded state
 //   k_forcing_pack    [cell][31] float grids -> [slot][cell] float4 in device order
@@ -1954,13 +1955,6 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
 __device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r, const int m) {
     const PostIn in = post_load(p, r, m);
     route_post_compute(p, r, m, in, p.a.river_stor[(size_t)m * p.stride + r]);
-}
-
-// post-pass of the cells [begin, end) (whole-day schedule: the cells of the narrow tail levels)
-__global__ void __launch_bounds__(128) k_post_range(const __grid_constant__ WgkParams p, const int begin, const int end) {
-    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= end) return;
-    route_post_cell(p, r, blockIdx.y);
 }
 
 __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkParams p) {
