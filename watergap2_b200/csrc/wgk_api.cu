@@ -1305,6 +1305,26 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
 }
 
 #ifdef WGK_PHASE_TIMING
+// development builds only (-DWGK_PHASE_TIMING): read and reset the in-situ warp durations of the thread-per-cell task kernels
+int wgk_debug_insitu(wgk_ctx *c, unsigned long long out[8]) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyFromSymbol(out, wgk::g_insitu, sizeof(unsigned long long) * 8));
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyToSymbol(wgk::g_insitu, z, sizeof z));
+    return WGK_OK;
+}
+// development builds only: globaltimer stamps of the level-0 tasks of the last call, out[2][2][512]; reset = start stamps to ~0ull
+int wgk_debug_stamps(wgk_ctx *c, unsigned long long *out, int reset) {
+    CU(cudaStreamSynchronize(c->stream));
+    if (out) CU(cudaMemcpyFromSymbol(out, wgk::g_stamp, sizeof(unsigned long long) * 2 * 2 * 512));
+    if (reset) {
+        std::vector<unsigned long long> z(2 * 2 * 512, 0ull);
+        for (int k = 0; k < 2; k++)
+            for (int d = 0; d < 512; d++) z[(k * 2 + 0) * 512 + d] = ~0ull;
+        CU(cudaMemcpyToSymbol(wgk::g_stamp, z.data(), sizeof(unsigned long long) * z.size()));
+    }
+    return WGK_OK;
+}
 // development builds only (-DWGK_PHASE_TIMING): read and reset the per-phase cycle counters of the tile kernels
 int wgk_debug_phases(wgk_ctx *c, unsigned long long out[8]) {
     CU(cudaStreamSynchronize(c->stream));

@@ -1208,6 +1208,20 @@ __device__ __forceinline__ void v_tail(const WgkParams &p, VTile<C> &sm, const i
 
 // number of days of river discharge kept in flight (temporal wavefront over the level graph)
 constexpr int QBUF_K = 32;
+#ifdef WGK_PHASE_TIMING  // development aid: in-situ warp durations of the thread-per-cell task kernels (tools/insitu_timing.py)
+__device__ unsigned long long g_insitu[8];  // {V cycles, V warps, R cycles, R warps, V level-0 cycles, V level-0 warps, R level-0 cycles, R level-0 warps}
+__device__ unsigned long long g_stamp[2][2][512];  // level-0 tasks: [V, R][first warp start, last warp end][day offset], globaltimer ns
+__device__ __forceinline__ unsigned long long insitu_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define WGK_INSITU_STAMP(kind_, which_, day_) do { if ((threadIdx.x & 31) == 0 && (day_) < 512) { \
+    if (which_) atomicMax(&g_stamp[kind_][1][day_], insitu_ns()); else atomicMin(&g_stamp[kind_][0][day_], insitu_ns()); } } while (0)
+#define WGK_INSITU_BEGIN() const long long insitu_t0_ = clock64()
+#define WGK_INSITU_END(k_, l0_) do { if ((threadIdx.x & 31) == 0) { const unsigned long long dt_ = (unsigned long long)(clock64() - insitu_t0_); \
+    atomicAdd(&g_insitu[k_], dt_); atomicAdd(&g_insitu[(k_) + 1], 1ull); if (l0_) { atomicAdd(&g_insitu[(k_) + 4], dt_); atomicAdd(&g_insitu[(k_) + 5], 1ull); } } } while (0)
+#else
+#define WGK_INSITU_BEGIN() do { } while (0)
+#define WGK_INSITU_END(k_, l0_) do { } while (0)
+#define WGK_INSITU_STAMP(kind_, which_, day_) do { } while (0)
+#endif
 
 // ----------------------------------------------------------------------------------------
 // routing helpers
@@ -1980,6 +1994,8 @@ __global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ Wgk
     const int m = blockIdx.y;
     const size_t mb = (size_t)m * p.stride;
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    WGK_INSITU_BEGIN();
+    if (level == 0) WGK_INSITU_STAMP(1, 0, dayofs);
     const RiverCtx c = load_ctx(p, r, mb + r, q);
     const PostIn in = post_load(p, r, m);  // same round of loads as the river context
     double Sr = c.prevR;
@@ -1988,6 +2004,8 @@ __global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ Wgk
         Sr = route_river(p, c, r, m, mb + r, q, gather_upstream(p, c, mb, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
     }
     route_post_compute(p, r, m, in, Sr);
+    WGK_INSITU_END(2, level == 0);
+    if (level == 0) WGK_INSITU_STAMP(1, 1, dayofs);
 }
 
 // vertical balance (+ local routing) of the cells [begin, end), one CTA per tile of 32 cells; tiles
@@ -2179,10 +2197,14 @@ __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_cells_pre_tpc(const __
     __shared__ SnowStage stage;
     const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= end) return;
+    WGK_INSITU_BEGIN();
+    if (begin == 0) WGK_INSITU_STAMP(0, 0, dayofs);
     LocalIn li;
     LocalFlux fx;
     if (vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, blockIdx.y, li, fx);
     else route_local_cell(p, r, blockIdx.y);
+    WGK_INSITU_END(0, begin == 0);
+    if (begin == 0) WGK_INSITU_STAMP(0, 1, dayofs);
 }
 
 // narrow levels [level_lo, level_hi) of one day in one persistent CTA per member, then the
