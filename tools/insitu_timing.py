@@ -53,4 +53,25 @@ for use_graph in (1, 0):
     f = lambda x: f"{np.median(x) / 1e3:.1f}"
     print(f"  level 0, us (median over days): V kernel first-start -> last-end {f(ve - vs)}, V end -> R start {f(rs - ve)}, "
           f"R kernel {f(re - rs)}, R end -> next V start {f(vs[1:] - re[:-1])}, day period {f(vs[1:] - vs[:-1])}")
+    wd = np.zeros((4, 1024), np.uint32)
+    L.wgk_debug_warpdur.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.wgk_debug_warpdur(m._c, wd.ctypes.data)
+    nw = int((wd[0] > 0).sum())
+    d = wd[:, :nw].astype(np.float64) / 1965.0
+    print(f"  level-0 vertical warps ({nw}), us on days 100/101/200/300: mean {d.mean(1).round(1)}, p90 {np.percentile(d, 90, axis=1).round(1)}, max {d.max(1).round(1)}")
+    top = [set(np.argsort(-d[k])[:nw // 10]) for k in range(4)]
+    print(f"  slowest 10 % of the warps shared between days 100&101: {len(top[0] & top[1])}/{nw // 10}, 100&200: {len(top[0] & top[2])}/{nw // 10}, 100&300: {len(top[0] & top[3])}/{nw // 10}; "
+          f"correlation of warp durations 100~101 {np.corrcoef(d[0], d[1])[0, 1]:.2f}, 100~200 {np.corrcoef(d[0], d[2])[0, 1]:.2f}")
+    # what the slow warps are made of
+    rank = np.asarray(m.device_order())
+    cell_of_pos = np.argsort(rank)
+    cls = wg.cell_classes(ini)[cell_of_pos]
+    T = forcing[3]["T"][:, 9][cell_of_pos]  # day offset 100 = 10 April
+    snow = m.get("snow")[cell_of_pos]
+    for name, idx in (("slowest 5 %", np.argsort(-d[0])[:nw // 20]), ("fastest 50 %", np.argsort(d[0])[:nw // 2])):
+        cells = np.concatenate([np.arange(i * 32, min(i * 32 + 32, 22056)) for i in idx])
+        ncls = np.mean([len(set(cls[i * 32:i * 32 + 32].tolist())) for i in idx])
+        print(f"  {name}: mean duration {d[0][idx].mean():.1f} us, distinct classes per warp {ncls:.1f}, share of cells with a water body {np.mean((cls[cells] & 7) > 0):.2f}, "
+              f"arid {np.mean((cls[cells] & 8) > 0):.2f}, mean T {T[cells].mean():.1f}, T spread in warp {np.mean([np.ptp(T[i * 32:i * 32 + 32]) for i in idx]):.1f}, "
+              f"cells with snow (end of run) {np.mean(snow[cells] > 0):.2f}")
     m.close()

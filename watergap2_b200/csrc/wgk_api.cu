@@ -1313,6 +1313,12 @@ int wgk_debug_insitu(wgk_ctx *c, unsigned long long out[8]) {
     CU(cudaMemcpyToSymbol(wgk::g_insitu, z, sizeof z));
     return WGK_OK;
 }
+// development builds only: cycles of every level-0 vertical warp on four days, out[4][1024]
+int wgk_debug_warpdur(wgk_ctx *c, unsigned int *out) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyFromSymbol(out, wgk::g_warpdur, sizeof(unsigned int) * 4 * 1024));
+    return WGK_OK;
+}
 // development builds only: globaltimer stamps of the level-0 tasks of the last call, out[2][2][512]; reset = start stamps to ~0ull
 int wgk_debug_stamps(wgk_ctx *c, unsigned long long *out, int reset) {
     CU(cudaStreamSynchronize(c->stream));

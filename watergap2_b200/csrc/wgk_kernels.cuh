@@ -1214,6 +1214,10 @@ __device__ unsigned long long g_stamp[2][2][512];  // level-0 tasks: [V, R][firs
 __device__ __forceinline__ unsigned long long insitu_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define WGK_INSITU_STAMP(kind_, which_, day_) do { if ((threadIdx.x & 31) == 0 && (day_) < 512) { \
     if (which_) atomicMax(&g_stamp[kind_][1][day_], insitu_ns()); else atomicMin(&g_stamp[kind_][0][day_], insitu_ns()); } } while (0)
+__device__ unsigned int g_warpdur[4][1024];  // cycles of every level-0 vertical warp on day offsets 100, 101, 200, 300 (persistence of slow warps)
+#define WGK_INSITU_WARPDUR(day_) do { const int slot_ = (day_) == 100 ? 0 : (day_) == 101 ? 1 : (day_) == 200 ? 2 : (day_) == 300 ? 3 : -1; \
+    const int w_ = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; \
+    if (slot_ >= 0 && (threadIdx.x & 31) == 0 && w_ < 1024 && blockIdx.y == 0) g_warpdur[slot_][w_] = (unsigned int)(clock64() - insitu_t0_); } while (0)
 #define WGK_INSITU_BEGIN() const long long insitu_t0_ = clock64()
 #define WGK_INSITU_END(k_, l0_) do { if ((threadIdx.x & 31) == 0) { const unsigned long long dt_ = (unsigned long long)(clock64() - insitu_t0_); \
     atomicAdd(&g_insitu[k_], dt_); atomicAdd(&g_insitu[(k_) + 1], 1ull); if (l0_) { atomicAdd(&g_insitu[(k_) + 4], dt_); atomicAdd(&g_insitu[(k_) + 5], 1ull); } } } while (0)
@@ -1221,6 +1225,7 @@ __device__ __forceinline__ unsigned long long insitu_ns() { unsigned long long t
 #define WGK_INSITU_BEGIN() do { } while (0)
 #define WGK_INSITU_END(k_, l0_) do { } while (0)
 #define WGK_INSITU_STAMP(kind_, which_, day_) do { } while (0)
+#define WGK_INSITU_WARPDUR(day_) do { } while (0)
 #endif
 
 // ----------------------------------------------------------------------------------------
@@ -2204,6 +2209,7 @@ __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_cells_pre_tpc(const __
     if (vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, blockIdx.y, li, fx);
     else route_local_cell(p, r, blockIdx.y);
     WGK_INSITU_END(0, begin == 0);
+    if (begin == 0) WGK_INSITU_WARPDUR(dayofs);
     if (begin == 0) WGK_INSITU_STAMP(0, 1, dayofs);
 }
 
