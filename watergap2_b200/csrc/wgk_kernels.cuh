@@ -981,30 +981,19 @@ __device__ __forceinline__ void v_band(const WgkParams &p, VTile<C> &sm, const V
             const int ce = sm.cap_elev[lane];
             if (ce > 0 && e0 + j > sm.cap_first[lane]) temp_elev = T - ((double)(ce - sm.elev0[lane]) * grad);
         }
-        double sub = 0., eff = 0.;
-        if (temp_elev <= fz) {  // accumulation and sublimation (:982-999)
-            s += prec;
-            if (s > pet) {
-                sub = pet;
-                s -= pet;
-            } else {
-                sub = s;
-                s = 0.;
-            }
-        } else {
-            eff = prec;
-        }
-        double melt = 0.;
-        if (temp_elev > mt && !(s < 0.)) {  // melt (:1003-1019)
-            const double m_raw = ddf * (temp_elev - mt);
-            if (m_raw > s) {
-                melt = s;
-                s = 0.;
-            } else {
-                melt = m_raw;
-                s -= m_raw;
-            }
-        }
+        // accumulation and sublimation (:982-999), melt (:1003-1019) as selects, so that the unrolled bands interleave
+        // (see vertical_cell)
+        const bool cold = temp_elev <= fz;
+        const double s_in = s + prec;
+        const bool over = s_in > pet;
+        const double sub = cold ? (over ? pet : s_in) : 0.;
+        s = cold ? (over ? s_in - pet : 0.) : s;
+        const double eff = cold ? 0. : prec;
+        const bool mlt = temp_elev > mt && !(s < 0.);
+        const double m_raw = ddf * (temp_elev - mt);
+        const bool all = m_raw > s;
+        const double melt = mlt ? (all ? s : m_raw) : 0.;
+        s = mlt ? (all ? 0. : s - m_raw) : s;
         if (slab == 0 && k0 + j == 0) sm.temp1[lane] = temp_elev;
         sm.contrib[Q_CHG][k0 + j][lane] = s - s0;
         sm.contrib[Q_EFF][k0 + j][lane] = eff + melt;
