@@ -213,10 +213,13 @@ def test_whole_day_schedule_equals_wavefront(world3000, monkeypatch):
         m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
         m.record_cells(np.arange(0, world3000.ng, 97, dtype=np.int32), 31)
         m.step_days(1, 0, 1, 0, 12)
+        m.month_begin()  # the monthly sums of the EnKF bridge are formed by the post-pass of every schedule
         m.step_days(13, 0, 13, 12, 5)
-        out.append(({k: m.get(k, 1) for k in wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS}, m.get_record(5, 1)))
-    for fields, rec in out[1:]:
+        out.append(({k: m.get(k, 1) for k in wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS}, m.get_record(5, 1),
+                    m.state_vector(np.arange(0, world3000.ng, 13, dtype=np.int32), "month", member=1)))
+    for fields, rec, vec in out[1:]:
         assert np.array_equal(out[0][1], rec)
+        assert np.array_equal(out[0][2], vec)
         for k in out[0][0]:
             assert np.array_equal(out[0][0][k], fields[k]), k
 

@@ -85,7 +85,11 @@ constexpr ConstDiv C100{100., 0.01}, C1E6{1000000., 1e-6}, C1000{1000., 0.001}, 
 // that all loads of the band loop are in flight while the thread evaluates radiation / PET /
 // canopy, and the loop itself reads shared memory.  Every thread copies and reads only its own
 // column, so no block-wide barrier is involved.
-constexpr int SNOW_CH = 10, SNOW_NCH = 10, VBLOCK = 128;
+#ifndef WGK_SNOW_CH
+#define WGK_SNOW_CH 5  // bands per staged chunk (divides 100); measured with the select-form band loop, ms per simulated year
+                      // at 1 / 64 members: 10 bands 23.5 / 869, 5 bands 22.0 / 850, 4 bands 22.1 / 857, 2 bands 23.3 / 934
+#endif
+constexpr int SNOW_CH = WGK_SNOW_CH, SNOW_NCH = 100 / WGK_SNOW_CH, VBLOCK = 128;
 #ifndef WGK_TPC_MINB
 #define WGK_TPC_MINB 4  // resident CTAs per SM the thread-per-cell kernels are compiled for (register cap 65536 / (128 * MINB));
                         // 5 and 6 spill and measured 9 % / 14 % slower at one member on B200
