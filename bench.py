@@ -203,7 +203,7 @@ def run_wgk(args):
     ach_v = bytes_v / (prof["vertical"] * 1e-3) / 1e9
     t_rout = prof["route_local"] + prof["route_levels"] + prof["route_tail"] + prof["route_post"]
     ach_r = BYTES_ROUTING * ncell * args.members / (t_rout * 1e-3) / 1e9
-    form = os.environ.get("WGK_VERTICAL_FORM") or ("bands" if ncell * args.members < 49152 else "cells")
+    form = os.environ.get("WGK_VERTICAL_FORM") or ("bands" if ncell * args.members < 32768 else "cells")
     kname = {"cells": "k_vertical_tpc", "bands": "k_vertical<VCfgSmall>", "bands2": "k_vertical<VCfgMid>"}[form]
     dominant = kname if prof["vertical"] >= t_rout else "routing sweep (k_route_local + k_route_level x L + k_route_tail)"
     # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/traffic.json, written by

@@ -503,7 +503,8 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
         if (e && !strcmp(e, "bands")) c->form = 1;
         else if (e && !strcmp(e, "bands2")) c->form = 2;
         else if (e && !strcmp(e, "cells")) c->form = 0;
-        else c->form = work < 49152 ? 1 : 0;  // measured crossover on B200 between 40 000 and 67 420 cell-members
+        else c->form = work < 32768 ? 1 : 0;  // measured crossover on B200 at about 30 000 cell-members (20 000: 16.4 vs 17.1 ms per
+                                              // year, 30 000: 17.9 vs 18.0, 40 000: 19.6 vs 18.7)
                                               // (the 2-threads-per-cell form never beat both others)
     }
     {   // Schedule of a multi-day call.  Few members: the (day, level) wavefront, which hides the level-to-level
