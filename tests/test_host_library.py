@@ -126,3 +126,69 @@ def test_host_driver_matches_reference_driver(host, world3000, tmp_path):
     sb = np.loadtxt(out / "snow_lastday.txt", skiprows=1)
     es = np.abs(sa - sb) / np.maximum(np.maximum(np.abs(sa), np.abs(sb)), 1.0)
     assert (es <= 1e-10).mean() > 0.995 and es.max() < 1e-6
+
+
+@pytest.mark.parametrize("scenario", ["bisection", "first_call_ok", "upper_limit_10pct_ok", "upper_limit_cfa", "lower_limit_cfa",
+                                      "lower_limit_10pct_ok", "start_at_upper_limit"])
+def test_calibGammaClass_lookalike_equals_reference(host, scenario, tmp_path):
+    """csrc/host/wg_calibration.cpp (calibGammaClass with the reference's method names) in the calibration loop of
+    integrateWGHM.cpp:1091-1116, on the inputs the compiled reference was given (tests/golden/ref_calibration.json): the same gamma
+    sequence and public state after every call, the same CALIBRATION.OUT / STAT_CORR_FACTOR.OUT / CALIBSTATUS.OUT lines, the same
+    correction grid."""
+    import ctypes
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "ref_calibration.json")) as f:
+        G = json.load(f)
+    sc = G["scenarios"][scenario]
+    y0, y1 = G["eval_start_year"], G["end_year"]
+    L = host
+    L.wg_calib_create.restype = ctypes.c_void_p
+    L.wg_calib_create.argtypes = [ctypes.c_short, ctypes.c_short, ctypes.c_short, ctypes.c_char_p]
+    L.wg_calib_destroy.argtypes = [ctypes.c_void_p]
+    L.wg_calib_set_observed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float]
+    L.wg_calib_set_year.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float]
+    L.wg_calib_find_new_gamma.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+    L.wg_calib_finish.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_char_p, ctypes.c_size_t]
+    L.wg_calib_correction_grid.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    with open(tmp_path / "RIVER.DAT", "w") as f:  # read by init(), like the reference
+        for y in range(y0, y1 + 1):
+            if y not in sc["skip_years"]:
+                f.write(f"{y} {G['observed_m3s'][y - y0]:.2f}\n")
+    h = L.wg_calib_create(y0, y1, G["station"], str(tmp_path).encode())
+    g9 = lambda x: "%.9g" % float(x)
+    gamma, test_run, k = np.float32(sc["gamma0"]), False, 0
+    ccf = np.ones(len(G["sbasin"]))
+    line = ctypes.create_string_buffer(512)
+    out = np.zeros(6)
+    try:
+        for _ in range(60):
+            for i in range(y1 - y0 + 1):
+                L.wg_calib_set_year(h, y0 + i, np.float32(G["base"][i] * (sc["s0"] + sc["s1"] / (1.0 + float(gamma)))),
+                                    np.float32(G["water_use"][i]), np.float32(G["inflow"][i]))
+            if test_run:
+                status = L.wg_calib_finish(h, gamma, line, 512)
+                assert line.value.decode() == sc["stat_corr_factor_out"][0]
+                assert [g9(gamma), str(int(out[5])), str(status), g9(out[4])] == sc["end"]
+                break
+            gamma_old = gamma
+            L.wg_calib_find_new_gamma(h, gamma_old, out.ctypes.data, line, 512)
+            gamma = np.float32(out[0])
+            assert [str(int(out[1])), g9(gamma_old), g9(gamma), str(int(out[2])), str(int(out[3])), g9(out[4]), str(int(out[5]))] == sc["calls"][k], k
+            mine, theirs = line.value.decode().split("\t"), sc["calibration_out"][k].split("\t")
+            if mine[12] == "?":
+                mine[12] = theirs[12]
+            assert mine == theirs, (k, mine, theirs)
+            k += 1
+            pot = np.ascontiguousarray(G["pot_cell_runoff"], np.float32)
+            sb = np.ascontiguousarray(G["sbasin"], np.int16)
+            L.wg_calib_correction_grid(h, pot.ctypes.data, pot.shape[0], sb.ctypes.data, sb.size, ccf.ctypes.data)
+            if gamma < 0:
+                test_run, gamma = True, gamma_old
+        assert k == len(sc["calls"]) and test_run
+    finally:
+        L.wg_calib_destroy(h)
+    assert [ln.strip() for ln in open(tmp_path / "CALIBSTATUS.OUT")] == sc["calibstatus_out"]
+    ours = [ln.rstrip("\n").split("\t") for ln in open(tmp_path / "CALIBRATION.OUT")]
+    assert len(ours) == len(sc["calibration_out"])
+    if sc["corr_factor_grid"] is not None:
+        assert np.array_equal(ccf.astype(np.float32), np.array(sc["corr_factor_grid"], np.float32))
