@@ -192,3 +192,34 @@ def test_calibGammaClass_lookalike_equals_reference(host, scenario, tmp_path):
     assert len(ours) == len(sc["calibration_out"])
     if sc["corr_factor_grid"] is not None:
         assert np.array_equal(ccf.astype(np.float32), np.array(sc["corr_factor_grid"], np.float32))
+
+
+def test_pdaf_bridge_lookalikes_equal_reference(host, golden):
+    """csrc/host/wg_pdaf_bridge.cpp (extract_sub / enkf_wghmstate over the host WghmStateFile and SnowInElevationFile classes) on
+    the month the compiled reference's extract_sub_ / enkf_wghmstate_ were run on (tests/golden/ref_ng1000_enkf.npz): state vector,
+    updated last day and snow in elevation bit for bit"""
+    import ctypes
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ref_ng1000_enkf.npz"))
+    g = {k: z[k] for k in z.files}
+    cells = g["cells"]
+    n, nd = cells.size, 31
+    contf = golden["d0/contfreq"][cells]
+    laf = np.where(g["before/status_laf_next"] == 0, g["before/land_area_frac"], g["before/land_area_frac_next"])
+    daily = np.zeros((n, 10, nd))
+    for k, name in enumerate(("canopy", "snow", "soil")):  # the month-end value on every day (integrateWGHM.cpp:843-847)
+        daily[:, k, :] = (g["before/" + name] * laf / contf)[:, None]
+    daily[:, 3:, :] = np.transpose(g["routing_mm"], (2, 1, 0))  # [31][7][n] -> [n][7][31]
+    snow = np.where((laf == 0.)[:, None], 0., g["before/snow_bands"] * laf[:, None] / contf[:, None])  # :833-837, (S * laf) / contfreq
+    snow = np.ascontiguousarray(snow)
+    out = [np.zeros((n, 10)) for _ in range(4)]
+    mean_field, pert = np.ascontiguousarray(g["mean_field"]), np.ascontiguousarray(g["perturb"])
+    host.wg_host_pdaf_cycle.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 8
+    rc = host.wg_host_pdaf_cycle(n, nd, np.ascontiguousarray(daily).ctypes.data, snow.ctypes.data, mean_field.ctypes.data, pert.ctypes.data,
+                                 *[o.ctypes.data for o in out])
+    assert rc == 0
+    extract, field, lastday, mean_after = out
+    assert np.array_equal(extract, g["enkf_extract"])
+    assert np.array_equal(field, g["enkf_field"])
+    assert np.array_equal(lastday, g["enkf_lastday"])
+    assert np.array_equal(snow[:, 1:], g["enkf_snow_elev"][:, 1:])
+    assert (mean_after[:, 1] <= 1000.).all() and (mean_after[:, [0, 1, 2, 4, 6, 7, 8]] >= 0.).all()
