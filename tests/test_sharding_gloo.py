@@ -106,3 +106,36 @@ def test_ensemble_statistics_world_size_2(tmp_path):
     r = torch.load(out)
     assert torch.allclose(r["mean"], r["ref_mean"], rtol=0, atol=1e-14)
     assert torch.allclose(r["var"], r["ref_var"], rtol=1e-12, atol=1e-14)
+
+
+def _crit_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from watergap2_b200 import calibration as cal
+    from watergap2_b200.ensemble import shard_members
+    nsets, nyears = 7, 3
+    lo, cnt = shard_members(nsets, world, rank)
+    hi = lo + cnt
+    rng = np.random.default_rng(5)
+    measured = rng.uniform(5., 9., nyears).astype(np.float32)
+    sims = rng.uniform(4., 10., (nsets, nyears)).astype(np.float32)  # every rank draws the same table, keeps its shard
+    mine = [[cal.criteria(measured, sims[k])] for k in range(lo, hi)]
+    allc = cal.gather_criteria(mine)
+    if rank == 0:
+        ref = [[cal.criteria(measured, sims[k])] for k in range(nsets)]
+        torch.save({"ok": allc == ref, "n": len(allc), "best": cal.best_member(allc, 0),
+                    "best_ref": int(np.argmin([r[0]["rel_difference"] for r in ref]))}, out)
+    dist.destroy_process_group()
+
+
+def test_sweep_criteria_gather_world_size_2(tmp_path):
+    """the calibration sweep over ranks: every rank evaluates the criteria of its own parameter sets, gather_criteria returns the
+    list of all sets in set order (config 3 of BASELINE.json: 1024 sets sharded over the GPUs)"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "crit.pt")
+    mp.spawn(_crit_worker, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["ok"] and r["n"] == 7 and r["best"] == r["best_ref"]
