@@ -1,7 +1,7 @@
 // wg_calibration.h - host-side look-alike of the reference's calibGammaClass (calibration.h / calibration.cpp:45-801):
 // the search for the runoff coefficient gamma of one calibration basin, driven by integrate_wghm_
 // (integrateWGHM.cpp:213-264, 967-972, 1091-1116).  Same method names and argument meaning; the model runs between two
-// findNewGamma() calls are the caller's (GPU runs through the C ABI, see wg_host_calibrate in wg_model.h).
+// findNewGamma() calls are the caller's (GPU runs through the C ABI; watergap2_b200/calibration.py::calibrate_gamma is that loop).
 //
 // Everything is single precision in the reference's operand order.  Files: CALIBRATION.OUT and STAT_CORR_FACTOR.OUT
 // get the reference's data lines, CALIBSTATUS.OUT its status; the prose of CALIBRATION.LOG is reduced to one line per call.
