@@ -63,3 +63,11 @@ def test_product_does_not_import_oracle():
                 if re.search(r"(from|import)\s+oracle|oracle/|wg_oracle|libwgoracle", txt):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/wgk.h is the drop-in boundary: it must compile as C99 (no C++ or torch types) for cgo / JNI / ctypes / Fortran bindings"""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "wgk.h"\nint main(void) { return wgk_field_id("snow") == 12345; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
