@@ -223,3 +223,73 @@ def test_pdaf_bridge_lookalikes_equal_reference(host, golden):
     assert np.array_equal(lastday, g["enkf_lastday"])
     assert np.array_equal(snow[:, 1:], g["enkf_snow_elev"][:, 1:])
     assert (mean_after[:, 1] <= 1000.).all() and (mean_after[:, [0, 1, 2, 4, 6, 7, 8]] >= 0.).all()
+
+
+def test_calibGammaClass_cpp_equals_python_on_random_scenarios(host, tmp_path):
+    """the two host implementations of the reference's gamma search (C++ calibGammaClass, Python GammaCalibration), both pinned
+    on the seven golden scenarios, against each other on 150 random response curves, start values and observation gaps: the same
+    gamma sequence, state, CALIBRATION.OUT and STAT_CORR_FACTOR.OUT lines"""
+    import ctypes
+    from watergap2_b200.calibration import GammaCalibration
+    L = host
+    L.wg_calib_create.restype = ctypes.c_void_p
+    L.wg_calib_create.argtypes = [ctypes.c_short, ctypes.c_short, ctypes.c_short, ctypes.c_char_p]
+    L.wg_calib_destroy.argtypes = [ctypes.c_void_p]
+    L.wg_calib_set_observed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float]
+    L.wg_calib_set_year.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float]
+    L.wg_calib_find_new_gamma.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+    L.wg_calib_finish.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_char_p, ctypes.c_size_t]
+    rng = np.random.default_rng(11)
+    line = ctypes.create_string_buffer(512)
+    out = np.zeros(6)
+    endings = set()
+    for case in range(150):
+        y0 = 1980
+        ny = int(rng.integers(1, 9))
+        y1 = y0 + ny - 1
+        obs = rng.uniform(50., 3000., ny)
+        have = rng.random(ny) < 0.85
+        have[rng.integers(0, ny)] = True
+        base = obs * 0.031536 * rng.uniform(0.9, 1.1, ny)
+        inflow, use = rng.uniform(0., 5., ny), rng.uniform(0., 1., ny)
+        s0, s1 = rng.uniform(0.3, 1.4), rng.uniform(0., 1.5)
+        gamma = np.float32(rng.choice([0.1, 0.3, 1.0, 2.0, 5.0, float(rng.uniform(0.1, 5.))]))
+        d = tmp_path / f"c{case}"
+        d.mkdir()
+        h = L.wg_calib_create(y0, y1, 3, str(d).encode())
+        py = GammaCalibration(y0, y1, 3)
+        for i in range(ny):
+            if have[i]:
+                L.wg_calib_set_observed(h, y0 + i, np.float32(obs[i]))
+                py.read_observed([y0 + i], [np.float32(obs[i])])
+        test_run = False
+        try:
+            for _ in range(80):
+                for i in range(ny):
+                    q = np.float32(base[i] * (s0 + s1 / (1.0 + float(gamma))))
+                    L.wg_calib_set_year(h, y0 + i, q, np.float32(use[i]), np.float32(inflow[i]))
+                    py.set_runoff(y0 + i, q)
+                    py.set_water_use(y0 + i, np.float32(use[i]))
+                    py.set_upst_inflow(y0 + i, np.float32(inflow[i]))
+                if test_run:
+                    status = L.wg_calib_finish(h, gamma, line, 512)
+                    cfs, pline = py.write_corr_factors(gamma)
+                    assert line.value.decode() == pline and status == py.calib_status, case
+                    endings.add((status, py.cell_corr_factor_ind))
+                    break
+                L.wg_calib_find_new_gamma(h, gamma, out.ctypes.data, line, 512)
+                g_py = py.find_new_gamma(gamma)
+                g_c = np.float32(out[0])
+                assert (np.isnan(g_c) and np.isnan(g_py)) or g_c == g_py, (case, g_c, g_py)
+                assert (int(out[1]), int(out[2]), int(out[3]), np.float32(out[4]), int(out[5])) == \
+                    (py.call_counter, py.gamma_cond, py.calib_status, py.cell_corr_factor, py.cell_corr_factor_ind), case
+                assert line.value.decode() == py.result_lines[-1], (case, line.value.decode(), py.result_lines[-1])
+                if np.isnan(g_c):
+                    break
+                if g_c < 0:
+                    test_run = True
+                else:
+                    gamma = g_c
+        finally:
+            L.wg_calib_destroy(h)
+    assert len(endings) >= 3  # 1 % criterion, 10 % criterion and CFA / CFS endings all occur

@@ -210,7 +210,8 @@ class GammaCalibration:
                 if self.measured[i] > -1:
                     s1 = _f(s1 + _f(_f(self.measured[i] - avg) * _f(self.measured[i] - avg)))
                     s2 = _f(s2 + _f(_f(self.sim_runoff[i] - self.measured[i]) * _f(self.sim_runoff[i] - self.measured[i])))
-            nse = _f(_f(s1 - s2) / s1)
+            with np.errstate(all="ignore"):  # all observed years equal: 0 / 0 or x / 0, as in the reference
+                nse = _f(_f(s1 - s2) / s1)
         else:
             nse = _f(-99)
         # 10 % criterion at a limit (:551-574)
