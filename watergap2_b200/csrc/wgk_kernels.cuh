@@ -89,7 +89,10 @@ constexpr ConstDiv C100{100., 0.01}, C1E6{1000000., 1e-6}, C1000{1000., 0.001}, 
 #define WGK_SNOW_CH 5  // bands per staged chunk (divides 100); measured with the select-form band loop, ms per simulated year
                       // at 1 / 64 members: 10 bands 23.5 / 869, 5 bands 22.0 / 850, 4 bands 22.1 / 857, 2 bands 23.3 / 934
 #endif
-constexpr int SNOW_CH = WGK_SNOW_CH, SNOW_NCH = 100 / WGK_SNOW_CH, VBLOCK = 128;
+#ifndef WGK_VBLOCK
+#define WGK_VBLOCK 128  // threads per CTA of the thread-per-cell kernels
+#endif
+constexpr int SNOW_CH = WGK_SNOW_CH, SNOW_NCH = 100 / WGK_SNOW_CH, VBLOCK = WGK_VBLOCK;
 #ifndef WGK_TPC_MINB
 #define WGK_TPC_MINB 4  // resident CTAs per SM the thread-per-cell kernels are compiled for (register cap 65536 / (128 * MINB));
                         // 5 and 6 spill and measured 9 % / 14 % slower at one member on B200
