@@ -206,6 +206,13 @@ static void dump_state(int day, bool with_snow) {
     put_f64("fswb_laf_next", day, routing.G_fswbLandAreaFracNextTimestep);
     put_f64("river_area_frac_next", day, routing.G_riverAreaFracNextTimestep_Frac);
     put_i16("status_laf_next", day, routing.statusStarted_landAreaFracNextTimestep);
+    if (options.subtract_use > 0) {  // water-use state
+        put_f64("wu_total_unsatisfied", day, routing.G_totalUnsatisfiedUse);
+        put_f64("wu_daily_remaining", day, routing.G_dailyRemainingUse);
+        put_f64("wu_daily_nus", day, routing.G_dailydailyNUs);
+        put_f64("wu_daily_nug", day, routing.G_dailydailyNUg);
+        put_f64("wu_actual_use", day, routing.G_actualUse);
+    }
 }
 
 static void dump_fluxes(int day, int doy) {
@@ -482,6 +489,9 @@ static int run_replay(int argc, char **argv) {
     for (actual_year = start_year; actual_year <= end_year; actual_year += options.time_step) {
         dailyWaterBalance.annualInit();
         routing.annualInit(actual_year, configFile->startMonth, *additionalOutIn);
+        // net abstractions of the year (integrateWGHM.cpp:645-647; SURVEY 8f-4, not on the product path yet)
+        if (((2 == options.subtract_use) || (3 == options.subtract_use)) && (0 == options.time_series))
+            routing.dailyNUInit(options.water_use_dir, actual_year, *calParam);
         day = 0;
         if (actual_year == configFile->startYear)
             for (int m = 1; m < configFile->startMonth; m++) day += number_of_days_in_month[m - 1];
@@ -529,6 +539,7 @@ static int run_replay(int argc, char **argv) {
                                                      *wghmState, *additionalOutIn, *snow_in_elevation, readinstatus, *calParam);
                 }
                 double tb = now();
+                if ((2 == options.subtract_use) || (3 == options.subtract_use)) routing.calcNextDay_M(month);  // integrateWGHM.cpp:794-796
                 routing.routing(actual_year, day, month, day_in_month, last_day_in_month[month], *wghmState,
                                 *additionalOutIn, readinstatus, *calParam);
                 double tc = now();

@@ -467,7 +467,7 @@ def default_params(w, variant=0):
     return p
 
 
-def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_discharge=True, params=None):
+def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_discharge=True, params=None, water_use=False):
     inp = os.path.join(out, "input")
     clim = os.path.join(out, "climate")
     rout = os.path.join(out, "routing")
@@ -531,6 +531,22 @@ def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_
             fh.write("%d %.2f %.2f %.1f %d %.2f %.2f\n" % r)
     opts = list(OPTIONS)
     opts[2] = grid_store
+    if water_use:
+        # SURVEY 8f-4 (next row): net abstractions from surface water / groundwater, m3 per month (routing.cpp:884-977),
+        # subtract_use = 2 with the other use options at their canonical 0
+        opts[OPTION_NAMES.index("subtract_use")] = 2  # 2 (and 3) read the net abstractions, integrateWGHM.cpp:645
+        rng = np.random.default_rng([w.seed, 4711])
+        has = rng.random(ng) < 0.35
+        for y in range(years[0], years[1] + 1):
+            season = 1.0 + 0.5 * np.sin(np.arange(12) / 12.0 * 2 * np.pi)
+            nus = np.where(has[:, None], rng.gamma(0.6, 4.0e6, (ng, 1)) * season[None, :], 0.0)
+            nus[rng.random(ng) < 0.05] *= -0.3          # return flows exceed the withdrawal in a few cells
+            nug = np.where(has[:, None], rng.gamma(0.6, 2.0e6, (ng, 1)) * season[None, :], 0.0) * rng.choice([1.0, -0.2], (ng, 1), p=[0.9, 0.1])
+            write_unf(f"{inp}/G_NETUSE_SW_m3_{y}.12.UNF0", nus, "f4")
+            write_unf(f"{inp}/G_NETUSE_GW_m3_{y}.12.UNF0", nug, "f4")
+            write_unf(f"{inp}/G_IRRIG_WITHDRAWAL_USE_SW_m3_{y}.12.UNF0", np.abs(nus) * 1.6, "f4")
+            write_unf(f"{inp}/G_IRRIG_CONS_USE_SW_m3_{y}.12.UNF0", np.abs(nus) * 0.8, "f4")
+        write_unf(f"{inp}/G_FRACTRETURNGW_IRRIG.UNF0", rng.uniform(0.1, 0.6, ng), "f4")
     with open(f"{out}/OPTIONS.DAT", "w") as fh:
         for name, v in zip(OPTION_NAMES, opts):
             fh.write(f"# {name}\nValue: {v}\n")
@@ -569,6 +585,7 @@ input_dir {inp}
 output_dir {outd}
 climate_dir {clim}
 routing_dir {rout}
+water_use_dir {inp}
 end_of_head
 """)
 

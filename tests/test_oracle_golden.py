@@ -1,4 +1,6 @@
 """CPU: the oracle restatement against golden vectors dumped from the compiled reference."""
+import os
+
 import numpy as np
 import pytest
 
@@ -130,3 +132,15 @@ def test_empty_and_edge_inputs(oracle_lib):
     for k in ("soil", "canopy", "snow", "river_stor", "gw"):
         v = o.field(k)
         assert np.isfinite(v).all() and (v >= 0).all(), k
+
+
+def test_wateruse_fixture_is_a_different_run(golden):
+    """groundwork for SURVEY 8f-4 (water use; not on the product path yet): the fixture made by
+    tests/golden/make_golden_wateruse.py holds the compiled reference's run with net abstractions - same world and cold start as
+    ref_ng1000.npz, different storages from the first day on, use left unsatisfied, groundwater depleted below zero"""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_ng1000_wateruse.npz"))
+    assert int(z["ng"]) == int(golden["ng"]) and {1, 2, 31, 59} <= set(int(d) for d in z["days"])
+    assert np.array_equal(z["d1/canopy"], golden["d1/canopy"])              # the vertical balance does not see the water use
+    assert not np.array_equal(z["d59/river_stor"], golden["d59/river_stor"])
+    assert (z["d59/wu_total_unsatisfied"] > 0).sum() > 50 and (z["d59/gw"] < 0).any()
+    assert z["input/G_NETUSE_SW_m3_1901.12.UNF0"].size == 12 * int(z["ng"])
