@@ -144,3 +144,17 @@ def test_wateruse_fixture_is_a_different_run(golden):
     assert not np.array_equal(z["d59/river_stor"], golden["d59/river_stor"])
     assert (z["d59/wu_total_unsatisfied"] > 0).sum() > 50 and (z["d59/gw"] < 0).any()
     assert z["input/G_NETUSE_SW_m3_1901.12.UNF0"].size == 12 * int(z["ng"])
+
+
+def test_wateruse_daily_abstraction_bit_exact(golden):
+    """oracle/water_use.py::daily_net_abstraction against G_dailydailyNUs / G_dailydailyNUg of the compiled reference (January and
+    February; the groundwater value of the first day, before updateNetAbstractionGW adapts it)"""
+    from oracle import water_use as wu
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_ng1000_wateruse.npz"))
+    par = golden["d0/params"].reshape(26, -1)
+    sw_m3, gw_m3 = z["input/G_NETUSE_SW_m3_1901.12.UNF0"], z["input/G_NETUSE_GW_m3_1901.12.UNF0"]
+    assert np.array_equal(wu.daily_net_abstraction(sw_m3, par[23], 0), z["d1/wu_daily_nus"])
+    assert np.array_equal(wu.daily_net_abstraction(sw_m3, par[23], 0), z["d31/wu_daily_nus"])
+    assert np.array_equal(wu.daily_net_abstraction(sw_m3, par[23], 1), z["d59/wu_daily_nus"])
+    assert np.array_equal(wu.daily_net_abstraction(gw_m3, par[24], 0), z["d1/wu_daily_nug"])
+    assert (z["d1/wu_daily_nus"] != 0).sum() > 100
