@@ -38,6 +38,12 @@
 //       station discharge to gamma read from <dir>/CALIB_IN.txt.  Runs inside <dir> (the class writes CALIBRATION.OUT,
 //       CALIBRATION.LOG, CALIBSTATUS.OUT, STAT_CORR_FACTOR.OUT and G_CORR_FACTOR.UNF0 into the working directory) and prints one
 //       "CALIB ..." line per findNewGamma call.
+//   ref_harness wu_unit <in.f64> <out.f64>
+//       calls the reference's routingClass::updateNetAbstractionGW (routing.cpp:5503-5572) cell by cell on seeded member
+//       arrays: in = [8][ng] doubles (dailyRemainingUse, withdrawalIrrigFromSwb, consumptiveUseIrrigFromSwb, fractreturngw_irrig,
+//       unsatisfiedNAsFromIrrig, unsatisfiedNAsFromOtherSectors, reducedReturnFlow, dailydailyNUg), out = [6][ng] (returned NAg,
+//       then the five arrays the function updates: dailyRemainingUse, unsatisfiedNAsFromIrrig, unsatisfiedNAsFromOtherSectors,
+//       reducedReturnFlow, dailydailyNUg).  Groundwork for SURVEY 8f-4.
 //   char name[32]; int32 day (0 = static/initial, k = after k-th simulated day);
 //   char dtype[8] ("f64","f32","i32","i16","i8"); int64 count; raw little-endian data.
 
@@ -386,6 +392,36 @@ static int run_calib(const char *dir) {
     return 0;
 }
 
+
+static int run_wu_unit(const char *in, const char *out) {
+    std::vector<double> v = read_f64(in);
+    if ((long)v.size() != 8L * ng) { fprintf(stderr, "wu_unit: expected 8 x %d doubles\n", (int)ng); return 2; }
+    for (int n = 0; n < ng; n++) {
+        routing.G_dailyRemainingUse[n] = v[0 * (size_t)ng + n];
+        routing.G_withdrawalIrrigFromSwb[n] = v[1 * (size_t)ng + n];
+        routing.G_consumptiveUseIrrigFromSwb[n] = v[2 * (size_t)ng + n];
+        routing.G_fractreturngw_irrig[n] = v[3 * (size_t)ng + n];
+        routing.G_unsatisfiedNAsFromIrrig[n] = v[4 * (size_t)ng + n];
+        routing.G_unsatisfiedNAsFromOtherSectors[n] = v[5 * (size_t)ng + n];
+        routing.G_reducedReturnFlow[n] = v[6 * (size_t)ng + n];
+        routing.G_dailydailyNUg[n] = v[7 * (size_t)ng + n];
+    }
+    std::vector<double> o(6 * (size_t)ng);
+    for (int n = 0; n < ng; n++) {
+        o[0 * (size_t)ng + n] = routing.updateNetAbstractionGW(n);
+        o[1 * (size_t)ng + n] = routing.G_dailyRemainingUse[n];
+        o[2 * (size_t)ng + n] = routing.G_unsatisfiedNAsFromIrrig[n];
+        o[3 * (size_t)ng + n] = routing.G_unsatisfiedNAsFromOtherSectors[n];
+        o[4 * (size_t)ng + n] = routing.G_reducedReturnFlow[n];
+        o[5 * (size_t)ng + n] = routing.G_dailydailyNUg[n];
+    }
+    FILE *f = fopen(out, "wb");
+    if (!f) { perror(out); return 2; }
+    fwrite(o.data(), 8, o.size(), f);
+    fclose(f);
+    return 0;
+}
+
 static int run_driver(const char *cfg) {
     std::string progName = "OL", path_mean;
     WghmStateFile *wghmState, *wghmMean;
@@ -612,6 +648,7 @@ int main(int argc, char **argv) {
     if (argc >= 3 && std::string(argv[1]) == "driver") return run_driver(argv[2]);
     if (argc >= 4 && std::string(argv[1]) == "replay") return run_replay(argc, argv);
     if (argc >= 3 && std::string(argv[1]) == "calib") return run_calib(argv[2]);
+    if (argc >= 4 && std::string(argv[1]) == "wu_unit") return run_wu_unit(argv[2], argv[3]);
     fprintf(stderr, "usage: ref_harness driver <config> | replay <config> <dump|-> [--days A-B] [--every K] "
                     "[--snow-days A-B] [--final-state PREFIX] [--time-only] [--day-times FILE]\n");
     return 1;

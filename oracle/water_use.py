@@ -4,8 +4,11 @@
                             calcNextDay_M (:7414-7440): the monthly net abstractions from surface water / groundwater in m3 per
                             month, times the cell's multiplier (M_NETABSSW / M_NETABSGW), as km3 per day of the given month
 
-Pinned against the compiled reference: tests/golden/ref_ng1000_wateruse.npz (tests/test_oracle_golden.py).  The use
-satisfaction inside routing() (:2193-2296, 2922-2946, 3590-3920) and updateNetAbstractionGW (:5503-5572) are not restated yet.
+  update_net_abstraction_gw()  routingClass::updateNetAbstractionGW (:5503-5572)
+
+Pinned against the compiled reference: tests/golden/ref_ng1000_wateruse.npz (a 59-day run with net abstractions, and the unit
+vectors of `ref_harness wu_unit`; tests/test_oracle_golden.py).  The use satisfaction inside routing() (:2193-2296, 2922-2946,
+3590-3920) is not restated yet.
 Only tests/ may import this module.
 """
 import numpy as np
@@ -18,3 +21,53 @@ def daily_net_abstraction(monthly_m3, multiplier, month):
     month 0..11 -> km3/day [ng]: (multiplier * value) / (1000000000. * (double) days)"""
     v = np.asarray(monthly_m3, np.float32).reshape(-1, 12)[:, month].astype(np.float64)
     return (np.asarray(multiplier, np.float64) * v) / (1000000000. * float(NDAYS[month]))
+
+
+def update_net_abstraction_gw(rem, wusi, cusi, frgi, uns_irr, uns_oth, red_rf, nug):
+    """routingClass::updateNetAbstractionGW (routing.cpp:5503-5572) for every cell at once: the net abstraction from
+    groundwater adapted to the surface-water use that stayed unsatisfied (rem > 0: return flows reduced) or was satisfied late
+    (rem < 0: return flows reintroduced).  Inputs [ng] doubles: dailyRemainingUse, withdrawalIrrigFromSwb,
+    consumptiveUseIrrigFromSwb, fractreturngw_irrig, unsatisfiedNAsFromIrrig, unsatisfiedNAsFromOtherSectors, reducedReturnFlow,
+    dailydailyNUg.  -> (NAg returned, rem, uns_irr, uns_oth, red_rf) after the call; nug itself is not modified by the function"""
+    rem, wusi, cusi, frgi = (np.array(x, np.float64) for x in (rem, wusi, cusi, frgi))
+    uns_irr, uns_oth, red_rf, nug = (np.array(x, np.float64) for x in (uns_irr, uns_oth, red_rf, nug))
+    out = nug.copy()
+    for n in range(rem.size):
+        if rem[n] > 1.e-12:
+            if wusi[n] > 0.:
+                eff = cusi[n] / wusi[n]
+                factor = 1 - (1 - frgi[n]) * (1 - eff)
+                wusi_new = 1 / factor * (wusi[n] * factor - rem[n])
+                if wusi_new < 0.:
+                    wusi_new = 0.
+                    uns_irr[n] += wusi[n] * factor
+                    uns_oth[n] += rem[n] - (wusi[n] * factor)
+                else:
+                    uns_irr[n] += rem[n]
+                change = frgi[n] * (1 - eff) * (wusi_new - wusi[n])
+                red_rf[n] += change
+                out[n] = nug[n] - change
+                rem[n] = 0.
+            else:
+                uns_oth[n] += rem[n]
+        elif rem[n] < -1.e-12:
+            from_irr = rem[n] + uns_oth[n]
+            if from_irr < 0.:
+                uns_oth[n] = 0.
+            else:
+                uns_oth[n] += rem[n]
+                rem[n] = 0.
+                continue
+            if uns_irr[n] == 0.:
+                rem[n] = 0.
+                continue
+            ratio = from_irr / uns_irr[n]
+            if ratio < -1.:
+                ratio = -1.
+                from_irr = uns_irr[n] * -1.
+            change = ratio * red_rf[n]
+            uns_irr[n] += from_irr
+            red_rf[n] += change
+            out[n] = nug[n] - change
+            rem[n] = 0.
+    return out, rem, uns_irr, uns_oth, red_rf

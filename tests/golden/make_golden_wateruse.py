@@ -40,6 +40,24 @@ def main():
     for fn in ("G_NETUSE_SW_m3_1901.12.UNF0", "G_NETUSE_GW_m3_1901.12.UNF0", "G_IRRIG_WITHDRAWAL_USE_SW_m3_1901.12.UNF0",
                "G_IRRIG_CONS_USE_SW_m3_1901.12.UNF0", "G_FRACTRETURNGW_IRRIG.UNF0"):
         out["input/" + fn] = rd(fn)
+    # unit vectors of updateNetAbstractionGW (routing.cpp:5503-5572) through `ref_harness wu_unit`: every branch
+    rng = np.random.default_rng(20240607)
+    n = NG
+    rem = rng.normal(0., 2e-4, n) * (rng.random(n) < 0.8)
+    rem[rng.random(n) < 0.05] = rng.uniform(-1e-12, 1e-12, 1)      # inside the numerical dead band
+    wusi = np.where(rng.random(n) < 0.7, rng.gamma(0.8, 3e-4, n), 0.)
+    cusi = wusi * rng.uniform(0.2, 0.9, n)
+    frgi = rng.uniform(0.05, 0.7, n)
+    uns_irr = np.where(rng.random(n) < 0.6, rng.gamma(0.8, 2e-4, n), 0.)
+    uns_oth = np.where(rng.random(n) < 0.5, rng.gamma(0.8, 1e-4, n), 0.)
+    red_rf = -rng.gamma(0.8, 1e-4, n) * (uns_irr > 0)
+    nug = rng.normal(1e-4, 2e-4, n)
+    vin = np.stack([rem, wusi, cusi, frgi, uns_irr, uns_oth, red_rf, nug])
+    fin, fout = os.path.join(tmp, "wu_in.f64"), os.path.join(tmp, "wu_out.f64")
+    vin.astype("<f8").tofile(fin)
+    subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", f"ref_harness_{NG}"), "wu_unit", fin, fout], stdout=subprocess.DEVNULL)
+    out["unit/in"] = vin
+    out["unit/out"] = np.fromfile(fout, "<f8").reshape(6, n)
     path = os.path.join(ROOT, "tests", "golden", f"ref_ng{NG}_wateruse.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) / 1e6, "MB", len(out), "arrays")

@@ -158,3 +158,16 @@ def test_wateruse_daily_abstraction_bit_exact(golden):
     assert np.array_equal(wu.daily_net_abstraction(sw_m3, par[23], 1), z["d59/wu_daily_nus"])
     assert np.array_equal(wu.daily_net_abstraction(gw_m3, par[24], 0), z["d1/wu_daily_nug"])
     assert (z["d1/wu_daily_nus"] != 0).sum() > 100
+
+
+def test_wateruse_update_net_abstraction_gw_bit_exact():
+    """oracle/water_use.py::update_net_abstraction_gw against the compiled reference's updateNetAbstractionGW on 1000 seeded
+    cells that reach every branch (return flows reduced / reintroduced, no irrigation withdrawal, dead band, ratio limit)"""
+    from oracle import water_use as wu
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_ng1000_wateruse.npz"))
+    vin, ref = z["unit/in"], z["unit/out"]
+    got = wu.update_net_abstraction_gw(*vin)
+    for k, name in enumerate(("NAg", "dailyRemainingUse", "unsatisfiedNAsFromIrrig", "unsatisfiedNAsFromOtherSectors", "reducedReturnFlow")):
+        assert np.array_equal(got[k], ref[k]), name
+    assert np.array_equal(ref[5], vin[7])  # G_dailydailyNUg itself is left to the caller
+    assert (got[0] != vin[7]).sum() > 300 and (got[1] == 0).all() or (np.abs(got[1]) <= 1e-12).sum() > 0
