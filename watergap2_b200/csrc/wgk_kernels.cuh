@@ -475,9 +475,14 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
                 s = fma(fma(-landAreaFrac, s, num), inv_laf, s);
                 if (fabs(s) <= MIN_STOR_VOL) s = 0.;
                 const double s0 = s;
-                if (s > 1000.) {  // :958-976 (rare)
-                    if (thresh_elev == 0) thresh_elev = elev_e;
-                    else if (thresh_elev > 0) temp_elev = dailyTempC - ((thresh_elev - elev0) * P_T_GRADNT);
+                {   // the 1000 mm rule (:958-976, rare): the first band above 1000 mm fixes the elevation whose temperature all
+                    // later bands above 1000 mm use.  Branch-free like the rest of the band, so that the unrolled bands of a
+                    // chunk form one basic block (21.8 vs 22.2 ms per simulated year).
+                    const bool big = s > 1000.;
+                    const bool first = big && thresh_elev == 0;
+                    const double t_thresh = dailyTempC - ((thresh_elev - elev0) * P_T_GRADNT);
+                    temp_elev = (big && !first && thresh_elev > 0) ? t_thresh : temp_elev;
+                    thresh_elev = first ? elev_e : thresh_elev;
                 }
                 // Accumulation and sublimation below the freezing threshold (:982-999), melt above the melting threshold
                 // (:1003-1019), written as selects: without branches the compiler interleaves the unrolled bands of a chunk and
