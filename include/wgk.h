@@ -116,7 +116,10 @@ int wgk_get_device_order(const wgk_ctx *ctx, int32_t *rank_of_cell);
  * wgk_set_forcing copies `ndays` days starting at channel 0 of the four host grids (reference
  * layout [ncell][stride], stride = 31 for the .31 monthly files) into slots slot0.. ;
  * member < 0 = shared by all members, else per-member forcing (EnKF perturbed forcing).
- * The transposition / permutation runs on the device. */
+ * The transposition / permutation runs on the device.  The copy is ASYNCHRONOUS on the library's copy stream
+ * (it overlaps the stepping of other slots): the four host buffers must stay valid and unchanged until the next
+ * wgk_synchronize() or until a later wgk_step_days call that reads these slots has been synchronised; pinned
+ * buffers make the copy truly asynchronous, pageable ones are staged by the CUDA runtime before the call returns. */
 int wgk_forcing_reserve(wgk_ctx *ctx, int nslots, int per_member);
 int wgk_set_forcing(wgk_ctx *ctx, int slot0, int ndays, int member, const float *prec, const float *temp,
                     const float *shortwave, const float *longwave, int stride);
@@ -143,9 +146,13 @@ int wgk_step_days(wgk_ctx *ctx, int day, int month, int day_in_month, int slot0,
 /* total water storage of one member in km3 (canopy+snow+soil on the land fraction, plus the
  * seven routing compartments): the daily global mass-balance check of BASELINE.md */
 int wgk_total_storage_km3(wgk_ctx *ctx, int member, double *out);
-/* per-day record of river discharge at `ncells` chosen cells for the last wgk_step_days call
- * (station series, routing.cpp:4232-4238); host out[ndays][ncells] */
+/* per-day record of river discharge at `ncells` chosen cells (station series, routing.cpp:4232-4238), `max_days` rows.
+ * wgk_record_cells starts the record at row 0; every wgk_step_days call appends its days after those of the calls
+ * before it (a multi-year calibration run is several calls); a call whose days do not fit into the remaining rows
+ * restarts the record at row 0 with its first day, and wgk_record_rewind does so explicitly.  wgk_get_record copies
+ * the first `ndays` rows to host out[ndays][ncells] and fails (WGK_ERR_ARG) when fewer rows have been recorded. */
 int wgk_record_cells(wgk_ctx *ctx, const int32_t *cells, int ncells, int max_days);
+int wgk_record_rewind(wgk_ctx *ctx);
 int wgk_get_record(wgk_ctx *ctx, int member, double *out, int ndays);
 /* ---- EnKF state bridge (what the PDAF coupling of the reference exchanges with the model) ----------
  * wgk_month_begin: start accumulating the daily WghmStateFile entries of the seven routing compartments
@@ -165,12 +172,44 @@ int wgk_state_vector(wgk_ctx *ctx, int member, int kind, const int32_t *cells, i
 int wgk_enkf_update(wgk_ctx *ctx, int member, const int32_t *cells, int ncells, const double *field, const double *prediction,
                     const double *mean_field);
 
+/* ---- ensemble statistics: the one exchange between GPUs -------------------------------------
+ * wgk_ensemble_moments: over ALL members of this context, sum and sum of squares of the extract_sub_ state vector
+ * (the values of wgk_state_vector with mean_field NULL, kind as there) of `cells` (0-based; NULL = all ncell cells in
+ * reference order), each [ncells][10] f64, members added in ascending order.  The results stay on the device in ONE
+ * library-owned buffer (*d_sumsq == *d_sum + 10 * ncells, valid until the next call), written stream-ordered on the
+ * context's stream, so that the caller can all-reduce 2 * 10 * ncells doubles over NCCL in place (one process per
+ * GPU; enKF2wghmState.cpp runs the members as separate processes and PDAF forms the statistics over MPI).
+ * wgk_moments_finish: mean = sum / nmember_total and population variance max(0, sumsq / nmember_total - mean^2) of
+ * the (all-reduced) buffers, in place on the device, copied to host mean / var ([ncells][10], either may be NULL). */
+int wgk_ensemble_moments(wgk_ctx *ctx, int kind, const int32_t *cells, int ncells, void **d_sum, void **d_sumsq);
+int wgk_moments_finish(wgk_ctx *ctx, int nmember_total, double *mean, double *var);
+
+/* ---- set-up of large ensembles and parameter sweeps on the device -------------------------------------------
+ * wgk_copy_index: copy every field of one scope (1 = parameter set, 2 = member: state and fluxes) from index src
+ * to index dst, device to device (an ensemble starts from one state; calibration runs share everything but the
+ * calibrated parameters).  wgk_fill_field: one value for all cells of a per-cell f64 field of one index (the
+ * reference calibrates one gamma / CFA per basin, calibration.cpp:266-527). */
+int wgk_copy_index(wgk_ctx *ctx, int scope, int src, int dst);
+int wgk_fill_field(wgk_ctx *ctx, int field, int index, double value);
+
 /* one simulated day with plain launches and CUDA events between the phases, on the context's
  * stream: ms[0] vertical, ms[1] routing pre-pass (cell-parallel), ms[2] wide routing levels
  * (one launch each), ms[3] narrow-level tail (one persistent CTA per member), ms[4] routing
  * post-pass (cell-parallel), ms[5] whole day.
  * Advances the model state by that day. Used by bench.py for the per-kernel roofline. */
 int wgk_profile_day(wgk_ctx *ctx, int day, int month, int day_in_month, int slot, float ms[6]);
+/* the same for the schedule wgk_step_days really runs for this context ((day, level) wavefront tasks, or the whole-day
+ * kernels of many-member runs): one simulated day as plain launches with an event pair around every launch, summed per
+ * kernel class: 0 vertical balance (+ local routing) kernels, 1 river-level kernels, 2 narrow-level tail kernels,
+ * 3 the rest.  Advances the model state by that day. */
+int wgk_profile_schedule(wgk_ctx *ctx, int day, int month, int day_in_month, int slot, float ms[4], int launches[4]);
+/* %globaltimer stamps of the level-0 tasks (the dominant kernels) INSIDE the running graph: enable != 0 switches them on
+ * (and resets them), 0 off; out (may be NULL) receives the stamps of the calls since the last reset as
+ * u64 [2: vertical task, river task][2: first warp start, last warp end][512 day offsets] in ns. */
+int wgk_stamps(wgk_ctx *ctx, int enable, unsigned long long *out);
+/* measured DFMA throughput of the context's GPU in TFLOP/s (8 independent FMA chains per thread, 8 CTAs of 256 per SM):
+ * the denominator of the FP64-pipe fractions bench.py reports */
+int wgk_fp64_peak(wgk_ctx *ctx, double *tflops);
 /* number of kernels this context has launched (graph nodes counted per replay) */
 int64_t wgk_kernel_launches(const wgk_ctx *ctx);
 

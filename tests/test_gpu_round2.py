@@ -1,0 +1,287 @@
+"""GPU (-m gpu): the timed configuration itself, the station record over several calls, device-side set-up of
+large ensembles, the ensemble-moments kernel and its NCCL all-reduce, long single calls against the oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from tests.util import ParityReport
+
+pytestmark = pytest.mark.gpu
+
+
+def _full_world():
+    from oracle import synth_world as sw, wg_init
+    w = sw.build_world(67420)
+    return w, wg_init.derive(w)
+
+
+def _year_model(w, ini, forcing, **kw):
+    import watergap2_b200 as wg
+    topo = ini["_topology"]
+    m = wg.Model(w.ng, **kw)
+    m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+    m.load(ini)
+    m.forcing_reserve(365)
+    slot = 0
+    for mon, f in enumerate(forcing):
+        nd = (31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31)[mon]
+        m.set_forcing(slot, nd, f["P"], f["T"], f["SW"], f["LW"])
+        slot += nd
+    return m
+
+
+def test_year_call_bit_equal_to_daily_calls_full_size():
+    """THE TIMED PATH of bench.py: one wgk_step_days(365) call at 67 420 cells - a graph of ~41 600 (day, level) tasks, the 32-slot
+    discharge ring wrapping 11 times - must equal, bit for bit, 365 one-day calls and the same call with plain launches
+    (use_graph = 0), in every state / flux field, the snow bands and the daily station record."""
+    from oracle import synth_world as sw, wg_init
+    w, ini = _full_world()
+    forcing = [sw.forcing_month(w, 1901, mon) for mon in range(1, 13)]
+    names = wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS + ["discharge", "snow_bands"]
+    stations = np.argsort(-w.acc)[:50].astype(np.int32)
+    out = []
+    for mode in ("year_graph", "daily_calls", "year_plain"):
+        m = _year_model(w, ini, forcing, use_graph=0 if mode == "year_plain" else 1)
+        m.record_cells(stations, 365)
+        if mode == "daily_calls":
+            from oracle import wgo
+            for sd in range(1, 366):
+                doy, mon, dom = wgo.calendar(sd)
+                m.step_days(doy, mon, dom, sd - 1, 1)
+        else:
+            m.step_days(1, 0, 1, 0, 365)
+        m.synchronize()
+        out.append(({k: m.get(k) for k in names}, m.get_record(365)))
+        m.close()
+    assert np.abs(out[0][1]).sum() > 0 and np.isfinite(out[0][1]).all()
+    for other in out[1:]:
+        assert np.array_equal(out[0][1], other[1])
+        for k in names:
+            assert np.array_equal(out[0][0][k], other[0][k]), k
+
+
+def test_record_accumulates_over_calls(world3000):
+    """the station record is indexed by a running day counter, so a multi-year calibration run (several
+    calls) finds every year in it; a call that does not fit restarts the record; reading more rows than recorded fails"""
+    from oracle import synth_world as sw, wg_init
+    import watergap2_b200 as wg
+    ini = wg_init.derive(world3000)
+    topo = ini["_topology"]
+    f = sw.forcing_month(world3000, 1901, 1)
+    cells = np.arange(5, world3000.ng, 61, dtype=np.int32)
+
+    def model():
+        m = wg.Model(world3000.ng, nmember=2)
+        m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+        m.load(ini)
+        m.forcing_reserve(31)
+        m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+        return m
+
+    a = model()
+    a.record_cells(cells, 93)
+    for _ in range(3):  # three 31-day "years" in three calls
+        a.step_days(1, 0, 1, 0, 31)
+    rec = a.get_record(93, 1)
+    b = model()
+    b.record_cells(cells, 31)
+    for y in range(3):  # the same run with a one-year record: every call restarts it
+        b.step_days(1, 0, 1, 0, 31)
+        assert np.array_equal(b.get_record(31, 1), rec[31 * y:31 * (y + 1)]), y
+    assert np.abs(rec[62:]).sum() > 0
+    with pytest.raises(wg.WgkError):
+        b.get_record(32, 0)  # more than max_days
+    b.record_rewind()
+    b.step_days(1, 0, 1, 0, 5)
+    with pytest.raises(wg.WgkError, match="holds 5 days"):
+        b.get_record(6, 0)
+    from watergap2_b200 import calibration as cal
+    crit = cal.sweep_criteria(a, np.full((3, cells.size), 1.0, np.float32), 3, days_per_year=31)
+    assert len(crit) == 2 and crit[0][0]["years"] == 3
+
+
+def test_clone_and_fill_equal_host_upload(world3000):
+    """wgk_copy_index / wgk_fill_field (set-up of 1024 parameter sets / 256 members on the device) give the same bits as
+    uploading every member and parameter set from the host"""
+    from oracle import synth_world as sw, wg_init
+    import watergap2_b200 as wg
+    w = world3000
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    f = sw.forcing_month(w, 1901, 1)
+    pb = np.array(ini["params"], np.float64).reshape(26, -1).copy()
+    pb[0, :], pb[1, :], pb[7, :], pb[15, :] = 2.75, 0.9, 0.02, 0.5
+    ini2 = dict(ini)
+    ini2["params"], ini2["gamma_hbv"], ini2["cfa"] = pb, pb[0].copy(), pb[1].copy()
+    out = []
+    for device_side in (False, True):
+        m = wg.Model(w.ng, nmember=3, npset=2)
+        m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+        if device_side:
+            m.load(ini, member=0, pset=0)
+            m.copy_pset(0, 1)
+            m.copy_member(0, 1)
+            m.copy_member(0, 2)
+            for name, v in (("gamma_hbv", 2.75), ("cfa", 0.9), ("p_swoutf", 0.02), ("p_snowfz", 0.5)):
+                m.fill(name, v, index=1)
+        else:
+            m.load(ini, pset=0)
+            m.load(ini2, pset=1, only={k for k in ini2 if m.has_field(k) and m.field_info(k)[2] == 1})
+        m.set_member_pset(0, 0)
+        m.set_member_pset(1, 1)
+        m.set_member_pset(2, 1)
+        m.forcing_reserve(31)
+        m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+        m.step_days(1, 0, 1, 0, 9)
+        out.append([{k: m.get(k, mem) for k in wg_init.STATE_FIELDS + ["discharge", "snow_bands"]} for mem in range(3)])
+        with pytest.raises(wg.WgkError):
+            m.fill("smax", 1.0)  # not an f64 field
+    for mem in range(3):
+        for k in out[0][mem]:
+            assert np.array_equal(out[0][mem][k], out[1][mem][k]), (mem, k)
+    assert not np.array_equal(out[0][0]["soil"], out[0][1]["soil"])
+    assert np.array_equal(out[0][1]["soil"], out[0][2]["soil"])
+
+
+def _ensemble_model(w, ini, nmember, device=0, seed=3, member0=0):
+    """members with their own perturbed forcing (global member index seeds the perturbation)"""
+    from oracle import synth_world as sw
+    import watergap2_b200 as wg
+    topo = ini["_topology"]
+    base = sw.forcing_month(w, 1901, 1)
+    m = wg.Model(w.ng, nmember=nmember, device=device)
+    m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+    m.load(ini)
+    m.forcing_reserve(31, per_member=True)
+    for k in range(nmember):
+        rng = np.random.default_rng([seed, member0 + k])
+        P = (base["P"] * np.exp(rng.normal(0., 0.1, base["P"].shape))).astype(np.float32)
+        T = (base["T"] + rng.normal(0., 1., base["T"].shape)).astype(np.float32)
+        m.set_forcing(0, 31, P, T, base["SW"], base["LW"], member=k)
+        m.synchronize()
+    return m
+
+
+def test_moments_kernel_equals_sequential_host_sum(world3000):
+    """k_ensemble_moments: sum and sum of squares of the extract_sub_ state vector over the members, bit-equal to adding
+    the wgk_state_vector values member by member on the host; all cells and a region; mean / variance of k_moments_finish"""
+    from oracle import wg_init
+    from watergap2_b200.ensemble import device_tensor, ensemble_state_moments
+    w = world3000
+    ini = wg_init.derive(w)
+    nm = 5
+    m = _ensemble_model(w, ini, nm)
+    m.month_begin()
+    m.step_days(1, 0, 1, 0, 12)
+    for kind in ("month", "lastday"):
+        for cells in (None, np.arange(7, w.ng, 13, dtype=np.int32)):
+            ps, pq, n = m.ensemble_moments(kind, cells)
+            m.synchronize()
+            got = device_tensor(ps, (2, n, 10), 0).cpu().numpy()
+            cl = np.arange(w.ng, dtype=np.int32) if cells is None else cells
+            s, ss = np.zeros((n, 10)), np.zeros((n, 10))
+            for k in range(nm):
+                v = m.state_vector(cl, kind, member=k)
+                s += v
+                ss += v * v
+            assert np.array_equal(got[0], s) and np.array_equal(got[1], ss), (kind, cells is None)
+    mean, var = ensemble_state_moments(m, nm, "month")
+    vs = np.stack([m.state_vector(np.arange(w.ng, dtype=np.int32), "month", member=k) for k in range(nm)])
+    assert np.allclose(mean, vs.mean(0), rtol=1e-13, atol=1e-300)
+    assert np.allclose(var, vs.var(0), rtol=1e-6, atol=1e-9 * np.abs(vs).max())
+    assert var[:, 2].max() > 0  # members really differ (soil)
+
+
+def _nccl_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle import synth_world as sw, wg_init
+    from watergap2_b200.ensemble import ensemble_state_moments, shard_members
+    w = sw.build_world(3000)
+    ini = wg_init.derive(w)
+    total = 7
+    first, count = shard_members(total, world, rank)
+    m = _ensemble_model(w, ini, count, device=rank, member0=first)
+    m.month_begin()
+    m.step_days(1, 0, 1, 0, 10)
+    t = {}
+    mean, var = ensemble_state_moments(m, total, "month", timing=t)
+    cells = np.arange(w.ng, dtype=np.int32)
+    mine = torch.from_numpy(np.stack([m.state_vector(cells, "month", member=k) for k in range(count)])).cuda()
+    pad = torch.zeros((4,) + tuple(mine.shape[1:]), dtype=torch.float64, device="cuda")
+    pad[:count] = mine
+    allv = torch.empty((world * 4,) + tuple(mine.shape[1:]), dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(allv, pad)
+    if rank == 0:
+        a = allv.cpu().numpy().reshape(world, 4, w.ng, 10)
+        vs = np.concatenate([a[r, :shard_members(total, world, r)[1]] for r in range(world)])
+        torch.save({"mean": mean, "var": var, "ref_mean": vs.mean(0), "ref_var": vs.var(0), "n": vs.shape[0], "t": t}, out)
+    dist.destroy_process_group()
+
+
+def test_ensemble_moments_over_nccl_world_size_2(tmp_path):
+    """SURVEY 8e config 4 on hardware: members sharded over 2 GPUs, k_ensemble_moments + ONE NCCL all-reduce on the
+    context's stream + k_moments_finish against the numpy statistic of all members (needs 2 GPUs: `gpurun --gpus 2`)"""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "mom.pt")
+    mp.spawn(_nccl_worker, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out, weights_only=False)
+    assert r["n"] == 7
+    assert np.allclose(r["mean"], r["ref_mean"], rtol=1e-13, atol=1e-300)
+    assert np.allclose(r["var"], r["ref_var"], rtol=1e-6, atol=1e-9 * np.abs(r["ref_mean"]).max())
+    assert r["t"]["allreduce_bytes"] == 2 * 3000 * 10 * 8
+
+
+def test_long_single_calls_vs_oracle(world3000):
+    """calls longer than the 32-day discharge ring against the oracle: three single calls of 40 days, both sides
+    re-synchronised to the oracle's state at the call boundaries (free run inside a call: policy of DESIGN.md 6)"""
+    from oracle import synth_world as sw, wg_init, wgo
+    import watergap2_b200 as wg
+    w = world3000
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    o = wgo.Oracle(w.ng)
+    for k, v in ini.items():
+        if not k.startswith("_") and o.has(k):
+            o.set(k, v)
+    m = wg.Model(w.ng)
+    m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+    m.load(ini)
+    m.forcing_reserve(365)
+    forcing = [sw.forcing_month(w, 1901, mon) for mon in range(1, 6)]
+    slot = 0
+    for mon, f in enumerate(forcing):
+        nd = (31, 28, 31, 30, 31)[mon]
+        m.set_forcing(slot, nd, f["P"], f["T"], f["SW"], f["LW"])
+        slot += nd
+    names = wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS
+    sd = 1
+    for block in range(3):
+        if block:
+            for name in wg_init.STATE_FIELDS + ["storage_transfer"]:
+                m.set(name, o.field(name))
+        doy, mon, dom = wgo.calendar(sd)
+        m.step_days(doy, mon, dom, sd - 1, 40)
+        for k in range(40):
+            doy, mon, dom = wgo.calendar(sd + k)
+            if dom == 1:
+                o.set_forcing_month(forcing[mon])
+            o.step_day(doy, mon, dom)
+        sd += 40
+        rep = ParityReport()
+        for name in names:
+            rep.add(name, o.field(name), m.get(name), tag=sd - 1)
+        cells = {f[2] for f in rep.flips}
+        assert len(cells) <= max(2, w.ng // 500) and rep.worst < 1e-6, (rep.summary(), sorted(rep.flips, key=lambda f: -f[5])[:10])

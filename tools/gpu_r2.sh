@@ -1,0 +1,31 @@
+#!/bin/bash
+# Round-2 GPU-box visits (one section per call; everything lands in gpurun_out/):
+#   gpurun --timeout 1500 -- 'bash tools/gpu_r2.sh a r2a'
+SEC=${1:-a}
+TAG=${2:-r2}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/${TAG}_gpu.txt 2>&1
+case $SEC in
+a)  # first visit: what the tightened floors do to the existing tests, the parity report, a first bench line with the sharded legs
+  timeout 1200 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_parity.py > $OUT/${TAG}_pytest_new.log 2>&1
+  tail -5 $OUT/${TAG}_pytest_new.log
+  timeout 900 python tools/parity_report.py --tag $TAG --write-golden-flips > $OUT/${TAG}_parity.log 2>&1
+  tail -12 $OUT/${TAG}_parity.log
+  cp tests/golden/gpu_flips_ng1000.json $OUT/${TAG}_gpu_flips_ng1000.json 2>/dev/null
+  timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+  tail -c 3000 $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err
+  timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q > $OUT/${TAG}_pytest_old.log 2>&1
+  tail -15 $OUT/${TAG}_pytest_old.log
+  ;;
+t)  # the whole GPU suite
+  timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
+  echo "pytest rc=$?" >> $OUT/${TAG}_pytest.log
+  tail -5 $OUT/${TAG}_pytest.log
+  ;;
+b)  # bench only
+  timeout 900 python bench.py --steps ${STEPS:-30} --warmup 3 ${BENCH_ARGS} > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+  tail -c 3000 $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err
+  ;;
+esac
+ls -la $OUT | grep ${TAG}_ | tail -20

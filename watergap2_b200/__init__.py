@@ -103,7 +103,15 @@ def lib():
     L.wgk_total_storage_km3.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double)]
     L.wgk_record_cells.argtypes = [vp, vp, ci, ci]
     L.wgk_get_record.argtypes = [vp, ci, vp, ci]
+    L.wgk_record_rewind.argtypes = [vp]
     L.wgk_profile_day.argtypes = [vp, ci, ci, ci, ci, ctypes.POINTER(ctypes.c_float)]
+    L.wgk_ensemble_moments.argtypes = [vp, ci, vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.wgk_moments_finish.argtypes = [vp, ci, vp, vp]
+    L.wgk_copy_index.argtypes = [vp, ci, ci, ci]
+    L.wgk_fill_field.argtypes = [vp, ci, ci, ctypes.c_double]
+    L.wgk_profile_schedule.argtypes = [vp, ci, ci, ci, ci, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ci)]
+    L.wgk_stamps.argtypes = [vp, ci, vp]
+    L.wgk_fp64_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.wgk_kernel_launches.argtypes = [vp]
     L.wgk_kernel_launches.restype = ctypes.c_int64
     _lib = L
@@ -287,6 +295,31 @@ class Model:
         assert all(x.size == c.size * 10 for x in a)
         self._ck(self._L.wgk_enkf_update(self._c, member, c.ctypes.data, c.size, *[x.ctypes.data for x in a]))
 
+    # -- ensemble statistics / device-side set-up ---------------------------------------------------
+    def ensemble_moments(self, kind="month", cells=None):
+        """-> (device pointer of sum, device pointer of sumsq, ncells): [ncells, 10] f64 each, contiguous
+        (sumsq directly behind sum), over the members of this context"""
+        c = None if cells is None else np.ascontiguousarray(cells, np.int32)
+        ps, pq = ctypes.c_void_p(), ctypes.c_void_p()
+        self._ck(self._L.wgk_ensemble_moments(self._c, {"month": 0, "lastday": 1}[kind], None if c is None else c.ctypes.data,
+                                              0 if c is None else c.size, ctypes.byref(ps), ctypes.byref(pq)))
+        return ps.value, pq.value, (self.ncell if c is None else c.size)
+
+    def moments_finish(self, nmember_total, ncells):
+        mean = np.empty((ncells, 10), np.float64)
+        var = np.empty((ncells, 10), np.float64)
+        self._ck(self._L.wgk_moments_finish(self._c, nmember_total, mean.ctypes.data, var.ctypes.data))
+        return mean, var
+
+    def copy_member(self, src, dst):
+        self._ck(self._L.wgk_copy_index(self._c, 2, src, dst))
+
+    def copy_pset(self, src, dst):
+        self._ck(self._L.wgk_copy_index(self._c, 1, src, dst))
+
+    def fill(self, name, value, index=0):
+        self._ck(self._L.wgk_fill_field(self._c, self.field_id(name), index, float(value)))
+
     # -- diagnostics ------------------------------------------------------------------------------
     def total_storage_km3(self, member=0):
         out = ctypes.c_double()
@@ -298,6 +331,9 @@ class Model:
         self._ck(self._L.wgk_record_cells(self._c, c.ctypes.data, c.size, max_days))
         self._nrec = c.size
 
+    def record_rewind(self):
+        self._ck(self._L.wgk_record_rewind(self._c))
+
     def get_record(self, ndays, member=0):
         out = np.empty((ndays, self._nrec), np.float64)
         self._ck(self._L.wgk_get_record(self._c, member, out.ctypes.data, ndays))
@@ -308,6 +344,22 @@ class Model:
         ms = (ctypes.c_float * 6)()
         self._ck(self._L.wgk_profile_day(self._c, day, month, dom, slot, ms))
         return dict(zip(("vertical", "route_local", "route_levels", "route_tail", "route_post", "day"), [float(x) for x in ms]))
+
+    def profile_schedule(self, day, month, dom, slot):
+        """-> {class: (ms, launches)} of one simulated day of the schedule step_days uses, every launch timed on its own"""
+        ms, n = (ctypes.c_float * 4)(), (ctypes.c_int * 4)()
+        self._ck(self._L.wgk_profile_schedule(self._c, day, month, dom, slot, ms, n))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("vertical", "river_level", "tail", "other"))}
+
+    def stamps(self, enable=True, read=False):
+        out = np.zeros((2, 2, 512), np.uint64) if read else None
+        self._ck(self._L.wgk_stamps(self._c, int(enable), None if out is None else out.ctypes.data))
+        return out
+
+    def fp64_peak_tflops(self):
+        v = ctypes.c_double()
+        self._ck(self._L.wgk_fp64_peak(self._c, ctypes.byref(v)))
+        return v.value
 
     @property
     def kernel_launches(self):

@@ -80,6 +80,28 @@ def best_member(crit, station=0):
     return int(np.argmin([c[station]["rel_difference"] for c in crit]))
 
 
+def gather_annual_runoff(annual, nsets_total, group=None, device=None):
+    """annual [sets_on_this_rank, nyears, nstation] (km3/year per recorded station) of every rank -> the table of all
+    `nsets_total` sets in set order (sets are sharded contiguously, ensemble.shard_members): ONE all-gather of a padded
+    f64 tensor (NCCL on the GPUs, gloo in the CPU tests) instead of pickled objects."""
+    import torch
+    import torch.distributed as dist
+    a = torch.as_tensor(np.ascontiguousarray(annual, np.float64))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return a.numpy()
+    world = dist.get_world_size(group)
+    cap = (nsets_total + world - 1) // world
+    pad = torch.zeros((cap,) + tuple(a.shape[1:]), dtype=torch.float64)
+    pad[:a.shape[0]] = a
+    if device is not None:
+        pad = pad.to(device)
+    out = torch.empty((world * cap,) + tuple(a.shape[1:]), dtype=torch.float64, device=pad.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    out = out.cpu().numpy().reshape((world, cap) + tuple(a.shape[1:]))
+    base, extra = divmod(nsets_total, world)
+    return np.concatenate([out[r, :base + (1 if r < extra else 0)] for r in range(world)], axis=0)
+
+
 def gather_criteria(crit, group=None):
     """all ranks' sweep_criteria lists concatenated in rank order (members are sharded contiguously, ensemble.shard_members)"""
     import torch.distributed as dist

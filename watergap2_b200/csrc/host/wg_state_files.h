@@ -149,9 +149,25 @@ class AdditionalOutputInputFile {
         std::ofstream s(fn, std::ios::binary);
         if (!s) throw std::runtime_error("In AdditionalOutputInputFile::save(): error by opening file " + fn);
         const unsigned width = 33;
-        s << "additional output input" << std::endl;
+        // title and column names are part of the file format (additionalOutputInputFile.cpp:327-383), kept byte for
+        // byte - including the leading blanks and the spelling - so that a file written here equals the reference's
+        static const char *const kColumns[53] = {
+            "G_days_since_start", "G_GrowingStatus", "G_PrecSum", "G_totalUnsatisfiedUse", "G_UnsatisfiedUsePrevYear", "K_release",
+            "G_landAreaFrac", "G_landAreaFracPrevTimestep", "G_locWetlAreaReductionFactor", "G_gloLakeEvapoReductionFactor",
+            "G_groundwaterStorage", "G_locLakeAreaReductionFactor", "G_gloWetlAreaReductionFactor", "G_gloResEvapoReductionFactor",
+            "G_fswbInit[n]", "G_gloWetlStorage", "G_fswbLandAreaFrac", "G_locWetlStorage[n]", "G_locLakeStorage[n]",
+            "G_riverStorage[n]", "G_soilwatercontent[n]", "G_gloLakeStorage[n]", "G_canopywatercontent[n]", "G_gloResStorage[n]",
+            "G_snow[n]", "G_withdrawalIrrigFromSwb[n]", "G_consumptiveUseIrrigFromSwb[n]", "G_unsatAllocUSE", "G_AllocUSE",
+            "G_secondcell", "G_daily_UnsatAllocUseNextDay[n]", " G_daily_allocatedUseNextDay[n]", " G_AllocUSETOneigborcell[n]",
+            " G_fswbLandAreaFracNextTimestep[n]", " G_PrevUnsatAllocUse[n]", " G_dailyRemainingUse", " G_dailyAllocatedUse[n]",
+            " G_PrevTotalUnstatisfieduse[n]", " G_reducedReturnFlow[n]", " G_unsatisfiedNAsFromIrrig[n]",
+            " G_dailySatisAllocatedUseInSecondCell", " G_dailyAllocatedUse", " G_unsatUseRiparian[n]", " G_ActualUse[secondCell]",
+            " G_glores_prevyear[n]", " G_fLocLake[n]", " G_fGloWet[n]", " G_fLocWet[n]", " G_unsatUseRiparian[i]",
+            " G_unsatisfiedNAsFromOtherSectors[n]", " G_reducedReturnFlowPrevYear[n]", " G_unsatisfiedNAsFromIrrigPrevYear[n]",
+            " G_unsatisfiedNAsFromOtherSectorsPrevYear[n]"};
+        s << "additional out- and input" << std::endl;
         s << std::setw(6) << std::setfill(' ') << "ID";
-        for (int j = 0; j < 53; j++) s << std::setw(width) << std::setfill(' ') << ("col" + std::to_string(j));
+        for (int j = 0; j < 53; j++) s << std::setw(width) << std::setfill(' ') << kColumns[j];
         s << std::endl;
         s.precision(16);
         for (size_t i = 0; i < ncell_; i++) {

@@ -90,6 +90,15 @@ struct wgk_ctx {
     double *d_record = nullptr;
     int32_t *d_record_cells = nullptr;
     int nrec = 0, record_max_days = 0;
+    int record_rows = 0;  // rows written since the record was (re)started
+
+    unsigned long long *d_stamps = nullptr;  // wgk_stamps: globaltimer stamps of the level-0 tasks
+
+    // ensemble moments (sum, sum of squares of the state vector over this context's members), [ncells][10] each
+    double *d_mom_sum = nullptr, *d_mom_sumsq = nullptr;
+    int32_t *d_mom_pos = nullptr;
+    size_t mom_cap = 0;
+    int mom_ncells = 0;
 
     // staging
     void *h_stage = nullptr;
@@ -200,6 +209,7 @@ WgkParams make_params(const wgk_ctx *c) {
     p.restart = c->opt.restart;
     p.month_acc = c->month_acc ? 1 : 0;
     p.nlevels = c->nlevels;
+    p.stamps = c->d_stamps;
     return p;
 }
 
@@ -462,6 +472,9 @@ int ensure_derived(wgk_ctx *c) {
     CU(cudaMalloc(&c->d_gbody, nb * sizeof(double)));
     CU(cudaMemset(c->d_gbody, 0, nb * sizeof(double)));
     c->ngbody = n;
+    // cells that are inactive (now) never write their discharge entry: no stale value of an earlier configuration may
+    // feed a downstream gather or the published discharge field (every active cell rewrites its entry before it is read)
+    CU(cudaMemsetAsync(c->d_qbuf, 0, (size_t)wgk::QBUF_K * c->nmember * c->stride * sizeof(double), c->stream));
     c->derived_dirty = false;
     drop_graph(c);
     return 0;
@@ -494,6 +507,9 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     c->npset = npset;
     if (opt) c->opt = *opt;
     else { c->opt.restart = 0; c->opt.tail_threshold = 0; c->opt.use_graph = 1; }
+    if ((c->opt.restart != 0 && c->opt.restart != 1) || (c->opt.use_graph != 0 && c->opt.use_graph != 1) || c->opt.tail_threshold < 0)
+        return fail(c, WGK_ERR_ARG, "wgk_options: restart %d / use_graph %d must be 0 or 1, tail_threshold %d >= 0", c->opt.restart,
+                    c->opt.use_graph, c->opt.tail_threshold);
     {   // Form of the vertical kernel.  Small problems cannot fill the GPU with one thread per cell: the
         // cell-day -> cell-day latency chain bounds the run and the band-parallel forms shorten it (5 threads
         // per cell while far from full, 2 threads per cell while all tiles still fit the SMs at once);
@@ -527,6 +543,7 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     }
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_forcing, cudaEventDisableTiming));
     // the tile kernels keep up to 36 KB per CTA in shared memory: ask for the largest carve-out
@@ -571,6 +588,7 @@ void wgk_destroy(wgk_ctx *c) {
     cudaFree(c->d_cell_of_rank); cudaFree(c->d_up_off); cudaFree(c->d_up_idx); cudaFree(c->d_down);
     cudaFree(c->d_level_off); cudaFree(c->d_member_pset); cudaFree(c->d_cal); cudaFree(c->d_forcing);
     cudaFree(c->d_gidx); cudaFree(c->d_gbody); cudaFree(c->d_cal_days); cudaFree(c->d_qbuf);
+    cudaFree(c->d_mom_sum); cudaFree(c->d_mom_sumsq); cudaFree(c->d_mom_pos); cudaFree(c->d_stamps);
     cudaFree(c->d_fstage); cudaFree(c->d_record); cudaFree(c->d_record_cells); cudaFree(c->d_partial);
     cudaFree(c->d_own_warp_begin); cudaFree(c->d_own_warp_end); cudaFree(c->d_own_cell_warp); cudaFree(c->d_own_progress);
     cudaFree(c->d_own_abort); cudaFree(c->d_rec_head); cudaFree(c->d_rec_next); cudaFree(c->d_own_timing); cudaFree(c->d_own_ring);
@@ -997,11 +1015,19 @@ static int forcing_after_step(wgk_ctx *c, int slot0, int ndays) {
     return WGK_OK;
 }
 
-static int fill_calendar(wgk_ctx *c, int day, int month, int dom, int slot, int ndays) {
+static int fill_calendar(wgk_ctx *c, int day, int month, int dom, int slot, int ndays, bool record = false) {
     if (day < 1 || day > 365 || month < 0 || month > 11 || dom < 1 || dom > 31) return fail(c, WGK_ERR_ARG, "bad date day=%d month=%d day_in_month=%d", day, month, dom);
     if (slot < 0 || slot >= c->forcing_nslots) return fail(c, WGK_ERR_ARG, "forcing slot %d not reserved", slot);
     if (ndays < 1 || ndays > MAX_CALL_DAYS) return fail(c, WGK_ERR_ARG, "1..%d days per call", MAX_CALL_DAYS);
-    wgk::k_fill_calendar<<<1, 1, 0, c->stream>>>(c->d_cal_days, day, month, dom, slot, ndays, c->forcing_nslots);
+    // station record: the rows of this call follow those of the calls before it; a call that does not fit into the
+    // remaining rows restarts the record at row 0 (wgk.h)
+    int rec_base = 0;
+    if (c->d_record && record) {
+        if (c->record_rows + ndays > c->record_max_days) c->record_rows = 0;
+        rec_base = c->record_rows;
+        c->record_rows = std::min(c->record_max_days, c->record_rows + ndays);
+    }
+    wgk::k_fill_calendar<<<1, 1, 0, c->stream>>>(c->d_cal_days, c->d_cal, day, month, dom, slot, ndays, c->forcing_nslots, rec_base);
     c->launches++;
     return WGK_OK;
 }
@@ -1065,7 +1091,7 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
     if (rc) return rc;
     if (ndays <= 0) return WGK_OK;
     CU(cudaSetDevice(c->device));
-    rc = fill_calendar(c, day, month, dom, slot0, ndays);
+    rc = fill_calendar(c, day, month, dom, slot0, ndays, true);
     if (rc) return rc;
     rc = ensure_derived(c);
     if (rc) return rc;
@@ -1191,6 +1217,99 @@ int wgk_enkf_update(wgk_ctx *c, int member, const int32_t *cells, int ncells, co
 }
 
 // ---------------------------------------------------------------------------------------
+// ensemble statistics (the only exchange between ranks, once per assimilation cycle)
+// ---------------------------------------------------------------------------------------
+int wgk_ensemble_moments(wgk_ctx *c, int kind, const int32_t *cells, int ncells, void **d_sum, void **d_sumsq) {
+    if (!c || (kind != 0 && kind != 1) || ncells < 0 || !d_sum || !d_sumsq) return WGK_ERR_ARG;
+    if (!c->have_topology) return fail(c, WGK_ERR_STATE, "no topology");
+    if (kind == 0 && (!c->month_acc || c->month_days <= 0)) return fail(c, WGK_ERR_STATE, "wgk_month_begin and at least one stepped day must precede monthly moments");
+    CU(cudaSetDevice(c->device));
+    const int n = cells ? ncells : c->ncell;
+    if (n == 0) return fail(c, WGK_ERR_ARG, "empty cell list");
+    if (c->mom_cap < (size_t)n) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_mom_sum); cudaFree(c->d_mom_sumsq); cudaFree(c->d_mom_pos);
+        c->d_mom_sum = c->d_mom_sumsq = nullptr;
+        c->d_mom_pos = nullptr;
+        c->mom_cap = 0;
+        // one allocation for both, so that a single all-reduce of 2 * n * 10 doubles covers sum and sumsq
+        CU(cudaMalloc(&c->d_mom_sum, sizeof(double) * 20 * (size_t)n));
+        c->d_mom_sumsq = nullptr;
+        CU(cudaMalloc(&c->d_mom_pos, sizeof(int32_t) * (size_t)n));
+        c->mom_cap = (size_t)n;
+    }
+    double *sum = c->d_mom_sum, *sumsq = c->d_mom_sum + (size_t)10 * n;
+    if (cells) {
+        std::vector<int32_t> pos(n);
+        for (int k = 0; k < n; k++) {
+            if (cells[k] < 0 || cells[k] >= c->ncell) return fail(c, WGK_ERR_ARG, "cell %d out of range", cells[k]);
+            pos[k] = c->rank_of_cell[cells[k]];
+        }
+        CU(cudaMemcpyAsync(c->d_mom_pos, pos.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));  // pos is a host temporary
+    }
+    wgk::k_ensemble_moments<<<(n + 127) / 128, 128, 0, c->stream>>>(make_params(c), kind, c->month_days, cells ? c->d_mom_pos : nullptr,
+                                                                    c->d_cell_of_rank, n, sum, sumsq);
+    c->launches++;
+    CU(cudaGetLastError());
+    c->mom_ncells = n;
+    *d_sum = sum;
+    *d_sumsq = sumsq;
+    return WGK_OK;
+}
+
+int wgk_moments_finish(wgk_ctx *c, int nmember_total, double *mean, double *var) {
+    if (!c || nmember_total <= 0) return WGK_ERR_ARG;
+    if (!c->d_mom_sum || c->mom_ncells <= 0) return fail(c, WGK_ERR_STATE, "wgk_ensemble_moments must be called first");
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)10 * c->mom_ncells;
+    double *sum = c->d_mom_sum, *sumsq = c->d_mom_sum + n;
+    wgk::k_moments_finish<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(sum, sumsq, n, (double)nmember_total);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (mean) CU(cudaMemcpyAsync(mean, sum, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (var) CU(cudaMemcpyAsync(var, sumsq, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return WGK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// device-side replication and uniform parameters (set-up of large ensembles / parameter sweeps)
+// ---------------------------------------------------------------------------------------
+int wgk_copy_index(wgk_ctx *c, int scope, int src, int dst) {
+    if (!c || (scope != WGK_SCOPE_PSET && scope != WGK_SCOPE_MEMBER)) return WGK_ERR_ARG;
+    const int rows = scope == WGK_SCOPE_PSET ? c->npset : c->nmember;
+    if (src < 0 || src >= rows || dst < 0 || dst >= rows) return fail(c, WGK_ERR_ARG, "index out of range (%d -> %d of %d)", src, dst, rows);
+    if (src == dst) return WGK_OK;
+    CU(cudaSetDevice(c->device));
+    for (int f = 0; f < WGK_F_COUNT; f++) {
+        if (kFields[f].scope != scope) continue;
+        const size_t bytes = field_row_elems(c, f) * kFields[f].elsize;
+        char *base = (char *)*field_slot(c, f);
+        CU(cudaMemcpyAsync(base + (size_t)dst * bytes, base + (size_t)src * bytes, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (scope == WGK_SCOPE_PSET) c->derived_dirty = true;
+    // (s_snowfree is a member field and is copied with the bands it describes)
+    return WGK_OK;
+}
+
+int wgk_fill_field(wgk_ctx *c, int field, int index, double value) {
+    if (!c) return WGK_ERR_ARG;
+    if (field < 0 || field >= WGK_F_COUNT) return fail(c, WGK_ERR_ARG, "unknown field %d", field);
+    const FieldInfo &fi = kFields[field];
+    if (strcmp(fi.dtype, "f64") != 0 || fi.bands != 1 || fi.scope == WGK_SCOPE_TABLE)
+        return fail(c, WGK_ERR_ARG, "wgk_fill_field: %s is not a per-cell f64 field", fi.name);
+    if (index < 0 || (size_t)index >= field_rows(c, field)) return fail(c, WGK_ERR_ARG, "index %d out of range for field %s", index, fi.name);
+    CU(cudaSetDevice(c->device));
+    double *dst = (double *)*field_slot(c, field) + (size_t)index * c->stride;
+    wgk::k_fill_f64<<<(c->ncell + 255) / 256, 256, 0, c->stream>>>(dst, c->ncell, value);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (fi.scope != WGK_SCOPE_MEMBER) c->derived_dirty = true;
+    return WGK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // diagnostics
 // ---------------------------------------------------------------------------------------
 int wgk_total_storage_km3(wgk_ctx *c, int member, double *out) {
@@ -1247,13 +1366,21 @@ int wgk_record_cells(wgk_ctx *c, const int32_t *cells, int ncells, int max_days)
         c->nrec = ncells;
         c->record_max_days = max_days;
     }
+    c->record_rows = 0;
     drop_graph(c);
     return WGK_OK;
 }
 
+int wgk_record_rewind(wgk_ctx *c) {
+    if (!c) return WGK_ERR_ARG;
+    c->record_rows = 0;
+    return WGK_OK;
+}
+
 int wgk_get_record(wgk_ctx *c, int member, double *out, int ndays) {
-    if (!c || !out || member < 0 || member >= c->nmember || ndays < 0 || ndays > c->record_max_days) return WGK_ERR_ARG;
+    if (!c || !out || member < 0 || member >= c->nmember || ndays < 0) return WGK_ERR_ARG;
     if (!c->d_record) return fail(c, WGK_ERR_STATE, "wgk_record_cells was not called");
+    if (ndays > c->record_rows) return fail(c, WGK_ERR_ARG, "the station record holds %d days (of at most %d), %d requested", c->record_rows, c->record_max_days, ndays);
     CU(cudaSetDevice(c->device));
     const size_t pitch = (size_t)c->nmember * c->nrec;
     CU(cudaMemcpy2DAsync(out, (size_t)c->nrec * sizeof(double), c->d_record + (size_t)member * c->nrec, pitch * sizeof(double),
@@ -1303,6 +1430,130 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     CU(cudaEventElapsedTime(&ms[5], ev[0], ev[5]));
     for (auto &e : ev) cudaEventDestroy(e);
     return publish_discharge(c, 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// measurement aids of bench.py (include/wgk.h "diagnostics")
+// ---------------------------------------------------------------------------------------
+int wgk_stamps(wgk_ctx *c, int enable, unsigned long long *out) {
+    if (!c) return WGK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)2 * 2 * wgk::STAMP_DAYS;
+    if (out) {
+        if (!c->d_stamps) return fail(c, WGK_ERR_STATE, "stamps are not enabled");
+        CU(cudaMemcpy(out, c->d_stamps, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (enable && !c->d_stamps) {
+        CU(cudaMalloc(&c->d_stamps, n * sizeof(unsigned long long)));
+        drop_graph(c);  // the pointer is part of the kernel parameters baked into the graphs
+    } else if (!enable && c->d_stamps) {
+        cudaFree(c->d_stamps);
+        c->d_stamps = nullptr;
+        drop_graph(c);
+    }
+    if (c->d_stamps) {  // reset: start stamps to the largest value, end stamps to 0
+        std::vector<unsigned long long> z(n, 0ull);
+        for (int k = 0; k < 2; k++)
+            for (int d = 0; d < wgk::STAMP_DAYS; d++) z[(size_t)(k * 2) * wgk::STAMP_DAYS + d] = ~0ull;
+        CU(cudaMemcpy(c->d_stamps, z.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+    return WGK_OK;
+}
+
+// one simulated day of the schedule wgk_step_days uses for this context, as plain launches with a CUDA event pair
+// around EVERY launch: ms[k] / launches[k] per kernel class, k = 0 vertical (+ local routing) kernels, 1 river level
+// kernels, 2 narrow-level tail kernels, 3 the rest (local routing / post-pass of the whole-day schedule, station record)
+int wgk_profile_schedule(wgk_ctx *c, int day, int month, int dom, int slot, float ms[4], int launches[4]) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (!ms || !launches) return WGK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    rc = fill_calendar(c, day, month, dom, slot, 1);
+    if (rc) return rc;
+    rc = ensure_derived(c);
+    if (rc) return rc;
+    rc = forcing_before_step(c);
+    if (rc) return rc;
+    const WgkParams p = make_params(c);
+    struct Rec { cudaEvent_t a, b; int cls; };
+    std::vector<Rec> recs;
+    auto timed = [&](int cls, auto &&launch) {
+        Rec r{};
+        r.cls = cls;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, c->stream);
+        launch();
+        cudaEventRecord(r.b, c->stream);
+        recs.push_back(r);
+    };
+    const dim3 block(128);
+    if (c->whole_day) {
+        const dim3 grid((c->ncell + 127) / 128, c->nmember);
+        timed(0, [&] { launch_vertical(c, p, 0); });
+        timed(3, [&] { wgk::k_route_local<<<grid, block, 0, c->stream>>>(p); });
+        for (int l = 0; l < c->tail_level0; l++) {
+            const dim3 g((c->level_off[l + 1] - c->level_off[l] + 127) / 128, c->nmember);
+            timed(1, [&] { wgk::k_route_level<<<g, block, 0, c->stream>>>(p, 0, l); });
+        }
+        if (c->tail_level0 < c->nlevels) timed(2, [&] { wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, 0, c->tail_level0, c->nlevels); });
+        timed(3, [&] { wgk::k_route_post<<<grid, block, 0, c->stream>>>(p); });
+    } else {
+        for (int l = 0; l < c->tail_level0; l++) {
+            const int begin = c->level_off[l], end = c->level_off[l + 1];
+            const dim3 g((end - begin + 127) / 128, c->nmember);
+            timed(0, [&] { launch_cells_pre(c, p, 0, begin, end); });
+            timed(1, [&] { wgk::k_river_level<<<g, block, 0, c->stream>>>(p, 0, l); });
+        }
+        for (size_t k = 0; k + 1 < c->chunk_lo.size(); k++) {
+            const int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
+            const int begin = c->level_off[lo], end = c->level_off[hi];
+            timed(0, [&] { launch_cells_pre(c, p, 0, begin, end); });
+            timed(2, [&] { wgk::k_tail_chunk<<<c->nmember, 256, 0, c->stream>>>(p, 0, lo, hi); });
+        }
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    for (int k = 0; k < 4; k++) { ms[k] = 0.f; launches[k] = 0; }
+    for (Rec &r : recs) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms[r.cls] += t;
+        launches[r.cls]++;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    c->launches += (int64_t)recs.size();
+    if (c->month_acc) c->month_days += 1;
+    return publish_discharge(c, 0);
+}
+
+int wgk_fp64_peak(wgk_ctx *c, double *tflops) {
+    if (!c || !tflops) return WGK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const int iters = 1 << 16, blocks = sms * 8, threads = 256;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    double best = 0.;
+    for (int rep = 0; rep < 4; rep++) {  // first repetition warms up
+        CU(cudaEventRecord(a, c->stream));
+        wgk::k_fp64_peak<<<blocks, threads, 0, c->stream>>>(c->d_partial, iters, 0.999999, 1e-6);
+        CU(cudaEventRecord(b, c->stream));
+        CU(cudaEventSynchronize(b));
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, a, b));
+        const double tf = 2. * 8. * iters * (double)blocks * threads / (t * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    c->launches += 4;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
+    return WGK_OK;
 }
 
 #ifdef WGK_PHASE_TIMING

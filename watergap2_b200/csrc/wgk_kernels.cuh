@@ -45,7 +45,7 @@ struct WgkParams {
     const int32_t *up_idx;        // upstream ranks, ascending (= reference accumulation order)
     const int32_t *down;          // [ncell] downstream rank or -1
     const int32_t *level_off;     // [nlevels+1]
-    int32_t *cal;                 // base calendar of the current call {day, month, day_in_month, slot}
+    int32_t *cal;                 // base of the current call {day, month, day_in_month, slot, first row of the station record}
     int32_t *cal_days;            // [max days per call][4] {day of year, month, day in month, forcing slot}
     double *qbuf;                 // [QBUF_K][nmember][stride] river discharge of the days in flight
     const int32_t *gidx;          // [ncell] index into the global-water-body scratch or -1
@@ -59,6 +59,8 @@ struct WgkParams {
     int restart;
     int month_acc;                // accumulate the daily WghmStateFile values of the month (EnKF bridge)
     int nlevels;
+    unsigned long long *stamps;   // optional (wgk_stamps): [2: V, R][2: first warp start, last warp end][STAMP_DAYS] %globaltimer ns of the
+                                  // level-0 tasks of a call, i.e. their duration INSIDE the running graph; null = off
 };
 
 namespace wgk {
@@ -1197,6 +1199,19 @@ __device__ __forceinline__ void v_tail(const WgkParams &p, VTile<C> &sm, const i
 
 // number of days of river discharge kept in flight (temporal wavefront over the level graph)
 constexpr int QBUF_K = 32;
+// run-time stamps of the level-0 tasks (bench.py: duration of the dominant kernel inside the timed graph)
+constexpr int STAMP_DAYS = 512;
+__device__ __forceinline__ void stamp_task(const WgkParams &p, const int kind, const int which, const int dayofs) {
+#ifndef WGK_EMU
+    if (p.stamps && (threadIdx.x & 31) == 0 && dayofs < STAMP_DAYS) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        unsigned long long *e = p.stamps + ((size_t)(kind * 2 + which)) * STAMP_DAYS + dayofs;
+        if (which) atomicMax(e, t);
+        else atomicMin(e, t);
+    }
+#endif
+}
 #ifdef WGK_PHASE_TIMING  // development aid: in-situ warp durations of the thread-per-cell task kernels (tools/insitu_timing.py)
 __device__ unsigned long long g_insitu[8];  // {V cycles, V warps, R cycles, R warps, V level-0 cycles, V level-0 warps, R level-0 cycles, R level-0 warps}
 __device__ unsigned long long g_stamp[2][2][512];  // level-0 tasks: [V, R][first warp start, last warp end][day offset], globaltimer ns
@@ -1990,6 +2005,7 @@ __global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ Wgk
     const size_t q = (size_t)p.member_pset[m] * p.stride + r;
     WGK_INSITU_BEGIN();
     if (level == 0) WGK_INSITU_STAMP(1, 0, dayofs);
+    if (level == 0) stamp_task(p, 1, 0, dayofs);
     const RiverCtx c = load_ctx(p, r, mb + r, q);
     const PostIn in = post_load(p, r, m);  // same round of loads as the river context
     double Sr = c.prevR;
@@ -2000,6 +2016,7 @@ __global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ Wgk
     route_post_compute(p, r, m, in, Sr);
     WGK_INSITU_END(2, level == 0);
     if (level == 0) WGK_INSITU_STAMP(1, 1, dayofs);
+    if (level == 0) stamp_task(p, 1, 1, dayofs);
 }
 
 // vertical balance (+ local routing) of the cells [begin, end), one CTA per tile of 32 cells; tiles
@@ -2193,6 +2210,7 @@ __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_cells_pre_tpc(const __
     if (r >= end) return;
     WGK_INSITU_BEGIN();
     if (begin == 0) WGK_INSITU_STAMP(0, 0, dayofs);
+    if (begin == 0) stamp_task(p, 0, 0, dayofs);
     LocalIn li;
     LocalFlux fx;
     if (vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, blockIdx.y, li, fx);
@@ -2200,6 +2218,7 @@ __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_cells_pre_tpc(const __
     WGK_INSITU_END(0, begin == 0);
     if (begin == 0) WGK_INSITU_WARPDUR(dayofs);
     if (begin == 0) WGK_INSITU_STAMP(0, 1, dayofs);
+    if (begin == 0) stamp_task(p, 0, 1, dayofs);
 }
 
 // narrow levels [level_lo, level_hi) of one day in one persistent CTA per member, then the
@@ -2358,8 +2377,8 @@ __global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) 
         if (ok) ring_put(ring + 2 * (size_t)r, qv, tag);
         WGK_OWNER_TICK(2);
         if (ok) route_post_compute(p, r, m, in, Sr);
-        if (rec0 >= 0 && d < p.record_max_days)
-            for (int k = rec0; k >= 0; k = s.rec_next[k]) p.record[((size_t)d * p.nmember + m) * p.nrec + k] = qv;
+        if (rec0 >= 0 && p.cal[4] + d < p.record_max_days)
+            for (int k = rec0; k >= 0; k = s.rec_next[k]) p.record[((size_t)(p.cal[4] + d) * p.nmember + m) * p.nrec + k] = qv;
         // once EVERY lane's gather of day d has returned (its values were used above) the warp has consumed day d;
         // the full mask matters: lanes still polling must not be overtaken by the producer of day d + QBUF_K
         __syncwarp(mask);
@@ -2377,8 +2396,10 @@ __global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) 
 // ----------------------------------------------------------------------------------------
 // calendar of the `ndays` days of one call, starting at (day, month, day_in_month, slot);
 // 365-day years (integrateWGHM.cpp:100-102), forcing slots cycle through the reserved ones
-__global__ void k_fill_calendar(int32_t *cal_days, int day, int month, int dom, int slot, int ndays, int nslots) {
+__global__ void k_fill_calendar(int32_t *cal_days, int32_t *cal, int day, int month, int dom, int slot, int ndays, int nslots, int rec_base) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    cal[0] = day; cal[1] = month; cal[2] = dom; cal[3] = slot;
+    cal[4] = rec_base;  // row of the station record that day offset 0 of this call writes (graphs are replayed unchanged)
     const int nd[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
     for (int d = 0; d < ndays; d++) {
         cal_days[4 * d] = day; cal_days[4 * d + 1] = month; cal_days[4 * d + 2] = dom; cal_days[4 * d + 3] = slot;
@@ -2393,12 +2414,14 @@ __global__ void k_fill_calendar(int32_t *cal_days, int day, int month, int dom, 
 
 // end of a simulated day: record the discharge of the station cells
 __global__ void k_end_of_day(const __grid_constant__ WgkParams p, const int dayofs) {
-    if (!p.record || dayofs >= p.record_max_days) return;
+    if (!p.record) return;
+    const int row = p.cal[4] + dayofs;  // rows accumulate over the calls since the record was (re)started
+    if (row >= p.record_max_days) return;
     const double *qday = qbuf_of_day(p, dayofs);
     const int total = p.nmember * p.nrec;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
         const int m = k / p.nrec, cidx = k % p.nrec;
-        p.record[(size_t)dayofs * total + k] = qday[(size_t)m * p.stride + p.record_cells[cidx]];
+        p.record[(size_t)row * total + k] = qday[(size_t)m * p.stride + p.record_cells[cidx]];
     }
 }
 
@@ -2487,6 +2510,70 @@ __global__ void __launch_bounds__(128) k_state_vector(const __grid_constant__ Wg
     double v[10];
     state_of_cell(p, pos[j], m, kind, ndays, v);
     for (int k = 0; k < 10; k++) out[(size_t)j * 10 + k] = v[k] - (mean_field ? mean_field[(size_t)j * 10 + k] : 0.);
+}
+
+// Ensemble moments of the state vector over the members of this context (what an assimilation
+// cycle exchanges once per month): sum[j][k] = sum over members of v, sumsq[j][k] = sum of v * v, v = the extract_sub_
+// value of compartment k of cell j (state_of_cell, so the values are those of k_state_vector bit for bit).  Every
+// member array is read exactly once, coalesced: a thread owns one device position and walks the members in
+// ascending order (fixed summation order -> reproducible, and equal to a sequential host sum).  `pos` == nullptr:
+// all cells, thread = device position, results stored at the reference cell number (cell_of_rank); else thread j
+// gathers device position pos[j].  The two outputs are plain device buffers the host all-reduces over NCCL.
+__global__ void __launch_bounds__(128) k_ensemble_moments(const __grid_constant__ WgkParams p, const int kind, const int ndays,
+                                                          const int32_t *__restrict__ pos, const int32_t *__restrict__ cell_of_rank,
+                                                          const int ncells, double *__restrict__ sum, double *__restrict__ sumsq) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncells) return;
+    const int x = pos ? pos[j] : j;
+    const size_t o = (size_t)(pos ? j : cell_of_rank[j]) * 10;
+    double s[10], ss[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) { s[k] = 0.; ss[k] = 0.; }
+    for (int m = 0; m < p.nmember; m++) {
+        double v[10];
+        state_of_cell(p, x, m, kind, ndays, v);
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            s[k] += v[k];
+            ss[k] += v[k] * v[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        sum[o + k] = s[k];
+        sumsq[o + k] = ss[k];
+    }
+}
+
+// mean and (population) variance from the all-reduced sums, in place: sum <- mean, sumsq <- max(0, E[x^2] - mean^2)
+__global__ void __launch_bounds__(256) k_moments_finish(double *__restrict__ sum, double *__restrict__ sumsq, const size_t n, const double nmember_total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mean = sum[i] / nmember_total;
+    double var = sumsq[i] / nmember_total - mean * mean;
+    if (var < 0.) var = 0.;
+    sum[i] = mean;
+    sumsq[i] = var;
+}
+
+// DFMA throughput of this GPU (north_star: "FP64 pipe utilisation against peak"): every thread runs 8 independent chains
+// of dependent fused multiply-adds from registers; flops = 2 * 8 * iters per thread.  `out` keeps the compiler honest.
+__global__ void __launch_bounds__(256) k_fp64_peak(double *__restrict__ out, const int iters, const double a, const double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3., x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123.456) out[0] = r;  // never true for the arguments used
+}
+
+// uniform value for one row of a per-cell f64 array (a calibration parameter of one parameter set, calibration.cpp
+// assigns one gamma / CFA per basin)
+__global__ void __launch_bounds__(256) k_fill_f64(double *__restrict__ dst, const int n, const double v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
 }
 
 // enkf_wghmstate_ (enKF2wghmState.cpp:89-121, 440-471) followed by the restore of the next cycle's start

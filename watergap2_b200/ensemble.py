@@ -127,6 +127,40 @@ class _CudaArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
+def device_tensor(ptr, shape, device, typestr="<f8"):
+    """zero-copy torch view of a device buffer owned by a wgk context"""
+    import torch
+    return torch.as_tensor(_CudaArray(ptr, shape, typestr), device=f"cuda:{device}")
+
+
+def ensemble_state_moments(model, nmember_total, kind="month", cells=None, group=None, timing=None):
+    """Mean and population variance, over ALL members of all ranks, of the extract_sub_ state vector [ncells, 10]
+    (what an assimilation cycle needs once per month).  Product path, nothing of it in eager PyTorch:
+    k_ensemble_moments reads the rank's member state once and leaves sum | sumsq in one device buffer, ONE in-place
+    all-reduce of 2 * ncells * 10 doubles (NCCL over NVLink, issued on the context's stream) adds the ranks, and
+    k_moments_finish turns the sums into the statistics.  `timing` (a dict) receives CUDA-event times in ms of the
+    moments kernel and of the collective.  -> (mean, var) as host arrays [ncells, 10]."""
+    import torch
+    import torch.distributed as dist
+    ps, _, n = model.ensemble_moments(kind, cells)
+    buf = device_tensor(ps, (2, n, 10), model.device)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    stream = torch.cuda.ExternalStream(model.stream, device=model.device)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timing is not None else None
+    with torch.cuda.stream(stream):
+        if ev:
+            ev[0].record(stream)
+        if multi:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        if ev:
+            ev[1].record(stream)
+    mean, var = model.moments_finish(nmember_total, n)
+    if ev:
+        timing["collective_ms"] = ev[0].elapsed_time(ev[1])
+        timing["allreduce_bytes"] = int(buf.numel() * 8)
+    return mean, var
+
+
 def member_tensor(model, field):
     """torch view [nmember, cell_stride] (device layout: routing order, padded) of a per-member
     f64 field of a wgk Model, without a copy"""
@@ -136,15 +170,15 @@ def member_tensor(model, field):
 
 
 def ensemble_mean_var(local, nmember_total, group=None):
-    """mean and (population) variance over ALL members of all ranks of `local` [members_on_this_rank, n]
-    (torch tensor on the rank's device).  Two all-reduces of n doubles each."""
+    """mean and (population) variance over ALL members of all ranks of a generic tensor `local`
+    [members_on_this_rank, n]: the host-logic form of the exchange (member sharding + one all-reduce of the stacked
+    sums), used by the gloo CPU tests and for fields outside the state vector.  The model state goes through
+    ensemble_state_moments (CUDA reduction kernel + NCCL)."""
     import torch
     import torch.distributed as dist
-    s = local.sum(0)
-    ss = (local * local).sum(0)
+    sums = torch.stack([local.sum(0), torch.einsum("mn,mn->n", local, local)])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(ss, op=dist.ReduceOp.SUM, group=group)
-    mean = s / nmember_total
-    var = torch.clamp(ss / nmember_total - mean * mean, min=0.0)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    mean = sums[0] / nmember_total
+    var = torch.clamp(sums[1] / nmember_total - mean * mean, min=0.0)
     return mean, var
