@@ -433,6 +433,7 @@ def leg_sweep(args, D, w, ini, forcing, nsets_total=1024):
 
     def step(k):
         m.step_days(1, 0, 1, 0, 31)
+        m.synchronize()  # (the record read-back below would wait for the month anyway; done here so that gather_ms is the exchange alone)
         t0 = time.perf_counter()
         annual = np.stack([cal.annual_runoff_km3(m.get_record(31, mem), 31) for mem in range(count)])  # [sets, 1, stations]
         table = cal.gather_annual_runoff(annual, nsets_total, device="cuda")

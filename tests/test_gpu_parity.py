@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from tests.util import assert_parity, golden_day
+from tests.util import FREE_RUN_MAX_REL, FREE_RUN_PPM, ONE_STEP_MAX_REL, ONE_STEP_PPM, ParityReport, assert_parity, golden_day
 
 pytestmark = pytest.mark.gpu
 
@@ -26,7 +26,13 @@ def form(request, monkeypatch):
 
 
 def test_gpu_vs_reference_golden(golden, form):
-    """59 days on the 1000-cell world, compared with what the compiled reference held in memory."""
+    """59 days on the 1000-cell world, compared with what the compiled reference held in memory, at 1e-10 on EVERY recorded
+    day (1, 2, 15, 31, 32, 45, 59).  Days 1 and 2 must hold without exception; from day 15 on every value beyond 1e-10 must be
+    one of the COMMITTED list tests/golden/gpu_flips_ng1000.json (generated on a B200 by tools/parity_report.py: cell 950,
+    a river reach at the evaporation-limited threshold of routing.cpp:3470-3520, and its downstream cells) and
+    within 2e-7."""
+    import json
+    import os
     ng = int(golden["ng"])
     d0 = golden_day(golden, 0)
     ro = np.zeros(ng, np.int32)
@@ -34,7 +40,10 @@ def test_gpu_vs_reference_golden(golden, form):
     m = _model_from(d0, ro, d0["downstream_cell"], ng)
     m.forcing_reserve(31)
     days = [int(d) for d in golden["days"]]
+    with open(os.path.join(os.path.dirname(__file__), "golden", "gpu_flips_ng1000.json")) as fh:
+        known = {(int(e[0]), e[1], int(e[2])) for e in json.load(fh)["entries"]}
     curm, nchk = -1, 0
+    rep = ParityReport()
     for sd in range(1, max(days) + 1):
         doy, mon, dom = ((sd - 1) % 365 + 1, 0 if sd <= 31 else 1, sd if sd <= 31 else sd - 31)
         if mon != curm:
@@ -43,15 +52,15 @@ def test_gpu_vs_reference_golden(golden, form):
             curm = mon
         m.step_days(doy, mon, dom, dom - 1, 1)
         if sd in days:
-            # free run: ulp-level differences grow along the trajectory, so the
-            # 1e-10 gate applies to the first month and a looser one to days 45 and 59
-            rtol = 1e-10 if sd <= 32 else 1e-7
             for name, ref in golden_day(golden, sd).items():
                 if m.has_field(name) and name != "status_laf_next":
-                    # free run: up to 0.5 % of the values may sit in noise-amplifying cells (<= 1e-6)
-                    assert_parity(name, ref, m.get(name), rtol=rtol, max_flips=max(1, ref.size // 200))
+                    rep.add(name, ref, m.get(name), tag=sd)
                     nchk += 1
     assert nchk > 200
+    new = [f for f in rep.flips if (int(f[0]), f[1], int(f[2])) not in known]
+    assert not new, f"values beyond 1e-10 that are not in tests/golden/gpu_flips_ng1000.json: {new[:10]}"
+    assert not [f for f in rep.flips if f[0] <= 2], "days 1 and 2 must hold 1e-10 without exception"
+    assert rep.worst <= 2e-7, rep.summary()
 
 
 def test_gpu_deep_snow_vs_reference_golden(golden_deep, form):
@@ -119,12 +128,12 @@ def _run_pair(world, ndays, nmember=1, use_graph=1, psets=None, block=1):
 
 
 def _compare(oracles, m, names, free_run=True):
-    flips = 0
+    """free-run policy of tests/util.py: at most FREE_RUN_PPM values per million beyond 1e-10, each within 1e-6, listed on failure"""
+    rep = ParityReport()
     for mem, o in enumerate(oracles):
         for name in names:
-            ref = o.field(name)
-            flips += assert_parity(name, ref, m.get(name, mem), max_flips=max(1, ref.size // 200) if free_run else 0)
-    return flips
+            rep.add(name, o.field(name), m.get(name, mem), tag=mem)
+    return rep.check(FREE_RUN_PPM if free_run else ONE_STEP_PPM, FREE_RUN_MAX_REL if free_run else ONE_STEP_MAX_REL, min_allowed=1, what="free run")
 
 
 def test_gpu_vs_oracle_3000_cells(world3000, form):
@@ -154,8 +163,7 @@ def _resync_run(world, ndays, check_every=1):
     m.set_topology(topo["rout_order"], topo["outflow_cell"])
     m.load(ini)
     m.forcing_reserve(31)
-    worst = 0.0
-    from tests.util import rel_err
+    rep = ParityReport()
     for sd in range(1, ndays + 1):
         doy, mon, dom = wgo.calendar(sd)
         if dom == 1:
@@ -169,22 +177,30 @@ def _resync_run(world, ndays, check_every=1):
         m.step_days(doy, mon, dom, dom - 1, 1)
         if sd % check_every == 0 or sd == ndays:
             for name in wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS:
-                ref, got = o.field(name), m.get(name)
-                assert_parity(name, ref, got)
-                if ref.dtype.kind == "f":
-                    worst = max(worst, float(rel_err(name, ref, got).max()))
-    return worst
+                rep.add(name, o.field(name), m.get(name), tag=sd)
+    return rep
+
+
+# storages proper (the fields north_star names): held to 1e-10 after one step with at most 0.1 per million exceptions
+STORAGES = {"soil", "snow", "gw", "loc_lake_stor", "loc_wetl_stor", "glo_lake_stor", "glo_wetl_stor", "res_stor", "river_stor",
+            "land_area_frac", "land_area_frac_next", "land_area_frac_prev"}
+
+
+def _check_one_step(rep, what):
+    n = rep.check(ONE_STEP_PPM, ONE_STEP_MAX_REL, what=what)
+    stor = [f for f in rep.flips if f[1] in STORAGES]
+    assert len(stor) <= max(1, rep.nvalues // 10_000_000), f"{what}: storages beyond 1e-10 after one step: {stor[:10]}"
+    print(f"{what}: {rep.summary()} flips by field: { {k: sum(1 for f in rep.flips if f[1] == k) for k in {f[1] for f in rep.flips}} }")
+    return n
 
 
 def test_one_step_parity_every_day_of_a_year(world3000):
-    worst = _resync_run(world3000, 365)
-    assert worst < 1e-10
+    _check_one_step(_resync_run(world3000, 365), "one step, 3000 cells, 365 days")
 
 
 def test_one_step_parity_full_size_120_days():
     from oracle import synth_world as sw
-    worst = _resync_run(sw.build_world(67420), 120, check_every=3)
-    assert worst < 1e-10
+    _check_one_step(_resync_run(sw.build_world(67420), 120, check_every=3), "one step, 67420 cells, 120 days")
 
 
 def test_free_run_full_size_20_days():
@@ -214,6 +230,7 @@ def test_whole_day_schedule_equals_wavefront(world3000, monkeypatch):
         m.record_cells(np.arange(0, world3000.ng, 97, dtype=np.int32), 31)
         m.step_days(1, 0, 1, 0, 12)
         m.month_begin()  # the monthly sums of the EnKF bridge are formed by the post-pass of every schedule
+        m.record_rewind()
         m.step_days(13, 0, 13, 12, 5)
         out.append(({k: m.get(k, 1) for k in wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS}, m.get_record(5, 1),
                     m.state_vector(np.arange(0, world3000.ng, 13, dtype=np.int32), "month", member=1)))
@@ -427,8 +444,10 @@ def test_tiny_worlds_all_forms(ng, monkeypatch):
         m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
         m.step_days(1, 0, 1, 0, 5)
         m.step_days(6, 0, 6, 5, 7)
+        rep = ParityReport()
         for name in wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS:
-            assert_parity(name, o.field(name), m.get(name), max_flips=max(1, ng // 200))
+            rep.add(name, o.field(name), m.get(name), tag=(form, sched))
+        rep.check(FREE_RUN_PPM, FREE_RUN_MAX_REL, min_allowed=1, what=f"ng={ng} {form} {sched}")
         assert abs(m.total_storage_km3() - o.total_storage_km3()) <= 1e-12 * abs(o.total_storage_km3()) + 1e-18
 
 
@@ -463,8 +482,10 @@ def test_per_member_forcing(world3000):
         o.set_forcing_month(f)
         for d in range(1, 11):
             o.step_day(d, 0, d)
+        rep = ParityReport()
         for name in wg_init.STATE_FIELDS + ["discharge", "surface_runoff"]:
-            assert_parity(name, o.field(name), m.get(name, mem), max_flips=max(1, w.ng // 200))
+            rep.add(name, o.field(name), m.get(name, mem), tag=mem)
+        rep.check(FREE_RUN_PPM, FREE_RUN_MAX_REL, min_allowed=1, what=f"member {mem}")
     assert not np.array_equal(m.get("soil", 0), m.get("soil", 1))
 
 

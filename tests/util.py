@@ -23,6 +23,16 @@ SCALE_KM3, SCALE_MM, SCALE_DIMLESS = 1e-9, 1e-6, 1e-6
 SCALE_RESIDUAL_MM = 1e-3
 
 
+# How many values may exceed RTOL (they are always LISTED, never hidden):
+#  one step from identical state: discharge = inflow + prevR - Sr - E and cell_runoff = discharge - upstream inflow are
+#    differences of storages, so the <= 2 ulp between CUDA's and glibc's exp()/pow() in Sr reappear magnified by Sr / discharge
+#    in slow reaches; measured on B200 (tools/parity_report.py, profiles/r2_parity.md): 0.9 - 1.5 values per million, worst 1.4e-8
+#  free runs of 20 - 60 days additionally let those last bits grow in the cells of DESIGN.md 6: measured 2 - 8 per million on
+#    the 3000 / 67420-cell worlds (worst 3.4e-9), 275 per million on the 1000-cell golden world (one cell, 1.03e-7)
+ONE_STEP_PPM, ONE_STEP_MAX_REL = 5.0, 1e-7
+FREE_RUN_PPM, FREE_RUN_MAX_REL = 50.0, 1e-6
+
+
 def floor_of(name):
     if name in KM3:
         return SCALE_KM3
@@ -95,6 +105,17 @@ class ParityReport:
             self.worst_pure = max(self.worst_pure, float(pe.max()))
         for k in np.nonzero(~(e <= RTOL))[0]:
             self.flips.append((tag, name, int(k), float(ref[k]), float(got[k]), float(e[k])))
+
+    def check(self, max_ppm, max_rel, min_allowed=0, what=""):
+        """the policy of DESIGN.md 6: at most max(min_allowed, max_ppm per million compared values) values beyond
+        1e-10, each within max_rel; a failure lists the offending values (worst first)"""
+        allowed = max(min_allowed, int(max_ppm * self.nvalues / 1e6))
+        worst = max((f[5] for f in self.flips), default=0.0)
+        if len(self.flips) > allowed or not (worst <= max_rel):
+            top = sorted(self.flips, key=lambda f: -f[5])[:12]
+            raise AssertionError(f"{what}: {len(self.flips)} of {self.nvalues} values beyond {RTOL:g} (allowed {allowed}), worst {worst:.3e} "
+                                 f"(allowed {max_rel:g}); (tag, field, index, ref, got, rel): {top}")
+        return len(self.flips)
 
     def summary(self):
         return {"values": self.nvalues, "worst_rel": self.worst, "worst_rel_no_floor": self.worst_pure,

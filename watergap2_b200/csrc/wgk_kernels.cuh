@@ -59,6 +59,22 @@ struct WgkParams {
     int restart;
     int month_acc;                // accumulate the daily WghmStateFile values of the month (EnKF bridge)
     int nlevels;
+    // Layout of the member- and parameter-set-scoped arrays:
+    //   mm == 0  cell-minor   [member][band][cell]: a warp = 32 consecutive cells of one member (few members, latency regime)
+    //   mm == 1  member-minor [band][cell][member]: a warp = 32 members of ONE cell (many members, throughput regime): statics
+    //            are warp-uniform loads and the 32 lanes share land cover, water-body class and nearly the same weather
+    int mm, mpad, ppad;           // mpad / ppad: rows of the member / parameter-set arrays (members padded to 32 when mm)
+    __host__ __device__ __forceinline__ size_t mi(const int m, const int r) const { return mm ? (size_t)r * mpad + m : (size_t)m * stride + r; }
+    __host__ __device__ __forceinline__ size_t qi_of(const int ps, const int r) const { return mm ? (size_t)r * ppad + ps : (size_t)ps * stride + r; }
+    __device__ __forceinline__ size_t qi(const int m, const int r) const { return qi_of(member_pset[m], r); }
+    // element (m, band b, r) of a band array with nb bands = bi(m, r, nb) + b * bs()
+    __host__ __device__ __forceinline__ size_t bi(const int m, const int r, const int nb) const { return mm ? (size_t)r * mpad + m : (size_t)m * nb * stride + r; }
+    __host__ __device__ __forceinline__ size_t bs() const { return mm ? (size_t)stride * mpad : (size_t)stride; }
+    // forcing [slot][fmember][cell] (cell-minor) / [slot][cell][fmember] (member-minor)
+    __host__ __device__ __forceinline__ size_t fi(const int slot, const int m, const int r) const {
+        if (!forcing_per_member) return (size_t)slot * stride + r;
+        return mm ? ((size_t)slot * stride + r) * mpad + m : ((size_t)slot * nmember + m) * stride + r;
+    }
     unsigned long long *stamps;   // optional (wgk_stamps): [2: V, R][2: first warp start, last warp end][STAMP_DAYS] %globaltimer ns of the
                                   // level-0 tasks of a call, i.e. their duration INSIDE the running graph; null = off
 };
@@ -207,8 +223,8 @@ struct LocalFlux {
 
 __device__ __forceinline__ LocalIn local_load(const WgkParams &p, const int r, const int m) {
     const WgkArrays &a = p.a;
-    const size_t i = (size_t)m * p.stride + r;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const size_t i = p.mi(m, r);
+    const size_t q = p.qi(m, r);
     LocalIn li;
     li.contcell = a.contcell[r];
     li.flags = a.s_flags[r];
@@ -239,7 +255,7 @@ __device__ __forceinline__ LocalIn local_load(const WgkParams &p, const int r, c
 
 __device__ __forceinline__ LocalFlux local_flux_load(const WgkParams &p, const int r, const int m) {
     const WgkArrays &a = p.a;
-    const size_t i = (size_t)m * p.stride + r;
+    const size_t i = p.mi(m, r);
     LocalFlux fx;
     fx.owPrec = a.openwater_prec[i];
     fx.owPET = a.openwater_pet[i];
@@ -257,8 +273,8 @@ __device__ __forceinline__ LocalFlux local_flux_load(const WgkParams &p, const i
 __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, const int m, const int slot, SnowStage *st,
                                               LocalIn *li = nullptr, LocalFlux *fx = nullptr) {
     const WgkArrays &a = p.a;
-    const size_t i = (size_t)m * p.stride + r;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const size_t i = p.mi(m, r);
+    const size_t q = p.qi(m, r);
     const int tid = threadIdx.x & (VBLOCK - 1);  // column of the (128-thread) staging block handed in by the kernel
     double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r + p.stride;
     const int32_t *__restrict__ E = a.s_elev32 + r + p.stride;
@@ -267,7 +283,7 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
     // trip instead of one per use (the compiler may not move a load above a store or an early return).
     const int in_contcell = a.contcell[r], in_tbc = a.toBeCalculated[r], started = a.status_laf_next[i];
     const double in_laf = a.land_area_frac[i], in_laf_next = a.land_area_frac_next[i], in_laf_prev = a.land_area_frac_prev[i];
-    const float4 f = p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r];
+    const float4 f = p.forcing[p.fi(slot, m, r)];
     const int lc = a.landcover[r] - 1;
     const double P_T_SNOWFZ = a.p_snowfz[q];
     const double P_T_SNOWMT = a.p_snowmt[q];
@@ -729,8 +745,8 @@ __device__ __forceinline__ void v_mode(const WgkParams &p, VTile<C> &sm, const i
 #endif
     int mode = 0;
     if (r >= begin && r < end && a.contcell[r]) {  // integrateWGHM.cpp:772
-        const size_t i = (size_t)m * p.stride + r;
-        const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+        const size_t i = p.mi(m, r);
+        const size_t q = p.qi(m, r);
         // daily.cpp:159-169, routing.h:246-251 (all candidates are loaded at once: one memory round trip)
         const int started = a.status_laf_next[i];
         const double laf_cur = a.land_area_frac[i], laf_next = a.land_area_frac_next[i], laf_prev = a.land_area_frac_prev[i];
@@ -743,7 +759,7 @@ __device__ __forceinline__ void v_mode(const WgkParams &p, VTile<C> &sm, const i
             mode = VM_ACTIVE;
             const bool noland = (landAreaFrac <= 0.);
             if (noland) mode |= VM_NOLAND;
-            const float4 f = p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r];
+            const float4 f = p.forcing[p.fi(slot, m, r)];
             const double T = (double)f.y;
             const double grad = a.p_gradnt[q], fz = a.p_snowfz[q];
             const double ddf = a.p_degday[q] * a.lct_ddf[a.landcover[r] - 1];  // (M_DEGDAY_F * ddf_lct) * (...) keeps the reference association
@@ -793,12 +809,12 @@ __device__ __forceinline__ void v_head(const WgkParams &p, VTile<C> &sm, const i
     const int mode = sm.mode[lane];
     if (!(mode & VM_ACTIVE)) return;
     const int r = r0 + lane;
-    const size_t i = (size_t)m * p.stride + r;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const size_t i = p.mi(m, r);
+    const size_t q = p.qi(m, r);
     const double landAreaFrac = sm.laf[lane], lafPrev = sm.lafPrev[lane];
     const int lc = VIN_K(K_lc, a.landcover[r]) - 1;
     const float4 f = C::PRE ? sm.pforce[C::PRE ? lane : 0]
-                            : p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r];
+                            : p.forcing[p.fi(slot, m, r)];
     double dailyPrec = (double)f.x;
     const double dailyTempC = (double)f.y;
     const double dailyShortWave = (double)f.z;
@@ -1068,8 +1084,8 @@ __device__ __forceinline__ void v_tail(const WgkParams &p, VTile<C> &sm, const i
     const int mode = sm.mode[lane];
     if (!(mode & VM_ACTIVE)) return;
     const int r = r0 + lane;
-    const size_t i = (size_t)m * p.stride + r;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const size_t i = p.mi(m, r);
+    const size_t q = p.qi(m, r);
     const bool noland = (mode & VM_NOLAND) != 0;
     const double landAreaFrac = sm.laf[lane], lafPrev = sm.lafPrev[lane];
     const double dailyPrec = sm.h_prec[lane], cfa = sm.h_cfa[lane], dailyCanopyEvapo = sm.h_canopy_evapo[lane];
@@ -1321,7 +1337,7 @@ __global__ void __launch_bounds__(128) k_derive_member(const __grid_constant__ W
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, const int m, const LocalIn &li, const LocalFlux &fx) {
     const WgkArrays &a = p.a;
-    const size_t i = (size_t)m * p.stride + r;
+    const size_t i = p.mi(m, r);
     a.river_evapo[i] = 0.;  // routing.cpp:1781
     if (!li.contcell) return;
     const int flags = li.flags;
@@ -1777,7 +1793,7 @@ __global__ void __launch_bounds__(128) k_route_level(const __grid_constant__ Wgk
     if (r >= end) return;
     const int m = blockIdx.y;
     const size_t mb = (size_t)m * p.stride;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const size_t q = p.qi(m, r);
     const RiverCtx c = load_ctx(p, r, mb + r, q);
     if (!(c.flags & FL_ACTIVE)) return;
     double *qday = qbuf_of_day(p, dayofs);
@@ -1837,8 +1853,8 @@ struct PostIn {
 
 __device__ __forceinline__ PostIn post_load(const WgkParams &p, const int r, const int m) {
     const WgkArrays &a = p.a;
-    const size_t i = (size_t)m * p.stride + r;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const size_t i = p.mi(m, r);
+    const size_t q = p.qi(m, r);
     PostIn in;
     in.flags = a.s_flags[r];
     in.contf = a.contfreq[r];
@@ -1865,7 +1881,7 @@ __device__ __forceinline__ PostIn post_load(const WgkParams &p, const int r, con
 
 __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int r, const int m, const PostIn &in, const double Sr) {
     const WgkArrays &a = p.a;
-    const size_t i = (size_t)m * p.stride + r;
+    const size_t i = p.mi(m, r);
     const int flags = in.flags;
     const double contf = in.contf;
     const double cellArea = in.area;
@@ -2002,7 +2018,7 @@ __global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ Wgk
     if (r >= end) return;
     const int m = blockIdx.y;
     const size_t mb = (size_t)m * p.stride;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const size_t q = p.qi(m, r);
     WGK_INSITU_BEGIN();
     if (level == 0) WGK_INSITU_STAMP(1, 0, dayofs);
     if (level == 0) stamp_task(p, 1, 0, dayofs);
@@ -2031,8 +2047,8 @@ __device__ __forceinline__ void v_preload(const WgkParams &p, VTile<C> &sm, cons
     const WgkArrays &a = p.a;
     const int r = r0 + lane;
     if (!C::PRE || r < begin || r >= end) return;
-    const size_t i = (size_t)m * p.stride + r;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const size_t i = p.mi(m, r);
+    const size_t q = p.qi(m, r);
     // four groups of copies, dealt round-robin to the warps 1 .. NW-1
 #pragma unroll
     for (int task = 1; task <= 4; task++) {
@@ -2054,7 +2070,7 @@ __device__ __forceinline__ void v_preload(const WgkParams &p, VTile<C> &sm, cons
         sm.pk[K_ldd][lane] = a.ldd[r];
     } else if (task == 3) {
         __pipeline_memcpy_async(&sm.pforce[lane],
-                                &p.forcing[((size_t)slot * (p.forcing_per_member ? p.nmember : 1) + (p.forcing_per_member ? m : 0)) * p.stride + r],
+                                &p.forcing[p.fi(slot, m, r)],
                                 sizeof(float4));
         VP_D(HI_p_prec, a.p_prec[q]); VP_D(HI_ptc_ari, a.p_ptc_ari[q]); VP_D(HI_ptc_hum, a.p_ptc_hum[q]);
         VP_D(HI_lai_precsum, a.lai_precsum[i]); VP_D(HI_snow, a.snow[i]); VP_D(HI_netrad, a.p_netrad[q]);
@@ -2334,7 +2350,7 @@ __global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) 
     const unsigned mask = __ballot_sync(0xffffffffu, valid);  // the lanes of this warp that own a cell
     const int m = blockIdx.y;
     const size_t mb = (size_t)m * p.stride;
-    const size_t q = (size_t)p.member_pset[m] * p.stride + r;
+    const size_t q = p.qi(m, r);
     uint32_t *prog = s.progress + (size_t)m * s.nwarps;
     const int up0 = valid ? p.up_off[r] : 0, up1 = valid ? p.up_off[r + 1] : 0;
     const int dn = valid ? p.down[r] : -1;
@@ -2454,7 +2470,7 @@ __global__ void __launch_bounds__(256) k_total_storage(const __grid_constant__ W
     const WgkArrays &a = p.a;
     double s = 0.;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.ncell; r += gridDim.x * blockDim.x) {
-        const size_t i = (size_t)m * p.stride + r;
+        const size_t i = p.mi(m, r);
         const double laf = (0 == a.status_laf_next[i]) ? a.land_area_frac[i] : a.land_area_frac_next[i];
         const double land = (a.canopy[i] + a.snow[i] + a.soil[i]) * a.area[r] / C1E6 * laf / C100;
         s += land + a.gw[i] + a.loc_lake_stor[i] + a.loc_wetl_stor[i] + a.glo_lake_stor[i] + a.glo_wetl_stor[i]
@@ -2483,7 +2499,7 @@ __device__ __forceinline__ double laf_of(const WgkArrays &a, const size_t i) {
 // `ndays` entries (Cell::mean): canopy / snow / soil carry the month-end value on every day of the month.
 __device__ __forceinline__ void state_of_cell(const WgkParams &p, const int x, const int m, const int kind, const int ndays, double v[10]) {
     const WgkArrays &a = p.a;
-    const size_t i = (size_t)m * p.stride + x;
+    const size_t i = p.mi(m, x);
     const double laf = laf_of(a, i), contf = a.contfreq[x];
     const double land[3] = {a.canopy[i] * laf / contf, a.snow[i] * laf / contf, a.soil[i] * laf / contf};
     const double denom = ((a.area[x] * (contf / C100)) / C1E6);
@@ -2587,7 +2603,7 @@ __global__ void __launch_bounds__(128) k_enkf_update(const __grid_constant__ Wgk
     if (j >= ncells) return;
     const WgkArrays &a = p.a;
     const int x = pos[j];
-    const size_t i = (size_t)m * p.stride + x;
+    const size_t i = p.mi(m, x);
     double w[10], mon[10];
     state_of_cell(p, x, m, 1, ndays, w);
     state_of_cell(p, x, m, 0, ndays, mon);
