@@ -102,10 +102,15 @@ int wgk_field_info(int field, const char **name, const char **dtype, int64_t *ho
 int wgk_set_field(wgk_ctx *ctx, int field, int index, const void *host, size_t bytes);
 int wgk_get_field(wgk_ctx *ctx, int field, int index, void *host, size_t bytes);
 int wgk_set_member_pset(wgk_ctx *ctx, int member, int pset);
-/* raw device pointer of a per-member field (device layout: routing order, padded row of
- * wgk_cell_stride() elements per member) for zero-copy collectives (NCCL via torch) */
+/* raw device pointer of element (member, device position 0) of a per-member field, for zero-copy access (NCCL via
+ * torch).  Device layout: positions in routing order; element (member, position x) lies wgk_member_stride() * member +
+ * wgk_cell_stride() * x elements behind the field's base.  wgk_layout: 0 = cell-minor [member][cell] (few members),
+ * 1 = member-minor [cell][member] with the members padded to a multiple of 32 (many members: a warp works on 32 members
+ * of one cell; chosen by wgk_create from the member count, results are bit-identical between the layouts). */
 void *wgk_device_ptr(wgk_ctx *ctx, int field, int member);
 int64_t wgk_cell_stride(const wgk_ctx *ctx);
+int64_t wgk_member_stride(const wgk_ctx *ctx);
+int wgk_layout(const wgk_ctx *ctx);
 /* rank_of_cell[n] = position of reference cell n in the device (routing) order */
 int wgk_get_device_order(const wgk_ctx *ctx, int32_t *rank_of_cell);
 

@@ -72,7 +72,7 @@ Emu *emu_create(int ncell, const int32_t *rout_order, const int32_t *downstream)
     p.up_idx = e->up_idx.data(); p.down = e->down.data(); p.level_off = e->level_off.data(); p.cal = e->cal;
     p.record = nullptr; p.record_cells = nullptr; p.nrec = 0; p.record_max_days = 0;
     p.ncell = ncell; p.stride = e->stride; p.nmember = 1; p.npset = 1; p.forcing_nslots = 31; p.forcing_per_member = 0;
-    p.restart = 0; p.nlevels = e->nlevels;
+    p.restart = 0; p.nlevels = e->nlevels; p.mm = 0; p.mpad = 1; p.ppad = 1;
     e->qbuf.assign((size_t)wgk::QBUF_K * e->stride, 0.0);
     p.qbuf = e->qbuf.data(); p.cal_days = e->cal_days;
     return e;

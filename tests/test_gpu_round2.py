@@ -285,3 +285,65 @@ def test_long_single_calls_vs_oracle(world3000):
             rep.add(name, o.field(name), m.get(name), tag=sd - 1)
         cells = {f[2] for f in rep.flips}
         assert len(cells) <= max(2, w.ng // 500) and rep.worst < 1e-6, (rep.summary(), sorted(rep.flips, key=lambda f: -f[5])[:10])
+
+
+def test_member_minor_layout_is_bit_identical(world3000, monkeypatch):
+    """lane = member: the member-minor layout [band][cell][member] (a warp = 32 members of one cell, chosen automatically for
+    large ensembles / parameter sweeps) against the cell-minor layout: 40 members (padded to 64 lanes) with 40 different
+    parameter sets and per-member forcing, 14 days; every state / flux field of several members, the snow bands, the station
+    record, the monthly state vector, the ensemble moments and the field round trip must be the same bits"""
+    from oracle import synth_world as sw, wg_init
+    import watergap2_b200 as wg
+    from watergap2_b200.ensemble import device_tensor
+    w = world3000
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    base = sw.forcing_month(w, 1901, 1)
+    nm = 40
+    names = wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS + ["discharge", "snow_bands"]
+    rng = np.random.default_rng(5)
+    forc = []
+    for k in range(nm):
+        forc.append(((base["P"] * np.exp(rng.normal(0., 0.1, base["P"].shape))).astype(np.float32),
+                     (base["T"] + rng.normal(0., 1.5, base["T"].shape)).astype(np.float32)))
+    cells = np.arange(3, w.ng, 17, dtype=np.int32)
+    out = []
+    for layout in ("cells", "members"):
+        monkeypatch.setenv("WGK_LAYOUT", layout)
+        monkeypatch.setenv("WGK_DAY_SCHEDULE", "wholeday")
+        monkeypatch.setenv("WGK_VERTICAL_FORM", "cells")
+        m = wg.Model(w.ng, nmember=nm, npset=nm)
+        assert m.layout == layout
+        m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+        m.load(ini, member=0, pset=0)
+        for k in range(1, nm):
+            m.copy_pset(0, k)
+            m.copy_member(0, k)
+            m.fill("gamma_hbv", 0.5 + 0.1 * k, index=k)
+            m.fill("p_snowfz", -1.0 + 0.05 * k, index=k)
+            m.fill("p_gwoutf", 0.005 + 0.001 * k, index=k)
+        soil7 = ini["soil"] + 3.25
+        m.set("soil", soil7, 7)  # host upload of one member's field in either layout
+        assert np.array_equal(m.get("soil", 7), soil7) and np.array_equal(m.get("soil", 6), ini["soil"])
+        assert np.array_equal(m.get("gamma_hbv", 3), np.full(w.ng, 0.5 + 0.1 * 3))
+        m.forcing_reserve(31, per_member=True)
+        for k in range(nm):
+            m.set_forcing(0, 31, forc[k][0], forc[k][1], base["SW"], base["LW"], member=k)
+            m.synchronize()
+        m.record_cells(cells[:20], 31)
+        m.step_days(1, 0, 1, 0, 4)
+        m.month_begin()
+        m.step_days(5, 0, 5, 4, 10)
+        ps, pq, n = m.ensemble_moments("month")
+        m.synchronize()
+        mom = device_tensor(ps, (2, n, 10), 0).cpu().numpy()
+        out.append(({(k, mem): m.get(k, mem) for k in names for mem in (0, 7, 31, 32, 39)}, m.get_record(14, 33),
+                    m.state_vector(cells, "month", member=38), mom, m.total_storage_km3(39)))
+        m.close()
+    assert np.array_equal(out[0][1], out[1][1]) and np.abs(out[0][1]).sum() > 0
+    assert np.array_equal(out[0][2], out[1][2])
+    assert np.array_equal(out[0][3], out[1][3])
+    assert out[0][4] == out[1][4]
+    for k in out[0][0]:
+        assert np.array_equal(out[0][0][k], out[1][0][k]), k
+    assert not np.array_equal(out[0][0][("soil", 0)], out[0][0][("soil", 39)])

@@ -93,6 +93,9 @@ def lib():
     L.wgk_device_ptr.restype = vp
     L.wgk_cell_stride.argtypes = [vp]
     L.wgk_cell_stride.restype = ctypes.c_int64
+    L.wgk_member_stride.argtypes = [vp]
+    L.wgk_member_stride.restype = ctypes.c_int64
+    L.wgk_layout.argtypes = [vp]
     L.wgk_get_device_order.argtypes = [vp, vp]
     L.wgk_forcing_reserve.argtypes = [vp, ci, ci]
     L.wgk_set_forcing.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, ci]
@@ -371,3 +374,12 @@ class Model:
     @property
     def cell_stride(self):
         return self._L.wgk_cell_stride(self._c)
+
+    @property
+    def member_stride(self):
+        return self._L.wgk_member_stride(self._c)
+
+    @property
+    def layout(self):
+        """'cells' ([member][cell], a warp = 32 cells of one member) or 'members' ([cell][member], a warp = 32 members of one cell)"""
+        return "members" if self._L.wgk_layout(self._c) == 1 else "cells"

@@ -51,6 +51,11 @@ const ParamMap kParamMap[] = {
 struct wgk_ctx {
     int device = 0;
     int ncell = 0, stride = 0, nmember = 0, npset = 0;
+    // layout of the member / parameter-set arrays (WgkParams): cell-minor [member][cell] or member-minor [cell][member]
+    bool mm = false;
+    int mpad = 0, ppad = 0;  // rows of the member / parameter-set arrays (padded to 32 when member-minor)
+    void *d_stage = nullptr;  // device staging row for strided uploads / downloads (member-minor)
+    size_t d_stage_bytes = 0;
     wgk_options opt{};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -161,6 +166,14 @@ void **field_slot(wgk_ctx *c, int f) { return (void **)((char *)&c->arrays + kFi
 size_t field_rows(const wgk_ctx *c, int f) {
     switch (kFields[f].scope) {
         case WGK_SCOPE_CELL: return 1;
+        case WGK_SCOPE_PSET: return (size_t)c->ppad;
+        case WGK_SCOPE_MEMBER: return (size_t)c->mpad;
+        default: return 1;
+    }
+}
+// valid indices of a field (members / parameter sets; the padded rows of the member-minor layout are not addressable)
+size_t field_index_count(const wgk_ctx *c, int f) {
+    switch (kFields[f].scope) {
         case WGK_SCOPE_PSET: return (size_t)c->npset;
         case WGK_SCOPE_MEMBER: return (size_t)c->nmember;
         default: return 1;
@@ -179,6 +192,36 @@ int ensure_stage(wgk_ctx *c, size_t bytes) {
     CU(cudaMallocHost(&c->h_stage, bytes));
     c->h_stage_bytes = bytes;
     return 0;
+}
+
+// distance (in elements) between two consecutive cells of one index of a member / parameter-set field: 1 in the cell-minor
+// layout, the padded row count in the member-minor layout ([band][cell][index])
+int index_pad(const wgk_ctx *c, int f) {
+    if (!c->mm) return 1;
+    if (kFields[f].scope == WGK_SCOPE_MEMBER) return c->mpad;
+    if (kFields[f].scope == WGK_SCOPE_PSET) return c->ppad;
+    return 1;
+}
+int ensure_dstage(wgk_ctx *c, size_t bytes) {
+    if (c->d_stage_bytes >= bytes) return 0;
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_stage);
+    c->d_stage = nullptr;
+    c->d_stage_bytes = 0;
+    CU(cudaMalloc(&c->d_stage, bytes));
+    c->d_stage_bytes = bytes;
+    return 0;
+}
+// dst[k * dst_stride] = src[k * src_stride] for k < n, elements of `es` bytes (1, 2, 4 or 8), on the context's stream
+void launch_strided(wgk_ctx *c, char *dst, size_t dst_stride, const char *src, size_t src_stride, size_t n, int es) {
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    switch (es) {
+        case 1: wgk::k_strided_copy<uint8_t><<<grid, 256, 0, c->stream>>>((uint8_t *)dst, dst_stride, (const uint8_t *)src, src_stride, n); break;
+        case 2: wgk::k_strided_copy<uint16_t><<<grid, 256, 0, c->stream>>>((uint16_t *)dst, dst_stride, (const uint16_t *)src, src_stride, n); break;
+        case 4: wgk::k_strided_copy<uint32_t><<<grid, 256, 0, c->stream>>>((uint32_t *)dst, dst_stride, (const uint32_t *)src, src_stride, n); break;
+        default: wgk::k_strided_copy<unsigned long long><<<grid, 256, 0, c->stream>>>((unsigned long long *)dst, dst_stride, (const unsigned long long *)src, src_stride, n); break;
+    }
+    c->launches++;
 }
 
 WgkParams make_params(const wgk_ctx *c) {
@@ -209,6 +252,9 @@ WgkParams make_params(const wgk_ctx *c) {
     p.restart = c->opt.restart;
     p.month_acc = c->month_acc ? 1 : 0;
     p.nlevels = c->nlevels;
+    p.mm = c->mm ? 1 : 0;
+    p.mpad = c->mpad;
+    p.ppad = c->ppad;
     p.stamps = c->d_stamps;
     return p;
 }
@@ -233,8 +279,13 @@ void *vertical_fn(const wgk_ctx *c) {
     return c->form == 1 ? (void *)wgk::k_vertical<wgk::VCfgSmall> : c->form == 2 ? (void *)wgk::k_vertical<wgk::VCfgMid> : (void *)wgk::k_vertical_tpc;
 }
 dim3 cells_pre_block(const wgk_ctx *c) { return dim3(c->form == 1 ? wgk::VCfgSmall::THREADS : c->form == 2 ? wgk::VCfgMid::THREADS : wgk::VBLOCK); }
+// grid of a cell-parallel kernel of `block` threads over `ncells` device positions (wgk::map_thread)
+dim3 cell_grid(const wgk_ctx *c, int ncells, int block) {
+    if (c->mm) return dim3((unsigned)(((long long)ncells * c->mpad + block - 1) / block), 1);
+    return dim3((ncells + block - 1) / block, c->nmember);
+}
 dim3 cells_pre_grid(const wgk_ctx *c, int begin, int end) {
-    return c->form ? dim3(wgk::v_num_tiles(begin, end), c->nmember) : dim3((end - begin + wgk::VBLOCK - 1) / wgk::VBLOCK, c->nmember);
+    return c->form ? dim3(wgk::v_num_tiles(begin, end), c->nmember) : cell_grid(c, end - begin, wgk::VBLOCK);
 }
 cudaError_t launch_cells_pre(wgk_ctx *c, const WgkParams &p, int d, int begin, int end) {
     void *args[] = {(void *)&p, &d, &begin, &end};
@@ -253,12 +304,12 @@ int enqueue_vertical(wgk_ctx *c, const WgkParams &p, int d) {
 }
 int enqueue_routing(wgk_ctx *c, const WgkParams &p, int d) {
     int n = 0;
-    dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
+    const dim3 block(128), grid = cell_grid(c, c->ncell, 128);
     wgk::k_route_local<<<grid, block, 0, c->stream>>>(p);
     n++;
     for (int l = 0; l < c->tail_level0; l++) {
         const int cnt = c->level_off[l + 1] - c->level_off[l];
-        dim3 g((cnt + 127) / 128, c->nmember);
+        const dim3 g = cell_grid(c, cnt, 128);
         wgk::k_route_level<<<g, block, 0, c->stream>>>(p, d, l);
         n++;
     }
@@ -279,7 +330,7 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
     for (int d = 0; d < ndays; d++) {
         for (int l = 0; l < c->tail_level0; l++) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
-            const dim3 g((end - begin + 127) / 128, c->nmember);
+            const dim3 g = cell_grid(c, end - begin, 128);
             launch_cells_pre(c, p, d, begin, end);
             wgk::k_river_level<<<g, block, 0, c->stream>>>(p, d, l);
             n += 2;
@@ -353,7 +404,7 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
         for (int l = 0; l < W; l++) {
             int begin = c->level_off[l], end = c->level_off[l + 1];
             int dd = d, ll = l;
-            const dim3 grid((end - begin + 127) / 128, c->nmember);
+            const dim3 grid = cell_grid(c, end - begin, 128);
             // V(d, l): vertical balance + local routing, waits only for the cells' own previous day
             void *a1[] = {&pp, &dd, &begin, &end};
             cudaGraphNode_t pre, node;
@@ -445,7 +496,7 @@ int launch_owner(wgk_ctx *c, const WgkParams &p, int ndays) {
 // parameter upload (never inside a graph capture)
 int ensure_derived(wgk_ctx *c) {
     if (c->member_dirty) {
-        dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
+        const dim3 block(128), grid = cell_grid(c, c->ncell, 128);
         wgk::k_derive_member<<<grid, block, 0, c->stream>>>(make_params(c));
         c->launches++;
         c->member_dirty = false;
@@ -468,13 +519,13 @@ int ensure_derived(wgk_ctx *c) {
     c->d_gbody = nullptr;
     CU(cudaMalloc(&c->d_gidx, sizeof(int32_t) * c->ncell));
     CU(cudaMemcpy(c->d_gidx, gidx.data(), sizeof(int32_t) * c->ncell, cudaMemcpyHostToDevice));
-    const size_t nb = (size_t)c->nmember * std::max(1, n) * wgk::GB_N;
+    const size_t nb = (size_t)c->mpad * std::max(1, n) * wgk::GB_N;
     CU(cudaMalloc(&c->d_gbody, nb * sizeof(double)));
     CU(cudaMemset(c->d_gbody, 0, nb * sizeof(double)));
     c->ngbody = n;
     // cells that are inactive (now) never write their discharge entry: no stale value of an earlier configuration may
     // feed a downstream gather or the published discharge field (every active cell rewrites its entry before it is read)
-    CU(cudaMemsetAsync(c->d_qbuf, 0, (size_t)wgk::QBUF_K * c->nmember * c->stride * sizeof(double), c->stream));
+    CU(cudaMemsetAsync(c->d_qbuf, 0, (size_t)wgk::QBUF_K * c->mpad * c->stride * sizeof(double), c->stream));
     c->derived_dirty = false;
     drop_graph(c);
     return 0;
@@ -537,6 +588,23 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
         // co-resident (<= 75 776 on B200).  Opt-in: measured slower than the wavefront (93 vs 67 us per day, see the kernel).
         c->owner_mode = (e && !strcmp(e, "owner")) ? 1 : 0;
     }
+    {   // Layout.  Many members in the throughput regime: member-minor, a warp = 32 members of one cell (lane = member), so that the
+        // lanes share the cell's statics, land cover, water-body class and nearly the same weather (cell-minor warps run 20 of 32
+        // lanes per instruction and are issue-bound, profiles/r1_k_vertical_tpc_m16.md).  It comes with the thread-per-cell kernels,
+        // the whole-day schedule and one launch per routing level (no persistent narrow-level CTA).  Results are bit-identical
+        // between the layouts (tests/test_gpu_round2.py::test_member_minor_layout_is_bit_identical).
+        const char *e = getenv("WGK_LAYOUT");  // "members" | "cells"
+        if (e && !strcmp(e, "members")) c->mm = true;
+        else if (e && !strcmp(e, "cells")) c->mm = false;
+        else c->mm = c->whole_day && c->form == 0 && c->owner_mode == 0 && nmember >= 32;
+        if (c->mm) {
+            c->form = 0;
+            c->whole_day = true;
+            c->owner_mode = 0;
+        }
+        c->mpad = c->mm ? (nmember + 31) / 32 * 32 : nmember;
+        c->ppad = c->mm ? (npset == 1 ? 1 : (npset + 31) / 32 * 32) : npset;
+    }
     if (c->opt.tail_threshold <= 0) {
         const char *e = getenv("WGK_TAIL_THRESHOLD");
         c->opt.tail_threshold = (e && atoi(e) > 0) ? atoi(e) : 256;
@@ -569,7 +637,7 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     CU(cudaMalloc(&c->d_partial, sizeof(double) * 256));
     CU(cudaMalloc(&c->d_cal_days, sizeof(int32_t) * 4 * MAX_CALL_DAYS));
     CU(cudaMemsetAsync(c->d_cal_days, 0, sizeof(int32_t) * 4 * MAX_CALL_DAYS, c->stream));
-    const size_t qn = (size_t)wgk::QBUF_K * nmember * c->stride;
+    const size_t qn = (size_t)wgk::QBUF_K * c->mpad * c->stride;
     if (cudaMalloc(&c->d_qbuf, qn * sizeof(double)) != cudaSuccess) return fail(c, WGK_ERR_NOMEM, "cudaMalloc discharge buffers");
     CU(cudaMemsetAsync(c->d_qbuf, 0, qn * sizeof(double), c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -588,7 +656,7 @@ void wgk_destroy(wgk_ctx *c) {
     cudaFree(c->d_cell_of_rank); cudaFree(c->d_up_off); cudaFree(c->d_up_idx); cudaFree(c->d_down);
     cudaFree(c->d_level_off); cudaFree(c->d_member_pset); cudaFree(c->d_cal); cudaFree(c->d_forcing);
     cudaFree(c->d_gidx); cudaFree(c->d_gbody); cudaFree(c->d_cal_days); cudaFree(c->d_qbuf);
-    cudaFree(c->d_mom_sum); cudaFree(c->d_mom_sumsq); cudaFree(c->d_mom_pos); cudaFree(c->d_stamps);
+    cudaFree(c->d_mom_sum); cudaFree(c->d_mom_sumsq); cudaFree(c->d_mom_pos); cudaFree(c->d_stamps); cudaFree(c->d_stage);
     cudaFree(c->d_fstage); cudaFree(c->d_record); cudaFree(c->d_record_cells); cudaFree(c->d_partial);
     cudaFree(c->d_own_warp_begin); cudaFree(c->d_own_warp_end); cudaFree(c->d_own_cell_warp); cudaFree(c->d_own_progress);
     cudaFree(c->d_own_abort); cudaFree(c->d_rec_head); cudaFree(c->d_rec_next); cudaFree(c->d_own_timing); cudaFree(c->d_own_ring);
@@ -704,7 +772,7 @@ int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downs
         }
     // narrow tail: first level from which every level has <= tail_threshold cells
     c->tail_level0 = c->nlevels;
-    for (int l = c->nlevels - 1; l >= 0; l--) {
+    for (int l = c->nlevels - 1; l >= 0 && !c->mm; l--) {  // (member-minor: every level is a launch of its own, nmember threads per cell)
         if (c->level_off[l + 1] - c->level_off[l] <= c->opt.tail_threshold) c->tail_level0 = l;
         else break;
     }
@@ -738,7 +806,7 @@ int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downs
         CU(upload(c->d_own_cell_warp, cw));
         if (c->d_own_progress) cudaFree(c->d_own_progress);
         c->d_own_progress = nullptr;
-        CU(cudaMalloc(&c->d_own_progress, sizeof(uint32_t) * (size_t)c->nmember * std::max(1, c->owner_nwarps)));
+        CU(cudaMalloc(&c->d_own_progress, sizeof(uint32_t) * (size_t)c->nmember * std::max(1, c->owner_nwarps)));  // (cell-minor only)
         CU(cudaMemset(c->d_own_progress, 0, sizeof(uint32_t) * (size_t)c->nmember * std::max(1, c->owner_nwarps)));
         if (c->d_own_ring) CU(cudaMemset(c->d_own_ring, 0, sizeof(unsigned long long) * 2 * wgk::QBUF_K * (size_t)c->nmember * c->stride));
         c->owner_base = 0;
@@ -769,7 +837,9 @@ int wgk_get_device_order(const wgk_ctx *c, int32_t *rank_of_cell) {
     return WGK_OK;
 }
 
-int64_t wgk_cell_stride(const wgk_ctx *c) { return c ? c->stride : 0; }
+int64_t wgk_cell_stride(const wgk_ctx *c) { return c ? (c->mm ? c->mpad : 1) : 0; }
+int64_t wgk_member_stride(const wgk_ctx *c) { return c ? (c->mm ? 1 : c->stride) : 0; }
+int wgk_layout(const wgk_ctx *c) { return c ? (c->mm ? 1 : 0) : WGK_ERR_ARG; }
 
 // ---------------------------------------------------------------------------------------
 // fields
@@ -798,7 +868,7 @@ int wgk_field_info(int field, const char **name, const char **dtype, int64_t *co
 
 static int set_field_raw(wgk_ctx *c, int f, int index, const void *host, size_t bytes) {
     const FieldInfo &fi = kFields[f];
-    if (index < 0 || (size_t)index >= field_rows(c, f)) return fail(c, WGK_ERR_ARG, "index %d out of range for field %s", index, fi.name);
+    if (index < 0 || (size_t)index >= field_index_count(c, f)) return fail(c, WGK_ERR_ARG, "index %d out of range for field %s", index, fi.name);
     const size_t row_elems = field_row_elems(c, f);
     char *dst = (char *)*field_slot(c, f) + (size_t)index * row_elems * fi.elsize;
     if (fi.scope == WGK_SCOPE_TABLE) {
@@ -826,7 +896,16 @@ static int set_field_raw(wgk_ctx *c, int f, int index, const void *host, size_t 
         const size_t n = (size_t)c->cell_of_rank[r];
         for (int b = 0; b < nb; b++) memcpy(tmp + ((size_t)b * st + r) * es, src + (n * nb + b) * es, es);
     }
-    CU(cudaMemcpyAsync(dst, tmp, row_bytes, cudaMemcpyHostToDevice, c->stream));
+    const int pad = index_pad(c, f);
+    if (pad > 1) {  // member-minor: the dense row [band][cell] goes to a device staging row and is scattered with stride `pad`
+        rc = ensure_dstage(c, row_bytes);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(c->d_stage, tmp, row_bytes, cudaMemcpyHostToDevice, c->stream));
+        launch_strided(c, (char *)*field_slot(c, f) + (size_t)index * es, (size_t)pad, (const char *)c->d_stage, 1, row_elems, es);
+        CU(cudaGetLastError());
+    } else {
+        CU(cudaMemcpyAsync(dst, tmp, row_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
     CU(cudaStreamSynchronize(c->stream));
     if (fi.scope != WGK_SCOPE_MEMBER) c->derived_dirty = true;
     if (f == WGK_F_snow_bands) c->member_dirty = true;
@@ -861,7 +940,7 @@ int wgk_get_field(wgk_ctx *c, int f, int index, void *host, size_t bytes) {
     if (f < 0 || f >= WGK_F_COUNT) return fail(c, WGK_ERR_ARG, "unknown field %d", f);
     CU(cudaSetDevice(c->device));
     const FieldInfo &fi = kFields[f];
-    if (index < 0 || (size_t)index >= field_rows(c, f)) return fail(c, WGK_ERR_ARG, "index %d out of range for field %s", index, fi.name);
+    if (index < 0 || (size_t)index >= field_index_count(c, f)) return fail(c, WGK_ERR_ARG, "index %d out of range for field %s", index, fi.name);
     const size_t row_elems = field_row_elems(c, f);
     const char *src = (const char *)*field_slot(c, f) + (size_t)index * row_elems * fi.elsize;
     if (fi.scope == WGK_SCOPE_TABLE) {
@@ -876,7 +955,16 @@ int wgk_get_field(wgk_ctx *c, int f, int index, void *host, size_t bytes) {
     const size_t row_bytes = row_elems * fi.elsize;
     int rc = ensure_stage(c, row_bytes);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(c->h_stage, src, row_bytes, cudaMemcpyDeviceToHost, c->stream));
+    const int pad = index_pad(c, f);
+    if (pad > 1) {  // member-minor: gather the strided elements of this index into a dense device row first
+        rc = ensure_dstage(c, row_bytes);
+        if (rc) return rc;
+        launch_strided(c, (char *)c->d_stage, 1, (const char *)*field_slot(c, f) + (size_t)index * fi.elsize, (size_t)pad, row_elems, fi.elsize);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(c->h_stage, c->d_stage, row_bytes, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        CU(cudaMemcpyAsync(c->h_stage, src, row_bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
     CU(cudaStreamSynchronize(c->stream));
     const int es = fi.elsize, nb = fi.bands, ng = c->ncell, st = c->stride;
     const char *tmp = (const char *)c->h_stage;
@@ -899,9 +987,9 @@ int wgk_set_member_pset(wgk_ctx *c, int member, int pset) {
 
 void *wgk_device_ptr(wgk_ctx *c, int f, int member) {
     if (!c || f < 0 || f >= WGK_F_COUNT) return nullptr;
-    if (member < 0 || (size_t)member >= field_rows(c, f)) return nullptr;
+    if (member < 0 || (size_t)member >= field_index_count(c, f)) return nullptr;
     if (f == WGK_F_snow_bands) c->member_dirty = true;  // the caller may write the bands on the device
-    return (char *)*field_slot(c, f) + (size_t)member * field_row_elems(c, f) * kFields[f].elsize;
+    return (char *)*field_slot(c, f) + (size_t)member * (index_pad(c, f) > 1 ? 1 : field_row_elems(c, f)) * kFields[f].elsize;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -914,7 +1002,7 @@ int wgk_forcing_reserve(wgk_ctx *c, int nslots, int per_member) {
     CU(cudaStreamSynchronize(c->stream));
     if (c->d_forcing) cudaFree(c->d_forcing);
     c->d_forcing = nullptr;
-    const size_t n = (size_t)nslots * (per_member ? c->nmember : 1) * c->stride;
+    const size_t n = (size_t)nslots * (per_member ? c->mpad : 1) * c->stride;
     cudaError_t e = cudaMalloc(&c->d_forcing, n * sizeof(float4));
     if (e != cudaSuccess) return fail(c, WGK_ERR_NOMEM, "cudaMalloc forcing (%zu bytes): %s", n * sizeof(float4), cudaGetErrorString(e));
     CU(cudaMemsetAsync(c->d_forcing, 0, n * sizeof(float4), c->stream));
@@ -961,12 +1049,15 @@ static int set_forcing_impl(wgk_ctx *c, int slot0, int ndays, int member, const 
     CU(cudaMemcpyAsync(dT, temp, elems * sizeof(float), cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(dS, sw, elems * sizeof(float), cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(dL, lw, elems * sizeof(float), cudaMemcpyHostToDevice, cs));
-    const int F = c->forcing_per_member ? c->nmember : 1;
+    // element (slot, member, cell) of the device forcing: WgkParams::fi
+    const int F = c->forcing_per_member ? c->mpad : 1;
     const size_t pitch = (size_t)F * c->stride;
-    float4 *dst = c->d_forcing + (size_t)slot0 * pitch + (size_t)(c->forcing_per_member ? member : 0) * c->stride;
+    const bool strided = c->mm && c->forcing_per_member;
+    const size_t cell_stride = strided ? (size_t)c->mpad : 1;
+    float4 *dst = c->d_forcing + (size_t)slot0 * pitch + (size_t)(c->forcing_per_member ? member : 0) * (strided ? 1 : c->stride);
     dim3 block(128), grid((c->ncell + 127) / 128, std::min(ndays, 31));
-    if (big_endian) wgk::k_forcing_pack<true><<<grid, block, 0, cs>>>(dst, dP, dT, dS, dL, c->d_cell_of_rank, c->ncell, ndays, stride, pitch);
-    else wgk::k_forcing_pack<false><<<grid, block, 0, cs>>>(dst, dP, dT, dS, dL, c->d_cell_of_rank, c->ncell, ndays, stride, pitch);
+    if (big_endian) wgk::k_forcing_pack<true><<<grid, block, 0, cs>>>(dst, dP, dT, dS, dL, c->d_cell_of_rank, c->ncell, ndays, stride, pitch, cell_stride);
+    else wgk::k_forcing_pack<false><<<grid, block, 0, cs>>>(dst, dP, dT, dS, dL, c->d_cell_of_rank, c->ncell, ndays, stride, pitch, cell_stride);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev_forcing, cs));
@@ -1034,7 +1125,7 @@ static int fill_calendar(wgk_ctx *c, int day, int month, int dom, int slot, int 
 
 // make the discharge of day offset `d` of the finished call the value of the "discharge" field
 static int publish_discharge(wgk_ctx *c, int d) {
-    const size_t n = (size_t)c->nmember * c->stride;
+    const size_t n = (size_t)c->mpad * c->stride;
     CU(cudaMemcpyAsync(c->arrays.discharge, c->d_qbuf + (size_t)(d % wgk::QBUF_K) * n, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return WGK_OK;
 }
@@ -1146,7 +1237,7 @@ int wgk_step_days(wgk_ctx *c, int day, int month, int dom, int slot0, int ndays)
 int wgk_month_begin(wgk_ctx *c) {
     if (!c) return WGK_ERR_ARG;
     CU(cudaSetDevice(c->device));
-    CU(cudaMemsetAsync(c->arrays.mon_acc, 0, (size_t)c->nmember * 7 * c->stride * sizeof(double), c->stream));
+    CU(cudaMemsetAsync(c->arrays.mon_acc, 0, (size_t)c->mpad * 7 * c->stride * sizeof(double), c->stream));
     if (!c->month_acc) drop_graph(c);  // the flag is part of the kernel parameters baked into the graphs
     c->month_acc = true;
     c->month_days = 0;
@@ -1286,7 +1377,13 @@ int wgk_copy_index(wgk_ctx *c, int scope, int src, int dst) {
         if (kFields[f].scope != scope) continue;
         const size_t bytes = field_row_elems(c, f) * kFields[f].elsize;
         char *base = (char *)*field_slot(c, f);
-        CU(cudaMemcpyAsync(base + (size_t)dst * bytes, base + (size_t)src * bytes, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        const int pad = index_pad(c, f);
+        if (pad > 1) {
+            const int es = kFields[f].elsize;
+            launch_strided(c, base + (size_t)dst * es, (size_t)pad, base + (size_t)src * es, (size_t)pad, field_row_elems(c, f), es);
+        } else {
+            CU(cudaMemcpyAsync(base + (size_t)dst * bytes, base + (size_t)src * bytes, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        }
     }
     if (scope == WGK_SCOPE_PSET) c->derived_dirty = true;
     // (s_snowfree is a member field and is copied with the bands it describes)
@@ -1299,10 +1396,11 @@ int wgk_fill_field(wgk_ctx *c, int field, int index, double value) {
     const FieldInfo &fi = kFields[field];
     if (strcmp(fi.dtype, "f64") != 0 || fi.bands != 1 || fi.scope == WGK_SCOPE_TABLE)
         return fail(c, WGK_ERR_ARG, "wgk_fill_field: %s is not a per-cell f64 field", fi.name);
-    if (index < 0 || (size_t)index >= field_rows(c, field)) return fail(c, WGK_ERR_ARG, "index %d out of range for field %s", index, fi.name);
+    if (index < 0 || (size_t)index >= field_index_count(c, field)) return fail(c, WGK_ERR_ARG, "index %d out of range for field %s", index, fi.name);
     CU(cudaSetDevice(c->device));
-    double *dst = (double *)*field_slot(c, field) + (size_t)index * c->stride;
-    wgk::k_fill_f64<<<(c->ncell + 255) / 256, 256, 0, c->stream>>>(dst, c->ncell, value);
+    const int pad = index_pad(c, field);
+    double *dst = (double *)*field_slot(c, field) + (size_t)index * (pad > 1 ? 1 : c->stride);
+    wgk::k_fill_f64<<<(c->ncell + 255) / 256, 256, 0, c->stream>>>(dst, c->ncell, (size_t)pad, value);
     c->launches++;
     CU(cudaGetLastError());
     if (fi.scope != WGK_SCOPE_MEMBER) c->derived_dirty = true;
@@ -1403,7 +1501,7 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     cudaEvent_t ev[6];
     for (auto &e : ev) CU(cudaEventCreate(&e));
     const WgkParams p = make_params(c);
-    dim3 block(128), grid((c->ncell + 127) / 128, c->nmember);
+    const dim3 block(128), grid = cell_grid(c, c->ncell, 128);
     CU(cudaEventRecord(ev[0], c->stream));
     launch_vertical(c, p, 0);
     CU(cudaEventRecord(ev[1], c->stream));
@@ -1412,7 +1510,7 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     int n = 3;
     for (int l = 0; l < c->tail_level0; l++) {
         const int cnt = c->level_off[l + 1] - c->level_off[l];
-        dim3 g((cnt + 127) / 128, c->nmember);
+        const dim3 g = cell_grid(c, cnt, 128);
         wgk::k_route_level<<<g, block, 0, c->stream>>>(p, 0, l);
         n++;
     }
@@ -1490,11 +1588,11 @@ int wgk_profile_schedule(wgk_ctx *c, int day, int month, int dom, int slot, floa
     };
     const dim3 block(128);
     if (c->whole_day) {
-        const dim3 grid((c->ncell + 127) / 128, c->nmember);
+        const dim3 grid = cell_grid(c, c->ncell, 128);
         timed(0, [&] { launch_vertical(c, p, 0); });
         timed(3, [&] { wgk::k_route_local<<<grid, block, 0, c->stream>>>(p); });
         for (int l = 0; l < c->tail_level0; l++) {
-            const dim3 g((c->level_off[l + 1] - c->level_off[l] + 127) / 128, c->nmember);
+            const dim3 g = cell_grid(c, c->level_off[l + 1] - c->level_off[l], 128);
             timed(1, [&] { wgk::k_route_level<<<g, block, 0, c->stream>>>(p, 0, l); });
         }
         if (c->tail_level0 < c->nlevels) timed(2, [&] { wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, 0, c->tail_level0, c->nlevels); });
@@ -1502,7 +1600,7 @@ int wgk_profile_schedule(wgk_ctx *c, int day, int month, int dom, int slot, floa
     } else {
         for (int l = 0; l < c->tail_level0; l++) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
-            const dim3 g((end - begin + 127) / 128, c->nmember);
+            const dim3 g = cell_grid(c, end - begin, 128);
             timed(0, [&] { launch_cells_pre(c, p, 0, begin, end); });
             timed(1, [&] { wgk::k_river_level<<<g, block, 0, c->stream>>>(p, 0, l); });
         }

@@ -75,6 +75,9 @@ struct WgkParams {
         if (!forcing_per_member) return (size_t)slot * stride + r;
         return mm ? ((size_t)slot * stride + r) * mpad + m : ((size_t)slot * nmember + m) * stride + r;
     }
+    // per-day scratch of the cells with a global water body: element k of (member m, slot gi) = gbody[gb(m, gi, nk) + k * gs()]
+    __host__ __device__ __forceinline__ size_t gb(const int m, const int gi, const int nk) const { return mm ? (size_t)gi * nk * mpad + m : ((size_t)m * ngbody + gi) * nk; }
+    __host__ __device__ __forceinline__ size_t gs() const { return mm ? (size_t)mpad : (size_t)1; }
     unsigned long long *stamps;   // optional (wgk_stamps): [2: V, R][2: first warp start, last warp end][STAMP_DAYS] %globaltimer ns of the
                                   // level-0 tasks of a call, i.e. their duration INSIDE the running graph; null = off
 };
@@ -98,6 +101,21 @@ __device__ __forceinline__ double operator/(const double x, const ConstDiv d) {
 constexpr ConstDiv C100{100., 0.01}, C1E6{1000000., 1e-6}, C1000{1000., 0.001}, C30{30., 1. / 30.},
                    C86400{86400., 1. / 86400.};
 
+// thread -> (device position r in [begin, end), member m) for the cell-parallel kernels.  Cell-minor layout: blockIdx.y = member,
+// consecutive threads = consecutive cells.  Member-minor layout: consecutive threads = consecutive members of ONE cell (a warp
+// never straddles two cells, mpad is a multiple of 32); lanes beyond the last member idle.
+__device__ __forceinline__ bool map_thread(const WgkParams &p, const int begin, const int end, int &r, int &m) {
+    if (p.mm) {
+        const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        r = begin + (int)(t / p.mpad);
+        m = (int)(t % p.mpad);
+        return r < end && m < p.nmember;
+    }
+    r = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    m = blockIdx.y;
+    return r < end;
+}
+
 // Shared-memory staging of the 100 snow bands of a cell: the band columns of the CTA's 128
 // cells are brought in by cp.async (LDGSTS) in chunks of SNOW_CH bands, double buffered, so
 // that all loads of the band loop are in flight while the thread evaluates radiation / PET /
@@ -120,11 +138,11 @@ struct SnowStage {
     int32_t e[2][SNOW_CH][VBLOCK];
 };
 __device__ __forceinline__ void stage_issue(SnowStage *st, const int buf, const int t, const double *S, const int32_t *E,
-                                            const size_t stride) {
+                                            const size_t sstride, const size_t estride) {
 #pragma unroll
     for (int k = 0; k < SNOW_CH; k++) {
-        __pipeline_memcpy_async(&st->s[buf][k][t], S + (size_t)k * stride, sizeof(double));
-        __pipeline_memcpy_async(&st->e[buf][k][t], E + (size_t)k * stride, sizeof(int32_t));
+        __pipeline_memcpy_async(&st->s[buf][k][t], S + (size_t)k * sstride, sizeof(double));
+        __pipeline_memcpy_async(&st->e[buf][k][t], E + (size_t)k * estride, sizeof(int32_t));
     }
     __pipeline_commit();
 }
@@ -276,7 +294,8 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
     const size_t i = p.mi(m, r);
     const size_t q = p.qi(m, r);
     const int tid = threadIdx.x & (VBLOCK - 1);  // column of the (128-thread) staging block handed in by the kernel
-    double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r + p.stride;
+    const size_t bs = p.bs();  // distance between two bands of the member's snow column
+    double *__restrict__ S = a.snow_bands + p.bi(m, r, WGK_NBAND_K) + bs;
     const int32_t *__restrict__ E = a.s_elev32 + r + p.stride;
 
     // Every input of the head is loaded here, unconditionally and before the first store: one memory round
@@ -323,8 +342,8 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
         bare = noland || (ddf >= 0. && t_top > P_T_SNOWFZ && t_bot > P_T_SNOWFZ);
     }
     if (!bare) {
-        stage_issue(st, 0, tid, S, E, p.stride);
-        stage_issue(st, 1, tid, S + (size_t)SNOW_CH * p.stride, E + (size_t)SNOW_CH * p.stride, p.stride);
+        stage_issue(st, 0, tid, S, E, bs, p.stride);
+        stage_issue(st, 1, tid, S + (size_t)SNOW_CH * bs, E + (size_t)SNOW_CH * p.stride, bs, p.stride);
     }
 
     double dailyPrec = (double)f.x;
@@ -470,7 +489,7 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
         for (int e = 1; e < 101; e++) {
             storage_transfer += *S / C100;
             *S = 0.;
-            S += p.stride;
+            S += bs;
         }
         snow = 0.;
     } else {
@@ -524,11 +543,11 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
                 snow += s;
                 nz |= (s != 0.);
                 dailyEffPrec += effmelt;
-                S[(size_t)(c * SNOW_CH + k) * p.stride] = s;
+                S[(size_t)(c * SNOW_CH + k) * bs] = s;
             }
             // refill the buffer just consumed with the chunk after next (same thread: no barrier)
             if (c + 2 < SNOW_NCH)
-                stage_issue(st, buf, tid, S + (size_t)(c + 2) * SNOW_CH * p.stride, E + (size_t)(c + 2) * SNOW_CH * p.stride, p.stride);
+                stage_issue(st, buf, tid, S + (size_t)(c + 2) * SNOW_CH * bs, E + (size_t)(c + 2) * SNOW_CH * p.stride, bs, p.stride);
         }
         snow /= 100.;
         dailyEffPrec /= 100.;
@@ -793,11 +812,12 @@ __device__ __forceinline__ void v_prefetch(const WgkParams &p, const VTile<C> &s
     const bool on = (mode & VM_ACTIVE) && !(mode & VM_BARE);
     const size_t r = (size_t)(r0 + lane);
     const int e0 = slab * C::SLAB + w * C::BPW + 1;
-    const double *__restrict__ S = p.a.snow_bands + ((size_t)m * WGK_NBAND_K + e0) * p.stride + r;
+    const size_t bs = p.bs();
+    const double *__restrict__ S = p.a.snow_bands + p.bi(m, (int)r, WGK_NBAND_K) + (size_t)e0 * bs;
     const int16_t *__restrict__ E = p.a.s_delev + (size_t)e0 * p.stride + r;
 #pragma unroll
     for (int j = 0; j < C::BPW; j++) {
-        ts.pre_s[j] = on ? S[(size_t)j * p.stride] : 0.;
+        ts.pre_s[j] = on ? S[(size_t)j * bs] : 0.;
         ts.pre_e[j] = on ? (int)E[(size_t)j * p.stride] : 0;
     }
 }
@@ -986,7 +1006,8 @@ __device__ __forceinline__ void v_band(const WgkParams &p, VTile<C> &sm, const V
     const int mode = sm.mode[lane];
     const bool store = (mode & VM_ACTIVE) && !(mode & VM_BARE);
     const int k0 = w * C::BPW, e0 = slab * C::SLAB + k0 + 1;
-    double *__restrict__ S = p.a.snow_bands + ((size_t)m * WGK_NBAND_K + e0) * p.stride + (size_t)(r0 + lane);
+    const size_t bs = p.bs();
+    double *__restrict__ S = p.a.snow_bands + p.bi(m, r0 + lane, WGK_NBAND_K) + (size_t)e0 * bs;
     if (mode & VM_NOLAND) {  // :916-922
 #pragma unroll
         for (int j = 0; j < C::BPW; j++) {
@@ -994,7 +1015,7 @@ __device__ __forceinline__ void v_band(const WgkParams &p, VTile<C> &sm, const V
             sm.contrib[Q_EFF][k0 + j][lane] = 0.;
             sm.contrib[Q_SUB][k0 + j][lane] = 0.;
             sm.contrib[Q_SNOW][k0 + j][lane] = 0.;
-            if (store) S[(size_t)j * p.stride] = 0.;
+            if (store) S[(size_t)j * bs] = 0.;
         }
         return;
     }
@@ -1029,7 +1050,7 @@ __device__ __forceinline__ void v_band(const WgkParams &p, VTile<C> &sm, const V
         sm.contrib[Q_EFF][k0 + j][lane] = eff + melt;
         sm.contrib[Q_SUB][k0 + j][lane] = sub;
         sm.contrib[Q_SNOW][k0 + j][lane] = s;
-        if (store) S[(size_t)j * p.stride] = s;
+        if (store) S[(size_t)j * bs] = s;
     }
 }
 
@@ -1289,7 +1310,7 @@ __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ W
     const int ps = blockIdx.y;
     if (r >= p.ncell) return;
     const WgkArrays &a = p.a;
-    const size_t q = (size_t)ps * p.stride + r;
+    const size_t q = p.qi_of(ps, r);
     a.s_c1[q] = 1. / (a.p_rivrgh[q] * a.roughness[r]);
     a.s_ekg[q] = exp(-1. * a.p_gwoutf[q]);  // routing.cpp:1940
     a.s_invkg[q] = (1. / a.p_gwoutf[q]);
@@ -1323,13 +1344,13 @@ __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ W
 // s_snowfree: all 100 elevation bands of the cell hold exactly zero snow (recomputed after every
 // upload of the band state; afterwards maintained by the vertical kernel)
 __global__ void __launch_bounds__(128) k_derive_member(const __grid_constant__ WgkParams p) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int m = blockIdx.y;
-    if (r >= p.ncell) return;
-    const double *S = p.a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + r;
+    int r, m;
+    if (!map_thread(p, 0, p.ncell, r, m)) return;
+    const double *S = p.a.snow_bands + p.bi(m, r, WGK_NBAND_K);
+    const size_t bs = p.bs();
     int nz = 0;
-    for (int b = 1; b < WGK_NBAND_K; b++) nz |= (S[(size_t)b * p.stride] != 0.);
-    p.a.s_snowfree[(size_t)m * p.stride + r] = (int8_t)(nz == 0);
+    for (int b = 1; b < WGK_NBAND_K; b++) nz |= (S[(size_t)b * bs] != 0.);
+    p.a.s_snowfree[p.mi(m, r)] = (int8_t)(nz == 0);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1485,24 +1506,25 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
             a.gw[i] = Sg;
         }
         if (flags & (FL_LAKE | FL_RES | FL_GLOWET)) {
-            double *g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;
-            g[GB_EKS] = exp(-1. * kS);
-            g[GB_INVKS] = (1. / kS);
-            g[GB_EKG] = li.ekg;
-            g[GB_INVKG] = li.invkg;
-            g[GB_GWRECH] = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
-            g[GB_LOC_GWR_LAK] = gwr_loclak;
-            g[GB_LOC_GWR_WET] = gwr_locwet;
+            double *g = p.gbody + p.gb(m, p.gidx[r], GB_N);
+            const size_t gs = p.gs();
+            g[GB_EKS * gs] = exp(-1. * kS);
+            g[GB_INVKS * gs] = (1. / kS);
+            g[GB_EKG * gs] = li.ekg;
+            g[GB_INVKG * gs] = li.invkg;
+            g[GB_GWRECH * gs] = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
+            g[GB_LOC_GWR_LAK * gs] = gwr_loclak;
+            g[GB_LOC_GWR_WET * gs] = gwr_locwet;
             if (flags & FL_LAKE) {  // :2630-2676
                 const double lake_area = a.lake_area[r];
                 const double rf = a.red_glo_lake[i];
                 double evapo = ((1.0 - cfa) * owPrec) + (cfa * owPET * rf);
                 if (evapo < 0.) evapo = 0.;
                 const double gwr = aridc ? 10. * rf * (lake_area / (cellArea * (contf / C100))) : 0.;
-                g[GB_L_PREC] = (owPrec * (lake_area / C1E6));
-                g[GB_L_GWR] = gwr;
-                g[GB_L_PET] = evapo * (lake_area / C1E6) + gwr * cellArea * (contf / C100) / C1E6 + 0.;
-                g[GB_L_MAX] = (lake_area)*li.lake_depth;
+                g[GB_L_PREC * gs] = (owPrec * (lake_area / C1E6));
+                g[GB_L_GWR * gs] = gwr;
+                g[GB_L_PET * gs] = evapo * (lake_area / C1E6) + gwr * cellArea * (contf / C100) / C1E6 + 0.;
+                g[GB_L_MAX * gs] = (lake_area)*li.lake_depth;
             }
             if (flags & FL_RES) {  // :2807-2870, 2960-2983
                 const double reservoir_area = a.reservoir_area[r];
@@ -1512,11 +1534,11 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 double evapo = ((1.0 - cfa) * owPrec) + (cfa * (owPET * rf));
                 if (evapo < 0.) evapo = 0.;
                 const double gwr = aridc ? 10. * rf * (reservoir_area / (cellArea * (contf / C100))) : 0.;
-                g[GB_R_PREC] = (owPrec * (reservoir_area / C1E6));
-                g[GB_R_GWR] = gwr;
-                g[GB_R_PET] = evapo * (reservoir_area / C1E6) + gwr * cellArea * (contf / C100) / C1E6;
-                g[GB_R_C] = stor_cap / (mean_outflow * 31536000. / 1000000000.);
-                g[GB_R_CAP] = stor_cap;
+                g[GB_R_PREC * gs] = (owPrec * (reservoir_area / C1E6));
+                g[GB_R_GWR * gs] = gwr;
+                g[GB_R_PET * gs] = evapo * (reservoir_area / C1E6) + gwr * cellArea * (contf / C100) / C1E6;
+                g[GB_R_C * gs] = stor_cap / (mean_outflow * 31536000. / 1000000000.);
+                g[GB_R_CAP * gs] = stor_cap;
                 double prov_rel = 0.;
                 const int res_type = a.res_type[r];
                 if (res_type == 1) {  // irrigation reservoir; water use is not simulated: monthlyUse == 0
@@ -1527,7 +1549,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 } else if (res_type == 2) {
                     prov_rel = mean_outflow;
                 }
-                g[GB_R_PROV] = prov_rel;
+                g[GB_R_PROV * gs] = prov_rel;
             }
             if (flags & FL_GLOWET) {  // :3178-3200
                 const double glo_wetland = a.glo_wetland[r];
@@ -1535,10 +1557,10 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 double evapo = ((1.0 - cfa) * (owPrec * rf)) + (cfa * (owPET * rf));
                 if (evapo < 0.) evapo = 0.;
                 const double gwr = aridc ? 10. * rf * glo_wetland / C100 / (contf / C100) : 0.;
-                g[GB_W_PREC] = (owPrec * rf * (cellArea / C1E6) * (glo_wetland / C100));
-                g[GB_W_GWR] = gwr;
-                g[GB_W_PET] = evapo * (cellArea / C1E6) * ((glo_wetland) / C100) + gwr * cellArea * (contf / C100) / C1E6;
-                g[GB_W_MAX] = ((glo_wetland) / C100) * cellArea * li.wetl_depth;
+                g[GB_W_PREC * gs] = (owPrec * rf * (cellArea / C1E6) * (glo_wetland / C100));
+                g[GB_W_GWR * gs] = gwr;
+                g[GB_W_PET * gs] = evapo * (cellArea / C1E6) * ((glo_wetland) / C100) + gwr * cellArea * (contf / C100) / C1E6;
+                g[GB_W_MAX * gs] = ((glo_wetland) / C100) * cellArea * li.wetl_depth;
             }
         }
         // river evaporation and precipitation on yesterday's river area fraction (:3425-3441)
@@ -1560,9 +1582,9 @@ __device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r
 }
 
 __global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ WgkParams p) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.ncell) return;
-    route_local_cell(p, r, blockIdx.y);
+    int r, m;
+    if (!map_thread(p, 0, p.ncell, r, m)) return;
+    route_local_cell(p, r, m);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1601,14 +1623,15 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
                                                    double inflow, const int flags, const int day, const int month,
                                                    double &gwToRiver) {
     const WgkArrays &a = p.a;
-    const double *g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;  // (no __restrict__: written earlier by the same thread in k_days_persistent)
-    const double ek = g[GB_EKS], invk = g[GB_INVKS];
+    const double *g = p.gbody + p.gb(m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
+    const size_t gs = p.gs();
+    const double ek = g[GB_EKS * gs], invk = g[GB_INVKS * gs];
     double gwr_glolak = 0., gwr_res = 0., gwr_glowet = 0.;
     if (flags & FL_LAKE) {  // :2677-2720
         const double prev = a.glo_lake_stor[i];
-        const double maxStorage = g[GB_L_MAX], PET = g[GB_L_PET];
-        gwr_glolak = g[GB_L_GWR];
-        const double totalInflow = inflow + g[GB_L_PREC];
+        const double maxStorage = g[GB_L_MAX * gs], PET = g[GB_L_PET * gs];
+        gwr_glolak = g[GB_L_GWR * gs];
+        const double totalInflow = inflow + g[GB_L_PREC * gs];
         const double PETmax = totalInflow + maxStorage + prev;
         double S, outflow;
         if (PET > PETmax) {
@@ -1632,12 +1655,12 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
         a.glo_lake_stor[i] = S;
     }
     if (flags & FL_RES) {  // :2871-3040
-        const double stor_cap = g[GB_R_CAP];
+        const double stor_cap = g[GB_R_CAP * gs];
         const double maxStorage = stor_cap;
         const double prev = a.res_stor[i];
-        const double PET = g[GB_R_PET];
-        gwr_res = g[GB_R_GWR];
-        const double totalInflow = inflow + g[GB_R_PREC];
+        const double PET = g[GB_R_PET * gs];
+        gwr_res = g[GB_R_GWR * gs];
+        const double totalInflow = inflow + g[GB_R_PREC * gs];
         const double PETmax = prev + totalInflow;
         double S;
         if (PET > PETmax) {
@@ -1654,7 +1677,7 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
             else Krel = S / (maxStorage * 0.85);
             a.k_release[i] = Krel;
         }
-        const double c_ratio = g[GB_R_C], prov_rel = g[GB_R_PROV];
+        const double c_ratio = g[GB_R_C * gs], prov_rel = g[GB_R_PROV * gs];
         double release;
         if (c_ratio >= 0.5) release = Krel * prov_rel;
         else
@@ -1678,9 +1701,9 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
     }
     if (flags & FL_GLOWET) {  // :3201-3260
         const double prev = a.glo_wetl_stor[i];
-        const double maxStorage = g[GB_W_MAX], PET = g[GB_W_PET];
-        gwr_glowet = g[GB_W_GWR];
-        const double totalInflow = inflow + g[GB_W_PREC];
+        const double maxStorage = g[GB_W_MAX * gs], PET = g[GB_W_PET * gs];
+        gwr_glowet = g[GB_W_GWR * gs];
+        const double totalInflow = inflow + g[GB_W_PREC * gs];
         const double PETmax = totalInflow + prev;
         double S, outflow;
         if (PET > PETmax) {
@@ -1700,12 +1723,12 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
         a.glo_wetl_stor[i] = S;
     }
     if (flags & FL_ARIDC) {  // :3305-3386
-        const double gwr_swb = g[GB_LOC_GWR_LAK] + gwr_glolak + g[GB_LOC_GWR_WET] + gwr_glowet + gwr_res;
+        const double gwr_swb = g[GB_LOC_GWR_LAK * gs] + gwr_glolak + g[GB_LOC_GWR_WET * gs] + gwr_glowet + gwr_res;
         a.gwr_swb[i] = gwr_swb;
-        const double netGWin = gwr_swb * a.area[r] * (a.contfreq[r] / C100) / C1E6 + g[GB_GWRECH];
+        const double netGWin = gwr_swb * a.area[r] * (a.contfreq[r] / C100) / C1E6 + g[GB_GWRECH * gs];
         const double prev = a.gw[i];
-        const double ekg = g[GB_EKG];
-        double Sg = prev * ekg + g[GB_INVKG] * netGWin * (1. - ekg);
+        const double ekg = g[GB_EKG * gs];
+        double Sg = prev * ekg + g[GB_INVKG * gs] * netGWin * (1. - ekg);
         if (fabs(Sg) <= MIN_STOR_VOL) Sg = 0.;
         double qq = prev - Sg + netGWin;
         if (qq <= 0.) {
@@ -1774,30 +1797,27 @@ __device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx
     return Sr;
 }
 
-__device__ __forceinline__ double gather_upstream(const WgkParams &p, const RiverCtx &c, const size_t mb,
+__device__ __forceinline__ double gather_upstream(const WgkParams &p, const RiverCtx &c, const int m,
                                                   const double *qday) {
     // upstream inflow in routing order (= order of the += at routing.cpp:3957)
     double s = 0.;
-    for (int k = c.up0; k < c.up1; k++) s += qday[mb + p.up_idx[k]];
+    for (int k = c.up0; k < c.up1; k++) s += qday[p.mi(m, p.up_idx[k])];
     return s;
 }
 
 __device__ __forceinline__ double *qbuf_of_day(const WgkParams &p, const int dayofs) {
-    return p.qbuf + (size_t)(dayofs % QBUF_K) * p.nmember * p.stride;
+    return p.qbuf + (size_t)(dayofs % QBUF_K) * p.mpad * p.stride;
 }
 
 // one dependency level per launch (wide levels), routing sweep only
 __global__ void __launch_bounds__(128) k_route_level(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
-    const int begin = p.level_off[level], end = p.level_off[level + 1];
-    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= end) return;
-    const int m = blockIdx.y;
-    const size_t mb = (size_t)m * p.stride;
-    const size_t q = p.qi(m, r);
-    const RiverCtx c = load_ctx(p, r, mb + r, q);
+    int r, m;
+    if (!map_thread(p, p.level_off[level], p.level_off[level + 1], r, m)) return;
+    const size_t i = p.mi(m, r), q = p.qi(m, r);
+    const RiverCtx c = load_ctx(p, r, i, q);
     if (!(c.flags & FL_ACTIVE)) return;
     double *qday = qbuf_of_day(p, dayofs);
-    route_river(p, c, r, m, mb + r, q, gather_upstream(p, c, mb, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
+    route_river(p, c, r, m, i, q, gather_upstream(p, c, m, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
 }
 
 // levels [level_lo, level_hi) inside one persistent CTA per member; levels are separated by
@@ -1807,20 +1827,18 @@ __global__ void __launch_bounds__(128) k_route_level(const __grid_constant__ Wgk
 __device__ __forceinline__ void sweep_levels(const WgkParams &p, const int m, const int dayofs, const int level_lo, const int level_hi) {
     const int day = p.cal_days[4 * dayofs], month = p.cal_days[4 * dayofs + 1];
     double *qday = qbuf_of_day(p, dayofs);
-    const size_t mb = (size_t)m * p.stride;
-    const size_t qb = (size_t)p.member_pset[m] * p.stride;
     int begin = p.level_off[level_lo], end = p.level_off[level_lo + 1];
     int r = begin + threadIdx.x;
     RiverCtx c;
     c.flags = 0;
-    if (r < end) c = load_ctx(p, r, mb + r, qb + r);
+    if (r < end) c = load_ctx(p, r, p.mi(m, r), p.qi(m, r));
     for (int level = level_lo; level < level_hi; level++) {
         if (r < end) {
-            if (c.flags & FL_ACTIVE) route_river(p, c, r, m, mb + r, qb + r, gather_upstream(p, c, mb, qday), day, month, qday);
+            if (c.flags & FL_ACTIVE) route_river(p, c, r, m, p.mi(m, r), p.qi(m, r), gather_upstream(p, c, m, qday), day, month, qday);
             // levels wider than the CTA (only possible when the tail threshold is raised)
             for (int r2 = r + blockDim.x; r2 < end; r2 += blockDim.x) {
-                const RiverCtx c2 = load_ctx(p, r2, mb + r2, qb + r2);
-                if (c2.flags & FL_ACTIVE) route_river(p, c2, r2, m, mb + r2, qb + r2, gather_upstream(p, c2, mb, qday), day, month, qday);
+                const RiverCtx c2 = load_ctx(p, r2, p.mi(m, r2), p.qi(m, r2));
+                if (c2.flags & FL_ACTIVE) route_river(p, c2, r2, m, p.mi(m, r2), p.qi(m, r2), gather_upstream(p, c2, m, qday), day, month, qday);
             }
         }
         if (level + 1 < level_hi) {
@@ -1828,7 +1846,7 @@ __device__ __forceinline__ void sweep_levels(const WgkParams &p, const int m, co
             end = p.level_off[level + 2];
             r = begin + threadIdx.x;
             c.flags = 0;
-            if (r < end) c = load_ctx(p, r, mb + r, qb + r);
+            if (r < end) c = load_ctx(p, r, p.mi(m, r), p.qi(m, r));
         }
         __syncthreads();
     }
@@ -1907,18 +1925,19 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
     }
     if ((flags & FL_ACTIVE) && (flags & (FL_LAKE | FL_RES | FL_GLOWET))) {
         // evaporation reduction factors of the global water bodies (:2790-2802, 3068-3078, 3287-3296)
-        const double *g = p.gbody + ((size_t)m * p.ngbody + p.gidx[r]) * GB_N;  // (no __restrict__: written earlier by the same thread in k_days_persistent)
+        const double *g = p.gbody + p.gb(m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
+        const size_t gs = p.gs();
         const double xexp = (in.evaredex * 3.32193);
         if (flags & FL_LAKE) {
-            const double maxStorage = g[GB_L_MAX];
+            const double maxStorage = g[GB_L_MAX * gs];
             a.red_glo_lake[i] = clamp01(1. - pow(fabs(a.glo_lake_stor[i] - maxStorage) / (2. * maxStorage), xexp));
         }
         if (flags & FL_RES) {
-            const double maxStorage = g[GB_R_CAP];
+            const double maxStorage = g[GB_R_CAP * gs];
             a.red_res[i] = clamp01(1. - pow(fabs(a.res_stor[i] - maxStorage) / maxStorage, 2.81383));
         }
         if (flags & FL_GLOWET) {
-            const double maxStorage = g[GB_W_MAX];
+            const double maxStorage = g[GB_W_MAX * gs];
             red_glo_wetl = clamp01(1. - pow(fabs(a.glo_wetl_stor[i] - maxStorage) / maxStorage, xexp));
         }
     }
@@ -1975,14 +1994,15 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
         // the day's entry of WghmStateFile for the seven routing compartments (routing.cpp:5002-5020), summed in
         // day order as Cell::mean does (wghmStateFile.cpp:711-728)
         const double denom = ((cellArea * (contf / C100)) / C1E6);
-        double *__restrict__ acc = a.mon_acc + (size_t)m * 7 * p.stride + r;
-        acc[0 * (size_t)p.stride] += a.loc_lake_stor[i] / denom;
-        acc[1 * (size_t)p.stride] += a.loc_wetl_stor[i] / denom;
-        acc[2 * (size_t)p.stride] += a.glo_lake_stor[i] / denom;
-        acc[3 * (size_t)p.stride] += a.glo_wetl_stor[i] / denom;
-        acc[4 * (size_t)p.stride] += a.res_stor[i] / denom;
-        acc[5 * (size_t)p.stride] += Sr / denom;
-        acc[6 * (size_t)p.stride] += a.gw[i] / denom;
+        double *__restrict__ acc = a.mon_acc + p.bi(m, r, 7);
+        const size_t bs = p.bs();
+        acc[0 * bs] += a.loc_lake_stor[i] / denom;
+        acc[1 * bs] += a.loc_wetl_stor[i] / denom;
+        acc[2 * bs] += a.glo_lake_stor[i] / denom;
+        acc[3 * bs] += a.glo_wetl_stor[i] / denom;
+        acc[4 * bs] += a.res_stor[i] / denom;
+        acc[5 * bs] += Sr / denom;
+        acc[6 * bs] += a.gw[i] / denom;
     }
     a.status_laf_next[i] = 1;
     // updateLandAreaFrac fused: prev <- cur, cur <- next
@@ -1993,13 +2013,13 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
 
 __device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r, const int m) {
     const PostIn in = post_load(p, r, m);
-    route_post_compute(p, r, m, in, p.a.river_stor[(size_t)m * p.stride + r]);
+    route_post_compute(p, r, m, in, p.a.river_stor[p.mi(m, r)]);
 }
 
 __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkParams p) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.ncell) return;
-    route_post_cell(p, r, blockIdx.y);
+    int r, m;
+    if (!map_thread(p, 0, p.ncell, r, m)) return;
+    route_post_cell(p, r, m);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -2013,21 +2033,18 @@ __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkP
 // upstream level); the vertical balance and the local routing of the same cells run in a separate,
 // earlier task (k_cells_pre) that only waits for the cells' own previous day
 __global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
-    const int begin = p.level_off[level], end = p.level_off[level + 1];
-    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= end) return;
-    const int m = blockIdx.y;
-    const size_t mb = (size_t)m * p.stride;
-    const size_t q = p.qi(m, r);
+    int r, m;
+    if (!map_thread(p, p.level_off[level], p.level_off[level + 1], r, m)) return;
+    const size_t i = p.mi(m, r), q = p.qi(m, r);
     WGK_INSITU_BEGIN();
     if (level == 0) WGK_INSITU_STAMP(1, 0, dayofs);
     if (level == 0) stamp_task(p, 1, 0, dayofs);
-    const RiverCtx c = load_ctx(p, r, mb + r, q);
+    const RiverCtx c = load_ctx(p, r, i, q);
     const PostIn in = post_load(p, r, m);  // same round of loads as the river context
     double Sr = c.prevR;
     if (c.flags & FL_ACTIVE) {
         double *qday = qbuf_of_day(p, dayofs);
-        Sr = route_river(p, c, r, m, mb + r, q, gather_upstream(p, c, mb, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
+        Sr = route_river(p, c, r, m, i, q, gather_upstream(p, c, m, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
     }
     route_post_compute(p, r, m, in, Sr);
     WGK_INSITU_END(2, level == 0);
@@ -2214,23 +2231,23 @@ __global__ void __launch_bounds__(C::THREADS, C::NW == 5 ? 6 : 12) k_vertical(co
 // thread-per-cell forms of k_vertical and k_cells_pre
 __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_vertical_tpc(const __grid_constant__ WgkParams p, const int dayofs) {
     __shared__ SnowStage stage;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.ncell) return;
-    vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3], &stage);
+    int r, m;
+    if (!map_thread(p, 0, p.ncell, r, m)) return;
+    vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3], &stage);
 }
 
 
 __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_cells_pre_tpc(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
     __shared__ SnowStage stage;
-    const int r = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= end) return;
+    int r, m;
+    if (!map_thread(p, begin, end, r, m)) return;
     WGK_INSITU_BEGIN();
     if (begin == 0) WGK_INSITU_STAMP(0, 0, dayofs);
     if (begin == 0) stamp_task(p, 0, 0, dayofs);
     LocalIn li;
     LocalFlux fx;
-    if (vertical_cell(p, r, blockIdx.y, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, blockIdx.y, li, fx);
-    else route_local_cell(p, r, blockIdx.y);
+    if (vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, m, li, fx);
+    else route_local_cell(p, r, m);
     WGK_INSITU_END(0, begin == 0);
     if (begin == 0) WGK_INSITU_WARPDUR(dayofs);
     if (begin == 0) WGK_INSITU_STAMP(0, 1, dayofs);
@@ -2349,7 +2366,7 @@ __global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) 
     const bool valid = w < s.nwarps && r < s.warp_end[w];  // lanes without a cell only take part in the barriers
     const unsigned mask = __ballot_sync(0xffffffffu, valid);  // the lanes of this warp that own a cell
     const int m = blockIdx.y;
-    const size_t mb = (size_t)m * p.stride;
+    const size_t mb = p.mi(m, 0);  // (the cell-owner schedule runs on the cell-minor layout only)
     const size_t q = p.qi(m, r);
     uint32_t *prog = s.progress + (size_t)m * s.nwarps;
     const int up0 = valid ? p.up_off[r] : 0, up1 = valid ? p.up_off[r + 1] : 0;
@@ -2373,7 +2390,7 @@ __global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) 
         const RiverCtx c = load_ctx(p, r, mb + r, q);
         const PostIn in = post_load(p, r, m);
         const uint32_t tag = s.base + (uint32_t)d + 1u;
-        unsigned long long *ring = s.ring + ((size_t)(d % QBUF_K) * p.nmember * p.stride + mb) * 2;
+        unsigned long long *ring = s.ring + ((size_t)(d % QBUF_K) * p.mpad * p.stride + mb) * 2;
         double Sr = c.prevR, qv = 0.;
         WGK_OWNER_TICK(0);
         if (c.flags & FL_ACTIVE) {
@@ -2437,7 +2454,7 @@ __global__ void k_end_of_day(const __grid_constant__ WgkParams p, const int dayo
     const int total = p.nmember * p.nrec;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
         const int m = k / p.nrec, cidx = k % p.nrec;
-        p.record[(size_t)row * total + k] = qday[(size_t)m * p.stride + p.record_cells[cidx]];
+        p.record[(size_t)row * total + k] = qday[p.mi(m, p.record_cells[cidx])];
     }
 }
 
@@ -2447,7 +2464,8 @@ __global__ void k_end_of_day(const __grid_constant__ WgkParams p, const int dayo
 template <bool SWAP>
 __global__ void k_forcing_pack(float4 *__restrict__ dst, const float *__restrict__ P, const float *__restrict__ T,
                                const float *__restrict__ SW, const float *__restrict__ LW,
-                               const int32_t *__restrict__ cell_of_rank, int ncell, int ndays, int src_stride, size_t slot_pitch) {
+                               const int32_t *__restrict__ cell_of_rank, int ncell, int ndays, int src_stride, size_t slot_pitch,
+                               size_t cell_stride) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= ncell) return;
     const int n = cell_of_rank[r];
@@ -2459,7 +2477,7 @@ __global__ void k_forcing_pack(float4 *__restrict__ dst, const float *__restrict
     };
     for (int d = blockIdx.y; d < ndays; d += gridDim.y) {
         const size_t s = (size_t)n * src_stride + d;
-        dst[(size_t)d * slot_pitch + r] = make_float4(word(P, s), word(T, s), word(SW, s), word(LW, s));
+        dst[(size_t)d * slot_pitch + (size_t)r * cell_stride] = make_float4(word(P, s), word(T, s), word(SW, s), word(LW, s));
     }
 }
 
@@ -2513,7 +2531,7 @@ __device__ __forceinline__ void state_of_cell(const WgkParams &p, const int x, c
             for (int d = 0; d < ndays; d++) s += land[k];
             v[k] = s / (double)ndays;
         }
-        for (int k = 0; k < 7; k++) v[3 + k] = a.mon_acc[((size_t)m * 7 + k) * p.stride + x] / (double)ndays;
+        for (int k = 0; k < 7; k++) v[3 + k] = a.mon_acc[p.bi(m, x, 7) + (size_t)k * p.bs()] / (double)ndays;
     }
 }
 
@@ -2587,9 +2605,17 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *__restrict__ out, con
 
 // uniform value for one row of a per-cell f64 array (a calibration parameter of one parameter set, calibration.cpp
 // assigns one gamma / CFA per basin)
-__global__ void __launch_bounds__(256) k_fill_f64(double *__restrict__ dst, const int n, const double v) {
+__global__ void __launch_bounds__(256) k_fill_f64(double *__restrict__ dst, const int n, const size_t stride, const double v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = v;
+    if (i < n) dst[(size_t)i * stride] = v;
+}
+
+// dst[k * dst_stride] = src[k * src_stride]: uploads, downloads and copies of one index of a member-minor array
+template <class T>
+__global__ void __launch_bounds__(256) k_strided_copy(T *__restrict__ dst, const size_t dst_stride, const T *__restrict__ src, const size_t src_stride,
+                                                      const size_t n) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) dst[k * dst_stride] = src[k * src_stride];
 }
 
 // enkf_wghmstate_ (enKF2wghmState.cpp:89-121, 440-471) followed by the restore of the next cycle's start
@@ -2621,14 +2647,15 @@ __global__ void __launch_bounds__(128) k_enkf_update(const __grid_constant__ Wgk
     const double laf = laf_of(a, i), contf = a.contfreq[x];
     const double snow_mean_before = mon[1];
     const double snow_after = fl[1] + mf[1];
-    double *__restrict__ S = a.snow_bands + (size_t)m * WGK_NBAND_K * p.stride + x;
+    double *__restrict__ S = a.snow_bands + p.bi(m, x, WGK_NBAND_K);
+    const size_t bs = p.bs();
     for (int e = 1; e < WGK_NBAND_K; e++) {
-        double sie = (laf == 0.) ? 0. : S[(size_t)e * p.stride] * laf / contf;
+        double sie = (laf == 0.) ? 0. : S[(size_t)e * bs] * laf / contf;
         if (snow_mean_before == 0) sie = snow_after / 100;
         else sie *= snow_after / snow_mean_before;
         if (sie < 0.) sie = 0.;
         if (sie > 1000.) sie = 1000.;
-        S[(size_t)e * p.stride] = (laf <= 0.) ? 0. : sie * contf / laf;  // daily.cpp:1904-1922
+        S[(size_t)e * bs] = (laf <= 0.) ? 0. : sie * contf / laf;  // daily.cpp:1904-1922
     }
     if (laf <= 0.) {
         a.canopy[i] = 0.;

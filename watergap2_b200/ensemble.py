@@ -161,14 +161,6 @@ def ensemble_state_moments(model, nmember_total, kind="month", cells=None, group
     return mean, var
 
 
-def member_tensor(model, field):
-    """torch view [nmember, cell_stride] (device layout: routing order, padded) of a per-member
-    f64 field of a wgk Model, without a copy"""
-    import torch
-    ptr = model.device_ptr(field, 0)
-    return torch.as_tensor(_CudaArray(ptr, (model.nmember, model.cell_stride)), device=f"cuda:{model.device}")
-
-
 def ensemble_mean_var(local, nmember_total, group=None):
     """mean and (population) variance over ALL members of all ranks of a generic tensor `local`
     [members_on_this_rank, n]: the host-logic form of the exchange (member sharding + one all-reduce of the stacked
