@@ -18,7 +18,12 @@
 
 namespace wgk { constexpr int NBAND = 101; }
 #define WGK_NBAND_K wgk::NBAND
-#include "wgk_kernels.cuh"
+#include "wgk_kernels.cuh"  // namespace wgk: kernels of the cell-minor layout
+#undef WGK_MM
+#define WGK_MM 1
+#include "wgk_kernels.cuh"  // namespace wgk_mm: the same kernels compiled for the member-minor layout (lane = member)
+// a layout-dependent kernel of the context's layout
+#define WGK_K(c_, name_) ((c_)->mm ? wgk_mm::name_ : wgk::name_)
 
 namespace {
 
@@ -273,10 +278,10 @@ int levels_per_chunk() {  // tuning knob (WGK_LEVELS_PER_CHUNK); measured optimu
 }
 
 void *cells_pre_fn(const wgk_ctx *c) {
-    return c->form == 1 ? (void *)wgk::k_cells_pre<wgk::VCfgSmall> : c->form == 2 ? (void *)wgk::k_cells_pre<wgk::VCfgMid> : (void *)wgk::k_cells_pre_tpc;
+    return c->form == 1 ? (void *)wgk::k_cells_pre<wgk::VCfgSmall> : c->form == 2 ? (void *)wgk::k_cells_pre<wgk::VCfgMid> : (void *)WGK_K(c, k_cells_pre_tpc);
 }
 void *vertical_fn(const wgk_ctx *c) {
-    return c->form == 1 ? (void *)wgk::k_vertical<wgk::VCfgSmall> : c->form == 2 ? (void *)wgk::k_vertical<wgk::VCfgMid> : (void *)wgk::k_vertical_tpc;
+    return c->form == 1 ? (void *)wgk::k_vertical<wgk::VCfgSmall> : c->form == 2 ? (void *)wgk::k_vertical<wgk::VCfgMid> : (void *)WGK_K(c, k_vertical_tpc);
 }
 dim3 cells_pre_block(const wgk_ctx *c) { return dim3(c->form == 1 ? wgk::VCfgSmall::THREADS : c->form == 2 ? wgk::VCfgMid::THREADS : wgk::VBLOCK); }
 // grid of a cell-parallel kernel of `block` threads over `ncells` device positions (wgk::map_thread)
@@ -305,19 +310,19 @@ int enqueue_vertical(wgk_ctx *c, const WgkParams &p, int d) {
 int enqueue_routing(wgk_ctx *c, const WgkParams &p, int d) {
     int n = 0;
     const dim3 block(128), grid = cell_grid(c, c->ncell, 128);
-    wgk::k_route_local<<<grid, block, 0, c->stream>>>(p);
+    WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p);
     n++;
     for (int l = 0; l < c->tail_level0; l++) {
         const int cnt = c->level_off[l + 1] - c->level_off[l];
         const dim3 g = cell_grid(c, cnt, 128);
-        wgk::k_route_level<<<g, block, 0, c->stream>>>(p, d, l);
+        WGK_K(c, k_route_level)<<<g, block, 0, c->stream>>>(p, d, l);
         n++;
     }
     if (c->tail_level0 < c->nlevels) {
         wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, d, c->tail_level0, c->nlevels);
         n++;
     }
-    wgk::k_route_post<<<grid, block, 0, c->stream>>>(p);
+    WGK_K(c, k_route_post)<<<grid, block, 0, c->stream>>>(p);
     n++;
     return n;
 }
@@ -332,7 +337,7 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
             const dim3 g = cell_grid(c, end - begin, 128);
             launch_cells_pre(c, p, d, begin, end);
-            wgk::k_river_level<<<g, block, 0, c->stream>>>(p, d, l);
+            WGK_K(c, k_river_level)<<<g, block, 0, c->stream>>>(p, d, l);
             n += 2;
         }
         for (size_t k = 0; k + 1 < c->chunk_lo.size(); k++) {
@@ -343,7 +348,7 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
             n += 2;
         }
         if (c->d_record) {
-            wgk::k_end_of_day<<<1, 256, 0, c->stream>>>(p, d);
+            WGK_K(c, k_end_of_day)<<<1, 256, 0, c->stream>>>(p, d);
             n++;
         }
     }
@@ -361,7 +366,7 @@ int enqueue_whole_days(wgk_ctx *c, const WgkParams &p, int ndays) {
         n += enqueue_vertical(c, p, d);
         n += enqueue_routing(c, p, d);
         if (c->d_record) {
-            wgk::k_end_of_day<<<1, 256, 0, c->stream>>>(p, d);
+            WGK_K(c, k_end_of_day)<<<1, 256, 0, c->stream>>>(p, d);
             n++;
         }
     }
@@ -413,7 +418,7 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
             // (fusing R(d, l) with V(d + 1, l) into one task - one kernel boundary per day on the own-cell
             //  recurrence instead of two - was measured SLOWER: 27.4 vs 24.6 ms per simulated year, with 32 or 64 buffers)
             void *a2[] = {&pp, &dd, &ll};
-            CU(add((void *)wgk::k_river_level, grid, dim3(128), a2, {pre, last, first_sweep ? reuse : nullptr}, &node));
+            CU(add((void *)WGK_K(c, k_river_level), grid, dim3(128), a2, {pre, last, first_sweep ? reuse : nullptr}, &node));
             first_sweep = false;
             prevW[l] = node;
             last = node;
@@ -434,7 +439,7 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
             int dd = d;
             void *a3[] = {&pp, &dd};
             cudaGraphNode_t e;
-            CU(add((void *)wgk::k_end_of_day, dim3(1), dim3(256), a3, {last}, &e));
+            CU(add((void *)WGK_K(c, k_end_of_day), dim3(1), dim3(256), a3, {last}, &e));
             last = e;
         }
         dayEnd[d] = last;
@@ -497,13 +502,13 @@ int launch_owner(wgk_ctx *c, const WgkParams &p, int ndays) {
 int ensure_derived(wgk_ctx *c) {
     if (c->member_dirty) {
         const dim3 block(128), grid = cell_grid(c, c->ncell, 128);
-        wgk::k_derive_member<<<grid, block, 0, c->stream>>>(make_params(c));
+        WGK_K(c, k_derive_member)<<<grid, block, 0, c->stream>>>(make_params(c));
         c->launches++;
         c->member_dirty = false;
     }
     if (!c->derived_dirty) return 0;
     dim3 block(128), grid((c->ncell + 127) / 128, c->npset);
-    wgk::k_derive_static<<<grid, block, 0, c->stream>>>(make_params(c));
+    WGK_K(c, k_derive_static)<<<grid, block, 0, c->stream>>>(make_params(c));
     c->launches++;
     // cells with a global lake / reservoir / global wetland get a slot in the per-day scratch
     std::vector<int8_t> flags(c->stride);
@@ -617,7 +622,8 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     // the tile kernels keep up to 36 KB per CTA in shared memory: ask for the largest carve-out
     for (const void *fn : {(const void *)wgk::k_cells_pre<wgk::VCfgSmall>, (const void *)wgk::k_cells_pre<wgk::VCfgMid>,
                            (const void *)wgk::k_vertical<wgk::VCfgSmall>, (const void *)wgk::k_vertical<wgk::VCfgMid>,
-                           (const void *)wgk::k_cells_pre_tpc, (const void *)wgk::k_vertical_tpc})
+                           (const void *)wgk::k_cells_pre_tpc, (const void *)wgk::k_vertical_tpc,
+                           (const void *)wgk_mm::k_cells_pre_tpc, (const void *)wgk_mm::k_vertical_tpc})
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     for (int f = 0; f < WGK_F_COUNT; f++) {
         const size_t bytes = field_rows(c, f) * field_row_elems(c, f) * kFields[f].elsize;
@@ -1281,7 +1287,7 @@ int wgk_state_vector(wgk_ctx *c, int member, int kind, const int32_t *cells, int
     BridgeBuffers b;
     int rc = bridge_upload(c, b, cells, ncells, mean_field, nullptr, nullptr);
     if (rc) return rc;
-    wgk::k_state_vector<<<(ncells + 127) / 128, 128, 0, c->stream>>>(make_params(c), member, kind, c->month_days, b.pos, ncells,
+    WGK_K(c, k_state_vector)<<<(ncells + 127) / 128, 128, 0, c->stream>>>(make_params(c), member, kind, c->month_days, b.pos, ncells,
                                                                      mean_field ? b.d[0] : nullptr, b.d[1]);
     c->launches++;
     CU(cudaGetLastError());
@@ -1299,7 +1305,7 @@ int wgk_enkf_update(wgk_ctx *c, int member, const int32_t *cells, int ncells, co
     BridgeBuffers b;
     int rc = bridge_upload(c, b, cells, ncells, field, prediction, mean_field);
     if (rc) return rc;
-    wgk::k_enkf_update<<<(ncells + 127) / 128, 128, 0, c->stream>>>(make_params(c), member, c->month_days, b.pos, ncells, b.d[0], b.d[1], b.d[2]);
+    WGK_K(c, k_enkf_update)<<<(ncells + 127) / 128, 128, 0, c->stream>>>(make_params(c), member, c->month_days, b.pos, ncells, b.d[0], b.d[1], b.d[2]);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -1339,7 +1345,7 @@ int wgk_ensemble_moments(wgk_ctx *c, int kind, const int32_t *cells, int ncells,
         CU(cudaMemcpyAsync(c->d_mom_pos, pos.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
         CU(cudaStreamSynchronize(c->stream));  // pos is a host temporary
     }
-    wgk::k_ensemble_moments<<<(n + 127) / 128, 128, 0, c->stream>>>(make_params(c), kind, c->month_days, cells ? c->d_mom_pos : nullptr,
+    WGK_K(c, k_ensemble_moments)<<<(n + 127) / 128, 128, 0, c->stream>>>(make_params(c), kind, c->month_days, cells ? c->d_mom_pos : nullptr,
                                                                     c->d_cell_of_rank, n, sum, sumsq);
     c->launches++;
     CU(cudaGetLastError());
@@ -1414,7 +1420,7 @@ int wgk_total_storage_km3(wgk_ctx *c, int member, double *out) {
     if (!c || !out || member < 0 || member >= c->nmember) return WGK_ERR_ARG;
     CU(cudaSetDevice(c->device));
     const int nblk = 128;
-    wgk::k_total_storage<<<nblk, 256, 0, c->stream>>>(make_params(c), member, c->d_partial);
+    WGK_K(c, k_total_storage)<<<nblk, 256, 0, c->stream>>>(make_params(c), member, c->d_partial);
     c->launches++;
     double part[128];
     CU(cudaMemcpyAsync(part, c->d_partial, sizeof(double) * nblk, cudaMemcpyDeviceToHost, c->stream));
@@ -1505,13 +1511,13 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     CU(cudaEventRecord(ev[0], c->stream));
     launch_vertical(c, p, 0);
     CU(cudaEventRecord(ev[1], c->stream));
-    wgk::k_route_local<<<grid, block, 0, c->stream>>>(p);
+    WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p);
     CU(cudaEventRecord(ev[2], c->stream));
     int n = 3;
     for (int l = 0; l < c->tail_level0; l++) {
         const int cnt = c->level_off[l + 1] - c->level_off[l];
         const dim3 g = cell_grid(c, cnt, 128);
-        wgk::k_route_level<<<g, block, 0, c->stream>>>(p, 0, l);
+        WGK_K(c, k_route_level)<<<g, block, 0, c->stream>>>(p, 0, l);
         n++;
     }
     CU(cudaEventRecord(ev[3], c->stream));
@@ -1520,7 +1526,7 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
         n++;
     }
     CU(cudaEventRecord(ev[4], c->stream));
-    wgk::k_route_post<<<grid, block, 0, c->stream>>>(p);
+    WGK_K(c, k_route_post)<<<grid, block, 0, c->stream>>>(p);
     CU(cudaEventRecord(ev[5], c->stream));
     c->launches += n;
     CU(cudaEventSynchronize(ev[5]));
@@ -1590,19 +1596,19 @@ int wgk_profile_schedule(wgk_ctx *c, int day, int month, int dom, int slot, floa
     if (c->whole_day) {
         const dim3 grid = cell_grid(c, c->ncell, 128);
         timed(0, [&] { launch_vertical(c, p, 0); });
-        timed(3, [&] { wgk::k_route_local<<<grid, block, 0, c->stream>>>(p); });
+        timed(3, [&] { WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p); });
         for (int l = 0; l < c->tail_level0; l++) {
             const dim3 g = cell_grid(c, c->level_off[l + 1] - c->level_off[l], 128);
-            timed(1, [&] { wgk::k_route_level<<<g, block, 0, c->stream>>>(p, 0, l); });
+            timed(1, [&] { WGK_K(c, k_route_level)<<<g, block, 0, c->stream>>>(p, 0, l); });
         }
         if (c->tail_level0 < c->nlevels) timed(2, [&] { wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, 0, c->tail_level0, c->nlevels); });
-        timed(3, [&] { wgk::k_route_post<<<grid, block, 0, c->stream>>>(p); });
+        timed(3, [&] { WGK_K(c, k_route_post)<<<grid, block, 0, c->stream>>>(p); });
     } else {
         for (int l = 0; l < c->tail_level0; l++) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
             const dim3 g = cell_grid(c, end - begin, 128);
             timed(0, [&] { launch_cells_pre(c, p, 0, begin, end); });
-            timed(1, [&] { wgk::k_river_level<<<g, block, 0, c->stream>>>(p, 0, l); });
+            timed(1, [&] { WGK_K(c, k_river_level)<<<g, block, 0, c->stream>>>(p, 0, l); });
         }
         for (size_t k = 0; k + 1 < c->chunk_lo.size(); k++) {
             const int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];

@@ -29,7 +29,8 @@
 //
 // Build with -fmad=false: the reference CPU build has no FMA contraction, and results are
 // compared at 1e-10 relative.  Expression shapes follow the reference line by line.
-#pragma once
+// (no include guard: wgk_api.cu includes this header twice, once per layout - see WGK_MM)
+
 #include <cstdint>
 #ifndef WGK_EMU  // tests/emu compiles this header for the host to check the kernel logic
 #include <cuda_pipeline.h>
@@ -37,6 +38,11 @@
 #endif
 #include "wgk_fields.h"
 
+#ifndef WGK_MM
+#define WGK_MM 0  // 0: kernels of the cell-minor layout in namespace wgk, 1: of the member-minor layout in namespace wgk_mm
+#endif
+#ifndef WGK_PARAMS_DEFINED
+#define WGK_PARAMS_DEFINED
 struct WgkParams {
     WgkArrays a;
     const int32_t *member_pset;   // [nmember]
@@ -63,26 +69,40 @@ struct WgkParams {
     //   mm == 0  cell-minor   [member][band][cell]: a warp = 32 consecutive cells of one member (few members, latency regime)
     //   mm == 1  member-minor [band][cell][member]: a warp = 32 members of ONE cell (many members, throughput regime): statics
     //            are warp-uniform loads and the 32 lanes share land cover, water-body class and nearly the same weather
+    // The kernels are compiled once per layout (namespaces wgk / wgk_mm, WGK_MM below) so that the index arithmetic of either
+    // is free of run-time selects; the index helpers mi() ... gs() live in the namespace.
     int mm, mpad, ppad;           // mpad / ppad: rows of the member / parameter-set arrays (members padded to 32 when mm)
-    __host__ __device__ __forceinline__ size_t mi(const int m, const int r) const { return mm ? (size_t)r * mpad + m : (size_t)m * stride + r; }
-    __host__ __device__ __forceinline__ size_t qi_of(const int ps, const int r) const { return mm ? (size_t)r * ppad + ps : (size_t)ps * stride + r; }
-    __device__ __forceinline__ size_t qi(const int m, const int r) const { return qi_of(member_pset[m], r); }
-    // element (m, band b, r) of a band array with nb bands = bi(m, r, nb) + b * bs()
-    __host__ __device__ __forceinline__ size_t bi(const int m, const int r, const int nb) const { return mm ? (size_t)r * mpad + m : (size_t)m * nb * stride + r; }
-    __host__ __device__ __forceinline__ size_t bs() const { return mm ? (size_t)stride * mpad : (size_t)stride; }
-    // forcing [slot][fmember][cell] (cell-minor) / [slot][cell][fmember] (member-minor)
-    __host__ __device__ __forceinline__ size_t fi(const int slot, const int m, const int r) const {
-        if (!forcing_per_member) return (size_t)slot * stride + r;
-        return mm ? ((size_t)slot * stride + r) * mpad + m : ((size_t)slot * nmember + m) * stride + r;
-    }
-    // per-day scratch of the cells with a global water body: element k of (member m, slot gi) = gbody[gb(m, gi, nk) + k * gs()]
-    __host__ __device__ __forceinline__ size_t gb(const int m, const int gi, const int nk) const { return mm ? (size_t)gi * nk * mpad + m : ((size_t)m * ngbody + gi) * nk; }
-    __host__ __device__ __forceinline__ size_t gs() const { return mm ? (size_t)mpad : (size_t)1; }
     unsigned long long *stamps;   // optional (wgk_stamps): [2: V, R][2: first warp start, last warp end][STAMP_DAYS] %globaltimer ns of the
                                   // level-0 tasks of a call, i.e. their duration INSIDE the running graph; null = off
 };
 
-namespace wgk {
+#endif  // WGK_PARAMS_DEFINED
+
+#undef WGK_NS
+#if WGK_MM
+#define WGK_NS wgk_mm
+#else
+#define WGK_NS wgk
+#endif
+namespace WGK_NS {
+
+constexpr bool MM = (WGK_MM != 0);
+// element (member m, device position r) of a member array / of a parameter-set array
+__host__ __device__ __forceinline__ size_t mi(const WgkParams &p, const int m, const int r) { return MM ? (size_t)r * p.mpad + m : (size_t)m * p.stride + r; }
+__host__ __device__ __forceinline__ size_t qi_of(const WgkParams &p, const int ps, const int r) { return MM ? (size_t)r * p.ppad + ps : (size_t)ps * p.stride + r; }
+__device__ __forceinline__ size_t qi(const WgkParams &p, const int m, const int r) { return qi_of(p, p.member_pset[m], r); }
+// element (m, band b, r) of a band array with nb bands = bi(p, m, r, nb) + b * band_stride(p)
+__host__ __device__ __forceinline__ size_t bi(const WgkParams &p, const int m, const int r, const int nb) { return MM ? (size_t)r * p.mpad + m : (size_t)m * nb * p.stride + r; }
+__host__ __device__ __forceinline__ size_t band_stride(const WgkParams &p) { return MM ? (size_t)p.stride * p.mpad : (size_t)p.stride; }
+// forcing [slot][fmember][cell] (cell-minor) / [slot][cell][fmember] (member-minor)
+__host__ __device__ __forceinline__ size_t fi(const WgkParams &p, const int slot, const int m, const int r) {
+    if (!p.forcing_per_member) return (size_t)slot * p.stride + r;
+    return MM ? ((size_t)slot * p.stride + r) * p.mpad + m : ((size_t)slot * p.nmember + m) * p.stride + r;
+}
+// per-day scratch of the cells with a global water body: element k of (member m, slot gi) = gbody[gb(p, m, gi, nk) + k * gbody_stride(p)]
+__host__ __device__ __forceinline__ size_t gb(const WgkParams &p, const int m, const int gi, const int nk) { return MM ? (size_t)gi * nk * p.mpad + m : ((size_t)m * p.ngbody + gi) * nk; }
+__host__ __device__ __forceinline__ size_t gbody_stride(const WgkParams &p) { return MM ? (size_t)p.mpad : (size_t)1; }
+
 
 constexpr double MIN_STOR_VOL = 1.e-15;  // routing.h:24
 
@@ -105,7 +125,7 @@ constexpr ConstDiv C100{100., 0.01}, C1E6{1000000., 1e-6}, C1000{1000., 0.001}, 
 // consecutive threads = consecutive cells.  Member-minor layout: consecutive threads = consecutive members of ONE cell (a warp
 // never straddles two cells, mpad is a multiple of 32); lanes beyond the last member idle.
 __device__ __forceinline__ bool map_thread(const WgkParams &p, const int begin, const int end, int &r, int &m) {
-    if (p.mm) {
+    if (MM) {
         const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
         r = begin + (int)(t / p.mpad);
         m = (int)(t % p.mpad);
@@ -241,8 +261,8 @@ struct LocalFlux {
 
 __device__ __forceinline__ LocalIn local_load(const WgkParams &p, const int r, const int m) {
     const WgkArrays &a = p.a;
-    const size_t i = p.mi(m, r);
-    const size_t q = p.qi(m, r);
+    const size_t i = mi(p, m, r);
+    const size_t q = qi(p, m, r);
     LocalIn li;
     li.contcell = a.contcell[r];
     li.flags = a.s_flags[r];
@@ -273,7 +293,7 @@ __device__ __forceinline__ LocalIn local_load(const WgkParams &p, const int r, c
 
 __device__ __forceinline__ LocalFlux local_flux_load(const WgkParams &p, const int r, const int m) {
     const WgkArrays &a = p.a;
-    const size_t i = p.mi(m, r);
+    const size_t i = mi(p, m, r);
     LocalFlux fx;
     fx.owPrec = a.openwater_prec[i];
     fx.owPET = a.openwater_pet[i];
@@ -291,18 +311,18 @@ __device__ __forceinline__ LocalFlux local_flux_load(const WgkParams &p, const i
 __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, const int m, const int slot, SnowStage *st,
                                               LocalIn *li = nullptr, LocalFlux *fx = nullptr) {
     const WgkArrays &a = p.a;
-    const size_t i = p.mi(m, r);
-    const size_t q = p.qi(m, r);
+    const size_t i = mi(p, m, r);
+    const size_t q = qi(p, m, r);
     const int tid = threadIdx.x & (VBLOCK - 1);  // column of the (128-thread) staging block handed in by the kernel
-    const size_t bs = p.bs();  // distance between two bands of the member's snow column
-    double *__restrict__ S = a.snow_bands + p.bi(m, r, WGK_NBAND_K) + bs;
+    const size_t bs = band_stride(p);  // distance between two bands of the member's snow column
+    double *__restrict__ S = a.snow_bands + bi(p, m, r, WGK_NBAND_K) + bs;
     const int32_t *__restrict__ E = a.s_elev32 + r + p.stride;
 
     // Every input of the head is loaded here, unconditionally and before the first store: one memory round
     // trip instead of one per use (the compiler may not move a load above a store or an early return).
     const int in_contcell = a.contcell[r], in_tbc = a.toBeCalculated[r], started = a.status_laf_next[i];
     const double in_laf = a.land_area_frac[i], in_laf_next = a.land_area_frac_next[i], in_laf_prev = a.land_area_frac_prev[i];
-    const float4 f = p.forcing[p.fi(slot, m, r)];
+    const float4 f = p.forcing[fi(p, slot, m, r)];
     const int lc = a.landcover[r] - 1;
     const double P_T_SNOWFZ = a.p_snowfz[q];
     const double P_T_SNOWMT = a.p_snowmt[q];
@@ -764,8 +784,8 @@ __device__ __forceinline__ void v_mode(const WgkParams &p, VTile<C> &sm, const i
 #endif
     int mode = 0;
     if (r >= begin && r < end && a.contcell[r]) {  // integrateWGHM.cpp:772
-        const size_t i = p.mi(m, r);
-        const size_t q = p.qi(m, r);
+        const size_t i = mi(p, m, r);
+        const size_t q = qi(p, m, r);
         // daily.cpp:159-169, routing.h:246-251 (all candidates are loaded at once: one memory round trip)
         const int started = a.status_laf_next[i];
         const double laf_cur = a.land_area_frac[i], laf_next = a.land_area_frac_next[i], laf_prev = a.land_area_frac_prev[i];
@@ -778,7 +798,7 @@ __device__ __forceinline__ void v_mode(const WgkParams &p, VTile<C> &sm, const i
             mode = VM_ACTIVE;
             const bool noland = (landAreaFrac <= 0.);
             if (noland) mode |= VM_NOLAND;
-            const float4 f = p.forcing[p.fi(slot, m, r)];
+            const float4 f = p.forcing[fi(p, slot, m, r)];
             const double T = (double)f.y;
             const double grad = a.p_gradnt[q], fz = a.p_snowfz[q];
             const double ddf = a.p_degday[q] * a.lct_ddf[a.landcover[r] - 1];  // (M_DEGDAY_F * ddf_lct) * (...) keeps the reference association
@@ -812,8 +832,8 @@ __device__ __forceinline__ void v_prefetch(const WgkParams &p, const VTile<C> &s
     const bool on = (mode & VM_ACTIVE) && !(mode & VM_BARE);
     const size_t r = (size_t)(r0 + lane);
     const int e0 = slab * C::SLAB + w * C::BPW + 1;
-    const size_t bs = p.bs();
-    const double *__restrict__ S = p.a.snow_bands + p.bi(m, (int)r, WGK_NBAND_K) + (size_t)e0 * bs;
+    const size_t bs = band_stride(p);
+    const double *__restrict__ S = p.a.snow_bands + bi(p, m, (int)r, WGK_NBAND_K) + (size_t)e0 * bs;
     const int16_t *__restrict__ E = p.a.s_delev + (size_t)e0 * p.stride + r;
 #pragma unroll
     for (int j = 0; j < C::BPW; j++) {
@@ -829,12 +849,12 @@ __device__ __forceinline__ void v_head(const WgkParams &p, VTile<C> &sm, const i
     const int mode = sm.mode[lane];
     if (!(mode & VM_ACTIVE)) return;
     const int r = r0 + lane;
-    const size_t i = p.mi(m, r);
-    const size_t q = p.qi(m, r);
+    const size_t i = mi(p, m, r);
+    const size_t q = qi(p, m, r);
     const double landAreaFrac = sm.laf[lane], lafPrev = sm.lafPrev[lane];
     const int lc = VIN_K(K_lc, a.landcover[r]) - 1;
     const float4 f = C::PRE ? sm.pforce[C::PRE ? lane : 0]
-                            : p.forcing[p.fi(slot, m, r)];
+                            : p.forcing[fi(p, slot, m, r)];
     double dailyPrec = (double)f.x;
     const double dailyTempC = (double)f.y;
     const double dailyShortWave = (double)f.z;
@@ -1006,8 +1026,8 @@ __device__ __forceinline__ void v_band(const WgkParams &p, VTile<C> &sm, const V
     const int mode = sm.mode[lane];
     const bool store = (mode & VM_ACTIVE) && !(mode & VM_BARE);
     const int k0 = w * C::BPW, e0 = slab * C::SLAB + k0 + 1;
-    const size_t bs = p.bs();
-    double *__restrict__ S = p.a.snow_bands + p.bi(m, r0 + lane, WGK_NBAND_K) + (size_t)e0 * bs;
+    const size_t bs = band_stride(p);
+    double *__restrict__ S = p.a.snow_bands + bi(p, m, r0 + lane, WGK_NBAND_K) + (size_t)e0 * bs;
     if (mode & VM_NOLAND) {  // :916-922
 #pragma unroll
         for (int j = 0; j < C::BPW; j++) {
@@ -1105,8 +1125,8 @@ __device__ __forceinline__ void v_tail(const WgkParams &p, VTile<C> &sm, const i
     const int mode = sm.mode[lane];
     if (!(mode & VM_ACTIVE)) return;
     const int r = r0 + lane;
-    const size_t i = p.mi(m, r);
-    const size_t q = p.qi(m, r);
+    const size_t i = mi(p, m, r);
+    const size_t q = qi(p, m, r);
     const bool noland = (mode & VM_NOLAND) != 0;
     const double landAreaFrac = sm.laf[lane], lafPrev = sm.lafPrev[lane];
     const double dailyPrec = sm.h_prec[lane], cfa = sm.h_cfa[lane], dailyCanopyEvapo = sm.h_canopy_evapo[lane];
@@ -1310,7 +1330,7 @@ __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ W
     const int ps = blockIdx.y;
     if (r >= p.ncell) return;
     const WgkArrays &a = p.a;
-    const size_t q = p.qi_of(ps, r);
+    const size_t q = qi_of(p, ps, r);
     a.s_c1[q] = 1. / (a.p_rivrgh[q] * a.roughness[r]);
     a.s_ekg[q] = exp(-1. * a.p_gwoutf[q]);  // routing.cpp:1940
     a.s_invkg[q] = (1. / a.p_gwoutf[q]);
@@ -1346,11 +1366,11 @@ __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ W
 __global__ void __launch_bounds__(128) k_derive_member(const __grid_constant__ WgkParams p) {
     int r, m;
     if (!map_thread(p, 0, p.ncell, r, m)) return;
-    const double *S = p.a.snow_bands + p.bi(m, r, WGK_NBAND_K);
-    const size_t bs = p.bs();
+    const double *S = p.a.snow_bands + bi(p, m, r, WGK_NBAND_K);
+    const size_t bs = band_stride(p);
     int nz = 0;
     for (int b = 1; b < WGK_NBAND_K; b++) nz |= (S[(size_t)b * bs] != 0.);
-    p.a.s_snowfree[p.mi(m, r)] = (int8_t)(nz == 0);
+    p.a.s_snowfree[mi(p, m, r)] = (int8_t)(nz == 0);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1358,7 +1378,7 @@ __global__ void __launch_bounds__(128) k_derive_member(const __grid_constant__ W
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, const int m, const LocalIn &li, const LocalFlux &fx) {
     const WgkArrays &a = p.a;
-    const size_t i = p.mi(m, r);
+    const size_t i = mi(p, m, r);
     a.river_evapo[i] = 0.;  // routing.cpp:1781
     if (!li.contcell) return;
     const int flags = li.flags;
@@ -1506,8 +1526,8 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
             a.gw[i] = Sg;
         }
         if (flags & (FL_LAKE | FL_RES | FL_GLOWET)) {
-            double *g = p.gbody + p.gb(m, p.gidx[r], GB_N);
-            const size_t gs = p.gs();
+            double *g = p.gbody + gb(p, m, p.gidx[r], GB_N);
+            const size_t gs = gbody_stride(p);
             g[GB_EKS * gs] = exp(-1. * kS);
             g[GB_INVKS * gs] = (1. / kS);
             g[GB_EKG * gs] = li.ekg;
@@ -1623,8 +1643,8 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
                                                    double inflow, const int flags, const int day, const int month,
                                                    double &gwToRiver) {
     const WgkArrays &a = p.a;
-    const double *g = p.gbody + p.gb(m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
-    const size_t gs = p.gs();
+    const double *g = p.gbody + gb(p, m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
+    const size_t gs = gbody_stride(p);
     const double ek = g[GB_EKS * gs], invk = g[GB_INVKS * gs];
     double gwr_glolak = 0., gwr_res = 0., gwr_glowet = 0.;
     if (flags & FL_LAKE) {  // :2677-2720
@@ -1801,7 +1821,7 @@ __device__ __forceinline__ double gather_upstream(const WgkParams &p, const Rive
                                                   const double *qday) {
     // upstream inflow in routing order (= order of the += at routing.cpp:3957)
     double s = 0.;
-    for (int k = c.up0; k < c.up1; k++) s += qday[p.mi(m, p.up_idx[k])];
+    for (int k = c.up0; k < c.up1; k++) s += qday[mi(p, m, p.up_idx[k])];
     return s;
 }
 
@@ -1813,7 +1833,7 @@ __device__ __forceinline__ double *qbuf_of_day(const WgkParams &p, const int day
 __global__ void __launch_bounds__(128) k_route_level(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
     int r, m;
     if (!map_thread(p, p.level_off[level], p.level_off[level + 1], r, m)) return;
-    const size_t i = p.mi(m, r), q = p.qi(m, r);
+    const size_t i = mi(p, m, r), q = qi(p, m, r);
     const RiverCtx c = load_ctx(p, r, i, q);
     if (!(c.flags & FL_ACTIVE)) return;
     double *qday = qbuf_of_day(p, dayofs);
@@ -1831,14 +1851,14 @@ __device__ __forceinline__ void sweep_levels(const WgkParams &p, const int m, co
     int r = begin + threadIdx.x;
     RiverCtx c;
     c.flags = 0;
-    if (r < end) c = load_ctx(p, r, p.mi(m, r), p.qi(m, r));
+    if (r < end) c = load_ctx(p, r, mi(p, m, r), qi(p, m, r));
     for (int level = level_lo; level < level_hi; level++) {
         if (r < end) {
-            if (c.flags & FL_ACTIVE) route_river(p, c, r, m, p.mi(m, r), p.qi(m, r), gather_upstream(p, c, m, qday), day, month, qday);
+            if (c.flags & FL_ACTIVE) route_river(p, c, r, m, mi(p, m, r), qi(p, m, r), gather_upstream(p, c, m, qday), day, month, qday);
             // levels wider than the CTA (only possible when the tail threshold is raised)
             for (int r2 = r + blockDim.x; r2 < end; r2 += blockDim.x) {
-                const RiverCtx c2 = load_ctx(p, r2, p.mi(m, r2), p.qi(m, r2));
-                if (c2.flags & FL_ACTIVE) route_river(p, c2, r2, m, p.mi(m, r2), p.qi(m, r2), gather_upstream(p, c2, m, qday), day, month, qday);
+                const RiverCtx c2 = load_ctx(p, r2, mi(p, m, r2), qi(p, m, r2));
+                if (c2.flags & FL_ACTIVE) route_river(p, c2, r2, m, mi(p, m, r2), qi(p, m, r2), gather_upstream(p, c2, m, qday), day, month, qday);
             }
         }
         if (level + 1 < level_hi) {
@@ -1846,16 +1866,18 @@ __device__ __forceinline__ void sweep_levels(const WgkParams &p, const int m, co
             end = p.level_off[level + 2];
             r = begin + threadIdx.x;
             c.flags = 0;
-            if (r < end) c = load_ctx(p, r, p.mi(m, r), p.qi(m, r));
+            if (r < end) c = load_ctx(p, r, mi(p, m, r), qi(p, m, r));
         }
         __syncthreads();
     }
 }
 
+#if !WGK_MM  // one persistent CTA per member: cell-minor layout only
 __global__ void __launch_bounds__(256) k_route_tail(const __grid_constant__ WgkParams p, const int dayofs, const int level_lo, const int level_hi) {
     sweep_levels(p, blockIdx.x, dayofs, level_lo, level_hi);
 }
 
+#endif  // !WGK_MM
 // ----------------------------------------------------------------------------------------
 // cell-parallel post-pass: river width / area fraction of the next day (:3546-3586), surface
 // water body fractions and next-day land area fraction (:5034-5188), updateLandAreaFrac
@@ -1871,8 +1893,8 @@ struct PostIn {
 
 __device__ __forceinline__ PostIn post_load(const WgkParams &p, const int r, const int m) {
     const WgkArrays &a = p.a;
-    const size_t i = p.mi(m, r);
-    const size_t q = p.qi(m, r);
+    const size_t i = mi(p, m, r);
+    const size_t q = qi(p, m, r);
     PostIn in;
     in.flags = a.s_flags[r];
     in.contf = a.contfreq[r];
@@ -1899,7 +1921,7 @@ __device__ __forceinline__ PostIn post_load(const WgkParams &p, const int r, con
 
 __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int r, const int m, const PostIn &in, const double Sr) {
     const WgkArrays &a = p.a;
-    const size_t i = p.mi(m, r);
+    const size_t i = mi(p, m, r);
     const int flags = in.flags;
     const double contf = in.contf;
     const double cellArea = in.area;
@@ -1925,8 +1947,8 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
     }
     if ((flags & FL_ACTIVE) && (flags & (FL_LAKE | FL_RES | FL_GLOWET))) {
         // evaporation reduction factors of the global water bodies (:2790-2802, 3068-3078, 3287-3296)
-        const double *g = p.gbody + p.gb(m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
-        const size_t gs = p.gs();
+        const double *g = p.gbody + gb(p, m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
+        const size_t gs = gbody_stride(p);
         const double xexp = (in.evaredex * 3.32193);
         if (flags & FL_LAKE) {
             const double maxStorage = g[GB_L_MAX * gs];
@@ -1994,8 +2016,8 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
         // the day's entry of WghmStateFile for the seven routing compartments (routing.cpp:5002-5020), summed in
         // day order as Cell::mean does (wghmStateFile.cpp:711-728)
         const double denom = ((cellArea * (contf / C100)) / C1E6);
-        double *__restrict__ acc = a.mon_acc + p.bi(m, r, 7);
-        const size_t bs = p.bs();
+        double *__restrict__ acc = a.mon_acc + bi(p, m, r, 7);
+        const size_t bs = band_stride(p);
         acc[0 * bs] += a.loc_lake_stor[i] / denom;
         acc[1 * bs] += a.loc_wetl_stor[i] / denom;
         acc[2 * bs] += a.glo_lake_stor[i] / denom;
@@ -2013,7 +2035,7 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
 
 __device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r, const int m) {
     const PostIn in = post_load(p, r, m);
-    route_post_compute(p, r, m, in, p.a.river_stor[p.mi(m, r)]);
+    route_post_compute(p, r, m, in, p.a.river_stor[mi(p, m, r)]);
 }
 
 __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkParams p) {
@@ -2035,7 +2057,7 @@ __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkP
 __global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
     int r, m;
     if (!map_thread(p, p.level_off[level], p.level_off[level + 1], r, m)) return;
-    const size_t i = p.mi(m, r), q = p.qi(m, r);
+    const size_t i = mi(p, m, r), q = qi(p, m, r);
     WGK_INSITU_BEGIN();
     if (level == 0) WGK_INSITU_STAMP(1, 0, dayofs);
     if (level == 0) stamp_task(p, 1, 0, dayofs);
@@ -2064,8 +2086,8 @@ __device__ __forceinline__ void v_preload(const WgkParams &p, VTile<C> &sm, cons
     const WgkArrays &a = p.a;
     const int r = r0 + lane;
     if (!C::PRE || r < begin || r >= end) return;
-    const size_t i = p.mi(m, r);
-    const size_t q = p.qi(m, r);
+    const size_t i = mi(p, m, r);
+    const size_t q = qi(p, m, r);
     // four groups of copies, dealt round-robin to the warps 1 .. NW-1
 #pragma unroll
     for (int task = 1; task <= 4; task++) {
@@ -2087,7 +2109,7 @@ __device__ __forceinline__ void v_preload(const WgkParams &p, VTile<C> &sm, cons
         sm.pk[K_ldd][lane] = a.ldd[r];
     } else if (task == 3) {
         __pipeline_memcpy_async(&sm.pforce[lane],
-                                &p.forcing[p.fi(slot, m, r)],
+                                &p.forcing[fi(p, slot, m, r)],
                                 sizeof(float4));
         VP_D(HI_p_prec, a.p_prec[q]); VP_D(HI_ptc_ari, a.p_ptc_ari[q]); VP_D(HI_ptc_hum, a.p_ptc_hum[q]);
         VP_D(HI_lai_precsum, a.lai_precsum[i]); VP_D(HI_snow, a.snow[i]); VP_D(HI_netrad, a.p_netrad[q]);
@@ -2215,6 +2237,7 @@ __device__ __forceinline__ void vertical_tile(const WgkParams &p, VTile<C> &sm, 
 #endif
 }
 
+#if !WGK_MM  // the band-parallel tile kernels run on the cell-minor layout only
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::NW == 5 ? 6 : 12) k_cells_pre(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
     __shared__ VTile<C> sm;
@@ -2228,6 +2251,7 @@ __global__ void __launch_bounds__(C::THREADS, C::NW == 5 ? 6 : 12) k_vertical(co
     vertical_tile<C, false>(p, sm, 0, p.ncell, blockIdx.y, dayofs);
 }
 
+#endif  // !WGK_MM
 // thread-per-cell forms of k_vertical and k_cells_pre
 __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_vertical_tpc(const __grid_constant__ WgkParams p, const int dayofs) {
     __shared__ SnowStage stage;
@@ -2254,6 +2278,7 @@ __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_cells_pre_tpc(const __
     if (begin == 0) stamp_task(p, 0, 1, dayofs);
 }
 
+#if !WGK_MM  // k_tail_chunk and the cell-owner schedule run on the cell-minor layout only
 // narrow levels [level_lo, level_hi) of one day in one persistent CTA per member, then the
 // post-pass of those cells
 __global__ void __launch_bounds__(256) k_tail_chunk(const __grid_constant__ WgkParams p, const int dayofs, const int level_lo, const int level_hi) {
@@ -2366,8 +2391,8 @@ __global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) 
     const bool valid = w < s.nwarps && r < s.warp_end[w];  // lanes without a cell only take part in the barriers
     const unsigned mask = __ballot_sync(0xffffffffu, valid);  // the lanes of this warp that own a cell
     const int m = blockIdx.y;
-    const size_t mb = p.mi(m, 0);  // (the cell-owner schedule runs on the cell-minor layout only)
-    const size_t q = p.qi(m, r);
+    const size_t mb = mi(p, m, 0);  // (the cell-owner schedule runs on the cell-minor layout only)
+    const size_t q = qi(p, m, r);
     uint32_t *prog = s.progress + (size_t)m * s.nwarps;
     const int up0 = valid ? p.up_off[r] : 0, up1 = valid ? p.up_off[r + 1] : 0;
     const int dn = valid ? p.down[r] : -1;
@@ -2424,6 +2449,7 @@ __global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) 
 }
 #endif  // WGK_EMU
 
+#endif  // !WGK_MM
 // ----------------------------------------------------------------------------------------
 // calendar, forcing, diagnostics
 // ----------------------------------------------------------------------------------------
@@ -2454,7 +2480,7 @@ __global__ void k_end_of_day(const __grid_constant__ WgkParams p, const int dayo
     const int total = p.nmember * p.nrec;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
         const int m = k / p.nrec, cidx = k % p.nrec;
-        p.record[(size_t)row * total + k] = qday[p.mi(m, p.record_cells[cidx])];
+        p.record[(size_t)row * total + k] = qday[mi(p, m, p.record_cells[cidx])];
     }
 }
 
@@ -2488,7 +2514,7 @@ __global__ void __launch_bounds__(256) k_total_storage(const __grid_constant__ W
     const WgkArrays &a = p.a;
     double s = 0.;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.ncell; r += gridDim.x * blockDim.x) {
-        const size_t i = p.mi(m, r);
+        const size_t i = mi(p, m, r);
         const double laf = (0 == a.status_laf_next[i]) ? a.land_area_frac[i] : a.land_area_frac_next[i];
         const double land = (a.canopy[i] + a.snow[i] + a.soil[i]) * a.area[r] / C1E6 * laf / C100;
         s += land + a.gw[i] + a.loc_lake_stor[i] + a.loc_wetl_stor[i] + a.glo_lake_stor[i] + a.glo_wetl_stor[i]
@@ -2517,7 +2543,7 @@ __device__ __forceinline__ double laf_of(const WgkArrays &a, const size_t i) {
 // `ndays` entries (Cell::mean): canopy / snow / soil carry the month-end value on every day of the month.
 __device__ __forceinline__ void state_of_cell(const WgkParams &p, const int x, const int m, const int kind, const int ndays, double v[10]) {
     const WgkArrays &a = p.a;
-    const size_t i = p.mi(m, x);
+    const size_t i = mi(p, m, x);
     const double laf = laf_of(a, i), contf = a.contfreq[x];
     const double land[3] = {a.canopy[i] * laf / contf, a.snow[i] * laf / contf, a.soil[i] * laf / contf};
     const double denom = ((a.area[x] * (contf / C100)) / C1E6);
@@ -2531,7 +2557,7 @@ __device__ __forceinline__ void state_of_cell(const WgkParams &p, const int x, c
             for (int d = 0; d < ndays; d++) s += land[k];
             v[k] = s / (double)ndays;
         }
-        for (int k = 0; k < 7; k++) v[3 + k] = a.mon_acc[p.bi(m, x, 7) + (size_t)k * p.bs()] / (double)ndays;
+        for (int k = 0; k < 7; k++) v[3 + k] = a.mon_acc[bi(p, m, x, 7) + (size_t)k * band_stride(p)] / (double)ndays;
     }
 }
 
@@ -2629,7 +2655,7 @@ __global__ void __launch_bounds__(128) k_enkf_update(const __grid_constant__ Wgk
     if (j >= ncells) return;
     const WgkArrays &a = p.a;
     const int x = pos[j];
-    const size_t i = p.mi(m, x);
+    const size_t i = mi(p, m, x);
     double w[10], mon[10];
     state_of_cell(p, x, m, 1, ndays, w);
     state_of_cell(p, x, m, 0, ndays, mon);
@@ -2647,8 +2673,8 @@ __global__ void __launch_bounds__(128) k_enkf_update(const __grid_constant__ Wgk
     const double laf = laf_of(a, i), contf = a.contfreq[x];
     const double snow_mean_before = mon[1];
     const double snow_after = fl[1] + mf[1];
-    double *__restrict__ S = a.snow_bands + p.bi(m, x, WGK_NBAND_K);
-    const size_t bs = p.bs();
+    double *__restrict__ S = a.snow_bands + bi(p, m, x, WGK_NBAND_K);
+    const size_t bs = band_stride(p);
     for (int e = 1; e < WGK_NBAND_K; e++) {
         double sie = (laf == 0.) ? 0. : S[(size_t)e * bs] * laf / contf;
         if (snow_mean_before == 0) sie = snow_after / 100;
@@ -2676,4 +2702,4 @@ __global__ void __launch_bounds__(128) k_enkf_update(const __grid_constant__ Wgk
     a.gw[i] = w[9] * denom;
 }
 
-}  // namespace wgk
+}  // namespace wgk / wgk_mm
