@@ -173,6 +173,10 @@ int wgk_get_record(wgk_ctx *ctx, int member, double *out, int ndays);
  * the start state of the next cycle (daily.cpp:1896-1924, routing.cpp:851-882).  field, prediction, mean_field:
  * host [ncells][10]. */
 int wgk_month_begin(wgk_ctx *ctx);
+/* the day's WghmStateFile entry of the seven routing compartments (routing.cpp:5002-5020: local lake, local wetland, global lake,
+ * global wetland, reservoir, river, groundwater in mm over the continental area) of all cells in reference order, host
+ * out[7][ncell]: packed on the device, ONE device-to-host copy (what the class shim routingClass::routing needs per day) */
+int wgk_get_day_state(wgk_ctx *ctx, int member, double *out);
 int wgk_state_vector(wgk_ctx *ctx, int member, int kind, const int32_t *cells, int ncells, const double *mean_field, double *out);
 int wgk_enkf_update(wgk_ctx *ctx, int member, const int32_t *cells, int ncells, const double *field, const double *prediction,
                     const double *mean_field);

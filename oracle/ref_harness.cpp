@@ -504,6 +504,10 @@ static int run_replay(int argc, char **argv) {
     if (configFile->additionalfile.empty()) routing.setStoragesToZero();
     else routing.setStorages(*wghmState, *additionalOutIn);
     if (configFile->startvaluefile.empty()) routing.setLakeWetlToMaximum(options.start_year);
+    if ((readinstatus == 1) && (additionalOutIn->additionalfilestatus == 1)) {  // integrateWGHM.cpp:311-316 (first_day_after_PDAF): restart from checkpoints
+        routing.annualInit(options.start_year, configFile->startMonth, *additionalOutIn);
+        routing.update_landarea_red_fac_PDAF(*calParam, *additionalOutIn);
+    }
     for (int n = 0; n < ng; ++n) G_toBeCalculated[n] = 1;  // options.basin == 1
     for (int n = 0; n < ng; n++) {
         dailyWaterBalance.G_gammaHBV[n] = calParam->getValue(P_GAMRUN_C, n);

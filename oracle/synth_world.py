@@ -467,7 +467,7 @@ def default_params(w, variant=0):
     return p
 
 
-def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_discharge=True, params=None, water_use=False):
+def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_discharge=True, params=None, water_use=False, time_series=0):
     inp = os.path.join(out, "input")
     clim = os.path.join(out, "climate")
     rout = os.path.join(out, "routing")
@@ -514,8 +514,26 @@ def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_
     write_unf(f"{inp}/GLWDunits.UNF4", np.arange(1, ng + 1), "i4")
     write_unf(f"{inp}/G_ROUGHNESS.UNF0", w.roughness, "f4")
     write_unf(f"{inp}/G_BANKFULL.UNF0", w.bankfull, "f4")
+    if time_series == 1:
+        # yearly [cell][365] files of climateYear.cpp:38-58 (time_series 1): the same daily values as the monthly .31 files
+        for y in range(years[0], years[1] + 1):
+            yr = {k: np.zeros((ng, 365), np.float32) for k in ("P", "T", "SW", "LW")}
+            d0 = 0
+            for m in range(1, 13):
+                nd = (31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31)[m - 1]
+                if months[0] <= m <= months[1] or years[0] != years[1]:
+                    f = forcing_month(w, y, m)
+                    for k in yr:
+                        yr[k][:, d0:d0 + nd] = f[k][:, :nd]
+                d0 += nd
+            write_unf(f"{clim}/G_GPCC_H08day_V20110128_{y}.365.UNF0", yr["P"], "f4")
+            write_unf(f"{clim}/G_TEMP_H08_int_{y}.365.UNF0", yr["T"], "f4")
+            write_unf(f"{clim}/G_SSRD_H08_int_{y}.365.UNF0", yr["SW"], "f4")
+            write_unf(f"{clim}/G_SLRD_H08_int_{y}.365.UNF0", yr["LW"], "f4")
     for y in range(years[0], years[1] + 1):
         for m in range(months[0], months[1] + 1):
+            if time_series == 1:
+                break
             f = forcing_month(w, y, m)
             write_unf(f"{clim}/GPREC_{y}_{m}.31.UNF0", f["P"], "f4")
             write_unf(f"{clim}/GTEMP_{y}_{m}.31.UNF0", f["T"], "f4")
@@ -531,6 +549,7 @@ def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_
             fh.write("%d %.2f %.2f %.1f %d %.2f %.2f\n" % r)
     opts = list(OPTIONS)
     opts[2] = grid_store
+    opts[OPTION_NAMES.index("time_series")] = time_series
     if water_use:
         # SURVEY 8f-4 (next row): net abstractions from surface water / groundwater, m3 per month (routing.cpp:884-977),
         # subtract_use = 2 with the other use options at their canonical 0

@@ -291,7 +291,8 @@ def test_member_minor_layout_is_bit_identical(world3000, monkeypatch):
     """lane = member: the member-minor layout [band][cell][member] (a warp = 32 members of one cell, chosen automatically for
     large ensembles / parameter sweeps) against the cell-minor layout: 40 members (padded to 64 lanes) with 40 different
     parameter sets and per-member forcing, 14 days; every state / flux field of several members, the snow bands, the station
-    record, the monthly state vector, the ensemble moments and the field round trip must be the same bits"""
+    record, the monthly state vector, the ensemble moments and the field round trip must be the same bits - with the whole-day
+    schedule and with the (day, level) wavefront graph on the member-minor layout (the schedule of 32 - 64 members per GPU)"""
     from oracle import synth_world as sw, wg_init
     import watergap2_b200 as wg
     from watergap2_b200.ensemble import device_tensor
@@ -308,9 +309,9 @@ def test_member_minor_layout_is_bit_identical(world3000, monkeypatch):
                      (base["T"] + rng.normal(0., 1.5, base["T"].shape)).astype(np.float32)))
     cells = np.arange(3, w.ng, 17, dtype=np.int32)
     out = []
-    for layout in ("cells", "members"):
+    for layout, sched in (("cells", "wholeday"), ("members", "wholeday"), ("members", "wavefront")):
         monkeypatch.setenv("WGK_LAYOUT", layout)
-        monkeypatch.setenv("WGK_DAY_SCHEDULE", "wholeday")
+        monkeypatch.setenv("WGK_DAY_SCHEDULE", sched)
         monkeypatch.setenv("WGK_VERTICAL_FORM", "cells")
         m = wg.Model(w.ng, nmember=nm, npset=nm)
         assert m.layout == layout
@@ -340,10 +341,12 @@ def test_member_minor_layout_is_bit_identical(world3000, monkeypatch):
         out.append(({(k, mem): m.get(k, mem) for k in names for mem in (0, 7, 31, 32, 39)}, m.get_record(14, 33),
                     m.state_vector(cells, "month", member=38), mom, m.total_storage_km3(39)))
         m.close()
-    assert np.array_equal(out[0][1], out[1][1]) and np.abs(out[0][1]).sum() > 0
-    assert np.array_equal(out[0][2], out[1][2])
-    assert np.array_equal(out[0][3], out[1][3])
-    assert out[0][4] == out[1][4]
-    for k in out[0][0]:
-        assert np.array_equal(out[0][0][k], out[1][0][k]), k
+    assert np.abs(out[0][1]).sum() > 0
+    for other in out[1:]:
+        assert np.array_equal(out[0][1], other[1])
+        assert np.array_equal(out[0][2], other[2])
+        assert np.array_equal(out[0][3], other[3])
+        assert out[0][4] == other[4]
+        for k in out[0][0]:
+            assert np.array_equal(out[0][0][k], other[0][k]), k
     assert not np.array_equal(out[0][0][("soil", 0)], out[0][0][("soil", 39)])

@@ -4,6 +4,7 @@ import ctypes
 import filecmp
 import os
 import re
+import shutil
 import subprocess
 
 import numpy as np
@@ -95,6 +96,100 @@ def test_checkpoint_codecs_round_trip_reference_files(host, world3000, tmp_path)
         out = str(tmp_path / ("rt_" + key))
         assert host.wg_host_state_roundtrip(kind.encode(), ref[key].encode(), out.encode(), 3000, err, 512) == 0, err.value
         assert filecmp.cmp(ref[key], out, shallow=False), kind
+
+
+def _restart_configs(tmp, world):
+    """world for January + February 1901; config1 = January from the cold start, config2 = February restarted from the three
+    checkpoint files `output/m1_*` (PDAF monthly cycle, integrateWGHM.cpp:292-316); -> (config1, config2, names of the files)"""
+    from oracle import synth_world as sw
+    sw.write_world(world, tmp, (1901, 1901), (1, 2))
+    cfg = open(os.path.join(tmp, "config.txt")).read()
+    out = os.path.join(tmp, "output")
+    files = ("wghm_state_lastday.txt", "snow_lastday.txt", "additional_lastday.txt")
+    c1, c2 = os.path.join(tmp, "config1.txt"), os.path.join(tmp, "config2.txt")
+    open(c1, "w").write(cfg.replace("end_month 2", "end_month 1"))
+    open(c2, "w").write(cfg.replace("start_month 1", "start_month 2").replace(
+        "param_json", f"wghm_state {out}/m1_wghm_state_lastday.txt\nsnowInElevation_startvalues {out}/m1_snow_lastday.txt\n"
+                      f"additionalOutIn_startvalues {out}/m1_additional_lastday.txt\nparam_json"))
+    return c1, c2, files
+
+
+def _run_ref(tmp, cfg, prefix, files):
+    log = open(os.path.join(tmp, "driver.log"), "a")
+    subprocess.check_call([HARNESS, "driver", cfg], stdout=log, stderr=log, cwd=tmp)
+    out = os.path.join(tmp, "output")
+    for k in files:
+        shutil.copy(os.path.join(out, k), os.path.join(out, prefix + k))
+
+
+def test_host_initialisation_cold_and_restart_equals_reference(host, world3000, tmp_path, oracle_lib):
+    """the start state the product's host classes would push to the device - cold start, and restart from the reference's own
+    checkpoint files (routingClass::initFractionStatusAdditionalOI, setStorages, annualInit, update_landarea_red_fac_PDAF,
+    dailyWaterBalanceClass::setStorages, the LAI restore) - is BIT-identical to the compiled reference's memory before its
+    first day (35 arrays); runs on the CPU (no context is created)"""
+    if not os.path.exists(HARNESS):
+        pytest.skip("compiled reference not available")
+    tmp = str(tmp_path)
+    c1, c2, files = _restart_configs(tmp, world3000)
+    _run_ref(tmp, c1, "m1_", files)
+    err = ctypes.create_string_buffer(1024)
+    for cfg, tag in ((c1, "cold"), (c2, "restart")):
+        subprocess.check_call([HARNESS, "replay", cfg, os.path.join(tmp, f"ref0_{tag}.wgd"), "--days", "0-0"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL, cwd=tmp)
+        assert host.wg_host_init_dump(cfg.encode(), 3000, os.path.join(tmp, f"host0_{tag}.wgd").encode(), err, 1024) == 0, err.value
+        ref = oracle_lib.read_dump(os.path.join(tmp, f"ref0_{tag}.wgd"), days={0})
+        got = oracle_lib.read_dump(os.path.join(tmp, f"host0_{tag}.wgd"), days={0})
+        n = 0
+        for key, g in got.items():
+            assert key in ref, key
+            assert np.array_equal(ref[key], g), (tag, key[0])
+            n += 1
+        assert n >= 35
+    r = oracle_lib.read_dump(os.path.join(tmp, "ref0_restart.wgd"), days={0})
+    assert r[("lai_days", 0)].any() and (r[("land_area_frac_prev", 0)] > 0).any()  # the restart really restored state
+
+
+@pytest.mark.gpu
+def test_host_driver_restart_matches_reference_driver(host, world3000, tmp_path):
+    """PDAF monthly cycle through checkpoints, end to end on the GPU: (a) February restarted from the REFERENCE's January
+    checkpoint files by both sides; (b) the product's own cycle - January, its three checkpoint files, February restarted from
+    them - against the reference doing the same through its own files.  Final state, snow-band and additional files compared."""
+    if not os.path.exists(HARNESS):
+        pytest.skip("compiled reference not available")
+    tmp = str(tmp_path)
+    c1, c2, files = _restart_configs(tmp, world3000)
+    out = os.path.join(tmp, "output")
+    _run_ref(tmp, c1, "m1_", files)
+    _run_ref(tmp, c2, "ref2_", files)
+    err = ctypes.create_string_buffer(1024)
+    secs = ctypes.c_double()
+
+    def compare(prefix_ref, what, frac_ok, worst_ok):
+        a = np.loadtxt(os.path.join(out, prefix_ref + "wghm_state_lastday.txt"), skiprows=2)
+        b = np.loadtxt(os.path.join(out, "wghm_state_lastday.txt"), skiprows=2)
+        e = np.abs(a[:, 1:] - b[:, 1:]) / np.maximum(np.maximum(np.abs(a[:, 1:]), np.abs(b[:, 1:])), 1e-6)  # mm over the continental area
+        assert (e <= 1e-10).mean() >= frac_ok and e.max() < worst_ok, (what, "state", float(e.max()), float((e > 1e-10).mean()))
+        sa = np.loadtxt(os.path.join(out, prefix_ref + "snow_lastday.txt"), skiprows=1)
+        sb = np.loadtxt(os.path.join(out, "snow_lastday.txt"), skiprows=1)
+        es = np.abs(sa - sb) / np.maximum(np.maximum(np.abs(sa), np.abs(sb)), 1e-6)
+        assert (es <= 1e-10).mean() >= frac_ok and es.max() < worst_ok, (what, "snow", float(es.max()))
+        aa = np.loadtxt(os.path.join(out, prefix_ref + "additional_lastday.txt"), skiprows=2)
+        ab = np.loadtxt(os.path.join(out, "additional_lastday.txt"), skiprows=2)
+        assert aa.shape == ab.shape == (3000, 54)
+        assert np.array_equal(aa[:, :3], ab[:, :3]), (what, "ID / LAI counters")  # integer state: exact
+        ea = np.abs(aa - ab) / np.maximum(np.maximum(np.abs(aa), np.abs(ab)), 1e-6)
+        assert (ea <= 1e-10).mean() >= frac_ok and ea.max() < worst_ok, (what, "additional", float(ea.max()), np.argwhere(ea > 1e-7)[:5].tolist())
+
+    # (a) both sides restart from the reference's files
+    assert host.wg_host_integrate(c2.encode(), 3000, 0, ctypes.byref(secs), err, 1024) == 28, err.value
+    compare("ref2_", "restart from the reference's checkpoint", 0.9995, 1e-6)
+    # (b) the product's own cycle
+    assert host.wg_host_integrate(c1.encode(), 3000, 0, ctypes.byref(secs), err, 1024) == 31, err.value
+    compare("m1_", "January", 0.9995, 1e-6)
+    for k in files:
+        shutil.copy(os.path.join(out, k), os.path.join(out, "m1_" + k))  # February now starts from the PRODUCT's checkpoint
+    assert host.wg_host_integrate(c2.encode(), 3000, 0, ctypes.byref(secs), err, 1024) == 28, err.value
+    compare("ref2_", "product's own monthly cycle", 0.995, 1e-5)
 
 
 @pytest.mark.gpu
@@ -288,3 +383,112 @@ def test_calibGammaClass_cpp_equals_python_on_random_scenarios(host, tmp_path):
         finally:
             L.wg_calib_destroy(h)
     assert len(endings) >= 3  # 1 % criterion, 10 % criterion and CFA / CFS endings all occur
+
+
+def test_b1_ffi_symbols_exported(host):
+    """B1: the reference's own FFI names (initializeWGHM.h:14, integrateWGHM.h:12) are exported by libwghost.so"""
+    for name in ("initialize_wghm_", "integrate_wghm_", "wg_host_integrate", "wg_host_init_dump"):
+        assert hasattr(host, name), name
+
+
+@pytest.mark.gpu
+def test_b1_entry_points_run_the_model(host, world3000, tmp_path):
+    """initialize_wghm_ / integrate_wghm_ called the way PDAF's Fortran side calls them (pointers by reference, long* dates,
+    program name): "OL" runs the configured period, writes the same files as the C++ driver and frees the objects; a PDAF-mode
+    call runs exactly the month it is given, from the checkpoint objects, and leaves the objects alive"""
+    if not os.path.exists(HARNESS):
+        pytest.skip("compiled reference not available")
+    tmp = str(tmp_path)
+    c1, c2, files = _restart_configs(tmp, world3000)
+    out = os.path.join(tmp, "output")
+    _run_ref(tmp, c1, "m1_", files)  # the checkpoint files config2 names
+    err = ctypes.create_string_buffer(1024)
+    secs = ctypes.c_double()
+    vp = ctypes.c_void_p
+
+    def call(cfg, prog, year, month):
+        st, cal, add, snow, mean, cf = vp(), vp(), vp(), vp(), vp(), vp()
+        y, m, step, total = ctypes.c_long(year), ctypes.c_long(month), ctypes.c_long(0), ctypes.c_long(1)
+        host.initialize_wghm_(cfg.encode(), ctypes.byref(st), ctypes.byref(cal), ctypes.byref(add), ctypes.byref(snow), ctypes.byref(y), ctypes.byref(m),
+                              prog.encode(), b"", ctypes.byref(mean))
+        assert st.value and cal.value and add.value and snow.value and mean.value
+        host.integrate_wghm_(cfg.encode(), ctypes.byref(cf), ctypes.byref(st), ctypes.byref(cal), ctypes.byref(add), ctypes.byref(snow),
+                             ctypes.byref(step), ctypes.byref(total), ctypes.byref(y), ctypes.byref(m), prog.encode())
+        return st, cal, add, snow, cf
+
+    host.initialize_wghm_.restype = None
+    host.integrate_wghm_.restype = None
+    # "OL": February from the checkpoint, as configured
+    assert host.wg_host_integrate(c2.encode(), 3000, 0, ctypes.byref(secs), err, 1024) == 28, err.value
+    for k in files:
+        shutil.copy(os.path.join(out, k), os.path.join(out, "drv_" + k))
+        os.remove(os.path.join(out, k))
+    st, cal, add, snow, cf = call(c2, "OL", 1901, 2)
+    assert not (st.value or cal.value or add.value or snow.value or cf.value)  # freed and nulled at the end of an OL run
+    for k in files:
+        assert filecmp.cmp(os.path.join(out, k), os.path.join(out, "drv_" + k), shallow=False), k
+        os.remove(os.path.join(out, k))
+    # PDAF mode: the dates of the call override the file's (config.txt says January .. February)
+    cfg_all = os.path.join(tmp, "config2_all.txt")
+    open(cfg_all, "w").write(open(c2).read().replace("start_month 2", "start_month 1"))
+    st, cal, add, snow, cf = call(cfg_all, "PDAF", 1901, 2)
+    assert st.value and cal.value and add.value and snow.value and cf.value  # the caller keeps the objects
+    for k in files:
+        assert filecmp.cmp(os.path.join(out, k), os.path.join(out, "drv_" + k), shallow=False), k
+
+
+def test_product_topology_builder_full_size_equals_oracle(host, oracle_lib, tmp_path):
+    """wg_rout_prepare.cpp at the BASELINE size (67 420 cells): every routing file it writes is byte-identical to the arrays of the
+    oracle's C topology builder, which is itself pinned against the compiled reference at this size (tests/test_oracle_vs_ref.py,
+    DESIGN.md 2): routing order, outflow cells, LDD, 9-slot inflow cells, flow accumulation, basins, cells to outlet"""
+    from oracle import synth_world as sw
+    w = sw.build_world(67420)
+    tmp = str(tmp_path)
+    sw.write_world(w, tmp, (1901, 1901), (1, 1), grid_store=0, daily_discharge=False)
+    err = ctypes.create_string_buffer(512)
+    nlev = ctypes.c_int()
+    rd = os.path.join(tmp, "routing2")
+    os.makedirs(rd)
+    assert host.wg_host_prepare_routing_files(os.path.join(tmp, "input").encode(), rd.encode(), 1, 67420, ctypes.byref(nlev), err, 512) == 0, err.value
+    t = oracle_lib.rout_prepare(w.flowdir, w.row, w.col, w.gcrc.T)
+    assert nlev.value == t["nlevels"]
+    for fn, key, dt in (("G_ROUT_ORDER.UNF4", "rout_order", ">i4"), ("G_OUTFLC.UNF4", "outflow_cell", ">i4"), ("G_LDD_2.UNF1", "ldd_2", "i1"),
+                        ("G_INFLC.9.UNF4", "inflow9", ">i4"), ("G_FLOW_ACC.UNF2", "flow_acc", ">i2"), ("G_BASINS.UNF2", "basins", ">u2"),
+                        ("G_BASINS_2.UNF2", "basins2", ">u2"), ("G_CELLS_TO_OUTLET.UNF2", "cells_to_outlet", ">u2")):
+        got = np.fromfile(os.path.join(rd, fn), dtype=dt)
+        assert np.array_equal(got, np.asarray(t[key]).ravel().astype(got.dtype)), fn
+
+
+@pytest.mark.gpu
+def test_host_built_context_equals_array_upload_full_size(host):
+    """the model bench.py and smoke() time is built by the product's host layer (wg_host_create_context: reference-format files ->
+    rout_prepare -> init sequence -> device); at 67 420 cells its device state and 5 stepped days are bit-identical to a context
+    loaded from the arrays of the init restatement (oracle/wg_init.py, itself bit-identical to the reference's day-0 memory)"""
+    import tempfile
+    import watergap2_b200 as wg
+    from oracle import synth_world as sw, wg_init
+    w = sw.build_world(67420)
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    tmp = tempfile.mkdtemp(prefix="wg_hostctx_")
+    try:
+        sw.write_world(w, tmp, (1901, 1901), (1, 1), grid_store=0, daily_discharge=False)
+        a = wg.Model.from_config(os.path.join(tmp, "config.txt"), w.ng, 0)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    b = wg.Model(w.ng)
+    b.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+    b.load(ini)
+    f = sw.forcing_month(w, 1901, 1)
+    names = wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS + ["discharge", "snow_bands"]
+    statics = [k for k in ini if not k.startswith("_") and k != "params" and a.has_field(k) and k not in names]
+    assert len(statics) > 40
+    for k in statics:
+        assert np.array_equal(a.get(k), b.get(k)), k
+    assert np.array_equal(a.device_order(), b.device_order())
+    for m in (a, b):
+        m.forcing_reserve(31)
+        m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+        m.step_days(1, 0, 1, 0, 5)
+    for k in names:
+        assert np.array_equal(a.get(k), b.get(k)), k

@@ -27,5 +27,18 @@ b)  # bench only
   timeout 900 python bench.py --steps ${STEPS:-30} --warmup 3 ${BENCH_ARGS} > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
   tail -c 3000 $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err
   ;;
+p)  # profiles: launch list of the bench command, full captures of the dominant kernels (1 member) and of the vertical kernel in both layouts (64 members)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches_bench.csv \
+      python bench.py --steps 1 --warmup 1 --no-cpu --legs none > $OUT/${TAG}_bench_under_ncu.log 2>&1
+  for K in k_cells_pre_tpc k_river_level k_tail_chunk; do
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^$K\$" -c 1 -f -o $OUT/${TAG}_${K}_m1 \
+        python tools/profile_run.py --members 1 --days 1 > $OUT/${TAG}_ncu_${K}_m1.log 2>&1
+  done
+  for L in cells members; do
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^k_vertical_tpc$' -c 1 -f -o $OUT/${TAG}_k_vertical_tpc_m64_$L \
+        python tools/profile_run.py --members 64 --days 1 --layout $L > $OUT/${TAG}_ncu_k_vertical_tpc_m64_$L.log 2>&1
+    tail -1 $OUT/${TAG}_ncu_k_vertical_tpc_m64_$L.log
+  done
+  ;;
 esac
 ls -la $OUT | grep ${TAG}_ | tail -20

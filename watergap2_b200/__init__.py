@@ -80,6 +80,7 @@ def lib():
     L.wgk_set_cell_classes.argtypes = [vp, vp]
     L.wgk_set_forcing_unf.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, ci]
     L.wgk_month_begin.argtypes = [vp]
+    L.wgk_get_day_state.argtypes = [vp, ci, vp]
     L.wgk_state_vector.argtypes = [vp, ci, ci, vp, ci, vp, vp]
     L.wgk_enkf_update.argtypes = [vp, ci, vp, ci, vp, vp, vp]
     L.wgk_num_levels.argtypes = [vp]
@@ -121,8 +122,44 @@ def lib():
     return L
 
 
+HOST_LIB_PATH = os.path.join(HERE, "libwghost.so")
+_host = None
+
+
+def host_lib():
+    """libwghost.so: the C++ drop-in layer (class look-alikes, routing-file builder, checkpoint codecs, integrate_wghm driver)"""
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise WgkError(f"{HOST_LIB_PATH} not found - run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib()  # libwgk.so first (libwghost links it)
+        H = ctypes.CDLL(HOST_LIB_PATH)
+        H.wg_host_create_context.restype = ctypes.c_void_p
+        H.wg_host_create_context.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
+        H.wg_host_integrate.restype = ctypes.c_long
+        H.wg_host_integrate.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_char_p, ctypes.c_size_t]
+        _host = H
+    return _host
+
+
 class Model:
     """One wgk context: `nmember` members of a `ncell` grid on one GPU."""
+
+    @classmethod
+    def from_config(cls, config_file, ncell, device=0):
+        """a ready-to-step single-member model built by the product's HOST LAYER (libwghost.so) from a reference-format
+        configuration: routing files (rout_prepare), init sequence of integrate_wghm_, statics / parameters / start state on the
+        device, 31 forcing slots reserved (wg_host_create_context)"""
+        err = ctypes.create_string_buffer(1024)
+        ptr = host_lib().wg_host_create_context(os.fsencode(config_file), ncell, device, err, 1024)
+        if not ptr:
+            raise WgkError(f"wg_host_create_context failed: {err.value.decode()}")
+        m = cls.__new__(cls)
+        m.ncell, m.nmember, m.npset, m.device = ncell, 1, 1, device
+        m._L = lib()
+        m._c = ctypes.c_void_p(ptr)
+        m._ids = {}
+        return m
 
     def __init__(self, ncell, nmember=1, npset=1, device=0, restart=0, tail_threshold=0, use_graph=1):
         self.ncell, self.nmember, self.npset, self.device = ncell, nmember, npset, device
@@ -282,6 +319,12 @@ class Model:
     # -- EnKF state bridge ------------------------------------------------------------------------
     def month_begin(self):
         self._ck(self._L.wgk_month_begin(self._c))
+
+    def day_state(self, member=0):
+        """[7, ncell]: the day's WghmStateFile entry of the routing compartments (mm over the continental area), reference order"""
+        out = np.empty((7, self.ncell), np.float64)
+        self._ck(self._L.wgk_get_day_state(self._c, member, out.ctypes.data))
+        return out
 
     def state_vector(self, cells, kind="month", member=0, mean_field=None):
         """[ncells, 10] state vector of extract_sub_ (mm over the continental area) for `cells` (0-based)"""

@@ -31,8 +31,8 @@ void calibParamClass::readJson(const std::string &file, int ncell) {
     std::stringstream ss;
     ss << f.rdbuf();
     const std::string txt = ss.str();
-    ncell_ = ncell;
-    v_.assign((size_t)26 * ncell, 0.0);
+    ncell_ = ncell > 0 ? ncell : 0;
+    v_.assign((size_t)26 * ncell_, 0.0);
     auto find_key = [&](const std::string &key) -> size_t {
         const std::string q = "\"" + key + "\"";
         size_t p = txt.find(q);
@@ -43,6 +43,11 @@ void calibParamClass::readJson(const std::string &file, int ncell) {
     size_t p = find_key("ng_param");
     if (p == std::string::npos) throw std::runtime_error("ERROR readJson(): calibParamJson.is_object() == false");
     const int ng_file = (int)strtod(txt.c_str() + p, nullptr);
+    if (ncell <= 0) {  // the B1 entry points take the cell count from the parameter file (the reference compiles it in, def.h:10)
+        ncell = ng_file;
+        ncell_ = ncell;
+        v_.assign((size_t)26 * ncell, 0.0);
+    }
     if (ng_file != ncell)
         throw std::runtime_error("ERROR readJson(): Predefined number of grid cells " + std::to_string(ncell) +
                                  " does not match number found in JSON object header " + std::to_string(ng_file));
@@ -57,6 +62,13 @@ void calibParamClass::readJson(const std::string &file, int ncell) {
             s = e;
             while (*s == ',' || *s == ' ' || *s == '\n') s++;
         }
+    }
+}
+
+ConfigFile::ConfigFile(const std::string &file, int year, int month, const std::string &progName) : ConfigFile(file) {
+    if (progName != "OL") {  // configFile.cpp:76-113: a PDAF cycle runs exactly the month it is called for
+        startMonth = endMonth = month;
+        startYear = endYear = year;
     }
 }
 
@@ -129,11 +141,12 @@ void geoClass::init(const std::string &in, int ncell, int resOpt) {  // geo.cpp:
 // ------------------------------------------------------------------------------------------
 // engine
 // ------------------------------------------------------------------------------------------
-Engine::Engine(int nc, int device) : ncell(nc), dailyWaterBalance(*this), routing(*this) {
-    wgk_options opt{0, 0, 1};
+Engine::Engine(int nc, int device, int restart) : ncell(nc), dailyWaterBalance(*this), routing(*this) {
+    if (device < 0) return;  // host-side initialisation only: no context, nothing can be stepped
+    wgk_options opt{restart, 0, 1};  // restart = additionalOutIn.additionalfilestatus (daily.cpp:165)
     check(wgk_create(&ctx, device, ncell, 1, 1, &opt), "wgk_create");
 }
-Engine::~Engine() { wgk_destroy(ctx); }
+Engine::~Engine() { if (ctx) wgk_destroy(ctx); }
 
 void Engine::check(int rc, const char *what) {
     if (rc != 0) throw std::runtime_error(std::string(what) + ": " + (ctx ? wgk_last_error(ctx) : "no CUDA device (wgk has no CPU fallback)"));
@@ -174,7 +187,7 @@ void dailyWaterBalanceClass::init(const std::string &input_dir, short) {  // rea
     G_SnowInElevation.initialize(ng);
 }
 
-void Engine::lai_init() {  // lai.cpp:40-148
+void Engine::lai_init(AdditionalOutputInputFile &additionalOutIn) {  // lai.cpp:40-148
     std::ifstream f(options.input_dir + "/LAI_22.DAT");
     if (!f) throw std::runtime_error("Can not open file " + options.input_dir + "/LAI_22.DAT for reading.");
     skip_comments(f);
@@ -191,6 +204,12 @@ void Engine::lai_init() {  // lai.cpp:40-148
         lai_factor_b[i] = (1 - decid[i]) * evergreen[i];
     }
     lai_days.initialize(ncell); lai_status.initialize(ncell); lai_precsum.initialize(ncell);
+    if (additionalOutIn.additionalfilestatus != 0)  // :53-65: growing-season state of the checkpoint (a cold start leaves the zeros)
+        for (int n = 0; n < ncell; n++) {
+            lai_days[n] = (int32_t)additionalOutIn.additionalOutputInput(n, 0);
+            lai_status[n] = (int32_t)additionalOutIn.additionalOutputInput(n, 1);
+            lai_precsum[n] = additionalOutIn.additionalOutputInput(n, 2);
+        }
 }
 
 void Engine::createMaxSoilWaterCapacityGrid() {  // s_max.cpp:40-75
@@ -268,7 +287,7 @@ void Engine::createGroundwaterGrids() {  // gw_frac.cpp:36-275
 // ------------------------------------------------------------------------------------------
 // routing class
 // ------------------------------------------------------------------------------------------
-void routingClass::init(short, const ConfigFile &) {  // routing.cpp:131-742 (canonical: antNatOpt 0, resOpt 1)
+void routingClass::init(short, const ConfigFile &, WghmStateFile &, AdditionalOutputInputFile &additionalOutIn) {  // routing.cpp:131-742 (canonical: antNatOpt 0, resOpt 1)
     const int ng = eng.ncell;
     const std::string in = eng.options.input_dir, rd = eng.options.routing_dir;
     for (auto *g : {&G_statCorrFact, &G_landAreaFrac, &G_landAreaFracNextTimestep, &G_landAreaFracPrevTimestep, &G_locLakeStorage,
@@ -279,7 +298,8 @@ void routingClass::init(short, const ConfigFile &) {  // routing.cpp:131-742 (ca
                     &G_reservoir_area, &G_reservoir_area_full, &G_stor_cap, &G_stor_cap_full, &G_mean_outflow, &G_mean_demand,
                     &G_riverLength, &G_RiverSlope, &G_Roughness, &G_bankfull_flow, &G_RiverWidth_bf, &G_RiverDepth_bf,
                     &G_riverBottomWidth, &G_riverStorageMax, &G_lakeDepthActive, &G_wetlDepthActive, &G_fswbInit, &G_fswbLandAreaFrac,
-                    &G_fswbLandAreaFracNextTimestep, &G_fGloLake, &G_riverAreaFracNextTimestep_Frac, &K_release, &G_riverDischarge})
+                    &G_fswbLandAreaFracNextTimestep, &G_fGloLake, &G_fLocLake, &G_fLocWet, &G_fGloWet, &G_riverAreaFracNextTimestep_Frac, &K_release,
+                    &G_riverDischarge})
         g->initialize(ng);
     statusStarted_landAreaFracNextTimestep.initialize(ng);
     statusStarted_landfreq.assign(ng, 0);
@@ -312,7 +332,7 @@ void routingClass::init(short, const ConfigFile &) {  // routing.cpp:131-742 (ca
     }
     for (int n = 0; n < ng; n++) {
         if (G_stor_cap_full[n] < 0.) G_stor_cap_full[n] = 0.;
-        K_release[n] = 0.1;
+        K_release[n] = (additionalOutIn.additionalfilestatus == 0) ? 0.1 : additionalOutIn.additionalOutputInput(n, 5);  // :388-392
         G_mean_outflow[n] = G_mean_outflow[n] * 12. * 1000000000. / 31536000.;
         G_mean_demand[n] = G_mean_demand[n] / 31536000.;
     }
@@ -337,12 +357,73 @@ void routingClass::initFractionStatus() {  // :745-765
     for (int n = 0; n < eng.ncell; n++) {
         statusStarted_landfreq[n] = 0;
         statusStarted_landAreaFracNextTimestep[n] = 0;
+        G_fLocLake[n] = G_loc_lake[n] / 100.;
+        G_fLocWet[n] = G_loc_wetland[n] / 100.;
         G_fGloLake[n] = G_glo_lake[n] / 100.;
-        G_fswbInit[n] = G_loc_lake[n] / 100. + G_loc_wetland[n] / 100. + G_glo_wetland[n] / 100.;
+        G_fGloWet[n] = G_glo_wetland[n] / 100.;
+        G_fswbInit[n] = G_fLocLake[n] + G_fLocWet[n] + G_fGloWet[n];
         G_fswbLandAreaFrac[n] = G_fswbInit[n];
         G_fswbLandAreaFracNextTimestep[n] = G_fswbLandAreaFrac[n];
     }
     statusStarted_updateGloResPrevYear = 0;
+}
+
+void routingClass::initFractionStatusAdditionalOI(AdditionalOutputInputFile &additionalOutIn) {  // :767-787
+    for (int n = 0; n < eng.ncell; n++) {
+        statusStarted_landfreq[n] = 0;
+        statusStarted_landAreaFracNextTimestep[n] = 0;
+        G_fLocLake[n] = additionalOutIn.additionalOutputInput(n, 45);
+        G_fLocWet[n] = additionalOutIn.additionalOutputInput(n, 47);
+        G_fGloLake[n] = G_glo_lake[n] / 100.;
+        G_fGloWet[n] = additionalOutIn.additionalOutputInput(n, 46);
+        G_fswbInit[n] = additionalOutIn.additionalOutputInput(n, 14);
+        G_fswbLandAreaFrac[n] = G_fswbInit[n];
+        G_fswbLandAreaFracNextTimestep[n] = G_fswbLandAreaFrac[n];
+    }
+    statusStarted_updateGloResPrevYear = 0;
+}
+
+// First day after a checkpoint (integrateWGHM.cpp:311-316): the reduction factors are re-derived from the restored storages, the
+// surface-water-body fractions from them, and the land area fraction of the checkpoint is corrected by the change of those
+// fractions against the checkpoint's G_fswbLandAreaFracNextTimestep (column 33).
+void routingClass::update_landarea_red_fac_PDAF(calibParamClass &calParam, AdditionalOutputInputFile &additionalOutIn) {
+    const double evapoReductionExp = 3.32193, evapoReductionExpReservoir = 2.81383;
+    auto clamp01 = [](double x) { return x < 0. ? 0. : (x > 1. ? 1. : x); };
+    for (int n = 0; n < eng.ncell; n++) {  // (the reference walks the cells in routing order; the statements are per cell)
+        const double ex = calParam.getValue(M_EVAREDEX, n) * evapoReductionExp;
+        const double cellArea = eng.geo.areaOfCellByArrayPos(n);
+        if (G_loc_lake[n] > 0.) {
+            const double maxStorage = ((G_loc_lake[n]) / 100.) * cellArea * G_lakeDepthActive[n];
+            G_locLakeAreaReductionFactor[n] = clamp01(1. - pow(fabs(G_locLakeStorage[n] - maxStorage) / (2. * maxStorage), ex));
+        }
+        if (G_loc_wetland[n] > 0.) {
+            const double maxStorage = ((G_loc_wetland[n]) / 100.) * cellArea * G_wetlDepthActive[n];
+            G_locWetlAreaReductionFactor[n] = clamp01(1. - pow(fabs(G_locWetlStorage[n] - maxStorage) / (maxStorage), ex));
+        }
+        if (G_glo_wetland[n] > 0.) {
+            const double maxStorage = ((G_glo_wetland[n]) / 100.) * cellArea * G_wetlDepthActive[n];
+            G_gloWetlAreaReductionFactor[n] = clamp01(1. - pow(fabs(G_gloWetlStorage[n] - maxStorage) / maxStorage, ex));
+        }
+        if (G_lake_area[n] > 0.) {
+            const double maxStorage = ((double)G_lake_area[n]) * G_lakeDepthActive[n];
+            G_gloLakeEvapoReductionFactor[n] = clamp01(1. - pow(fabs(G_gloLakeStorage[n] - maxStorage) / (2. * maxStorage), ex));
+        }
+        if (G_reservoir_area[n] > 0.) {
+            const double maxStorage = G_stor_cap[n];
+            G_gloResEvapoReductionFactor[n] = clamp01(1. - pow(fabs(G_gloResStorage[n] - maxStorage) / maxStorage, evapoReductionExpReservoir));
+        }
+        G_fLocLake[n] = ((G_loc_lake[n] > 0.) && (G_locLakeAreaReductionFactor[n] > 0.)) ? (G_locLakeAreaReductionFactor[n] * G_loc_lake[n] / 100.) : 0.;
+        G_fLocWet[n] = ((G_loc_wetland[n] > 0.) && (G_locWetlAreaReductionFactor[n] > 0.)) ? (G_locWetlAreaReductionFactor[n] * G_loc_wetland[n] / 100.) : 0.;
+        G_fGloWet[n] = ((G_glo_wetland[n] > 0.) && (G_gloWetlAreaReductionFactor[n] > 0.)) ? (G_gloWetlAreaReductionFactor[n] * G_glo_wetland[n] / 100.) : 0.;
+        G_fswbLandAreaFracNextTimestep[n] = G_fLocLake[n] + G_fLocWet[n] + G_fGloWet[n];
+        G_fswbLandAreaFrac[n] = additionalOutIn.additionalOutputInput(n, 33);
+        const double changePct = G_fswbLandAreaFracNextTimestep[n] * 100. - G_fswbLandAreaFrac[n] * 100.;
+        G_landAreaFrac[n] = additionalOutIn.additionalOutputInput(n, 6);
+        G_landAreaFrac[n] = G_landAreaFrac[n] - (changePct);
+        if (G_landAreaFrac[n] < 0.) G_landAreaFrac[n] = 0.;
+        G_landAreaFracPrevTimestep[n] = additionalOutIn.additionalOutputInput(n, 7);
+        statusStarted_landfreq[n] = 1;
+    }
 }
 
 void routingClass::setStoragesToZero() {  // :789-847 (riverveloOpt 1: rivers start empty)
@@ -377,7 +458,7 @@ void routingClass::setLakeWetlToMaximum(short) {  // :5647-5720 (resYearOpt 0)
     }
 }
 
-void routingClass::annualInit(short, int) {  // :979-1291 (resYearOpt 0: G_RES_<reference year>; no commissioning dynamics)
+void routingClass::annualInit(short year, int start_month, AdditionalOutputInputFile &additionalOutIn) {  // :979-1415 (resYearOpt 0: G_RES_<reference year>)
     const int ng = eng.ncell, ref = eng.options.resYearReference;
     for (int n = 0; n < ng; n++) { G_reservoir_area[n] = 0.; G_stor_cap[n] = 0.; }
     for (int n = 0; n < ng; n++)
@@ -400,28 +481,38 @@ void routingClass::annualInit(short, int) {  // :979-1291 (resYearOpt 0: G_RES_<
             statusStarted_landfreq[n] = 1;
         }
     }
+    // :1296-1415: a reservoir fraction that grew against the previous year takes land area and the water stored on it.  With
+    // resYearOpt 0 the fraction is the reference year's in every year, so the change is zero; the previous year's fraction of a
+    // checkpoint comes back from column 44.
+    for (int n = 0; n < ng; n++) {
+        if (additionalOutIn.additionalfilestatus == 1) G_glores_prevyear[n] = additionalOutIn.additionalOutputInput(n, 44);
+        if (start_month == 1 || year > eng.options.start_year)
+            if (G_glo_res[n] - G_glores_prevyear[n] > 0.)
+                throw std::runtime_error("routing.annualInit: a reservoir fraction grew against the previous year (cell " + std::to_string(n + 1) +
+                                         "): reservoir commissioning (resYearOpt 1, routing.cpp:1310-1412) is outside the implemented options");
+    }
 }
 
 void routingClass::routing(short, short day, short month, short dom, short, WghmStateFile &st, AdditionalOutputInputFile &, short, calibParamClass &) {
     eng.check(wgk_routing_day(eng.ctx, day, month, dom), "wgk_routing_day");
-    // wghmState of the day (routing.cpp:5002-5020): km3 -> mm over the continental area
-    pull();
-    for (int n = 0; n < eng.ncell; n++) {
-        const double f = ((eng.geo.areaOfCellByArrayPos(n) * (eng.geo.G_contfreq[n] / 100.)) / 1000000.);
+    // wghmState of the day (routing.cpp:5002-5020), packed on the device: one copy of [7][ncell] instead of 22 field downloads;
+    // the public grids are synchronised lazily (pull()) by whoever reads them
+    day_state.resize((size_t)7 * eng.ncell);
+    eng.check(wgk_get_day_state(eng.ctx, 0, day_state.data()), "wgk_get_day_state");
+    const size_t ng = (size_t)eng.ncell;
+    for (size_t n = 0; n < ng; n++) {
         Cell &c = st.cell(n);
-        c.locallake(dom - 1) = G_locLakeStorage[n] / f; c.localwetland(dom - 1) = G_locWetlStorage[n] / f;
-        c.globallake(dom - 1) = G_gloLakeStorage[n] / f; c.globalwetland(dom - 1) = G_gloWetlStorage[n] / f;
-        c.reservoir(dom - 1) = G_gloResStorage[n] / f; c.river(dom - 1) = G_riverStorage[n] / f;
-        c.groundwater(dom - 1) = G_groundwaterStorage[n] / f;
+        c.locallake(dom - 1) = day_state[0 * ng + n]; c.localwetland(dom - 1) = day_state[1 * ng + n];
+        c.globallake(dom - 1) = day_state[2 * ng + n]; c.globalwetland(dom - 1) = day_state[3 * ng + n];
+        c.reservoir(dom - 1) = day_state[4 * ng + n]; c.river(dom - 1) = day_state[5 * ng + n];
+        c.groundwater(dom - 1) = day_state[6 * ng + n];
     }
 }
 
-void routingClass::updateLandAreaFrac(AdditionalOutputInputFile &add) {
+void routingClass::updateLandAreaFrac(AdditionalOutputInputFile &) {
+    // fused into the routing post-pass on the device; columns 6 / 7 of the checkpoint (:5347-5350) are filled from the
+    // synchronised grids when a checkpoint is due (fill_additional)
     eng.check(wgk_update_land_area_frac(eng.ctx), "wgk_update_land_area_frac");
-    for (int n = 0; n < eng.ncell; n++) {  // :5347-5350
-        add.additionalOutputInput(n, 6) = G_landAreaFrac[n];
-        add.additionalOutputInput(n, 7) = G_landAreaFracPrevTimestep[n];
-    }
 }
 
 void routingClass::pull() {
@@ -543,21 +634,20 @@ void Engine::set_forcing_month(int month1, int year) {  // climate.cpp:93-123 (.
 // ------------------------------------------------------------------------------------------
 // integrate_wghm-shaped driver
 // ------------------------------------------------------------------------------------------
-long integrate_wghm(const std::string &config_file, int ncell, int device, double *seconds_day_loop) {
-    ConfigFile cfg(config_file);
-    Engine E(ncell, device);
+// initialize_wghm (initializeWGHM.cpp:32-72) + everything integrate_wghm_ does before its year loop (integrateWGHM.cpp:127-476),
+// on the host grids: a cold start, or a restart from the three checkpoint files of the config (PDAF monthly cycle)
+void load_start_state(const ConfigFile &cfg, int ncell, ModelState &S, calibParamClass &calParam) {  // initializeWGHM.cpp:32-72
+    if (!cfg.startvaluefile.empty()) S.wghmState.load(cfg.startvaluefile);
+    calParam.readJson(cfg.parameterfile, ncell);
+    if (!cfg.additionalfile.empty()) S.additionalOutIn.load(cfg.additionalfile);  // sets additionalfilestatus = 1
+    if (!cfg.snowInElevationfile.empty()) S.snow_in_elevation.load(cfg.snowInElevationfile);
+}
+
+void initialize_model(Engine &E, const ConfigFile &cfg, ModelStateRef S) {
+    const int ncell = E.ncell;
     E.options.init(cfg);
     E.options.require_canonical();
-    WghmStateFile wghmState(ncell, 1);
-    if (!cfg.startvaluefile.empty()) wghmState.load(cfg.startvaluefile);
-    E.calParam.readJson(cfg.parameterfile, ncell);
-    AdditionalOutputInputFile additionalOutIn(ncell);
-    SnowInElevationFile snow_in_elevation(ncell);
-    if (!cfg.additionalfile.empty() || !cfg.snowInElevationfile.empty())
-        throw std::runtime_error("restart from additionalOutIn / snowInElevation start values is not implemented yet");
-    const short number_of_days_in_month[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
-    const short last_day_in_month[12] = {30, 58, 89, 119, 150, 180, 211, 242, 272, 303, 333, 364};
-    short readinstatus = 1;
+    AdditionalOutputInputFile &additionalOutIn = S.additionalOutIn;
     // init sequence, integrateWGHM.cpp:127-286
     if (1 == E.options.rout_prepare) E.topo = prepare_routing_files(E.options.input_dir, E.options.routing_dir, 1, E.options.resOpt, ncell);
     E.geo.init(E.options.input_dir, ncell, E.options.resOpt);
@@ -566,14 +656,20 @@ long integrate_wghm(const std::string &config_file, int ncell, int device, doubl
     E.G_aindex.initialize(ncell);
     E.G_aindex.read(E.options.input_dir + "/G_ARID_HUMID.UNF2");
     E.dailyWaterBalance.G_Elevation.read(E.options.input_dir + "/G_ELEV_RANGE.101.UNF2");
-    E.lai_init();
-    E.routing.init(0, cfg);
+    E.lai_init(additionalOutIn);
+    E.routing.init(0, cfg, S.wghmState, additionalOutIn);
     E.routing.initLakeDepthActive(E.calParam);
     E.routing.initWetlDepthActive(E.calParam);
     // body of the single-pass calibration loop, :291-476
-    E.routing.initFractionStatus();
-    E.routing.setStoragesToZero();
+    if (additionalOutIn.additionalfilestatus == 0) E.routing.initFractionStatus();
+    if (additionalOutIn.additionalfilestatus == 1) E.routing.initFractionStatusAdditionalOI(additionalOutIn);
+    if (cfg.additionalfile.empty()) E.routing.setStoragesToZero();
+    else E.routing.setStorages(S.wghmState, additionalOutIn);
     if (cfg.startvaluefile.empty()) E.routing.setLakeWetlToMaximum(E.options.start_year);
+    if (additionalOutIn.additionalfilestatus == 1) {  // :311-316, first day after a checkpoint
+        E.routing.annualInit(E.options.start_year, cfg.startMonth, additionalOutIn);
+        E.routing.update_landarea_red_fac_PDAF(E.calParam, additionalOutIn);
+    }
     E.G_toBeCalculated.initialize(ncell);
     E.G_toBeCalculated.fill(1);
     for (int n = 0; n < ncell; n++) {
@@ -581,9 +677,61 @@ long integrate_wghm(const std::string &config_file, int ncell, int device, doubl
         E.dailyWaterBalance.G_cellCorrFact[n] = E.calParam.getValue(P_CFA, n);
         E.routing.G_statCorrFact[n] = E.calParam.getValue(P_CFS, n);
     }
-    E.dailyWaterBalance.setStoragesToZero();
+    if (cfg.additionalfile.empty()) E.dailyWaterBalance.setStoragesToZero();
+    else E.dailyWaterBalance.setStorages(S.wghmState, S.snow_in_elevation, additionalOutIn);
     E.createMaxSoilWaterCapacityGrid();
     E.createGroundwaterGrids();
+}
+
+// the columns of the additionalOutIn checkpoint that the hot path owns, as the reference leaves them after the last day of a
+// month (lai.cpp:168-173, daily.cpp:1258-1262, routing.cpp:3080, 5050-5071, 5165-5170, 5207-5241, 5347-5350); the water-use
+// columns keep what was loaded (zeros on a cold start)
+static void fill_additional(Engine &E, AdditionalOutputInputFile &add, short month) {
+    const int ncell = E.ncell;
+    routingClass &r = E.routing;
+    dailyWaterBalanceClass &d = E.dailyWaterBalance;
+    Grid<int32_t> ld, ls;
+    Grid<double> lp, fll, flw, fgw;
+    E.get("lai_days", ld); E.get("lai_status", ls); E.get("lai_precsum", lp);
+    E.get("f_loc_lake", fll); E.get("f_loc_wet", flw); E.get("f_glo_wet", fgw);
+    for (int n = 0; n < ncell; n++) {
+        auto col = [&](int j) -> double & { return add.additionalOutputInput(n, j); };
+        if (E.geo.G_contcell[n]) {  // the per-cell writes of lai / calcNewDay only happen for computed cells
+            col(0) = ld[n]; col(1) = ls[n]; col(2) = lp[n];
+            col(20) = d.G_soilWaterContent[n]; col(22) = d.G_canopyWaterContent[n]; col(24) = d.G_snow[n];
+        }
+        if (r.G_reservoir_area[n] > 0.) col(5) = r.K_release[n];
+        col(6) = r.G_landAreaFrac[n]; col(7) = r.G_landAreaFracPrevTimestep[n];
+        col(8) = r.G_locWetlAreaReductionFactor[n]; col(9) = r.G_gloLakeEvapoReductionFactor[n]; col(10) = r.G_groundwaterStorage[n];
+        col(11) = r.G_locLakeAreaReductionFactor[n]; col(12) = r.G_gloWetlAreaReductionFactor[n]; col(13) = r.G_gloResEvapoReductionFactor[n];
+        col(14) = r.G_fswbInit[n]; col(15) = r.G_gloWetlStorage[n]; col(17) = r.G_locWetlStorage[n]; col(18) = r.G_locLakeStorage[n];
+        col(19) = r.G_riverStorage[n]; col(21) = r.G_gloLakeStorage[n]; col(23) = r.G_gloResStorage[n];
+        col(33) = r.G_fswbLandAreaFracNextTimestep[n]; col(36) = r.G_fGloLake[n];
+        col(44) = (month == 11) ? r.G_glo_res[n] : r.G_glores_prevyear[n];
+        col(45) = fll[n]; col(47) = flw[n]; col(46) = fgw[n];
+    }
+}
+
+long integrate_wghm(const std::string &config_file, int ncell, int device, double *seconds_day_loop) {
+    ConfigFile cfg(config_file);
+    ModelState S(ncell);
+    calibParamClass cal;
+    load_start_state(cfg, ncell, S, cal);
+    Engine E(ncell, device, S.additionalOutIn.additionalfilestatus);
+    E.calParam = cal;
+    return run_model(E, cfg, S, seconds_day_loop);
+}
+
+// initialisation + the year / month / day loop of integrate_wghm_ (integrateWGHM.cpp:127-917) on the state objects of S
+long run_model(Engine &E, const ConfigFile &cfg, ModelStateRef S, double *seconds_day_loop) {
+    const int ncell = E.ncell;
+    initialize_model(E, cfg, S);
+    WghmStateFile &wghmState = S.wghmState;
+    AdditionalOutputInputFile &additionalOutIn = S.additionalOutIn;
+    SnowInElevationFile &snow_in_elevation = S.snow_in_elevation;
+    const short number_of_days_in_month[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    const short last_day_in_month[12] = {30, 58, 89, 119, 150, 180, 211, 242, 272, 303, 333, 364};
+    short readinstatus = 1;
     E.check(wgk_forcing_reserve(E.ctx, 31, 0), "wgk_forcing_reserve");
 
     long ndays = 0;
@@ -591,7 +739,7 @@ long integrate_wghm(const std::string &config_file, int ncell, int device, doubl
     bool pushed = false;
     for (short year = E.options.start_year; year <= E.options.end_year; year++) {
         E.dailyWaterBalance.annualInit();
-        E.routing.annualInit(year, cfg.startMonth);
+        E.routing.annualInit(year, cfg.startMonth, additionalOutIn);
         if (!pushed) { E.push_static(); E.push_state(); pushed = true; }  // (yearly reservoir changes do not occur with resYearOpt 0)
         short day = 0;
         if (year == cfg.startYear) for (int m = 1; m < cfg.startMonth; m++) day += number_of_days_in_month[m - 1];
@@ -604,6 +752,7 @@ long integrate_wghm(const std::string &config_file, int ncell, int device, doubl
         for (short month = start_month - 1; month < end_month; month++) {
             E.set_forcing_month(month + 1, year);
             wghmState.resetCells(number_of_days_in_month[month]);
+            E.check(wgk_month_begin(E.ctx), "wgk_month_begin");  // the post-pass keeps what the month's checkpoint needs
             const auto t0 = std::chrono::steady_clock::now();
             for (short dom = 1; dom <= number_of_days_in_month[month]; dom++) {
                 day++;
@@ -620,6 +769,7 @@ long integrate_wghm(const std::string &config_file, int ncell, int device, doubl
             secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             // month-end rescale, integrateWGHM.cpp:830-847
             E.dailyWaterBalance.pull();
+            E.routing.pull();
             for (int n = 0; n < ncell; n++) {
                 const double laf = E.routing.getLandAreaFrac(n), cf = E.geo.G_contfreq[n];
                 for (short e = 0; e <= 100; e++)
@@ -630,22 +780,11 @@ long integrate_wghm(const std::string &config_file, int ncell, int device, doubl
                     wghmState.cell(n).soil(dom - 1) = E.dailyWaterBalance.G_soilWaterContent[n] * laf / cf;
                 }
             }
+            fill_additional(E, additionalOutIn, month);
             if (year == E.options.end_year && month + 1 == end_month) {  // :853-901
                 if (!cfg.outputmeanfile.empty()) wghmState.saveMean(cfg.outputmeanfile);
                 if (!cfg.outputlastdayfile.empty()) wghmState.saveDay(cfg.outputlastdayfile, number_of_days_in_month[month] - 1);
-                if (!cfg.outputadditionalfile.empty()) {
-                    // columns the hot path owns (additionalOutputInputFile.cpp:19-71)
-                    Grid<int32_t> ld, ls; Grid<double> lp;
-                    E.get("lai_days", ld); E.get("lai_status", ls); E.get("lai_precsum", lp);
-                    for (int n = 0; n < ncell; n++) {
-                        additionalOutIn.additionalOutputInput(n, 0) = ld[n]; additionalOutIn.additionalOutputInput(n, 1) = ls[n];
-                        additionalOutIn.additionalOutputInput(n, 2) = lp[n]; additionalOutIn.additionalOutputInput(n, 5) = E.routing.K_release[n];
-                        additionalOutIn.additionalOutputInput(n, 10) = E.routing.G_groundwaterStorage[n];
-                        additionalOutIn.additionalOutputInput(n, 14) = E.routing.G_fswbInit[n];
-                        additionalOutIn.additionalOutputInput(n, 33) = E.routing.G_fswbLandAreaFracNextTimestep[n];
-                    }
-                    additionalOutIn.save(cfg.outputadditionalfile);
-                }
+                if (!cfg.outputadditionalfile.empty()) additionalOutIn.save(cfg.outputadditionalfile);
                 if (!cfg.outputsnowlastdayfile.empty()) snow_in_elevation.save(cfg.outputsnowlastdayfile);
             }
         }
@@ -654,7 +793,106 @@ long integrate_wghm(const std::string &config_file, int ncell, int device, doubl
     return ndays;
 }
 
+// host grids after initialize_model (+ the first annualInit of the year loop) as a record dump; no context is created
+static void dump_put(FILE *f, const char *name, const char *dtype, int64_t count, const void *data, size_t elsize) {
+    char nm[32] = {0}, dt[8] = {0};
+    strncpy(nm, name, 31);
+    strncpy(dt, dtype, 7);
+    const int32_t d = 0;
+    fwrite(nm, 1, 32, f); fwrite(&d, 4, 1, f); fwrite(dt, 1, 8, f); fwrite(&count, 8, 1, f); fwrite(data, elsize, (size_t)count, f);
+}
+void init_dump(const std::string &config_file, int ncell, const std::string &dump_file) {
+    ConfigFile cfg(config_file);
+    Engine E(ncell, -1);
+    ModelState S(ncell);
+    load_start_state(cfg, ncell, S, E.calParam);
+    initialize_model(E, cfg, S);
+    E.dailyWaterBalance.annualInit();
+    E.routing.annualInit(E.options.start_year, cfg.startMonth, S.additionalOutIn);
+    FILE *f = fopen(dump_file.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot write " + dump_file);
+    auto f64 = [&](const char *name, Grid<double> &g) { dump_put(f, name, "f64", ncell, g.data(), 8); };
+    routingClass &r = E.routing;
+    dailyWaterBalanceClass &d = E.dailyWaterBalance;
+    f64("canopy", d.G_canopyWaterContent); f64("soil", d.G_soilWaterContent); f64("snow", d.G_snow);
+    dump_put(f, "snow_bands", "f64", (int64_t)ncell * 101, d.G_SnowInElevation.data(), 8);
+    dump_put(f, "lai_days", "i32", ncell, E.lai_days.data(), 4); dump_put(f, "lai_status", "i32", ncell, E.lai_status.data(), 4);
+    f64("lai_precsum", E.lai_precsum);
+    f64("gw", r.G_groundwaterStorage); f64("loc_lake_stor", r.G_locLakeStorage); f64("loc_wetl_stor", r.G_locWetlStorage);
+    f64("glo_lake_stor", r.G_gloLakeStorage); f64("glo_wetl_stor", r.G_gloWetlStorage); f64("res_stor", r.G_gloResStorage);
+    f64("river_stor", r.G_riverStorage); f64("red_loc_lake", r.G_locLakeAreaReductionFactor); f64("red_loc_wetl", r.G_locWetlAreaReductionFactor);
+    f64("red_glo_lake", r.G_gloLakeEvapoReductionFactor); f64("red_glo_wetl", r.G_gloWetlAreaReductionFactor); f64("red_res", r.G_gloResEvapoReductionFactor);
+    f64("red_river", r.G_riverAreaReductionFactor); f64("k_release", r.K_release); f64("land_area_frac", r.G_landAreaFrac);
+    f64("land_area_frac_prev", r.G_landAreaFracPrevTimestep); f64("land_area_frac_next", r.G_landAreaFracNextTimestep);
+    f64("fswb_laf", r.G_fswbLandAreaFrac); f64("fswb_laf_next", r.G_fswbLandAreaFracNextTimestep); f64("fswb_init", r.G_fswbInit);
+    f64("river_area_frac_next", r.G_riverAreaFracNextTimestep_Frac); f64("f_glo_lake", r.G_fGloLake);
+    dump_put(f, "status_laf_next", "i16", ncell, r.statusStarted_landAreaFracNextTimestep.data(), 2);
+    f64("reservoir_area", r.G_reservoir_area); f64("stor_cap", r.G_stor_cap); f64("lake_area", r.G_lake_area);
+    dump_put(f, "smax", "f32", ncell, E.G_Smax.data(), 4); dump_put(f, "gwfactor", "f32", ncell, E.G_gwFactor.data(), 4);
+    fclose(f);
+}
+
 }  // namespace wg
+
+// ------------------------------------------------------------------------------------------
+// B1: the Fortran / C entry points of the reference with their signatures and ownership rules (initializeWGHM.h:11-15,
+// integrateWGHM.h:9-13).  The callee news the objects into the caller's pointer references; integrate_wghm_ deletes them at the
+// configured end date in "OL" mode (integrateWGHM.cpp:1139-1160); errors leave as C++ exceptions, as in the reference.
+// The cell count is a run-time value here: it is the ng_param header of the parameter file.  The GPU is $WGK_DEVICE (default 0).
+// ------------------------------------------------------------------------------------------
+extern "C" {
+void initialize_wghm_(const char *s, wg::WghmStateFile *&initstate, wg::calibParamClass *&initcal, wg::AdditionalOutputInputFile *&initaddio,
+                      wg::SnowInElevationFile *&initsnow, long *year, long *month, const char *s2, const char *s3, wg::WghmStateFile *&wghmMean) {
+    using namespace wg;
+    const std::string progName(s2 ? s2 : "OL"), pathMean(s3 ? s3 : "");
+    ConfigFile cfg(s, (int)*year, (int)*month, progName);
+    initcal = new calibParamClass;
+    if (!cfg.parameterfile.empty()) initcal->readJson(cfg.parameterfile, 0);
+    const int ncell = initcal->ncell();
+    if (ncell <= 0) throw std::runtime_error("initialize_wghm_: the parameter file (param_json) must give the number of cells (ng_param)");
+    initstate = new WghmStateFile(ncell, 1);
+    if (!cfg.startvaluefile.empty()) initstate->load(cfg.startvaluefile);
+    wghmMean = new WghmStateFile(ncell, 1);
+    if (!pathMean.empty()) wghmMean->load(pathMean);
+    initaddio = new AdditionalOutputInputFile(ncell);
+    if (!cfg.additionalfile.empty()) initaddio->load(cfg.additionalfile);  // additionalfilestatus = 1
+    initsnow = new SnowInElevationFile(ncell);
+    if (!cfg.snowInElevationfile.empty()) initsnow->load(cfg.snowInElevationfile);
+}
+
+void integrate_wghm_(const char *s, wg::ConfigFile *&configFile, wg::WghmStateFile *&wghmState, wg::calibParamClass *&calParam,
+                     wg::AdditionalOutputInputFile *&additionalOutIn, wg::SnowInElevationFile *&snow_in_elevation, long *step, long *total_steps,
+                     long *year, long *month, const char *s2) {
+    using namespace wg;
+    (void)step; (void)total_steps;
+    const std::string progName(s2 ? s2 : "OL");
+    configFile = new ConfigFile(s, (int)*year, (int)*month, progName);
+    const int ncell = calParam->ncell();
+    const char *dev = getenv("WGK_DEVICE");
+    {
+        Engine E(ncell, dev ? atoi(dev) : 0, additionalOutIn->additionalfilestatus);
+        E.calParam = *calParam;
+        ModelStateRef S{*wghmState, *additionalOutIn, *snow_in_elevation};
+        run_model(E, *configFile, S, nullptr);
+    }
+    if (progName == "OL") {  // the run is over: the reference frees what initialize_wghm_ allocated
+        delete wghmState; wghmState = nullptr;
+        delete calParam; calParam = nullptr;
+        delete additionalOutIn; additionalOutIn = nullptr;
+        delete snow_in_elevation; snow_in_elevation = nullptr;
+        delete configFile; configFile = nullptr;
+    }
+}
+// C++ aliases of the reference (initializeWGHM.h:19, integrateWGHM.h:17)
+}
+void initialize_wghm(const char *s, wg::WghmStateFile *&a, wg::calibParamClass *&b, wg::AdditionalOutputInputFile *&c, wg::SnowInElevationFile *&d,
+                     long *year, long *month, const char *s2, const char *s3, wg::WghmStateFile *&m) {
+    initialize_wghm_(s, a, b, c, d, year, month, s2, s3, m);
+}
+void integrate_wghm(const char *s, wg::ConfigFile *&cf, wg::WghmStateFile *&a, wg::calibParamClass *&b, wg::AdditionalOutputInputFile *&c,
+                    wg::SnowInElevationFile *&d, long *step, long *total_steps, long *year, long *month, const char *s2) {
+    integrate_wghm_(s, cf, a, b, c, d, step, total_steps, year, month, s2);
+}
 
 extern "C" {
 long wg_host_integrate(const char *config_file, int ncell, int device, double *seconds_day_loop, char *err, size_t errlen) {
@@ -673,6 +911,41 @@ int wg_host_state_roundtrip(const char *kind, const char *in, const char *out, i
         else if (k == "snow") { wg::SnowInElevationFile f(ncell); f.load(in); f.save(out); }
         else if (k == "additional") { wg::AdditionalOutputInputFile f(ncell); f.load(in); f.save(out); }
         else throw std::runtime_error("unknown kind " + k);
+        return 0;
+    } catch (std::exception &e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}
+// a ready-to-step context from a reference-format configuration: initialize_wghm + the init sequence of integrate_wghm_ + the
+// first annualInit on the host, statics / parameters / start state pushed to the device, 31 forcing slots reserved.  The caller
+// owns the returned wgk_ctx (wgk_destroy); the benchmark and smoke() build their model this way, through the product's own
+// host layer (topology builder included) instead of test infrastructure.
+void *wg_host_create_context(const char *config_file, int ncell, int device, char *err, size_t errlen) {
+    try {
+        wg::ConfigFile cfg(config_file);
+        wg::ModelState S(ncell);
+        wg::calibParamClass cal;
+        wg::load_start_state(cfg, ncell, S, cal);
+        wg::Engine E(ncell, device, S.additionalOutIn.additionalfilestatus);
+        E.calParam = cal;
+        wg::initialize_model(E, cfg, S);
+        E.dailyWaterBalance.annualInit();
+        E.routing.annualInit(E.options.start_year, cfg.startMonth, S.additionalOutIn);
+        E.push_static();
+        E.push_state();
+        E.check(wgk_forcing_reserve(E.ctx, 31, 0), "wgk_forcing_reserve");
+        wgk_ctx *ctx = E.ctx;
+        E.ctx = nullptr;  // ownership moves to the caller
+        return ctx;
+    } catch (std::exception &e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        return nullptr;
+    }
+}
+int wg_host_init_dump(const char *config_file, int ncell, const char *dump_file, char *err, size_t errlen) {
+    try {
+        wg::init_dump(config_file, ncell, dump_file);
         return 0;
     } catch (std::exception &e) {
         if (err && errlen) snprintf(err, errlen, "%s", e.what());

@@ -48,6 +48,7 @@ class calibParamClass {
 
 struct ConfigFile {  // configFile.cpp:20-231
     explicit ConfigFile(const std::string &file);
+    ConfigFile(const std::string &file, int year, int month, const std::string &progName);  // configFile.cpp: "OL" keeps the file's dates
     std::string startvaluefile, parameterfile, snowInElevationfile, additionalfile, outputmeanfile, outputlastdayfile,
         outputsnowlastdayfile, outputadditionalfile, runtimeoptionsfile, outputoptionsfile, routingoptionsfile, stationsfile,
         inputDir, outputDir, climateDir, routingDir;
@@ -105,13 +106,15 @@ class routingClass {
   public:
     explicit routingClass(Engine &e) : eng(e) {}
     const double minStorVol = 1.e-15;
-    void init(short nBasins, const ConfigFile &cfg);                          // routing.cpp:131-742
-    void annualInit(short year, int start_month);                            // :979-1495
+    void init(short nBasins, const ConfigFile &cfg, WghmStateFile &, AdditionalOutputInputFile &);  // routing.cpp:131-742 (K_release :388-392)
+    void annualInit(short year, int start_month, AdditionalOutputInputFile &);  // :979-1495
     void initLakeDepthActive(const calibParamClass &);                        // :5613-5619
     void initWetlDepthActive(const calibParamClass &);                        // :5621-5628
     void setStoragesToZero();                                                 // :789-847
     void setStorages(WghmStateFile &, AdditionalOutputInputFile &);           // :851-882
     void initFractionStatus();                                                // :745-765
+    void initFractionStatusAdditionalOI(AdditionalOutputInputFile &);         // :767-787 (restart: fractions from the checkpoint)
+    void update_landarea_red_fac_PDAF(calibParamClass &, AdditionalOutputInputFile &);  // :5354-5475 (restart: first day after a checkpoint)
     void setLakeWetlToMaximum(short start_year);                              // :5647-5720
     void routing(short year, short day, short month, short day_in_month, short last_day_in_month, WghmStateFile &,
                  AdditionalOutputInputFile &, short readinstatus, calibParamClass &);  // :1629
@@ -128,7 +131,8 @@ class routingClass {
         G_loc_res, G_glo_wetland, G_loc_wetland, G_reg_lake, G_glo_res, G_glores_prevyear, G_lake_area, G_reservoir_area,
         G_reservoir_area_full, G_stor_cap, G_stor_cap_full, G_mean_outflow, G_mean_demand, G_riverLength, G_RiverSlope,
         G_Roughness, G_bankfull_flow, G_RiverWidth_bf, G_RiverDepth_bf, G_riverBottomWidth, G_riverStorageMax,
-        G_lakeDepthActive, G_wetlDepthActive, G_fswbInit, G_fswbLandAreaFrac, G_fswbLandAreaFracNextTimestep, G_fGloLake,
+        G_lakeDepthActive, G_wetlDepthActive, G_fswbInit, G_fswbLandAreaFrac, G_fswbLandAreaFracNextTimestep, G_fGloLake, G_fLocLake,
+        G_fLocWet, G_fGloWet,
         G_riverAreaFracNextTimestep_Frac, K_release, G_riverDischarge;
     Grid<int16_t> statusStarted_landAreaFracNextTimestep;
     Grid<int8_t> G_res_type, G_start_month, G_reg_lake_status, G_LDD;
@@ -138,12 +142,13 @@ class routingClass {
 
   private:
     Engine &eng;
+    std::vector<double> day_state;  // [7][ncell] of the last routed day
 };
 
 // Everything the reference keeps in process globals (globals.cpp:7-33), per model instance.
 class Engine {
   public:
-    Engine(int ncell, int device = 0);
+    Engine(int ncell, int device = 0, int restart = 0);  // device < 0: host-side initialisation only (no context; tests of the init logic)
     ~Engine();
     int ncell;
     wgk_ctx *ctx = nullptr;
@@ -164,7 +169,7 @@ class Engine {
     Grid<double> lai_precsum;
     // init-time derivations
     void land_init();                  // land.cpp:21-33
-    void lai_init();                   // lai.cpp:40-148
+    void lai_init(AdditionalOutputInputFile &);  // lai.cpp:40-148 (restart: growing-season state from the checkpoint, :53-65)
     void createMaxSoilWaterCapacityGrid();  // s_max.cpp:40-75
     void createGroundwaterGrids();     // gw_frac.cpp:36-275
     // device synchronisation
@@ -179,8 +184,46 @@ class Engine {
 // integrate_wghm_-shaped driver (integrateWGHM.cpp:38-1168, open-loop "OL" mode, canonical
 // options): config.txt in, txt state files out.  Returns simulated days.
 long integrate_wghm(const std::string &config_file, int ncell, int device, double *seconds_day_loop);
+void init_dump(const std::string &config_file, int ncell, const std::string &dump_file);
+
+// the three state objects of a run (what initialize_wghm_ allocates and integrate_wghm_ works on)
+struct ModelState {
+    explicit ModelState(int ncell) : wghmState(ncell, 1), additionalOutIn(ncell), snow_in_elevation(ncell) {}
+    WghmStateFile wghmState;
+    AdditionalOutputInputFile additionalOutIn;
+    SnowInElevationFile snow_in_elevation;
+};
+struct ModelStateRef {
+    WghmStateFile &wghmState;
+    AdditionalOutputInputFile &additionalOutIn;
+    SnowInElevationFile &snow_in_elevation;
+    ModelStateRef(WghmStateFile &a, AdditionalOutputInputFile &b, SnowInElevationFile &c) : wghmState(a), additionalOutIn(b), snow_in_elevation(c) {}
+    ModelStateRef(ModelState &s) : wghmState(s.wghmState), additionalOutIn(s.additionalOutIn), snow_in_elevation(s.snow_in_elevation) {}
+};
+// initialize_wghm (initializeWGHM.cpp:32-72): start values and parameters from the files named in the config
+void load_start_state(const ConfigFile &cfg, int ncell, ModelState &S, calibParamClass &calParam);
+// everything integrate_wghm_ does before its year loop (integrateWGHM.cpp:127-476), on the host grids of E: cold start or restart
+// from checkpoint objects (PDAF monthly cycle); E.calParam must be set
+void initialize_model(Engine &E, const ConfigFile &cfg, ModelStateRef S);
+// initialisation + the year / month / day loop; returns the simulated days
+long run_model(Engine &E, const ConfigFile &cfg, ModelStateRef S, double *seconds_day_loop);
 
 }  // namespace wg
+
+// B1, the reference's own FFI (initializeWGHM.h:11-15, integrateWGHM.h:9-13): same names, argument order, by-reference pointers and
+// ownership, so that the Fortran (PDAF) side links unchanged
+extern "C" {
+void initialize_wghm_(const char *s, wg::WghmStateFile *&initstate, wg::calibParamClass *&initcal, wg::AdditionalOutputInputFile *&initaddio,
+                      wg::SnowInElevationFile *&initsnow, long *year, long *month, const char *s2, const char *s3, wg::WghmStateFile *&wghmMean);
+void integrate_wghm_(const char *s, wg::ConfigFile *&configFile, wg::WghmStateFile *&wghmState, wg::calibParamClass *&calParam,
+                     wg::AdditionalOutputInputFile *&additionalOutIn, wg::SnowInElevationFile *&snow_in_elevation, long *step, long *total_steps,
+                     long *year, long *month, const char *s2);
+}
+void initialize_wghm(const char *s, wg::WghmStateFile *&initstate, wg::calibParamClass *&initcal, wg::AdditionalOutputInputFile *&initaddio,
+                     wg::SnowInElevationFile *&initsnow, long *year, long *month, const char *s2, const char *s3, wg::WghmStateFile *&wghmMean);
+void integrate_wghm(const char *s, wg::ConfigFile *&configFile, wg::WghmStateFile *&wghmState, wg::calibParamClass *&calParam,
+                    wg::AdditionalOutputInputFile *&additionalOutIn, wg::SnowInElevationFile *&snow_in_elevation, long *step, long *total_steps,
+                    long *year, long *month, const char *s2);
 
 extern "C" {
 // C entry used by tests / other languages: runs the drop-in driver on a reference-format config
@@ -188,4 +231,9 @@ long wg_host_integrate(const char *config_file, int ncell, int device, double *s
 int wg_host_state_roundtrip(const char *kind, const char *in, const char *out, int ncell, char *err, size_t errlen);
 // flow topology from the reference-format input directory into the routing directory
 int wg_host_prepare_routing_files(const char *input_dir, const char *routing_dir, int resOpt, int ncell, int *nlevels, char *err, size_t errlen);
+// host-side initialisation only (no GPU needed): the start state integrate_wghm would push to the device, written as a record dump
+// (name[32], day i32 = 0, dtype[8], count i64, data) with the record names of the test fixtures
+// ready-to-step context built by the host layer from a reference-format configuration (the caller owns it: wgk_destroy)
+void *wg_host_create_context(const char *config_file, int ncell, int device, char *err, size_t errlen);
+int wg_host_init_dump(const char *config_file, int ncell, const char *dump_file, char *err, size_t errlen);
 }

@@ -77,6 +77,7 @@ struct wgk_ctx {
     // class inside each dependency level
     std::vector<int32_t> rank_of_cell, cell_of_rank, level_off, level_of_rank;
     std::vector<uint8_t> cell_class;
+    int32_t *d_rank_of_cell = nullptr;
     int32_t *d_cell_of_rank = nullptr, *d_up_off = nullptr, *d_up_idx = nullptr, *d_down = nullptr, *d_level_off = nullptr;
     int32_t *d_member_pset = nullptr;
     std::vector<int32_t> member_pset;
@@ -283,12 +284,24 @@ void *cells_pre_fn(const wgk_ctx *c) {
 void *vertical_fn(const wgk_ctx *c) {
     return c->form == 1 ? (void *)wgk::k_vertical<wgk::VCfgSmall> : c->form == 2 ? (void *)wgk::k_vertical<wgk::VCfgMid> : (void *)WGK_K(c, k_vertical_tpc);
 }
-dim3 cells_pre_block(const wgk_ctx *c) { return dim3(c->form == 1 ? wgk::VCfgSmall::THREADS : c->form == 2 ? wgk::VCfgMid::THREADS : wgk::VBLOCK); }
 // grid of a cell-parallel kernel of `block` threads over `ncells` device positions (wgk::map_thread)
 dim3 cell_grid(const wgk_ctx *c, int ncells, int block) {
+#if WGK_MM_UNIFORM_CELL
+    if (c->mm) return dim3(ncells, (c->mpad + std::min(block, c->mpad) - 1) / std::min(block, c->mpad));
+#else
     if (c->mm) return dim3((unsigned)(((long long)ncells * c->mpad + block - 1) / block), 1);
+#endif
     return dim3((ncells + block - 1) / block, c->nmember);
 }
+// threads per CTA of a cell-parallel kernel whose cell-minor form uses `block`
+dim3 cell_block(const wgk_ctx *c, int block) {
+#if WGK_MM_UNIFORM_CELL
+    if (c->mm) return dim3(std::min(block, c->mpad));
+#endif
+    (void)c;
+    return dim3(block);
+}
+dim3 cells_pre_block(const wgk_ctx *c) { return c->form == 1 ? dim3(wgk::VCfgSmall::THREADS) : c->form == 2 ? dim3(wgk::VCfgMid::THREADS) : cell_block(c, wgk::VBLOCK); }
 dim3 cells_pre_grid(const wgk_ctx *c, int begin, int end) {
     return c->form ? dim3(wgk::v_num_tiles(begin, end), c->nmember) : cell_grid(c, end - begin, wgk::VBLOCK);
 }
@@ -309,7 +322,7 @@ int enqueue_vertical(wgk_ctx *c, const WgkParams &p, int d) {
 }
 int enqueue_routing(wgk_ctx *c, const WgkParams &p, int d) {
     int n = 0;
-    const dim3 block(128), grid = cell_grid(c, c->ncell, 128);
+    const dim3 block = cell_block(c, 128), grid = cell_grid(c, c->ncell, 128);
     WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p);
     n++;
     for (int l = 0; l < c->tail_level0; l++) {
@@ -331,7 +344,7 @@ int enqueue_routing(wgk_ctx *c, const WgkParams &p, int d) {
 // stream satisfies every dependency (used when use_graph == 0)
 int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
     int n = 0;
-    dim3 block(128);
+    const dim3 block = cell_block(c, 128);
     for (int d = 0; d < ndays; d++) {
         for (int l = 0; l < c->tail_level0; l++) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
@@ -418,7 +431,7 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
             // (fusing R(d, l) with V(d + 1, l) into one task - one kernel boundary per day on the own-cell
             //  recurrence instead of two - was measured SLOWER: 27.4 vs 24.6 ms per simulated year, with 32 or 64 buffers)
             void *a2[] = {&pp, &dd, &ll};
-            CU(add((void *)WGK_K(c, k_river_level), grid, dim3(128), a2, {pre, last, first_sweep ? reuse : nullptr}, &node));
+            CU(add((void *)WGK_K(c, k_river_level), grid, cell_block(c, 128), a2, {pre, last, first_sweep ? reuse : nullptr}, &node));
             first_sweep = false;
             prevW[l] = node;
             last = node;
@@ -501,7 +514,7 @@ int launch_owner(wgk_ctx *c, const WgkParams &p, int ndays) {
 // parameter upload (never inside a graph capture)
 int ensure_derived(wgk_ctx *c) {
     if (c->member_dirty) {
-        const dim3 block(128), grid = cell_grid(c, c->ncell, 128);
+        const dim3 block = cell_block(c, 128), grid = cell_grid(c, c->ncell, 128);
         WGK_K(c, k_derive_member)<<<grid, block, 0, c->stream>>>(make_params(c));
         c->launches++;
         c->member_dirty = false;
@@ -588,23 +601,26 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
         const char *e = getenv("WGK_DAY_SCHEDULE");  // "owner" | "wavefront" | "wholeday"
         if (e && !strcmp(e, "wavefront")) c->whole_day = false;
         else if (e && !strcmp(e, "wholeday")) c->whole_day = true;
-        else c->whole_day = (nmember >= 32 && (long long)nmember * ncell >= 2000000);
+        else c->whole_day = (nmember >= 32 && (long long)nmember * ncell >= 6400000);
         // "owner": one launch per call, a thread owns its cell for all days (k_days_owner); needs every cell-member
         // co-resident (<= 75 776 on B200).  Opt-in: measured slower than the wavefront (93 vs 67 us per day, see the kernel).
         c->owner_mode = (e && !strcmp(e, "owner")) ? 1 : 0;
     }
-    {   // Layout.  Many members in the throughput regime: member-minor, a warp = 32 members of one cell (lane = member), so that the
-        // lanes share the cell's statics, land cover, water-body class and nearly the same weather (cell-minor warps run 20 of 32
-        // lanes per instruction and are issue-bound, profiles/r1_k_vertical_tpc_m16.md).  It comes with the thread-per-cell kernels,
-        // the whole-day schedule and one launch per routing level (no persistent narrow-level CTA).  Results are bit-identical
-        // between the layouts (tests/test_gpu_round2.py::test_member_minor_layout_is_bit_identical).
+    {   // Layout.  From 32 members on: member-minor, a warp = 32 members of one cell (lane = member), so that the lanes share the
+        // cell's statics, land cover, water-body class and nearly the same weather (cell-minor warps run 20 of 32 lanes per
+        // instruction and are issue-bound, profiles/r1_k_vertical_tpc_m16.md; member-minor: 32 of 32, 34 % fewer warp
+        // instructions, profiles/r2_k_vertical_tpc_m64_*.md).  It comes with the thread-per-cell kernels and one launch per
+        // routing level (no persistent narrow-level CTA).  Results are bit-identical between the layouts
+        // (tests/test_gpu_round2.py::test_member_minor_layout_is_bit_identical).
+        // Measured on B200, 0.5 degree grid, 10^9 cell-days/s (members: member-minor + wavefront / member-minor + whole-day /
+        // cell-minor + whole-day / cell-minor + wavefront): 32: 1.66 / 1.47 / 1.43 / 1.42, 64: 1.96 / 1.89 / 1.69 / 1.46,
+        // 128: 2.05 / 2.13 / 1.87 / 1.49, 256: - / 2.29 / 1.93 / - : hence the whole-day schedule from ~6.4 M cell-members.
         const char *e = getenv("WGK_LAYOUT");  // "members" | "cells"
         if (e && !strcmp(e, "members")) c->mm = true;
         else if (e && !strcmp(e, "cells")) c->mm = false;
-        else c->mm = c->whole_day && c->form == 0 && c->owner_mode == 0 && nmember >= 32;
+        else c->mm = c->form == 0 && c->owner_mode == 0 && nmember >= 32;
         if (c->mm) {
             c->form = 0;
-            c->whole_day = true;
             c->owner_mode = 0;
         }
         c->mpad = c->mm ? (nmember + 31) / 32 * 32 : nmember;
@@ -659,6 +675,7 @@ void wgk_destroy(wgk_ctx *c) {
     if (c->ev_forcing) cudaEventDestroy(c->ev_forcing);
     drop_graph(c);
     for (void *d : c->allocs) cudaFree(d);
+    cudaFree(c->d_rank_of_cell);
     cudaFree(c->d_cell_of_rank); cudaFree(c->d_up_off); cudaFree(c->d_up_idx); cudaFree(c->d_down);
     cudaFree(c->d_level_off); cudaFree(c->d_member_pset); cudaFree(c->d_cal); cudaFree(c->d_forcing);
     cudaFree(c->d_gidx); cudaFree(c->d_gbody); cudaFree(c->d_cal_days); cudaFree(c->d_qbuf);
@@ -793,6 +810,7 @@ int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downs
         return cudaMemcpy(dptr, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice);
     };
     CU(upload(c->d_cell_of_rank, c->cell_of_rank));
+    CU(upload(c->d_rank_of_cell, c->rank_of_cell));
     CU(upload(c->d_up_off, up_off));
     CU(upload(c->d_up_idx, up_idx));
     CU(upload(c->d_down, down));
@@ -1313,6 +1331,21 @@ int wgk_enkf_update(wgk_ctx *c, int member, const int32_t *cells, int ncells, co
     return WGK_OK;
 }
 
+int wgk_get_day_state(wgk_ctx *c, int member, double *out) {
+    if (!c || !out || member < 0 || member >= c->nmember) return WGK_ERR_ARG;
+    if (!c->have_topology) return fail(c, WGK_ERR_STATE, "no topology");
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = sizeof(double) * 7 * (size_t)c->ncell;
+    int rc = ensure_dstage(c, bytes);
+    if (rc) return rc;
+    WGK_K(c, k_pack_day_state)<<<(c->ncell + 127) / 128, 128, 0, c->stream>>>(make_params(c), member, c->d_rank_of_cell, (double *)c->d_stage);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return WGK_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // ensemble statistics (the only exchange between ranks, once per assimilation cycle)
 // ---------------------------------------------------------------------------------------
@@ -1507,7 +1540,7 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     cudaEvent_t ev[6];
     for (auto &e : ev) CU(cudaEventCreate(&e));
     const WgkParams p = make_params(c);
-    const dim3 block(128), grid = cell_grid(c, c->ncell, 128);
+    const dim3 block = cell_block(c, 128), grid = cell_grid(c, c->ncell, 128);
     CU(cudaEventRecord(ev[0], c->stream));
     launch_vertical(c, p, 0);
     CU(cudaEventRecord(ev[1], c->stream));
@@ -1592,7 +1625,7 @@ int wgk_profile_schedule(wgk_ctx *c, int day, int month, int dom, int slot, floa
         cudaEventRecord(r.b, c->stream);
         recs.push_back(r);
     };
-    const dim3 block(128);
+    const dim3 block = cell_block(c, 128);
     if (c->whole_day) {
         const dim3 grid = cell_grid(c, c->ncell, 128);
         timed(0, [&] { launch_vertical(c, p, 0); });

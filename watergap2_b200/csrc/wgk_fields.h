@@ -135,6 +135,11 @@
     /* ---- monthly sums of the seven routing compartments in mm over the continental area (the daily values the \
        reference writes to WghmStateFile, routing.cpp:5002-5020), band-major [7][cell]; only while enabled ---- */ \
     X(mon_acc, double, "f64", MEMBER, 7) \
+    /* ---- surface-water-body fractions as formed BEFORE the river-area correction (G_fLocLake / G_fLocWet / G_fGloWet at \
+       routing.cpp:5044-5070: columns 45, 47, 46 of the additionalOutIn checkpoint); written only while the monthly accumulation is on ---- */ \
+    X(f_loc_lake, double, "f64", MEMBER, 1) \
+    X(f_loc_wet, double, "f64", MEMBER, 1) \
+    X(f_glo_wet, double, "f64", MEMBER, 1) \
     /* ---- derived from the member state (k_derive_member), maintained by the vertical kernel ---- */ \
     X(s_snowfree, int8_t, "i8", MEMBER, 1) \
     /* ---- land cover tables (LCT_22.DAT / LAI_22.DAT; daily.h:204-208, lai.h) ---- */ \

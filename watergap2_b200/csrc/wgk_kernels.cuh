@@ -38,6 +38,10 @@
 #endif
 #include "wgk_fields.h"
 
+#ifndef WGK_MM_UNIFORM_CELL
+#define WGK_MM_UNIFORM_CELL 1  // member-minor thread mapping: one cell per CTA (see map_thread); measured on B200 against the linear mapping,
+                               // with 5 resident CTAs per SM: 1024 sets 2.65 vs 2.55, 256 members 2.29 vs 2.17 x 10^9 cell-days/s
+#endif
 #ifndef WGK_MM
 #define WGK_MM 0  // 0: kernels of the cell-minor layout in namespace wgk, 1: of the member-minor layout in namespace wgk_mm
 #endif
@@ -126,10 +130,18 @@ constexpr ConstDiv C100{100., 0.01}, C1E6{1000000., 1e-6}, C1000{1000., 0.001}, 
 // never straddles two cells, mpad is a multiple of 32); lanes beyond the last member idle.
 __device__ __forceinline__ bool map_thread(const WgkParams &p, const int begin, const int end, int &r, int &m) {
     if (MM) {
+#if WGK_MM_UNIFORM_CELL
+        // one cell per CTA (blockIdx.x), the CTA's threads = min(128, mpad) consecutive members, blockIdx.y = member block: the cell
+        // index is uniform over the CTA, so the compiler keeps the cell's statics in uniform registers
+        r = begin + blockIdx.x;
+        m = blockIdx.y * blockDim.x + threadIdx.x;
+        return m < p.nmember;
+#else
         const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
         r = begin + (int)(t / p.mpad);
         m = (int)(t % p.mpad);
         return r < end && m < p.nmember;
+#endif
     }
     r = begin + blockIdx.x * blockDim.x + threadIdx.x;
     m = blockIdx.y;
@@ -152,6 +164,15 @@ constexpr int SNOW_CH = WGK_SNOW_CH, SNOW_NCH = 100 / WGK_SNOW_CH, VBLOCK = WGK_
 #ifndef WGK_TPC_MINB
 #define WGK_TPC_MINB 4  // resident CTAs per SM the thread-per-cell kernels are compiled for (register cap 65536 / (128 * MINB));
                         // 5 and 6 spill and measured 9 % / 14 % slower at one member on B200
+#endif
+#ifndef WGK_TPC_MINB_MM
+#define WGK_TPC_MINB_MM 5  // member-minor instantiation: with the cell index uniform over the CTA the kernel fits 96 registers without spills
+#endif
+#undef WGK_TPC_MINB_EFF
+#if WGK_MM
+#define WGK_TPC_MINB_EFF WGK_TPC_MINB_MM
+#else
+#define WGK_TPC_MINB_EFF WGK_TPC_MINB
 #endif
 struct SnowStage {
     double s[2][SNOW_CH][VBLOCK];
@@ -1967,6 +1988,11 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
     double fLocLake = ((loc_lake > 0.) && (red_loc_lake > 0.)) ? (red_loc_lake * loc_lake / C100) : 0.;
     double fLocWet = ((loc_wetland > 0.) && (red_loc_wetl > 0.)) ? (red_loc_wetl * loc_wetland / C100) : 0.;
     double fGloWet = ((glo_wetland > 0.) && (red_glo_wetl > 0.)) ? (red_glo_wetl * glo_wetland / C100) : 0.;
+    if (p.month_acc) {  // the uncorrected fractions, as the checkpoint keeps them (routing.cpp:5050-5071)
+        a.f_loc_lake[i] = fLocLake;
+        a.f_loc_wet[i] = fLocWet;
+        a.f_glo_wet[i] = fGloWet;
+    }
     const double fswb_old = in.fswb_old;
     double fswb_next = fLocLake + fLocWet + fGloWet;
     const double fGloLake = in.f_glo_lake;
@@ -2253,7 +2279,7 @@ __global__ void __launch_bounds__(C::THREADS, C::NW == 5 ? 6 : 12) k_vertical(co
 
 #endif  // !WGK_MM
 // thread-per-cell forms of k_vertical and k_cells_pre
-__global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_vertical_tpc(const __grid_constant__ WgkParams p, const int dayofs) {
+__global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB_EFF) k_vertical_tpc(const __grid_constant__ WgkParams p, const int dayofs) {
     __shared__ SnowStage stage;
     int r, m;
     if (!map_thread(p, 0, p.ncell, r, m)) return;
@@ -2261,7 +2287,16 @@ __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_vertical_tpc(const __g
 }
 
 
-__global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB) k_cells_pre_tpc(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
+#ifndef WGK_PRE_MINB_MM
+#define WGK_PRE_MINB_MM WGK_TPC_MINB_MM  // vertical + local routing in one kernel needs more registers: tuning knob of its member-minor form
+#endif
+#undef WGK_PRE_MINB_EFF
+#if WGK_MM
+#define WGK_PRE_MINB_EFF WGK_PRE_MINB_MM
+#else
+#define WGK_PRE_MINB_EFF WGK_TPC_MINB
+#endif
+__global__ void __launch_bounds__(VBLOCK, WGK_PRE_MINB_EFF) k_cells_pre_tpc(const __grid_constant__ WgkParams p, const int dayofs, const int begin, const int end) {
     __shared__ SnowStage stage;
     int r, m;
     if (!map_thread(p, begin, end, r, m)) return;
@@ -2570,6 +2605,22 @@ __global__ void __launch_bounds__(128) k_state_vector(const __grid_constant__ Wg
     double v[10];
     state_of_cell(p, pos[j], m, kind, ndays, v);
     for (int k = 0; k < 10; k++) out[(size_t)j * 10 + k] = v[k] - (mean_field ? mean_field[(size_t)j * 10 + k] : 0.);
+}
+
+// the day's WghmStateFile entry of the seven routing compartments (routing.cpp:5002-5020: km3 -> mm over the continental area) of
+// every cell, in REFERENCE cell order, out[k][n], k = local lake, local wetland, global lake, global wetland, reservoir, river,
+// groundwater: one packed device-to-host copy per simulated day for the class shim routingClass::routing
+__global__ void __launch_bounds__(128) k_pack_day_state(const __grid_constant__ WgkParams p, const int m, const int32_t *__restrict__ rank_of_cell,
+                                                        double *__restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.ncell) return;
+    const WgkArrays &a = p.a;
+    const int x = rank_of_cell[n];
+    const size_t i = mi(p, m, x);
+    const double denom = ((a.area[x] * (a.contfreq[x] / C100)) / C1E6);
+    const double stor[7] = {a.loc_lake_stor[i], a.loc_wetl_stor[i], a.glo_lake_stor[i], a.glo_wetl_stor[i], a.res_stor[i], a.river_stor[i], a.gw[i]};
+#pragma unroll
+    for (int k = 0; k < 7; k++) out[(size_t)k * p.ncell + n] = stor[k] / denom;
 }
 
 // Ensemble moments of the state vector over the members of this context (what an assimilation
