@@ -218,6 +218,11 @@ static void dump_state(int day, bool with_snow) {
         put_f64("wu_daily_nus", day, routing.G_dailydailyNUs);
         put_f64("wu_daily_nug", day, routing.G_dailydailyNUg);
         put_f64("wu_actual_use", day, routing.G_actualUse);
+        put_f64("wu_uns_irr", day, routing.G_unsatisfiedNAsFromIrrig);
+        put_f64("wu_uns_oth", day, routing.G_unsatisfiedNAsFromOtherSectors);
+        put_f64("wu_red_rf", day, routing.G_reducedReturnFlow);
+        put_f64("wu_wusi", day, routing.G_withdrawalIrrigFromSwb);
+        put_f64("wu_cusi", day, routing.G_consumptiveUseIrrigFromSwb);
     }
 }
 

@@ -71,3 +71,17 @@ def update_net_abstraction_gw(rem, wusi, cusi, frgi, uns_irr, uns_oth, red_rf, n
             out[n] = nug[n] - change
             rem[n] = 0.
     return out, rem, uns_irr, uns_oth, red_rf
+
+
+def month_inputs(files, params, month):
+    """the water-use inputs of one month for the oracle / the kernels, km3 per day: dict of wu_nus_month, wu_nug_month (net
+    abstractions times M_NETABSSW / M_NETABSGW, dailyNUInit), wu_wusi_month, wu_cusi_month (irrigation withdrawal / consumptive
+    use from surface water, routing.cpp:3907-3908: no multiplier).  `files` maps the input file names (G_NETUSE_SW_m3_..,
+    G_NETUSE_GW_m3_.., G_IRRIG_WITHDRAWAL_USE_SW_m3_.., G_IRRIG_CONS_USE_SW_m3_..) to their float32 [ng][12] contents."""
+    par = np.asarray(params, np.float64).reshape(26, -1)
+    one = np.ones(par.shape[1])
+    key = lambda stem: next(v for k, v in files.items() if stem in k)
+    return {"wu_nus_month": daily_net_abstraction(key("G_NETUSE_SW_m3"), par[23], month),
+            "wu_nug_month": daily_net_abstraction(key("G_NETUSE_GW_m3"), par[24], month),
+            "wu_wusi_month": daily_net_abstraction(key("G_IRRIG_WITHDRAWAL_USE_SW_m3"), one, month),
+            "wu_cusi_month": daily_net_abstraction(key("G_IRRIG_CONS_USE_SW_m3"), one, month)}

@@ -38,6 +38,7 @@ def derive(w, params=None, resYearReference=2000):
     cd, slope_f, length_f = wgo.river_geometry(w.altitude, w.meander, topo["outflow_cell"], topo["ldd"], w.row, w.col)
     alloc, start_month = wgo.reservoir_prepare(w.resarea, w.mean_outflow, w.mean_outflow12, topo["outflow_cell"])
     out["_topology"] = topo
+    out["wu_alloc_coeff"] = np.asarray(alloc, f64).reshape(ng, 5)  # G_ALLOC_COEFF.5.UNF0 read into a Grid<double> (routing.cpp:361)
 
     # ---- geo.cpp -------------------------------------------------------------------------
     area = w.area_row.astype(f64)[w.row.astype(int) - 1]

@@ -19,6 +19,7 @@
 struct wgo_ctx {
     int ncell;
     int restart; /* additionalOutIn.additionalfilestatus */
+    int subtract_use; /* options.subtract_use */
 #define X(name, ctype, dt, per) ctype *name;
     WGO_FIELDS(X)
 #undef X
@@ -46,6 +47,7 @@ void wgo_destroy(wgo_ctx *c) {
 
 int wgo_ncell(const wgo_ctx *c) { return c->ncell; }
 void wgo_set_restart(wgo_ctx *c, int restart) { c->restart = restart; }
+void wgo_set_subtract_use(wgo_ctx *c, int subtract_use) { c->subtract_use = subtract_use; }
 
 void *wgo_field(wgo_ctx *c, const char *name, const char **dtype, int64_t *count) {
 #define X(fname, ctype, dt, per) \
@@ -509,9 +511,77 @@ static double gw_step(double *Sg, double netGWin, double k) {
     return q;
 }
 
+/* routingClass::updateNetAbstractionGW, routing.cpp:5503-5572: the day's net abstraction from groundwater, adapted to the
+ * surface-water use that stayed unsatisfied the day before (return flows reduced) or was satisfied late (reintroduced) */
+static double update_net_abstraction_gw(wgo_ctx *c, int n) {
+    double NAgnew, returnflowChange, eff, frgi, factor, WUsiNew, dailyRemainingUseFromIrrig, reintroducedRatio;
+    if (c->wu_daily_remaining[n] > 1.e-12) {
+        if (c->wu_wusi[n] > 0.) {
+            eff = c->wu_cusi[n] / c->wu_wusi[n];
+            frgi = c->wu_frgi[n];
+            factor = 1 - (1 - frgi) * (1 - eff);
+            WUsiNew = 1 / factor * (c->wu_wusi[n] * factor - c->wu_daily_remaining[n]);
+            if (WUsiNew < 0.) {
+                WUsiNew = 0.;
+                c->wu_uns_irr[n] += c->wu_wusi[n] * factor;
+                c->wu_uns_oth[n] += c->wu_daily_remaining[n] - (c->wu_wusi[n] * factor);
+            } else {
+                c->wu_uns_irr[n] += c->wu_daily_remaining[n];
+            }
+            returnflowChange = (frgi * (1 - eff) * (WUsiNew - c->wu_wusi[n]));
+            c->wu_red_rf[n] += returnflowChange;
+            NAgnew = c->wu_daily_nug[n] - returnflowChange;
+            c->wu_daily_remaining[n] = 0.;
+            return NAgnew;
+        } else {
+            c->wu_uns_oth[n] += c->wu_daily_remaining[n];
+            return c->wu_daily_nug[n];
+        }
+    } else if (c->wu_daily_remaining[n] < -1.e-12) {
+        dailyRemainingUseFromIrrig = c->wu_daily_remaining[n] + c->wu_uns_oth[n];
+        if (dailyRemainingUseFromIrrig < 0.) {
+            c->wu_uns_oth[n] = 0.;
+        } else {
+            c->wu_uns_oth[n] += c->wu_daily_remaining[n];
+            c->wu_daily_remaining[n] = 0.;
+            return c->wu_daily_nug[n];
+        }
+        if (c->wu_uns_irr[n] == 0.) {
+            c->wu_daily_remaining[n] = 0.;
+            return c->wu_daily_nug[n];
+        }
+        reintroducedRatio = (dailyRemainingUseFromIrrig / c->wu_uns_irr[n]);
+        if (reintroducedRatio < -1.) {
+            reintroducedRatio = -1.;
+            dailyRemainingUseFromIrrig = c->wu_uns_irr[n] * -1.;
+        }
+        returnflowChange = (reintroducedRatio * c->wu_red_rf[n]);
+        c->wu_uns_irr[n] += dailyRemainingUseFromIrrig;
+        c->wu_red_rf[n] += returnflowChange;
+        NAgnew = c->wu_daily_nug[n] - returnflowChange;
+        c->wu_daily_remaining[n] = 0.;
+        return NAgnew;
+    }
+    return c->wu_daily_nug[n];
+}
+/* the adaptation in front of each of the four groundwater balances (routing.cpp:1929-1935, 1991-1996, 2076-2081, 2132-2137, 3325-3330) */
+static double net_gw_use(wgo_ctx *c, int n) {
+    if (c->subtract_use <= 0) return 0.;
+    if (c->wu_daily_remaining[n] != 0.) c->wu_daily_nug[n] = update_net_abstraction_gw(c, n);
+    return c->wu_daily_nug[n];
+}
+
 void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
     (void)day_in_month;
     const int ng = c->ncell;
+    const int wu = c->subtract_use > 0;
+    static const int numberOfDaysInMonthWU[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    (void)numberOfDaysInMonthWU;
+    if (wu) /* routingClass::calcNextDay_M, routing.cpp:7432-7440 (integrateWGHM.cpp:794-796) */
+        for (int n = 0; n < ng; n++) {
+            c->wu_daily_nus[n] = c->wu_nus_month[n];
+            c->wu_daily_nug[n] = c->wu_nug_month[n];
+        }
     const short first_day_in_month[12] = {1, 32, 60, 91, 121, 152, 182, 213, 244, 274, 305, 335}; /* routing.cpp:1634 */
     const double lakeOutflowExp = 1.5, wetlOutflowExp = 2.5, evapoReductionExp = 3.32193,
                  evapoReductionExpReservoir = 2.81383; /* :124-129 */
@@ -557,6 +627,7 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
         /* humid, not an inland sink (:1979-2033) */
         if ((0 == c->arid[n]) && (ldd >= 0)) {
             netGWin = (double)c->gw_recharge[n] * cellArea * ((double)c->land_area_frac[n] / 100.) / 1000000.;
+            if (wu) netGWin -= net_gw_use(c, n);
             groundwater_runoff_km3 = gw_step(&c->gw[n], netGWin, kG);
             localGWRunoffIntoRiver = (1. - fswb_catchment) * groundwater_runoff_km3;
             localGWRunoff = fswb_catchment * groundwater_runoff_km3;
@@ -565,6 +636,7 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
         /* inland sinks (:2123-2176) */
         if (ldd < 0) {
             netGWin = c->gw_recharge[n] * cellArea * (c->land_area_frac[n] / 100.) / 1000000.;
+            if (wu) netGWin -= net_gw_use(c, n);
             groundwater_runoff_km3 = gw_step(&c->gw[n], netGWin, kG);
             if (c->land_area_frac[n] == 0.)
                 dailyLocalSurfaceRunoff = c->storage_transfer[n] * cellArea / 1000000. * c->land_area_frac_prev[n] / 100.;
@@ -574,9 +646,14 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
             localRunoff = dailyLocalSurfaceRunoff + localGWRunoff;
         }
 
+        /* :2193-2296 with use_alloc 0, delayedUseSatisfaction 0, aggrNUsGloLakResOpt 0: the day's desired use is the net
+         * abstraction from surface water (negative = return flow) */
+        double remainingUse = 0., dailyActualUse = 0., remainingUseGloLake = 0., remainingUseRes = 0.;
+        if (wu && 1 == c->toBeCalculated[n]) remainingUse = c->wu_daily_nus[n];
+
         double transportedVolume = 0., inflowUpstream = 0.;
         if (0 != c->toBeCalculated[n]) { /* :2308 */
-            double inflow = localRunoff, outflow = 0., maxStorage, totalInflow, PETgwr, PETgwrMax;
+            double inflow = localRunoff, outflow = 0., maxStorage, totalInflow, PETgwr, PETgwrMax, locLakeMaxStorage = 0.;
             const double kS = PAR(c, WGO_P_SWOUTF_C, n);
             const double contf = c->contfreq[n];
 
@@ -584,6 +661,7 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
             if (c->loc_lake[n] > 0.) {
                 const double prev = c->loc_lake_stor[n];
                 maxStorage = ((c->loc_lake[n]) / 100.) * cellArea * c->lake_depth_active[n];
+                locLakeMaxStorage = maxStorage; /* G_locLakeMaxStorage, :2321 */
                 const double r = c->red_loc_lake[n];
                 double evapo = ((1.0 - cfa) * owPrec * r) + (cfa * (owPET * r));
                 if (evapo < 0.) evapo = 0.;
@@ -672,7 +750,9 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
                 totalInflow = inflow + (owPrec * ((double)c->lake_area[n] / 1000000.));
                 if (aridc) gwr_glolak = Kswbgw * r * ((double)c->lake_area[n] / (cellArea * (contf / 100.)));
                 else gwr_glolak = 0.;
-                const double remainingUseGloLake = 0.; /* subtract_use == 0 */
+                if (c->reservoir_area[n] > 0.) remainingUseGloLake = 0.5 * remainingUse; /* :2681-2686 */
+                else remainingUseGloLake = remainingUse;
+                const double remainingUseGloLakeStart = remainingUseGloLake;
                 double PETgwrRemUse = evapo * ((double)c->lake_area[n] / 1000000.)
                                       + gwr_glolak * cellArea * (contf / 100.) / 1000000. + remainingUseGloLake;
                 double PETgwrRemUseMax = totalInflow + maxStorage + prev;
@@ -681,6 +761,8 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
                     outflow = 0.;
                     evapo *= PETgwrRemUseMax / PETgwrRemUse;
                     gwr_glolak *= PETgwrRemUseMax / PETgwrRemUse;
+                    if (remainingUseGloLake > 0.) remainingUseGloLake -= remainingUseGloLake * PETgwrRemUseMax / PETgwrRemUse; /* :2710-2716 */
+                    else remainingUseGloLake = 0.;
                 } else {
                     c->glo_lake_stor[n] = prev * exp(-1. * kS) + (1. / kS) * (totalInflow - PETgwrRemUse) * (1. - exp(-1. * kS));
                     outflow = totalInflow + prev - c->glo_lake_stor[n] - PETgwrRemUse;
@@ -692,9 +774,11 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
                         outflow = 0.;
                         c->glo_lake_stor[n] = prev + totalInflow - PETgwrRemUse;
                     }
+                    remainingUseGloLake = 0.; /* :2752 */
                 }
                 if (fabs(c->glo_lake_stor[n]) <= MIN_STOR_VOL) c->glo_lake_stor[n] = 0.;
                 inflow = outflow;
+                dailyActualUse = remainingUseGloLakeStart - remainingUseGloLake; /* :2788 */
                 c->red_glo_lake[n] = 1. - pow(fabs(c->glo_lake_stor[n] - maxStorage) / (2. * maxStorage),
                                               (M_EVAREDEX * evapoReductionExp));
                 if (c->red_glo_lake[n] < 0.) c->red_glo_lake[n] = 0.;
@@ -713,6 +797,9 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
                 totalInflow = inflow + (owPrec * ((double)c->reservoir_area[n] / 1000000.));
                 if (aridc) gwr_res = Kswbgw * r * ((double)c->reservoir_area[n] / (cellArea * (contf / 100.)));
                 else gwr_res = 0.;
+                if (c->lake_area[n] > 0.) remainingUseRes = 0.5 * remainingUse + remainingUseGloLake; /* :2869-2875 */
+                else remainingUseRes = remainingUse;
+                const double remainingUseResStart = remainingUseRes;
                 PETgwr = evapo * ((double)c->reservoir_area[n] / 1000000.) + gwr_res * cellArea * (contf / 100.) / 1000000.;
                 PETgwrMax = prev + totalInflow;
                 if (PETgwr > PETgwrMax) {
@@ -721,6 +808,22 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
                     evapo *= PETgwrMax / PETgwr;
                 } else {
                     c->res_stor[n] = prev + totalInflow - PETgwr;
+                }
+                if (wu) { /* :2922-2946 */
+                    if (remainingUseRes < 0.) {
+                        c->res_stor[n] -= remainingUseRes;
+                        remainingUseRes = 0.;
+                    } else {
+                        if (c->res_stor[n] > (0.1 * c->stor_cap[n])) {
+                            if (remainingUseRes < (c->res_stor[n] - (c->stor_cap[n] * 0.1))) {
+                                c->res_stor[n] -= remainingUseRes;
+                                remainingUseRes = 0.;
+                            } else {
+                                remainingUseRes -= (c->res_stor[n] - (c->stor_cap[n] * 0.1));
+                                c->res_stor[n] = c->stor_cap[n] * 0.1;
+                            }
+                        }
+                    }
                 }
                 if (fabs(c->res_stor[n]) <= MIN_STOR_VOL) c->res_stor[n] = 0.;
                 if (month == c->start_month[n] - 1) { /* :2945-2956 */
@@ -732,6 +835,16 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
                 if ((c->res_type[n] + 0) == 1) { /* irrigation; without water use dailyUse == 0 (:2960-2977) */
                     dailyUse = 0.0;
                     static const int numberOfDaysInMonth[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+                    if (wu) { /* :2961-2973: own use plus the share of up to 5 downstream cells without a reservoir (note the
+                                 reference's un-decremented index into G_reservoir_area) */
+                        dailyUse = c->wu_daily_nus[n];
+                        short i = 0;
+                        int downstreamCell = c->downstream_cell[n];
+                        while (i < 5 && downstreamCell > 0 && downstreamCell < ng && c->reservoir_area[downstreamCell] <= 0) {
+                            dailyUse += c->wu_daily_nus[downstreamCell - 1] * c->wu_alloc_coeff[(size_t)n * 5 + i++];
+                            downstreamCell = c->downstream_cell[downstreamCell - 1];
+                        }
+                    }
                     monthlyUse = dailyUse * numberOfDaysInMonth[month];
                     monthlyUse = monthlyUse * 1000000000. / (numberOfDaysInMonth[month] * 86400.);
                     if (c->mean_demand[n] >= 0.5 * c->mean_outflow[n])
@@ -759,9 +872,16 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
                     c->res_stor[n] = 0.;
                 }
                 inflow = outflow;
+                dailyActualUse += remainingUseResStart - remainingUseRes; /* :3068 */
                 c->red_res[n] = 1. - pow(fabs(c->res_stor[n] - maxStorage) / maxStorage, evapoReductionExpReservoir);
                 if (c->red_res[n] < 0.) c->red_res[n] = 0.;
                 if (c->red_res[n] > 1.) c->red_res[n] = 1.;
+            }
+
+            /* :3166-3172 (aggrNUsGloLakResOpt 0) */
+            if (wu && (c->reservoir_area[n] > 0. || c->lake_area[n] > 0.)) {
+                if (c->reservoir_area[n] > 0.) remainingUse = remainingUseRes;
+                else if (c->lake_area[n] > 0.) remainingUse = remainingUseGloLake;
             }
 
             /* global wetland, :3178-3297 */
@@ -803,6 +923,7 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
                 c->gwr_swb[n] = gwr_loclak + gwr_glolak + gwr_locwet + gwr_glowet + gwr_res;
                 netGWin = c->gwr_swb[n] * cellArea * (contf / 100.) / 1000000.
                           + (double)c->gw_recharge[n] * cellArea * ((double)c->land_area_frac[n] / 100.) / 1000000.;
+                if (wu) netGWin -= net_gw_use(c, n);
                 groundwater_runoff_km3 = gw_step(&c->gw[n], netGWin, kG);
                 localGWRunoffIntoRiver = groundwater_runoff_km3;
             }
@@ -821,19 +942,22 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
             c->river_evapo[n] = ((1.0 - cfa) * (owPrec) + (cfa * owPET)) * c->river_area_frac[n] / 100. * cellArea / 1000000.;
             double riverPrecip = owPrec * c->river_area_frac[n] / 100. * cellArea / 1000000.;
             c->river_inflow[n] += riverPrecip;
-            const double remainingUse = 0.;
             double RiverEvapoRemUse = remainingUse + c->river_evapo[n];
+            const double remainingUseRiverStart = remainingUse;
             double RivEvapoRemUseMax = c->river_inflow[n] + (K * prevR * exp(-1. * K)) / (1. - exp(-1. * K));
             if (RiverEvapoRemUse > RivEvapoRemUseMax) {
                 c->river_stor[n] = 0.;
                 transportedVolume = c->river_inflow[n] + prevR - RivEvapoRemUseMax;
                 if (transportedVolume < 0.) transportedVolume = 0.;
+                if (remainingUse > 0.) remainingUse -= remainingUse * RivEvapoRemUseMax / RiverEvapoRemUse; /* :3489-3492 */
+                else remainingUse = 0.;
                 c->river_evapo[n] *= RivEvapoRemUseMax / RiverEvapoRemUse;
             } else {
                 c->river_stor[n] = prevR * exp(-1. * K) + (1. / K) * (c->river_inflow[n] - RiverEvapoRemUse) * (1. - exp(-1. * K));
                 if (fabs(c->river_stor[n]) <= MIN_STOR_VOL) c->river_stor[n] = 0.;
                 transportedVolume = c->river_inflow[n] + prevR - c->river_stor[n] - RiverEvapoRemUse;
                 if (transportedVolume < 0.) transportedVolume = 0.;
+                remainingUse = 0.; /* :3512 */
             }
             /* river width / area fraction of the next day, :3546-3586 */
             {
@@ -848,6 +972,31 @@ void wgo_routing_day(wgo_ctx *c, int day, int month, int day_in_month) {
                 if (c->red_river[n] > 1.) c->red_river[n] = 1.;
                 c->river_area_frac_next[n] = c->red_river[n] * c->river_length[n] * width * 100. / cellArea;
                 c->river_area_frac_change[n] = c->river_area_frac_next[n] - c->river_area_frac[n];
+            }
+            if (wu) {
+                /* what the river could not supply is taken from the local lake, :3590-3624 */
+                if ((c->loc_lake[n] > 0.) && (remainingUse > 0.)) {
+                    if (c->loc_lake_stor[n] > (-1.) * locLakeMaxStorage) {
+                        if (remainingUse < (locLakeMaxStorage + c->loc_lake_stor[n])) {
+                            c->loc_lake_stor[n] -= remainingUse;
+                            remainingUse = 0.;
+                        } else {
+                            remainingUse -= (locLakeMaxStorage + c->loc_lake_stor[n]);
+                            c->loc_lake_stor[n] = (-1.) * locLakeMaxStorage;
+                        }
+                    }
+                    c->red_loc_lake[n] = 1. - pow(fabs(c->loc_lake_stor[n] - locLakeMaxStorage) / (2. * locLakeMaxStorage),
+                                                  (M_EVAREDEX * evapoReductionExp));
+                    if (c->red_loc_lake[n] < 0.) c->red_loc_lake[n] = 0.;
+                    if (c->red_loc_lake[n] > 1.) c->red_loc_lake[n] = 1.;
+                }
+                dailyActualUse += remainingUseRiverStart - remainingUse; /* :3625 */
+                c->wu_actual_use[n] += dailyActualUse;                   /* :3736 */
+                /* use_alloc 0, delayedUseSatisfaction 0, :3889-3900 */
+                c->wu_total_unsatisfied[n] += remainingUse;
+                c->wu_daily_remaining[n] = remainingUse;
+                c->wu_wusi[n] = c->wu_wusi_month[n]; /* :3907-3908 */
+                c->wu_cusi[n] = c->wu_cusi_month[n];
             }
             /* :3923-3928 */
             if (ldd < 0) c->cell_runoff[n] = 0. - inflowUpstream;

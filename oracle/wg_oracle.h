@@ -74,7 +74,15 @@ enum {
     X(river_evapo, double, "f64", 1) X(gwr_swb, double, "f64", 1) X(cell_runoff, double, "f64", 1) \
     X(river_inflow, double, "f64", 1) X(river_area_frac, double, "f64", 1) \
     X(river_area_frac_change, double, "f64", 1) X(thresh_elev, int32_t, "i32", 1) \
-    X(wghm_routing_mm, double, "f64", 7)
+    X(wghm_routing_mm, double, "f64", 7) \
+    /* ---- water use (subtract_use 2, use_alloc 0, delayedUseSatisfaction 0, aggrNUsGloLakResOpt 0) ---- \
+       inputs of the current MONTH in km3/day (dailyNUInit routing.cpp:884-977 + calcNextDay_M :7432-7440; the irrigation \
+       withdrawal / consumptive use from surface water :3907-3908), statics, and the per-cell state */ \
+    X(wu_nus_month, double, "f64", 1) X(wu_nug_month, double, "f64", 1) X(wu_wusi_month, double, "f64", 1) \
+    X(wu_cusi_month, double, "f64", 1) X(wu_frgi, double, "f64", 1) X(wu_alloc_coeff, double, "f64", 5) \
+    X(wu_daily_nus, double, "f64", 1) X(wu_daily_nug, double, "f64", 1) X(wu_total_unsatisfied, double, "f64", 1) \
+    X(wu_daily_remaining, double, "f64", 1) X(wu_uns_irr, double, "f64", 1) X(wu_uns_oth, double, "f64", 1) \
+    X(wu_red_rf, double, "f64", 1) X(wu_wusi, double, "f64", 1) X(wu_cusi, double, "f64", 1) X(wu_actual_use, double, "f64", 1)
 
 typedef struct wgo_ctx wgo_ctx;
 
@@ -85,6 +93,8 @@ int wgo_ncell(const wgo_ctx *c);
 void *wgo_field(wgo_ctx *c, const char *name, const char **dtype, int64_t *count);
 /* additionalOutIn.additionalfilestatus (daily.cpp:165): 1 = restart from a checkpoint */
 void wgo_set_restart(wgo_ctx *c, int restart);
+/* options.subtract_use: 0 no water use (canonical), 2 net abstractions from surface water and groundwater */
+void wgo_set_subtract_use(wgo_ctx *c, int subtract_use);
 
 /* one simulated day; day 1..365, month 0..11, day_in_month 1..31 (integrateWGHM.cpp:755-798) */
 void wgo_vertical_day(wgo_ctx *c, int day, int month, int day_in_month);

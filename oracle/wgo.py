@@ -36,6 +36,7 @@ def _bind(_lib):
         _lib.wgo_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p),
                                    ctypes.POINTER(ctypes.c_int64)]
         _lib.wgo_set_restart.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        _lib.wgo_set_subtract_use.argtypes = [ctypes.c_void_p, ctypes.c_int]
         for f in ("wgo_vertical_day", "wgo_routing_day"):
             getattr(_lib, f).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         _lib.wgo_update_land_area_frac.argtypes = [ctypes.c_void_p]

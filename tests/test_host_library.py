@@ -492,3 +492,31 @@ def test_host_built_context_equals_array_upload_full_size(host):
         m.step_days(1, 0, 1, 0, 5)
     for k in names:
         assert np.array_equal(a.get(k), b.get(k)), k
+
+
+@pytest.mark.gpu
+def test_yearly_365_forcing_files_match_reference_driver(host, world3000, tmp_path):
+    """time_series 1: the year's forcing from the [cell][365] big-endian files of climateYear.cpp:38-58 (bytes uploaded as they are,
+    swapped and packed on the device) - January and February through the product's driver against the reference's driver reading
+    the same files (the option also switches the Rg_max table of gw_frac.cpp, so the run differs from the .31 run)"""
+    if not os.path.exists(HARNESS):
+        pytest.skip("compiled reference not available")
+    from oracle import synth_world as sw
+    tmp = str(tmp_path)
+    sw.write_world(world3000, tmp, (1901, 1901), (1, 2), time_series=1)
+    assert os.path.exists(os.path.join(tmp, "climate", "G_TEMP_H08_int_1901.365.UNF0"))
+    cfg = os.path.join(tmp, "config.txt")
+    files = ("wghm_state_lastday.txt", "snow_lastday.txt", "additional_lastday.txt")
+    _run_ref(tmp, cfg, "ref_", files)
+    err = ctypes.create_string_buffer(1024)
+    secs = ctypes.c_double()
+    assert host.wg_host_integrate(cfg.encode(), 3000, 0, ctypes.byref(secs), err, 1024) == 59, err.value
+    out = os.path.join(tmp, "output")
+    a = np.loadtxt(os.path.join(out, "ref_wghm_state_lastday.txt"), skiprows=2)
+    b = np.loadtxt(os.path.join(out, "wghm_state_lastday.txt"), skiprows=2)
+    e = np.abs(a[:, 1:] - b[:, 1:]) / np.maximum(np.maximum(np.abs(a[:, 1:]), np.abs(b[:, 1:])), 1e-6)
+    assert (e <= 1e-10).mean() > 0.999 and e.max() < 1e-6, (float(e.max()), float((e > 1e-10).mean()))
+    sa = np.loadtxt(os.path.join(out, "ref_snow_lastday.txt"), skiprows=1)
+    sb = np.loadtxt(os.path.join(out, "snow_lastday.txt"), skiprows=1)
+    es = np.abs(sa - sb) / np.maximum(np.maximum(np.abs(sa), np.abs(sb)), 1e-6)
+    assert (es <= 1e-10).mean() > 0.999 and es.max() < 1e-6

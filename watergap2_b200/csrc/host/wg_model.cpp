@@ -110,10 +110,12 @@ void optionClass::init(const ConfigFile &cfg) {
 
 void optionClass::require_canonical() const {
     struct { int idx, want; const char *name; } req[] = {
-        {5, 0, "time_series"}, {6, 1, "cloud"}, {7, 1, "intercept"}, {8, 0, "calc_albedo"}, {9, 0, "petOpt"}, {10, 1, "use_kc"},
+        {6, 1, "cloud"}, {7, 1, "intercept"}, {8, 0, "calc_albedo"}, {9, 0, "petOpt"}, {10, 1, "use_kc"},
         {14, 1, "riverveloOpt"}, {15, 0, "subtract_use"}, {18, 0, "clclOpt"}, {20, 1, "resOpt"}, {21, 0, "statcorrOpt"},
         {22, 1, "aridareaOpt"}, {23, 1, "fractionalRoutingOpt"}, {24, 1, "riverEvapoOpt"}, {27, 0, "resYearOpt"},
         {31, 0, "antNatOpt"}, {34, 0, "calc_wtemp"}, {35, 0, "glacierOpt"}, {1, 1, "basin"}};
+    if (v[5] != 0 && v[5] != 1)  // monthly .31 files (climate.cpp:93-138) or yearly .365 files (climateYear.cpp:38-79)
+        throw std::runtime_error("option time_series = " + std::to_string(v[5]) + " is outside the implemented hot path (0: .31 files, 1: .365 files)");
     for (auto &r : req)
         if (v[r.idx] != r.want)
             throw std::runtime_error(std::string("option ") + r.name + " = " + std::to_string(v[r.idx]) +
@@ -552,7 +554,9 @@ void dailyWaterBalanceClass::setStorages(WghmStateFile &st, SnowInElevationFile 
 }
 
 void dailyWaterBalanceClass::calcNewDayAll(short day, short month, short dom) {
-    eng.check(wgk_vertical_day(eng.ctx, day, month, dom, dom - 1), "wgk_vertical_day");
+    // forcing slot of the day: the month's .31 grids lie in slots 0..30, the year's .365 grids in slots 0..364
+    const int slot = (eng.options.time_series == 1) ? day - 1 : dom - 1;
+    eng.check(wgk_vertical_day(eng.ctx, day, month, dom, slot), "wgk_vertical_day");
 }
 
 void dailyWaterBalanceClass::calcNewDay(short day, short month, short dom, short, short year, int, WghmStateFile &, AdditionalOutputInputFile &,
@@ -629,6 +633,25 @@ void Engine::set_forcing_month(int month1, int year) {  // climate.cpp:93-123 (.
     T.read(c + "/GTEMP" + sfx); P.read(c + "/GPREC" + sfx); SW.read(c + "/GSHORTWAVE" + sfx); LW.read(c + "/GLONGWAVE_DOWN" + sfx);
     check(wgk_set_forcing(ctx, 0, 31, -1, P.data(), T.data(), SW.data(), LW.data(), 31), "wgk_set_forcing");
     check(wgk_synchronize(ctx), "sync");  // the host grids go out of scope
+}
+
+// the year's forcing from the [cell][365] files of climateYear.cpp:38-58 (time_series 1): the BYTES of the four big-endian files
+// go to the device as they are, byte order and layout are converted there (wgk_set_forcing_unf)
+void Engine::set_forcing_year(int year) {
+    const std::string c = options.climate_dir, y = std::to_string(year);
+    const std::string files[4] = {c + "/G_GPCC_H08day_V20110128_" + y + ".365.UNF0", c + "/G_TEMP_H08_int_" + y + ".365.UNF0",
+                                  c + "/G_SSRD_H08_int_" + y + ".365.UNF0", c + "/G_SLRD_H08_int_" + y + ".365.UNF0"};
+    std::vector<char> raw[4];
+    const size_t bytes = (size_t)ncell * 365 * sizeof(float);
+    for (int k = 0; k < 4; k++) {
+        std::ifstream f(files[k], std::ios::binary);
+        if (!f) throw std::runtime_error(files[k] + " not found.");
+        raw[k].resize(bytes);
+        f.read(raw[k].data(), (std::streamsize)bytes);
+        if ((size_t)f.gcount() != bytes) throw std::runtime_error(files[k] + ": short read");
+    }
+    check(wgk_set_forcing_unf(ctx, 0, 365, -1, raw[0].data(), raw[1].data(), raw[2].data(), raw[3].data(), 365), "wgk_set_forcing_unf");
+    check(wgk_synchronize(ctx), "sync");  // the host buffers go out of scope
 }
 
 // ------------------------------------------------------------------------------------------
@@ -732,7 +755,8 @@ long run_model(Engine &E, const ConfigFile &cfg, ModelStateRef S, double *second
     const short number_of_days_in_month[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
     const short last_day_in_month[12] = {30, 58, 89, 119, 150, 180, 211, 242, 272, 303, 333, 364};
     short readinstatus = 1;
-    E.check(wgk_forcing_reserve(E.ctx, 31, 0), "wgk_forcing_reserve");
+    const bool yearly_forcing = (E.options.time_series == 1);
+    E.check(wgk_forcing_reserve(E.ctx, yearly_forcing ? 365 : 31, 0), "wgk_forcing_reserve");
 
     long ndays = 0;
     double secs = 0.;
@@ -741,6 +765,7 @@ long run_model(Engine &E, const ConfigFile &cfg, ModelStateRef S, double *second
         E.dailyWaterBalance.annualInit();
         E.routing.annualInit(year, cfg.startMonth, additionalOutIn);
         if (!pushed) { E.push_static(); E.push_state(); pushed = true; }  // (yearly reservoir changes do not occur with resYearOpt 0)
+        if (yearly_forcing) E.set_forcing_year(year);  // integrateWGHM.cpp:565-568
         short day = 0;
         if (year == cfg.startYear) for (int m = 1; m < cfg.startMonth; m++) day += number_of_days_in_month[m - 1];
         short start_month = cfg.startMonth, end_month = cfg.endMonth;
@@ -750,7 +775,7 @@ long run_model(Engine &E, const ConfigFile &cfg, ModelStateRef S, double *second
             else { start_month = 1; end_month = 12; }
         }
         for (short month = start_month - 1; month < end_month; month++) {
-            E.set_forcing_month(month + 1, year);
+            if (!yearly_forcing) E.set_forcing_month(month + 1, year);
             wghmState.resetCells(number_of_days_in_month[month]);
             E.check(wgk_month_begin(E.ctx), "wgk_month_begin");  // the post-pass keeps what the month's checkpoint needs
             const auto t0 = std::chrono::steady_clock::now();

@@ -176,6 +176,7 @@ class Engine {
     void push_static();                // topology + statics + parameter-derived arrays
     void push_state();                 // host state grids -> device
     void set_forcing_month(int month1, int year);  // climate.cpp:93-138 (.31 files)
+    void set_forcing_year(int year);               // climateYear.cpp:38-58 (.365 files, time_series 1)
     void check(int rc, const char *what);
     template <class T, int C> void set(const char *name, const Grid<T, C> &g, int index = 0);
     template <class T, int C> void get(const char *name, Grid<T, C> &g, int index = 0);

@@ -142,7 +142,12 @@ class SnowInElevationFile {
 
 class AdditionalOutputInputFile {
   public:
-    explicit AdditionalOutputInputFile(size_t ncell = 0) : ncell_(ncell), v_(ncell * 53, 0.0) {}
+    explicit AdditionalOutputInputFile(size_t ncell = 0) : ncell_(ncell), v_(ncell * 53, 0.0) {
+        for (size_t i = 0; i < ncell; i++) {  // start values of additionalOutputInputFile.cpp:72-84: K_release 0.1, reduction factors 1
+            v_[i * 53 + 5] = 0.1;
+            for (int j : {8, 9, 11, 12, 13}) v_[i * 53 + j] = 1.;
+        }
+    }
     int additionalfilestatus = 0;
     double &additionalOutputInput(int i, int j) { return v_[(size_t)i * 53 + j]; }
     void save(const std::string &fn) {

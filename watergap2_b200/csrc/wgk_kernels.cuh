@@ -2288,7 +2288,8 @@ __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB_EFF) k_vertical_tpc(const
 
 
 #ifndef WGK_PRE_MINB_MM
-#define WGK_PRE_MINB_MM WGK_TPC_MINB_MM  // vertical + local routing in one kernel needs more registers: tuning knob of its member-minor form
+#define WGK_PRE_MINB_MM 4  // vertical + local routing in one kernel spills at 96 registers; measured on B200 (10^9 cell-days/s, wavefront,
+                           // 4 / 5 resident CTAs): 32 members 1.78 / 1.67, 64 members 2.00 / 1.97
 #endif
 #undef WGK_PRE_MINB_EFF
 #if WGK_MM
