@@ -63,6 +63,12 @@ typedef struct {
     int restart;            /* additionalOutIn.additionalfilestatus (daily.cpp:165): 0 cold start, 1 from checkpoint */
     int tail_threshold;     /* routing levels with <= this many cells are run by one persistent CTA per member (0 = auto) */
     int use_graph;          /* 1: one CUDA graph of (day, level) tasks per wgk_step_days call (default), 0: plain launches in dependency order */
+    int subtract_use;       /* options.subtract_use (option.cpp): 0 no water use (canonical), 2 net abstractions from surface water and
+                               groundwater satisfied inside routing() with use_alloc 0, delayedUseSatisfaction 0, aggrNUsGloLakResOpt 0
+                               (routing.cpp:1929-1935, 2193-2296, 2678-2788, 2866-2977, 3466-3512, 3590-3625, 3889-3908, 5503-5572).
+                               The "wu_*" fields exist only then: the month's inputs in km3 per day are set by the caller at every
+                               month start (wu_nus_month, wu_nug_month per parameter set; wu_wusi_month, wu_cusi_month), wu_frgi and
+                               wu_alloc_coeff [ncell][5] once. */
 } wgk_options;
 
 /* ---- life cycle ---------------------------------------------------------------------- */

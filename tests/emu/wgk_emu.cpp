@@ -142,7 +142,7 @@ static void emu_cells_pre_tiles(Emu *e, int begin, int end) {
                 each([&](int w, int lane, VThread<C> &t) { if (w < 4) v_sum<C>(sm, t, slab, w, lane); });
             }
         }
-        for (int lane = 0; lane < 32; lane++) v_finish<C, true>(p, sm, r0, begin, end, m, lane);
+        for (int lane = 0; lane < 32; lane++) v_finish<C, true>(p, sm, r0, begin, end, m, lane, p.cal_days[1]);
     }
 }
 

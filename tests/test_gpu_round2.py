@@ -350,3 +350,60 @@ def test_member_minor_layout_is_bit_identical(world3000, monkeypatch):
         for k in out[0][0]:
             assert np.array_equal(out[0][0][k], other[0][k]), k
     assert not np.array_equal(out[0][0][("soil", 0)], out[0][0][("soil", 39)])
+
+
+def test_water_use_vs_reference_golden(golden, monkeypatch):
+    """SURVEY 8f-4 on the GPU: net abstractions from surface water and groundwater (subtract_use 2) on the 1000-cell golden world,
+    January and February, against what the COMPILED REFERENCE held in memory (tests/golden/ref_ng1000_wateruse.npz): storages,
+    fluxes and the water-use bookkeeping (unsatisfied use, adapted groundwater abstraction, reduced return flows, actual use).
+    Days 1 and 2 must hold 1e-10 without exception; days 31 and 59 under the free-run policy, listed.  Both schedules."""
+    from oracle import synth_world as sw, water_use as wu, wg_init
+    import watergap2_b200 as wg
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_ng1000_wateruse.npz"))
+    ng = int(z["ng"])
+    w = sw.build_world(ng)
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    par = np.asarray(ini["params"]).reshape(26, -1)
+    files = {k[6:]: z[k] for k in z.files if k.startswith("input/")}
+    wu_names = ["wu_total_unsatisfied", "wu_daily_remaining", "wu_daily_nug", "wu_actual_use", "wu_uns_irr", "wu_uns_oth", "wu_red_rf", "wu_wusi", "wu_cusi"]
+    for sched in ("wavefront", "wholeday"):
+        monkeypatch.setenv("WGK_DAY_SCHEDULE", sched)
+        m = wg.Model(ng, subtract_use=2)
+        m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+        m.load(ini)
+        m.set("wu_frgi", z["input/G_FRACTRETURNGW_IRRIG.UNF0"].astype(np.float64))
+        m.forcing_reserve(31)
+        sd = 1
+        nchk = 0
+        for mon, ndays in ((0, 31), (1, 28)):
+            f = sw.forcing_month(w, 1901, mon + 1)
+            m.set_forcing(0, 31, f["P"], f["T"], f["SW"], f["LW"])
+            for k, v in wu.month_inputs(files, par, mon).items():
+                m.set(k, v)
+            done = 0
+            for stop in ((1, 2, 31) if mon == 0 else (28,)):
+                n = stop - done
+                doy = sd
+                m.step_days(doy, mon, done + 1, done, n)
+                sd += n
+                done = stop
+                day = sd - 1
+                rep = ParityReport()
+                for key in z.files:
+                    if key.startswith(f"d{day}/"):
+                        name = key.split("/", 1)[1]
+                        if m.has_field(name) and name != "status_laf_next":
+                            rep.add(name, z[key], m.get(name), tag=day)
+                            nchk += 1
+                print(sched, "day", day, rep.summary(), sorted(rep.flips, key=lambda f: -f[5])[:6])
+                if day <= 2:
+                    assert not rep.flips, rep.flips[:10]
+                else:
+                    cells = {f[2] if f[1] != "snow_bands" else f[2] // 101 for f in rep.flips}
+                    assert len(cells) <= 12 and rep.worst < 1e-6, (rep.summary(), sorted(rep.flips, key=lambda f: -f[5])[:10])
+        assert nchk > 150
+        assert (m.get("wu_total_unsatisfied") > 0).sum() > 50 and (m.get("wu_red_rf") != 0).any() and (m.get("gw") < 0).any()
+        m.close()
+    with pytest.raises(wg.WgkError, match="subtract_use"):
+        wg.Model(ng).get("wu_red_rf")  # the water-use arrays exist only with water use

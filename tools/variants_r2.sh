@@ -1,16 +1,14 @@
 cd $GRAFT_REPO_ROOT
-for V in libwgk libwgk_pre4; do
- for NM in 32 64; do
-  WGK_LIB=$PWD/watergap2_b200/$V.so timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu --legs enkf --enkf-members $NM > gpurun_out/pre_${V}_$NM.json 2> gpurun_out/pre_${V}_$NM.err
-  python - <<PY
-import json
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2e_pytest.log 2>&1; tail -5 gpurun_out/r2e_pytest.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2e_smoke.log 2>&1; tail -3 gpurun_out/r2e_smoke.log
+# single-member knobs (one simulated year per step)
+for K in "WGK_TAIL_THRESHOLD=128" "WGK_TAIL_THRESHOLD=512" "WGK_TAIL_THRESHOLD=1024" "WGK_LEVELS_PER_CHUNK=2" "WGK_LEVELS_PER_CHUNK=3" "X=0"; do
+  env $K timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu --legs none > gpurun_out/knob.json 2> gpurun_out/knob.err
+  python - "$K" <<'PY'
+import json, sys
 try:
-    e=json.load(open("gpurun_out/pre_${V}_$NM.json"))["sharded"]["enkf_256"]
-    print("$V $NM members: %.4f e9 cd/s, %.2f ms/step" % (e["value"]/1e9, e["ms_per_step"]))
-except Exception as ex: print("$V $NM failed", ex, open("gpurun_out/pre_${V}_$NM.err").read()[-300:])
+    d=json.load(open("gpurun_out/knob.json")); g=d["roofline"]["dominant_kernel"]["in_graph"]
+    print(sys.argv[1], "%.3f ms/yr, %.4f e9 cd/s, launches/yr %d, V0 %.1f us R0 %.1f us period %.1f us" % (d["ms_per_step"], d["value"]/1e9, d["gpu_launches"]/d["steps"], g["vertical_task_us"], g["river_task_us"], g["day_period_us"]))
+except Exception as e: print(sys.argv[1], "failed", e, open("gpurun_out/knob.err").read()[-300:])
 PY
- done
 done
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2d_pytest.log 2>&1; tail -5 gpurun_out/r2d_pytest.log
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2d_smoke.log 2>&1; tail -3 gpurun_out/r2d_smoke.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2d_bench.json 2> gpurun_out/r2d_bench.err; tail -c 1500 gpurun_out/r2d_bench.json; tail -3 gpurun_out/r2d_bench.err

@@ -33,7 +33,7 @@ def cell_classes(fields):
 
 
 class _Options(ctypes.Structure):
-    _fields_ = [("restart", ctypes.c_int), ("tail_threshold", ctypes.c_int), ("use_graph", ctypes.c_int)]
+    _fields_ = [("restart", ctypes.c_int), ("tail_threshold", ctypes.c_int), ("use_graph", ctypes.c_int), ("subtract_use", ctypes.c_int)]
 
 
 _lib = None
@@ -161,11 +161,11 @@ class Model:
         m._ids = {}
         return m
 
-    def __init__(self, ncell, nmember=1, npset=1, device=0, restart=0, tail_threshold=0, use_graph=1):
+    def __init__(self, ncell, nmember=1, npset=1, device=0, restart=0, tail_threshold=0, use_graph=1, subtract_use=0):
         self.ncell, self.nmember, self.npset, self.device = ncell, nmember, npset, device
         self._L = lib()
         self._c = ctypes.c_void_p()
-        opt = _Options(restart, tail_threshold, use_graph)
+        opt = _Options(restart, tail_threshold, use_graph, subtract_use)
         rc = self._L.wgk_create(ctypes.byref(self._c), device, ncell, nmember, npset, ctypes.byref(opt))
         if rc != 0:
             msg = self._L.wgk_last_error(self._c).decode() if self._c else "no CUDA device (wgk has no CPU fallback)"

@@ -145,7 +145,7 @@ void geoClass::init(const std::string &in, int ncell, int resOpt) {  // geo.cpp:
 // ------------------------------------------------------------------------------------------
 Engine::Engine(int nc, int device, int restart) : ncell(nc), dailyWaterBalance(*this), routing(*this) {
     if (device < 0) return;  // host-side initialisation only: no context, nothing can be stepped
-    wgk_options opt{restart, 0, 1};  // restart = additionalOutIn.additionalfilestatus (daily.cpp:165)
+    wgk_options opt{restart, 0, 1, 0};  // restart = additionalOutIn.additionalfilestatus (daily.cpp:165)
     check(wgk_create(&ctx, device, ncell, 1, 1, &opt), "wgk_create");
 }
 Engine::~Engine() { if (ctx) wgk_destroy(ctx); }

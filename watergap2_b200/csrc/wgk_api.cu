@@ -78,6 +78,8 @@ struct wgk_ctx {
     std::vector<int32_t> rank_of_cell, cell_of_rank, level_off, level_of_rank;
     std::vector<uint8_t> cell_class;
     int32_t *d_rank_of_cell = nullptr;
+    std::vector<int32_t> down_pos;       // downstream device position of every device position, or -1
+    int32_t *d_wu_res_idx = nullptr;     // water use: [5][stride] downstream cells an irrigation reservoir serves
     int32_t *d_cell_of_rank = nullptr, *d_up_off = nullptr, *d_up_idx = nullptr, *d_down = nullptr, *d_level_off = nullptr;
     int32_t *d_member_pset = nullptr;
     std::vector<int32_t> member_pset;
@@ -257,6 +259,8 @@ WgkParams make_params(const wgk_ctx *c) {
     p.forcing_per_member = c->forcing_per_member;
     p.restart = c->opt.restart;
     p.month_acc = c->month_acc ? 1 : 0;
+    p.subtract_use = c->opt.subtract_use;
+    p.wu_res_idx = c->d_wu_res_idx;
     p.nlevels = c->nlevels;
     p.mm = c->mm ? 1 : 0;
     p.mpad = c->mpad;
@@ -323,7 +327,7 @@ int enqueue_vertical(wgk_ctx *c, const WgkParams &p, int d) {
 int enqueue_routing(wgk_ctx *c, const WgkParams &p, int d) {
     int n = 0;
     const dim3 block = cell_block(c, 128), grid = cell_grid(c, c->ncell, 128);
-    WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p);
+    WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p, d);
     n++;
     for (int l = 0; l < c->tail_level0; l++) {
         const int cnt = c->level_off[l + 1] - c->level_off[l];
@@ -541,6 +545,28 @@ int ensure_derived(wgk_ctx *c) {
     CU(cudaMalloc(&c->d_gbody, nb * sizeof(double)));
     CU(cudaMemset(c->d_gbody, 0, nb * sizeof(double)));
     c->ngbody = n;
+    if (c->opt.subtract_use > 0) {
+        // irrigation reservoirs release for their own use and for up to 5 downstream cells without a reservoir (routing.cpp:2961-2973).
+        // The reference tests G_reservoir_area[downstreamCell] with the 1-based cell number as a 0-based index, i.e. the cell
+        // numbered downstreamCell + 1; that indexing is reproduced here (an index of ng ends the chain).
+        std::vector<double> res((size_t)c->stride);
+        CU(cudaMemcpyAsync(res.data(), c->arrays.reservoir_area, sizeof(double) * c->stride, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        std::vector<int32_t> idx((size_t)5 * c->stride, -1);
+        const int ng = c->ncell;
+        auto refnum_down = [&](int x) { return c->down_pos[x] >= 0 ? c->cell_of_rank[c->down_pos[x]] + 1 : 0; };
+        for (int x = 0; x < ng; x++) {
+            int i = 0, dc = refnum_down(x);
+            while (i < 5 && dc > 0 && dc < ng && res[c->rank_of_cell[dc]] <= 0) {
+                const int xd = c->rank_of_cell[dc - 1];
+                idx[(size_t)i * c->stride + x] = xd;
+                i++;
+                dc = refnum_down(xd);
+            }
+        }
+        if (!c->d_wu_res_idx) CU(cudaMalloc(&c->d_wu_res_idx, sizeof(int32_t) * idx.size()));
+        CU(cudaMemcpy(c->d_wu_res_idx, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice));
+    }
     // cells that are inactive (now) never write their discharge entry: no stale value of an earlier configuration may
     // feed a downstream gather or the published discharge field (every active cell rewrites its entry before it is read)
     CU(cudaMemsetAsync(c->d_qbuf, 0, (size_t)wgk::QBUF_K * c->mpad * c->stride * sizeof(double), c->stream));
@@ -575,7 +601,9 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     c->nmember = nmember;
     c->npset = npset;
     if (opt) c->opt = *opt;
-    else { c->opt.restart = 0; c->opt.tail_threshold = 0; c->opt.use_graph = 1; }
+    else { c->opt.restart = 0; c->opt.tail_threshold = 0; c->opt.use_graph = 1; c->opt.subtract_use = 0; }
+    if (c->opt.subtract_use != 0 && c->opt.subtract_use != 2)
+        return fail(c, WGK_ERR_ARG, "wgk_options.subtract_use %d: 0 (no water use) or 2 (net abstractions) are implemented", c->opt.subtract_use);
     if ((c->opt.restart != 0 && c->opt.restart != 1) || (c->opt.use_graph != 0 && c->opt.use_graph != 1) || c->opt.tail_threshold < 0)
         return fail(c, WGK_ERR_ARG, "wgk_options: restart %d / use_graph %d must be 0 or 1, tail_threshold %d >= 0", c->opt.restart,
                     c->opt.use_graph, c->opt.tail_threshold);
@@ -642,6 +670,7 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
                            (const void *)wgk_mm::k_cells_pre_tpc, (const void *)wgk_mm::k_vertical_tpc})
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     for (int f = 0; f < WGK_F_COUNT; f++) {
+        if (c->opt.subtract_use == 0 && strncmp(kFields[f].name, "wu_", 3) == 0) continue;  // the water-use arrays exist only with water use
         const size_t bytes = field_rows(c, f) * field_row_elems(c, f) * kFields[f].elsize;
         void *d = nullptr;
         cudaError_t e = cudaMalloc(&d, bytes);
@@ -675,7 +704,7 @@ void wgk_destroy(wgk_ctx *c) {
     if (c->ev_forcing) cudaEventDestroy(c->ev_forcing);
     drop_graph(c);
     for (void *d : c->allocs) cudaFree(d);
-    cudaFree(c->d_rank_of_cell);
+    cudaFree(c->d_rank_of_cell); cudaFree(c->d_wu_res_idx);
     cudaFree(c->d_cell_of_rank); cudaFree(c->d_up_off); cudaFree(c->d_up_idx); cudaFree(c->d_down);
     cudaFree(c->d_level_off); cudaFree(c->d_member_pset); cudaFree(c->d_cal); cudaFree(c->d_forcing);
     cudaFree(c->d_gidx); cudaFree(c->d_gbody); cudaFree(c->d_cal_days); cudaFree(c->d_qbuf);
@@ -814,6 +843,7 @@ int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downs
     CU(upload(c->d_up_off, up_off));
     CU(upload(c->d_up_idx, up_idx));
     CU(upload(c->d_down, down));
+    c->down_pos = down;
     CU(upload(c->d_level_off, c->level_off));
     {   // cell-owner schedule: warps of <= 32 consecutive cells that never straddle a dependency level
         std::vector<int32_t> wb, we, cw(std::max(1, ng), 0);
@@ -893,6 +923,7 @@ int wgk_field_info(int field, const char **name, const char **dtype, int64_t *co
 static int set_field_raw(wgk_ctx *c, int f, int index, const void *host, size_t bytes) {
     const FieldInfo &fi = kFields[f];
     if (index < 0 || (size_t)index >= field_index_count(c, f)) return fail(c, WGK_ERR_ARG, "index %d out of range for field %s", index, fi.name);
+    if (!*field_slot(c, f)) return fail(c, WGK_ERR_STATE, "field %s exists only with wgk_options.subtract_use > 0", fi.name);
     const size_t row_elems = field_row_elems(c, f);
     char *dst = (char *)*field_slot(c, f) + (size_t)index * row_elems * fi.elsize;
     if (fi.scope == WGK_SCOPE_TABLE) {
@@ -965,6 +996,7 @@ int wgk_get_field(wgk_ctx *c, int f, int index, void *host, size_t bytes) {
     CU(cudaSetDevice(c->device));
     const FieldInfo &fi = kFields[f];
     if (index < 0 || (size_t)index >= field_index_count(c, f)) return fail(c, WGK_ERR_ARG, "index %d out of range for field %s", index, fi.name);
+    if (!*field_slot(c, f)) return fail(c, WGK_ERR_STATE, "field %s exists only with wgk_options.subtract_use > 0", fi.name);
     const size_t row_elems = field_row_elems(c, f);
     const char *src = (const char *)*field_slot(c, f) + (size_t)index * row_elems * fi.elsize;
     if (fi.scope == WGK_SCOPE_TABLE) {
@@ -1011,7 +1043,7 @@ int wgk_set_member_pset(wgk_ctx *c, int member, int pset) {
 
 void *wgk_device_ptr(wgk_ctx *c, int f, int member) {
     if (!c || f < 0 || f >= WGK_F_COUNT) return nullptr;
-    if (member < 0 || (size_t)member >= field_index_count(c, f)) return nullptr;
+    if (member < 0 || (size_t)member >= field_index_count(c, f) || !*field_slot(c, f)) return nullptr;
     if (f == WGK_F_snow_bands) c->member_dirty = true;  // the caller may write the bands on the device
     return (char *)*field_slot(c, f) + (size_t)member * (index_pad(c, f) > 1 ? 1 : field_row_elems(c, f)) * kFields[f].elsize;
 }
@@ -1413,7 +1445,7 @@ int wgk_copy_index(wgk_ctx *c, int scope, int src, int dst) {
     if (src == dst) return WGK_OK;
     CU(cudaSetDevice(c->device));
     for (int f = 0; f < WGK_F_COUNT; f++) {
-        if (kFields[f].scope != scope) continue;
+        if (kFields[f].scope != scope || !*field_slot(c, f)) continue;
         const size_t bytes = field_row_elems(c, f) * kFields[f].elsize;
         char *base = (char *)*field_slot(c, f);
         const int pad = index_pad(c, f);
@@ -1544,7 +1576,7 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     CU(cudaEventRecord(ev[0], c->stream));
     launch_vertical(c, p, 0);
     CU(cudaEventRecord(ev[1], c->stream));
-    WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p);
+    WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p, 0);
     CU(cudaEventRecord(ev[2], c->stream));
     int n = 3;
     for (int l = 0; l < c->tail_level0; l++) {
@@ -1629,7 +1661,7 @@ int wgk_profile_schedule(wgk_ctx *c, int day, int month, int dom, int slot, floa
     if (c->whole_day) {
         const dim3 grid = cell_grid(c, c->ncell, 128);
         timed(0, [&] { launch_vertical(c, p, 0); });
-        timed(3, [&] { WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p); });
+        timed(3, [&] { WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p, 0); });
         for (int l = 0; l < c->tail_level0; l++) {
             const dim3 g = cell_grid(c, c->level_off[l + 1] - c->level_off[l], 128);
             timed(1, [&] { WGK_K(c, k_route_level)<<<g, block, 0, c->stream>>>(p, 0, l); });

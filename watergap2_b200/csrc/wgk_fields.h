@@ -140,6 +140,26 @@
     X(f_loc_lake, double, "f64", MEMBER, 1) \
     X(f_loc_wet, double, "f64", MEMBER, 1) \
     X(f_glo_wet, double, "f64", MEMBER, 1) \
+    /* ---- water use (allocated only with wgk_options.subtract_use > 0).  Inputs of the current month in km3 per \
+       day: net abstraction from surface water / groundwater times the cell's multiplier (dailyNUInit routing.cpp:884-977, \
+       calcNextDay_M :7432-7440), irrigation withdrawal / consumptive use from surface water (:3907-3908); statics: fraction of \
+       the irrigation return flow that reaches groundwater, allocation coefficients of irrigation reservoirs [cell][5] \
+       (G_ALLOC_COEFF.5.UNF0); state per member: the bookkeeping of updateNetAbstractionGW (:5503-5572) and of :3889-3908 ---- */ \
+    X(wu_nus_month, double, "f64", PSET, 1) \
+    X(wu_nug_month, double, "f64", PSET, 1) \
+    X(wu_wusi_month, double, "f64", CELL, 1) \
+    X(wu_cusi_month, double, "f64", CELL, 1) \
+    X(wu_frgi, double, "f64", CELL, 1) \
+    X(wu_alloc_coeff, double, "f64", CELL, 5) \
+    X(wu_total_unsatisfied, double, "f64", MEMBER, 1) \
+    X(wu_daily_remaining, double, "f64", MEMBER, 1) \
+    X(wu_uns_irr, double, "f64", MEMBER, 1) \
+    X(wu_uns_oth, double, "f64", MEMBER, 1) \
+    X(wu_red_rf, double, "f64", MEMBER, 1) \
+    X(wu_wusi, double, "f64", MEMBER, 1) \
+    X(wu_cusi, double, "f64", MEMBER, 1) \
+    X(wu_actual_use, double, "f64", MEMBER, 1) \
+    X(wu_daily_nug, double, "f64", MEMBER, 1) \
     /* ---- derived from the member state (k_derive_member), maintained by the vertical kernel ---- */ \
     X(s_snowfree, int8_t, "i8", MEMBER, 1) \
     /* ---- land cover tables (LCT_22.DAT / LAI_22.DAT; daily.h:204-208, lai.h) ---- */ \

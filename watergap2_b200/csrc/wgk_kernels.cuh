@@ -68,6 +68,8 @@ struct WgkParams {
     int forcing_nslots, forcing_per_member;
     int restart;
     int month_acc;                // accumulate the daily WghmStateFile values of the month (EnKF bridge)
+    int subtract_use;             // options.subtract_use: 0 no water use, 2 net abstractions
+    const int32_t *wu_res_idx;    // [5][stride] device position of the i-th downstream cell whose use an irrigation reservoir serves, or -1
     int nlevels;
     // Layout of the member- and parameter-set-scoped arrays:
     //   mm == 0  cell-minor   [member][band][cell]: a warp = 32 consecutive cells of one member (few members, latency regime)
@@ -1313,6 +1315,70 @@ __device__ unsigned int g_warpdur[4][1024];  // cycles of every level-0 vertical
 // ----------------------------------------------------------------------------------------
 // routing helpers
 // ----------------------------------------------------------------------------------------
+// ----------------------------------------------------------------------------------------
+// water use: subtract_use 2 with use_alloc 0, delayedUseSatisfaction 0, aggrNUsGloLakResOpt 0
+// ----------------------------------------------------------------------------------------
+// The day's net abstraction from groundwater in front of a groundwater balance (routing.cpp:1929-1935 and its four copies):
+// calcNextDay_M resets it to the month's value, updateNetAbstractionGW (:5503-5572) adapts it to the surface-water use that
+// stayed unsatisfied the day before (return flows reduced) or was satisfied late (reintroduced).  Returns what is subtracted
+// from the net groundwater inflow.
+__device__ __noinline__ double wu_net_gw_use(const WgkParams &p, const int r, const size_t i, const size_t q) {
+    const WgkArrays &a = p.a;
+    const double nug = a.wu_nug_month[q];
+    double out = nug;
+    double rem = a.wu_daily_remaining[i];
+    if (rem != 0.) {
+        if (rem > 1.e-12) {
+            const double wusi = a.wu_wusi[i];
+            if (wusi > 0.) {
+                const double eff = a.wu_cusi[i] / wusi;
+                const double frgi = a.wu_frgi[r];
+                const double factor = 1 - (1 - frgi) * (1 - eff);
+                double WUsiNew = 1 / factor * (wusi * factor - rem);
+                if (WUsiNew < 0.) {
+                    WUsiNew = 0.;
+                    a.wu_uns_irr[i] += wusi * factor;
+                    a.wu_uns_oth[i] += rem - (wusi * factor);
+                } else {
+                    a.wu_uns_irr[i] += rem;
+                }
+                const double returnflowChange = (frgi * (1 - eff) * (WUsiNew - wusi));
+                a.wu_red_rf[i] += returnflowChange;
+                out = nug - returnflowChange;
+                a.wu_daily_remaining[i] = 0.;
+            } else {
+                a.wu_uns_oth[i] += rem;
+            }
+        } else if (rem < -1.e-12) {
+            const double uns_oth = a.wu_uns_oth[i], uns_irr = a.wu_uns_irr[i];
+            double fromIrrig = rem + uns_oth;
+            if (fromIrrig < 0.) {
+                a.wu_uns_oth[i] = 0.;
+                if (uns_irr == 0.) {
+                    a.wu_daily_remaining[i] = 0.;
+                } else {
+                    double ratio = (fromIrrig / uns_irr);
+                    if (ratio < -1.) {
+                        ratio = -1.;
+                        fromIrrig = uns_irr * -1.;
+                    }
+                    const double red_rf = a.wu_red_rf[i];
+                    const double returnflowChange = (ratio * red_rf);
+                    a.wu_uns_irr[i] = uns_irr + fromIrrig;
+                    a.wu_red_rf[i] = red_rf + returnflowChange;
+                    out = nug - returnflowChange;
+                    a.wu_daily_remaining[i] = 0.;
+                }
+            } else {
+                a.wu_uns_oth[i] = uns_oth + rem;
+                a.wu_daily_remaining[i] = 0.;
+            }
+        }
+    }
+    a.wu_daily_nug[i] = out;
+    return out;
+}
+
 // groundwater linear reservoir (routing.cpp:1938-1958 and four identical copies)
 __device__ __forceinline__ double gw_step(double &Sg, double netGWin, double ek, double invk) {
     // ek = exp(-1. * k) and invk = (1. / k) depend on the parameter P_GWOUTF_C only: derived once (k_derive_static)
@@ -1342,7 +1408,7 @@ enum { GB_L_PREC, GB_L_PET, GB_L_MAX, GB_L_GWR, GB_R_PREC, GB_R_PET, GB_R_GWR, G
        GB_LOC_GWR_WET, GB_N = 24 };
 
 // cell class bits (s_flags, derived once from the statics by k_derive_static)
-constexpr int FL_ACTIVE = 1, FL_LDD_OUT = 2, FL_ARIDC = 4, FL_LAKE = 8, FL_RES = 16, FL_GLOWET = 32;
+constexpr int FL_ACTIVE = 1, FL_LDD_OUT = 2, FL_ARIDC = 4, FL_LAKE = 8, FL_RES = 16, FL_GLOWET = 32, FL_TBC1 = 64;  // FL_TBC1: G_toBeCalculated == 1
 
 // one-time derivation of inflow-independent river constants (routing.cpp:7293-7296):
 //   s_c1 = 1 / (M_RIVRGH_C * roughness),  s_slope_pow = pow(slope, 0.5),  s_flags
@@ -1378,6 +1444,7 @@ __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ W
         if (a.lake_area[r] > 0.) f |= FL_LAKE;
         if (a.reservoir_area[r] > 0.) f |= FL_RES;
         if (a.glo_wetland[r] > 0) f |= FL_GLOWET;
+        if (a.contcell[r] && (1 == a.toBeCalculated[r])) f |= FL_TBC1;
         a.s_flags[r] = (int8_t)f;
     }
 }
@@ -1397,7 +1464,8 @@ __global__ void __launch_bounds__(128) k_derive_member(const __grid_constant__ W
 // ----------------------------------------------------------------------------------------
 // cell-parallel pre-pass of the routing day: everything that does not depend on upstream cells
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void local_compute(const WgkParams &p, const int r, const int m, const LocalIn &li, const LocalFlux &fx) {
+__device__ __forceinline__ void local_compute(const WgkParams &p, const int r, const int m, const LocalIn &li, const LocalFlux &fx,
+                                              const int wu_month) {  // wu_month: month 0..11 of the day (only read with water use)
     const WgkArrays &a = p.a;
     const size_t i = mi(p, m, r);
     a.river_evapo[i] = 0.;  // routing.cpp:1781
@@ -1429,7 +1497,8 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
         localRunoff = fswb_catchment * dailyLocalSurfaceRunoff;
     }
     if ((0 == arid) && (ldd >= 0)) {  // :1979-2033
-        const double netGWin = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
+        double netGWin = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
+        if (p.subtract_use > 0) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));
         double Sg = li.gw;
         const double qg = gw_step(Sg, netGWin, li.ekg, li.invkg);
         a.gw[i] = Sg;
@@ -1438,7 +1507,8 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
         localRunoff = (fswb_catchment * dailyLocalSurfaceRunoff) + localGWRunoff;
     }
     if (ldd < 0) {  // :2123-2176
-        const double netGWin = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
+        double netGWin = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
+        if (p.subtract_use > 0) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));
         double Sg = li.gw;
         const double qg = gw_step(Sg, netGWin, li.ekg, li.invkg);
         a.gw[i] = Sg;
@@ -1541,7 +1611,8 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
         if (aridc && !(flags & (FL_LAKE | FL_RES | FL_GLOWET))) {
             const double gwr_swb = gwr_loclak + 0. + gwr_locwet + 0. + 0.;
             a.gwr_swb[i] = gwr_swb;
-            const double netGWin = gwr_swb * cellArea * (contf / C100) / C1E6 + fx.gw_recharge * cellArea * (laf / C100) / C1E6;
+            double netGWin = gwr_swb * cellArea * (contf / C100) / C1E6 + fx.gw_recharge * cellArea * (laf / C100) / C1E6;
+            if (p.subtract_use > 0) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));
             double Sg = li.gw;
             localGWRunoffIntoRiver = gw_step(Sg, netGWin, li.ekg, li.invkg);
             a.gw[i] = Sg;
@@ -1582,8 +1653,21 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 g[GB_R_CAP * gs] = stor_cap;
                 double prov_rel = 0.;
                 const int res_type = a.res_type[r];
-                if (res_type == 1) {  // irrigation reservoir; water use is not simulated: monthlyUse == 0
-                    const double monthlyUse = 0.;
+                if (res_type == 1) {  // irrigation reservoir (:2960-2977)
+                    double monthlyUse = 0.;
+                    if (p.subtract_use > 0) {
+                        // own use plus the share of up to 5 downstream cells that have no reservoir (the chain is resolved on the
+                        // host, wgk_api.cu ensure_derived, with the reference's indexing of G_reservoir_area)
+                        double dailyUse = a.wu_nus_month[qi(p, m, r)];
+                        for (int k = 0; k < 5; k++) {
+                            const int x = p.wu_res_idx[(size_t)k * p.stride + r];
+                            if (x < 0) break;
+                            dailyUse += a.wu_nus_month[qi(p, m, x)] * a.wu_alloc_coeff[(size_t)k * p.stride + r];
+                        }
+                        const int ndim[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+                        monthlyUse = dailyUse * ndim[wu_month];
+                        monthlyUse = monthlyUse * 1000000000. / (ndim[wu_month] * 86400.);
+                    }
                     const double mean_demand = a.mean_demand[r];
                     if (mean_demand >= 0.5 * mean_outflow) prov_rel = mean_outflow / 2. * (1. + monthlyUse / mean_demand);
                     else prov_rel = mean_outflow + monthlyUse - mean_demand;
@@ -1617,15 +1701,15 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
 }
 
 
-__device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r, const int m) {
+__device__ __forceinline__ void route_local_cell(const WgkParams &p, const int r, const int m, const int wu_month) {
     const LocalIn li = local_load(p, r, m);
-    local_compute(p, r, m, li, local_flux_load(p, r, m));
+    local_compute(p, r, m, li, local_flux_load(p, r, m), wu_month);
 }
 
-__global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ WgkParams p) {
+__global__ void __launch_bounds__(128) k_route_local(const __grid_constant__ WgkParams p, const int dayofs) {
     int r, m;
     if (!map_thread(p, 0, p.ncell, r, m)) return;
-    route_local_cell(p, r, m);
+    route_local_cell(p, r, m, p.cal_days[4 * dayofs + 1]);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1662,7 +1746,11 @@ __device__ __forceinline__ RiverCtx load_ctx(const WgkParams &p, const int r, co
 // post-pass.  Returns the inflow handed to the river.
 __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int r, const int m, const size_t i,
                                                    double inflow, const int flags, const int day, const int month,
-                                                   double &gwToRiver) {
+                                                   double &gwToRiver, double &remainingUse, double &dailyActualUse) {
+    // remainingUse / dailyActualUse: water use (0 / untouched without it).  The day's surface-water use is taken from the global
+    // lake (routing.cpp:2678-2788) and the reservoir (:2866-2946, 3068); what they cannot supply goes on to the river (:3166-3172).
+    const bool wu = p.subtract_use > 0;
+    double remainingUseGloLake = 0., remainingUseRes = 0.;
     const WgkArrays &a = p.a;
     const double *g = p.gbody + gb(p, m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
     const size_t gs = gbody_stride(p);
@@ -1670,7 +1758,9 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
     double gwr_glolak = 0., gwr_res = 0., gwr_glowet = 0.;
     if (flags & FL_LAKE) {  // :2677-2720
         const double prev = a.glo_lake_stor[i];
-        const double maxStorage = g[GB_L_MAX * gs], PET = g[GB_L_PET * gs];
+        remainingUseGloLake = (flags & FL_RES) ? 0.5 * remainingUse : remainingUse;  // :2681-2686 (0 without water use)
+        const double remainingUseGloLakeStart = remainingUseGloLake;
+        const double maxStorage = g[GB_L_MAX * gs], PET = g[GB_L_PET * gs] + remainingUseGloLake;
         gwr_glolak = g[GB_L_GWR * gs];
         const double totalInflow = inflow + g[GB_L_PREC * gs];
         const double PETmax = totalInflow + maxStorage + prev;
@@ -1679,6 +1769,8 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
             S = (-1.) * maxStorage;
             outflow = 0.;
             gwr_glolak *= PETmax / PET;
+            if (remainingUseGloLake > 0.) remainingUseGloLake -= remainingUseGloLake * PETmax / PET;  // :2710-2716
+            else remainingUseGloLake = 0.;
         } else {
             S = prev * ek + invk * (totalInflow - PET) * (1. - ek);
             outflow = totalInflow + prev - S - PET;
@@ -1690,9 +1782,11 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
                 outflow = 0.;
                 S = prev + totalInflow - PET;
             }
+            remainingUseGloLake = 0.;  // :2752
         }
         if (fabs(S) <= MIN_STOR_VOL) S = 0.;
         inflow = outflow;
+        dailyActualUse = remainingUseGloLakeStart - remainingUseGloLake;  // :2788
         a.glo_lake_stor[i] = S;
     }
     if (flags & FL_RES) {  // :2871-3040
@@ -1703,12 +1797,28 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
         gwr_res = g[GB_R_GWR * gs];
         const double totalInflow = inflow + g[GB_R_PREC * gs];
         const double PETmax = prev + totalInflow;
+        remainingUseRes = (flags & FL_LAKE) ? 0.5 * remainingUse + remainingUseGloLake : remainingUse;  // :2869-2875
+        const double remainingUseResStart = remainingUseRes;
         double S;
         if (PET > PETmax) {
             S = prev + totalInflow - PETmax;
             gwr_res *= PETmax / PET;
         } else {
             S = prev + totalInflow - PET;
+        }
+        if (wu) {  // :2922-2946: return flows are added; abstractions only above 10 % of the capacity
+            if (remainingUseRes < 0.) {
+                S -= remainingUseRes;
+                remainingUseRes = 0.;
+            } else if (S > (0.1 * stor_cap)) {
+                if (remainingUseRes < (S - (stor_cap * 0.1))) {
+                    S -= remainingUseRes;
+                    remainingUseRes = 0.;
+                } else {
+                    remainingUseRes -= (S - (stor_cap * 0.1));
+                    S = stor_cap * 0.1;
+                }
+            }
         }
         if (fabs(S) <= MIN_STOR_VOL) S = 0.;
         double Krel = a.k_release[i];
@@ -1738,8 +1848,10 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
             S = 0.;
         }
         inflow = outflow;
+        dailyActualUse += remainingUseResStart - remainingUseRes;  // :3068
         a.res_stor[i] = S;
     }
+    if (wu && (flags & (FL_LAKE | FL_RES))) remainingUse = (flags & FL_RES) ? remainingUseRes : remainingUseGloLake;  // :3166-3172
     if (flags & FL_GLOWET) {  // :3201-3260
         const double prev = a.glo_wetl_stor[i];
         const double maxStorage = g[GB_W_MAX * gs], PET = g[GB_W_PET * gs];
@@ -1766,7 +1878,8 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
     if (flags & FL_ARIDC) {  // :3305-3386
         const double gwr_swb = g[GB_LOC_GWR_LAK * gs] + gwr_glolak + g[GB_LOC_GWR_WET * gs] + gwr_glowet + gwr_res;
         a.gwr_swb[i] = gwr_swb;
-        const double netGWin = gwr_swb * a.area[r] * (a.contfreq[r] / C100) / C1E6 + g[GB_GWRECH * gs];
+        double netGWin = gwr_swb * a.area[r] * (a.contfreq[r] / C100) / C1E6 + g[GB_GWRECH * gs];
+        if (wu) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));  // :3325-3330
         const double prev = a.gw[i];
         const double ekg = g[GB_EKG * gs];
         double Sg = prev * ekg + g[GB_INVKG * gs] * netGWin * (1. - ekg);
@@ -1788,11 +1901,17 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
 // the sum of upstream discharges; writes discharge / storage and returns nothing
 __device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx &c, const int r, const int m, const size_t i,
                                             const size_t q, const double inflowUpstream, const int day, const int month,
-                                            double *__restrict__ qday, double *qout = nullptr) {
+                                            double *__restrict__ qday, double *qout = nullptr, double *red_loc_lake_out = nullptr) {
     const WgkArrays &a = p.a;
     double inflow = c.inflow_local + inflowUpstream;  // :2623
     double gwToRiver = c.gw_to_river;
-    if (c.flags & (FL_LAKE | FL_RES | FL_GLOWET)) inflow = route_global_bodies(p, r, m, i, inflow, c.flags, day, month, gwToRiver);
+    // water use (:2193-2296 with use_alloc 0, delayedUseSatisfaction 0, aggrNUsGloLakResOpt 0): the day's desired use is the month's
+    // net abstraction from surface water (negative = return flow)
+    const bool wu = p.subtract_use > 0;
+    double remainingUse = 0., dailyActualUse = 0.;
+    if (wu && (c.flags & FL_TBC1)) remainingUse = a.wu_nus_month[q];
+    if (c.flags & (FL_LAKE | FL_RES | FL_GLOWET))
+        inflow = route_global_bodies(p, r, m, i, inflow, c.flags, day, month, gwToRiver, remainingUse, dailyActualUse);
     double riverInflow = inflow;
     if (c.flags & FL_LDD_OUT) {
         riverInflow += c.runoff_to_river;
@@ -1812,7 +1931,8 @@ __device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx
     const double prevR = c.prevR;
     double riverEvapo = c.evapo;
     riverInflow += c.precip;
-    const double RiverEvapoRemUse = 0. + riverEvapo;
+    const double RiverEvapoRemUse = remainingUse + riverEvapo;  // (0. + evaporation without water use)
+    const double remainingUseRiverStart = remainingUse;
     const double eK = exp(-1. * K);
     const double RivEvapoRemUseMax = riverInflow + (K * prevR * eK) / (1. - eK);
     double Sr, transportedVolume;
@@ -1820,12 +1940,42 @@ __device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx
         Sr = 0.;
         transportedVolume = riverInflow + prevR - RivEvapoRemUseMax;
         if (transportedVolume < 0.) transportedVolume = 0.;
+        if (remainingUse > 0.) remainingUse -= remainingUse * RivEvapoRemUseMax / RiverEvapoRemUse;  // :3489-3492
+        else remainingUse = 0.;
         riverEvapo *= RivEvapoRemUseMax / RiverEvapoRemUse;
     } else {
         Sr = prevR * eK + (1. / K) * (riverInflow - RiverEvapoRemUse) * (1. - eK);
         if (fabs(Sr) <= MIN_STOR_VOL) Sr = 0.;
         transportedVolume = riverInflow + prevR - Sr - RiverEvapoRemUse;
         if (transportedVolume < 0.) transportedVolume = 0.;
+        remainingUse = 0.;  // :3512
+    }
+    if (wu) {
+        // what the river could not supply is taken from the local lake (:3590-3624), whose reduction factor is formed anew
+        const double loc_lake = a.loc_lake[r];
+        if ((loc_lake > 0.) && (remainingUse > 0.)) {
+            const double maxStorage = ((loc_lake) / C100) * a.area[r] * a.lake_depth_active[q];
+            double S = a.loc_lake_stor[i];
+            if (S > (-1.) * maxStorage) {
+                if (remainingUse < (maxStorage + S)) {
+                    S -= remainingUse;
+                    remainingUse = 0.;
+                } else {
+                    remainingUse -= (maxStorage + S);
+                    S = (-1.) * maxStorage;
+                }
+            }
+            a.loc_lake_stor[i] = S;
+            const double red = clamp01(1. - pow(fabs(S - maxStorage) / (2. * maxStorage), (a.p_evaredex[q] * 3.32193)));
+            a.red_loc_lake[i] = red;
+            if (red_loc_lake_out) *red_loc_lake_out = red;
+        }
+        dailyActualUse += remainingUseRiverStart - remainingUse;  // :3625
+        a.wu_actual_use[i] += dailyActualUse;                     // :3736
+        a.wu_total_unsatisfied[i] += remainingUse;                // :3897-3900 (use_alloc 0, delayedUseSatisfaction 0)
+        a.wu_daily_remaining[i] = remainingUse;
+        a.wu_wusi[i] = a.wu_wusi_month[r];                        // :3907-3908
+        a.wu_cusi[i] = a.wu_cusi_month[r];
     }
     // (inland sinks have no downstream cell; the reference keeps their river outflow out of the
     //  discharge grid, routing.cpp:4219-4221, and books it as evaporation, :3935-3937)
@@ -2088,11 +2238,12 @@ __global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ Wgk
     if (level == 0) WGK_INSITU_STAMP(1, 0, dayofs);
     if (level == 0) stamp_task(p, 1, 0, dayofs);
     const RiverCtx c = load_ctx(p, r, i, q);
-    const PostIn in = post_load(p, r, m);  // same round of loads as the river context
+    PostIn in = post_load(p, r, m);  // same round of loads as the river context
     double Sr = c.prevR;
     if (c.flags & FL_ACTIVE) {
         double *qday = qbuf_of_day(p, dayofs);
-        Sr = route_river(p, c, r, m, i, q, gather_upstream(p, c, m, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday);
+        Sr = route_river(p, c, r, m, i, q, gather_upstream(p, c, m, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday, nullptr,
+                         &in.red_loc_lake);  // (water use may take from the local lake after the river: its reduction factor changes)
     }
     route_post_compute(p, r, m, in, Sr);
     WGK_INSITU_END(2, level == 0);
@@ -2191,7 +2342,7 @@ __device__ __forceinline__ LocalIn local_from_tile(const VTile<C> &sm, const int
 // tail of the tile (warp 0): soil / runoff, then the local routing with the fluxes handed over in registers
 template <class C, bool LOCAL>
 __device__ __forceinline__ void v_finish(const WgkParams &p, VTile<C> &sm, const int r0, const int begin, const int end, const int m,
-                                         const int lane) {
+                                         const int lane, const int wu_month) {
     double flux[3] = {0., 0., 0.};
     v_tail<C>(p, sm, r0, m, lane, flux);
     const int r = r0 + lane;
@@ -2206,7 +2357,7 @@ __device__ __forceinline__ void v_finish(const WgkParams &p, VTile<C> &sm, const
         } else {
             fx = local_flux_load(p, r, m);  // cells outside the computed region keep their last fluxes
         }
-        local_compute(p, r, m, C::PRE ? local_from_tile<C>(sm, lane) : local_load(p, r, m), fx);
+        local_compute(p, r, m, C::PRE ? local_from_tile<C>(sm, lane) : local_load(p, r, m), fx, wu_month);
     }
 }
 
@@ -2256,7 +2407,7 @@ __device__ __forceinline__ void vertical_tile(const WgkParams &p, VTile<C> &sm, 
         v_bare_sums<C>(p, sm, r0, lane);
         WGK_TICK(3);
     }
-    v_finish<C, LOCAL>(p, sm, r0, begin, end, m, lane);
+    v_finish<C, LOCAL>(p, sm, r0, begin, end, m, lane, p.cal_days[4 * dayofs + 1]);
     WGK_TICK(4);
 #ifdef WGK_PHASE_TIMING
     if (threadIdx.x == 0) atomicAdd(&g_phase[bands ? 6 : 7], 1ull);
@@ -2306,8 +2457,8 @@ __global__ void __launch_bounds__(VBLOCK, WGK_PRE_MINB_EFF) k_cells_pre_tpc(cons
     if (begin == 0) stamp_task(p, 0, 0, dayofs);
     LocalIn li;
     LocalFlux fx;
-    if (vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, m, li, fx);
-    else route_local_cell(p, r, m);
+    if (vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, m, li, fx, p.cal_days[4 * dayofs + 1]);
+    else route_local_cell(p, r, m, p.cal_days[4 * dayofs + 1]);
     WGK_INSITU_END(0, begin == 0);
     if (begin == 0) WGK_INSITU_WARPDUR(dayofs);
     if (begin == 0) WGK_INSITU_STAMP(0, 1, dayofs);
@@ -2443,13 +2594,13 @@ __global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) 
         {   // vertical balance + local routing of the day (k_cells_pre_tpc)
             LocalIn li;
             LocalFlux fx;
-            if (vertical_cell(p, r, m, p.cal_days[4 * d + 3], stage, &li, &fx)) local_compute(p, r, m, li, fx);
-            else route_local_cell(p, r, m);
+            if (vertical_cell(p, r, m, p.cal_days[4 * d + 3], stage, &li, &fx)) local_compute(p, r, m, li, fx, p.cal_days[4 * d + 1]);
+            else route_local_cell(p, r, m, p.cal_days[4 * d + 1]);
         }
         // river reach + post-pass (k_river_level); everything that does not depend on upstream cells is loaded
         // before the hand-off is awaited
         const RiverCtx c = load_ctx(p, r, mb + r, q);
-        const PostIn in = post_load(p, r, m);
+        PostIn in = post_load(p, r, m);
         const uint32_t tag = s.base + (uint32_t)d + 1u;
         unsigned long long *ring = s.ring + ((size_t)(d % QBUF_K) * p.mpad * p.stride + mb) * 2;
         double Sr = c.prevR, qv = 0.;
@@ -2462,7 +2613,7 @@ __global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) 
                 inflowUpstream += v;
             }
             WGK_OWNER_TICK(1);
-            if (ok) Sr = route_river(p, c, r, m, mb + r, q, inflowUpstream, p.cal_days[4 * d], p.cal_days[4 * d + 1], p.a.discharge, &qv);
+            if (ok) Sr = route_river(p, c, r, m, mb + r, q, inflowUpstream, p.cal_days[4 * d], p.cal_days[4 * d + 1], p.a.discharge, &qv, &in.red_loc_lake);
         } else {
             p.a.discharge[mb + r] = 0.;
         }
