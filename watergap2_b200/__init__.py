@@ -156,6 +156,7 @@ class Model:
             raise WgkError(f"wg_host_create_context failed: {err.value.decode()}")
         m = cls.__new__(cls)
         m.ncell, m.nmember, m.npset, m.device = ncell, 1, 1, device
+        m.subtract_use = 0
         m._L = lib()
         m._c = ctypes.c_void_p(ptr)
         m._ids = {}
@@ -163,6 +164,7 @@ class Model:
 
     def __init__(self, ncell, nmember=1, npset=1, device=0, restart=0, tail_threshold=0, use_graph=1, subtract_use=0):
         self.ncell, self.nmember, self.npset, self.device = ncell, nmember, npset, device
+        self.subtract_use = subtract_use
         self._L = lib()
         self._c = ctypes.c_void_p()
         opt = _Options(restart, tail_threshold, use_graph, subtract_use)
@@ -261,6 +263,8 @@ class Model:
         for name, arr in fields.items():
             if name.startswith("_") or (only is not None and name not in only) or not self.has_field(name):
                 continue
+            if name.startswith("wu_") and not getattr(self, "subtract_use", 0):
+                continue  # the water-use arrays exist only with subtract_use > 0
             _, _, scope = self.field_info(name)
             if scope == 1:
                 idx = range(self.npset) if pset is None else [pset]

@@ -22,8 +22,16 @@ namespace wgk { constexpr int NBAND = 101; }
 #undef WGK_MM
 #define WGK_MM 1
 #include "wgk_kernels.cuh"  // namespace wgk_mm: the same kernels compiled for the member-minor layout (lane = member)
+#undef WGK_WU
+#define WGK_WU 1
+#include "wgk_kernels.cuh"  // namespace wgk_mm_wu: member-minor, the kernels that contain water use compiled with it
+#undef WGK_MM
+#define WGK_MM 0
+#include "wgk_kernels.cuh"  // namespace wgk_wu: cell-minor with water use
 // a layout-dependent kernel of the context's layout
 #define WGK_K(c_, name_) ((c_)->mm ? wgk_mm::name_ : wgk::name_)
+// a kernel that contains water-use code: by layout and by wgk_options.subtract_use
+#define WGK_KW(c_, name_) ((c_)->opt.subtract_use > 0 ? ((c_)->mm ? wgk_mm_wu::name_ : wgk_wu::name_) : ((c_)->mm ? wgk_mm::name_ : wgk::name_))
 
 namespace {
 
@@ -283,7 +291,9 @@ int levels_per_chunk() {  // tuning knob (WGK_LEVELS_PER_CHUNK); measured optimu
 }
 
 void *cells_pre_fn(const wgk_ctx *c) {
-    return c->form == 1 ? (void *)wgk::k_cells_pre<wgk::VCfgSmall> : c->form == 2 ? (void *)wgk::k_cells_pre<wgk::VCfgMid> : (void *)WGK_K(c, k_cells_pre_tpc);
+    if (c->opt.subtract_use > 0 && c->form)
+        return c->form == 1 ? (void *)wgk_wu::k_cells_pre<wgk_wu::VCfgSmall> : (void *)wgk_wu::k_cells_pre<wgk_wu::VCfgMid>;
+    return c->form == 1 ? (void *)wgk::k_cells_pre<wgk::VCfgSmall> : c->form == 2 ? (void *)wgk::k_cells_pre<wgk::VCfgMid> : (void *)WGK_KW(c, k_cells_pre_tpc);
 }
 void *vertical_fn(const wgk_ctx *c) {
     return c->form == 1 ? (void *)wgk::k_vertical<wgk::VCfgSmall> : c->form == 2 ? (void *)wgk::k_vertical<wgk::VCfgMid> : (void *)WGK_K(c, k_vertical_tpc);
@@ -327,16 +337,16 @@ int enqueue_vertical(wgk_ctx *c, const WgkParams &p, int d) {
 int enqueue_routing(wgk_ctx *c, const WgkParams &p, int d) {
     int n = 0;
     const dim3 block = cell_block(c, 128), grid = cell_grid(c, c->ncell, 128);
-    WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p, d);
+    WGK_KW(c, k_route_local)<<<grid, block, 0, c->stream>>>(p, d);
     n++;
     for (int l = 0; l < c->tail_level0; l++) {
         const int cnt = c->level_off[l + 1] - c->level_off[l];
         const dim3 g = cell_grid(c, cnt, 128);
-        WGK_K(c, k_route_level)<<<g, block, 0, c->stream>>>(p, d, l);
+        WGK_KW(c, k_route_level)<<<g, block, 0, c->stream>>>(p, d, l);
         n++;
     }
     if (c->tail_level0 < c->nlevels) {
-        wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, d, c->tail_level0, c->nlevels);
+        (c->opt.subtract_use > 0 ? wgk_wu::k_route_tail : wgk::k_route_tail)<<<c->nmember, 256, 0, c->stream>>>(p, d, c->tail_level0, c->nlevels);
         n++;
     }
     WGK_K(c, k_route_post)<<<grid, block, 0, c->stream>>>(p);
@@ -354,14 +364,14 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
             const dim3 g = cell_grid(c, end - begin, 128);
             launch_cells_pre(c, p, d, begin, end);
-            WGK_K(c, k_river_level)<<<g, block, 0, c->stream>>>(p, d, l);
+            WGK_KW(c, k_river_level)<<<g, block, 0, c->stream>>>(p, d, l);
             n += 2;
         }
         for (size_t k = 0; k + 1 < c->chunk_lo.size(); k++) {
             const int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
             const int begin = c->level_off[lo], end = c->level_off[hi];
             launch_cells_pre(c, p, d, begin, end);
-            wgk::k_tail_chunk<<<c->nmember, 256, 0, c->stream>>>(p, d, lo, hi);
+            (c->opt.subtract_use > 0 ? wgk_wu::k_tail_chunk : wgk::k_tail_chunk)<<<c->nmember, 256, 0, c->stream>>>(p, d, lo, hi);
             n += 2;
         }
         if (c->d_record) {
@@ -435,7 +445,7 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
             // (fusing R(d, l) with V(d + 1, l) into one task - one kernel boundary per day on the own-cell
             //  recurrence instead of two - was measured SLOWER: 27.4 vs 24.6 ms per simulated year, with 32 or 64 buffers)
             void *a2[] = {&pp, &dd, &ll};
-            CU(add((void *)WGK_K(c, k_river_level), grid, cell_block(c, 128), a2, {pre, last, first_sweep ? reuse : nullptr}, &node));
+            CU(add((void *)WGK_KW(c, k_river_level), grid, cell_block(c, 128), a2, {pre, last, first_sweep ? reuse : nullptr}, &node));
             first_sweep = false;
             prevW[l] = node;
             last = node;
@@ -447,7 +457,7 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
             cudaGraphNode_t pre, sweep;
             CU(add(pre_fn, pre_grid(begin, end), pre_block, a1, {prevT[k]}, &pre));
             void *a2[] = {&pp, &dd, &lo, &hi};
-            CU(add((void *)wgk::k_tail_chunk, dim3(c->nmember), dim3(256), a2, {pre, last, first_sweep ? reuse : nullptr}, &sweep));
+            CU(add((void *)(c->opt.subtract_use > 0 ? wgk_wu::k_tail_chunk : wgk::k_tail_chunk), dim3(c->nmember), dim3(256), a2, {pre, last, first_sweep ? reuse : nullptr}, &sweep));
             first_sweep = false;
             prevT[k] = sweep;
             last = sweep;
@@ -477,15 +487,15 @@ bool owner_usable(wgk_ctx *c) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
         const size_t smem = sizeof(wgk::SnowStage) * (wgk::OWN_BLOCK / wgk::VBLOCK);
-        cudaFuncSetAttribute(wgk::k_days_owner, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wgk::k_days_owner, wgk::OWN_BLOCK, smem);
+        cudaFuncSetAttribute((c->opt.subtract_use > 0 ? (const void *)wgk_wu::k_days_owner : (const void *)wgk::k_days_owner), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (c->opt.subtract_use > 0 ? (const void *)wgk_wu::k_days_owner : (const void *)wgk::k_days_owner), wgk::OWN_BLOCK, smem);
         const long long ctas = (long long)((c->owner_nwarps + wgk::OWN_BLOCK / 32 - 1) / (wgk::OWN_BLOCK / 32)) * c->nmember;
         c->owner_fits = (coop && ctas <= (long long)nb * sms) ? 1 : 0;
     }
     return c->owner_fits == 1;
 }
 int launch_owner(wgk_ctx *c, const WgkParams &p, int ndays) {
-    wgk::WgkOwner s{};
+    WgkOwner s{};
     s.warp_begin = c->d_own_warp_begin;
     s.warp_end = c->d_own_warp_end;
     s.cell_warp = c->d_own_cell_warp;
@@ -508,7 +518,7 @@ int launch_owner(wgk_ctx *c, const WgkParams &p, int ndays) {
     c->owner_base += (uint32_t)ndays;
     const dim3 grid((c->owner_nwarps + wgk::OWN_BLOCK / 32 - 1) / (wgk::OWN_BLOCK / 32), c->nmember);
     void *args[] = {(void *)&p, (void *)&s, (void *)&ndays};
-    CU(cudaLaunchCooperativeKernel((void *)wgk::k_days_owner, grid, dim3(wgk::OWN_BLOCK), args,
+    CU(cudaLaunchCooperativeKernel((c->opt.subtract_use > 0 ? (const void *)wgk_wu::k_days_owner : (const void *)wgk::k_days_owner), grid, dim3(wgk::OWN_BLOCK), args,
                                    sizeof(wgk::SnowStage) * (wgk::OWN_BLOCK / wgk::VBLOCK), c->stream));
     c->launches += 1;
     return WGK_OK;
@@ -667,7 +677,9 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     for (const void *fn : {(const void *)wgk::k_cells_pre<wgk::VCfgSmall>, (const void *)wgk::k_cells_pre<wgk::VCfgMid>,
                            (const void *)wgk::k_vertical<wgk::VCfgSmall>, (const void *)wgk::k_vertical<wgk::VCfgMid>,
                            (const void *)wgk::k_cells_pre_tpc, (const void *)wgk::k_vertical_tpc,
-                           (const void *)wgk_mm::k_cells_pre_tpc, (const void *)wgk_mm::k_vertical_tpc})
+                           (const void *)wgk_mm::k_cells_pre_tpc, (const void *)wgk_mm::k_vertical_tpc,
+                           (const void *)wgk_wu::k_cells_pre<wgk_wu::VCfgSmall>, (const void *)wgk_wu::k_cells_pre<wgk_wu::VCfgMid>,
+                           (const void *)wgk_wu::k_cells_pre_tpc, (const void *)wgk_mm_wu::k_cells_pre_tpc})
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     for (int f = 0; f < WGK_F_COUNT; f++) {
         if (c->opt.subtract_use == 0 && strncmp(kFields[f].name, "wu_", 3) == 0) continue;  // the water-use arrays exist only with water use
@@ -1576,18 +1588,18 @@ int wgk_profile_day(wgk_ctx *c, int day, int month, int dom, int slot, float ms[
     CU(cudaEventRecord(ev[0], c->stream));
     launch_vertical(c, p, 0);
     CU(cudaEventRecord(ev[1], c->stream));
-    WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p, 0);
+    WGK_KW(c, k_route_local)<<<grid, block, 0, c->stream>>>(p, 0);
     CU(cudaEventRecord(ev[2], c->stream));
     int n = 3;
     for (int l = 0; l < c->tail_level0; l++) {
         const int cnt = c->level_off[l + 1] - c->level_off[l];
         const dim3 g = cell_grid(c, cnt, 128);
-        WGK_K(c, k_route_level)<<<g, block, 0, c->stream>>>(p, 0, l);
+        WGK_KW(c, k_route_level)<<<g, block, 0, c->stream>>>(p, 0, l);
         n++;
     }
     CU(cudaEventRecord(ev[3], c->stream));
     if (c->tail_level0 < c->nlevels) {
-        wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, 0, c->tail_level0, c->nlevels);
+        (c->opt.subtract_use > 0 ? wgk_wu::k_route_tail : wgk::k_route_tail)<<<c->nmember, 256, 0, c->stream>>>(p, 0, c->tail_level0, c->nlevels);
         n++;
     }
     CU(cudaEventRecord(ev[4], c->stream));
@@ -1661,25 +1673,25 @@ int wgk_profile_schedule(wgk_ctx *c, int day, int month, int dom, int slot, floa
     if (c->whole_day) {
         const dim3 grid = cell_grid(c, c->ncell, 128);
         timed(0, [&] { launch_vertical(c, p, 0); });
-        timed(3, [&] { WGK_K(c, k_route_local)<<<grid, block, 0, c->stream>>>(p, 0); });
+        timed(3, [&] { WGK_KW(c, k_route_local)<<<grid, block, 0, c->stream>>>(p, 0); });
         for (int l = 0; l < c->tail_level0; l++) {
             const dim3 g = cell_grid(c, c->level_off[l + 1] - c->level_off[l], 128);
-            timed(1, [&] { WGK_K(c, k_route_level)<<<g, block, 0, c->stream>>>(p, 0, l); });
+            timed(1, [&] { WGK_KW(c, k_route_level)<<<g, block, 0, c->stream>>>(p, 0, l); });
         }
-        if (c->tail_level0 < c->nlevels) timed(2, [&] { wgk::k_route_tail<<<c->nmember, 256, 0, c->stream>>>(p, 0, c->tail_level0, c->nlevels); });
+        if (c->tail_level0 < c->nlevels) timed(2, [&] { (c->opt.subtract_use > 0 ? wgk_wu::k_route_tail : wgk::k_route_tail)<<<c->nmember, 256, 0, c->stream>>>(p, 0, c->tail_level0, c->nlevels); });
         timed(3, [&] { WGK_K(c, k_route_post)<<<grid, block, 0, c->stream>>>(p); });
     } else {
         for (int l = 0; l < c->tail_level0; l++) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
             const dim3 g = cell_grid(c, end - begin, 128);
             timed(0, [&] { launch_cells_pre(c, p, 0, begin, end); });
-            timed(1, [&] { WGK_K(c, k_river_level)<<<g, block, 0, c->stream>>>(p, 0, l); });
+            timed(1, [&] { WGK_KW(c, k_river_level)<<<g, block, 0, c->stream>>>(p, 0, l); });
         }
         for (size_t k = 0; k + 1 < c->chunk_lo.size(); k++) {
             const int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
             const int begin = c->level_off[lo], end = c->level_off[hi];
             timed(0, [&] { launch_cells_pre(c, p, 0, begin, end); });
-            timed(2, [&] { wgk::k_tail_chunk<<<c->nmember, 256, 0, c->stream>>>(p, 0, lo, hi); });
+            timed(2, [&] { (c->opt.subtract_use > 0 ? wgk_wu::k_tail_chunk : wgk::k_tail_chunk)<<<c->nmember, 256, 0, c->stream>>>(p, 0, lo, hi); });
         }
     }
     CU(cudaStreamSynchronize(c->stream));

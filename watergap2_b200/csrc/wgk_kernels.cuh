@@ -82,17 +82,47 @@ struct WgkParams {
                                   // level-0 tasks of a call, i.e. their duration INSIDE the running graph; null = off
 };
 
+// cell-owner schedule (k_days_owner): its hand-off structures
+struct WgkOwner {
+    const int32_t *warp_begin, *warp_end;  // [nwarps] device-order cell range of a warp (one level, <= 32 cells)
+    const int32_t *cell_warp;              // [ncell] warp that owns a cell
+    unsigned long long *ring;              // [QBUF_K][nmember][stride][2] tagged discharge entries
+    uint32_t *progress;                    // [nmember][nwarps] tag of the last day a warp has consumed
+    int32_t *abort;                        // set when a wait timed out
+    const int32_t *rec_head, *rec_next;    // station records of a cell: rec_head[cell] -> k, rec_next[k] -> k' (or -1)
+    long long *timing;                     // optional [nwarps][4] cycles of lane 0: vertical+local, waits, river+hand-off, post (tools/owner_timing.py)
+    uint32_t base;                         // tag of day offset d of this call = base + d + 1 (days stepped so far by this context)
+    int nwarps;
+};
 #endif  // WGK_PARAMS_DEFINED
 
+#ifndef WGK_WU
+#define WGK_WU 0  // 1: the kernels that contain water use compiled WITH it, in namespaces wgk_wu / wgk_mm_wu; the canonical
+                  // configuration (subtract_use 0) runs kernels without a trace of it (it cost 5 % of the single-member year as a run-time branch)
+#endif
 #undef WGK_NS
-#if WGK_MM
+#if WGK_MM && WGK_WU
+#define WGK_NS wgk_mm_wu
+#elif WGK_MM
 #define WGK_NS wgk_mm
+#elif WGK_WU
+#define WGK_NS wgk_wu
 #else
 #define WGK_NS wgk
 #endif
 namespace WGK_NS {
 
 constexpr bool MM = (WGK_MM != 0);
+constexpr bool WU = (WGK_WU != 0);
+#undef WGK_WU_PARAMS
+#undef WGK_WU_ARGS
+#if WGK_WU  // the out-of-line global-water-body function carries the day's use only in the water-use build
+#define WGK_WU_PARAMS , double &remainingUse, double &dailyActualUse
+#define WGK_WU_ARGS , remainingUse, dailyActualUse
+#else
+#define WGK_WU_PARAMS
+#define WGK_WU_ARGS
+#endif
 // element (member m, device position r) of a member array / of a parameter-set array
 __host__ __device__ __forceinline__ size_t mi(const WgkParams &p, const int m, const int r) { return MM ? (size_t)r * p.mpad + m : (size_t)m * p.stride + r; }
 __host__ __device__ __forceinline__ size_t qi_of(const WgkParams &p, const int ps, const int r) { return MM ? (size_t)r * p.ppad + ps : (size_t)ps * p.stride + r; }
@@ -1410,6 +1440,7 @@ enum { GB_L_PREC, GB_L_PET, GB_L_MAX, GB_L_GWR, GB_R_PREC, GB_R_PET, GB_R_GWR, G
 // cell class bits (s_flags, derived once from the statics by k_derive_static)
 constexpr int FL_ACTIVE = 1, FL_LDD_OUT = 2, FL_ARIDC = 4, FL_LAKE = 8, FL_RES = 16, FL_GLOWET = 32, FL_TBC1 = 64;  // FL_TBC1: G_toBeCalculated == 1
 
+#if !WGK_WU  // no water use inside: compiled once per layout
 // one-time derivation of inflow-independent river constants (routing.cpp:7293-7296):
 //   s_c1 = 1 / (M_RIVRGH_C * roughness),  s_slope_pow = pow(slope, 0.5),  s_flags
 __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ WgkParams p) {
@@ -1461,6 +1492,7 @@ __global__ void __launch_bounds__(128) k_derive_member(const __grid_constant__ W
     p.a.s_snowfree[mi(p, m, r)] = (int8_t)(nz == 0);
 }
 
+#endif  // !WGK_WU
 // ----------------------------------------------------------------------------------------
 // cell-parallel pre-pass of the routing day: everything that does not depend on upstream cells
 // ----------------------------------------------------------------------------------------
@@ -1498,7 +1530,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
     }
     if ((0 == arid) && (ldd >= 0)) {  // :1979-2033
         double netGWin = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
-        if (p.subtract_use > 0) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));
+        if (WU) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));
         double Sg = li.gw;
         const double qg = gw_step(Sg, netGWin, li.ekg, li.invkg);
         a.gw[i] = Sg;
@@ -1508,7 +1540,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
     }
     if (ldd < 0) {  // :2123-2176
         double netGWin = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
-        if (p.subtract_use > 0) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));
+        if (WU) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));
         double Sg = li.gw;
         const double qg = gw_step(Sg, netGWin, li.ekg, li.invkg);
         a.gw[i] = Sg;
@@ -1612,7 +1644,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
             const double gwr_swb = gwr_loclak + 0. + gwr_locwet + 0. + 0.;
             a.gwr_swb[i] = gwr_swb;
             double netGWin = gwr_swb * cellArea * (contf / C100) / C1E6 + fx.gw_recharge * cellArea * (laf / C100) / C1E6;
-            if (p.subtract_use > 0) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));
+            if (WU) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));
             double Sg = li.gw;
             localGWRunoffIntoRiver = gw_step(Sg, netGWin, li.ekg, li.invkg);
             a.gw[i] = Sg;
@@ -1655,7 +1687,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 const int res_type = a.res_type[r];
                 if (res_type == 1) {  // irrigation reservoir (:2960-2977)
                     double monthlyUse = 0.;
-                    if (p.subtract_use > 0) {
+                    if (WU) {
                         // own use plus the share of up to 5 downstream cells that have no reservoir (the chain is resolved on the
                         // host, wgk_api.cu ensure_derived, with the reference's indexing of G_reservoir_area)
                         double dailyUse = a.wu_nus_month[qi(p, m, r)];
@@ -1746,10 +1778,13 @@ __device__ __forceinline__ RiverCtx load_ctx(const WgkParams &p, const int r, co
 // post-pass.  Returns the inflow handed to the river.
 __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int r, const int m, const size_t i,
                                                    double inflow, const int flags, const int day, const int month,
-                                                   double &gwToRiver, double &remainingUse, double &dailyActualUse) {
+                                                   double &gwToRiver WGK_WU_PARAMS) {
+#if !WGK_WU
+    double remainingUse = 0., dailyActualUse = 0.;  // (no water use: the terms below fold away)
+#endif
     // remainingUse / dailyActualUse: water use (0 / untouched without it).  The day's surface-water use is taken from the global
     // lake (routing.cpp:2678-2788) and the reservoir (:2866-2946, 3068); what they cannot supply goes on to the river (:3166-3172).
-    const bool wu = p.subtract_use > 0;
+    constexpr bool wu = WU;
     double remainingUseGloLake = 0., remainingUseRes = 0.;
     const WgkArrays &a = p.a;
     const double *g = p.gbody + gb(p, m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
@@ -1907,11 +1942,11 @@ __device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx
     double gwToRiver = c.gw_to_river;
     // water use (:2193-2296 with use_alloc 0, delayedUseSatisfaction 0, aggrNUsGloLakResOpt 0): the day's desired use is the month's
     // net abstraction from surface water (negative = return flow)
-    const bool wu = p.subtract_use > 0;
+    constexpr bool wu = WU;
     double remainingUse = 0., dailyActualUse = 0.;
     if (wu && (c.flags & FL_TBC1)) remainingUse = a.wu_nus_month[q];
     if (c.flags & (FL_LAKE | FL_RES | FL_GLOWET))
-        inflow = route_global_bodies(p, r, m, i, inflow, c.flags, day, month, gwToRiver, remainingUse, dailyActualUse);
+        inflow = route_global_bodies(p, r, m, i, inflow, c.flags, day, month, gwToRiver WGK_WU_ARGS);
     double riverInflow = inflow;
     if (c.flags & FL_LDD_OUT) {
         riverInflow += c.runoff_to_river;
@@ -2214,12 +2249,14 @@ __device__ __forceinline__ void route_post_cell(const WgkParams &p, const int r,
     route_post_compute(p, r, m, in, p.a.river_stor[mi(p, m, r)]);
 }
 
+#if !WGK_WU  // no water use inside
 __global__ void __launch_bounds__(128) k_route_post(const __grid_constant__ WgkParams p) {
     int r, m;
     if (!map_thread(p, 0, p.ncell, r, m)) return;
     route_post_cell(p, r, m);
 }
 
+#endif  // !WGK_WU
 // ----------------------------------------------------------------------------------------
 // temporal wavefront: one kernel per (day, dependency level).  A cell of level l on day d needs
 // its own state of day d-1 and the discharge of its upstream cells (levels < l) of day d, so
@@ -2242,8 +2279,10 @@ __global__ void __launch_bounds__(128) k_river_level(const __grid_constant__ Wgk
     double Sr = c.prevR;
     if (c.flags & FL_ACTIVE) {
         double *qday = qbuf_of_day(p, dayofs);
+        double red_ll = in.red_loc_lake;  // (water use may take from the local lake after the river: its reduction factor changes)
         Sr = route_river(p, c, r, m, i, q, gather_upstream(p, c, m, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday, nullptr,
-                         &in.red_loc_lake);  // (water use may take from the local lake after the river: its reduction factor changes)
+                         WU ? &red_ll : nullptr);
+        if (WU) in.red_loc_lake = red_ll;
     }
     route_post_compute(p, r, m, in, Sr);
     WGK_INSITU_END(2, level == 0);
@@ -2421,6 +2460,7 @@ __global__ void __launch_bounds__(C::THREADS, C::NW == 5 ? 6 : 12) k_cells_pre(c
     vertical_tile<C, true>(p, sm, begin, end, blockIdx.y, dayofs);
 }
 
+#if !WGK_WU  // no water use inside
 // the vertical balance alone over the whole grid (wgk_vertical_day, wgk_profile_day)
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::NW == 5 ? 6 : 12) k_vertical(const __grid_constant__ WgkParams p, const int dayofs) {
@@ -2429,7 +2469,9 @@ __global__ void __launch_bounds__(C::THREADS, C::NW == 5 ? 6 : 12) k_vertical(co
 }
 
 #endif  // !WGK_MM
+#endif  // !WGK_WU
 // thread-per-cell forms of k_vertical and k_cells_pre
+#if !WGK_WU  // no water use inside
 __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB_EFF) k_vertical_tpc(const __grid_constant__ WgkParams p, const int dayofs) {
     __shared__ SnowStage stage;
     int r, m;
@@ -2438,6 +2480,7 @@ __global__ void __launch_bounds__(VBLOCK, WGK_TPC_MINB_EFF) k_vertical_tpc(const
 }
 
 
+#endif  // !WGK_WU
 #ifndef WGK_PRE_MINB_MM
 #define WGK_PRE_MINB_MM 4  // vertical + local routing in one kernel spills at 96 registers; measured on B200 (10^9 cell-days/s, wavefront,
                            // 4 / 5 resident CTAs): 32 members 1.78 / 1.67, 64 members 2.00 / 1.97
@@ -2500,17 +2543,6 @@ __global__ void __launch_bounds__(256) k_tail_chunk(const __grid_constant__ WgkP
 // keeps a CTA's warps in step (below) repairs that but couples them to the slowest hand-off among them
 // (CTAs of 512 / 256 / 128 threads: 112 / 90 / 90 us per day; without any hand-off wait the barrier form runs at 63 us).
 // ----------------------------------------------------------------------------------------
-struct WgkOwner {
-    const int32_t *warp_begin, *warp_end;  // [nwarps] device-order cell range of a warp (one level, <= 32 cells)
-    const int32_t *cell_warp;              // [ncell] warp that owns a cell
-    unsigned long long *ring;              // [QBUF_K][nmember][stride][2] tagged discharge entries
-    uint32_t *progress;                    // [nmember][nwarps] tag of the last day a warp has consumed
-    int32_t *abort;                        // set when a wait timed out
-    const int32_t *rec_head, *rec_next;    // station records of a cell: rec_head[cell] -> k, rec_next[k] -> k' (or -1)
-    long long *timing;                     // optional [nwarps][4] cycles of lane 0: vertical+local, waits, river+hand-off, post (tools/owner_timing.py)
-    uint32_t base;                         // tag of day offset d of this call = base + d + 1 (days stepped so far by this context)
-    int nwarps;
-};
 constexpr long long WGK_SPIN_LIMIT = 4000000000LL;  // ~2 s at 1.965 GHz
 
 // all polling goes to L2 (relaxed at GPU scope), never to the non-coherent L1
@@ -2613,7 +2645,9 @@ __global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) 
                 inflowUpstream += v;
             }
             WGK_OWNER_TICK(1);
-            if (ok) Sr = route_river(p, c, r, m, mb + r, q, inflowUpstream, p.cal_days[4 * d], p.cal_days[4 * d + 1], p.a.discharge, &qv, &in.red_loc_lake);
+            double red_ll = in.red_loc_lake;
+            if (ok) Sr = route_river(p, c, r, m, mb + r, q, inflowUpstream, p.cal_days[4 * d], p.cal_days[4 * d + 1], p.a.discharge, &qv, WU ? &red_ll : nullptr);
+            if (WU) in.red_loc_lake = red_ll;
         } else {
             p.a.discharge[mb + r] = 0.;
         }
@@ -2637,6 +2671,7 @@ __global__ void __launch_bounds__(OWN_BLOCK, WGK_TPC_MINB * VBLOCK / OWN_BLOCK) 
 #endif  // WGK_EMU
 
 #endif  // !WGK_MM
+#if !WGK_WU  // calendar, forcing, diagnostics, state bridge: no water use inside
 // ----------------------------------------------------------------------------------------
 // calendar, forcing, diagnostics
 // ----------------------------------------------------------------------------------------
@@ -2904,5 +2939,7 @@ __global__ void __launch_bounds__(128) k_enkf_update(const __grid_constant__ Wgk
     a.river_stor[i] = w[8] * denom;
     a.gw[i] = w[9] * denom;
 }
+
+#endif  // !WGK_WU
 
 }  // namespace wgk / wgk_mm
