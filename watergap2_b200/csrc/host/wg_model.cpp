@@ -87,7 +87,8 @@ ConfigFile::ConfigFile(const std::string &file) {
             {"output_state_lastday", &outputlastdayfile}, {"output_snowInElevation_lastday", &outputsnowlastdayfile},
             {"additionalOutIn_lastday", &outputadditionalfile}, {"runtime_options", &runtimeoptionsfile},
             {"output_options", &outputoptionsfile}, {"routing", &routingoptionsfile}, {"stations", &stationsfile},
-            {"input_dir", &inputDir}, {"output_dir", &outputDir}, {"climate_dir", &climateDir}, {"routing_dir", &routingDir}};
+            {"input_dir", &inputDir}, {"output_dir", &outputDir}, {"climate_dir", &climateDir}, {"routing_dir", &routingDir},
+            {"water_use_dir", &waterUseDir}};
         std::map<std::string, int *> num = {{"start_month", &startMonth}, {"start_year", &startYear}, {"end_month", &endMonth},
                                             {"end_year", &endYear}, {"time_step", &timeStep}, {"num_init_years", &numInitYears}};
         if (str.count(tag)) ss >> *str[tag];
@@ -105,17 +106,22 @@ void optionClass::init(const ConfigFile &cfg) {
     while (f && std::getline(f, line))
         if (line.compare(0, 6, "Value:") == 0 && i < 36) v[i++] = atoi(line.c_str() + 7);
     input_dir = cfg.inputDir; output_dir = cfg.outputDir; climate_dir = cfg.climateDir; routing_dir = cfg.routingDir;
+    water_use_dir = cfg.waterUseDir;
     start_year = cfg.startYear; end_year = cfg.endYear;
 }
 
 void optionClass::require_canonical() const {
     struct { int idx, want; const char *name; } req[] = {
         {6, 1, "cloud"}, {7, 1, "intercept"}, {8, 0, "calc_albedo"}, {9, 0, "petOpt"}, {10, 1, "use_kc"},
-        {14, 1, "riverveloOpt"}, {15, 0, "subtract_use"}, {18, 0, "clclOpt"}, {20, 1, "resOpt"}, {21, 0, "statcorrOpt"},
+        {14, 1, "riverveloOpt"}, {18, 0, "clclOpt"}, {20, 1, "resOpt"}, {21, 0, "statcorrOpt"},
         {22, 1, "aridareaOpt"}, {23, 1, "fractionalRoutingOpt"}, {24, 1, "riverEvapoOpt"}, {27, 0, "resYearOpt"},
         {31, 0, "antNatOpt"}, {34, 0, "calc_wtemp"}, {35, 0, "glacierOpt"}, {1, 1, "basin"}};
     if (v[5] != 0 && v[5] != 1)  // monthly .31 files (climate.cpp:93-138) or yearly .365 files (climateYear.cpp:38-79)
         throw std::runtime_error("option time_series = " + std::to_string(v[5]) + " is outside the implemented hot path (0: .31 files, 1: .365 files)");
+    if (v[15] != 0 && v[15] != 2)
+        throw std::runtime_error("option subtract_use = " + std::to_string(v[15]) + " is outside the implemented hot path (0: no water use, 2: net abstractions)");
+    if (v[15] == 2 && (v[16] != 0 || v[17] != 0 || v[25] != 0))
+        throw std::runtime_error("water use is implemented with use_alloc 0, delayedUseSatisfaction 0, aggrNUsGloLakResOpt 0");
     for (auto &r : req)
         if (v[r.idx] != r.want)
             throw std::runtime_error(std::string("option ") + r.name + " = " + std::to_string(v[r.idx]) +
@@ -143,9 +149,9 @@ void geoClass::init(const std::string &in, int ncell, int resOpt) {  // geo.cpp:
 // ------------------------------------------------------------------------------------------
 // engine
 // ------------------------------------------------------------------------------------------
-Engine::Engine(int nc, int device, int restart) : ncell(nc), dailyWaterBalance(*this), routing(*this) {
+Engine::Engine(int nc, int device, int restart, int subtract_use) : ncell(nc), dailyWaterBalance(*this), routing(*this) {
     if (device < 0) return;  // host-side initialisation only: no context, nothing can be stepped
-    wgk_options opt{restart, 0, 1, 0};  // restart = additionalOutIn.additionalfilestatus (daily.cpp:165)
+    wgk_options opt{restart, 0, 1, subtract_use};  // restart = additionalOutIn.additionalfilestatus (daily.cpp:165)
     check(wgk_create(&ctx, device, ncell, 1, 1, &opt), "wgk_create");
 }
 Engine::~Engine() { if (ctx) wgk_destroy(ctx); }
@@ -321,8 +327,14 @@ void routingClass::init(short, const ConfigFile &, WghmStateFile &, AdditionalOu
     G_stor_cap_full.read(in + "/G_STORAGE_CAPACITY.UNF0");
     Grid<double> mean_NUs(ng);
     mean_NUs.read(in + "/G_NUs_1971_2000.UNF0");
-    Grid<double, 5> alloc(ng);
+    Grid<double, 5> &alloc = G_alloc_coeff;
+    alloc.initialize(ng);
     alloc.read(rd + "/G_ALLOC_COEFF.5.UNF0");
+    for (auto *g : {&G_fractreturngw_irrig, &G_totalUnsatisfiedUse, &G_UnsatisfiedUsePrevYear, &G_unsatisfiedNAsFromIrrig, &G_unsatisfiedNAsFromIrrigPrevYear,
+                    &G_unsatisfiedNAsFromOtherSectors, &G_unsatisfiedNAsFromOtherSectorsPrevYear, &G_reducedReturnFlow, &G_reducedReturnFlowPrevYear,
+                    &G_dailyRemainingUse, &G_withdrawalIrrigFromSwb, &G_consumptiveUseIrrigFromSwb, &G_actualUse})
+        g->initialize(ng);
+    if (eng.options.subtract_use > 0) G_fractreturngw_irrig.read(in + "/G_FRACTRETURNGW_IRRIG.UNF0");  // :541-543
     for (int n = 0; n < ng; n++) {  // :361-377 (incl. the reference's un-decremented index into G_reservoir_area_full)
         G_mean_demand[n] = mean_NUs[n];
         short i = 0;
@@ -433,8 +445,20 @@ void routingClass::setStoragesToZero() {  // :789-847 (riverveloOpt 1: rivers st
         g->fill(0.);
 }
 
-void routingClass::setStorages(WghmStateFile &st, AdditionalOutputInputFile &) {  // :851-882
+void routingClass::setStorages(WghmStateFile &st, AdditionalOutputInputFile &add) {  // :851-882
     for (int n = 0; n < eng.ncell; n++) {
+        G_totalUnsatisfiedUse[n] = add.additionalOutputInput(n, 3);
+        G_UnsatisfiedUsePrevYear[n] = add.additionalOutputInput(n, 4);
+        G_reducedReturnFlow[n] = add.additionalOutputInput(n, 38);
+        G_reducedReturnFlowPrevYear[n] = add.additionalOutputInput(n, 50);
+        G_unsatisfiedNAsFromIrrig[n] = add.additionalOutputInput(n, 39);
+        G_unsatisfiedNAsFromIrrigPrevYear[n] = add.additionalOutputInput(n, 51);
+        G_unsatisfiedNAsFromOtherSectors[n] = add.additionalOutputInput(n, 49);
+        G_unsatisfiedNAsFromOtherSectorsPrevYear[n] = add.additionalOutputInput(n, 52);
+        // what routing() reloads on the first day after a checkpoint (:1706-1743), as far as use_alloc 0 has it
+        G_dailyRemainingUse[n] = add.additionalOutputInput(n, 35);
+        G_withdrawalIrrigFromSwb[n] = add.additionalOutputInput(n, 25);
+        G_consumptiveUseIrrigFromSwb[n] = add.additionalOutputInput(n, 26);
         const double f = ((eng.geo.areaOfCellByArrayPos(n) * (eng.geo.G_contfreq[n] / 100.)) / 1000000.);
         Cell &c = st.cell(n);
         G_locLakeStorage[n] = c.locallake(0) * f; G_locWetlStorage[n] = c.localwetland(0) * f; G_gloLakeStorage[n] = c.globallake(0) * f;
@@ -462,6 +486,13 @@ void routingClass::setLakeWetlToMaximum(short) {  // :5647-5720 (resYearOpt 0)
 
 void routingClass::annualInit(short year, int start_month, AdditionalOutputInputFile &additionalOutIn) {  // :979-1415 (resYearOpt 0: G_RES_<reference year>)
     const int ng = eng.ncell, ref = eng.options.resYearReference;
+    if (additionalOutIn.additionalfilestatus == 0 || start_month == 1 || year > eng.options.start_year)  // :986-1008
+        for (int n = 0; n < ng; n++) {
+            G_UnsatisfiedUsePrevYear[n] = G_totalUnsatisfiedUse[n];
+            G_unsatisfiedNAsFromIrrigPrevYear[n] = G_unsatisfiedNAsFromIrrig[n];
+            G_unsatisfiedNAsFromOtherSectorsPrevYear[n] = G_unsatisfiedNAsFromOtherSectors[n];
+            G_reducedReturnFlowPrevYear[n] = G_reducedReturnFlow[n];
+        }
     for (int n = 0; n < ng; n++) { G_reservoir_area[n] = 0.; G_stor_cap[n] = 0.; }
     for (int n = 0; n < ng; n++)
         if (G_reg_lake_status[n] == 1) { G_reservoir_area[n] = G_reservoir_area_full[n]; G_stor_cap[n] = G_stor_cap_full[n]; }
@@ -492,6 +523,101 @@ void routingClass::annualInit(short year, int start_month, AdditionalOutputInput
             if (G_glo_res[n] - G_glores_prevyear[n] > 0.)
                 throw std::runtime_error("routing.annualInit: a reservoir fraction grew against the previous year (cell " + std::to_string(n + 1) +
                                          "): reservoir commissioning (resYearOpt 1, routing.cpp:1310-1412) is outside the implemented options");
+    }
+}
+
+// ---- water use (subtract_use 2) --------------------------------------------------------------
+void routingClass::dailyNUInit(const std::string &dir, short new_year, calibParamClass &calParam) {  // :884-977 (aggrNUsGloLakResOpt 0)
+    const int ng = eng.ncell;
+    const short numberOfDaysInMonth[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    for (auto *g : {&G_dailyNUs, &G_dailyNUg, &G_monthlyWUIrrigFromSwb, &G_monthlyCUIrrigFromSwb}) g->initialize(ng);
+    const std::string y = std::to_string(new_year);
+    G_dailyNUs.read(dir + "/G_NETUSE_SW_m3_" + y + ".12.UNF0");
+    G_dailyNUg.read(dir + "/G_NETUSE_GW_m3_" + y + ".12.UNF0");
+    G_monthlyWUIrrigFromSwb.read(dir + "/G_IRRIG_WITHDRAWAL_USE_SW_m3_" + y + ".12.UNF0");
+    G_monthlyCUIrrigFromSwb.read(dir + "/G_IRRIG_CONS_USE_SW_m3_" + y + ".12.UNF0");
+    for (int n = 0; n < ng; n++)
+        for (short month = 0; month < 12; month++) {
+            G_dailyNUs(n, month) = calParam.getValue(M_NETABSSW, n) * G_dailyNUs(n, month);
+            G_dailyNUg(n, month) = calParam.getValue(M_NETABSGW, n) * G_dailyNUg(n, month);
+        }
+    for (short month = 0; month <= 11; month++)
+        for (int n = 0; n <= ng - 1; n++) {
+            G_dailyNUs(n, month) = G_dailyNUs(n, month) / (1000000000. * (double)numberOfDaysInMonth[month]);
+            G_dailyNUg(n, month) = G_dailyNUg(n, month) / (1000000000. * (double)numberOfDaysInMonth[month]);
+        }
+}
+
+void routingClass::pushWaterUseMonth(short month) {  // what calcNextDay_M (:7432-7440) and :3907-3908 read on every day of the month
+    const int ng = eng.ncell;
+    const short numberOfDaysInMonth[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    Grid<double> nus(ng), nug(ng), wusi(ng), cusi(ng);
+    for (int n = 0; n < ng; n++) {
+        nus[n] = G_dailyNUs(n, month);
+        nug[n] = G_dailyNUg(n, month);
+        wusi[n] = G_monthlyWUIrrigFromSwb(n, month) / (1000000000. * (double)numberOfDaysInMonth[month]);
+        cusi[n] = G_monthlyCUIrrigFromSwb(n, month) / (1000000000. * (double)numberOfDaysInMonth[month]);
+    }
+    eng.set("wu_nus_month", nus); eng.set("wu_nug_month", nug); eng.set("wu_wusi_month", wusi); eng.set("wu_cusi_month", cusi);
+}
+
+void routingClass::pullWaterUse() {
+    Engine &e = eng;
+    e.get("wu_total_unsatisfied", G_totalUnsatisfiedUse); e.get("wu_uns_irr", G_unsatisfiedNAsFromIrrig);
+    e.get("wu_uns_oth", G_unsatisfiedNAsFromOtherSectors); e.get("wu_red_rf", G_reducedReturnFlow);
+    e.get("wu_daily_remaining", G_dailyRemainingUse); e.get("wu_wusi", G_withdrawalIrrigFromSwb);
+    e.get("wu_cusi", G_consumptiveUseIrrigFromSwb); e.get("wu_actual_use", G_actualUse);
+}
+
+void routingClass::pushWaterUseState() {
+    Engine &e = eng;
+    e.set("wu_total_unsatisfied", G_totalUnsatisfiedUse); e.set("wu_uns_irr", G_unsatisfiedNAsFromIrrig);
+    e.set("wu_uns_oth", G_unsatisfiedNAsFromOtherSectors); e.set("wu_red_rf", G_reducedReturnFlow);
+    e.set("wu_daily_remaining", G_dailyRemainingUse); e.set("wu_wusi", G_withdrawalIrrigFromSwb);
+    e.set("wu_cusi", G_consumptiveUseIrrigFromSwb); e.set("wu_actual_use", G_actualUse);
+}
+
+void routingClass::annualWaterUsePostProcessing(short, AdditionalOutputInputFile &add) {  // :5246-5306 (host grids synchronised by the caller)
+    for (int n = 0; n <= eng.ncell - 1; n++) {
+        if (G_totalUnsatisfiedUse[n] < G_UnsatisfiedUsePrevYear[n]) {
+            G_UnsatisfiedUsePrevYear[n] = G_totalUnsatisfiedUse[n];
+            G_unsatisfiedNAsFromIrrigPrevYear[n] = G_unsatisfiedNAsFromIrrig[n];
+            G_unsatisfiedNAsFromOtherSectorsPrevYear[n] = G_unsatisfiedNAsFromOtherSectors[n];
+            G_reducedReturnFlowPrevYear[n] = G_reducedReturnFlow[n];
+            G_unsatisfiedNAsFromIrrig[n] = 0.;
+            G_unsatisfiedNAsFromOtherSectors[n] = 0.;
+            G_reducedReturnFlow[n] = 0.;
+            G_totalUnsatisfiedUse[n] = 0.;
+        } else {
+            G_totalUnsatisfiedUse[n] -= G_UnsatisfiedUsePrevYear[n];
+            G_unsatisfiedNAsFromIrrig[n] -= G_unsatisfiedNAsFromIrrigPrevYear[n];
+            G_unsatisfiedNAsFromOtherSectors[n] -= G_unsatisfiedNAsFromOtherSectorsPrevYear[n];
+            G_reducedReturnFlow[n] -= G_reducedReturnFlowPrevYear[n];
+            if ((G_unsatisfiedNAsFromIrrig[n] + G_unsatisfiedNAsFromOtherSectors[n]) < 0) {
+                G_unsatisfiedNAsFromIrrig[n] = 0;
+                G_unsatisfiedNAsFromOtherSectors[n] = 0;
+                G_reducedReturnFlow[n] = 0;
+            } else if (G_unsatisfiedNAsFromOtherSectors[n] < 0) {
+                G_unsatisfiedNAsFromIrrig[n] += G_unsatisfiedNAsFromOtherSectors[n];
+                G_unsatisfiedNAsFromOtherSectors[n] = 0;
+            } else if (G_unsatisfiedNAsFromIrrig[n] < 0) {
+                G_unsatisfiedNAsFromOtherSectors[n] += G_unsatisfiedNAsFromIrrig[n];
+                G_unsatisfiedNAsFromIrrig[n] = 0;
+                G_reducedReturnFlow[n] = 0;
+            }
+            if (G_reducedReturnFlow[n] > 0) {
+                G_reducedReturnFlow[n] = 0;
+                G_unsatisfiedNAsFromIrrig[n] = 0;
+            }
+        }
+        add.additionalOutputInput(n, 3) = G_totalUnsatisfiedUse[n];
+        add.additionalOutputInput(n, 4) = G_UnsatisfiedUsePrevYear[n];
+        add.additionalOutputInput(n, 50) = G_reducedReturnFlowPrevYear[n];
+        add.additionalOutputInput(n, 51) = G_unsatisfiedNAsFromIrrigPrevYear[n];
+        add.additionalOutputInput(n, 52) = G_unsatisfiedNAsFromOtherSectorsPrevYear[n];
+        add.additionalOutputInput(n, 38) = G_reducedReturnFlow[n];
+        add.additionalOutputInput(n, 39) = G_unsatisfiedNAsFromIrrig[n];
+        add.additionalOutputInput(n, 49) = G_unsatisfiedNAsFromOtherSectors[n];
     }
 }
 
@@ -609,6 +735,10 @@ void Engine::push_static() {
     table("lct_albedo_snow", dailyWaterBalance.albedoSnow_lct, sizeof dailyWaterBalance.albedoSnow_lct);
     table("lct_ddf", dailyWaterBalance.ddf_lct, sizeof dailyWaterBalance.ddf_lct);
     table("lct_emissivity", dailyWaterBalance.emissivity_lct, sizeof dailyWaterBalance.emissivity_lct);
+    if (options.subtract_use > 0) {
+        set("wu_frgi", routing.G_fractreturngw_irrig);
+        set("wu_alloc_coeff", routing.G_alloc_coeff);
+    }
 }
 
 void Engine::push_state() {
@@ -732,6 +862,12 @@ static void fill_additional(Engine &E, AdditionalOutputInputFile &add, short mon
         col(33) = r.G_fswbLandAreaFracNextTimestep[n]; col(36) = r.G_fGloLake[n];
         col(44) = (month == 11) ? r.G_glo_res[n] : r.G_glores_prevyear[n];
         col(45) = fll[n]; col(47) = flw[n]; col(46) = fgw[n];
+        if (E.options.subtract_use > 0) {  // :5025-5029, 5231-5240 (use_alloc 0: the allocation columns stay 0)
+            col(3) = r.G_totalUnsatisfiedUse[n]; col(4) = r.G_UnsatisfiedUsePrevYear[n]; col(50) = r.G_reducedReturnFlowPrevYear[n];
+            col(51) = r.G_unsatisfiedNAsFromIrrigPrevYear[n]; col(52) = r.G_unsatisfiedNAsFromOtherSectorsPrevYear[n];
+            col(35) = r.G_dailyRemainingUse[n]; col(38) = r.G_reducedReturnFlow[n]; col(39) = r.G_unsatisfiedNAsFromIrrig[n];
+            col(49) = r.G_unsatisfiedNAsFromOtherSectors[n]; col(25) = r.G_withdrawalIrrigFromSwb[n]; col(26) = r.G_consumptiveUseIrrigFromSwb[n];
+        }
     }
 }
 
@@ -740,7 +876,9 @@ long integrate_wghm(const std::string &config_file, int ncell, int device, doubl
     ModelState S(ncell);
     calibParamClass cal;
     load_start_state(cfg, ncell, S, cal);
-    Engine E(ncell, device, S.additionalOutIn.additionalfilestatus);
+    optionClass opt;
+    opt.init(cfg);
+    Engine E(ncell, device, S.additionalOutIn.additionalfilestatus, opt.subtract_use);
     E.calParam = cal;
     return run_model(E, cfg, S, seconds_day_loop);
 }
@@ -764,7 +902,13 @@ long run_model(Engine &E, const ConfigFile &cfg, ModelStateRef S, double *second
     for (short year = E.options.start_year; year <= E.options.end_year; year++) {
         E.dailyWaterBalance.annualInit();
         E.routing.annualInit(year, cfg.startMonth, additionalOutIn);
-        if (!pushed) { E.push_static(); E.push_state(); pushed = true; }  // (yearly reservoir changes do not occur with resYearOpt 0)
+        if (!pushed) {  // (yearly reservoir changes do not occur with resYearOpt 0)
+            E.push_static();
+            E.push_state();
+            if (E.options.subtract_use > 0) E.routing.pushWaterUseState();
+            pushed = true;
+        }
+        if (E.options.subtract_use > 0) E.routing.dailyNUInit(E.options.water_use_dir, year, E.calParam);  // integrateWGHM.cpp:645-647
         if (yearly_forcing) E.set_forcing_year(year);  // integrateWGHM.cpp:565-568
         short day = 0;
         if (year == cfg.startYear) for (int m = 1; m < cfg.startMonth; m++) day += number_of_days_in_month[m - 1];
@@ -776,6 +920,7 @@ long run_model(Engine &E, const ConfigFile &cfg, ModelStateRef S, double *second
         }
         for (short month = start_month - 1; month < end_month; month++) {
             if (!yearly_forcing) E.set_forcing_month(month + 1, year);
+            if (E.options.subtract_use > 0) E.routing.pushWaterUseMonth(month);  // calcNextDay_M, integrateWGHM.cpp:794-796
             wghmState.resetCells(number_of_days_in_month[month]);
             E.check(wgk_month_begin(E.ctx), "wgk_month_begin");  // the post-pass keeps what the month's checkpoint needs
             const auto t0 = std::chrono::steady_clock::now();
@@ -805,7 +950,12 @@ long run_model(Engine &E, const ConfigFile &cfg, ModelStateRef S, double *second
                     wghmState.cell(n).soil(dom - 1) = E.dailyWaterBalance.G_soilWaterContent[n] * laf / cf;
                 }
             }
+            if (E.options.subtract_use > 0) E.routing.pullWaterUse();
             fill_additional(E, additionalOutIn, month);
+            if (E.options.subtract_use > 0 && month == 11) {  // integrateWGHM.cpp:944: the year's use bookkeeping
+                E.routing.annualWaterUsePostProcessing(year, additionalOutIn);
+                E.routing.pushWaterUseState();
+            }
             if (year == E.options.end_year && month + 1 == end_month) {  // :853-901
                 if (!cfg.outputmeanfile.empty()) wghmState.saveMean(cfg.outputmeanfile);
                 if (!cfg.outputlastdayfile.empty()) wghmState.saveDay(cfg.outputlastdayfile, number_of_days_in_month[month] - 1);
@@ -895,7 +1045,9 @@ void integrate_wghm_(const char *s, wg::ConfigFile *&configFile, wg::WghmStateFi
     const int ncell = calParam->ncell();
     const char *dev = getenv("WGK_DEVICE");
     {
-        Engine E(ncell, dev ? atoi(dev) : 0, additionalOutIn->additionalfilestatus);
+        optionClass opt;
+        opt.init(*configFile);
+        Engine E(ncell, dev ? atoi(dev) : 0, additionalOutIn->additionalfilestatus, opt.subtract_use);
         E.calParam = *calParam;
         ModelStateRef S{*wghmState, *additionalOutIn, *snow_in_elevation};
         run_model(E, *configFile, S, nullptr);
@@ -952,13 +1104,16 @@ void *wg_host_create_context(const char *config_file, int ncell, int device, cha
         wg::ModelState S(ncell);
         wg::calibParamClass cal;
         wg::load_start_state(cfg, ncell, S, cal);
-        wg::Engine E(ncell, device, S.additionalOutIn.additionalfilestatus);
+        wg::optionClass opt;
+        opt.init(cfg);
+        wg::Engine E(ncell, device, S.additionalOutIn.additionalfilestatus, opt.subtract_use);
         E.calParam = cal;
         wg::initialize_model(E, cfg, S);
         E.dailyWaterBalance.annualInit();
         E.routing.annualInit(E.options.start_year, cfg.startMonth, S.additionalOutIn);
         E.push_static();
         E.push_state();
+        if (E.options.subtract_use > 0) E.routing.pushWaterUseState();
         E.check(wgk_forcing_reserve(E.ctx, 31, 0), "wgk_forcing_reserve");
         wgk_ctx *ctx = E.ctx;
         E.ctx = nullptr;  // ownership moves to the caller

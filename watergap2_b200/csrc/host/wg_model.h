@@ -51,7 +51,7 @@ struct ConfigFile {  // configFile.cpp:20-231
     ConfigFile(const std::string &file, int year, int month, const std::string &progName);  // configFile.cpp: "OL" keeps the file's dates
     std::string startvaluefile, parameterfile, snowInElevationfile, additionalfile, outputmeanfile, outputlastdayfile,
         outputsnowlastdayfile, outputadditionalfile, runtimeoptionsfile, outputoptionsfile, routingoptionsfile, stationsfile,
-        inputDir, outputDir, climateDir, routingDir;
+        inputDir, outputDir, climateDir, routingDir, waterUseDir;
     int startMonth = 0, startYear = 0, endMonth = 0, endYear = 0, timeStep = 0, numInitYears = 0;
 };
 
@@ -60,10 +60,10 @@ struct optionClass {  // option.cpp:173-620, OPTIONS.DAT order
     int v[36] = {0};
     int &fileEndianType = v[0], &basin = v[1], &grid_store = v[2], &time_series = v[5], &cloud = v[6], &intercept = v[7],
         &calc_albedo = v[8], &petOpt = v[9], &use_kc = v[10], &rout_prepare = v[12], &riverveloOpt = v[14],
-        &subtract_use = v[15], &clclOpt = v[18], &permaOpt = v[19], &resOpt = v[20], &statcorrOpt = v[21],
-        &aridareaOpt = v[22], &fractionalRoutingOpt = v[23], &riverEvapoOpt = v[24], &resYearOpt = v[27],
+        &subtract_use = v[15], &use_alloc = v[16], &delayedUseSatisfaction = v[17], &clclOpt = v[18], &permaOpt = v[19], &resOpt = v[20], &statcorrOpt = v[21],
+        &aridareaOpt = v[22], &fractionalRoutingOpt = v[23], &riverEvapoOpt = v[24], &aggrNUsGloLakResOpt = v[25], &resYearOpt = v[27],
         &resYearReference = v[28], &antNatOpt = v[31], &calc_wtemp = v[34], &glacierOpt = v[35];
-    std::string input_dir, output_dir, climate_dir, routing_dir;
+    std::string input_dir, output_dir, climate_dir, routing_dir, water_use_dir;
     int start_year = 0, end_year = 0;
     void require_canonical() const;  // throws for option values outside the implemented hot path
 };
@@ -124,6 +124,18 @@ class routingClass {
     }
     void pull();
     void updateGloResPrevYear_pct() { G_glores_prevyear = G_glo_res; }
+    // water use (subtract_use 2): the year's net abstractions (routing.cpp:884-977), the month's daily values for the
+    // device (calcNextDay_M :7432-7440 is the same value on every day of a month), the year-end bookkeeping (:5246-5306)
+    void dailyNUInit(const std::string &input_directory, short new_year, calibParamClass &);
+    void pushWaterUseMonth(short month);
+    void pullWaterUse();
+    void pushWaterUseState();
+    void annualWaterUsePostProcessing(short year, AdditionalOutputInputFile &);
+    Grid<double, 12> G_dailyNUs, G_dailyNUg, G_monthlyWUIrrigFromSwb, G_monthlyCUIrrigFromSwb;
+    Grid<double, 5> G_alloc_coeff;
+    Grid<double> G_fractreturngw_irrig, G_totalUnsatisfiedUse, G_UnsatisfiedUsePrevYear, G_unsatisfiedNAsFromIrrig,
+        G_unsatisfiedNAsFromIrrigPrevYear, G_unsatisfiedNAsFromOtherSectors, G_unsatisfiedNAsFromOtherSectorsPrevYear, G_reducedReturnFlow,
+        G_reducedReturnFlowPrevYear, G_dailyRemainingUse, G_withdrawalIrrigFromSwb, G_consumptiveUseIrrigFromSwb, G_actualUse;
     Grid<double> G_statCorrFact, G_landAreaFrac, G_landAreaFracNextTimestep, G_landAreaFracPrevTimestep, G_locLakeStorage,
         G_locWetlStorage, G_gloLakeStorage, G_gloWetlStorage, G_gloResStorage, G_riverStorage, G_groundwaterStorage,
         G_locLakeAreaReductionFactor, G_locWetlAreaReductionFactor, G_gloLakeEvapoReductionFactor,
@@ -148,7 +160,7 @@ class routingClass {
 // Everything the reference keeps in process globals (globals.cpp:7-33), per model instance.
 class Engine {
   public:
-    Engine(int ncell, int device = 0, int restart = 0);  // device < 0: host-side initialisation only (no context; tests of the init logic)
+    Engine(int ncell, int device = 0, int restart = 0, int subtract_use = 0);  // device < 0: host-side initialisation only (no context; tests of the init logic)
     ~Engine();
     int ncell;
     wgk_ctx *ctx = nullptr;
