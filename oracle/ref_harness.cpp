@@ -294,14 +294,48 @@ static void run_enkf(const std::string &dir, ConfigFile *&configFile, WghmStateF
         c.groundwater(0) = meanf[i * 10 + 9];
     }
     long oy = 0, total_nr_calPar = 26, calpar_size = 0, ny = n * 10, step = 0, total_steps = 100, year = year_, month = month_;
+    // optional parameter half (extractsub.cpp:81-340, enKF2wghmState.cpp:127-431): calibration units of the region's cells
+    //   calpar_index.bin int32 [nunit][26] (1: parameter is in the state vector), groupmatrixindex.bin int32 [nunit][n]
+    //   (0 or the 1-based cell number), calpar_range.bin f64 [2][26], calpar_perturb.bin f64 [number of ones]
+    std::vector<int> calpar_index, gmi;
+    std::vector<double> calpar_range, calpar_pert;
+    {
+        FILE *f = fopen((dir + "/calpar_index.bin").c_str(), "rb");
+        if (f) {
+            fseek(f, 0, SEEK_END);
+            const long cnt = ftell(f) / 4;
+            fseek(f, 0, SEEK_SET);
+            calpar_index.resize(cnt);
+            if (fread(calpar_index.data(), 4, cnt, f) != (size_t)cnt) exit(2);
+            fclose(f);
+            oy = cnt / 26;
+            gmi.resize(oy * n);
+            f = fopen((dir + "/groupmatrixindex.bin").c_str(), "rb");
+            if (!f || fread(gmi.data(), 4, gmi.size(), f) != gmi.size()) { fprintf(stderr, "enkf: groupmatrixindex.bin\n"); exit(2); }
+            fclose(f);
+            calpar_range = read_f64(dir + "/calpar_range.bin");
+            calpar_pert = read_f64(dir + "/calpar_perturb.bin");
+            for (int v : calpar_index) calpar_size += v == 1;
+            if ((long)calpar_pert.size() != calpar_size || calpar_range.size() != 52) { fprintf(stderr, "enkf: parameter inputs\n"); exit(2); }
+        }
+    }
     double *output = nullptr;
-    extract_sub_(ids_file.c_str(), wghmState, output, &oy, calParam, &total_nr_calPar, &calpar_size, nullptr, "", wghmMean, nullptr);
+    extract_sub_(ids_file.c_str(), wghmState, output, &oy, calParam, &total_nr_calPar, &calpar_size,
+                 calpar_index.empty() ? nullptr : calpar_index.data(), "", wghmMean, gmi.empty() ? nullptr : gmi.data());
     put("enkf_extract", 9000, "f64", n * 10, output, 8);
-    std::vector<double> prediction(output, output + n * 10), field(n * 10);
+    std::vector<double> prediction(output, output + n * 10 + calpar_size), field(n * 10 + calpar_size);
     for (long k = 0; k < n * 10; k++) field[k] = prediction[k] + pert[k];
+    for (long k = 0; k < calpar_size; k++) field[n * 10 + k] = prediction[n * 10 + k] + calpar_pert[k];
     delete[] output;
+    ny = n * 10 + calpar_size;
     put("enkf_field", 9000, "f64", n * 10, field.data(), 8);
     put("enkf_prediction", 9000, "f64", n * 10, prediction.data(), 8);
+    if (calpar_size > 0) {
+        put("enkf_par_extract", 9000, "f64", calpar_size, prediction.data() + n * 10, 8);
+        put("enkf_par_field", 9000, "f64", calpar_size, field.data() + n * 10, 8);
+        configFile->outputparameter = dir + "/parameters_out.json";
+        if (configFile->calibrationfile.empty()) configFile->calibrationfile = configFile->parameterfile;  // the run's own JSON
+    }
     // monthly mean of every cell as the reference forms it (Cell::mean, wghmStateFile.cpp:711)
     {
         std::vector<double> mm((size_t)ng * 10);
@@ -321,8 +355,9 @@ static void run_enkf(const std::string &dir, ConfigFile *&configFile, WghmStateF
     WghmStateFile *wghmStateMean = nullptr;
     const std::string s2 = dir + "/";
     enkf_wghmstate_(ids_file.c_str(), field.data(), prediction.data(), configFile, wghmState, additionalOutIn, snow, &step, &total_steps,
-                    &year, &month, &ny, factor, wghmStateMean, s2.c_str(), calParam, &calpar_size, "", "", "", wghmMean, nullptr, &oy,
-                    &total_nr_calPar, nullptr, nullptr);
+                    &year, &month, &ny, factor, wghmStateMean, s2.c_str(), calParam, &calpar_size, (dir + "/calpar").c_str(),
+                    (dir + "/arcid_gcrc.txt").c_str(), "", wghmMean, calpar_range.empty() ? nullptr : calpar_range.data(), &oy,
+                    &total_nr_calPar, calpar_index.empty() ? nullptr : calpar_index.data(), gmi.empty() ? nullptr : gmi.data());
     std::vector<double> last(n * 10), sie(n * 101);
     for (long i = 0; i < n; i++) {
         Cell &c = wghmState->cell(ids[i] - 1);

@@ -315,6 +315,53 @@ def test_pdaf_bridge_lookalikes_equal_reference(host, golden):
     assert (mean_after[:, 1] <= 1000.).all() and (mean_after[:, [0, 1, 2, 4, 6, 7, 8]] >= 0.).all()
 
 
+def test_pdaf_parameter_half_equals_reference(host, tmp_path):
+    """parameter half of the PDAF exchange (extractsub.cpp:81-340, enKF2wghmState.cpp:127-431, parameterJsonFile.cpp) against
+    the compiled reference (tests/golden/ref_ng1000_enkf_par.npz): the appended part of the extract vector bit-equal, the
+    time-evolution text file byte-identical, the parameter JSON of the next cycle byte-identical apart from its creation time,
+    and that JSON read back by the product's own calibParamClass::readJson"""
+    import ctypes
+    import json
+    from oracle import synth_world as sw
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_ng1000_enkf_par.npz"))
+    ng = 1000
+    p_in = g["parameters_in"]
+    js = {"ng_param": ng, "gcrc_cellnumber": list(range(1, ng + 1)), "arc_id": list(range(1, ng + 1))}
+    for k, name in enumerate(sw.PARAM_NAMES):
+        js[name] = [float(v) for v in p_in[k]]
+    pfile = tmp_path / "parameters.json"
+    pfile.write_text(json.dumps(js))
+    arc = tmp_path / "arcid_gcrc.txt"
+    arc.write_text("arcid gcrc\n" + "".join(f"{100000 + 3 * c} {c + 1}\n" for c in range(ng)))
+    ids = np.ascontiguousarray(g["cells"] + 1, np.int32)
+    index, gmi = np.ascontiguousarray(g["calpar_index"], np.int32), np.ascontiguousarray(g["groupmatrixindex"], np.int32)
+    rng_, pert = np.ascontiguousarray(g["calpar_range"]), np.ascontiguousarray(g["calpar_perturb"])
+    nunit, npar = index.shape[0], int((index == 1).sum())
+    extract, field, mat = np.zeros(npar), np.zeros(npar), np.zeros((26, nunit))
+    txt, out = tmp_path / "calpar_1901-01.txt", tmp_path / "parameters_out.json"
+    host.wg_host_pdaf_parameters.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4 + \
+        [ctypes.c_char_p] * 3 + [ctypes.c_void_p] * 3
+    rc = host.wg_host_pdaf_parameters(str(pfile).encode(), ids.size, ids.ctypes.data, nunit, index.ctypes.data, gmi.ctypes.data,
+                                      rng_.ctypes.data, pert.ctypes.data, str(txt).encode(), str(out).encode(), str(arc).encode(),
+                                      extract.ctypes.data, field.ctypes.data, mat.ctypes.data)
+    assert rc == npar
+    assert np.array_equal(extract, g["par_extract"]) and np.array_equal(field, g["par_field"])
+    assert txt.read_bytes() == bytes(g["cda_txt"])
+    # clamped where the analysis left the range (root depth of unit 0 above, outflow coefficient below, gamma of unit 1 below)
+    assert mat[3, 0] == rng_[1, 3] and mat[7, 0] == rng_[0, 7] and mat[0, 1] == rng_[0, 0]
+    lines = [l for l in out.read_bytes().split(b"\n") if not l.startswith(b'"creation_datetime"')]
+    assert b"\n".join(lines) == bytes(g["json"])
+    # the next cycle reads this file (initialize_wghm_ -> calibParamClass::readJson): valid JSON, cells of a unit carry its value
+    back = json.loads(out.read_text())
+    assert back["ng_param"] == ng and len(back["arc_id"]) == ng
+    for u in range(nunit):
+        cells = gmi[u][gmi[u] > 0] - 1
+        for j in (0, 3, 7, 22, 25):
+            assert np.allclose(np.array(back[sw.PARAM_NAMES[j]])[cells], mat[j, u], rtol=1e-5)
+    outside = np.setdiff1d(np.arange(ng), gmi[gmi > 0] - 1)
+    assert np.allclose(np.array(back[sw.PARAM_NAMES[0]])[outside], p_in[0][outside], rtol=1e-5)
+
+
 def test_calibGammaClass_cpp_equals_python_on_random_scenarios(host, tmp_path):
     """the two host implementations of the reference's gamma search (C++ calibGammaClass, Python GammaCalibration), both pinned
     on the seven golden scenarios, against each other on 150 random response curves, start values and observation gaps: the same
@@ -387,7 +434,7 @@ def test_calibGammaClass_cpp_equals_python_on_random_scenarios(host, tmp_path):
 
 def test_b1_ffi_symbols_exported(host):
     """B1: the reference's own FFI names (initializeWGHM.h:14, integrateWGHM.h:12) are exported by libwghost.so"""
-    for name in ("initialize_wghm_", "integrate_wghm_", "wg_host_integrate", "wg_host_init_dump"):
+    for name in ("initialize_wghm_", "integrate_wghm_", "extract_sub_", "enkf_wghmstate_", "wg_host_integrate", "wg_host_init_dump"):
         assert hasattr(host, name), name
 
 
@@ -435,6 +482,84 @@ def test_b1_entry_points_run_the_model(host, world3000, tmp_path):
     assert st.value and cal.value and add.value and snow.value and cf.value  # the caller keeps the objects
     for k in files:
         assert filecmp.cmp(os.path.join(out, k), os.path.join(out, "drv_" + k), shallow=False), k
+
+
+@pytest.mark.gpu
+def test_pdaf_cycle_through_the_fortran_symbols(host, world1000, tmp_path):
+    """One assimilation cycle the way PDAF's Fortran side drives it, on the month the compiled reference's cycle was recorded on
+    (tests/golden/ref_ng1000_enkf.npz, ref_ng1000_enkf_par.npz): initialize_wghm_ -> integrate_wghm_ (January 1901 on the GPU) ->
+    extract_sub_ -> analysis -> enkf_wghmstate_.  The state vector, the updated last day and snow in elevation follow the
+    reference within the free-run bound of a month (1e-6 relative); the parameter half is CPU arithmetic on the parameter file and
+    is byte-identical; the files of the next cycle are written."""
+    from oracle import synth_world as sw
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_ng1000_enkf.npz"))
+    gp = np.load(os.path.join(ROOT, "tests", "golden", "ref_ng1000_enkf_par.npz"))
+    tmp = str(tmp_path)
+    ng = 1000
+    sw.write_world(world1000, tmp, (1901, 1901), (1, 1))
+    out = os.path.join(tmp, "output")
+    cfg = os.path.join(tmp, "config.txt")
+    with open(cfg, "a") as f:
+        f.write(f"output_state_mean {out}/mean_001.txt\noutput_calibration_parameters {out}/parameters_out.json\n"
+                f"calibration_parameters {tmp}/parameters.json\n")
+    cells = g["cells"]
+    assert np.array_equal(cells, gp["cells"])
+    n = cells.size
+    ids_file = os.path.join(tmp, "ids.txt")
+    open(ids_file, "w").write("ID lon lat\n" + "".join(f"{c + 1} 0.0 0.0\n" for c in cells))
+    arc = os.path.join(tmp, "arcid_gcrc.txt")
+    open(arc, "w").write("arcid gcrc\n" + "".join(f"{100000 + 3 * c} {c + 1}\n" for c in range(ng)))
+    mean_file = os.path.join(tmp, "temporal_mean.txt")   # WghmStateFile text: title, column header, ID TWS 10 compartments
+    mf = np.zeros((ng, 10))
+    mf[cells] = g["mean_field"]
+    with open(mean_file, "w") as f:
+        f.write("WGHM water storage states\nID TWS ...\n")
+        for c in range(ng):
+            f.write(f"{c + 1} {mf[c].sum()!r} " + " ".join(repr(float(v)) for v in mf[c]) + "\n")
+    vp = ctypes.c_void_p
+    for fn in ("initialize_wghm_", "integrate_wghm_", "extract_sub_", "enkf_wghmstate_"):
+        getattr(host, fn).restype = None
+    st, cal, add, snow, mean, cf = vp(), vp(), vp(), vp(), vp(), vp()
+    y, m, step, total = ctypes.c_long(1901), ctypes.c_long(1), ctypes.c_long(0), ctypes.c_long(100)
+    host.initialize_wghm_(cfg.encode(), ctypes.byref(st), ctypes.byref(cal), ctypes.byref(add), ctypes.byref(snow), ctypes.byref(y), ctypes.byref(m),
+                          b"PDAF", mean_file.encode(), ctypes.byref(mean))
+    host.integrate_wghm_(cfg.encode(), ctypes.byref(cf), ctypes.byref(st), ctypes.byref(cal), ctypes.byref(add), ctypes.byref(snow),
+                         ctypes.byref(step), ctypes.byref(total), ctypes.byref(y), ctypes.byref(m), b"PDAF")
+    index, gmi = np.ascontiguousarray(gp["calpar_index"], np.int32), np.ascontiguousarray(gp["groupmatrixindex"], np.int32)
+    rng_ = np.ascontiguousarray(gp["calpar_range"])
+    npar = int((index == 1).sum())
+    oy, total_par, calpar_size = ctypes.c_long(index.shape[0]), ctypes.c_long(26), ctypes.c_long(npar)
+    outp = ctypes.POINTER(ctypes.c_double)()
+    host.extract_sub_(ids_file.encode(), ctypes.byref(st), ctypes.byref(outp), ctypes.byref(oy), ctypes.byref(cal), ctypes.byref(total_par),
+                      ctypes.byref(calpar_size), index.ctypes.data_as(vp), b"", ctypes.byref(mean), gmi.ctypes.data_as(vp))
+    vec = np.ctypeslib.as_array(outp, shape=(n * 10 + npar,)).copy()
+    ref = g["enkf_extract"].ravel()
+    assert np.allclose(vec[:n * 10], ref, rtol=1e-6, atol=1e-9), np.abs(vec[:n * 10] - ref).max()
+    assert np.array_equal(vec[n * 10:], gp["par_extract"])
+    field = vec.copy()
+    field[:n * 10] += g["perturb"].ravel()
+    field[n * 10:] += gp["calpar_perturb"]
+    ny = ctypes.c_long(field.size)
+    factor, smean = ctypes.POINTER(ctypes.c_double)(), vp()
+    host.enkf_wghmstate_(ids_file.encode(), field.ctypes.data_as(vp), vec.ctypes.data_as(vp), ctypes.byref(cf), ctypes.byref(st), ctypes.byref(add),
+                         ctypes.byref(snow), ctypes.byref(step), ctypes.byref(total), ctypes.byref(y), ctypes.byref(m), ctypes.byref(ny),
+                         ctypes.byref(factor), ctypes.byref(smean), (out + "/").encode(), ctypes.byref(cal), ctypes.byref(calpar_size),
+                         (out + "/calpar").encode(), arc.encode(), b"", ctypes.byref(mean), rng_.ctypes.data_as(vp), ctypes.byref(oy),
+                         ctypes.byref(total_par), index.ctypes.data_as(vp), gmi.ctypes.data_as(vp))
+    assert st.value and cal.value and cf.value and not smean.value  # the objects live on for the next cycle
+    last = np.loadtxt(os.path.join(out, "wghm_state_lastday.txt"), skiprows=2)
+    assert last.shape == (ng, 12)
+    ref = g["enkf_lastday"]
+    got = last[cells, 2:]
+    assert np.allclose(got, ref, rtol=1e-6, atol=1e-9), np.abs(got - ref).max()
+    assert np.allclose(last[:, 1], last[:, 2:].sum(1), rtol=1e-12, atol=1e-9)  # TWS column
+    sn = np.loadtxt(os.path.join(out, "snow_lastday.txt"), skiprows=1)[cells][:, -100:]  # id, 101 values per cell
+    assert np.allclose(sn, g["enkf_snow_elev"][:, 1:], rtol=1e-6, atol=1e-9)
+    for fn in ("mean_001_1901-01.txt", "states_mean_update_001_1901-01.txt", "additional_lastday.txt"):
+        assert os.path.getsize(os.path.join(out, fn)) > 0, fn
+    assert open(os.path.join(out, "calpar_1901-01.txt"), "rb").read() == bytes(gp["cda_txt"])
+    lines = [l for l in open(os.path.join(out, "parameters_out.json"), "rb").read().split(b"\n") if not l.startswith(b'"creation_datetime"')]
+    assert b"\n".join(lines) == bytes(gp["json"])
 
 
 def test_product_topology_builder_full_size_equals_oracle(host, oracle_lib, tmp_path):

@@ -15,7 +15,7 @@ namespace wg {
 // ------------------------------------------------------------------------------------------
 // parameters / config / options
 // ------------------------------------------------------------------------------------------
-static const char *kParamNames[26] = {  // calib_param.cpp:140-171
+const char *const kParamNames[26] = {  // calib_param.cpp:140-171
     "gammaHBV_runoff_coeff", "CFA_cellCorrFactor", "CFS_statCorrFactor", "root_depth_multiplier",
     "river_roughness_coeff_mult", "lake_depth", "wetland_depth", "surfacewater_outflow_coefficient",
     "evapo_red_fact_exp_mult", "net_radiation_mult", "PT_coeff_humid", "PT_coeff_arid", "max_daily_PET", "mcwh",
@@ -82,7 +82,8 @@ ConfigFile::ConfigFile(const std::string &file) {
         if (!(ss >> tag) || tag[0] == '#') continue;
         if (tag == "end_of_head") break;
         std::map<std::string, std::string *> str = {
-            {"wghm_state", &startvaluefile}, {"param_json", &parameterfile}, {"snowInElevation_startvalues", &snowInElevationfile},
+            {"wghm_state", &startvaluefile}, {"param_json", &parameterfile}, {"calibration_parameters", &calibrationfile},
+            {"output_calibration_parameters", &outputparameter}, {"snowInElevation_startvalues", &snowInElevationfile},
             {"additionalOutIn_startvalues", &additionalfile}, {"output_state_mean", &outputmeanfile},
             {"output_state_lastday", &outputlastdayfile}, {"output_snowInElevation_lastday", &outputsnowlastdayfile},
             {"additionalOutIn_lastday", &outputadditionalfile}, {"runtime_options", &runtimeoptionsfile},

@@ -34,6 +34,8 @@ enum eCalibParam {  // calib_param.h:72-101
     P_GWOUTF_C, M_NETABSSW, M_NETABSGW, M_PREC
 };
 
+extern const char *const kParamNames[26];  // calib_param.cpp:140-171, eCalibParam order
+
 class calibParamClass {
   public:
     void readJson(const std::string &file, int ncell);  // calib_param.cpp:185-284 (key names :140-171)
@@ -51,7 +53,7 @@ struct ConfigFile {  // configFile.cpp:20-231
     ConfigFile(const std::string &file, int year, int month, const std::string &progName);  // configFile.cpp: "OL" keeps the file's dates
     std::string startvaluefile, parameterfile, snowInElevationfile, additionalfile, outputmeanfile, outputlastdayfile,
         outputsnowlastdayfile, outputadditionalfile, runtimeoptionsfile, outputoptionsfile, routingoptionsfile, stationsfile,
-        inputDir, outputDir, climateDir, routingDir, waterUseDir;
+        inputDir, outputDir, climateDir, routingDir, waterUseDir, calibrationfile, outputparameter;
     int startMonth = 0, startYear = 0, endMonth = 0, endYear = 0, timeStep = 0, numInitYears = 0;
 };
 
