@@ -117,6 +117,10 @@ void *wgk_device_ptr(wgk_ctx *ctx, int field, int member);
 int64_t wgk_cell_stride(const wgk_ctx *ctx);
 int64_t wgk_member_stride(const wgk_ctx *ctx);
 int wgk_layout(const wgk_ctx *ctx);
+/* schedule of a multi-day call chosen by wgk_create (bit flags): 1 = whole-grid kernels day after day (many members), else
+ * the (day, level) wavefront graph; 2 = the wavefront's wide levels run as one task per (day, level) (vertical part and river
+ * part in one kernel, programmatic edge from the upstream level), else as two; 4 = cell-owner kernel (opt-in). */
+int wgk_schedule(const wgk_ctx *ctx);
 /* rank_of_cell[n] = position of reference cell n in the device (routing) order */
 int wgk_get_device_order(const wgk_ctx *ctx, int32_t *rank_of_cell);
 

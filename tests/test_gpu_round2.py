@@ -455,3 +455,42 @@ def test_water_use_one_step_parity_59_days(golden, oracle_lib):
     print("water use, one step:", rep.summary(), sorted(rep.flips, key=lambda f: -f[5])[:8])
     rep.check(ONE_STEP_PPM, ONE_STEP_MAX_REL, min_allowed=2, what="water use, one step, 59 days")
     assert (o.field("wu_total_unsatisfied") > 0).sum() > 50
+
+
+def test_fused_level_tasks_are_bit_identical(world3000, monkeypatch):
+    """opt-in task forms of the wavefront graph (WGK_LEVEL_TASKS): vertical + river part of a wide level in one kernel with a
+    programmatic edge from the upstream level ("fused", k_level_day with griddepcontrol.wait), or for the headwater level only
+    ("fused0"), against the default two-kernel tasks: 45 days in one call, every state / flux field, the snow bands and the
+    station record the same bits"""
+    from oracle import synth_world as sw, wg_init
+    import watergap2_b200 as wg
+    w = world3000
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    names = wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS + ["discharge", "snow_bands"]
+    cells = np.arange(3, w.ng, 17, dtype=np.int32)[:20]
+    monkeypatch.setenv("WGK_VERTICAL_FORM", "cells")
+    monkeypatch.setenv("WGK_TAIL_THRESHOLD", "16")  # several wide levels on the small world
+    out = []
+    for mode in ("split", "fused", "fused0"):
+        monkeypatch.setenv("WGK_LEVEL_TASKS", mode)
+        m = wg.Model(w.ng)
+        assert (m.schedule & 2 != 0) == (mode != "split")
+        m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
+        m.load(ini)
+        m.forcing_reserve(59)
+        slot = 0
+        for mon in (1, 2):
+            f = sw.forcing_month(w, 1901, mon)
+            nd = f["P"].shape[0]
+            m.set_forcing(slot, nd, f["P"], f["T"], f["SW"], f["LW"])
+            slot += nd
+        m.record_cells(cells, 45)
+        m.step_days(1, 0, 1, 0, 45)
+        m.synchronize()
+        out.append(({k: m.get(k) for k in names}, m.get_record(45)))
+        m.close()
+    for st, rec in out[1:]:
+        for k in names:
+            assert np.array_equal(st[k], out[0][0][k]), k
+        assert np.array_equal(rec, out[0][1])

@@ -499,9 +499,9 @@ def test_pdaf_cycle_through_the_fortran_symbols(host, world1000, tmp_path):
     sw.write_world(world1000, tmp, (1901, 1901), (1, 1))
     out = os.path.join(tmp, "output")
     cfg = os.path.join(tmp, "config.txt")
-    with open(cfg, "a") as f:
-        f.write(f"output_state_mean {out}/mean_001.txt\noutput_calibration_parameters {out}/parameters_out.json\n"
-                f"calibration_parameters {tmp}/parameters.json\n")
+    text = open(cfg).read()
+    open(cfg, "w").write(text.replace("end_of_head", f"output_state_mean {out}/mean_001.txt\noutput_calibration_parameters {out}/parameters_out.json\n"
+                                                     f"calibration_parameters {tmp}/parameters.json\nend_of_head"))
     cells = g["cells"]
     assert np.array_equal(cells, gp["cells"])
     n = cells.size
@@ -515,7 +515,7 @@ def test_pdaf_cycle_through_the_fortran_symbols(host, world1000, tmp_path):
     with open(mean_file, "w") as f:
         f.write("WGHM water storage states\nID TWS ...\n")
         for c in range(ng):
-            f.write(f"{c + 1} {mf[c].sum()!r} " + " ".join(repr(float(v)) for v in mf[c]) + "\n")
+            f.write(f"{c + 1} {float(mf[c].sum())!r} " + " ".join(repr(float(v)) for v in mf[c]) + "\n")
     vp = ctypes.c_void_p
     for fn in ("initialize_wghm_", "integrate_wghm_", "extract_sub_", "enkf_wghmstate_"):
         getattr(host, fn).restype = None

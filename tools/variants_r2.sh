@@ -1,8 +1,12 @@
-cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_gpu_round2.py -m gpu -x -q -s -k "water_use" > gpurun_out/r2f_wu.log 2>&1; tail -25 gpurun_out/r2f_wu.log | cut -c1-1200
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2f_pytest.log 2>&1; tail -4 gpurun_out/r2f_pytest.log
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --legs none > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err
-python - <<'PY'
-import json
-d=json.load(open("gpurun_out/r2f_bench.json")); print("headline %.3f ms/yr %.4f e9" % (d["ms_per_step"], d["value"]/1e9))
-PY
+#!/bin/bash
+# scratch: single-member timeline experiments
+mkdir -p gpurun_out
+run() { tag=$1; shift; env "$@" STAMP_TAG=$tag timeout 300 python tools/stamps_report.py > gpurun_out/stamps_$tag.json 2> gpurun_out/stamps_$tag.err; cat gpurun_out/stamps_$tag.json; }
+run base WGK_X=0
+run reuse8 WGK_REUSE_EVERY=8
+run prio WGK_NODE_PRIORITY=-1
+run fused0 WGK_LEVEL_TASKS=fused0
+run fused0_reuse8 WGK_LEVEL_TASKS=fused0 WGK_REUSE_EVERY=8
+run all3 WGK_LEVEL_TASKS=fused0 WGK_REUSE_EVERY=8 WGK_NODE_PRIORITY=-1
+timeout 600 python -m pytest tests/test_host_library.py -x -q -m gpu > gpurun_out/r2h_pytest.log 2>&1
+tail -3 gpurun_out/r2h_pytest.log

@@ -97,6 +97,7 @@ def lib():
     L.wgk_member_stride.argtypes = [vp]
     L.wgk_member_stride.restype = ctypes.c_int64
     L.wgk_layout.argtypes = [vp]
+    L.wgk_schedule.argtypes = [vp]
     L.wgk_get_device_order.argtypes = [vp, vp]
     L.wgk_forcing_reserve.argtypes = [vp, ci, ci]
     L.wgk_set_forcing.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, ci]
@@ -425,6 +426,11 @@ class Model:
     @property
     def member_stride(self):
         return self._L.wgk_member_stride(self._c)
+
+    @property
+    def schedule(self):
+        """bit flags of wgk_schedule: 1 whole-day kernels (else the (day, level) wavefront), 2 fused level tasks, 4 cell owner"""
+        return self._L.wgk_schedule(self._c)
 
     @property
     def layout(self):

@@ -289,6 +289,7 @@ void extract_sub_(const char *s, wg::WghmStateFile *&wghmState, double *&output,
                   int *groupmatrixindex) {
     using namespace wg;
     (void)calPar_filename;
+    try {
     const std::vector<int> ids = read_region_ids(s);
     const long nr_par = *calpar_size;
     output = new double[ids.size() * 10 + nr_par];
@@ -300,6 +301,10 @@ void extract_sub_(const char *s, wg::WghmStateFile *&wghmState, double *&output,
         if ((long)par.size() != nr_par) throw std::runtime_error("extract_sub_: calpar_size does not match calPar_index");
         for (long k = 0; k < nr_par; k++) output[ids.size() * 10 + k] = par[k];
     }
+    } catch (std::exception &e) {  // the reference rethrows with this prefix (extractsub.cpp:341-344)
+        fprintf(stderr, "extract_sub_: %s\n", e.what());
+        throw std::runtime_error(std::string("In watergap::main():\n") + e.what());
+    }
 }
 
 void enkf_wghmstate_(const char *s, double *field, double *prediction, wg::ConfigFile *&configFile, wg::WghmStateFile *&wghmState,
@@ -310,6 +315,7 @@ void enkf_wghmstate_(const char *s, double *field, double *prediction, wg::Confi
                      long *oy, long *total_nr_calPar, int *calPar_index, int *groupmatrixindex) {
     using namespace wg;
     (void)calPar_filename;
+    try {
     const long nr_par = *calpar_size;
     char date[32];
     snprintf(date, sizeof date, "_%ld-%02ld", *year, *month);
@@ -345,7 +351,7 @@ void enkf_wghmstate_(const char *s, double *field, double *prediction, wg::Confi
             str += date;
             str += ".txt";
         }
-        wghmStateMean->saveMean(str);
+        if (str.size() > 4 && str.compare(str.size() - 4, 4, ".txt") == 0) wghmStateMean->saveMean(str);
     }
     if (!configFile->outputadditionalfile.empty()) additionalOutIn->save(configFile->outputadditionalfile);
     output = nullptr;  // the reference frees its snow factors before returning
@@ -357,6 +363,10 @@ void enkf_wghmstate_(const char *s, double *field, double *prediction, wg::Confi
         delete additionalOutIn; additionalOutIn = nullptr;
         delete snow_in_elevation; snow_in_elevation = nullptr;
         delete configFile; configFile = nullptr;
+    }
+    } catch (std::exception &e) {  // enKF2wghmState.cpp:586-589
+        fprintf(stderr, "enkf_wghmstate_: %s\n", e.what());
+        throw std::runtime_error(std::string("In watergap::main():\n") + e.what());
     }
 }
 }  // extern "C"

@@ -140,6 +140,8 @@ struct wgk_ctx {
     bool month_acc = false;     // EnKF bridge: accumulate the daily WghmStateFile entries of the month
     int month_days = 0;
     bool whole_day = false;     // many members: whole-grid kernels day after day instead of the (day, level) wavefront
+    int level_tasks = 0;        // wavefront: V(d, l) and R(d, l) of a wide level as one task (k_level_day): 0 no, 1 every wide level
+                                // (programmatic edges between the levels), 2 level 0 only (headwater cells: no upstream level)
     int form = 0;               // vertical kernel form: 0 thread per cell, 1 band-parallel 5 threads/cell, 2 band-parallel 2 threads/cell
     int32_t *d_gidx = nullptr;  // [ncell] index into the global-water-body scratch or -1
     double *d_gbody = nullptr;  // [nmember][ngbody][GB_N]
@@ -363,6 +365,11 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
         for (int l = 0; l < c->tail_level0; l++) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
             const dim3 g = cell_grid(c, end - begin, 128);
+            if (c->level_tasks == 1 || (c->level_tasks == 2 && l == 0)) {
+                WGK_KW(c, k_level_day)<<<g, block, 0, c->stream>>>(p, d, l);
+                n += 1;
+                continue;
+            }
             launch_cells_pre(c, p, d, begin, end);
             WGK_KW(c, k_river_level)<<<g, block, 0, c->stream>>>(p, d, l);
             n += 2;
@@ -437,6 +444,25 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
             int begin = c->level_off[l], end = c->level_off[l + 1];
             int dd = d, ll = l;
             const dim3 grid = cell_grid(c, end - begin, 128);
+            if (c->level_tasks == 1 || (c->level_tasks == 2 && l == 0)) {
+                // VR(d, l): full edges from the level's own previous day (and the discharge-buffer reuse), a programmatic edge from
+                // the upstream level of the same day: the grid starts once the upstream grid is resident and waits inside the
+                // kernel, after its vertical part, for the upstream grid to complete
+                void *a[] = {&pp, &dd, &ll};
+                cudaGraphNode_t node;
+                CU(add((void *)WGK_KW(c, k_level_day), grid, cell_block(c, 128), a, {prevW[l], first_sweep ? reuse : nullptr}, &node));
+                if (last) {
+                    cudaGraphEdgeData ed{};
+                    ed.from_port = cudaGraphKernelNodePortLaunchCompletion;
+                    ed.to_port = 0;
+                    ed.type = cudaGraphDependencyTypeProgrammatic;
+                    CU(cudaGraphAddDependencies_v2(g, &last, &node, &ed, 1));
+                }
+                first_sweep = false;
+                prevW[l] = node;
+                last = node;
+                continue;
+            }
             // V(d, l): vertical balance + local routing, waits only for the cells' own previous day
             void *a1[] = {&pp, &dd, &begin, &end};
             cudaGraphNode_t pre, node;
@@ -466,7 +492,7 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
             int dd = d;
             void *a3[] = {&pp, &dd};
             cudaGraphNode_t e;
-            CU(add((void *)WGK_K(c, k_end_of_day), dim3(1), dim3(256), a3, {last}, &e));
+            CU(add((void *)WGK_K(c, k_end_of_day), dim3(1), dim3(256), a3, {last, d > 0 ? dayEnd[d - 1] : nullptr}, &e));  // day ends in order
             last = e;
         }
         dayEnd[d] = last;
@@ -663,6 +689,17 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
         }
         c->mpad = c->mm ? (nmember + 31) / 32 * 32 : nmember;
         c->ppad = c->mm ? (npset == 1 ? 1 : (npset + 31) / 32 * 32) : npset;
+    }
+    {   // Tasks of the wavefront: two kernels per (day, wide level) - vertical balance + local routing, then river + post once the
+        // upstream level is through.  Opt-in (WGK_LEVEL_TASKS): "fused" = one kernel per (day, level) with a programmatic
+        // (launch-completion) edge from the upstream level and griddepcontrol.wait between the two parts (k_level_day);
+        // "fused0" = only the headwater level, which has no upstream, as one kernel.  Both were measured SLOWER on B200
+        // (0.5 degree grid, one member, ms per simulated year: split 22.2, fused 23.7, fused0 23.8): the fused kernel takes
+        // 56 us where the two take 35 + 11 us plus a 6 us (median) edge, so the own-cell recurrence V(d,0) -> R(d,0) -> V(d+1,0)
+        // gets longer, not shorter.  Also measured without effect: launch priority on the level-0/1 nodes, the discharge-buffer
+        // reuse edge on every 8th day only (median edge 3.5 us instead of 6, same mean).
+        const char *e = getenv("WGK_LEVEL_TASKS");  // "split" | "fused" | "fused0"
+        c->level_tasks = c->form != 0 ? 0 : (e && !strcmp(e, "fused")) ? 1 : (e && !strcmp(e, "fused0")) ? 2 : 0;
     }
     if (c->opt.tail_threshold <= 0) {
         const char *e = getenv("WGK_TAIL_THRESHOLD");
@@ -906,6 +943,9 @@ int wgk_get_device_order(const wgk_ctx *c, int32_t *rank_of_cell) {
 int64_t wgk_cell_stride(const wgk_ctx *c) { return c ? (c->mm ? c->mpad : 1) : 0; }
 int64_t wgk_member_stride(const wgk_ctx *c) { return c ? (c->mm ? 1 : c->stride) : 0; }
 int wgk_layout(const wgk_ctx *c) { return c ? (c->mm ? 1 : 0) : WGK_ERR_ARG; }
+int wgk_schedule(const wgk_ctx *c) {
+    return c ? ((c->whole_day ? 1 : 0) | (!c->whole_day && c->level_tasks ? 2 : 0) | (c->owner_mode == 1 ? 4 : 0)) : WGK_ERR_ARG;
+}
 
 // ---------------------------------------------------------------------------------------
 // fields
@@ -1684,6 +1724,10 @@ int wgk_profile_schedule(wgk_ctx *c, int day, int month, int dom, int slot, floa
         for (int l = 0; l < c->tail_level0; l++) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
             const dim3 g = cell_grid(c, end - begin, 128);
+            if (c->level_tasks == 1 || (c->level_tasks == 2 && l == 0)) {
+                timed(1, [&] { WGK_KW(c, k_level_day)<<<g, block, 0, c->stream>>>(p, 0, l); });
+                continue;
+            }
             timed(0, [&] { launch_cells_pre(c, p, 0, begin, end); });
             timed(1, [&] { WGK_KW(c, k_river_level)<<<g, block, 0, c->stream>>>(p, 0, l); });
         }

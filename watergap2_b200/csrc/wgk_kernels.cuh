@@ -2508,6 +2508,45 @@ __global__ void __launch_bounds__(VBLOCK, WGK_PRE_MINB_EFF) k_cells_pre_tpc(cons
     if (begin == 0) stamp_task(p, 0, 1, dayofs);
 }
 
+// V(d, l) and R(d, l) of one wide level in ONE task: the vertical balance + local routing of the level's cells, then - after
+// the upstream level of the same day has completed - their river reach + post-pass, cell by cell in the same thread.  In the
+// wavefront graph the edge from the upstream level's task is a PROGRAMMATIC one (launch-completion port): this grid starts as
+// soon as the upstream grid is resident, works through its vertical part next to it, and griddepcontrol.wait holds it until the
+// upstream grid has completed and its discharge is visible.  The own-cell recurrence of a level then crosses one kernel
+// boundary per day instead of two, and the graph has half the nodes.  (Launched without a programmatic edge - plain stream
+// order - the wait returns at once.)
+__global__ void __launch_bounds__(VBLOCK, WGK_PRE_MINB_EFF) k_level_day(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
+    __shared__ SnowStage stage;
+    int r, m;
+    const bool on = map_thread(p, p.level_off[level], p.level_off[level + 1], r, m);
+    if (on) {
+        if (level == 0) stamp_task(p, 0, 0, dayofs);
+        LocalIn li;
+        LocalFlux fx;
+        if (vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, m, li, fx, p.cal_days[4 * dayofs + 1]);
+        else route_local_cell(p, r, m, p.cal_days[4 * dayofs + 1]);
+        if (level == 0) stamp_task(p, 0, 1, dayofs);
+    }
+#ifdef __CUDA_ARCH__
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+    if (!on) return;
+    if (level == 0) stamp_task(p, 1, 0, dayofs);
+    const size_t i = mi(p, m, r), q = qi(p, m, r);
+    const RiverCtx c = load_ctx(p, r, i, q);
+    PostIn in = post_load(p, r, m);
+    double Sr = c.prevR;
+    if (c.flags & FL_ACTIVE) {
+        double *qday = qbuf_of_day(p, dayofs);
+        double red_ll = in.red_loc_lake;
+        Sr = route_river(p, c, r, m, i, q, gather_upstream(p, c, m, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday, nullptr,
+                         WU ? &red_ll : nullptr);
+        if (WU) in.red_loc_lake = red_ll;
+    }
+    route_post_compute(p, r, m, in, Sr);
+    if (level == 0) stamp_task(p, 1, 1, dayofs);
+}
+
 #if !WGK_MM  // k_tail_chunk and the cell-owner schedule run on the cell-minor layout only
 // narrow levels [level_lo, level_hi) of one day in one persistent CTA per member, then the
 // post-pass of those cells
