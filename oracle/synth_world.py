@@ -467,7 +467,27 @@ def default_params(w, variant=0):
     return p
 
 
-def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_discharge=True, params=None, water_use=False, time_series=0):
+def reservoir_years(w, years):
+    """resYearOpt 1 variant of the world's reservoirs (routing.cpp:1052-1412): a third operates from the start - every second of
+    them with 60 % of its land-cover fraction in the first year and the full fraction from the second (the "existing reservoir
+    grew" branch) -, a third comes on line in the second year, a third in the third.
+    -> (start_year [ng] int32, {year: G_RES_<year> fraction [ng]})"""
+    idx = np.flatnonzero(w.resarea > 0)
+    start = w.res_start_year.copy()
+    frac = {}
+    for y in range(years[0], years[1] + 1):
+        frac[y] = np.zeros(w.ng)
+    for i, n in enumerate(idx):
+        k = i % 3
+        start[n] = years[0] + k if k else min(int(start[n]), years[0] - 1)
+        for y in frac:
+            if y >= start[n]:
+                frac[y][n] = w.glores[n] * (0.6 if (k == 0 and i % 2 and y == years[0]) else 1.0)
+    return start.astype(np.int32), frac
+
+
+def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_discharge=True, params=None, water_use=False, time_series=0,
+                res_year_opt=0):
     inp = os.path.join(out, "input")
     clim = os.path.join(out, "climate")
     rout = os.path.join(out, "routing")
@@ -503,7 +523,10 @@ def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_
     write_unf(f"{inp}/G_RESAREA.UNF0", w.resarea, "f4")
     write_unf(f"{inp}/G_REG_LAKE.UNF1", w.reg_status, "i1")
     write_unf(f"{inp}/G_RES_TYPE.UNF1", w.res_type, "i1")
-    write_unf(f"{inp}/G_START_YEAR.UNF4", w.res_start_year, "i4")
+    res_start, res_frac = (w.res_start_year, {}) if not res_year_opt else reservoir_years(w, years)
+    write_unf(f"{inp}/G_START_YEAR.UNF4", res_start, "i4")
+    for y, fr in res_frac.items():
+        write_unf(f"{inp}/G_RES/G_RES_{y}.UNF0", fr, "f4")
     write_unf(f"{inp}/G_STORAGE_CAPACITY.UNF0", w.stor_cap, "f4")
     write_unf(f"{inp}/G_MEAN_OUTFLOW.UNF0", w.mean_outflow, "f4")
     write_unf(f"{inp}/G_MEAN_OUTFLOW.12.UNF0", w.mean_outflow12, "f4")
@@ -531,7 +554,7 @@ def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_
             write_unf(f"{clim}/G_SSRD_H08_int_{y}.365.UNF0", yr["SW"], "f4")
             write_unf(f"{clim}/G_SLRD_H08_int_{y}.365.UNF0", yr["LW"], "f4")
     for y in range(years[0], years[1] + 1):
-        for m in range(months[0], months[1] + 1):
+        for m in (range(1, 13) if years[0] != years[1] else range(months[0], months[1] + 1)):  # several years: every month
             if time_series == 1:
                 break
             f = forcing_month(w, y, m)
@@ -550,6 +573,11 @@ def write_world(w, out, years=(1901, 1901), months=(1, 12), grid_store=6, daily_
     opts = list(OPTIONS)
     opts[2] = grid_store
     opts[OPTION_NAMES.index("time_series")] = time_series
+    if res_year_opt:  # the reference year has to lie inside [first, last] (option.cpp:639)
+        opts[OPTION_NAMES.index("resYearOpt")] = 1
+        opts[OPTION_NAMES.index("resYearReference")] = years[0]
+        opts[OPTION_NAMES.index("resYearFirstToUse")] = years[0]
+        opts[OPTION_NAMES.index("resYearLastToUse")] = years[1]
     if water_use:
         # SURVEY 8f-4 (next row): net abstractions from surface water / groundwater, m3 per month (routing.cpp:884-977),
         # subtract_use = 2 with the other use options at their canonical 0

@@ -114,6 +114,28 @@ def _restart_configs(tmp, world):
     return c1, c2, files
 
 
+def _compare_checkpoints(out, prefix_ref, what, frac_ok, worst_ok, ncell):
+    """the three checkpoint files in `out` against the reference's copies `<prefix_ref>*`: share of values within 1e-10
+    (relative, floor 1e-6) and the worst value"""
+    a = np.loadtxt(os.path.join(out, prefix_ref + "wghm_state_lastday.txt"), skiprows=2)
+    b = np.loadtxt(os.path.join(out, "wghm_state_lastday.txt"), skiprows=2)
+    e = np.abs(a[:, 1:] - b[:, 1:]) / np.maximum(np.maximum(np.abs(a[:, 1:]), np.abs(b[:, 1:])), 1e-6)  # mm over the continental area
+    bad = np.argwhere(e > max(1e-7, worst_ok))[:12]  # (cell, column: 0 TWS, 1 canopy, 2 snow, 3 soil, 4.. the routing storages)
+    assert (e <= 1e-10).mean() >= frac_ok and e.max() < worst_ok, (what, "state", float(e.max()), float((e > 1e-10).mean()),
+                                                                    [(int(i), int(j), float(a[i, 1 + j]), float(b[i, 1 + j])) for i, j in bad])
+    sa = np.loadtxt(os.path.join(out, prefix_ref + "snow_lastday.txt"), skiprows=1)
+    sb = np.loadtxt(os.path.join(out, "snow_lastday.txt"), skiprows=1)
+    es = np.abs(sa - sb) / np.maximum(np.maximum(np.abs(sa), np.abs(sb)), 1e-6)
+    assert (es <= 1e-10).mean() >= frac_ok and es.max() < worst_ok, (what, "snow", float(es.max()))
+    aa = np.loadtxt(os.path.join(out, prefix_ref + "additional_lastday.txt"), skiprows=2)
+    ab = np.loadtxt(os.path.join(out, "additional_lastday.txt"), skiprows=2)
+    assert aa.shape == ab.shape == (ncell, 54)
+    assert np.array_equal(aa[:, :3], ab[:, :3]), (what, "ID / LAI counters")  # integer state: exact
+    ea = np.abs(aa - ab) / np.maximum(np.maximum(np.abs(aa), np.abs(ab)), 1e-6)
+    assert (ea <= 1e-10).mean() >= frac_ok and ea.max() < worst_ok, (what, "additional", float(ea.max()), np.argwhere(ea > 1e-7)[:5].tolist())
+    return float(max(e.max(), es.max(), ea.max())), float(min((e <= 1e-10).mean(), (es <= 1e-10).mean(), (ea <= 1e-10).mean()))
+
+
 def _run_ref(tmp, cfg, prefix, files):
     log = open(os.path.join(tmp, "driver.log"), "a")
     subprocess.check_call([HARNESS, "driver", cfg], stdout=log, stderr=log, cwd=tmp)
@@ -165,20 +187,7 @@ def test_host_driver_restart_matches_reference_driver(host, world3000, tmp_path)
     secs = ctypes.c_double()
 
     def compare(prefix_ref, what, frac_ok, worst_ok):
-        a = np.loadtxt(os.path.join(out, prefix_ref + "wghm_state_lastday.txt"), skiprows=2)
-        b = np.loadtxt(os.path.join(out, "wghm_state_lastday.txt"), skiprows=2)
-        e = np.abs(a[:, 1:] - b[:, 1:]) / np.maximum(np.maximum(np.abs(a[:, 1:]), np.abs(b[:, 1:])), 1e-6)  # mm over the continental area
-        assert (e <= 1e-10).mean() >= frac_ok and e.max() < worst_ok, (what, "state", float(e.max()), float((e > 1e-10).mean()))
-        sa = np.loadtxt(os.path.join(out, prefix_ref + "snow_lastday.txt"), skiprows=1)
-        sb = np.loadtxt(os.path.join(out, "snow_lastday.txt"), skiprows=1)
-        es = np.abs(sa - sb) / np.maximum(np.maximum(np.abs(sa), np.abs(sb)), 1e-6)
-        assert (es <= 1e-10).mean() >= frac_ok and es.max() < worst_ok, (what, "snow", float(es.max()))
-        aa = np.loadtxt(os.path.join(out, prefix_ref + "additional_lastday.txt"), skiprows=2)
-        ab = np.loadtxt(os.path.join(out, "additional_lastday.txt"), skiprows=2)
-        assert aa.shape == ab.shape == (3000, 54)
-        assert np.array_equal(aa[:, :3], ab[:, :3]), (what, "ID / LAI counters")  # integer state: exact
-        ea = np.abs(aa - ab) / np.maximum(np.maximum(np.abs(aa), np.abs(ab)), 1e-6)
-        assert (ea <= 1e-10).mean() >= frac_ok and ea.max() < worst_ok, (what, "additional", float(ea.max()), np.argwhere(ea > 1e-7)[:5].tolist())
+        _compare_checkpoints(out, prefix_ref, what, frac_ok, worst_ok, 3000)
 
     # (a) both sides restart from the reference's files
     assert host.wg_host_integrate(c2.encode(), 3000, 0, ctypes.byref(secs), err, 1024) == 28, err.value
@@ -560,6 +569,65 @@ def test_pdaf_cycle_through_the_fortran_symbols(host, world1000, tmp_path):
     assert open(os.path.join(out, "calpar_1901-01.txt"), "rb").read() == bytes(gp["cda_txt"])
     lines = [l for l in open(os.path.join(out, "parameters_out.json"), "rb").read().split(b"\n") if not l.startswith(b'"creation_datetime"')]
     assert b"\n".join(lines) == bytes(gp["json"])
+
+
+@pytest.mark.gpu
+def test_reservoirs_coming_on_line_match_reference_driver(host, world3000, tmp_path):
+    """resYearOpt 1 (routing.cpp:1052-1412): reservoirs and their land-cover fraction G_RES_<year> start operating in their
+    start year - a third from the beginning (half of those with 60 % of their fraction in 1901 and the full fraction from
+    1902), a third on 1902-01-01, a third on 1903-01-01.  annualInit of the following years: the new or grown reservoirs take
+    land area and the water stored on it; statics and storages go back to the device.
+    (a) December 1901 .. February 1902 in one run (new and grown reservoirs on 1902-01-01);
+    (b) January 1903 restarted from the reference's checkpoint of December 1902 (the previous year's fractions come from column
+        44 of the additional file);
+    (c) December 1901 .. January 1903 in one run, 427 days across both dates, with the bound of a long free run.
+    The three checkpoint files against the compiled reference's driver."""
+    if not os.path.exists(HARNESS):
+        pytest.skip("compiled reference not available")
+    from oracle import synth_world as sw
+    tmp = str(tmp_path)
+    w = world3000
+    start, frac = sw.reservoir_years(w, (1901, 1903))
+    new02, grown02 = (frac[1902] > 0) & (frac[1901] == 0), (frac[1902] > frac[1901]) & (frac[1901] > 0)
+    new03 = (frac[1903] > 0) & (frac[1902] == 0)
+    assert new02.sum() >= 5 and grown02.sum() >= 3 and new03.sum() >= 5
+    sw.write_world(w, tmp, (1901, 1903), (12, 1), res_year_opt=1)
+    out = os.path.join(tmp, "output")
+    files = ("wghm_state_lastday.txt", "snow_lastday.txt", "additional_lastday.txt")
+    text = open(os.path.join(tmp, "config.txt")).read()
+    err = ctypes.create_string_buffer(1024)
+    secs = ctypes.c_double()
+
+    def config(name, y0, m0, y1, m1, restart_prefix=None):
+        t = text.replace("start_year 1901", f"start_year {y0}").replace("start_month 12", f"start_month {m0}")
+        t = t.replace("end_year 1903", f"end_year {y1}").replace("end_month 1", f"end_month {m1}")
+        if restart_prefix:
+            t = t.replace("param_json", f"wghm_state {out}/{restart_prefix}wghm_state_lastday.txt\nsnowInElevation_startvalues "
+                          f"{out}/{restart_prefix}snow_lastday.txt\nadditionalOutIn_startvalues {out}/{restart_prefix}additional_lastday.txt\nparam_json")
+        path = os.path.join(tmp, name)
+        open(path, "w").write(t)
+        return path
+
+    # (a) new and grown reservoirs on 1902-01-01, in one run
+    ca = config("config_a.txt", 1901, 12, 1902, 2)
+    _run_ref(tmp, ca, "refA_", files)
+    assert host.wg_host_integrate(ca.encode(), 3000, 0, ctypes.byref(secs), err, 1024) == 31 + 31 + 28, err.value
+    print("(a)", _compare_checkpoints(out, "refA_", "December 1901 .. February 1902", 0.999, 1e-6, 3000))
+    a = np.loadtxt(os.path.join(out, "wghm_state_lastday.txt"), skiprows=2)
+    assert (a[new02, 9] > 0).sum() >= 5  # RESERVOIR column: the new reservoirs hold water
+    # (b) the reference's year 1902 as the checkpoint, January 1903 by both sides
+    cy = config("config_y.txt", 1901, 12, 1902, 12)
+    _run_ref(tmp, cy, "dec02_", files)
+    cb = config("config_b.txt", 1903, 1, 1903, 1, restart_prefix="dec02_")
+    _run_ref(tmp, cb, "refB_", files)
+    assert host.wg_host_integrate(cb.encode(), 3000, 0, ctypes.byref(secs), err, 1024) == 31, err.value
+    print("(b)", _compare_checkpoints(out, "refB_", "January 1903 restarted from the December checkpoint", 0.999, 1e-6, 3000))
+    # (c) 427 days in one run: a cell whose river dries out a day earlier or later changes its river area (up to a per cent of the
+    # cell) and with it everything downstream, so single cells leave the 1e-6 bound of the short runs; the share stays
+    cc = config("config_c.txt", 1901, 12, 1903, 1)
+    _run_ref(tmp, cc, "refC_", files)
+    assert host.wg_host_integrate(cc.encode(), 3000, 0, ctypes.byref(secs), err, 1024) == 31 + 365 + 31, err.value
+    print("(c)", _compare_checkpoints(out, "refC_", "427-day run across two commissioning dates", 0.995, 0.5, 3000))
 
 
 def test_product_topology_builder_full_size_equals_oracle(host, oracle_lib, tmp_path):

@@ -115,10 +115,12 @@ void optionClass::require_canonical() const {
     struct { int idx, want; const char *name; } req[] = {
         {6, 1, "cloud"}, {7, 1, "intercept"}, {8, 0, "calc_albedo"}, {9, 0, "petOpt"}, {10, 1, "use_kc"},
         {14, 1, "riverveloOpt"}, {18, 0, "clclOpt"}, {20, 1, "resOpt"}, {21, 0, "statcorrOpt"},
-        {22, 1, "aridareaOpt"}, {23, 1, "fractionalRoutingOpt"}, {24, 1, "riverEvapoOpt"}, {27, 0, "resYearOpt"},
+        {22, 1, "aridareaOpt"}, {23, 1, "fractionalRoutingOpt"}, {24, 1, "riverEvapoOpt"},
         {31, 0, "antNatOpt"}, {34, 0, "calc_wtemp"}, {35, 0, "glacierOpt"}, {1, 1, "basin"}};
     if (v[5] != 0 && v[5] != 1)  // monthly .31 files (climate.cpp:93-138) or yearly .365 files (climateYear.cpp:38-79)
         throw std::runtime_error("option time_series = " + std::to_string(v[5]) + " is outside the implemented hot path (0: .31 files, 1: .365 files)");
+    if (v[27] != 0 && v[27] != 1)
+        throw std::runtime_error("option resYearOpt = " + std::to_string(v[27]) + " must be 0 (reference year) or 1 (reservoirs start operating in their year)");
     if (v[15] != 0 && v[15] != 2)
         throw std::runtime_error("option subtract_use = " + std::to_string(v[15]) + " is outside the implemented hot path (0: no water use, 2: net abstractions)");
     if (v[15] == 2 && (v[16] != 0 || v[17] != 0 || v[25] != 0))
@@ -314,6 +316,8 @@ void routingClass::init(short, const ConfigFile &, WghmStateFile &, AdditionalOu
     statusStarted_landfreq.assign(ng, 0);
     G_res_type.initialize(ng); G_start_month.initialize(ng); G_reg_lake_status.initialize(ng); G_LDD.initialize(ng);
     G_res_start_year.initialize(ng); G_downstreamCell.initialize(ng); G_routOrder.initialize(ng);
+    G_outflow_cell_assignment.initialize(ng);
+    G_outflow_cell_assignment.read(in + "/G_OUTFLOW_CELL_ASSIGNMENT.UNF4");  // :290
     G_glo_lake.read(in + "/G_GLOLAK.UNF0"); G_loc_lake.read(in + "/G_LOCLAK.UNF0"); G_glo_wetland.read(in + "/G_GLOWET.UNF0");
     G_loc_wetland.read(in + "/G_LOCWET.UNF0"); G_lake_area.read(in + "/G_LAKAREA.UNF0"); G_reservoir_area_full.read(in + "/G_RESAREA.UNF0");
     G_reg_lake.read(in + "/G_REGLAKE.UNF0"); G_reg_lake_status.read(in + "/G_REG_LAKE.UNF1");
@@ -468,45 +472,65 @@ void routingClass::setStorages(WghmStateFile &st, AdditionalOutputInputFile &add
     }
 }
 
-void routingClass::setLakeWetlToMaximum(short) {  // :5647-5720 (resYearOpt 0)
+void routingClass::setLakeWetlToMaximum(short start_year) {  // :5647-5720
     const int ref = eng.options.resYearReference;
+    const bool byYear = eng.options.resYearOpt == 1;
     for (int n = 0; n < eng.ncell; n++) {
         const double A = eng.geo.areaOfCellByArrayPos(n);
         G_locLakeStorage[n] = (G_loc_lake[n] / 100.) * A * G_lakeDepthActive[n];
         G_locWetlStorage[n] = (G_loc_wetland[n] / 100.) * A * G_wetlDepthActive[n];
         G_gloLakeStorage[n] = G_lake_area[n] * G_lakeDepthActive[n];
         G_gloWetlStorage[n] = (G_glo_wetland[n] / 100.) * A * G_wetlDepthActive[n];
-        if (ref >= G_res_start_year[n] && G_stor_cap_full[n] > -99) G_gloResStorage[n] = G_stor_cap_full[n];
-        G_gloResEvapoReductionFactor[n] = 0.;  // the second if/else of the reference overrides the first with resYearOpt == 0
-        if (G_reg_lake_status[n] == 1 && ref < G_res_start_year[n]) G_gloResStorage[n] += G_reservoir_area_full[n] * G_lakeDepthActive[n];
+        if (!byYear && ref >= G_res_start_year[n] && G_stor_cap_full[n] > -99) G_gloResStorage[n] = G_stor_cap_full[n];
+        // the second if/else of the reference (:5678-5683) decides the factor: 0 with resYearOpt 0, 1 for the reservoirs that
+        // operate at the start of a resYearOpt 1 run
+        if (byYear && start_year >= G_res_start_year[n] && G_stor_cap_full[n] > -99) {
+            G_gloResEvapoReductionFactor[n] = 1.;
+            G_gloResStorage[n] = G_stor_cap_full[n];
+        } else
+            G_gloResEvapoReductionFactor[n] = 0.;
+        if (G_reg_lake_status[n] == 1 && (byYear ? start_year : ref) < G_res_start_year[n])
+            G_gloResStorage[n] += G_reservoir_area_full[n] * G_lakeDepthActive[n];
         G_locLakeAreaReductionFactor[n] = 1.; G_locWetlAreaReductionFactor[n] = 1.; G_gloLakeEvapoReductionFactor[n] = 1.; G_gloWetlAreaReductionFactor[n] = 1.;
         G_riverAreaReductionFactor[n] = 0.5;
         G_riverAreaFracNextTimestep_Frac[n] = G_riverAreaReductionFactor[n] * G_riverLength[n] * G_RiverWidth_bf[n] / 1000. / A;
     }
 }
 
-void routingClass::annualInit(short year, int start_month, AdditionalOutputInputFile &additionalOutIn) {  // :979-1415 (resYearOpt 0: G_RES_<reference year>)
-    const int ng = eng.ncell, ref = eng.options.resYearReference;
-    if (additionalOutIn.additionalfilestatus == 0 || start_month == 1 || year > eng.options.start_year)  // :986-1008
+// routing.cpp:979-1415 without the output arrays: the year's reservoir statics (resYearOpt 0: those of the reference year in every
+// year; 1: reservoirs and their land-cover fraction G_RES_<year> come on line in their start year), the first year's land area
+// fraction, and - parts 3/4 - the land area and the water stored on it that a new reservoir takes.  Works on the host grids
+// (synchronised with the device at every month end, run_model); yearlyChanged tells the caller what to send back.
+void routingClass::annualInit(short year, int start_month, AdditionalOutputInputFile &additionalOutIn) {
+    const int ng = eng.ncell;
+    const optionClass &o = eng.options;
+    if (additionalOutIn.additionalfilestatus == 0 || start_month == 1 || year > o.start_year)  // :986-1008
         for (int n = 0; n < ng; n++) {
             G_UnsatisfiedUsePrevYear[n] = G_totalUnsatisfiedUse[n];
             G_unsatisfiedNAsFromIrrigPrevYear[n] = G_unsatisfiedNAsFromIrrig[n];
             G_unsatisfiedNAsFromOtherSectorsPrevYear[n] = G_unsatisfiedNAsFromOtherSectors[n];
             G_reducedReturnFlowPrevYear[n] = G_reducedReturnFlow[n];
         }
+    const Grid<double> area_before = G_reservoir_area, cap_before = G_stor_cap, lake_before = G_lake_area;
     for (int n = 0; n < ng; n++) { G_reservoir_area[n] = 0.; G_stor_cap[n] = 0.; }
     for (int n = 0; n < ng; n++)
         if (G_reg_lake_status[n] == 1) { G_reservoir_area[n] = G_reservoir_area_full[n]; G_stor_cap[n] = G_stor_cap_full[n]; }
-    G_glo_res.read(eng.options.input_dir + "/G_RES/G_RES_" + std::to_string(ref) + ".UNF0");
+    int resYear = o.resYearReference;  // :1052-1078
+    if (o.resYearOpt == 1) resYear = year > o.resYearLastToUse ? o.resYearLastToUse : year < o.resYearFirstToUse ? o.resYearFirstToUse : year;
+    G_glo_res.read(o.input_dir + "/G_RES/G_RES_" + std::to_string(resYear) + ".UNF0");
     if (0 == statusStarted_updateGloResPrevYear) { updateGloResPrevYear_pct(); statusStarted_updateGloResPrevYear = 1; }
     for (int n = 0; n < ng; n++)
-        if (ref >= G_res_start_year[n]) { G_reservoir_area[n] = G_reservoir_area_full[n]; G_stor_cap[n] = G_stor_cap_full[n]; }
+        if (resYear >= G_res_start_year[n]) { G_reservoir_area[n] = G_reservoir_area_full[n]; G_stor_cap[n] = G_stor_cap_full[n]; }
     for (int n = 0; n < ng; n++)
-        if (G_reservoir_area[n] > 0. && ref >= G_res_start_year[n] && ((G_res_type[n] + 0 == 0) || G_mean_outflow[n] <= 0.)) {
+        if (G_reservoir_area[n] > 0. && resYear >= G_res_start_year[n] && ((G_res_type[n] + 0 == 0) || G_mean_outflow[n] <= 0.)) {
             G_lake_area[n] += G_reservoir_area_full[n];  // treated as a global lake (:1107-1146)
             G_reservoir_area[n] = 0.;
             G_reservoir_area_full[n] = 0.;
         }
+    yearlyChanged = false;
+    for (int n = 0; n < ng; n++)
+        if (G_reservoir_area[n] != area_before[n] || G_stor_cap[n] != cap_before[n] || G_lake_area[n] != lake_before[n]) yearlyChanged = true;
+    // part 3 (:1180-1291), first year only (G_fwaterfreq / G_landfreq / G_landWaterExclGloLakAreaFrac feed output grids only)
     for (int n = 0; n < ng; n++) {
         if (0 == statusStarted_landfreq[n]) {
             G_landAreaFrac[n] = (eng.geo.G_contfreq[n] - (G_glo_lake[n] + G_glo_wetland[n] + G_loc_lake[n] + G_loc_wetland[n] + G_glo_res[n]));
@@ -515,16 +539,40 @@ void routingClass::annualInit(short year, int start_month, AdditionalOutputInput
             statusStarted_landfreq[n] = 1;
         }
     }
-    // :1296-1415: a reservoir fraction that grew against the previous year takes land area and the water stored on it.  With
-    // resYearOpt 0 the fraction is the reference year's in every year, so the change is zero; the previous year's fraction of a
-    // checkpoint comes back from column 44.
+    // part 4 (:1296-1415): a reservoir fraction that grew against the previous year takes land area and the water stored on it.
+    // With resYearOpt 0 the fraction is the reference year's in every year and nothing changes; the previous year's fraction of
+    // a checkpoint comes back from column 44.
+    auto &d = eng.dailyWaterBalance;
     for (int n = 0; n < ng; n++) {
         if (additionalOutIn.additionalfilestatus == 1) G_glores_prevyear[n] = additionalOutIn.additionalOutputInput(n, 44);
-        if (start_month == 1 || year > eng.options.start_year)
-            if (G_glo_res[n] - G_glores_prevyear[n] > 0.)
-                throw std::runtime_error("routing.annualInit: a reservoir fraction grew against the previous year (cell " + std::to_string(n + 1) +
-                                         "): reservoir commissioning (resYearOpt 1, routing.cpp:1310-1412) is outside the implemented options");
+        if (!(start_month == 1 || year > o.start_year)) continue;
+        const double glores_change = G_glo_res[n] - G_glores_prevyear[n];
+        if (!(glores_change > 0.)) continue;
+        yearlyChanged = true;
+        if (G_glores_prevyear[n] > 0.) G_landAreaFrac[n] = G_landAreaFrac[n] - glores_change;  // an existing reservoir grew
+        else G_landAreaFrac[n] = G_landAreaFrac[n] - G_glo_res[n];                              // a new one
+        if (G_landAreaFrac[n] < 0.) G_landAreaFrac[n] = 0.;
+        // net change against the day before yesterday; not negative = fractional routing only: no change at all
+        const double laf_change = G_landAreaFrac[n] - G_landAreaFracPrevTimestep[n];
+        if (laf_change >= 0.) {
+            G_landAreaFrac[n] = G_landAreaFracPrevTimestep[n];
+        } else {
+            // the water on the lost land (mm over the cell) goes to the reservoir of the outflow cell, km3
+            const double A = eng.geo.areaOfCellByArrayPos(n);
+            const double canopy_km3 = d.G_canopyWaterContent[n] * A / 1000000.0 * ((-laf_change) / 100.0);
+            const double soil_km3 = d.G_soilWaterContent[n] * A / 1000000.0 * ((-laf_change) / 100.0);
+            const double snow_km3 = d.G_snow[n] * A / 1000000.0 * ((-laf_change) / 100.0);
+            G_gloResStorage[G_outflow_cell_assignment[n] - 1] += canopy_km3 + soil_km3 + snow_km3;
+            G_landAreaFracNextTimestep[n] = G_landAreaFrac[n];  // no second rescaling in calcNewDay
+        }
     }
+}
+
+// what annualInit may have changed, back to the device (the statics re-derive the kernels' per-cell constants on the next call)
+void routingClass::pushYearly() {
+    Engine &e = eng;
+    e.set("lake_area", G_lake_area); e.set("reservoir_area", G_reservoir_area); e.set("stor_cap", G_stor_cap);
+    e.set("land_area_frac", G_landAreaFrac); e.set("land_area_frac_next", G_landAreaFracNextTimestep); e.set("res_stor", G_gloResStorage);
 }
 
 // ---- water use (subtract_use 2) --------------------------------------------------------------
@@ -710,7 +758,7 @@ void Engine::push_static() {
     std::vector<uint8_t> cls(ncell);
     for (int n = 0; n < ncell; n++)
         cls[n] = (uint8_t)((routing.G_loc_lake[n] > 0.) * 1 + (routing.G_loc_wetland[n] > 0.) * 2
-                           + ((routing.G_lake_area[n] > 0.) || (routing.G_reservoir_area[n] > 0.) || (routing.G_glo_wetland[n] > 0.)) * 4
+                           + ((routing.G_lake_area[n] > 0.) || (routing.G_reservoir_area_full[n] > 0.) || (routing.G_glo_wetland[n] > 0.)) * 4
                            + (G_aindex[n] == 1) * 8);
     check(wgk_set_cell_classes(ctx, cls.data()), "wgk_set_cell_classes");
     check(wgk_set_topology(ctx, routing.G_routOrder.data(), routing.G_downstreamCell.data()), "wgk_set_topology");
@@ -903,11 +951,13 @@ long run_model(Engine &E, const ConfigFile &cfg, ModelStateRef S, double *second
     for (short year = E.options.start_year; year <= E.options.end_year; year++) {
         E.dailyWaterBalance.annualInit();
         E.routing.annualInit(year, cfg.startMonth, additionalOutIn);
-        if (!pushed) {  // (yearly reservoir changes do not occur with resYearOpt 0)
+        if (!pushed) {
             E.push_static();
             E.push_state();
             if (E.options.subtract_use > 0) E.routing.pushWaterUseState();
             pushed = true;
+        } else if (E.routing.yearlyChanged) {  // resYearOpt 1: reservoirs that start operating this year
+            E.routing.pushYearly();
         }
         if (E.options.subtract_use > 0) E.routing.dailyNUInit(E.options.water_use_dir, year, E.calParam);  // integrateWGHM.cpp:645-647
         if (yearly_forcing) E.set_forcing_year(year);  // integrateWGHM.cpp:565-568
@@ -964,6 +1014,7 @@ long run_model(Engine &E, const ConfigFile &cfg, ModelStateRef S, double *second
                 if (!cfg.outputsnowlastdayfile.empty()) snow_in_elevation.save(cfg.outputsnowlastdayfile);
             }
         }
+        if (end_month == 12) E.routing.updateGloResPrevYear_pct();  // integrateWGHM.cpp:921-922
     }
     if (seconds_day_loop) *seconds_day_loop = secs;
     return ndays;

@@ -64,7 +64,7 @@ struct optionClass {  // option.cpp:173-620, OPTIONS.DAT order
         &calc_albedo = v[8], &petOpt = v[9], &use_kc = v[10], &rout_prepare = v[12], &riverveloOpt = v[14],
         &subtract_use = v[15], &use_alloc = v[16], &delayedUseSatisfaction = v[17], &clclOpt = v[18], &permaOpt = v[19], &resOpt = v[20], &statcorrOpt = v[21],
         &aridareaOpt = v[22], &fractionalRoutingOpt = v[23], &riverEvapoOpt = v[24], &aggrNUsGloLakResOpt = v[25], &resYearOpt = v[27],
-        &resYearReference = v[28], &antNatOpt = v[31], &calc_wtemp = v[34], &glacierOpt = v[35];
+        &resYearReference = v[28], &resYearFirstToUse = v[29], &resYearLastToUse = v[30], &antNatOpt = v[31], &calc_wtemp = v[34], &glacierOpt = v[35];
     std::string input_dir, output_dir, climate_dir, routing_dir, water_use_dir;
     int start_year = 0, end_year = 0;
     void require_canonical() const;  // throws for option values outside the implemented hot path
@@ -110,6 +110,7 @@ class routingClass {
     const double minStorVol = 1.e-15;
     void init(short nBasins, const ConfigFile &cfg, WghmStateFile &, AdditionalOutputInputFile &);  // routing.cpp:131-742 (K_release :388-392)
     void annualInit(short year, int start_month, AdditionalOutputInputFile &);  // :979-1495
+    void pushYearly();  // statics / storages annualInit changed (reservoirs coming on line, resYearOpt 1) -> device
     void initLakeDepthActive(const calibParamClass &);                        // :5613-5619
     void initWetlDepthActive(const calibParamClass &);                        // :5621-5628
     void setStoragesToZero();                                                 // :789-847
@@ -150,7 +151,8 @@ class routingClass {
         G_riverAreaFracNextTimestep_Frac, K_release, G_riverDischarge;
     Grid<int16_t> statusStarted_landAreaFracNextTimestep;
     Grid<int8_t> G_res_type, G_start_month, G_reg_lake_status, G_LDD;
-    Grid<int32_t> G_res_start_year, G_downstreamCell, G_routOrder;
+    Grid<int32_t> G_res_start_year, G_downstreamCell, G_routOrder, G_outflow_cell_assignment;
+    bool yearlyChanged = false;  // the last annualInit changed reservoir statics / storages the device holds (resYearOpt 1)
     short statusStarted_updateGloResPrevYear = 0;
     std::vector<short> statusStarted_landfreq;
 
