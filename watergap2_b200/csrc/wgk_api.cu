@@ -1790,6 +1790,14 @@ int wgk_debug_insitu(wgk_ctx *c, unsigned long long out[8]) {
     CU(cudaMemcpyToSymbol(wgk::g_insitu, z, sizeof z));
     return WGK_OK;
 }
+// development builds only: cycles per phase of the thread-per-cell vertical step, out[2][2][8] (see g_vphase); read and reset
+int wgk_debug_vphases(wgk_ctx *c, unsigned long long *out) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyFromSymbol(out, wgk::g_vphase, sizeof(unsigned long long) * 32));
+    unsigned long long z[32] = {0};
+    CU(cudaMemcpyToSymbol(wgk::g_vphase, z, sizeof z));
+    return WGK_OK;
+}
 // development builds only: cycles of every level-0 vertical warp on four days, out[4][1024]
 int wgk_debug_warpdur(wgk_ctx *c, unsigned int *out) {
     CU(cudaStreamSynchronize(c->stream));

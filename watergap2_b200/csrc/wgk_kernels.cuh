@@ -206,10 +206,26 @@ constexpr int SNOW_CH = WGK_SNOW_CH, SNOW_NCH = 100 / WGK_SNOW_CH, VBLOCK = WGK_
 #else
 #define WGK_TPC_MINB_EFF WGK_TPC_MINB
 #endif
+#ifndef WGK_SNOW_NBUF
+#define WGK_SNOW_NBUF 2  // staged chunks in flight per thread
+#endif
+#ifndef WGK_BAND_FORM
+#define WGK_BAND_FORM 1  // 0: band by band, 1: the bands of a chunk stage by stage (see vertical_cell)
+#endif
+constexpr int SNOW_NBUF = WGK_SNOW_NBUF;
+static_assert(SNOW_NBUF >= 2 && SNOW_NBUF <= SNOW_NCH && SNOW_NBUF <= 8, "stage depth");
 struct SnowStage {
-    double s[2][SNOW_CH][VBLOCK];
-    int32_t e[2][SNOW_CH][VBLOCK];
+    double s[SNOW_NBUF][SNOW_CH][VBLOCK];
+    int32_t e[SNOW_NBUF][SNOW_CH][VBLOCK];
 };
+// before chunk c is read: all but the youngest min(NBUF - 1, chunks after c) copy groups must have landed
+__device__ __forceinline__ void stage_wait(const int remaining) {
+    if (remaining >= SNOW_NBUF - 1) { __pipeline_wait_prior(SNOW_NBUF - 1); return; }
+#pragma unroll
+    for (int n = SNOW_NBUF - 2; n >= 1; n--)
+        if (remaining == n) { __pipeline_wait_prior(n); return; }
+    __pipeline_wait_prior(0);
+}
 __device__ __forceinline__ void stage_issue(SnowStage *st, const int buf, const int t, const double *S, const int32_t *E,
                                             const size_t sstride, const size_t estride) {
 #pragma unroll
@@ -356,6 +372,20 @@ __device__ __forceinline__ LocalFlux local_flux_load(const WgkParams &p, const i
     return fx;
 }
 
+#ifdef WGK_PHASE_TIMING  // development aid: cycles per phase of vertical_cell / local routing, per warp (tools/vphase_timing.py)
+__device__ unsigned long long g_vphase[2][2][8];  // [level 0?][warp runs the band loop?][phase 0..6 cycles summed over warps, 7 = warps]
+#define WGK_VT_BEGIN() long long vt_ = clock64(), vt_d_[7] = {0, 0, 0, 0, 0, 0, 0}; int vt_lane_ = 0, vt_cls_ = 0
+#define WGK_VT_CLASS(run_) do { const unsigned b_ = __ballot_sync(__activemask(), (run_)); vt_cls_ = b_ != 0; \
+    vt_lane_ = (b_ ? __ffs(b_) : __ffs(__activemask())) - 1; } while (0)
+#define WGK_VT(k_) do { const long long t_ = clock64(); vt_d_[k_] += t_ - vt_; vt_ = t_; } while (0)
+#define WGK_VT_FLUSH(l0_) do { if ((int)(threadIdx.x & 31) == vt_lane_) { \
+    for (int k_ = 0; k_ < 7; k_++) atomicAdd(&g_vphase[l0_][vt_cls_][k_], (unsigned long long)vt_d_[k_]); atomicAdd(&g_vphase[l0_][vt_cls_][7], 1ull); } } while (0)
+#else
+#define WGK_VT_BEGIN() do { } while (0)
+#define WGK_VT_CLASS(run_) do { } while (0)
+#define WGK_VT(k_) do { } while (0)
+#define WGK_VT_FLUSH(l0_) do { } while (0)
+#endif
 // ----------------------------------------------------------------------------------------
 // vertical water balance, one thread per cell (throughput form, used when members x cells fill the GPU)
 // ----------------------------------------------------------------------------------------
@@ -367,6 +397,7 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
     const size_t i = mi(p, m, r);
     const size_t q = qi(p, m, r);
     const int tid = threadIdx.x & (VBLOCK - 1);  // column of the (128-thread) staging block handed in by the kernel
+    WGK_VT_BEGIN();
     const size_t bs = band_stride(p);  // distance between two bands of the member's snow column
     double *__restrict__ S = a.snow_bands + bi(p, m, r, WGK_NBAND_K) + bs;
     const int32_t *__restrict__ E = a.s_elev32 + r + p.stride;
@@ -399,6 +430,7 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
     else lafPrev = landAreaFrac;
 
     if (1 != in_tbc) return false;  // daily.cpp:177
+    WGK_VT(0);
 
     // second round: the land-cover tables (18 entries each, cache resident)
     const double ddf = in_degday * a.lct_ddf[lc];  // (M_DEGDAY_F * ddf_lct) * (...) keeps the reference association
@@ -414,9 +446,11 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
         const double t_top = (double)f.y - ((double)in_de_max * P_T_GRADNT), t_bot = (double)f.y - ((double)in_de_min * P_T_GRADNT);
         bare = noland || (ddf >= 0. && t_top > P_T_SNOWFZ && t_bot > P_T_SNOWFZ);
     }
+    WGK_VT_CLASS(!bare);
+    WGK_VT(1);
     if (!bare) {
-        stage_issue(st, 0, tid, S, E, bs, p.stride);
-        stage_issue(st, 1, tid, S + (size_t)SNOW_CH * bs, E + (size_t)SNOW_CH * p.stride, bs, p.stride);
+#pragma unroll
+        for (int b = 0; b < SNOW_NBUF; b++) stage_issue(st, b, tid, S + (size_t)b * SNOW_CH * bs, E + (size_t)b * SNOW_CH * p.stride, bs, p.stride);
     }
 
     double dailyPrec = (double)f.x;
@@ -542,6 +576,7 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
     a.canopy[i] = canopy;
     if (dailySoilPET < 0.) dailySoilPET = 0.0;
 
+    WGK_VT(2);
     // snow in 100 elevation bands (:913-1062)
     double TempElevMax = 0., snowStorageChange = 0., snow = 0.;
     int nz = 0;
@@ -571,10 +606,70 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
         // ~25-instruction division per band; the result is the correctly rounded quotient
         const double inv_laf = 1. / landAreaFrac;
         int thresh_elev = 0;
+#if WGK_BAND_FORM == 1
+        // Staged form: the bands of a chunk go through every stage together (rescale, 1000 mm rule, temperatures, the cold and
+        // the warm branch as selects, the ordered sums), so that the instruction stream the scheduler sees is already
+        // interleaved: the ~15 dependent FP64 operations of a band overlap with those of the other bands of the chunk, and
+        // the only band-to-band dependencies left are the integer select of the 1000 mm rule and the four running sums
+        // (same additions in the same order as the band-by-band form: same bits).
         for (int c = 0; c < SNOW_NCH; c++) {
-            const int buf = c & 1;
-            if (c + 1 < SNOW_NCH) __pipeline_wait_prior(1);
-            else __pipeline_wait_prior(0);
+            const int buf = c % SNOW_NBUF;
+            stage_wait(SNOW_NCH - 1 - c);
+            double s0[SNOW_CH], sv[SNOW_CH], tv[SNOW_CH], ev[SNOW_CH], mv[SNOW_CH];
+            int el[SNOW_CH];
+#pragma unroll
+            for (int k = 0; k < SNOW_CH; k++) {
+                el[k] = st->e[buf][k][tid];
+                const double num = st->s[buf][k][tid] * lafPrev;
+                double s = num * inv_laf;
+                s = fma(fma(-landAreaFrac, s, num), inv_laf, s);
+                s0[k] = (fabs(s) <= MIN_STOR_VOL) ? 0. : s;
+            }
+#pragma unroll
+            for (int k = 0; k < SNOW_CH; k++) {  // the 1000 mm rule (:958-976): integer selects only
+                const bool big = s0[k] > 1000.;
+                const bool first = big && thresh_elev == 0;
+                const int e_eff = (big && !first && thresh_elev > 0) ? thresh_elev : el[k];
+                thresh_elev = first ? el[k] : thresh_elev;
+                el[k] = e_eff;
+            }
+#pragma unroll
+            for (int k = 0; k < SNOW_CH; k++) tv[k] = dailyTempC - ((el[k] - elev0) * P_T_GRADNT);
+            if (c == 0) TempElevMax = tv[0];
+#pragma unroll
+            for (int k = 0; k < SNOW_CH; k++) {  // accumulation and sublimation below the freezing threshold (:982-999)
+                const bool cold = tv[k] <= P_T_SNOWFZ;
+                const double s_in = s0[k] + daily_prec_to_soil;
+                const bool over = s_in > dailySoilPET;
+                ev[k] = cold ? (over ? dailySoilPET : s_in) : 0.;
+                sv[k] = cold ? (over ? s_in - dailySoilPET : 0.) : s0[k];
+                mv[k] = cold ? 0. : daily_prec_to_soil;
+            }
+#pragma unroll
+            for (int k = 0; k < SNOW_CH; k++) {  // melt above the melting threshold (:1003-1019)
+                const double s = sv[k];
+                const bool melt = tv[k] > P_T_SNOWMT && !(s < 0.);
+                const double m_raw = ddf * (tv[k] - P_T_SNOWMT);
+                const bool all = m_raw > s;
+                mv[k] += melt ? (all ? s : m_raw) : 0.;
+                sv[k] = melt ? (all ? 0. : s - m_raw) : s;
+            }
+#pragma unroll
+            for (int k = 0; k < SNOW_CH; k++) {
+                dailySnowEvapo += ev[k];
+                snowStorageChange += sv[k] - s0[k];
+                snow += sv[k];
+                dailyEffPrec += mv[k];
+                nz |= (sv[k] != 0.);
+                S[(size_t)(c * SNOW_CH + k) * bs] = sv[k];
+            }
+            if (c + SNOW_NBUF < SNOW_NCH)
+                stage_issue(st, buf, tid, S + (size_t)(c + SNOW_NBUF) * SNOW_CH * bs, E + (size_t)(c + SNOW_NBUF) * SNOW_CH * p.stride, bs, p.stride);
+        }
+#else
+        for (int c = 0; c < SNOW_NCH; c++) {
+            const int buf = c % SNOW_NBUF;
+            stage_wait(SNOW_NCH - 1 - c);
 #pragma unroll
             for (int k = 0; k < SNOW_CH; k++) {
                 const int elev_e = st->e[buf][k][tid];
@@ -619,9 +714,10 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
                 S[(size_t)(c * SNOW_CH + k) * bs] = s;
             }
             // refill the buffer just consumed with the chunk after next (same thread: no barrier)
-            if (c + 2 < SNOW_NCH)
-                stage_issue(st, buf, tid, S + (size_t)(c + 2) * SNOW_CH * bs, E + (size_t)(c + 2) * SNOW_CH * p.stride, bs, p.stride);
+            if (c + SNOW_NBUF < SNOW_NCH)
+                stage_issue(st, buf, tid, S + (size_t)(c + SNOW_NBUF) * SNOW_CH * bs, E + (size_t)(c + SNOW_NBUF) * SNOW_CH * p.stride, bs, p.stride);
         }
+#endif
         snow /= 100.;
         dailyEffPrec /= 100.;
         dailySnowEvapo /= 100.;
@@ -630,6 +726,7 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
     }
     a.snow[i] = snow;
     if (!bare) a.s_snowfree[i] = (int8_t)(nz == 0);
+    WGK_VT(3);
 
     double gw_recharge_out = 0.;
     // inputs of the soil part: one round of loads
@@ -644,6 +741,7 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
         immediate_runoff = 0.5 * dailyEffPrec * builtup;
         dailyEffPrec -= immediate_runoff;
     }
+    WGK_VT(4);
 
     // soil and AET (:1080-1239)
     const double Smax = (double)in_smax;
@@ -742,6 +840,8 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
         fx->surface_runoff = total_daily_runoff - daily_gw_recharge;
         fx->gw_recharge = gw_recharge_out;
     }
+    WGK_VT(5);
+    WGK_VT_FLUSH(r < p.level_off[1]);
     return true;
 }
 
