@@ -308,13 +308,16 @@ def run_headline(args, D, w, ini, forcing):
     wavefront = cls["other"][1] == 0
     lv = np.bincount(m.levels(), minlength=m.nlevels)
     form = os.environ.get("WGK_VERTICAL_FORM") or ("bands" if ncell * args.members < 32768 else "cells")
+    fused = wavefront and bool(m.schedule & 2)  # one task per (day, level): k_level_day = vertical + local routing + river + post
     vname = {"cells": "k_cells_pre_tpc", "bands": "k_cells_pre<VCfg<5,4,1>>", "bands2": "k_cells_pre<VCfg<2,5,0>>"}[form] if wavefront else \
             {"cells": "k_vertical_tpc", "bands": "k_vertical<VCfg<5,4,1>>", "bands2": "k_vertical<VCfg<2,5,0>>"}[form]
+    if fused and cls["river_level"][1] == 0:
+        vname = "k_level_day"
     names = {"vertical": vname, "river_level": "k_river_level" if wavefront else "k_route_level",
              "tail": "k_tail_chunk" if wavefront else "k_route_tail", "other": "k_route_local + k_route_post"}
     day_ms = sum(v[0] for v in cls.values())
     dom_key = max(cls, key=lambda k: cls[k][0])
-    bytes_v_day = (BYTES_VERTICAL + (BYTES_LOCAL_ROUTING if wavefront else 0)) * ncell * args.members
+    bytes_v_day = (BYTES_VERTICAL + (BYTES_ROUTING if vname == "k_level_day" else BYTES_LOCAL_ROUTING if wavefront else 0)) * ncell * args.members
     in_graph = None
     if wavefront and m.nlevels > 0:
         m.stamps(True)
@@ -325,17 +328,23 @@ def run_headline(args, D, w, ini, forcing):
         m.synchronize()
         st = m.stamps(False, read=True)[:, :, 20:360].astype(np.int64)
         vdur, rdur = st[0, 1] - st[0, 0], st[1, 1] - st[1, 0]
+        if vname == "k_level_day":  # one task: first warp into its V part -> last warp out of its R part
+            vdur = st[1, 1] - st[0, 0]
         period = st[0, 0][1:] - st[0, 0][:-1]
         n0 = int(lv[0])
-        b0 = (BYTES_VERTICAL + BYTES_LOCAL_ROUTING) * n0 * args.members
+        b0 = (BYTES_VERTICAL + (BYTES_ROUTING if vname == "k_level_day" else BYTES_LOCAL_ROUTING)) * n0 * args.members
         in_graph = {"level0_cells": n0, "vertical_task_us": round(float(np.median(vdur)) / 1e3, 2),
                     "river_task_us": round(float(np.median(rdur)) / 1e3, 2), "day_period_us": round(float(np.median(period)) / 1e3, 2),
                     "day_period_mean_us": round(float(np.mean(period)) / 1e3, 2),
                     "vertical_task_bytes": b0, "vertical_task_gbs": round(b0 / (float(np.median(vdur)) * 1e-9) / 1e9, 1),
                     "vertical_task_frac": round(b0 / (float(np.median(vdur)) * 1e-9) / 1e9 / peak, 4),
                     "how": "%globaltimer stamps of the level-0 tasks inside the running 365-day graph (wgk_stamps), median over days 20..360 "
-                           "of an extra simulated year outside the timed region; the level-0 vertical task is the head of the own-cell "
-                           "recurrence V(d,0) -> R(d,0) -> V(d+1,0) that bounds a single member"}
+                           "of an extra simulated year outside the timed region; " +
+                           ("vertical_task = the whole fused task k_level_day(d, 0) (first warp into its vertical part -> last warp out of "
+                            "its river part), river_task = the span of the river parts inside it; the own-cell recurrence "
+                            "F(d,l) -> F(d+1,l) of every level bounds a single member" if vname == "k_level_day" else
+                            "the level-0 vertical task is the head of the own-cell "
+                            "recurrence V(d,0) -> R(d,0) -> V(d+1,0) that bounds a single member")}
     traffic = None
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (tools/ncu_summary.py traffic)
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
@@ -360,7 +369,8 @@ def run_headline(args, D, w, ini, forcing):
             "algorithmic_bytes_per_day": bytes_v_day, "achieved": round(ach_v, 1), "frac": round(ach_v / peak, 4),
             "traffic_first_launch": traffic,
             "how": "CUDA event pair around every launch of one simulated day of the timed schedule (wgk_profile_schedule, plain "
-                   "launches in task order, mean of 10 days); bytes = (2099 vertical + 300 local routing) x cells x members",
+                   "launches in task order, mean of 10 days); bytes = " + ("(2099 vertical + 617 routing)" if vname == "k_level_day" else
+                   "(2099 vertical + 300 local routing)") + " x cells x members",
             "in_graph": in_graph} if dom_key == "vertical" else {"name": names[dom_key], "share_of_kernel_time": round(cls[dom_key][0] / day_ms, 4)},
         "kernel_classes_ms_per_day": {names[k]: {"ms": round(v[0], 5), "launches": v[1]} for k, v in cls.items() if v[1]},
         "fp64": {"peak_tflops_measured": round(fp64_peak, 2), "how": "k_fp64_peak: 8 independent DFMA chains per thread, 8 x 256 threads per SM, best of 3",

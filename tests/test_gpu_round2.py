@@ -472,17 +472,17 @@ def test_fused_level_tasks_are_bit_identical(world3000, monkeypatch):
     monkeypatch.setenv("WGK_VERTICAL_FORM", "cells")
     monkeypatch.setenv("WGK_TAIL_THRESHOLD", "16")  # several wide levels on the small world
     out = []
-    for mode in ("split", "fused", "fused0"):
+    for mode, wave_tail in (("split", ""), ("fused", "0"), ("fused", "16"), ("fusedfull", "0"), ("fused0", "")):
         monkeypatch.setenv("WGK_LEVEL_TASKS", mode)
+        monkeypatch.setenv("WGK_WAVE_TAIL_THRESHOLD", wave_tail) if wave_tail else monkeypatch.delenv("WGK_WAVE_TAIL_THRESHOLD", raising=False)
         m = wg.Model(w.ng)
         assert (m.schedule & 2 != 0) == (mode != "split")
         m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
         m.load(ini)
         m.forcing_reserve(59)
         slot = 0
-        for mon in (1, 2):
+        for mon, nd in ((1, 31), (2, 28)):
             f = sw.forcing_month(w, 1901, mon)
-            nd = f["P"].shape[0]
             m.set_forcing(slot, nd, f["P"], f["T"], f["SW"], f["LW"])
             slot += nd
         m.record_cells(cells, 45)

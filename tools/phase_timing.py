@@ -10,10 +10,11 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 import watergap2_b200 as wg  # noqa: E402
 
-lib = os.path.join(ROOT, "watergap2_b200", "libwgk_phase.so")
-subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
-                       "-std=c++17", "-DWGK_PHASE_TIMING", "-shared", "-Xcompiler", "-fPIC", "--cudart", "static", "-o", lib,
-                       os.path.join(ROOT, "watergap2_b200", "csrc", "wgk_api.cu")])
+lib = os.environ.get("WGK_LIB") or os.path.join(ROOT, "watergap2_b200", "libwgk_phase.so")
+if not os.environ.get("WGK_LIB"):
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
+                           "-std=c++17", "-DWGK_PHASE_TIMING", "-shared", "-Xcompiler", "-fPIC", "--cudart", "static", "-o", lib,
+                           os.path.join(ROOT, "watergap2_b200", "csrc", "wgk_api.cu")])
 if len(sys.argv) > 1 and sys.argv[1] == "--build-only":
     sys.exit(0)
 wg.LIB_PATH = lib

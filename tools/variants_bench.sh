@@ -3,8 +3,11 @@
 #   gpurun -- 'bash tools/variants_bench.sh tag name1 name2 ...'   (extra environment: VENV="WGK_X=1 ...")
 tag=$1; shift
 mkdir -p gpurun_out
+[ -n "$GRAFT_REPO_ROOT" ] || { echo "run on the GPU box (the variant replaces watergap2_b200/libwgk.so of the scratch copy)"; exit 1; }
 for v in "$@"; do
-  env WGK_LIB=$PWD/variants/libwgk_$v.so $VENV timeout 300 python bench.py --steps ${STEPS:-6} --warmup 3 --no-cpu --legs none > gpurun_out/${tag}_$v.json 2> gpurun_out/${tag}_$v.err
+  # libwghost.so links watergap2_b200/libwgk.so: the variant must BE that file, or two copies of the library get mixed
+  cp variants/libwgk_$v.so watergap2_b200/libwgk.so
+  env $VENV timeout 300 python bench.py --steps ${STEPS:-6} --warmup 3 --no-cpu --legs none > gpurun_out/${tag}_$v.json 2> gpurun_out/${tag}_$v.err
   python - "$v" gpurun_out/${tag}_$v.json <<'PY'
 import sys, json
 v, f = sys.argv[1:3]

@@ -18,7 +18,7 @@ import watergap2_b200 as wg  # noqa: E402
 w, ini = bench.build_inputs()
 forcing = bench.year_forcing(w)
 names = ["first loads", "tables+classify", "head (LAI, PET, canopy)", "bands", "soil loads", "soil", "(unused)"]
-for use_graph in (1, 0):
+for use_graph in ((1, 0) if not os.environ.get("GRAPH_ONLY") else (1,)):
     topo = ini["_topology"]
     m = wg.Model(w.ng, nmember=1, use_graph=use_graph)
     m.set_topology(topo["rout_order"], topo["outflow_cell"], cell_class=wg.cell_classes(ini))
@@ -45,3 +45,10 @@ for use_graph in (1, 0):
             ph = out[l0, cls, :7].astype(float) / n / 1965.0
             print(f"  {'level 0' if l0 else 'levels >0'} {'band-loop warps' if cls else 'bare warps     '} n/day {n / 365:7.1f}  sum {ph.sum():6.2f} us: "
                   + ", ".join(f"{names[k]} {ph[k]:.2f}" for k in range(6)))
+    wd = np.zeros((4, 1024), np.uint32)
+    L.wgk_debug_warpdur.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.wgk_debug_warpdur(m._c, wd.ctypes.data)
+    for k, nm in enumerate(["day 100: V part", "day 100: V + R", "day 200: V part", "day 200: V + R"]):
+        x = wd[k][wd[k] > 0] / 1965.0
+        if x.size:
+            print(f"  level-0 warps, {nm}: n {x.size}, mean {x.mean():.1f}, p50 {np.median(x):.1f}, p90 {np.percentile(x, 90):.1f}, p99 {np.percentile(x, 99):.1f}, max {x.max():.1f} us")

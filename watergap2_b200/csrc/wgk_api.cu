@@ -130,6 +130,9 @@ struct wgk_ctx {
     int32_t *d_cal_days = nullptr;
     double *d_qbuf = nullptr;
     std::vector<int> chunk_lo;  // tail chunks: levels [chunk_lo[c], chunk_lo[c+1])
+    int wave_level0 = 0;             // the wavefront's own split into wide levels [0, wave_level0) and tail chunks (fused level
+    std::vector<int> wave_chunk_lo;  // tasks treat every level as wide; otherwise = tail_level0 / chunk_lo)
+    int wave_tail_threshold = -1;    // < 0: the context's tail threshold
 
     // CUDA graphs of the (day, level) wavefront, one per call length
     std::map<int, cudaGraphExec_t> graphs;
@@ -140,6 +143,7 @@ struct wgk_ctx {
     bool month_acc = false;     // EnKF bridge: accumulate the daily WghmStateFile entries of the month
     int month_days = 0;
     bool whole_day = false;     // many members: whole-grid kernels day after day instead of the (day, level) wavefront
+    int level_edges = 0;        // fused level tasks: 0 programmatic edge from the upstream level, 1 full edge
     int level_tasks = 0;        // wavefront: V(d, l) and R(d, l) of a wide level as one task (k_level_day): 0 no, 1 every wide level
                                 // (programmatic edges between the levels), 2 level 0 only (headwater cells: no upstream level)
     int form = 0;               // vertical kernel form: 0 thread per cell, 1 band-parallel 5 threads/cell, 2 band-parallel 2 threads/cell
@@ -276,6 +280,10 @@ WgkParams make_params(const wgk_ctx *c) {
     p.mpad = c->mpad;
     p.ppad = c->ppad;
     p.stamps = c->d_stamps;
+    {
+        const char *e = getenv("WGK_STAMP_LEVEL");
+        p.stamp_level = e ? atoi(e) : 0;
+    }
     return p;
 }
 
@@ -362,11 +370,11 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
     int n = 0;
     const dim3 block = cell_block(c, 128);
     for (int d = 0; d < ndays; d++) {
-        for (int l = 0; l < c->tail_level0; l++) {
+        for (int l = 0; l < c->wave_level0; l++) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
             const dim3 g = cell_grid(c, end - begin, 128);
             if (c->level_tasks == 1 || (c->level_tasks == 2 && l == 0)) {
-                WGK_KW(c, k_level_day)<<<g, block, 0, c->stream>>>(p, d, l);
+                WGK_KW(c, k_level_day)<<<cell_grid(c, end - begin, wgk::VBLOCK), cell_block(c, wgk::VBLOCK), 0, c->stream>>>(p, d, l);
                 n += 1;
                 continue;
             }
@@ -374,8 +382,8 @@ int enqueue_wavefront_serial(wgk_ctx *c, const WgkParams &p, int ndays) {
             WGK_KW(c, k_river_level)<<<g, block, 0, c->stream>>>(p, d, l);
             n += 2;
         }
-        for (size_t k = 0; k + 1 < c->chunk_lo.size(); k++) {
-            const int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
+        for (size_t k = 0; k + 1 < c->wave_chunk_lo.size(); k++) {
+            const int lo = c->wave_chunk_lo[k], hi = c->wave_chunk_lo[k + 1];
             const int begin = c->level_off[lo], end = c->level_off[hi];
             launch_cells_pre(c, p, d, begin, end);
             (c->opt.subtract_use > 0 ? wgk_wu::k_tail_chunk : wgk::k_tail_chunk)<<<c->nmember, 256, 0, c->stream>>>(p, d, lo, hi);
@@ -415,8 +423,8 @@ int enqueue_whole_days(wgk_ctx *c, const WgkParams &p, int ndays) {
 int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphExec_t *out, int *nnodes) {
     cudaGraph_t g;
     CU(cudaGraphCreate(&g, 0));
-    const int W = c->tail_level0;
-    const int C = (int)c->chunk_lo.size() - 1 > 0 ? (int)c->chunk_lo.size() - 1 : 0;
+    const int W = c->wave_level0;
+    const int C = (int)c->wave_chunk_lo.size() - 1 > 0 ? (int)c->wave_chunk_lo.size() - 1 : 0;
     std::vector<cudaGraphNode_t> prevW(W, nullptr), prevT(C, nullptr), dayEnd(ndays, nullptr);
     int count = 0;
     auto add = [&](void *fn, dim3 grid, dim3 block, void **args, std::vector<cudaGraphNode_t> deps, cudaGraphNode_t *node) -> cudaError_t {
@@ -450,8 +458,10 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
                 // kernel, after its vertical part, for the upstream grid to complete
                 void *a[] = {&pp, &dd, &ll};
                 cudaGraphNode_t node;
-                CU(add((void *)WGK_KW(c, k_level_day), grid, cell_block(c, 128), a, {prevW[l], first_sweep ? reuse : nullptr}, &node));
-                if (last) {
+                const bool plain = c->level_edges == 1;  // full edge from the upstream level instead of the programmatic one
+                CU(add((void *)WGK_KW(c, k_level_day), cell_grid(c, end - begin, wgk::VBLOCK), cell_block(c, wgk::VBLOCK), a,
+                       {prevW[l], plain ? last : nullptr, first_sweep ? reuse : nullptr}, &node));
+                if (last && !plain) {
                     cudaGraphEdgeData ed{};
                     ed.from_port = cudaGraphKernelNodePortLaunchCompletion;
                     ed.to_port = 0;
@@ -477,7 +487,7 @@ int build_wavefront_graph(wgk_ctx *c, const WgkParams &p, int ndays, cudaGraphEx
             last = node;
         }
         for (int k = 0; k < C; k++) {
-            int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
+            int lo = c->wave_chunk_lo[k], hi = c->wave_chunk_lo[k + 1];
             int begin = c->level_off[lo], end = c->level_off[hi], dd = d;
             void *a1[] = {&pp, &dd, &begin, &end};
             cudaGraphNode_t pre, sweep;
@@ -690,16 +700,27 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
         c->mpad = c->mm ? (nmember + 31) / 32 * 32 : nmember;
         c->ppad = c->mm ? (npset == 1 ? 1 : (npset + 31) / 32 * 32) : npset;
     }
-    {   // Tasks of the wavefront: two kernels per (day, wide level) - vertical balance + local routing, then river + post once the
-        // upstream level is through.  Opt-in (WGK_LEVEL_TASKS): "fused" = one kernel per (day, level) with a programmatic
-        // (launch-completion) edge from the upstream level and griddepcontrol.wait between the two parts (k_level_day);
-        // "fused0" = only the headwater level, which has no upstream, as one kernel.  Both were measured SLOWER on B200
-        // (0.5 degree grid, one member, ms per simulated year: split 22.2, fused 23.7, fused0 23.8): the fused kernel takes
-        // 56 us where the two take 35 + 11 us plus a 6 us (median) edge, so the own-cell recurrence V(d,0) -> R(d,0) -> V(d+1,0)
-        // gets longer, not shorter.  Also measured without effect: launch priority on the level-0/1 nodes, the discharge-buffer
-        // reuse edge on every 8th day only (median edge 3.5 us instead of 6, same mean).
-        const char *e = getenv("WGK_LEVEL_TASKS");  // "split" | "fused" | "fused0"
-        c->level_tasks = c->form != 0 ? 0 : (e && !strcmp(e, "fused")) ? 1 : (e && !strcmp(e, "fused0")) ? 2 : 0;
+    {   // Tasks of the wavefront.  "split": two kernels per (day, wide level) - vertical balance + local routing, then river +
+        // post once the upstream level is through - and a persistent one-CTA sweep per narrow level.  "fused": ONE kernel per
+        // (day, level) for every level (k_level_day: V part, griddepcontrol.wait, R part) with a programmatic
+        // (launch-completion) edge from the upstream level, so that the grid starts while the upstream grid runs; "fusedfull":
+        // the same with a full edge; "fused0": only the headwater level.  Measured on B200 (0.5 degree grid, one member, ms per
+        // simulated year; k_level_day compiled for 2 resident CTAs per SM = no register cap, WGK_LEVEL_MINB):
+        //   split, narrow levels <= 256 cells as tail chunks   21.7        fused, tail chunks <= 256 cells   24.0
+        //   split, every level wide                            20.8        fused, tail chunks <= 8 cells     22.3
+        //   fusedfull, every level a fused task                27.0        fused, every level a fused task   19.9
+        // With the 128-register cap of the thread-per-cell kernels the fused task loses (20.6, and 23.7 with tail chunks - the
+        // round-2 measurement that had kept "split" the default): the V and R parts share one register budget.  The narrow
+        // levels must be fused tasks as well: every level has the own-cell recurrence V(d,l) -> R(d,l) -> V(d+1,l), and the
+        // slowest one paces the whole wavefront.
+        const char *e = getenv("WGK_LEVEL_TASKS");  // "split" | "fused" | "fused0" | "fusedfull"
+        const bool fused_default = c->form == 0 && !c->mm && !c->whole_day && c->opt.subtract_use == 0;
+        const int want = (e && (!strcmp(e, "fused") || !strcmp(e, "fusedfull"))) ? 1 : (e && !strcmp(e, "fused0")) ? 2 : (e && !strcmp(e, "split")) ? 0
+                         : (fused_default ? 1 : 0);
+        c->level_tasks = c->form != 0 ? 0 : want;
+        c->level_edges = (e && !strcmp(e, "fusedfull")) ? 1 : 0;
+        const char *t = getenv("WGK_WAVE_TAIL_THRESHOLD");  // narrow levels of the wavefront as tail chunks up to this many cells
+        c->wave_tail_threshold = t ? atoi(t) : (c->level_tasks == 1 ? 0 : -1);
     }
     if (c->opt.tail_threshold <= 0) {
         const char *e = getenv("WGK_TAIL_THRESHOLD");
@@ -842,10 +863,20 @@ int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downs
     // device position: rank order, stably re-sorted by class inside each level
     std::vector<int32_t> r_of_pos(ng), pos_of_r(ng);
     for (int r = 0; r < ng; r++) r_of_pos[r] = r;
-    if (!c->cell_class.empty())
+    if (!c->cell_class.empty()) {
+        const char *e = getenv("WGK_CLASS_ORDER");  // "asc" | "desc" | "cost"
+        const int mode = (e && !strcmp(e, "desc")) ? 1 : (e && !strcmp(e, "cost")) ? 2 : 0;
+        auto key = [&](int r) -> int {
+            const int k = c->cell_class[cell_of_r[r]];
+            if (mode == 0) return k;
+            if (mode == 1) return 255 - k;
+            const int cost = 3 * ((k >> 2) & 1) + (k & 1) + ((k >> 1) & 1);  // global water body, local lake, local wetland
+            return (7 - cost) * 256 + k;
+        };
         for (int l = 0; l < c->nlevels; l++)
             std::stable_sort(r_of_pos.begin() + c->level_off[l], r_of_pos.begin() + c->level_off[l + 1],
-                             [&](int a, int b) { return c->cell_class[cell_of_r[a]] < c->cell_class[cell_of_r[b]]; });
+                             [&](int a, int b) { return key(a) < key(b); });
+    }
     for (int x = 0; x < ng; x++) pos_of_r[r_of_pos[x]] = x;
     c->rank_of_cell.assign(ng, -1);
     c->cell_of_rank.assign(ng, -1);
@@ -880,6 +911,18 @@ int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downs
     c->chunk_lo.clear();
     for (int l = c->tail_level0; l < c->nlevels; l += levels_per_chunk()) c->chunk_lo.push_back(l);
     if (c->tail_level0 < c->nlevels) c->chunk_lo.push_back(c->nlevels);
+    c->wave_level0 = c->tail_level0;
+    c->wave_chunk_lo = c->chunk_lo;
+    if (c->wave_tail_threshold >= 0 && !c->mm) {
+        c->wave_level0 = c->nlevels;
+        for (int l = c->nlevels - 1; l >= 0; l--) {
+            if (c->level_off[l + 1] - c->level_off[l] <= c->wave_tail_threshold) c->wave_level0 = l;
+            else break;
+        }
+        c->wave_chunk_lo.clear();
+        for (int l = c->wave_level0; l < c->nlevels; l += levels_per_chunk()) c->wave_chunk_lo.push_back(l);
+        if (c->wave_level0 < c->nlevels) c->wave_chunk_lo.push_back(c->nlevels);
+    }
     auto upload = [&](int32_t *&dptr, const std::vector<int32_t> &v) -> cudaError_t {
         if (dptr) cudaFree(dptr);
         dptr = nullptr;
@@ -1721,18 +1764,18 @@ int wgk_profile_schedule(wgk_ctx *c, int day, int month, int dom, int slot, floa
         if (c->tail_level0 < c->nlevels) timed(2, [&] { (c->opt.subtract_use > 0 ? wgk_wu::k_route_tail : wgk::k_route_tail)<<<c->nmember, 256, 0, c->stream>>>(p, 0, c->tail_level0, c->nlevels); });
         timed(3, [&] { WGK_K(c, k_route_post)<<<grid, block, 0, c->stream>>>(p); });
     } else {
-        for (int l = 0; l < c->tail_level0; l++) {
+        for (int l = 0; l < c->wave_level0; l++) {
             const int begin = c->level_off[l], end = c->level_off[l + 1];
             const dim3 g = cell_grid(c, end - begin, 128);
             if (c->level_tasks == 1 || (c->level_tasks == 2 && l == 0)) {
-                timed(1, [&] { WGK_KW(c, k_level_day)<<<g, block, 0, c->stream>>>(p, 0, l); });
+                timed(0, [&] { WGK_KW(c, k_level_day)<<<cell_grid(c, end - begin, wgk::VBLOCK), cell_block(c, wgk::VBLOCK), 0, c->stream>>>(p, 0, l); });
                 continue;
             }
             timed(0, [&] { launch_cells_pre(c, p, 0, begin, end); });
             timed(1, [&] { WGK_KW(c, k_river_level)<<<g, block, 0, c->stream>>>(p, 0, l); });
         }
-        for (size_t k = 0; k + 1 < c->chunk_lo.size(); k++) {
-            const int lo = c->chunk_lo[k], hi = c->chunk_lo[k + 1];
+        for (size_t k = 0; k + 1 < c->wave_chunk_lo.size(); k++) {
+            const int lo = c->wave_chunk_lo[k], hi = c->wave_chunk_lo[k + 1];
             const int begin = c->level_off[lo], end = c->level_off[hi];
             timed(0, [&] { launch_cells_pre(c, p, 0, begin, end); });
             timed(2, [&] { (c->opt.subtract_use > 0 ? wgk_wu::k_tail_chunk : wgk::k_tail_chunk)<<<c->nmember, 256, 0, c->stream>>>(p, 0, lo, hi); });

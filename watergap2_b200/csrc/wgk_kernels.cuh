@@ -80,6 +80,7 @@ struct WgkParams {
     int mm, mpad, ppad;           // mpad / ppad: rows of the member / parameter-set arrays (members padded to 32 when mm)
     unsigned long long *stamps;   // optional (wgk_stamps): [2: V, R][2: first warp start, last warp end][STAMP_DAYS] %globaltimer ns of the
                                   // level-0 tasks of a call, i.e. their duration INSIDE the running graph; null = off
+    int stamp_level;              // level whose fused task (k_level_day) is stamped (0; WGK_STAMP_LEVEL for the timeline tools)
 };
 
 // cell-owner schedule (k_days_owner): its hand-off structures
@@ -1432,6 +1433,9 @@ __device__ unsigned int g_warpdur[4][1024];  // cycles of every level-0 vertical
 #define WGK_INSITU_WARPDUR(day_) do { const int slot_ = (day_) == 100 ? 0 : (day_) == 101 ? 1 : (day_) == 200 ? 2 : (day_) == 300 ? 3 : -1; \
     const int w_ = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; \
     if (slot_ >= 0 && (threadIdx.x & 31) == 0 && w_ < 1024 && blockIdx.y == 0) g_warpdur[slot_][w_] = (unsigned int)(clock64() - insitu_t0_); } while (0)
+#define WGK_INSITU_WARPDUR2(day_, which_) do { const int slot_ = (day_) == 100 ? (which_) : (day_) == 200 ? 2 + (which_) : -1; \
+    const int w_ = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; \
+    if (slot_ >= 0 && (threadIdx.x & 31) == 0 && w_ < 1024 && blockIdx.y == 0) g_warpdur[slot_][w_] = (unsigned int)(clock64() - insitu_t0_); } while (0)
 #define WGK_INSITU_BEGIN() const long long insitu_t0_ = clock64()
 #define WGK_INSITU_END(k_, l0_) do { if ((threadIdx.x & 31) == 0) { const unsigned long long dt_ = (unsigned long long)(clock64() - insitu_t0_); \
     atomicAdd(&g_insitu[k_], dt_); atomicAdd(&g_insitu[(k_) + 1], 1ull); if (l0_) { atomicAdd(&g_insitu[(k_) + 4], dt_); atomicAdd(&g_insitu[(k_) + 5], 1ull); } } } while (0)
@@ -1440,6 +1444,7 @@ __device__ unsigned int g_warpdur[4][1024];  // cycles of every level-0 vertical
 #define WGK_INSITU_END(k_, l0_) do { } while (0)
 #define WGK_INSITU_STAMP(kind_, which_, day_) do { } while (0)
 #define WGK_INSITU_WARPDUR(day_) do { } while (0)
+#define WGK_INSITU_WARPDUR2(day_, which_) do { } while (0)
 #endif
 
 // ----------------------------------------------------------------------------------------
@@ -2615,36 +2620,69 @@ __global__ void __launch_bounds__(VBLOCK, WGK_PRE_MINB_EFF) k_cells_pre_tpc(cons
 // upstream grid has completed and its discharge is visible.  The own-cell recurrence of a level then crosses one kernel
 // boundary per day instead of two, and the graph has half the nodes.  (Launched without a programmatic edge - plain stream
 // order - the wait returns at once.)
-__global__ void __launch_bounds__(VBLOCK, WGK_PRE_MINB_EFF) k_level_day(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
+#ifndef WGK_LEVEL_MINB
+#define WGK_LEVEL_MINB 2  // the fused task holds the V and the R part in one register budget: no cap (164 registers); with the
+                          // 128 of the split kernels it measured 20.6 instead of 19.9 ms per simulated year
+#endif
+#undef WGK_LEVEL_MINB_EFF
+#if WGK_MM
+#define WGK_LEVEL_MINB_EFF WGK_PRE_MINB_MM
+#else
+#define WGK_LEVEL_MINB_EFF WGK_LEVEL_MINB
+#endif
+__global__ void __launch_bounds__(VBLOCK, WGK_LEVEL_MINB_EFF) k_level_day(const __grid_constant__ WgkParams p, const int dayofs, const int level) {
     __shared__ SnowStage stage;
     int r, m;
     const bool on = map_thread(p, p.level_off[level], p.level_off[level + 1], r, m);
+    WGK_INSITU_BEGIN();
     if (on) {
-        if (level == 0) stamp_task(p, 0, 0, dayofs);
+        if (level == p.stamp_level) stamp_task(p, 0, 0, dayofs);
         LocalIn li;
         LocalFlux fx;
         if (vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, m, li, fx, p.cal_days[4 * dayofs + 1]);
         else route_local_cell(p, r, m, p.cal_days[4 * dayofs + 1]);
-        if (level == 0) stamp_task(p, 0, 1, dayofs);
+        if (level == p.stamp_level) stamp_task(p, 0, 1, dayofs);
+        if (level == 0) WGK_INSITU_WARPDUR2(dayofs, 0);
+    }
+    // everything the R part needs that does not come from the upstream level is loaded BEFORE the wait (own-cell values this
+    // thread has just written, statics, the indices of the upstream cells): after the wait only the gather of the upstream
+    // discharge is left between the hand-off and the arithmetic
+    size_t i = 0, q = 0;
+    RiverCtx c;
+    PostIn in;
+    int up[8];
+    c.flags = 0;
+    if (on) {
+        i = mi(p, m, r);
+        q = qi(p, m, r);
+        c = load_ctx(p, r, i, q);
+        in = post_load(p, r, m);
+#pragma unroll
+        for (int k = 0; k < 8; k++) up[k] = (c.up0 + k < c.up1) ? p.up_idx[c.up0 + k] : -1;
     }
 #ifdef __CUDA_ARCH__
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
     if (!on) return;
-    if (level == 0) stamp_task(p, 1, 0, dayofs);
-    const size_t i = mi(p, m, r), q = qi(p, m, r);
-    const RiverCtx c = load_ctx(p, r, i, q);
-    PostIn in = post_load(p, r, m);
+    if (level == p.stamp_level) stamp_task(p, 1, 0, dayofs);
     double Sr = c.prevR;
     if (c.flags & FL_ACTIVE) {
         double *qday = qbuf_of_day(p, dayofs);
         double red_ll = in.red_loc_lake;
-        Sr = route_river(p, c, r, m, i, q, gather_upstream(p, c, m, qday), p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday, nullptr,
+        // upstream inflow in routing order (= order of the += at routing.cpp:3957); a cell has at most 8 neighbours
+        double inflow_up = 0.;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (up[k] >= 0) inflow_up += qday[mi(p, m, up[k])];
+        for (int k = c.up0 + 8; k < c.up1; k++) inflow_up += qday[mi(p, m, p.up_idx[k])];  // (never on a D8 network)
+        Sr = route_river(p, c, r, m, i, q, inflow_up, p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday, nullptr,
                          WU ? &red_ll : nullptr);
         if (WU) in.red_loc_lake = red_ll;
     }
     route_post_compute(p, r, m, in, Sr);
-    if (level == 0) stamp_task(p, 1, 1, dayofs);
+    if (level == p.stamp_level) stamp_task(p, 1, 1, dayofs);
+    if (level == 0) WGK_INSITU_WARPDUR2(dayofs, 1);
+    WGK_INSITU_END(0, level == 0);
 }
 
 #if !WGK_MM  // k_tail_chunk and the cell-owner schedule run on the cell-minor layout only
