@@ -714,7 +714,10 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
         // levels must be fused tasks as well: every level has the own-cell recurrence V(d,l) -> R(d,l) -> V(d+1,l), and the
         // slowest one paces the whole wavefront.
         const char *e = getenv("WGK_LEVEL_TASKS");  // "split" | "fused" | "fused0" | "fusedfull"
-        const bool fused_default = c->form == 0 && !c->mm && !c->whole_day && c->opt.subtract_use == 0;
+        // The fused task wins while the run is latency-bound and loses once the kernels fill the GPU (one member, cells on the GPU,
+        // ms per simulated month fused / split: 135 k 3.02 / 3.59, 270 k 5.38 / 5.76, 539 k 10.04 / 10.27, 1.08 M 19.13 / 18.92,
+        // 2.16 M 37.2 / 35.8): default below 800 k cell-members.
+        const bool fused_default = c->form == 0 && !c->mm && !c->whole_day && c->opt.subtract_use == 0 && (long long)nmember * ncell < 800000;
         const int want = (e && (!strcmp(e, "fused") || !strcmp(e, "fusedfull"))) ? 1 : (e && !strcmp(e, "fused0")) ? 2 : (e && !strcmp(e, "split")) ? 0
                          : (fused_default ? 1 : 0);
         c->level_tasks = c->form != 0 ? 0 : want;

@@ -392,6 +392,10 @@ __device__ unsigned long long g_vphase[2][2][8];  // [level 0?][warp runs the ba
 // ----------------------------------------------------------------------------------------
 // -> true when the cell was computed; then *li (if given) holds the inputs of the local routing, loaded together
 // with those of the soil part, and *fx today's fluxes (otherwise the caller reads both from global memory)
+// EARLY: the inputs of the soil part and of the local routing are loaded before the band loop instead of after it (the compiler
+// cannot move a load above the band stores), one memory round trip less on the cell-day chain at the price of ~40 registers
+// held across the loop: for the kernel without a register cap (k_level_day)
+template <bool EARLY = false>
 __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, const int m, const int slot, SnowStage *st,
                                               LocalIn *li = nullptr, LocalFlux *fx = nullptr) {
     const WgkArrays &a = p.a;
@@ -578,6 +582,18 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
     if (dailySoilPET < 0.) dailySoilPET = 0.0;
 
     WGK_VT(2);
+    float e_builtup = 0.f, e_smax = 0.f, e_gwfactor = 0.f;
+    double e_soil = 0., e_gamma = 0., e_pcrit = 0., e_transfer_old = 0.;
+    short e_rgmax = 0;
+    int e_texture = 0, e_ldd = 0;
+    if (EARLY) {
+        e_builtup = a.builtup[r]; e_smax = a.smax[q]; e_gwfactor = a.gwfactor[q];
+        e_soil = a.soil[i]; e_gamma = a.gamma_hbv[q]; e_pcrit = a.p_pcrit[q];
+        e_rgmax = a.rgmax[q];
+        e_texture = a.texture[r]; e_ldd = a.ldd[r];
+        e_transfer_old = a.storage_transfer[i];
+        if (li) *li = local_load(p, r, m);
+    }
     // snow in 100 elevation bands (:913-1062)
     double TempElevMax = 0., snowStorageChange = 0., snow = 0.;
     int nz = 0;
@@ -607,7 +623,7 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
         // ~25-instruction division per band; the result is the correctly rounded quotient
         const double inv_laf = 1. / landAreaFrac;
         int thresh_elev = 0;
-#if WGK_BAND_FORM == 1
+#if WGK_BAND_FORM >= 1
         // Staged form: the bands of a chunk go through every stage together (rescale, 1000 mm rule, temperatures, the cold and
         // the warm branch as selects, the ordered sums), so that the instruction stream the scheduler sees is already
         // interleaved: the ~15 dependent FP64 operations of a band overlap with those of the other bands of the chunk, and
@@ -626,6 +642,12 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
                 s = fma(fma(-landAreaFrac, s, num), inv_laf, s);
                 s0[k] = (fabs(s) <= MIN_STOR_VOL) ? 0. : s;
             }
+#if WGK_BAND_FORM == 2
+            bool anybig = false;
+#pragma unroll
+            for (int k = 0; k < SNOW_CH; k++) anybig |= s0[k] > 1000.;
+            if (anybig || thresh_elev != 0)  // rare (a band above 1000 mm somewhere in the cell): the rule stays off the common path
+#endif
 #pragma unroll
             for (int k = 0; k < SNOW_CH; k++) {  // the 1000 mm rule (:958-976): integer selects only
                 const bool big = s0[k] > 1000.;
@@ -661,7 +683,11 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
                 snowStorageChange += sv[k] - s0[k];
                 snow += sv[k];
                 dailyEffPrec += mv[k];
+#if WGK_BAND_FORM == 2 && defined(__CUDA_ARCH__)
+                nz |= (__double2hiint(sv[k]) & 0x7fffffff) | __double2loint(sv[k]);  // != 0. on the bits (-0. counts as zero)
+#else
                 nz |= (sv[k] != 0.);
+#endif
                 S[(size_t)(c * SNOW_CH + k) * bs] = sv[k];
             }
             if (c + SNOW_NBUF < SNOW_NCH)
@@ -731,12 +757,12 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
 
     double gw_recharge_out = 0.;
     // inputs of the soil part: one round of loads
-    const float builtup = a.builtup[r], in_smax = a.smax[q], gwFactor = a.gwfactor[q];
-    const double in_soil = a.soil[i], in_gamma = a.gamma_hbv[q], in_pcrit = a.p_pcrit[q];
-    const short Rgmax = a.rgmax[q];
-    const int in_texture = a.texture[r], in_ldd = a.ldd[r];
-    const double in_transfer_old = a.storage_transfer[i];
-    if (li) *li = local_load(p, r, m);
+    const float builtup = EARLY ? e_builtup : a.builtup[r], in_smax = EARLY ? e_smax : a.smax[q], gwFactor = EARLY ? e_gwfactor : a.gwfactor[q];
+    const double in_soil = EARLY ? e_soil : a.soil[i], in_gamma = EARLY ? e_gamma : a.gamma_hbv[q], in_pcrit = EARLY ? e_pcrit : a.p_pcrit[q];
+    const short Rgmax = EARLY ? e_rgmax : a.rgmax[q];
+    const int in_texture = EARLY ? e_texture : a.texture[r], in_ldd = EARLY ? e_ldd : a.ldd[r];
+    const double in_transfer_old = EARLY ? e_transfer_old : a.storage_transfer[i];
+    if (li && !EARLY) *li = local_load(p, r, m);
     // immediate runoff (:1068-1071)
     if (builtup > 0.) {
         immediate_runoff = 0.5 * dailyEffPrec * builtup;
@@ -2624,6 +2650,9 @@ __global__ void __launch_bounds__(VBLOCK, WGK_PRE_MINB_EFF) k_cells_pre_tpc(cons
 #define WGK_LEVEL_MINB 2  // the fused task holds the V and the R part in one register budget: no cap (164 registers); with the
                           // 128 of the split kernels it measured 20.6 instead of 19.9 ms per simulated year
 #endif
+#ifndef WGK_LEVEL_EARLY
+#define WGK_LEVEL_EARLY 0
+#endif
 #undef WGK_LEVEL_MINB_EFF
 #if WGK_MM
 #define WGK_LEVEL_MINB_EFF WGK_PRE_MINB_MM
@@ -2639,7 +2668,7 @@ __global__ void __launch_bounds__(VBLOCK, WGK_LEVEL_MINB_EFF) k_level_day(const 
         if (level == p.stamp_level) stamp_task(p, 0, 0, dayofs);
         LocalIn li;
         LocalFlux fx;
-        if (vertical_cell(p, r, m, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, m, li, fx, p.cal_days[4 * dayofs + 1]);
+        if (vertical_cell<WGK_LEVEL_EARLY != 0>(p, r, m, p.cal_days[4 * dayofs + 3], &stage, &li, &fx)) local_compute(p, r, m, li, fx, p.cal_days[4 * dayofs + 1]);
         else route_local_cell(p, r, m, p.cal_days[4 * dayofs + 1]);
         if (level == p.stamp_level) stamp_task(p, 0, 1, dayofs);
         if (level == 0) WGK_INSITU_WARPDUR2(dayofs, 0);
