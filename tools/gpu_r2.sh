@@ -40,5 +40,21 @@ p)  # profiles: launch list of the bench command, full captures of the dominant 
     tail -1 $OUT/${TAG}_ncu_k_vertical_tpc_m64_$L.log
   done
   ;;
+f)  # final visit: the whole GPU suite, the default bench line, the reference arm, launch list and full capture of the fused task
+  timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
+  echo "pytest rc=$?" >> $OUT/${TAG}_pytest.log
+  tail -4 $OUT/${TAG}_pytest.log
+  timeout 900 python bench.py --steps 30 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+  tail -c 400 $OUT/${TAG}_bench.err
+  timeout 600 python bench.py --impl reference --steps 6 --warmup 3 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
+  tail -c 600 $OUT/${TAG}_bench_ref.json
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches_bench.csv \
+      python bench.py --steps 1 --warmup 1 --no-cpu --legs none > $OUT/${TAG}_bench_under_ncu.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^k_level_day$' -c 1 -f -o $OUT/${TAG}_k_level_day_m1 \
+      python tools/profile_run.py --members 1 --days 1 > $OUT/${TAG}_ncu_k_level_day_m1.log 2>&1
+  tail -2 $OUT/${TAG}_ncu_k_level_day_m1.log
+  python smoke_entry.py 2>/dev/null || python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1
+  tail -3 $OUT/${TAG}_smoke.log
+  ;;
 esac
 ls -la $OUT | grep ${TAG}_ | tail -20

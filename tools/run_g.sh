@@ -1,8 +1,9 @@
-for M in 2 4 8; do for mode in fused split; do
-WGK_LEVEL_TASKS=$mode timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu --legs none --members $M > gpurun_out/r2u_${mode}_$M.json 2>/dev/null
-python - $mode $M gpurun_out/r2u_${mode}_$M.json <<'PY'
+for v in k0 kf1 kf2 kf1n3 k0n3; do
+cp variants/libwgk_$v.so watergap2_b200/libwgk.so
+timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu --legs none --members 128 > gpurun_out/r2v_$v.json 2>/dev/null
+python - $v gpurun_out/r2v_$v.json <<'PY'
 import json,sys
-d=json.loads(open(sys.argv[3]).read().strip().splitlines()[-1])
-print(sys.argv[1], 'members', sys.argv[2], '%.3e' % d['value'], round(d['ms_per_step'],2), 'ms/yr')
+d=json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+print(sys.argv[1], 'members 128', '%.3e' % d['value'], round(d['ms_per_step'],2), 'ms/yr', d['roofline']['kernel'][:100])
 PY
-done; done
+done
