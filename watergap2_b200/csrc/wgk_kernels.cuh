@@ -148,6 +148,13 @@ constexpr double MIN_STOR_VOL = 1.e-15;  // routing.h:24
 // significand of c not all ones the result IS the correctly rounded quotient x / c, i.e. bit-identical to the
 // division it replaces, in 3 dependent FP64 instructions instead of ~25 (there are ~80 such divisions on the
 // path of one cell-day).  tests/test_kernel_logic_cpu.py::test_const_division_is_exact checks 4e7 operands.
+// pow() of the hot path.  WGK_POW_OUTLINE: ONE out-of-line copy per kernel variant instead of ~300 inlined instructions at each of
+// the ~12 call sites of a cell-day (code size against the instruction cache; the fused task k_level_day is 120 KB of SASS)
+#if defined(WGK_POW_OUTLINE) && defined(__CUDA_ARCH__)
+__device__ __noinline__ double wg_pow(const double x, const double y) { return pow(x, y); }
+#else
+__device__ __forceinline__ double wg_pow(const double x, const double y) { return pow(x, y); }
+#endif
 struct ConstDiv {
     double c, rc;
 };
@@ -562,7 +569,7 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
                 daily_prec_to_soil = dailyPrec - canopy_deficiency;
             }
             const double canopy_water_content = canopy;
-            dailyCanopyEvapo = dailyPET * pow((canopy_water_content / max_canopy_storage), 0.66666666);
+            dailyCanopyEvapo = dailyPET * wg_pow((canopy_water_content / max_canopy_storage), 0.66666666);
             if (dailyCanopyEvapo > canopy_water_content) {
                 dailyCanopyEvapo = canopy_water_content;
                 dailySoilPET = dailyPET - canopy_water_content;
@@ -793,7 +800,7 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
         if (TempElevMax > P_T_SNOWFZ) {
             if (Smax > 0.) {
                 const double soil_saturation = soil / Smax;
-                daily_runoff = dailyEffPrec * pow(soil_saturation, in_gamma);
+                daily_runoff = dailyEffPrec * wg_pow(soil_saturation, in_gamma);
                 if (dailySoilPET > (maxDailyPET - dailyCanopyEvapo) * soil_saturation)
                     dailyAET = (maxDailyPET - dailyCanopyEvapo) * soil_saturation;
                 else
@@ -1130,7 +1137,7 @@ __device__ __forceinline__ void v_head(const WgkParams &p, VTile<C> &sm, const i
                 daily_prec_to_soil = dailyPrec - canopy_deficiency;
             }
             const double canopy_water_content = canopy;
-            dailyCanopyEvapo = dailyPET * pow((canopy_water_content / max_canopy_storage), 0.66666666);
+            dailyCanopyEvapo = dailyPET * wg_pow((canopy_water_content / max_canopy_storage), 0.66666666);
             if (dailyCanopyEvapo > canopy_water_content) {
                 dailyCanopyEvapo = canopy_water_content;
                 dailySoilPET = dailyPET - canopy_water_content;
@@ -1361,7 +1368,7 @@ __device__ __forceinline__ void v_tail(const WgkParams &p, VTile<C> &sm, const i
         if (TempElevMax > P_T_SNOWFZ) {
             if (Smax > 0.) {
                 const double soil_saturation = soil / Smax;
-                daily_runoff = dailyEffPrec * pow(soil_saturation, VIN_D(TI_gamma, a.gamma_hbv[q]));
+                daily_runoff = dailyEffPrec * wg_pow(soil_saturation, VIN_D(TI_gamma, a.gamma_hbv[q]));
                 if (dailySoilPET > (maxDailyPET - dailyCanopyEvapo) * soil_saturation)
                     dailyAET = (maxDailyPET - dailyCanopyEvapo) * soil_saturation;
                 else
@@ -1709,7 +1716,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 {
                     const double x = (prev / maxStorage);  // pow(x, 1.5) (:2440) as x * sqrt(x), <= 1 ulp apart
                     #ifdef WGK_LIBM_POW
-                    outflow = kS * prev * pow(x, 1.5);
+                    outflow = kS * prev * wg_pow(x, 1.5);
 #else
                     outflow = kS * prev * (x * sqrt(x));
 #endif
@@ -1726,7 +1733,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
             }
             inflow = outflow;
             a.loc_lake_stor[i] = S;
-            a.red_loc_lake[i] = clamp01(1. - pow(fabs(S - maxStorage) / (2. * maxStorage), (M_EVAREDEX * 3.32193)));
+            a.red_loc_lake[i] = clamp01(1. - wg_pow(fabs(S - maxStorage) / (2. * maxStorage), (M_EVAREDEX * 3.32193)));
         }
         const double loc_wetland = li.loc_wetland;
         if (loc_wetland > 0.) {  // local wetland, :2495-2617
@@ -1752,7 +1759,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 {
                     const double x = (S / maxStorage);  // pow(x, 2.5) (:2580) as x * x * sqrt(x)
                     #ifdef WGK_LIBM_POW
-                    outflow = kS * S * pow(x, 2.5);
+                    outflow = kS * S * wg_pow(x, 2.5);
 #else
                     outflow = kS * S * ((x * x) * sqrt(x));
 #endif
@@ -1767,7 +1774,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
             }
             inflow = outflow;
             a.loc_wetl_stor[i] = S;
-            a.red_loc_wetl[i] = clamp01(1. - pow(fabs(S - maxStorage) / (maxStorage), (M_EVAREDEX * 3.32193)));
+            a.red_loc_wetl[i] = clamp01(1. - wg_pow(fabs(S - maxStorage) / (maxStorage), (M_EVAREDEX * 3.32193)));
         }
         // arid cells without global lake / reservoir / global wetland: the groundwater step below
         // the surface water bodies (:3305-3386) does not depend on upstream inflow either
@@ -2086,7 +2093,7 @@ __device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx
     // routingClass::getRiverVelocity (routing.cpp:7274-7307); pow(x, 2/3) is evaluated as
     // cbrt(x*x): same value to ~1 ulp with a much shorter dependent chain
     const double incoming_discharge = (riverInflow * 1000. * 1000. * 1000.) / C86400;  // (60. * 60. * 24.)
-    const double riverDepth = 0.349 * pow(incoming_discharge, 0.341);
+    const double riverDepth = 0.349 * wg_pow(incoming_discharge, 0.341);
     const double crossSectionalArea = riverDepth * (2.0 * riverDepth + c.bw);
     const double wettedPerimeter = c.bw + 2.0 * riverDepth * sqrt(5.0);
     const double hydraulicRad = crossSectionalArea / wettedPerimeter;
@@ -2132,7 +2139,7 @@ __device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx
                 }
             }
             a.loc_lake_stor[i] = S;
-            const double red = clamp01(1. - pow(fabs(S - maxStorage) / (2. * maxStorage), (a.p_evaredex[q] * 3.32193)));
+            const double red = clamp01(1. - wg_pow(fabs(S - maxStorage) / (2. * maxStorage), (a.p_evaredex[q] * 3.32193)));
             a.red_loc_lake[i] = red;
             if (red_loc_lake_out) *red_loc_lake_out = red;
         }
@@ -2278,7 +2285,7 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
         const double wbf = in.wbf;
         if (width > wbf / C1000) width = wbf / C1000;
         const double smaxr = in.smaxr;
-        red_river = clamp01(1. - pow(fabs(Sr - smaxr) / smaxr, (in.evaredex * 3.32193)));
+        red_river = clamp01(1. - wg_pow(fabs(Sr - smaxr) / smaxr, (in.evaredex * 3.32193)));
         raf_next = red_river * river_length * width * 100. / cellArea;
         raf_change = raf_next - raf;
     }
@@ -2289,15 +2296,15 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
         const double xexp = (in.evaredex * 3.32193);
         if (flags & FL_LAKE) {
             const double maxStorage = g[GB_L_MAX * gs];
-            a.red_glo_lake[i] = clamp01(1. - pow(fabs(a.glo_lake_stor[i] - maxStorage) / (2. * maxStorage), xexp));
+            a.red_glo_lake[i] = clamp01(1. - wg_pow(fabs(a.glo_lake_stor[i] - maxStorage) / (2. * maxStorage), xexp));
         }
         if (flags & FL_RES) {
             const double maxStorage = g[GB_R_CAP * gs];
-            a.red_res[i] = clamp01(1. - pow(fabs(a.res_stor[i] - maxStorage) / maxStorage, 2.81383));
+            a.red_res[i] = clamp01(1. - wg_pow(fabs(a.res_stor[i] - maxStorage) / maxStorage, 2.81383));
         }
         if (flags & FL_GLOWET) {
             const double maxStorage = g[GB_W_MAX * gs];
-            red_glo_wetl = clamp01(1. - pow(fabs(a.glo_wetl_stor[i] - maxStorage) / maxStorage, xexp));
+            red_glo_wetl = clamp01(1. - wg_pow(fabs(a.glo_wetl_stor[i] - maxStorage) / maxStorage, xexp));
         }
     }
     const double loc_lake = in.loc_lake, loc_wetland = in.loc_wetland;
