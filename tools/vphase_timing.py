@@ -52,3 +52,9 @@ for use_graph in ((1, 0) if not os.environ.get("GRAPH_ONLY") else (1,)):
         x = wd[k][wd[k] > 0] / 1965.0
         if x.size:
             print(f"  level-0 warps, {nm}: n {x.size}, mean {x.mean():.1f}, p50 {np.median(x):.1f}, p90 {np.percentile(x, 90):.1f}, p99 {np.percentile(x, 99):.1f}, max {x.max():.1f} us")
+    if os.environ.get("DUMP_WARPDUR"):
+        order = m.device_order()           # device position of every cell
+        cls = wg.cell_classes(ini)
+        snowfree = m.get("s_snowfree") if m.has_field("s_snowfree") else None
+        np.savez(os.path.join(ROOT, "gpurun_out", "warpdur.npz"), wd=wd, order=order, cls=cls, levels=m.levels(),
+                 snow=m.get("snow"), lat=w.lat)

@@ -755,11 +755,24 @@ void dailyWaterBalanceClass::pull() {
 void Engine::push_static() {
     // class key per cell (which water-body code the cell needs): lets the library store cells of equal class
     // next to each other inside a routing level; results do not depend on it (include/wgk.h)
+    // High 4 bits (opt-in, WGK_COLD_BINS=1..16; measured without gain, see watergap2_b200.cell_classes): a coldness bin from
+    // latitude and mean elevation (coldest first; 27 - 0.55 |lat| - 0.0045 m as a climatological mean temperature - it only
+    // orders cells), so that the cells of a warp / CTA tend to be either all in the 100-band snow loop or all out of it
     std::vector<uint8_t> cls(ncell);
-    for (int n = 0; n < ncell; n++)
-        cls[n] = (uint8_t)((routing.G_loc_lake[n] > 0.) * 1 + (routing.G_loc_wetland[n] > 0.) * 2
-                           + ((routing.G_lake_area[n] > 0.) || (routing.G_reservoir_area_full[n] > 0.) || (routing.G_glo_wetland[n] > 0.)) * 4
-                           + (G_aindex[n] == 1) * 8);
+    const char *cb = getenv("WGK_COLD_BINS");
+    const int nbins = cb ? std::min(16, atoi(cb)) : 0;
+    for (int n = 0; n < ncell; n++) {
+        int key = (routing.G_loc_lake[n] > 0.) * 1 + (routing.G_loc_wetland[n] > 0.) * 2
+                  + ((routing.G_lake_area[n] > 0.) || (routing.G_reservoir_area_full[n] > 0.) || (routing.G_glo_wetland[n] > 0.)) * 4
+                  + (G_aindex[n] == 1) * 8;
+        if (nbins > 0) {
+            const double lat = 90.25 - 0.5 * (double)geo.G_row[n];
+            const double t = 27.0 - 0.55 * std::fabs(lat) - 0.0045 * (double)dailyWaterBalance.G_Elevation(n, 0);
+            const int bin = (int)std::floor((t + 30.0) / 60.0 * nbins);
+            key += 16 * std::max(0, std::min(nbins - 1, bin));
+        }
+        cls[n] = (uint8_t)key;
+    }
     check(wgk_set_cell_classes(ctx, cls.data()), "wgk_set_cell_classes");
     check(wgk_set_topology(ctx, routing.G_routOrder.data(), routing.G_downstreamCell.data()), "wgk_set_topology");
     Grid<double> area(ncell);

@@ -868,12 +868,14 @@ int wgk_set_topology(wgk_ctx *c, const int32_t *rout_order, const int32_t *downs
     for (int r = 0; r < ng; r++) r_of_pos[r] = r;
     if (!c->cell_class.empty()) {
         const char *e = getenv("WGK_CLASS_ORDER");  // "asc" | "desc" | "cost"
-        const int mode = (e && !strcmp(e, "desc")) ? 1 : (e && !strcmp(e, "cost")) ? 2 : 0;
+        const int mode = (e && !strcmp(e, "desc")) ? 1 : (e && !strcmp(e, "cost")) ? 2 : (e && !strcmp(e, "asc2")) ? 3 : (e && !strcmp(e, "cost2")) ? 4 : 0;
         auto key = [&](int r) -> int {
             const int k = c->cell_class[cell_of_r[r]];
             if (mode == 0) return k;
             if (mode == 1) return 255 - k;
             const int cost = 3 * ((k >> 2) & 1) + (k & 1) + ((k >> 1) & 1);  // global water body, local lake, local wetland
+            if (mode == 3) return (k & 15) * 16 + (k >> 4);                    // water-body class first, the high 4 bits inside it
+            if (mode == 4) return (7 - cost) * 256 + (k & 15) * 16 + (k >> 4);
             return (7 - cost) * 256 + k;
         };
         for (int l = 0; l < c->nlevels; l++)

@@ -148,6 +148,21 @@ constexpr double MIN_STOR_VOL = 1.e-15;  // routing.h:24
 // significand of c not all ones the result IS the correctly rounded quotient x / c, i.e. bit-identical to the
 // division it replaces, in 3 dependent FP64 instructions instead of ~25 (there are ~80 such divisions on the
 // path of one cell-day).  tests/test_kernel_logic_cpu.py::test_const_division_is_exact checks 4e7 operands.
+// the two 32-bit words of a double (integer tests on the bits)
+__device__ __forceinline__ int hi_word(const double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    long long b; memcpy(&b, &x, 8); return (int)(b >> 32);
+#endif
+}
+__device__ __forceinline__ int lo_word(const double x) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(x);
+#else
+    long long b; memcpy(&b, &x, 8); return (int)(b & 0xffffffffll);
+#endif
+}
 // pow() of the hot path.  WGK_POW_OUTLINE: ONE out-of-line copy per kernel variant instead of ~300 inlined instructions at each of
 // the ~12 call sites of a cell-day (code size against the instruction cache; the fused task k_level_day is 120 KB of SASS)
 #if defined(WGK_POW_OUTLINE) && defined(__CUDA_ARCH__)
@@ -636,11 +651,23 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
         // interleaved: the ~15 dependent FP64 operations of a band overlap with those of the other bands of the chunk, and
         // the only band-to-band dependencies left are the integer select of the 1000 mm rule and the four running sums
         // (same additions in the same order as the band-by-band form: same bits).
+        // Form 2 additionally trims the instruction count of a band (the loop is half of all instructions of a cell-day, and
+        // the FP64 instructions take two issue slots each):
+        //  * the rare 1000 mm rule behind ONE test per chunk on the largest high word of the rescaled bands (a band can only
+        //    exceed 1000 mm if its high word reaches that of 1000.0; the exact comparison is made on the rare path);
+        //  * "x = c ? (o ? a - b : 0) : y" as ONE subtraction of a selected subtrahend: below the freezing threshold the new storage
+        //    is (s + P) - sublimation with sublimation = o ? PET : s + P, and (s + P) - (s + P) is the +0 the branch assigns; above
+        //    the melting threshold it is s - melt with melt = all ? s : m, and s - s = +0; where the branch is not taken the
+        //    subtrahend is +0 and x - 0 = x.  Same bits, four selects and no extra subtraction per band less;
+        //  * the "any band non-zero" flag from the bits of the result instead of an FP64 compare.
         for (int c = 0; c < SNOW_NCH; c++) {
             const int buf = c % SNOW_NBUF;
             stage_wait(SNOW_NCH - 1 - c);
             double s0[SNOW_CH], sv[SNOW_CH], tv[SNOW_CH], ev[SNOW_CH], mv[SNOW_CH];
             int el[SNOW_CH];
+#if WGK_BAND_FORM == 2
+            int hmax = 0;
+#endif
 #pragma unroll
             for (int k = 0; k < SNOW_CH; k++) {
                 el[k] = st->e[buf][k][tid];
@@ -648,12 +675,12 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
                 double s = num * inv_laf;
                 s = fma(fma(-landAreaFrac, s, num), inv_laf, s);
                 s0[k] = (fabs(s) <= MIN_STOR_VOL) ? 0. : s;
+#if WGK_BAND_FORM == 2
+                { const int hw_ = hi_word(s0[k]); hmax = hw_ > hmax ? hw_ : hmax; }
+#endif
             }
 #if WGK_BAND_FORM == 2
-            bool anybig = false;
-#pragma unroll
-            for (int k = 0; k < SNOW_CH; k++) anybig |= s0[k] > 1000.;
-            if (anybig || thresh_elev != 0)  // rare (a band above 1000 mm somewhere in the cell): the rule stays off the common path
+            if (hmax >= 0x408F4000 || thresh_elev != 0)  // (0x408F4000 = high word of 1000.0) rare: the rule stays off the common path
 #endif
 #pragma unroll
             for (int k = 0; k < SNOW_CH; k++) {  // the 1000 mm rule (:958-976): integer selects only
@@ -666,6 +693,35 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
 #pragma unroll
             for (int k = 0; k < SNOW_CH; k++) tv[k] = dailyTempC - ((el[k] - elev0) * P_T_GRADNT);
             if (c == 0) TempElevMax = tv[0];
+#if WGK_BAND_FORM == 2
+#pragma unroll
+            for (int k = 0; k < SNOW_CH; k++) {  // accumulation and sublimation below the freezing threshold (:982-999)
+                const bool cold = tv[k] <= P_T_SNOWFZ;
+                const double s_in = s0[k] + daily_prec_to_soil;
+                const double sub = (s_in > dailySoilPET) ? dailySoilPET : s_in;
+                ev[k] = cold ? sub : 0.;
+                sv[k] = (cold ? s_in : s0[k]) - ev[k];
+                mv[k] = cold ? 0. : daily_prec_to_soil;
+            }
+#pragma unroll
+            for (int k = 0; k < SNOW_CH; k++) {  // melt above the melting threshold (:1003-1019)
+                const double s = sv[k];
+                const bool melt = tv[k] > P_T_SNOWMT && !(s < 0.);
+                const double m_raw = ddf * (tv[k] - P_T_SNOWMT);
+                const double mm = melt ? ((m_raw > s) ? s : m_raw) : 0.;
+                mv[k] += mm;
+                sv[k] = s - mm;
+            }
+#pragma unroll
+            for (int k = 0; k < SNOW_CH; k++) {
+                dailySnowEvapo += ev[k];
+                snowStorageChange += sv[k] - s0[k];
+                snow += sv[k];
+                dailyEffPrec += mv[k];
+                nz |= (hi_word(sv[k]) & 0x7fffffff) | lo_word(sv[k]);  // != 0. on the bits (-0. counts as zero)
+                S[(size_t)(c * SNOW_CH + k) * bs] = sv[k];
+            }
+#else
 #pragma unroll
             for (int k = 0; k < SNOW_CH; k++) {  // accumulation and sublimation below the freezing threshold (:982-999)
                 const bool cold = tv[k] <= P_T_SNOWFZ;
@@ -690,13 +746,10 @@ __device__ __forceinline__ bool vertical_cell(const WgkParams &p, const int r, c
                 snowStorageChange += sv[k] - s0[k];
                 snow += sv[k];
                 dailyEffPrec += mv[k];
-#if WGK_BAND_FORM == 2 && defined(__CUDA_ARCH__)
-                nz |= (__double2hiint(sv[k]) & 0x7fffffff) | __double2loint(sv[k]);  // != 0. on the bits (-0. counts as zero)
-#else
                 nz |= (sv[k] != 0.);
-#endif
                 S[(size_t)(c * SNOW_CH + k) * bs] = sv[k];
             }
+#endif
             if (c + SNOW_NBUF < SNOW_NCH)
                 stage_issue(st, buf, tid, S + (size_t)(c + SNOW_NBUF) * SNOW_CH * bs, E + (size_t)(c + SNOW_NBUF) * SNOW_CH * p.stride, bs, p.stride);
         }
@@ -1442,7 +1495,10 @@ __device__ __forceinline__ void v_tail(const WgkParams &p, VTile<C> &sm, const i
 }
 
 // number of days of river discharge kept in flight (temporal wavefront over the level graph)
-constexpr int QBUF_K = 32;
+#ifndef WGK_QBUF_K
+#define WGK_QBUF_K 32
+#endif
+constexpr int QBUF_K = WGK_QBUF_K;
 // run-time stamps of the level-0 tasks (bench.py: duration of the dominant kernel inside the timed graph)
 constexpr int STAMP_DAYS = 512;
 __device__ __forceinline__ void stamp_task(const WgkParams &p, const int kind, const int which, const int dayofs) {
