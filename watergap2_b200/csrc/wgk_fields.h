@@ -127,6 +127,8 @@
     X(s_slope_pow, double, "f64", PSET, 1) \
     X(s_ekg, double, "f64", PSET, 1) \
     X(s_invkg, double, "f64", PSET, 1) \
+    X(s_eks, double, "f64", PSET, 1) \
+    X(s_invks, double, "f64", PSET, 1) \
     X(s_flags, int8_t, "i8", CELL, 1) \
     X(s_elev32, int32_t, "i32", CELL, 101) \
     X(s_delev, int16_t, "i16", CELL, 101) \

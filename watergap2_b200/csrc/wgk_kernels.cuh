@@ -1646,6 +1646,8 @@ __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ W
     a.s_c1[q] = 1. / (a.p_rivrgh[q] * a.roughness[r]);
     a.s_ekg[q] = exp(-1. * a.p_gwoutf[q]);  // routing.cpp:1940
     a.s_invkg[q] = (1. / a.p_gwoutf[q]);
+    a.s_eks[q] = exp(-1. * a.p_swoutf[q]);  // exp(-k) and 1/k of the global lakes / wetlands (routing.cpp:2741, 3237)
+    a.s_invks[q] = (1. / a.p_swoutf[q]);
     a.s_slope_pow[q] = pow(a.river_slope[r], 0.5);
     if (ps == 0) {
         // band elevation minus cell mean elevation (the integer the lapse rate multiplies, daily.cpp:935) and its extremes
@@ -1666,9 +1668,11 @@ __global__ void __launch_bounds__(128) k_derive_static(const __grid_constant__ W
         if (a.contcell[r] && (0 != a.toBeCalculated[r])) f |= FL_ACTIVE;
         if (ldd >= 0) f |= FL_LDD_OUT;
         if ((1 == a.arid[r]) && (ldd >= 0)) f |= FL_ARIDC;
+#ifndef WGK_EXP_NOGLOB  // (timing experiment only: no global water bodies anywhere)
         if (a.lake_area[r] > 0.) f |= FL_LAKE;
         if (a.reservoir_area[r] > 0.) f |= FL_RES;
         if (a.glo_wetland[r] > 0) f |= FL_GLOWET;
+#endif
         if (a.contcell[r] && (1 == a.toBeCalculated[r])) f |= FL_TBC1;
         a.s_flags[r] = (int8_t)f;
     }
@@ -1844,18 +1848,31 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
             a.gw[i] = Sg;
         }
         if (flags & (FL_LAKE | FL_RES | FL_GLOWET)) {
+            // Cells with a global water body are 8 % of the grid and the slowest warps of every level (they pace the single
+            // member: without them the simulated year takes 15.6 instead of 18.4 ms).  Every input of the three blocks below is
+            // therefore loaded HERE, in one round and before the first store (the compiler cannot move a load above the stores
+            // to g[]), instead of one dependent round of loads per block; exp(-k) and 1/k come from the one-time derivation.
+            const size_t q_ = qi(p, m, r);
+            const bool hasL = (flags & FL_LAKE) != 0, hasR = (flags & FL_RES) != 0, hasW = (flags & FL_GLOWET) != 0;
+            const double in_eks = a.s_eks[q_], in_invks = a.s_invks[q_];
+            const double in_lake_area = hasL ? a.lake_area[r] : 0., in_red_glo_lake = hasL ? a.red_glo_lake[i] : 0.;
+            const double in_reservoir_area = hasR ? a.reservoir_area[r] : 0., in_stor_cap = hasR ? a.stor_cap[r] : 0.;
+            const double in_mean_outflow = hasR ? a.mean_outflow[r] : 0., in_red_res = hasR ? a.red_res[i] : 0.;
+            const double in_mean_demand = hasR ? a.mean_demand[r] : 0.;
+            const int in_res_type = hasR ? a.res_type[r] : 0;
+            const double in_glo_wetland = hasW ? a.glo_wetland[r] : 0., in_red_glo_wetl = hasW ? a.red_glo_wetl[i] : 0.;
             double *g = p.gbody + gb(p, m, p.gidx[r], GB_N);
             const size_t gs = gbody_stride(p);
-            g[GB_EKS * gs] = exp(-1. * kS);
-            g[GB_INVKS * gs] = (1. / kS);
+            g[GB_EKS * gs] = in_eks;
+            g[GB_INVKS * gs] = in_invks;
             g[GB_EKG * gs] = li.ekg;
             g[GB_INVKG * gs] = li.invkg;
             g[GB_GWRECH * gs] = fx.gw_recharge * cellArea * (laf / C100) / C1E6;
             g[GB_LOC_GWR_LAK * gs] = gwr_loclak;
             g[GB_LOC_GWR_WET * gs] = gwr_locwet;
             if (flags & FL_LAKE) {  // :2630-2676
-                const double lake_area = a.lake_area[r];
-                const double rf = a.red_glo_lake[i];
+                const double lake_area = in_lake_area;
+                const double rf = in_red_glo_lake;
                 double evapo = ((1.0 - cfa) * owPrec) + (cfa * owPET * rf);
                 if (evapo < 0.) evapo = 0.;
                 const double gwr = aridc ? 10. * rf * (lake_area / (cellArea * (contf / C100))) : 0.;
@@ -1865,10 +1882,10 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 g[GB_L_MAX * gs] = (lake_area)*li.lake_depth;
             }
             if (flags & FL_RES) {  // :2807-2870, 2960-2983
-                const double reservoir_area = a.reservoir_area[r];
-                const double stor_cap = a.stor_cap[r];
-                const double mean_outflow = a.mean_outflow[r];
-                const double rf = a.red_res[i];
+                const double reservoir_area = in_reservoir_area;
+                const double stor_cap = in_stor_cap;
+                const double mean_outflow = in_mean_outflow;
+                const double rf = in_red_res;
                 double evapo = ((1.0 - cfa) * owPrec) + (cfa * (owPET * rf));
                 if (evapo < 0.) evapo = 0.;
                 const double gwr = aridc ? 10. * rf * (reservoir_area / (cellArea * (contf / C100))) : 0.;
@@ -1878,7 +1895,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 g[GB_R_C * gs] = stor_cap / (mean_outflow * 31536000. / 1000000000.);
                 g[GB_R_CAP * gs] = stor_cap;
                 double prov_rel = 0.;
-                const int res_type = a.res_type[r];
+                const int res_type = in_res_type;
                 if (res_type == 1) {  // irrigation reservoir (:2960-2977)
                     double monthlyUse = 0.;
                     if (WU) {
@@ -1894,7 +1911,7 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                         monthlyUse = dailyUse * ndim[wu_month];
                         monthlyUse = monthlyUse * 1000000000. / (ndim[wu_month] * 86400.);
                     }
-                    const double mean_demand = a.mean_demand[r];
+                    const double mean_demand = in_mean_demand;
                     if (mean_demand >= 0.5 * mean_outflow) prov_rel = mean_outflow / 2. * (1. + monthlyUse / mean_demand);
                     else prov_rel = mean_outflow + monthlyUse - mean_demand;
                 } else if (res_type == 2) {
@@ -1903,8 +1920,8 @@ __device__ __forceinline__ void local_compute(const WgkParams &p, const int r, c
                 g[GB_R_PROV * gs] = prov_rel;
             }
             if (flags & FL_GLOWET) {  // :3178-3200
-                const double glo_wetland = a.glo_wetland[r];
-                const double rf = a.red_glo_wetl[i];
+                const double glo_wetland = in_glo_wetland;
+                const double rf = in_red_glo_wetl;
                 double evapo = ((1.0 - cfa) * (owPrec * rf)) + (cfa * (owPET * rf));
                 if (evapo < 0.) evapo = 0.;
                 const double gwr = aridc ? 10. * rf * glo_wetland / C100 / (contf / C100) : 0.;
@@ -1983,15 +2000,29 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
     const WgkArrays &a = p.a;
     const double *g = p.gbody + gb(p, m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
     const size_t gs = gbody_stride(p);
+    // every input of the blocks below in ONE round of loads, before the first store (a block's own loads after the previous
+    // block's store cost the cells with global water bodies - the slowest warps of every level - one dependent round trip each)
+    const bool hasL = (flags & FL_LAKE) != 0, hasR = (flags & FL_RES) != 0, hasW = (flags & FL_GLOWET) != 0, hasA = (flags & FL_ARIDC) != 0;
     const double ek = g[GB_EKS * gs], invk = g[GB_INVKS * gs];
+    const double l_prev = hasL ? a.glo_lake_stor[i] : 0., l_max = hasL ? g[GB_L_MAX * gs] : 0., l_pet = hasL ? g[GB_L_PET * gs] : 0.;
+    const double l_gwr = hasL ? g[GB_L_GWR * gs] : 0., l_prec = hasL ? g[GB_L_PREC * gs] : 0.;
+    const double r_cap = hasR ? g[GB_R_CAP * gs] : 0., r_prev = hasR ? a.res_stor[i] : 0., r_pet = hasR ? g[GB_R_PET * gs] : 0.;
+    const double r_gwr = hasR ? g[GB_R_GWR * gs] : 0., r_prec = hasR ? g[GB_R_PREC * gs] : 0., r_krel = hasR ? a.k_release[i] : 0.;
+    const double r_c = hasR ? g[GB_R_C * gs] : 0., r_prov = hasR ? g[GB_R_PROV * gs] : 0.;
+    const int r_start_month = hasR ? a.start_month[r] : 0;
+    const double w_prev = hasW ? a.glo_wetl_stor[i] : 0., w_max = hasW ? g[GB_W_MAX * gs] : 0., w_pet = hasW ? g[GB_W_PET * gs] : 0.;
+    const double w_gwr = hasW ? g[GB_W_GWR * gs] : 0., w_prec = hasW ? g[GB_W_PREC * gs] : 0.;
+    const double a_gwr_lak = hasA ? g[GB_LOC_GWR_LAK * gs] : 0., a_gwr_wet = hasA ? g[GB_LOC_GWR_WET * gs] : 0., a_gwrech = hasA ? g[GB_GWRECH * gs] : 0.;
+    const double a_ekg = hasA ? g[GB_EKG * gs] : 0., a_invkg = hasA ? g[GB_INVKG * gs] : 0.;
+    const double a_area = hasA ? a.area[r] : 0., a_contf = hasA ? a.contfreq[r] : 0., a_gw = hasA ? a.gw[i] : 0.;
     double gwr_glolak = 0., gwr_res = 0., gwr_glowet = 0.;
     if (flags & FL_LAKE) {  // :2677-2720
-        const double prev = a.glo_lake_stor[i];
+        const double prev = l_prev;
         remainingUseGloLake = (flags & FL_RES) ? 0.5 * remainingUse : remainingUse;  // :2681-2686 (0 without water use)
         const double remainingUseGloLakeStart = remainingUseGloLake;
-        const double maxStorage = g[GB_L_MAX * gs], PET = g[GB_L_PET * gs] + remainingUseGloLake;
-        gwr_glolak = g[GB_L_GWR * gs];
-        const double totalInflow = inflow + g[GB_L_PREC * gs];
+        const double maxStorage = l_max, PET = l_pet + remainingUseGloLake;
+        gwr_glolak = l_gwr;
+        const double totalInflow = inflow + l_prec;
         const double PETmax = totalInflow + maxStorage + prev;
         double S, outflow;
         if (PET > PETmax) {
@@ -2019,12 +2050,12 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
         a.glo_lake_stor[i] = S;
     }
     if (flags & FL_RES) {  // :2871-3040
-        const double stor_cap = g[GB_R_CAP * gs];
+        const double stor_cap = r_cap;
         const double maxStorage = stor_cap;
-        const double prev = a.res_stor[i];
-        const double PET = g[GB_R_PET * gs];
-        gwr_res = g[GB_R_GWR * gs];
-        const double totalInflow = inflow + g[GB_R_PREC * gs];
+        const double prev = r_prev;
+        const double PET = r_pet;
+        gwr_res = r_gwr;
+        const double totalInflow = inflow + r_prec;
         const double PETmax = prev + totalInflow;
         remainingUseRes = (flags & FL_LAKE) ? 0.5 * remainingUse + remainingUseGloLake : remainingUse;  // :2869-2875
         const double remainingUseResStart = remainingUseRes;
@@ -2050,14 +2081,14 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
             }
         }
         if (fabs(S) <= MIN_STOR_VOL) S = 0.;
-        double Krel = a.k_release[i];
+        double Krel = r_krel;
         const int fdim[12] = {1, 32, 60, 91, 121, 152, 182, 213, 244, 274, 305, 335};
-        if (month == a.start_month[r] - 1 && day == fdim[month]) {  // :2945-2956
+        if (month == r_start_month - 1 && day == fdim[month]) {  // :2945-2956
             if (S < (stor_cap * 0.1)) Krel = 0.1;
             else Krel = S / (maxStorage * 0.85);
             a.k_release[i] = Krel;
         }
-        const double c_ratio = g[GB_R_C * gs], prov_rel = g[GB_R_PROV * gs];
+        const double c_ratio = r_c, prov_rel = r_prov;
         double release;
         if (c_ratio >= 0.5) release = Krel * prov_rel;
         else
@@ -2082,10 +2113,10 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
     }
     if (wu && (flags & (FL_LAKE | FL_RES))) remainingUse = (flags & FL_RES) ? remainingUseRes : remainingUseGloLake;  // :3166-3172
     if (flags & FL_GLOWET) {  // :3201-3260
-        const double prev = a.glo_wetl_stor[i];
-        const double maxStorage = g[GB_W_MAX * gs], PET = g[GB_W_PET * gs];
-        gwr_glowet = g[GB_W_GWR * gs];
-        const double totalInflow = inflow + g[GB_W_PREC * gs];
+        const double prev = w_prev;
+        const double maxStorage = w_max, PET = w_pet;
+        gwr_glowet = w_gwr;
+        const double totalInflow = inflow + w_prec;
         const double PETmax = totalInflow + prev;
         double S, outflow;
         if (PET > PETmax) {
@@ -2105,13 +2136,13 @@ __device__ __noinline__ double route_global_bodies(const WgkParams &p, const int
         a.glo_wetl_stor[i] = S;
     }
     if (flags & FL_ARIDC) {  // :3305-3386
-        const double gwr_swb = g[GB_LOC_GWR_LAK * gs] + gwr_glolak + g[GB_LOC_GWR_WET * gs] + gwr_glowet + gwr_res;
+        const double gwr_swb = a_gwr_lak + gwr_glolak + a_gwr_wet + gwr_glowet + gwr_res;
         a.gwr_swb[i] = gwr_swb;
-        double netGWin = gwr_swb * a.area[r] * (a.contfreq[r] / C100) / C1E6 + g[GB_GWRECH * gs];
+        double netGWin = gwr_swb * a_area * (a_contf / C100) / C1E6 + a_gwrech;
         if (wu) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));  // :3325-3330
-        const double prev = a.gw[i];
-        const double ekg = g[GB_EKG * gs];
-        double Sg = prev * ekg + g[GB_INVKG * gs] * netGWin * (1. - ekg);
+        const double prev = a_gw;
+        const double ekg = a_ekg;
+        double Sg = prev * ekg + a_invkg * netGWin * (1. - ekg);
         if (fabs(Sg) <= MIN_STOR_VOL) Sg = 0.;
         double qq = prev - Sg + netGWin;
         if (qq <= 0.) {
@@ -2346,22 +2377,22 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
         raf_change = raf_next - raf;
     }
     if ((flags & FL_ACTIVE) && (flags & (FL_LAKE | FL_RES | FL_GLOWET))) {
-        // evaporation reduction factors of the global water bodies (:2790-2802, 3068-3078, 3287-3296)
+        // evaporation reduction factors of the global water bodies (:2790-2802, 3068-3078, 3287-3296): the six inputs in one round
+        // of loads, then the three pow() back to back for every lane (an absent body gets harmless arguments and no store) - in
+        // a warp that holds lakes, reservoirs and wetlands their chains overlap instead of following each other branch by branch
         const double *g = p.gbody + gb(p, m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
         const size_t gs = gbody_stride(p);
         const double xexp = (in.evaredex * 3.32193);
-        if (flags & FL_LAKE) {
-            const double maxStorage = g[GB_L_MAX * gs];
-            a.red_glo_lake[i] = clamp01(1. - wg_pow(fabs(a.glo_lake_stor[i] - maxStorage) / (2. * maxStorage), xexp));
-        }
-        if (flags & FL_RES) {
-            const double maxStorage = g[GB_R_CAP * gs];
-            a.red_res[i] = clamp01(1. - wg_pow(fabs(a.res_stor[i] - maxStorage) / maxStorage, 2.81383));
-        }
-        if (flags & FL_GLOWET) {
-            const double maxStorage = g[GB_W_MAX * gs];
-            red_glo_wetl = clamp01(1. - wg_pow(fabs(a.glo_wetl_stor[i] - maxStorage) / maxStorage, xexp));
-        }
+        const bool hasL = (flags & FL_LAKE) != 0, hasR = (flags & FL_RES) != 0, hasW = (flags & FL_GLOWET) != 0;
+        const double maxL = hasL ? g[GB_L_MAX * gs] : 1., storL = hasL ? a.glo_lake_stor[i] : 0.;
+        const double maxR = hasR ? g[GB_R_CAP * gs] : 1., storR = hasR ? a.res_stor[i] : 0.;
+        const double maxW = hasW ? g[GB_W_MAX * gs] : 1., storW = hasW ? a.glo_wetl_stor[i] : 0.;
+        const double powL = wg_pow(fabs(storL - maxL) / (2. * maxL), xexp);
+        const double powR = wg_pow(fabs(storR - maxR) / maxR, 2.81383);
+        const double powW = wg_pow(fabs(storW - maxW) / maxW, xexp);
+        if (hasL) a.red_glo_lake[i] = clamp01(1. - powL);
+        if (hasR) a.red_res[i] = clamp01(1. - powR);
+        if (hasW) red_glo_wetl = clamp01(1. - powW);
     }
     const double loc_lake = in.loc_lake, loc_wetland = in.loc_wetland;
     double fLocLake = ((loc_lake > 0.) && (red_loc_lake > 0.)) ? (red_loc_lake * loc_lake / C100) : 0.;
