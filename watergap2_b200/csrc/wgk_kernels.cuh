@@ -1987,7 +1987,14 @@ __device__ __forceinline__ RiverCtx load_ctx(const WgkParams &p, const int r, co
 // for the few cells that have them: only the inflow-dependent arithmetic; exp(), 1/k, evaporation
 // and recharge demands come from the pre-pass (GBody), the reduction-factor pow() is done by the
 // post-pass.  Returns the inflow handed to the river.
-__device__ __noinline__ double route_global_bodies(const WgkParams &p, const int r, const int m, const size_t i,
+// (inlined: as an out-of-line function its call cost the cells with global water bodies a stack frame and the single member
+//  1.3 % of the year; WGK_GB_NOINLINE keeps the round-1 form)
+#ifdef WGK_GB_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+double route_global_bodies(const WgkParams &p, const int r, const int m, const size_t i,
                                                    double inflow, const int flags, const int day, const int month,
                                                    double &gwToRiver WGK_WU_PARAMS) {
 #if !WGK_WU
