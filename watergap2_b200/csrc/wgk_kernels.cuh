@@ -1987,14 +1987,12 @@ __device__ __forceinline__ RiverCtx load_ctx(const WgkParams &p, const int r, co
 // for the few cells that have them: only the inflow-dependent arithmetic; exp(), 1/k, evaporation
 // and recharge demands come from the pre-pass (GBody), the reduction-factor pow() is done by the
 // post-pass.  Returns the inflow handed to the river.
-// (inlined: as an out-of-line function its call cost the cells with global water bodies a stack frame and the single member
-//  1.3 % of the year; WGK_GB_NOINLINE keeps the round-1 form)
-#ifdef WGK_GB_NOINLINE
-__device__ __noinline__
-#else
-__device__ __forceinline__
-#endif
-double route_global_bodies(const WgkParams &p, const int r, const int m, const size_t i,
+// BATCH (the fused task k_level_day, where these cells are the slowest warps of every level): every input of the blocks in ONE
+// round of loads before the first store, and the routine inlined - a block's own loads after the previous block's store cost one
+// dependent round trip each, the call a stack frame (17.4 -> 17.1 ms per simulated year).  The throughput kernels keep the
+// out-of-line form with the loads inside the blocks: batched, k_route_level needs 103 instead of 80 registers.
+template <bool BATCH>
+__device__ __forceinline__ double route_global_bodies_impl(const WgkParams &p, const int r, const int m, const size_t i,
                                                    double inflow, const int flags, const int day, const int month,
                                                    double &gwToRiver WGK_WU_PARAMS) {
 #if !WGK_WU
@@ -2007,9 +2005,8 @@ double route_global_bodies(const WgkParams &p, const int r, const int m, const s
     const WgkArrays &a = p.a;
     const double *g = p.gbody + gb(p, m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
     const size_t gs = gbody_stride(p);
-    // every input of the blocks below in ONE round of loads, before the first store (a block's own loads after the previous
-    // block's store cost the cells with global water bodies - the slowest warps of every level - one dependent round trip each)
-    const bool hasL = (flags & FL_LAKE) != 0, hasR = (flags & FL_RES) != 0, hasW = (flags & FL_GLOWET) != 0, hasA = (flags & FL_ARIDC) != 0;
+    const bool hasL = BATCH && (flags & FL_LAKE) != 0, hasR = BATCH && (flags & FL_RES) != 0, hasW = BATCH && (flags & FL_GLOWET) != 0,
+               hasA = BATCH && (flags & FL_ARIDC) != 0;
     const double ek = g[GB_EKS * gs], invk = g[GB_INVKS * gs];
     const double l_prev = hasL ? a.glo_lake_stor[i] : 0., l_max = hasL ? g[GB_L_MAX * gs] : 0., l_pet = hasL ? g[GB_L_PET * gs] : 0.;
     const double l_gwr = hasL ? g[GB_L_GWR * gs] : 0., l_prec = hasL ? g[GB_L_PREC * gs] : 0.;
@@ -2024,12 +2021,12 @@ double route_global_bodies(const WgkParams &p, const int r, const int m, const s
     const double a_area = hasA ? a.area[r] : 0., a_contf = hasA ? a.contfreq[r] : 0., a_gw = hasA ? a.gw[i] : 0.;
     double gwr_glolak = 0., gwr_res = 0., gwr_glowet = 0.;
     if (flags & FL_LAKE) {  // :2677-2720
-        const double prev = l_prev;
+        const double prev = BATCH ? l_prev : a.glo_lake_stor[i];
         remainingUseGloLake = (flags & FL_RES) ? 0.5 * remainingUse : remainingUse;  // :2681-2686 (0 without water use)
         const double remainingUseGloLakeStart = remainingUseGloLake;
-        const double maxStorage = l_max, PET = l_pet + remainingUseGloLake;
-        gwr_glolak = l_gwr;
-        const double totalInflow = inflow + l_prec;
+        const double maxStorage = BATCH ? l_max : g[GB_L_MAX * gs], PET = (BATCH ? l_pet : g[GB_L_PET * gs]) + remainingUseGloLake;
+        gwr_glolak = BATCH ? l_gwr : g[GB_L_GWR * gs];
+        const double totalInflow = inflow + (BATCH ? l_prec : g[GB_L_PREC * gs]);
         const double PETmax = totalInflow + maxStorage + prev;
         double S, outflow;
         if (PET > PETmax) {
@@ -2057,12 +2054,12 @@ double route_global_bodies(const WgkParams &p, const int r, const int m, const s
         a.glo_lake_stor[i] = S;
     }
     if (flags & FL_RES) {  // :2871-3040
-        const double stor_cap = r_cap;
+        const double stor_cap = BATCH ? r_cap : g[GB_R_CAP * gs];
         const double maxStorage = stor_cap;
-        const double prev = r_prev;
-        const double PET = r_pet;
-        gwr_res = r_gwr;
-        const double totalInflow = inflow + r_prec;
+        const double prev = BATCH ? r_prev : a.res_stor[i];
+        const double PET = BATCH ? r_pet : g[GB_R_PET * gs];
+        gwr_res = BATCH ? r_gwr : g[GB_R_GWR * gs];
+        const double totalInflow = inflow + (BATCH ? r_prec : g[GB_R_PREC * gs]);
         const double PETmax = prev + totalInflow;
         remainingUseRes = (flags & FL_LAKE) ? 0.5 * remainingUse + remainingUseGloLake : remainingUse;  // :2869-2875
         const double remainingUseResStart = remainingUseRes;
@@ -2088,14 +2085,14 @@ double route_global_bodies(const WgkParams &p, const int r, const int m, const s
             }
         }
         if (fabs(S) <= MIN_STOR_VOL) S = 0.;
-        double Krel = r_krel;
+        double Krel = BATCH ? r_krel : a.k_release[i];
         const int fdim[12] = {1, 32, 60, 91, 121, 152, 182, 213, 244, 274, 305, 335};
-        if (month == r_start_month - 1 && day == fdim[month]) {  // :2945-2956
+        if (month == (BATCH ? r_start_month : (int)a.start_month[r]) - 1 && day == fdim[month]) {  // :2945-2956
             if (S < (stor_cap * 0.1)) Krel = 0.1;
             else Krel = S / (maxStorage * 0.85);
             a.k_release[i] = Krel;
         }
-        const double c_ratio = r_c, prov_rel = r_prov;
+        const double c_ratio = BATCH ? r_c : g[GB_R_C * gs], prov_rel = BATCH ? r_prov : g[GB_R_PROV * gs];
         double release;
         if (c_ratio >= 0.5) release = Krel * prov_rel;
         else
@@ -2120,10 +2117,10 @@ double route_global_bodies(const WgkParams &p, const int r, const int m, const s
     }
     if (wu && (flags & (FL_LAKE | FL_RES))) remainingUse = (flags & FL_RES) ? remainingUseRes : remainingUseGloLake;  // :3166-3172
     if (flags & FL_GLOWET) {  // :3201-3260
-        const double prev = w_prev;
-        const double maxStorage = w_max, PET = w_pet;
-        gwr_glowet = w_gwr;
-        const double totalInflow = inflow + w_prec;
+        const double prev = BATCH ? w_prev : a.glo_wetl_stor[i];
+        const double maxStorage = BATCH ? w_max : g[GB_W_MAX * gs], PET = BATCH ? w_pet : g[GB_W_PET * gs];
+        gwr_glowet = BATCH ? w_gwr : g[GB_W_GWR * gs];
+        const double totalInflow = inflow + (BATCH ? w_prec : g[GB_W_PREC * gs]);
         const double PETmax = totalInflow + prev;
         double S, outflow;
         if (PET > PETmax) {
@@ -2143,13 +2140,13 @@ double route_global_bodies(const WgkParams &p, const int r, const int m, const s
         a.glo_wetl_stor[i] = S;
     }
     if (flags & FL_ARIDC) {  // :3305-3386
-        const double gwr_swb = a_gwr_lak + gwr_glolak + a_gwr_wet + gwr_glowet + gwr_res;
+        const double gwr_swb = (BATCH ? a_gwr_lak : g[GB_LOC_GWR_LAK * gs]) + gwr_glolak + (BATCH ? a_gwr_wet : g[GB_LOC_GWR_WET * gs]) + gwr_glowet + gwr_res;
         a.gwr_swb[i] = gwr_swb;
-        double netGWin = gwr_swb * a_area * (a_contf / C100) / C1E6 + a_gwrech;
+        double netGWin = gwr_swb * (BATCH ? a_area : a.area[r]) * ((BATCH ? a_contf : a.contfreq[r]) / C100) / C1E6 + (BATCH ? a_gwrech : g[GB_GWRECH * gs]);
         if (wu) netGWin -= wu_net_gw_use(p, r, i, qi(p, m, r));  // :3325-3330
-        const double prev = a_gw;
-        const double ekg = a_ekg;
-        double Sg = prev * ekg + a_invkg * netGWin * (1. - ekg);
+        const double prev = BATCH ? a_gw : a.gw[i];
+        const double ekg = BATCH ? a_ekg : g[GB_EKG * gs];
+        double Sg = prev * ekg + (BATCH ? a_invkg : g[GB_INVKG * gs]) * netGWin * (1. - ekg);
         if (fabs(Sg) <= MIN_STOR_VOL) Sg = 0.;
         double qq = prev - Sg + netGWin;
         if (qq <= 0.) {
@@ -2164,8 +2161,16 @@ double route_global_bodies(const WgkParams &p, const int r, const int m, const s
     return inflow;
 }
 
+// out-of-line form for the throughput kernels (one copy of the code, small register footprint at the call site)
+__device__ __noinline__ double route_global_bodies(const WgkParams &p, const int r, const int m, const size_t i,
+                                                   double inflow, const int flags, const int day, const int month,
+                                                   double &gwToRiver WGK_WU_PARAMS) {
+    return route_global_bodies_impl<false>(p, r, m, i, inflow, flags, day, month, gwToRiver WGK_WU_ARGS);
+}
+
 // river reach of one cell (routing.cpp:3388-3545), given the inflow-independent context and
 // the sum of upstream discharges; writes discharge / storage and returns nothing
+template <bool BATCH = false>
 __device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx &c, const int r, const int m, const size_t i,
                                             const size_t q, const double inflowUpstream, const int day, const int month,
                                             double *__restrict__ qday, double *qout = nullptr, double *red_loc_lake_out = nullptr) {
@@ -2178,7 +2183,8 @@ __device__ __forceinline__ double route_river(const WgkParams &p, const RiverCtx
     double remainingUse = 0., dailyActualUse = 0.;
     if (wu && (c.flags & FL_TBC1)) remainingUse = a.wu_nus_month[q];
     if (c.flags & (FL_LAKE | FL_RES | FL_GLOWET))
-        inflow = route_global_bodies(p, r, m, i, inflow, c.flags, day, month, gwToRiver WGK_WU_ARGS);
+        inflow = BATCH ? route_global_bodies_impl<true>(p, r, m, i, inflow, c.flags, day, month, gwToRiver WGK_WU_ARGS)
+                       : route_global_bodies(p, r, m, i, inflow, c.flags, day, month, gwToRiver WGK_WU_ARGS);
     double riverInflow = inflow;
     if (c.flags & FL_LDD_OUT) {
         riverInflow += c.runoff_to_river;
@@ -2385,8 +2391,8 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
     }
     if ((flags & FL_ACTIVE) && (flags & (FL_LAKE | FL_RES | FL_GLOWET))) {
         // evaporation reduction factors of the global water bodies (:2790-2802, 3068-3078, 3287-3296): the six inputs in one round
-        // of loads, then the three pow() back to back for every lane (an absent body gets harmless arguments and no store) - in
-        // a warp that holds lakes, reservoirs and wetlands their chains overlap instead of following each other branch by branch
+        // of loads; in a warp that holds lakes, reservoirs and wetlands the three pow() are evaluated back to back for every lane
+        // (an absent body gets harmless arguments and no store), so that their chains overlap instead of following each other
         const double *g = p.gbody + gb(p, m, p.gidx[r], GB_N);  // (no __restrict__: written earlier by the same thread in k_days_persistent)
         const size_t gs = gbody_stride(p);
         const double xexp = (in.evaredex * 3.32193);
@@ -2394,12 +2400,26 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
         const double maxL = hasL ? g[GB_L_MAX * gs] : 1., storL = hasL ? a.glo_lake_stor[i] : 0.;
         const double maxR = hasR ? g[GB_R_CAP * gs] : 1., storR = hasR ? a.res_stor[i] : 0.;
         const double maxW = hasW ? g[GB_W_MAX * gs] : 1., storW = hasW ? a.glo_wetl_stor[i] : 0.;
-        const double powL = wg_pow(fabs(storL - maxL) / (2. * maxL), xexp);
-        const double powR = wg_pow(fabs(storR - maxR) / maxR, 2.81383);
-        const double powW = wg_pow(fabs(storW - maxW) / maxW, xexp);
-        if (hasL) a.red_glo_lake[i] = clamp01(1. - powL);
-        if (hasR) a.red_res[i] = clamp01(1. - powR);
-        if (hasW) red_glo_wetl = clamp01(1. - powW);
+        // how many kinds of water body the lanes of this warp hold: with one kind a plain branch (no wasted pow - a member-minor
+        // warp is 32 members of ONE cell), with several all three back to back
+#ifdef __CUDA_ARCH__
+        const unsigned am = __activemask();
+        const int kinds = (__ballot_sync(am, hasL) != 0) + (__ballot_sync(am, hasR) != 0) + (__ballot_sync(am, hasW) != 0);
+#else
+        const int kinds = 1;
+#endif
+        if (kinds > 1) {
+            const double powL = wg_pow(fabs(storL - maxL) / (2. * maxL), xexp);
+            const double powR = wg_pow(fabs(storR - maxR) / maxR, 2.81383);
+            const double powW = wg_pow(fabs(storW - maxW) / maxW, xexp);
+            if (hasL) a.red_glo_lake[i] = clamp01(1. - powL);
+            if (hasR) a.red_res[i] = clamp01(1. - powR);
+            if (hasW) red_glo_wetl = clamp01(1. - powW);
+        } else {
+            if (hasL) a.red_glo_lake[i] = clamp01(1. - wg_pow(fabs(storL - maxL) / (2. * maxL), xexp));
+            if (hasR) a.red_res[i] = clamp01(1. - wg_pow(fabs(storR - maxR) / maxR, 2.81383));
+            if (hasW) red_glo_wetl = clamp01(1. - wg_pow(fabs(storW - maxW) / maxW, xexp));
+        }
     }
     const double loc_lake = in.loc_lake, loc_wetland = in.loc_wetland;
     double fLocLake = ((loc_lake > 0.) && (red_loc_lake > 0.)) ? (red_loc_lake * loc_lake / C100) : 0.;
@@ -2805,8 +2825,8 @@ __global__ void __launch_bounds__(VBLOCK, WGK_LEVEL_MINB_EFF) k_level_day(const 
         for (int k = 0; k < 8; k++)
             if (up[k] >= 0) inflow_up += qday[mi(p, m, up[k])];
         for (int k = c.up0 + 8; k < c.up1; k++) inflow_up += qday[mi(p, m, p.up_idx[k])];  // (never on a D8 network)
-        Sr = route_river(p, c, r, m, i, q, inflow_up, p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday, nullptr,
-                         WU ? &red_ll : nullptr);
+        Sr = route_river<true>(p, c, r, m, i, q, inflow_up, p.cal_days[4 * dayofs], p.cal_days[4 * dayofs + 1], qday, nullptr,
+                               WU ? &red_ll : nullptr);
         if (WU) in.red_loc_lake = red_ll;
     }
     route_post_compute(p, r, m, in, Sr);
