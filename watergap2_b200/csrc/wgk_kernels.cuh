@@ -2402,7 +2402,7 @@ __device__ __forceinline__ void route_post_compute(const WgkParams &p, const int
         const double maxW = hasW ? g[GB_W_MAX * gs] : 1., storW = hasW ? a.glo_wetl_stor[i] : 0.;
         // how many kinds of water body the lanes of this warp hold: with one kind a plain branch (no wasted pow - a member-minor
         // warp is 32 members of ONE cell), with several all three back to back
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(WGK_NO_POW3)
         const unsigned am = __activemask();
         const int kinds = (__ballot_sync(am, hasL) != 0) + (__ballot_sync(am, hasR) != 0) + (__ballot_sync(am, hasW) != 0);
 #else
