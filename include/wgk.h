@@ -86,11 +86,13 @@ int wgk_set_stream(wgk_ctx *ctx, void *cuda_stream);
 /* rout_order[n]: 1-based routing rank of cell n (G_ROUT_ORDER.UNF4, rout_prepare.cpp:834-886);
  * downstream_cell[n]: 1-based number of the cell n drains to, 0 = none (G_OUTFLC.UNF4). */
 int wgk_set_topology(wgk_ctx *ctx, const int32_t *rout_order, const int32_t *downstream_cell);
-/* Optional, BEFORE wgk_set_topology: a small class key per cell (e.g. bit 0 local lake, bit 1 local wetland,
- * bit 2 global lake/reservoir/wetland, bit 3 arid).  Inside one dependency level the device order is free
- * (the upstream sums keep the reference's order through the CSR), so cells of equal class are stored next
- * to each other and the warps of the cell-parallel kernels skip the water-body code they do not need.
- * Results do not depend on it.  NULL resets to plain routing order. */
+/* Optional, BEFORE wgk_set_topology: a small class key per cell: bit 0 local lake, bit 1 local wetland,
+ * bit 2 global lake/reservoir/wetland, bit 3 arid (bits 4-7: free for the caller, a secondary key).  Inside one
+ * dependency level the device order is free (the upstream sums keep the reference's order through the CSR), so
+ * cells of equal class are stored next to each other and the warps of the cell-parallel kernels skip the
+ * water-body code they do not need; the classes with the longest code path (bit 2, then bits 0 / 1) come first
+ * inside a level, so that the slowest warps of a kernel start first.  Results do not depend on it.  NULL resets
+ * to plain routing order. */
 int wgk_set_cell_classes(wgk_ctx *ctx, const uint8_t *cell_class);
 int wgk_num_levels(const wgk_ctx *ctx);
 /* level[n] (0-based dependency level of cell n) for ncell cells; for tests and basin sharding */
@@ -118,8 +120,9 @@ int64_t wgk_cell_stride(const wgk_ctx *ctx);
 int64_t wgk_member_stride(const wgk_ctx *ctx);
 int wgk_layout(const wgk_ctx *ctx);
 /* schedule of a multi-day call chosen by wgk_create (bit flags): 1 = whole-grid kernels day after day (many members), else
- * the (day, level) wavefront graph; 2 = the wavefront's wide levels run as one task per (day, level) (vertical part and river
- * part in one kernel, programmatic edge from the upstream level), else as two; 4 = cell-owner kernel (opt-in). */
+ * the (day, level) wavefront graph; 2 = the wavefront's levels run as ONE task per (day, level) (vertical part and river part in
+ * one kernel, programmatic edge from the upstream level; the default below 800 000 cell-members), else as two kernels per wide
+ * level and one persistent CTA per narrow level; 4 = cell-owner kernel (opt-in). */
 int wgk_schedule(const wgk_ctx *ctx);
 /* rank_of_cell[n] = position of reference cell n in the device (routing) order */
 int wgk_get_device_order(const wgk_ctx *ctx, int32_t *rank_of_cell);

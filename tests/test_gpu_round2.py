@@ -458,9 +458,10 @@ def test_water_use_one_step_parity_59_days(golden, oracle_lib):
 
 
 def test_fused_level_tasks_are_bit_identical(world3000, monkeypatch):
-    """opt-in task forms of the wavefront graph (WGK_LEVEL_TASKS): vertical + river part of a wide level in one kernel with a
-    programmatic edge from the upstream level ("fused", k_level_day with griddepcontrol.wait), or for the headwater level only
-    ("fused0"), against the default two-kernel tasks: 45 days in one call, every state / flux field, the snow bands and the
+    """task forms of the wavefront graph (WGK_LEVEL_TASKS): vertical + river part of a level in one kernel with a programmatic edge
+    from the upstream level ("fused", k_level_day with griddepcontrol.wait - the default of small problems - with every level a
+    fused task or with the narrow levels as tail chunks), with a full edge ("fusedfull"), or for the headwater level only
+    ("fused0"), against the two-kernel tasks ("split"): 45 days in one call, every state / flux field, the snow bands and the
     station record the same bits"""
     from oracle import synth_world as sw, wg_init
     import watergap2_b200 as wg
@@ -494,3 +495,18 @@ def test_fused_level_tasks_are_bit_identical(world3000, monkeypatch):
         for k in names:
             assert np.array_equal(st[k], out[0][0][k]), k
         assert np.array_equal(rec, out[0][1])
+
+
+@pytest.mark.gpu
+def test_default_task_form_follows_problem_size(monkeypatch):
+    """wgk_create picks the fused (day, level) tasks for latency-bound problems (cell-minor layout, below 800 000 cell-members)
+    and the two-kernel tasks beyond, and says so in wgk_schedule (bit 2); water use keeps the two-kernel tasks"""
+    import watergap2_b200 as wg
+    for k in ("WGK_LEVEL_TASKS", "WGK_DAY_SCHEDULE", "WGK_LAYOUT"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("WGK_VERTICAL_FORM", "cells")
+    for ncell, nmember, use, fused in ((67420, 1, 0, True), (67420, 8, 0, True), (67420, 16, 0, False), (900000, 1, 0, False), (67420, 1, 2, False)):
+        m = wg.Model(ncell, nmember=nmember, subtract_use=use)
+        assert (m.schedule & 1) == 0, (ncell, nmember)
+        assert ((m.schedule & 2) != 0) == fused, (ncell, nmember, use, m.schedule)
+        m.close()
