@@ -307,7 +307,7 @@ def run_headline(args, D, w, ini, forcing):
             cls[k][1] = n
     wavefront = cls["other"][1] == 0
     lv = np.bincount(m.levels(), minlength=m.nlevels)
-    form = os.environ.get("WGK_VERTICAL_FORM") or ("bands" if ncell * args.members < 32768 else "cells")
+    form = os.environ.get("WGK_VERTICAL_FORM") or "cells"
     fused = wavefront and bool(m.schedule & 2)  # one task per (day, level): k_level_day = vertical + local routing + river + post
     vname = {"cells": "k_cells_pre_tpc", "bands": "k_cells_pre<VCfg<5,4,1>>", "bands2": "k_cells_pre<VCfg<2,5,0>>"}[form] if wavefront else \
             {"cells": "k_vertical_tpc", "bands": "k_vertical<VCfg<5,4,1>>", "bands2": "k_vertical<VCfg<2,5,0>>"}[form]

@@ -653,18 +653,15 @@ int wgk_create(wgk_ctx **out, int device, int ncell, int nmember, int npset, con
     if ((c->opt.restart != 0 && c->opt.restart != 1) || (c->opt.use_graph != 0 && c->opt.use_graph != 1) || c->opt.tail_threshold < 0)
         return fail(c, WGK_ERR_ARG, "wgk_options: restart %d / use_graph %d must be 0 or 1, tail_threshold %d >= 0", c->opt.restart,
                     c->opt.use_graph, c->opt.tail_threshold);
-    {   // Form of the vertical kernel.  Small problems cannot fill the GPU with one thread per cell: the
-        // cell-day -> cell-day latency chain bounds the run and the band-parallel forms shorten it (5 threads
-        // per cell while far from full, 2 threads per cell while all tiles still fit the SMs at once);
-        // beyond that the thread-per-cell form, which keeps every lane busy in the scalar parts of the step.
+    {   // Form of the vertical kernel.  The band-parallel tile forms (5 or 2 threads per cell in the band loop) were the default
+        // of small problems in round 1, when the thread-per-cell kernels ran as two-kernel tasks; against the fused (day, level)
+        // task of round 2 they lose at every size (one member, ms per simulated year, tile form / thread per cell in fused
+        // tasks: 3 000 cells 14.1 / 10.4, 10 000 16.4 / 10.9, 20 000 16.7 / 11.1, 30 000 18.5 / 11.9, 67 420 28.8 / 16.9),
+        // so the thread-per-cell form is the default everywhere and the tile forms stay selectable (and tested).
         const char *e = getenv("WGK_VERTICAL_FORM");  // "cells" | "bands" | "bands2" (tests exercise all)
-        const long long work = (long long)nmember * ncell;
         if (e && !strcmp(e, "bands")) c->form = 1;
         else if (e && !strcmp(e, "bands2")) c->form = 2;
-        else if (e && !strcmp(e, "cells")) c->form = 0;
-        else c->form = work < 32768 ? 1 : 0;  // measured crossover on B200 at about 30 000 cell-members (20 000: 16.4 vs 17.1 ms per
-                                              // year, 30 000: 17.9 vs 18.0, 40 000: 19.6 vs 18.7)
-                                              // (the 2-threads-per-cell form never beat both others)
+        else c->form = 0;
     }
     {   // Schedule of a multi-day call.  Few members: the (day, level) wavefront, which hides the level-to-level
         // latency chain of a day behind the following days.  Many members: every kernel fills the GPU on its own, and
