@@ -71,3 +71,21 @@ def test_header_is_plain_c(tmp_path):
     src = tmp_path / "t.c"
     src.write_text('#include "wgk.h"\nint main(void) { return wgk_field_id("snow") == 12345; }\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
+
+
+def test_cell_class_key_with_coldness_bins():
+    """the sort key of Model.set_topology(cell_class=...): low 4 bits = water-body class, high 4 bits = the opt-in coldness bin
+    (coldest first) from the 0.5 degree row and the mean elevation; off by default"""
+    import numpy as np
+    import watergap2_b200 as wg
+    f = {"loc_lake": np.array([0., 1., 0., 0.]), "loc_wetland": np.array([0., 2., 0., 0.]), "lake_area": np.array([0., 0., 3., 0.]),
+         "reservoir_area": np.zeros(4), "glo_wetland": np.zeros(4), "arid": np.array([0, 0, 0, 1]),
+         "row": np.array([20, 100, 180, 340], np.int16), "elevation": np.array([[4000] + [0] * 100, [100] + [0] * 100, [0] * 101, [10] * 101], np.int16)}
+    assert wg.cell_classes(f, cold_bins=0).tolist() == [0, 3, 4, 8]
+    k = wg.cell_classes(f, cold_bins=16)
+    assert (k & 15).tolist() == [0, 3, 4, 8]
+    lat = 90.25 - 0.5 * f["row"].astype(float)
+    t = 27.0 - 0.55 * np.abs(lat) - 0.0045 * f["elevation"][:, 0]
+    assert (k >> 4).tolist() == np.clip(np.floor((t + 30.0) / 60.0 * 16), 0, 15).astype(int).tolist()
+    assert (k >> 4)[0] < (k >> 4)[2]  # the high mountain cell near the pole sorts before the tropical lowland cell
+    assert wg.coldness_bin(np.array([180]), np.array([0]), 4).tolist() == [3]
