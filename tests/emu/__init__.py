@@ -38,7 +38,7 @@ class Emu:
         dn = np.ascontiguousarray(downstream, np.int32)
         self.e = L.emu_create(ncell, ro.ctypes.data, dn.ctypes.data)
         L.emu_set_form.argtypes = [vp, ci]
-        L.emu_set_form(self.e, {"bands": 0, "cells": 1, "bands2": 2}[form])
+        L.emu_set_form(self.e, {"bands": 0, "cells": 1, "bands2": 2, "fused": 3}[form])
 
     def set(self, name, arr, dtype):
         a = np.ascontiguousarray(np.asarray(arr).astype(dtype))

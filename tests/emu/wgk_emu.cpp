@@ -30,7 +30,8 @@ struct Emu {
     int32_t cal_days[8] = {0};
     int32_t cal[8] = {0};
     bool derived = false;
-    int form = 0;  // 0: band-parallel tiles (5 warps), 1: thread per cell, 2: band-parallel tiles (2 warps)
+    int form = 0;  // 0: band-parallel tiles (5 warps), 1: thread per cell, 2: band-parallel tiles (2 warps),
+                   // 3: the fused (day, level) task k_level_day (thread per cell; vertical + local routing + river + post)
 };
 
 template <class K, class... A> static void launch(K kern, dim3 grid, dim3 block, A... args) {
@@ -186,6 +187,14 @@ void emu_day(Emu *e, int day, int month, int dom, int slot, int tail_level0) {
             if (e->p.a.s_flags[r] & (wgk::FL_LAKE | wgk::FL_RES | wgk::FL_GLOWET)) e->gidx[r] = n++;
         e->gbody.assign((size_t)std::max(1, n) * wgk::GB_N, 0.0);
         e->p.gidx = e->gidx.data(); e->p.gbody = e->gbody.data(); e->p.ngbody = n;
+    }
+    if (e->form == 3) {  // one fused task per level, in level order (what the wavefront graph runs for small problems)
+        for (int l = 0; l < e->nlevels; l++) {
+            const int n = e->level_off[l + 1] - e->level_off[l];
+            launch(wgk::k_level_day, dim3((n + wgk::VBLOCK - 1) / wgk::VBLOCK, 1), dim3(wgk::VBLOCK), p, 0, l);
+        }
+        memcpy(p.a.discharge, wgk::qbuf_of_day(p, 0), sizeof(double) * e->stride);
+        return;
     }
     int t0 = tail_level0 < 0 ? e->nlevels : tail_level0;
     for (int l = 0; l < t0; l++) {

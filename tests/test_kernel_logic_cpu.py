@@ -18,7 +18,7 @@ import pytest
 from tests.util import ParityReport, rel_err
 
 
-@pytest.mark.parametrize("tail_level0,form", [(-1, "bands"), (3, "bands"), (3, "cells"), (-1, "bands2")])
+@pytest.mark.parametrize("tail_level0,form", [(-1, "bands"), (3, "bands"), (3, "cells"), (-1, "bands2"), (-1, "fused")])
 def test_kernel_source_on_host_matches_oracle(world3000, oracle_lib, tail_level0, form):
     from oracle import synth_world as sw, wg_init
     from tests.emu import Emu
@@ -52,7 +52,7 @@ def test_kernel_source_on_host_matches_oracle(world3000, oracle_lib, tail_level0
     assert worst > 0  # the four substitutions are really in effect
 
 
-@pytest.mark.parametrize("form", ["bands", "cells", "bands2"])
+@pytest.mark.parametrize("form", ["bands", "cells", "bands2", "fused"])
 def test_kernel_source_deep_snow_vs_reference_golden(golden_deep, oracle_lib, form):
     """band-parallel snow kernel on packs of up to 1400 mm per band (1000 mm cap, daily.cpp:958-976)
     against what the compiled reference held in memory; the snow bands themselves must be within
@@ -102,3 +102,27 @@ def test_const_division_is_exact():
     L.emu_test_constdiv.restype = ctypes.c_long
     L.emu_test_constdiv.argtypes = [ctypes.c_long, ctypes.c_ulonglong]
     assert L.emu_test_constdiv(5_000_000, 20240607) == 0
+
+
+def test_fused_task_equals_split_tasks_on_host(world3000, oracle_lib):
+    """the fused (day, level) task k_level_day (inputs of the global-water-body blocks in one round of loads, routine inlined) and
+    the split tasks (k_cells_pre_tpc, out-of-line routine with the loads inside the blocks) are the same arithmetic: executed on
+    the host, 10 days from the cold start, every state / flux field bit for bit"""
+    from oracle import synth_world as sw, wg_init
+    from tests.emu import Emu
+    w = world3000
+    ini = wg_init.derive(w)
+    topo = ini["_topology"]
+    o = oracle_lib.Oracle(w.ng)
+    f = sw.forcing_month(w, 1901, 1)
+    names = wg_init.STATE_FIELDS + wg_init.FLUX_FIELDS
+    out = []
+    for form in ("cells", "fused"):
+        e = Emu(w.ng, topo["rout_order"], topo["outflow_cell"], form)
+        e.load(ini, o)
+        e.set_forcing(f)
+        for sd in range(1, 11):
+            e.day(sd, 0, sd, sd - 1, -1)
+        out.append({nm: e.get(nm, o.field(nm)) for nm in names})
+    for nm in names:
+        assert np.array_equal(out[0][nm], out[1][nm]), nm
